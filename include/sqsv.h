@@ -1,0 +1,158 @@
+/*
+ * sqsv.h — C ABI of the B200-native state-vector engine (libsqsv.so).
+ *
+ * This is the drop-in boundary for the state-vector hot path of SlowQuant
+ * (reference: slowquant/unitary_coupled_cluster/{ci_spaces,operator_state_algebra,
+ * density_matrix}.py and the rdm/energy/gradient methods of ups_wavefunction.py).
+ * The reference has no FFI layer; its boundary is the Python function surface.
+ * Every entry point below names the reference function it replaces (file:line,
+ * relative to the reference root); the Python shim in slowquant_b200/ binds these
+ * with ctypes and keeps the reference's call signatures.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary;
+ *   - pointers named *_dev are CUDA device pointers on the space's device,
+ *     pointers named *_host are host pointers; the caller owns all of them;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns an int status (SQ_OK == 0); nothing throws;
+ *     sq_last_error() returns a thread-local message for the last failure;
+ *   - the CI vector is the row-major matrix C[Ia][Ib] of fp64 amplitudes,
+ *     Ia = alpha-string index, Ib = beta-string index, idx = Ia*Nb + Ib, which is
+ *     exactly the determinant ordering of get_indexing (ci_spaces.py:76-116);
+ *   - spin-orbital index = 2*spatial + (0 alpha | 1 beta), as in the reference.
+ */
+#ifndef SQSV_H
+#define SQSV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQ_OK 0
+#define SQ_ERR_INVALID 1     /* bad argument                                  -> ValueError */
+#define SQ_ERR_CUDA 2        /* CUDA runtime failure                          -> RuntimeError */
+#define SQ_ERR_OUTSIDE 3     /* operator string leaves the CI space           -> KeyError
+                                (operator_state_algebra.py:131-135, do_unsafe=False) */
+#define SQ_ERR_UNSUPPORTED 4 /* feature not available in this build           -> NotImplementedError */
+#define SQ_ERR_NOMEM 5
+
+/* excitation-operator type codes; mirror UpsStructure.excitation_operator_type
+ * (util.py:642-1073) */
+#define SQ_EXC_SA_SINGLE 0
+#define SQ_EXC_SINGLE 1
+#define SQ_EXC_DOUBLE 2
+#define SQ_EXC_TRIPLE 3
+#define SQ_EXC_QUADRUPLE 4
+#define SQ_EXC_QUINTUPLE 5
+#define SQ_EXC_SEXTUPLE 6
+#define SQ_EXC_SA_DOUBLE_1 7
+#define SQ_EXC_SA_DOUBLE_2 8
+#define SQ_EXC_SA_DOUBLE_3 9
+#define SQ_EXC_SA_DOUBLE_4 10
+#define SQ_EXC_SA_DOUBLE_5 11
+
+typedef struct sq_space sq_space;   /* CI space: string lists + device tables (CI_Info, ci_spaces.py:9-53) */
+typedef struct sq_layout sq_layout; /* compiled ansatz layout (UpsStructure, util.py:642)                 */
+
+const char* sq_last_error(void);
+int sq_version(void);
+
+/* ---- CI space (replaces get_indexing, ci_spaces.py:76-116) ------------------------------------ */
+
+/* Build alpha/beta string lists in itertools.combinations order, rank tables and device copies.
+ * [row_begin,row_end) is the range of alpha strings (rows of C) resident on this device; pass
+ * 0,-1 for the whole vector.  device = CUDA ordinal; device = -1 builds a host-only space (integer
+ * tables, export/rank functions; no kernels). */
+int sq_space_create(int n_orb, int n_alpha, int n_beta, int device, int64_t row_begin,
+                    int64_t row_end, sq_space** out);
+int sq_space_destroy(sq_space* sp);
+int64_t sq_space_num_det(const sq_space* sp);
+int64_t sq_space_num_strings(const sq_space* sp, int spin /*0 alpha, 1 beta*/);
+int64_t sq_space_local_rows(const sq_space* sp);
+/* host copy of the occupation bitmask of every string (bit o = spatial orbital o) */
+int sq_space_export_strings(const sq_space* sp, int spin, uint32_t* out_host);
+/* idx2det[first .. first+count) as the reference's determinant integers
+ * (interleaved a0 b0 a1 b1 ..., orbital 0 most significant; ci_spaces.py:99-107) */
+int sq_space_export_idx2det(const sq_space* sp, int64_t first, int64_t count, int64_t* out_host);
+/* det2idx for n determinants; -1 where the determinant is not in the space (ci_spaces.py:106) */
+int sq_space_det2idx(const sq_space* sp, int64_t n, const int64_t* dets_host, int64_t* idx_host);
+
+/* ---- ansatz layout (mirrors UpsStructure lists, util.py:645-651) ---------------------------- */
+
+/* exc_type[k] is an SQ_EXC_* code; the indices of operator k are
+ * idx_flat[idx_offsets[k] .. idx_offsets[k+1]) exactly as stored in
+ * UpsStructure.excitation_indices (spatial (i,a)/(i,j,a,b) for sa_*, spin-orbital tuples otherwise). */
+int sq_layout_create(sq_space* sp, int n_ops, const int32_t* exc_type, const int32_t* idx_offsets,
+                     const int32_t* idx_flat, sq_layout** out);
+/* sa_double_1..5 generators are sums of products of E_pq; the symbolic normal ordering stays on the
+ * host (fermionic_operator.py), which attaches the normal-ordered strings of T_k = G - G^dagger here.
+ * String s consists of ops_flat[op_offsets[s] .. op_offsets[s+1]), each entry = 2*spin_orbital + dagger,
+ * in label order (creators first; fermionic_operator.py:27-104). */
+int sq_layout_attach_generator(sq_layout* lay, int k, int n_strings, const int32_t* ops_flat,
+                               const int32_t* op_offsets, const double* coeffs);
+int sq_layout_destroy(sq_layout* lay);
+int sq_layout_num_ops(const sq_layout* lay);
+/* number of kernel launches sq_ups_apply would issue for ops [first,last) (all |theta| > 1e-28) */
+int sq_layout_num_launches(const sq_layout* lay, int first, int last);
+
+/* ---- unitary product state (construct_ups_state, operator_state_algebra.py:963-1412;
+ *      propagate_unitary, :1867-2309) ---------------------------------------------------------- */
+
+/* In place: state <- U_{last-1} ... U_{first} state  (dagger=0), or the adjoint product
+ * (reversed order, theta -> -theta; :990-1001) when dagger=1.  thetas_host has one entry per layout
+ * operator; operators with |theta| < 1e-28 are skipped (:998). */
+int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                 int dagger, double* state_dev, void* stream);
+/* out <- T_k in   (get_grad_action, :2757-2865; sa_single uses Ta + Tb) */
+int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, double* out_dev,
+                   void* stream);
+/* Fused reverse sweep of ups_wavefunction.py:1114-1138 for operators [first,last):
+ *   grad_host[k] = 2 <bra| T_k |ket>;  bra <- U_k bra;  ket <- U_k ket   (k ascending). */
+int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                      double* bra_dev, double* ket_dev, double* grad_host, void* stream);
+
+/* ---- generic operator application (apply_operator_serial/threaded, :53-219; propagate_state
+ *      inner loop, :596-628) -------------------------------------------------------------------- */
+
+/* out (+)= sum_s coeffs[s] * string_s |in>.  Strings as in sq_layout_attach_generator.  in_dev and
+ * out_dev must not alias.  skip_outside != 0 reproduces do_unsafe=True (strings that leave the space
+ * are skipped); otherwise such a string returns SQ_ERR_OUTSIDE. */
+int sq_apply_strings(sq_space* sp, int n_strings, const int32_t* ops_flat, const int32_t* op_offsets,
+                     const double* coeffs, const double* in_dev, double* out_dev, int accumulate,
+                     int skip_outside, void* stream);
+
+/* ---- BLAS-1 on CI vectors -------------------------------------------------------------------- */
+int sq_dot(sq_space* sp, const double* a_dev, const double* b_dev, double* out_host, void* stream);
+int sq_axpy(sq_space* sp, double alpha, const double* x_dev, double* y_dev, void* stream);
+int sq_scale_copy(sq_space* sp, double alpha, const double* x_dev, double* y_dev, void* stream);
+
+/* ---- Hamiltonian and reduced density matrices ------------------------------------------------ */
+
+/* sigma <- H|in> with the folded active-space Hamiltonian
+ *   H = e_core + sum_pq h_act[p][q] E_pq + 1/2 sum_pqrs g_act[p][q][r][s] e_pqrs
+ * (hamiltonian_0i_0a folded, operators.py:476-529 + fermionic_operator.py:379-471);
+ * h_act_host [n][n], g_act_host [n][n][n][n] in chemists' notation. */
+int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, const double* g_act_host,
+             const double* in_dev, double* out_dev, void* stream);
+/* rdm1[p][q] = <bra|E_pq|ket>, rdm2[p][q][r][s] = <bra|E_pq E_rs|ket> - delta_qr rdm1[p][s]
+ * (ups_wavefunction.py:409-476); rdm2_host may be NULL. */
+int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_dev, double* rdm1_host,
+             double* rdm2_host, void* stream);
+
+/* ---- introspection (host only; works on a space created with device = -1) -------------------- */
+/* closed-form action of one ladder string on the determinant with occupation masks (A,B):
+ * valid = passes the screens of operator_state_algebra.py:118-123, (tgtA,tgtB) = flipped masks,
+ * sign = phase of :127-134. */
+int sq_debug_string_action(const sq_space* sp, const int32_t* ops, int n_ops, uint32_t A, uint32_t B,
+                           int* valid, uint32_t* tgtA, uint32_t* tgtB, int* sign);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* number of kernels this library has launched since load (all spaces) */
+int64_t sq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQSV_H */

@@ -1,0 +1,699 @@
+// extern "C" entry points: ansatz layout compilation, unitary-product-state application, gradient
+// sweep, generic operator application.  See include/sqsv.h for the reference functions each replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sqsv_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// table construction
+// ---------------------------------------------------------------------------------------------
+static inline int neg_of(uint32_t m, uint32_t par) { return __builtin_popcount(m & par) & 1; }
+
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& v) {
+  *dptr = nullptr;
+  if (v.empty()) return SQ_OK;
+  SQ_CUDA(cudaMalloc(dptr, sizeof(T) * v.size()));
+  SQ_CUDA(cudaMemcpy(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return SQ_OK;
+}
+
+// Tables for the spatial orbital pair (i,a): generators
+//   Ta = a+_{a,alpha} a_{i,alpha} - h.c.   Tb = a+_{a,beta} a_{i,beta} - h.c.     (sa_single; osa.py:1006-1007)
+//   D  = a+_{a,alpha} a+_{a,beta} a_{i,beta} a_{i,alpha} - h.c.                   (pair double; util.py:705)
+static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
+  if (i < 0 || a < 0 || i >= sp->n_orb || a >= sp->n_orb || i == a) {
+    sq_set_error("orbital pair (%d,%d) outside the active space / degenerate", i, a);
+    return SQ_ERR_INVALID;
+  }
+  pt->i = i;
+  pt->a = a;
+  StringAction actA, actB, actD;
+  int32_t la[2] = {2 * (2 * a) + 1, 2 * (2 * i)};
+  int32_t lb[2] = {2 * (2 * a + 1) + 1, 2 * (2 * i + 1)};
+  // normal-ordered pair double: creators descending (2a+1, 2a), annihilators descending (2i+1, 2i), factor -1
+  int32_t ld[4] = {2 * (2 * a + 1) + 1, 2 * (2 * a) + 1, 2 * (2 * i + 1), 2 * (2 * i)};
+  SQ_CHECK(sq_make_string_action(sp, la, 2, &actA));
+  SQ_CHECK(sq_make_string_action(sp, lb, 2, &actB));
+  SQ_CHECK(sq_make_string_action(sp, ld, 4, &actD));
+  const uint32_t bi = 1u << i, ba = 1u << a;
+  std::vector<uint32_t> codeA(sp->NA), codeB(sp->NB);
+  std::vector<int32_t> rows;
+  int64_t nsrcA_local = 0, ninertA_local = 0;
+  for (int64_t I = 0; I < sp->NA; ++I) {
+    const uint32_t m = sp->strA[I];
+    uint32_t cls = SQ_CLS_INERT, partner = 0;
+    if ((m & bi) && !(m & ba)) {
+      cls = SQ_CLS_SRC;
+      partner = (uint32_t)sp->rankA[m ^ bi ^ ba];
+    } else if (!(m & bi) && (m & ba)) {
+      cls = SQ_CLS_TGT;
+    }
+    uint32_t code = cls;
+    if (cls == SQ_CLS_SRC) {
+      const int negS = ((actA.s0 < 0) ? 1 : 0) ^ neg_of(m, actA.parA);
+      code |= (uint32_t)negS << 2;
+      code |= (uint32_t)neg_of(m, actD.parA) << 4;
+      code |= partner << 5;
+    }
+    code |= (uint32_t)neg_of(m, actB.parA) << 3;   // factor an alpha string gives the beta single
+    codeA[I] = code;
+    if (I >= sp->row_begin && I < sp->row_end) {
+      if (cls == SQ_CLS_SRC) {
+        if ((int64_t)partner < sp->row_begin || (int64_t)partner >= sp->row_end) {
+          sq_set_error("orbital pair (%d,%d): partner alpha row %u of row %lld is on another device", i, a,
+                       partner, (long long)I);
+          return SQ_ERR_UNSUPPORTED;
+        }
+        rows.push_back((int32_t)I);
+        ++nsrcA_local;
+      } else if (cls == SQ_CLS_INERT) {
+        rows.push_back((int32_t)I);
+        ++ninertA_local;
+      } else {
+        // tgt rows ride with their (local) src row
+        const int64_t src = sp->rankA[m ^ bi ^ ba];
+        if (src < sp->row_begin || src >= sp->row_end) {
+          sq_set_error("orbital pair (%d,%d): source alpha row of row %lld is on another device", i, a, (long long)I);
+          return SQ_ERR_UNSUPPORTED;
+        }
+      }
+    }
+  }
+  int64_t nsrcB = 0;
+  for (int64_t I = 0; I < sp->NB; ++I) {
+    const uint32_t m = sp->strB[I];
+    uint32_t cls = SQ_CLS_INERT, partner = 0;
+    if ((m & bi) && !(m & ba)) {
+      cls = SQ_CLS_SRC;
+      partner = (uint32_t)sp->rankB[m ^ bi ^ ba];
+      ++nsrcB;
+    } else if (!(m & bi) && (m & ba)) {
+      cls = SQ_CLS_TGT;
+    }
+    uint32_t code = cls;
+    if (cls == SQ_CLS_SRC) {
+      const int negS = ((actB.s0 < 0) ? 1 : 0) ^ neg_of(m, actB.parB);
+      code |= (uint32_t)negS << 2;
+      // the pair-double constant sign (-1 from normal ordering times s0) is folded into the beta factor
+      const int negD = ((-actD.s0 < 0) ? 1 : 0) ^ neg_of(m, actD.parB);
+      code |= (uint32_t)negD << 4;
+      code |= partner << 5;
+    }
+    code |= (uint32_t)neg_of(m, actA.parB) << 3;   // factor a beta string gives the alpha single
+    codeB[I] = code;
+  }
+  pt->n_rows = (int64_t)rows.size();
+  pt->n_src_rows = nsrcA_local;
+  pt->n_src_cols = nsrcB;
+  // amplitudes touched by a block containing sa_single: everything except inert x inert
+  pt->touched = 2 * nsrcA_local * sp->NB + ninertA_local * 2 * nsrcB;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  SQ_CHECK(upload(&pt->d_codeA, codeA));
+  SQ_CHECK(upload(&pt->d_codeB, codeB));
+  SQ_CHECK(upload(&pt->d_rowsA, rows));
+  return SQ_OK;
+}
+
+// normal-order a product  a+_{c0} a+_{c1} ... a_{d0} a_{d1} ...  of distinct operators: creators sorted
+// descending, then annihilators sorted descending (fermionic_operator.py:27-104); returns the sign, or 0
+// when an index repeats inside a block (the product vanishes).
+static int normal_order_blocks(std::vector<int>& crea, std::vector<int>& anni) {
+  int sign = 1;
+  auto sort_desc = [&](std::vector<int>& v) -> bool {
+    for (size_t x = 0; x < v.size(); ++x)
+      for (size_t y = 0; y + 1 < v.size() - x; ++y) {
+        if (v[y] == v[y + 1]) return false;
+        if (v[y] < v[y + 1]) {
+          std::swap(v[y], v[y + 1]);
+          sign = -sign;
+        }
+      }
+    for (size_t y = 0; y + 1 < v.size(); ++y)
+      if (v[y] == v[y + 1]) return false;
+    return true;
+  };
+  if (!sort_desc(crea)) return 0;
+  if (!sort_desc(anni)) return 0;
+  return sign;
+}
+
+// Tables for G = a+_{a} a+_{b} ... a_{j} a_{i}  (operators.py:145-359) given the reference's index tuple
+// (i,j,..,a,b,..).
+static int build_gen_tables(sq_space* sp, const std::vector<int>& idx, GenTables* gt, bool* null_op) {
+  const int rank = (int)idx.size() / 2;
+  *null_op = false;
+  std::vector<int> crea(idx.begin() + rank, idx.end());            // a, b, c, ... in product order
+  std::vector<int> anni(idx.begin(), idx.begin() + rank);          // i, j, k, ...
+  std::reverse(anni.begin(), anni.end());                          // product order is ... a_k a_j a_i
+  for (int so : idx)
+    if (so < 0 || so >= 2 * sp->n_orb) {
+      sq_set_error("spin-orbital index %d outside the active space", so);
+      return SQ_ERR_INVALID;
+    }
+  const int sgnG = normal_order_blocks(crea, anni);
+  if (sgnG == 0) {
+    *null_op = true;
+    return SQ_OK;
+  }
+  for (int c : crea)
+    for (int d : anni)
+      if (c == d) {
+        sq_set_error("excitation generator with a shared creation/annihilation index %d is not a Givens rotation", c);
+        return SQ_ERR_UNSUPPORTED;
+      }
+  std::vector<int32_t> label;
+  for (int c : crea) label.push_back(2 * c + 1);
+  for (int d : anni) label.push_back(2 * d);
+  StringAction act;
+  SQ_CHECK(sq_make_string_action(sp, label.data(), (int)label.size(), &act));
+  gt->act = act;
+  if (!act.conserving) {
+    // spin-flipping generator leaves the (N_alpha, N_beta) sector: T|state> = 0 inside the space; the
+    // reference would raise KeyError.  Mirror that.
+    sq_set_error("excitation generator does not conserve N_alpha / N_beta");
+    return SQ_ERR_OUTSIDE;
+  }
+  std::vector<int32_t> srcRows, tgtRows, colCode(sp->NB, -1);
+  std::vector<int8_t> sgnRows;
+  for (int64_t I = sp->row_begin; I < sp->row_end; ++I) {
+    const uint32_t m = sp->strA[I];
+    if ((m & act.occA) != act.occA || (m & act.empA) != 0u) continue;
+    const int64_t t = sp->rankA[m ^ act.flipA];
+    if (t < sp->row_begin || t >= sp->row_end) {
+      sq_set_error("generator pairs alpha row %lld with row %lld on another device", (long long)I, (long long)t);
+      return SQ_ERR_UNSUPPORTED;
+    }
+    srcRows.push_back((int32_t)I);
+    tgtRows.push_back((int32_t)t);
+    const int neg = ((sgnG * act.s0 < 0) ? 1 : 0) ^ neg_of(m, act.parA);
+    sgnRows.push_back(neg ? -1 : 1);
+  }
+  int64_t nvalid = 0;
+  for (int64_t I = 0; I < sp->NB; ++I) {
+    const uint32_t m = sp->strB[I];
+    if ((m & act.occB) != act.occB || (m & act.empB) != 0u) continue;
+    const int32_t t = sp->rankB[m ^ act.flipB];
+    colCode[I] = (t << 1) | neg_of(m, act.parB);
+    ++nvalid;
+  }
+  gt->n_rows = (int64_t)srcRows.size();
+  gt->n_cols_valid = nvalid;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  SQ_CHECK(upload(&gt->d_srcRows, srcRows));
+  SQ_CHECK(upload(&gt->d_tgtRows, tgtRows));
+  SQ_CHECK(upload(&gt->d_sgnRows, sgnRows));
+  SQ_CHECK(upload(&gt->d_colCode, colCode));
+  return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------------------
+extern "C" int sq_layout_create(sq_space* sp, int n_ops, const int32_t* exc_type, const int32_t* idx_offsets,
+                                const int32_t* idx_flat, sq_layout** out) {
+  if (!sp || !out || n_ops < 0 || (n_ops > 0 && (!exc_type || !idx_offsets || !idx_flat))) return SQ_ERR_INVALID;
+  *out = nullptr;
+  if (sp->device < 0) {
+    sq_set_error("sq_layout_create: host-only space (device = -1) cannot run kernels");
+    return SQ_ERR_INVALID;
+  }
+  sq_layout* lay = new sq_layout();
+  lay->sp = sp;
+  lay->ops.resize(n_ops);
+  int status = SQ_OK;
+  for (int k = 0; k < n_ops && status == SQ_OK; ++k) {
+    LayoutOp& op = lay->ops[k];
+    op.type = exc_type[k];
+    op.idx.assign(idx_flat + idx_offsets[k], idx_flat + idx_offsets[k + 1]);
+    const int ni = (int)op.idx.size();
+    auto get_pair = [&](int i, int a) -> int {
+      auto key = std::make_pair(i, a);
+      auto it = lay->pair_index.find(key);
+      if (it != lay->pair_index.end()) return it->second;
+      PairTables pt;
+      status = build_pair_tables(sp, i, a, &pt);
+      if (status != SQ_OK) return -1;
+      lay->pairs.push_back(pt);
+      lay->pair_index[key] = (int)lay->pairs.size() - 1;
+      return (int)lay->pairs.size() - 1;
+    };
+    if (op.type == SQ_EXC_SA_SINGLE) {
+      if (ni != 2) { sq_set_error("sa_single needs 2 indices, got %d", ni); status = SQ_ERR_INVALID; break; }
+      op.pair = get_pair(op.idx[0], op.idx[1]);
+    } else if (op.type >= SQ_EXC_SINGLE && op.type <= SQ_EXC_SEXTUPLE) {
+      const int want = 2 * (op.type - SQ_EXC_SINGLE + 1);
+      if (ni != want) {
+        sq_set_error("excitation type %d needs %d indices, got %d", op.type, want, ni);
+        status = SQ_ERR_INVALID;
+        break;
+      }
+      if (op.type == SQ_EXC_DOUBLE && (op.idx[0] % 2 == 0) && op.idx[1] == op.idx[0] + 1 && (op.idx[2] % 2 == 0) &&
+          op.idx[3] == op.idx[2] + 1 && op.idx[0] != op.idx[2]) {
+        op.pair_double = true;
+        op.pair = get_pair(op.idx[0] / 2, op.idx[2] / 2);
+      } else {
+        auto it = lay->gen_index.find(op.idx);
+        if (it != lay->gen_index.end()) {
+          op.gen = it->second;
+          op.null_op = (op.gen < 0);
+        } else {
+          GenTables gt;
+          bool null_op = false;
+          status = build_gen_tables(sp, op.idx, &gt, &null_op);
+          if (status != SQ_OK) break;
+          if (null_op) {
+            op.null_op = true;
+            lay->gen_index[op.idx] = -1;
+          } else {
+            lay->gens.push_back(gt);
+            op.gen = (int)lay->gens.size() - 1;
+            lay->gen_index[op.idx] = op.gen;
+          }
+        }
+      }
+    } else if (op.type >= SQ_EXC_SA_DOUBLE_1 && op.type <= SQ_EXC_SA_DOUBLE_5) {
+      if (ni != 4) { sq_set_error("sa_double needs 4 indices, got %d", ni); status = SQ_ERR_INVALID; break; }
+      // generator strings are attached by the host (sq_layout_attach_generator)
+    } else {
+      sq_set_error("Got unknown excitation type code %d", op.type);
+      status = SQ_ERR_INVALID;
+    }
+  }
+  if (status != SQ_OK) {
+    sq_layout_destroy(lay);
+    return status;
+  }
+  *out = lay;
+  return SQ_OK;
+}
+
+static int parse_strings(sq_space* sp, int n_strings, const int32_t* ops_flat, const int32_t* op_offsets,
+                         const double* coeffs, int skip_outside, std::vector<StringAction>* acts,
+                         std::vector<double>* cf) {
+  acts->clear();
+  cf->clear();
+  for (int s = 0; s < n_strings; ++s) {
+    StringAction a;
+    SQ_CHECK(sq_make_string_action(sp, ops_flat + op_offsets[s], op_offsets[s + 1] - op_offsets[s], &a));
+    if (!a.conserving) {
+      if (skip_outside) continue;
+      sq_set_error("operator string %d takes determinants outside the CI space (N_alpha/N_beta not conserved)", s);
+      return SQ_ERR_OUTSIDE;
+    }
+    acts->push_back(a);
+    cf->push_back(coeffs[s]);
+  }
+  return SQ_OK;
+}
+
+extern "C" int sq_layout_attach_generator(sq_layout* lay, int k, int n_strings, const int32_t* ops_flat,
+                                          const int32_t* op_offsets, const double* coeffs) {
+  if (!lay || k < 0 || k >= (int)lay->ops.size() || n_strings < 0) return SQ_ERR_INVALID;
+  LayoutOp& op = lay->ops[k];
+  if (op.type < SQ_EXC_SA_DOUBLE_1 || op.type > SQ_EXC_SA_DOUBLE_5) {
+    sq_set_error("sq_layout_attach_generator: operator %d is not an sa_double", k);
+    return SQ_ERR_INVALID;
+  }
+  GenOp* g = new GenOp();
+  int st = parse_strings(lay->sp, n_strings, ops_flat, op_offsets, coeffs, 0, &g->strings, &g->coeffs);
+  if (st != SQ_OK) {
+    delete g;
+    return st;
+  }
+  delete op.multi;
+  op.multi = g;
+  return SQ_OK;
+}
+
+extern "C" int sq_layout_destroy(sq_layout* lay) {
+  if (!lay) return SQ_OK;
+  cudaSetDevice(lay->sp->device);
+  for (auto& pt : lay->pairs) {
+    cudaFree(pt.d_codeA);
+    cudaFree(pt.d_codeB);
+    cudaFree(pt.d_rowsA);
+  }
+  for (auto& gt : lay->gens) {
+    cudaFree(gt.d_srcRows);
+    cudaFree(gt.d_tgtRows);
+    cudaFree(gt.d_sgnRows);
+    cudaFree(gt.d_colCode);
+  }
+  for (auto& op : lay->ops) delete op.multi;
+  delete lay;
+  return SQ_OK;
+}
+
+extern "C" int sq_layout_num_ops(const sq_layout* lay) { return lay ? (int)lay->ops.size() : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// execution plan: consecutive operators on the same orbital pair fuse into one tile launch
+// ---------------------------------------------------------------------------------------------
+struct Run {
+  int kind;          // 0 tile run, 1 generic single-string, 2 multi-string (sa_double), 3 skip
+  int first, last;   // layout ops [first,last) in *execution* order (already reversed for dagger)
+};
+
+static inline bool is_tile_op(const LayoutOp& op) { return op.pair >= 0; }
+static inline int tile_steps_of(const LayoutOp& op) { return op.pair_double ? 1 : 2; }
+
+// order[] lists the operators in execution order; runs group them
+static void plan_runs(const sq_layout* lay, const std::vector<int>& order, const double* thetas,
+                      std::vector<std::vector<int>>* runs) {
+  runs->clear();
+  std::vector<int> cur;
+  int cur_pair = -1, cur_steps = 0;
+  auto flush = [&]() {
+    if (!cur.empty()) runs->push_back(cur);
+    cur.clear();
+    cur_pair = -1;
+    cur_steps = 0;
+  };
+  for (int k : order) {
+    const LayoutOp& op = lay->ops[k];
+    if (std::fabs(thetas[k]) < 1e-28) continue;   // operator_state_algebra.py:998
+    if (is_tile_op(op)) {
+      const int st = tile_steps_of(op);
+      if (op.pair != cur_pair || cur_steps + st > SQ_MAX_PROGRAM) flush();
+      cur.push_back(k);
+      cur_pair = op.pair;
+      cur_steps += st;
+    } else {
+      flush();
+      runs->push_back(std::vector<int>{k});
+    }
+  }
+  flush();
+}
+
+static void exec_order(int first, int last, int dagger, std::vector<int>* order) {
+  order->clear();
+  if (!dagger)
+    for (int k = first; k < last; ++k) order->push_back(k);
+  else
+    for (int k = last - 1; k >= first; --k) order->push_back(k);
+}
+
+extern "C" int sq_layout_num_launches(const sq_layout* lay, int first, int last) {
+  if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
+  std::vector<double> th(lay->ops.size(), 1.0);
+  std::vector<int> order;
+  exec_order(first, last, 0, &order);
+  std::vector<std::vector<int>> runs;
+  plan_runs(lay, order, th.data(), &runs);
+  int n = 0;
+  for (auto& r : runs) {
+    const LayoutOp& op = lay->ops[r[0]];
+    if (is_tile_op(op)) n += 1;
+    else if (op.gen >= 0) n += 1;
+    else if (op.multi) {
+      static const int napp[5] = {2, 4, 4, 8, 10};
+      n += 2 * napp[op.type - SQ_EXC_SA_DOUBLE_1];
+    }
+  }
+  return n;
+}
+
+// closed forms of exp(theta T) for the spin-adapted doubles (operator_state_algebra.py:1086-1409):
+// out += sum_m w_m(theta) T^m out with the reference's coefficient tables.
+static int sa_double_poly(sq_space* sp, const GenOp& g, int type, double theta, double* state, cudaStream_t st) {
+  SQ_CHECK(sq_ensure_work(sp, 0));
+  SQ_CHECK(sq_ensure_work(sp, 1));
+  double* tmp[2] = {sp->d_work[0], sp->d_work[1]};
+  std::vector<double> w;   // weight of T^m out, m = 1..
+  const double r2 = std::sqrt(2.0), r3 = std::sqrt(3.0);
+  if (type == SQ_EXC_SA_DOUBLE_1) {
+    w = {std::sin(theta), 1.0 - std::cos(theta)};   // osa.py:1069-1085
+  } else if (type == SQ_EXC_SA_DOUBLE_2 || type == SQ_EXC_SA_DOUBLE_3) {
+    const double S[2] = {1.0, r2 / 2};
+    const double k1[2] = {-1, 2 * r2}, k3[2] = {-2, 2 * r2}, k2[2] = {1, -4}, k4[2] = {2, -4};
+    const double* ks[4] = {k1, k2, k3, k4};
+    for (int m = 0; m < 4; ++m) {
+      double v = 0;
+      for (int f = 0; f < 2; ++f) v += ks[m][f] * ((m % 2 == 0) ? std::sin(S[f] * theta) : (std::cos(S[f] * theta) - 1));
+      w.push_back(v);
+    }
+  } else if (type == SQ_EXC_SA_DOUBLE_4) {
+    const double S[4] = {1.0, r2, r2 / 2, 0.5};
+    const double k1[4] = {2.0 / 3, -r2 / 42, -8 * r2 / 3, 128.0 / 21};
+    const double k3[4] = {13.0 / 3, -r2 / 6, -44 * r2 / 3, 64.0 / 3};
+    const double k5[4] = {22.0 / 3, -r2 / 3, -52 * r2 / 3, 64.0 / 3};
+    const double k7[4] = {8.0 / 3, -4 * r2 / 21, -16 * r2 / 3, 128.0 / 21};
+    const double k2[4] = {-2.0 / 3, 1.0 / 42, 16.0 / 3, -256.0 / 21};
+    const double k4[4] = {-13.0 / 3, 1.0 / 6, 88.0 / 3, -128.0 / 3};
+    const double k6[4] = {-22.0 / 3, 1.0 / 3, 104.0 / 3, -128.0 / 3};
+    const double k8[4] = {-8.0 / 3, 4.0 / 21, 32.0 / 3, -256.0 / 21};
+    const double* ks[8] = {k1, k2, k3, k4, k5, k6, k7, k8};
+    for (int m = 0; m < 8; ++m) {
+      double v = 0;
+      for (int f = 0; f < 4; ++f) v += ks[m][f] * ((m % 2 == 0) ? std::sin(S[f] * theta) : (std::cos(S[f] * theta) - 1));
+      w.push_back(v);
+    }
+  } else if (type == SQ_EXC_SA_DOUBLE_5) {
+    const double S[5] = {r2, r2 / 2, r3 / 3, r3 / 2, r3 / 6};
+    const double k1[5] = {r2 / 1150, 8 * r2 / 5, -54 * r3 / 25, -16 * r3 / 75, 432 * r3 / 115};
+    const double k3[5] = {11 * r2 / 690, 404 * r2 / 15, -171 * r3 / 5, -56 * r3 / 15, 2952 * r3 / 115};
+    const double k5[5] = {133 * r2 / 1725, 308 * r2 / 3, -2718 * r3 / 25, -1192 * r3 / 75, 1368 * r3 / 23};
+    const double k7[5] = {16 * r2 / 115, 608 * r2 / 5, -576 * r3 / 5, -112 * r3 / 5, 6192 * r3 / 115};
+    const double k9[5] = {48 * r2 / 575, 192 * r2 / 5, -864 * r3 / 25, -192 * r3 / 25, 1728 * r3 / 115};
+    const double k2[5] = {-1.0 / 1150, -16.0 / 5, 162.0 / 25, 32.0 / 75, -2592.0 / 115};
+    const double k4[5] = {-11.0 / 690, -808.0 / 15, 513.0 / 5, 112.0 / 15, -17712.0 / 115};
+    const double k6[5] = {-133.0 / 1725, -616.0 / 3, 8154.0 / 25, 2384.0 / 75, -8208.0 / 23};
+    const double k8[5] = {-16.0 / 115, -1216.0 / 5, 1728.0 / 5, 224.0 / 5, -37152.0 / 115};
+    const double k10[5] = {-48.0 / 575, -384.0 / 5, 2592.0 / 25, 384.0 / 25, -10368.0 / 115};
+    const double* ks[10] = {k1, k2, k3, k4, k5, k6, k7, k8, k9, k10};
+    for (int m = 0; m < 10; ++m) {
+      double v = 0;
+      for (int f = 0; f < 5; ++f) v += ks[m][f] * ((m % 2 == 0) ? std::sin(S[f] * theta) : (std::cos(S[f] * theta) - 1));
+      w.push_back(v);
+    }
+  } else {
+    return SQ_ERR_INVALID;
+  }
+  // sa_double_1 in the reference evaluates T and T^2 on the *old* out before updating; the higher
+  // cases update out progressively -- both are the same polynomial in T applied to the old vector,
+  // because every power is generated from the previous power (tmp), never from the updated out.
+  const double* src = state;
+  for (size_t m = 0; m < w.size(); ++m) {
+    double* dst = tmp[m & 1];
+    if (m == 0) {
+      // T^1: source is the state itself; it must not be modified until tmp holds T state
+      SQ_CHECK(sq_launch_gather(sp, g.strings, g.coeffs, src, dst, 0, st));
+    } else {
+      SQ_CHECK(sq_launch_gather(sp, g.strings, g.coeffs, tmp[(m - 1) & 1], dst, 0, st));
+    }
+    SQ_CHECK(sq_launch_axpy(sp, w[m], dst, state, st));
+  }
+  return SQ_OK;
+}
+
+static int run_tile(sq_space* sp, sq_layout* lay, const std::vector<int>& run, const double* thetas, int dagger,
+                    TileStep* steps, int* n_steps, int* step_op) {
+  int n = 0;
+  for (int k : run) {
+    const LayoutOp& op = lay->ops[k];
+    const double th = dagger ? -thetas[k] : thetas[k];
+    const double c = std::cos(th), s = std::sin(th);
+    if (op.pair_double) {
+      steps[n] = {2, c, s};
+      step_op[n++] = k;
+    } else {
+      // sa_single: alpha rotation then beta rotation (osa.py:1009-1042); they commute
+      steps[n] = {0, c, s};
+      step_op[n++] = k;
+      steps[n] = {1, c, s};
+      step_op[n++] = k;
+    }
+  }
+  *n_steps = n;
+  return SQ_OK;
+}
+
+extern "C" int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                            double* state_dev, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !state_dev) return SQ_ERR_INVALID;
+  const int P = (int)lay->ops.size();
+  if (first < 0 || last > P || first > last || (first < last && !thetas_host)) {
+    sq_set_error("sq_ups_apply: bad operator range [%d,%d) for %d operators", first, last, P);
+    return SQ_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  std::vector<int> order;
+  exec_order(first, last, dagger, &order);
+  std::vector<std::vector<int>> runs;
+  plan_runs(lay, order, thetas_host, &runs);
+  for (auto& run : runs) {
+    const LayoutOp& op = lay->ops[run[0]];
+    if (is_tile_op(op)) {
+      TileStep steps[SQ_MAX_PROGRAM];
+      int step_op[SQ_MAX_PROGRAM], n_steps = 0;
+      SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
+      SQ_CHECK(sq_launch_tile(sp, lay->pairs[op.pair], steps, n_steps, state_dev, st));
+    } else if (op.null_op) {
+      continue;
+    } else if (op.gen >= 0) {
+      const double th = dagger ? -thetas_host[run[0]] : thetas_host[run[0]];
+      SQ_CHECK(sq_launch_gen_rot(sp, lay->gens[op.gen], std::cos(th), std::sin(th), state_dev, st));
+    } else if (op.type >= SQ_EXC_SA_DOUBLE_1 && op.type <= SQ_EXC_SA_DOUBLE_5) {
+      if (!op.multi) {
+        sq_set_error("sa_double operator %d has no generator attached (sq_layout_attach_generator)", run[0]);
+        return SQ_ERR_INVALID;
+      }
+      const double th = dagger ? -thetas_host[run[0]] : thetas_host[run[0]];
+      SQ_CHECK(sa_double_poly(sp, *op.multi, op.type, th, state_dev, st));
+    } else {
+      sq_set_error("Got unknown excitation type code %d", op.type);
+      return SQ_ERR_INVALID;
+    }
+  }
+  return SQ_OK;
+}
+
+extern "C" int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, double* out_dev, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !in_dev || !out_dev || k < 0 || k >= (int)lay->ops.size()) return SQ_ERR_INVALID;
+  if (in_dev == out_dev) {
+    sq_set_error("sq_grad_action: in and out must not alias");
+    return SQ_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  const LayoutOp& op = lay->ops[k];
+  if (is_tile_op(op)) {
+    // T|in> through the gather kernel with the generator's strings (Ta + Tb for sa_single, osa.py:2794-2806)
+    const PairTables& pt = lay->pairs[op.pair];
+    const int i = pt.i, a = pt.a;
+    std::vector<std::vector<int32_t>> labels;
+    std::vector<double> cf;
+    if (op.pair_double) {
+      labels.push_back({2 * (2 * a + 1) + 1, 2 * (2 * a) + 1, 2 * (2 * i + 1), 2 * (2 * i)});
+      cf.push_back(-1.0);
+      labels.push_back({2 * (2 * i + 1) + 1, 2 * (2 * i) + 1, 2 * (2 * a + 1), 2 * (2 * a)});
+      cf.push_back(1.0);
+    } else {
+      labels.push_back({2 * (2 * a) + 1, 2 * (2 * i)});
+      cf.push_back(1.0);
+      labels.push_back({2 * (2 * i) + 1, 2 * (2 * a)});
+      cf.push_back(-1.0);
+      labels.push_back({2 * (2 * a + 1) + 1, 2 * (2 * i + 1)});
+      cf.push_back(1.0);
+      labels.push_back({2 * (2 * i + 1) + 1, 2 * (2 * a + 1)});
+      cf.push_back(-1.0);
+    }
+    std::vector<StringAction> acts(labels.size());
+    for (size_t s = 0; s < labels.size(); ++s)
+      SQ_CHECK(sq_make_string_action(sp, labels[s].data(), (int)labels[s].size(), &acts[s]));
+    return sq_launch_gather(sp, acts, cf, in_dev, out_dev, 0, st);
+  }
+  if (op.null_op) {
+    SQ_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (size_t)sp->local_len(), st));
+    return SQ_OK;
+  }
+  if (op.gen >= 0) return sq_launch_gen_apply(sp, lay->gens[op.gen], in_dev, out_dev, st);
+  if (op.multi) return sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, in_dev, out_dev, 0, st);
+  sq_set_error("sq_grad_action: operator %d has no generator", k);
+  return SQ_ERR_INVALID;
+}
+
+extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                                 double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !bra_dev || !ket_dev || !grad_host) return SQ_ERR_INVALID;
+  const int P = (int)lay->ops.size();
+  if (first < 0 || last > P || first > last) return SQ_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  for (int k = first; k < last; ++k) grad_host[k - first] = 0.0;
+  // zero-theta operators still contribute a gradient; only the rotation is skipped.  Plan with all
+  // operators (thetas replaced by 1 for the planner), rotations with c=1,s=0 are exact identities.
+  std::vector<double> plan_th(P, 1.0);
+  std::vector<int> order;
+  exec_order(first, last, 0, &order);
+  std::vector<std::vector<int>> runs;
+  plan_runs(lay, order, plan_th.data(), &runs);
+  for (auto& run : runs) {
+    const LayoutOp& op = lay->ops[run[0]];
+    if (is_tile_op(op)) {
+      TileStep steps[SQ_MAX_PROGRAM];
+      int step_op[SQ_MAX_PROGRAM], n_steps = 0;
+      SQ_CHECK(run_tile(sp, lay, run, thetas_host, 0, steps, &n_steps, step_op));
+      for (int s = 0; s < n_steps; ++s)
+        if (std::fabs(thetas_host[step_op[s]]) < 1e-28) { steps[s].c = 1.0; steps[s].s = 0.0; }
+      double g[SQ_MAX_PROGRAM];
+      SQ_CHECK(sq_launch_tile_grad(sp, lay->pairs[op.pair], steps, n_steps, bra_dev, ket_dev, g, st));
+      for (int s = 0; s < n_steps; ++s) grad_host[step_op[s] - first] += 2.0 * g[s];
+    } else if (op.null_op) {
+      continue;
+    } else if (op.gen >= 0) {
+      const int k = run[0];
+      double th = thetas_host[k];
+      double c = std::cos(th), s = std::sin(th);
+      if (std::fabs(th) < 1e-28) { c = 1.0; s = 0.0; }
+      double g = 0.0;
+      SQ_CHECK(sq_launch_gen_grad(sp, lay->gens[op.gen], c, s, bra_dev, ket_dev, &g, st));
+      grad_host[k - first] = 2.0 * g;
+    } else if (op.multi) {
+      const int k = run[0];
+      SQ_CHECK(sq_ensure_work(sp, 2));
+      SQ_CHECK(sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, ket_dev, sp->d_work[2], 0, st));
+      double g = 0.0;
+      SQ_CHECK(sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st));
+      grad_host[k - first] = 2.0 * g;
+      if (std::fabs(thetas_host[k]) >= 1e-28) {
+        SQ_CHECK(sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st));
+        SQ_CHECK(sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st));
+      }
+    } else {
+      sq_set_error("sq_ups_grad_sweep: operator %d has no generator", run[0]);
+      return SQ_ERR_INVALID;
+    }
+  }
+  return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic operators and BLAS-1
+// ---------------------------------------------------------------------------------------------
+extern "C" int sq_apply_strings(sq_space* sp, int n_strings, const int32_t* ops_flat, const int32_t* op_offsets,
+                                const double* coeffs, const double* in_dev, double* out_dev, int accumulate,
+                                int skip_outside, void* stream) {
+  if (!sp || n_strings < 0 || !in_dev || !out_dev || (n_strings > 0 && (!ops_flat || !op_offsets || !coeffs)))
+    return SQ_ERR_INVALID;
+  if (in_dev == out_dev) {
+    sq_set_error("sq_apply_strings: in and out must not alias");
+    return SQ_ERR_INVALID;
+  }
+  if (sp->device < 0) {
+    sq_set_error("sq_apply_strings: host-only space (device = -1) cannot run kernels");
+    return SQ_ERR_INVALID;
+  }
+  SQ_CUDA(cudaSetDevice(sp->device));
+  std::vector<StringAction> acts;
+  std::vector<double> cf;
+  SQ_CHECK(parse_strings(sp, n_strings, ops_flat, op_offsets, coeffs, skip_outside, &acts, &cf));
+  return sq_launch_gather(sp, acts, cf, in_dev, out_dev, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int sq_dot(sq_space* sp, const double* a_dev, const double* b_dev, double* out_host, void* stream) {
+  if (!sp || !a_dev || !b_dev || !out_host) return SQ_ERR_INVALID;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  if (sp->local_len() == 0) {
+    *out_host = 0.0;
+    return SQ_OK;
+  }
+  return sq_launch_dot(sp, a_dev, b_dev, out_host, (cudaStream_t)stream);
+}
+
+extern "C" int sq_axpy(sq_space* sp, double alpha, const double* x_dev, double* y_dev, void* stream) {
+  if (!sp || !x_dev || !y_dev) return SQ_ERR_INVALID;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  return sq_launch_axpy(sp, alpha, x_dev, y_dev, (cudaStream_t)stream);
+}
+
+extern "C" int sq_scale_copy(sq_space* sp, double alpha, const double* x_dev, double* y_dev, void* stream) {
+  if (!sp || !x_dev || !y_dev) return SQ_ERR_INVALID;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  return sq_launch_scale_copy(sp, alpha, x_dev, y_dev, (cudaStream_t)stream);
+}

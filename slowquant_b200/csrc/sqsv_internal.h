@@ -1,0 +1,149 @@
+// Internal structures of libsqsv (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "sqsv.h"
+
+#define SQ_MAX_ORB 32          // string occupation masks are uint32_t
+#define SQ_MAX_STRING_OPS 32   // ladder operators per normal-ordered string
+#define SQ_MAX_PROGRAM 8       // fused rotation steps per tile launch
+
+extern std::atomic<int64_t> g_sq_launches;
+void sq_set_error(const char* fmt, ...);
+
+#define SQ_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      sq_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+      return SQ_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define SQ_CHECK(st)            \
+  do {                          \
+    int s_ = (st);              \
+    if (s_ != SQ_OK) return s_; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Action of ONE normal-ordered ladder-operator string on a determinant |A,B> (A/B = alpha/beta
+// occupation masks, bit o = spatial orbital o), in *source* form:
+//   valid(src)  <=>  (A & occA)==occA && (A & empA)==0 && (B & occB)==occB && (B & empB)==0
+//   tgt         =    (A ^ flipA, B ^ flipB)
+//   sign        =    s0 * (-1)^{popc(A & parA) + popc(B & parB)}
+// This closed form is equivalent to the reference's sequential bit-flip/popcount loop
+// (operator_state_algebra.py:118-135): the phase contributed by ladder operator k is
+// popc((src ^ F_k) & below_k), and parities of popcounts add as XOR of masks.
+// ---------------------------------------------------------------------------------------------
+struct StringAction {
+  uint32_t occA, empA, flipA, parA;
+  uint32_t occB, empB, flipB, parB;
+  int s0;        // +1 / -1
+  bool conserving;  // keeps N_alpha and N_beta (otherwise the string leaves the CI space)
+  // target-form screens (for the gather kernel): tgt must have tocc* set and temp* clear
+  uint32_t toccA, tempA, toccB, tempB;
+};
+
+// packed per-string code used by the tile kernels (one uint32 per alpha / beta string):
+//   bits 1:0  class: 0 inert, 1 src (i occupied, a empty), 2 tgt
+//   bit  2    same-spin single-excitation sign negative         (src only)
+//   bit  3    cross sign negative: factor this string gives the other spin's single (all strings)
+//   bit  4    pair-double sign factor negative                  (src only)
+//   bits 31:5 partner string index                              (src only)
+#define SQ_CLS_INERT 0u
+#define SQ_CLS_SRC 1u
+#define SQ_CLS_TGT 2u
+
+struct PairTables {       // tables for one spatial orbital pair (i,a)
+  int i, a;
+  uint32_t* d_codeA = nullptr;   // [NA]
+  uint32_t* d_codeB = nullptr;   // [NB]
+  int32_t* d_rowsA = nullptr;    // alpha rows that are src or inert (tgt rows ride with their src)
+  int64_t n_rows = 0;            // local row items
+  int64_t n_src_rows = 0, n_src_cols = 0;
+  int64_t touched = 0;           // amplitudes a full sa_single(+double) block touches (local rows)
+};
+
+struct GenTables {        // tables for one generic excitation generator G (single string)
+  StringAction act;
+  int32_t* d_srcRows = nullptr;  // alpha strings valid as source (local rows)
+  int32_t* d_tgtRows = nullptr;  // their targets
+  int8_t* d_sgnRows = nullptr;   // alpha sign factor (includes s0)
+  int64_t n_rows = 0;
+  int32_t* d_colCode = nullptr;  // [NB]: (partner<<1 | neg) for valid beta sources, -1 otherwise
+  int64_t n_cols_valid = 0;
+};
+
+struct sq_space {
+  int n_orb, n_alpha, n_beta, device;
+  int64_t NA, NB, ndet;
+  int64_t row_begin, row_end;       // local alpha rows
+  uint64_t binom[SQ_MAX_ORB + 2][SQ_MAX_ORB + 2];
+  std::vector<uint32_t> strA, strB; // occupation masks in itertools.combinations order
+  std::vector<int32_t> rankA, rankB;  // mask -> string index (-1 if wrong electron count); 2^n entries
+  uint32_t *d_strA = nullptr, *d_strB = nullptr;
+  int32_t *d_rankA = nullptr, *d_rankB = nullptr;
+  // reduction scratch
+  double* d_partial = nullptr;
+  int64_t n_partial = 0;
+  double* h_pinned = nullptr;       // small pinned staging buffer
+  // lazily allocated full-vector work buffers (sa_double polynomial, sigma)
+  double* d_work[3] = {nullptr, nullptr, nullptr};
+  int64_t local_len() const { return (row_end - row_begin) * NB; }
+};
+
+struct GenOp {   // generic multi-string generator (sa_double_*)
+  std::vector<StringAction> strings;
+  std::vector<double> coeffs;
+};
+
+struct LayoutOp {
+  int type;
+  std::vector<int> idx;
+  int pair = -1;      // index into sq_layout::pairs (sa_single / pair-double)
+  bool pair_double = false;
+  int gen = -1;       // index into sq_layout::gens (generic single-string generator)
+  bool null_op = false;  // generator vanishes identically
+  GenOp* multi = nullptr;
+};
+
+struct sq_layout {
+  sq_space* sp;
+  std::vector<LayoutOp> ops;
+  std::vector<PairTables> pairs;
+  std::map<std::pair<int, int>, int> pair_index;
+  std::vector<GenTables> gens;
+  std::map<std::vector<int>, int> gen_index;
+};
+
+// host helpers (sqsv_space.cu)
+int sq_rank_mask(const sq_space* sp, int spin, uint32_t mask);   // -1 if not in list
+int sq_make_string_action(const sq_space* sp, const int32_t* ops, int n_ops, StringAction* out);
+int sq_ensure_work(sq_space* sp, int which);
+int sq_ensure_partial(sq_space* sp, int64_t n);
+
+// kernel launchers (sqsv_kernels.cu)
+struct TileStep { int kind; double c, s; };   // kind: 0 alpha-rot, 1 beta-rot, 2 pair-double rot
+int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
+                   double* state, cudaStream_t st);
+int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
+                        double* bra, double* ket, double* grad_out_host, cudaStream_t st);
+int sq_launch_gen_rot(sq_space* sp, const GenTables& gt, double c, double s, double* state,
+                      cudaStream_t st);
+int sq_launch_gen_apply(sq_space* sp, const GenTables& gt, const double* in, double* out,
+                        cudaStream_t st);
+int sq_launch_gen_grad(sq_space* sp, const GenTables& gt, double c, double s, double* bra, double* ket,
+                       double* grad_out_host, cudaStream_t st);
+int sq_launch_gather(sq_space* sp, const std::vector<StringAction>& strings,
+                     const std::vector<double>& coeffs, const double* in, double* out, int accumulate,
+                     cudaStream_t st);
+int sq_launch_dot(sq_space* sp, const double* a, const double* b, double* out_host, cudaStream_t st);
+int sq_launch_axpy(sq_space* sp, double alpha, const double* x, double* y, cudaStream_t st);
+int sq_launch_scale_copy(sq_space* sp, double alpha, const double* x, double* y, cudaStream_t st);

@@ -1,0 +1,384 @@
+"""Operator-state algebra on the B200 engine.
+
+Same function names, argument order and error behaviour as the reference's
+slowquant/unitary_coupled_cluster/operator_state_algebra.py; the numerics run in libsqsv's CUDA kernels.
+
+State vectors may be numpy arrays (host; copied to the device and back on every call, exactly the
+reference's value semantics) or ``torch.float64`` CUDA tensors (device resident; results are new CUDA
+tensors).  Inputs are never modified.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+
+from slowquant_b200 import _lib
+from slowquant_b200.ci_spaces import CI_Info
+from slowquant_b200.fermionic_operator import FermionicOperator
+from slowquant_b200.operators import ActiveSpaceHamiltonian, G2_sa
+from slowquant_b200.util import UccStructure, UpsStructure
+
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int32)
+
+
+# ---- plumbing -----------------------------------------------------------------------------------
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device_of(ci_info: CI_Info) -> torch.device:
+    return torch.device("cuda", ci_info.device)
+
+
+def _to_device(state, ci_info: CI_Info, copy: bool = True) -> tuple[torch.Tensor, bool]:
+    """Return (fp64 CUDA tensor holding a private copy of `state`, input_was_numpy)."""
+    dev = _device_of(ci_info)
+    if isinstance(state, torch.Tensor):
+        if state.dtype != torch.float64:
+            raise TypeError(f"state tensors must be float64, got {state.dtype}")
+        t = state.to(dev)
+        if copy and t.data_ptr() == state.data_ptr():
+            t = t.clone()
+        t = t.contiguous()
+        was_numpy = False
+    else:
+        arr = np.ascontiguousarray(state, dtype=np.float64)
+        t = torch.from_numpy(arr).to(dev)
+        was_numpy = True
+    if t.numel() != ci_info.local_len:
+        raise ValueError(f"state has {t.numel()} elements, the CI space holds {ci_info.local_len}")
+    return t, was_numpy
+
+
+def _from_device(t: torch.Tensor, was_numpy: bool):
+    if was_numpy:
+        return t.cpu().numpy()
+    return t
+
+
+def _ptr(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def encode_operator(op: FermionicOperator) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Flatten a FermionicOperator into (ops_flat, offsets, coeffs); entry = 2*spin_orbital + dagger."""
+    labels = op.operators
+    n = len(labels)
+    offsets = np.zeros(n + 1, dtype=np.int32)
+    flat: list[int] = []
+    coeffs = np.empty(n, dtype=np.float64)
+    for s, (label, fac) in enumerate(labels.items()):
+        for idx, dag in label:
+            flat.append(2 * int(idx) + (1 if dag else 0))
+        offsets[s + 1] = len(flat)
+        coeffs[s] = fac
+    ops_flat = np.asarray(flat, dtype=np.int32) if flat else np.zeros(1, dtype=np.int32)
+    return ops_flat, offsets, coeffs
+
+
+def _apply_operator(op: FermionicOperator, src: torch.Tensor, dst: torch.Tensor, ci_info: CI_Info, do_unsafe: bool) -> None:
+    """dst <- op|src> (strings applied by the gather kernel; replaces osa.py:596-628)."""
+    lib = _lib.load()
+    ops_flat, offsets, coeffs = encode_operator(op)
+    _lib.check(
+        lib.sq_apply_strings(
+            ci_info._handle,
+            len(coeffs),
+            ops_flat.ctypes.data_as(_PI),
+            offsets.ctypes.data_as(_PI),
+            coeffs.ctypes.data_as(_PD),
+            _ptr(src),
+            _ptr(dst),
+            0,
+            1 if do_unsafe else 0,
+            _stream(),
+        )
+    )
+
+
+_SIGMA_AVAILABLE = True
+
+
+def _apply_hamiltonian(op: ActiveSpaceHamiltonian, src: torch.Tensor, dst: torch.Tensor, ci_info: CI_Info) -> bool:
+    """dst <- H|src> through the dedicated sigma kernel; False if it cannot be used for this operator."""
+    global _SIGMA_AVAILABLE
+    if not _SIGMA_AVAILABLE:
+        return False
+    if op._ops is not None:  # operator was modified / materialised: treat as generic strings
+        return False
+    if op.num_inactive_orbs != ci_info.num_inactive_orbs or op.num_active_orbs != ci_info.num_active_orbs:
+        return False
+    lib = _lib.load()
+    e_core, h_eff, g_act = op.folded_integrals()
+    status = lib.sq_sigma(
+        ci_info._handle,
+        e_core,
+        h_eff.ctypes.data_as(_PD),
+        g_act.ctypes.data_as(_PD),
+        _ptr(src),
+        _ptr(dst),
+        _stream(),
+    )
+    if status == _lib.SQ_ERR_UNSUPPORTED:
+        _SIGMA_AVAILABLE = False
+        return False
+    _lib.check(status)
+    return True
+
+
+_SA_CASE = {"sa_double_1": 1, "sa_double_2": 2, "sa_double_3": 3, "sa_double_4": 4, "sa_double_5": 5}
+
+
+def compile_layout(ci_info: CI_Info, wf_struct: UpsStructure) -> C.c_void_p:
+    """Compile (and cache on the CI_Info) the device layout for an ansatz structure."""
+    types = wf_struct.excitation_operator_type
+    indices = wf_struct.excitation_indices
+    key = (id(wf_struct), len(types), hash(tuple(types)), hash(tuple(tuple(int(x) for x in t) for t in indices)))
+    lay = ci_info._layouts.get(key)
+    if lay is not None:
+        return lay
+    lib = _lib.load()
+    n = len(types)
+    codes = np.empty(max(n, 1), dtype=np.int32)
+    offsets = np.zeros(n + 1, dtype=np.int32)
+    flat: list[int] = []
+    off = ci_info.space_extension_offset
+    for k, (t, idx) in enumerate(zip(types, indices)):
+        if t not in _lib.EXC_CODES:
+            raise ValueError(f"Got unknown excitation type, {t}")
+        codes[k] = _lib.EXC_CODES[t]
+        shift = off if t.startswith("sa_") else 2 * off
+        flat.extend(int(x) + shift for x in idx)
+        offsets[k + 1] = len(flat)
+    flat_arr = np.asarray(flat, dtype=np.int32) if flat else np.zeros(1, dtype=np.int32)
+    handle = C.c_void_p()
+    _lib.check(
+        lib.sq_layout_create(
+            ci_info._handle, n, codes.ctypes.data_as(_PI), offsets.ctypes.data_as(_PI), flat_arr.ctypes.data_as(_PI), C.byref(handle)
+        )
+    )
+    # spin-adapted doubles: attach the normal-ordered strings of T = G - G^dagger (osa.py:1063-1065, 1087-1092, ...)
+    gen_cache: dict[tuple, tuple] = {}
+    for k, (t, idx) in enumerate(zip(types, indices)):
+        if t in _SA_CASE:
+            i, j, a, b = (int(x) + off for x in idx)
+            ck = (i, j, a, b, t)
+            if ck not in gen_cache:
+                gen_cache[ck] = encode_operator(G2_sa(i, j, a, b, _SA_CASE[t], True))
+            ops_flat, op_offsets, coeffs = gen_cache[ck]
+            _lib.check(
+                lib.sq_layout_attach_generator(
+                    handle, k, len(coeffs), ops_flat.ctypes.data_as(_PI), op_offsets.ctypes.data_as(_PI), coeffs.ctypes.data_as(_PD)
+                )
+            )
+    ci_info._layouts[key] = handle
+    return handle
+
+
+def _thetas_array(thetas: Sequence[float], n: int) -> np.ndarray:
+    th = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64))
+    if th.size != n:
+        raise ValueError(f"Expected {n} theta values got {th.size}")
+    return th
+
+
+def _ups_apply_inplace(
+    t: torch.Tensor, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, first: int, last: int, dagger: bool
+) -> None:
+    lib = _lib.load()
+    lay = compile_layout(ci_info, ups_struct)
+    th = _thetas_array(thetas, len(ups_struct.excitation_operator_type))
+    _lib.check(
+        lib.sq_ups_apply(ci_info._handle, lay, th.ctypes.data_as(_PD), first, last, 1 if dagger else 0, _ptr(t), _stream())
+    )
+
+
+# ---- public surface -----------------------------------------------------------------------------
+def construct_ups_state(state, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, dagger: bool = False):
+    r"""Apply the unitary product :math:`U_N \dots U_0` (or its adjoint) to `state` (osa.py:963-1412)."""
+    t, was_numpy = _to_device(state, ci_info)
+    _ups_apply_inplace(t, ci_info, thetas, ups_struct, 0, len(ups_struct.excitation_operator_type), dagger)
+    return _from_device(t, was_numpy)
+
+
+def propagate_unitary(state, idx: int, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure):
+    """Apply the single unitary number `idx` of the layout (osa.py:1867-2309)."""
+    n = len(ups_struct.excitation_operator_type)
+    if not 0 <= idx < n:
+        raise IndexError(f"unitary index {idx} out of range for {n} operators")
+    t, was_numpy = _to_device(state, ci_info)
+    _ups_apply_inplace(t, ci_info, thetas, ups_struct, idx, idx + 1, False)
+    return _from_device(t, was_numpy)
+
+
+def get_grad_action(state, idx: int, ci_info: CI_Info, ups_struct: UpsStructure):
+    r"""Apply the generator :math:`T_{idx}` to `state` (osa.py:2757-2865)."""
+    n = len(ups_struct.excitation_operator_type)
+    if not 0 <= idx < n:
+        raise IndexError(f"operator index {idx} out of range for {n} operators")
+    lib = _lib.load()
+    lay = compile_layout(ci_info, ups_struct)
+    t, was_numpy = _to_device(state, ci_info, copy=False)
+    out = torch.empty_like(t)
+    _lib.check(lib.sq_grad_action(ci_info._handle, lay, idx, _ptr(t), _ptr(out), _stream()))
+    return _from_device(out, was_numpy)
+
+
+def construct_ucc_state(state, ci_info: CI_Info, thetas: Sequence[float], ucc_struct: UccStructure, dagger: bool = False):
+    """exp(T - T^dagger)|state> for the non-factorised UCC (osa.py:870-896), matrix free."""
+    from slowquant_b200.ucc_state import expm_multiply_operator, get_ucc_T
+
+    T = get_ucc_T(thetas, ucc_struct, ci_info.space_extension_offset)
+    t, was_numpy = _to_device(state, ci_info, copy=False)
+    out = expm_multiply_operator(T, t, ci_info, -1.0 if dagger else 1.0)
+    return _from_device(out, was_numpy)
+
+
+def propagate_state(
+    operators: list[FermionicOperator | str],
+    state,
+    ci_info: CI_Info,
+    thetas: Sequence[float] | None = None,
+    wf_struct: UpsStructure | UccStructure | None = None,
+    do_folding: bool = True,
+    do_unsafe: bool = False,
+):
+    r"""Apply `operators` right to left to `state` (osa.py:472-630).
+
+    Elements are FermionicOperators (folded to the active space unless ``do_folding=False``) or the strings
+    ``"U"`` / ``"Ud"`` for the ansatz unitary and its adjoint.  Returns a new state.
+    """
+    if len(operators) == 0:
+        return np.copy(state) if not isinstance(state, torch.Tensor) else state.clone()
+    cur, was_numpy = _to_device(state, ci_info)
+    tmp = None
+    for op in operators[::-1]:
+        if isinstance(op, str):
+            if op not in ("U", "Ud"):
+                raise ValueError(f"Unknown str operator, expected ('U', 'Ud') got {op}")
+            dagger = op == "Ud"
+            if isinstance(wf_struct, UpsStructure) or (
+                not isinstance(wf_struct, UccStructure) and hasattr(wf_struct, "grad_param_R")
+            ):
+                if thetas is None:
+                    raise ValueError("theta must be different from None")
+                _ups_apply_inplace(cur, ci_info, thetas, wf_struct, 0, len(wf_struct.excitation_operator_type), dagger)
+            elif isinstance(wf_struct, UccStructure):
+                if thetas is None:
+                    raise ValueError("theta must be different from None")
+                cur = construct_ucc_state(cur, ci_info, thetas, wf_struct, dagger=dagger)
+            else:
+                raise TypeError(f"Got unknown wave function structure type, {type(wf_struct)}")
+        else:
+            if tmp is None:
+                tmp = torch.empty_like(cur)
+            done = False
+            if do_folding and isinstance(op, ActiveSpaceHamiltonian):
+                done = _apply_hamiltonian(op, cur, tmp, ci_info)
+            if not done:
+                if do_folding:
+                    op_folded = op.get_folded_operator(
+                        ci_info.num_inactive_orbs, ci_info.num_active_orbs, ci_info.num_virtual_orbs
+                    )
+                else:
+                    op_folded = op
+                _apply_operator(op_folded, cur, tmp, ci_info, do_unsafe)
+            cur, tmp = tmp, cur
+    return _from_device(cur, was_numpy)
+
+
+def _dot(a: torch.Tensor, b: torch.Tensor, ci_info: CI_Info) -> float:
+    lib = _lib.load()
+    out = C.c_double(0.0)
+    _lib.check(lib.sq_dot(ci_info._handle, _ptr(a), _ptr(b), C.byref(out), _stream()))
+    return float(out.value)
+
+
+def expectation_value(
+    bra,
+    operators: list[FermionicOperator | str],
+    ket,
+    ci_info: CI_Info,
+    thetas: Sequence[float] | None = None,
+    wf_struct: UpsStructure | UccStructure | None = None,
+    do_folding: bool = True,
+    do_unsafe: bool = False,
+) -> float:
+    """<bra| operators |ket> as a Python float (osa.py:784-824)."""
+    ket_t, _ = _to_device(ket, ci_info, copy=False)
+    op_ket = propagate_state(operators, ket_t, ci_info, thetas, wf_struct, do_folding=do_folding, do_unsafe=do_unsafe)
+    bra_t, _ = _to_device(bra, ci_info, copy=False)
+    val = _dot(bra_t, op_ket, ci_info)
+    if not isinstance(val, float):
+        raise ValueError(f"Calculated expectation value is not a float, got type {type(val)}")
+    return val
+
+
+def ups_gradient_sweep(
+    bra, ket, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure
+) -> tuple[np.ndarray, object, object]:
+    r"""Fused reverse sweep of ups_wavefunction.py:1114-1138.
+
+    For every operator k (ascending): ``g[k] = 2 <bra|T_k|ket>``, then ``bra <- U_k bra``, ``ket <- U_k ket``.
+    Returns (g, bra_final, ket_final).
+    """
+    lib = _lib.load()
+    lay = compile_layout(ci_info, ups_struct)
+    n = len(ups_struct.excitation_operator_type)
+    th = _thetas_array(thetas, n)
+    b, b_np = _to_device(bra, ci_info)
+    k, k_np = _to_device(ket, ci_info)
+    g = np.zeros(n, dtype=np.float64)
+    _lib.check(
+        lib.sq_ups_grad_sweep(ci_info._handle, lay, th.ctypes.data_as(_PD), 0, n, _ptr(b), _ptr(k), g.ctypes.data_as(_PD), _stream())
+    )
+    return g, _from_device(b, b_np), _from_device(k, k_np)
+
+
+# ---- state-averaged twins: batches [n_states, N_det] (osa.py:633-781, 827-867, 1415-1864, 2312-2976) ----
+def _map_states(fn, states):
+    if isinstance(states, torch.Tensor):
+        return torch.stack([fn(s) for s in states])
+    return np.array([fn(s) for s in states])
+
+
+def propagate_state_SA(operators, state, ci_info, thetas=None, wf_struct=None, do_folding=True, do_unsafe=False):
+    return _map_states(lambda s: propagate_state(operators, s, ci_info, thetas, wf_struct, do_folding, do_unsafe), state)
+
+
+def expectation_value_SA(bra, operators, ket, ci_info, thetas=None, wf_struct=None, do_folding=True) -> float:
+    val = 0.0
+    for b, k in zip(bra, ket):
+        val += expectation_value(b, operators, k, ci_info, thetas, wf_struct, do_folding=do_folding)
+    return val / len(bra)
+
+
+def construct_ups_state_SA(state, ci_info, thetas, ups_struct, dagger=False):
+    return _map_states(lambda s: construct_ups_state(s, ci_info, thetas, ups_struct, dagger), state)
+
+
+def propagate_unitary_SA(state, idx, ci_info, thetas, ups_struct):
+    return _map_states(lambda s: propagate_unitary(s, idx, ci_info, thetas, ups_struct), state)
+
+
+def get_grad_action_SA(state, idx, ci_info, ups_struct):
+    return _map_states(lambda s: get_grad_action(s, idx, ci_info, ups_struct), state)
+
+
+def build_operator_matrix(op: FermionicOperator, ci_info: CI_Info, do_unsafe: bool = False) -> np.ndarray:
+    """Dense matrix of an (unfolded) operator, column j = op|j> (osa.py:413-469).  Small spaces only."""
+    n = ci_info.num_det
+    dev = _device_of(ci_info)
+    mat = np.zeros((n, n), dtype=np.float64)
+    unit = torch.zeros(n, dtype=torch.float64, device=dev)
+    out = torch.empty_like(unit)
+    for j in range(n):
+        unit.zero_()
+        unit[j] = 1.0
+        _apply_operator(op, unit, out, ci_info, do_unsafe)
+        mat[:, j] = out.cpu().numpy()
+    return mat
