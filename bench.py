@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: tUPS layer applications per second at CAS(16,16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cas N_ORB] [--layers L]
+
+A *step* applies one L-layer tUPS circuit (L = 16 -> 720 ansatz operators, reference util.py:694-745) to
+the resident 165 636 900-amplitude fp64 CI vector.  `value` = layers/s with the vector resident in HBM;
+`e2e` = the same through the public `construct_ups_state(numpy_state, ...)` call with pinned HOST buffers
+(H2D of the state + D2H of the result inside the timed region).  One JSON line is printed by rank 0.
+
+N > 1 (torchrun): the CAS(16,16) vector fits one GPU, so ranks run independent replicas of the workload
+(different theta sets, as RotoSolve / finite-difference columns do) -- weak scaling, no data-path collective.
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP over all host
+cores) on a bounded sample of the same workload; /root/reference itself is pure Python + numba and does
+not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "tUPS layer applications/s at CAS(16,16)"
+UNIT = "layers/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cas", type=int, default=16, help="active orbitals n; CAS(n,n)")
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n: int, L: int) -> str:
+    from math import comb
+
+    nd = comb(n, n // 2) ** 2
+    return f"synthetic random-parameter tUPS CAS({n},{n}) state construction, {nd} determinants, L={L} layers ({3 * (n - 1) * L} operators) per step"
+
+
+def measured_peak() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples: list[int] = []
+        self.reasons: set[str] = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown",
+            nv.nvmlClocksThrottleReasonApplicationsClocksSetting: "applications_clocks_setting",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self) -> dict:
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference algorithm on a bounded sample
+# ---------------------------------------------------------------------------------------------
+_CPU_CACHE: dict = {}
+
+
+def cpu_sample(n: int) -> dict:
+    """Time ONE exp(theta T) rotation (the pair `double` of the first tUPS brick: 6 string passes +
+    the numpy closed form, reference osa.py:1043-1085) on the dense CAS(n,n) vector with the oracle's
+    OpenMP restatement of apply_operator_threaded (osa.py:139-219), and scale to one layer.
+
+    One tUPS layer on n orbitals has (n-1) bricks [sa_single, double, sa_single]; an sa_single is two such
+    rotations in sequence (alpha then beta, osa.py:1009-1042), so a layer costs 5(n-1) rotations.
+    """
+    from oracle import sq_oracle as orc
+
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    ne = n // 2
+    if n not in _CPU_CACHE:
+        sp = orc.get_indexing(0, n, 0, ne, ne)
+        rng = np.random.default_rng(1234)
+        state = rng.normal(size=sp.num_det)
+        state /= np.linalg.norm(state)
+        _CPU_CACHE[n] = (sp, state)
+    sp, state = _CPU_CACHE[n]
+    types, idx = orc.tiled_layout(n, 1)
+    assert types[1] == "double"
+    t0 = time.perf_counter()
+    orc.construct_ups_state(state, sp, [0.7], types[1:2], idx[1:2], threaded=True)
+    dt = time.perf_counter() - t0
+    rotations_per_layer = 5 * (n - 1)
+    layer_s = dt * rotations_per_layer
+    return {
+        "value": 1.0 / layer_s,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"1 of the {rotations_per_layer} exp(theta T) rotations of one tUPS layer (pair double of the first "
+        f"brick, 6 string passes) on the dense CAS({n},{n}) vector ({sp.num_det} determinants): {dt:.2f} s, "
+        f"scaled x{rotations_per_layer} to one layer",
+        "seconds_per_sample": dt,
+    }
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, L = args.cas, args.layers
+    for _ in range(args.warmup):
+        cpu_sample(n)
+    t_total = 0.0
+    res = None
+    for _ in range(args.steps):
+        res = cpu_sample(n)
+        t_total += res["seconds_per_sample"]
+    mean_sample = t_total / max(args.steps, 1)
+    layer_s = mean_sample * 5 * (n - 1)
+    value = 1.0 / layer_s
+    cpu = dict(res)
+    cpu["value"] = value
+    cpu.pop("seconds_per_sample", None)
+    line = {
+        "impl": "reference",
+        "metric": METRIC if n == 16 else f"tUPS layer applications/s at CAS({n},{n})",
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * layer_s * L,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(n, L), "step_is": "bounded sample: one exp(theta T) rotation, scaled to L layers"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the engine")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from slowquant_b200 import _lib
+    from slowquant_b200.ci_spaces import get_indexing
+    from slowquant_b200.operator_state_algebra import _ups_apply_inplace, compile_layout, construct_ups_state
+    from slowquant_b200.util import UpsStructure
+
+    lib = _lib.load()
+    n, L = args.cas, args.layers
+    ne = n // 2
+    info = get_indexing(0, n, 0, ne, ne, device=local_rank)
+    lay = UpsStructure()
+    lay.create_tiled(n, {"n_layers": L, "do_tups": True})
+    P = lay.n_params
+    rng = np.random.default_rng(1234 + rank)
+    thetas = rng.uniform(-np.pi, np.pi, P)
+    handle = compile_layout(info, lay)
+    launches_per_step = int(lib.sq_layout_num_launches(handle, 0, P))
+    touched_per_step = int(lib.sq_layout_touched_amplitudes(handle, 0, P))
+
+    state = torch.zeros(info.num_det, dtype=torch.float64, device=dev)
+    state[0] = 1.0  # HF determinant ("1"*ne*2 + "0"*...), index 0
+
+    def step():
+        _ups_apply_inplace(state, info, thetas, lay, 0, P, False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = int(lib.sq_launch_count())
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = int(lib.sq_launch_count()) - launches0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    norm = float(torch.linalg.norm(state))
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * L * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.zeros(info.num_det, dtype=torch.float64).pin_memory()
+        host_in[0] = 1.0
+        np_in = host_in.numpy()
+        out = construct_ups_state(np_in, info, thetas, lay)  # warm-up (pinned pool, layout cache)
+        del out
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            out = construct_ups_state(np_in, info, thetas, lay)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t2 = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": world * L * n_e2e / float(t2.item()),
+            "unit": UNIT,
+            "h2d_bytes_per_step": int(8 * info.num_det + 8 * P),
+            "d2h_bytes_per_step": int(8 * info.num_det),
+            "steps": n_e2e,
+            "norm_check": float(np.linalg.norm(out)),
+        }
+        del out, host_in, np_in
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        launch_ms = ms_max / max(launches, 1)
+        bytes_per_launch = 16.0 * touched_per_step / max(launches_per_step, 1)
+        achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        roofline = {
+            "kernel": "tile_kernel (fused sa_single+double+sa_single brick)",
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": peak,
+            "peak_source": peak_src,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": None,
+            "algorithmic_bytes_per_launch": bytes_per_launch,
+            "avg_launch_ms": launch_ms,
+            "full_sweep_equiv_GBps": 16.0 * info.num_det / (launch_ms * 1e-3) / 1e9,
+        }
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cpu = cpu_sample(n)
+                cpu.pop("seconds_per_sample", None)
+            except Exception as exc:  # the baseline is a reported number, never a gate
+                cpu = {"error": repr(exc)}
+        line = {
+            "metric": METRIC if n == 16 else f"tUPS layer applications/s at CAS({n},{n})",
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": workload_name(n, L),
+                "l2_policy": "inputs larger than L2 (1.325 GB vector vs 126 MB L2)",
+                "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one CAS vector per GPU), no collective",
+                "fusion": "3 operators (one brick) per kernel launch",
+            },
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "state_norm": norm,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

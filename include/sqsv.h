@@ -96,6 +96,8 @@ int sq_layout_destroy(sq_layout* lay);
 int sq_layout_num_ops(const sq_layout* lay);
 /* number of kernel launches sq_ups_apply would issue for ops [first,last) (all |theta| > 1e-28) */
 int sq_layout_num_launches(const sq_layout* lay, int first, int last);
+/* amplitudes those launches read and write; algorithmic HBM bytes = 16 * this (roofline accounting) */
+int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last);
 
 /* ---- unitary product state (construct_ups_state, operator_state_algebra.py:963-1412;
  *      propagate_unitary, :1867-2309) ---------------------------------------------------------- */

@@ -98,11 +98,16 @@ static inline int64_t det2idx(const orc_space* s, int64_t det) {
   const int n = s->n;
   if (det < 0 || (n < 32 && (det >> (2 * n)) != 0)) return -1;
   uint32_t a = 0, b = 0;
+#ifdef __BMI2__
+  a = (uint32_t)__builtin_ia32_pext_di((unsigned long long)det, 0xAAAAAAAAAAAAAAAAull);
+  b = (uint32_t)__builtin_ia32_pext_di((unsigned long long)det, 0x5555555555555555ull);
+#else
   for (int o = 0; o < n; ++o) {
     int sh = 2 * (n - 1 - o);
     a = (a << 1) | (uint32_t)((det >> (sh + 1)) & 1);
     b = (b << 1) | (uint32_t)((det >> sh) & 1);
   }
+#endif
   int32_t ra = s->rankA[a], rb = s->rankB[b];
   if (ra < 0 || rb < 0) return -1;
   return (int64_t)ra * s->NB + rb;
@@ -112,9 +117,8 @@ int64_t orc_det2idx(const orc_space* s, int64_t det) { return det2idx(s, det); }
 
 /* Brian Kernighan popcount, as operator_state_algebra.py:33-50 */
 static inline int bitcount(int64_t x) {
-  int b = 0;
-  while (x > 0) { x &= x - 1; ++b; }
-  return b;
+  /* same value as the Kernighan loop of the reference for x >= 0 */
+  return __builtin_popcountll((unsigned long long)x);
 }
 
 /* parity_check[k] = the k most significant of the 2n determinant bits (osa.py:518-522) */

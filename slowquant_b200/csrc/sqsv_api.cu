@@ -417,6 +417,35 @@ extern "C" int sq_layout_num_launches(const sq_layout* lay, int first, int last)
   return n;
 }
 
+// amplitudes read+written by the launches of ops [first,last): the algorithmic traffic of sq_ups_apply is
+// 16 bytes (one fp64 read + one fp64 write) per touched amplitude per launch.
+extern "C" int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last) {
+  if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
+  std::vector<double> th(lay->ops.size(), 1.0);
+  std::vector<int> order;
+  exec_order(first, last, 0, &order);
+  std::vector<std::vector<int>> runs;
+  plan_runs(lay, order, th.data(), &runs);
+  const sq_space* sp = lay->sp;
+  int64_t total = 0;
+  for (auto& r : runs) {
+    const LayoutOp& op = lay->ops[r[0]];
+    if (is_tile_op(op)) {
+      const PairTables& pt = lay->pairs[op.pair];
+      bool has_single = false;
+      for (int k : r) has_single |= !lay->ops[k].pair_double;
+      total += has_single ? pt.touched : 2 * pt.n_src_rows * pt.n_src_cols;
+    } else if (op.gen >= 0) {
+      total += 2 * lay->gens[op.gen].n_rows * lay->gens[op.gen].n_cols_valid;
+    } else if (op.multi) {
+      static const int napp[5] = {2, 4, 4, 8, 10};
+      // each power: gather (read + write) and axpy (2 reads + write) over the whole vector
+      total += (int64_t)napp[op.type - SQ_EXC_SA_DOUBLE_1] * 3 * sp->local_len();
+    }
+  }
+  return total;
+}
+
 // closed forms of exp(theta T) for the spin-adapted doubles (operator_state_algebra.py:1086-1409):
 // out += sum_m w_m(theta) T^m out with the reference's coefficient tables.
 static int sa_double_poly(sq_space* sp, const GenOp& g, int type, double theta, double* state, cudaStream_t st) {

@@ -1,0 +1,275 @@
+"""CPU checks of the product's host side: symbolic algebra, ansatz layouts, integer tables of the C ABI
+(host-only space, device = -1) and the closed-form string action, against the reference goldens and the
+oracle.  No kernels run here."""
+import ctypes as C
+import itertools
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_opdict_close, json_to_opdict
+from oracle import sq_oracle as orc
+from slowquant_b200 import _lib
+from slowquant_b200 import operators as ops
+from slowquant_b200.fermionic_operator import FermionicOperator
+from slowquant_b200.util import UpsStructure
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(f"{ROOT}/include/sqsv.h").read()
+    declared = set(re.findall(r"\b(sq_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load()
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"libsqsv.so does not export {name}"
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.sq_version() >= 100
+
+
+def _host_space(n, na, nb):
+    lib = _lib.load()
+    h = C.c_void_p()
+    _lib.check(lib.sq_space_create(n, na, nb, -1, 0, -1, C.byref(h)))
+    return lib, h
+
+
+def test_idx2det_and_det2idx_bit_exact(golden):
+    arrays, _, _ = golden
+    for key in arrays.files:
+        if not key.startswith("idx2det_"):
+            continue
+        n, na, nb = (int(x) for x in key.split("_")[1:])
+        lib, h = _host_space(n, na, nb)
+        ref = arrays[key]
+        nd = lib.sq_space_num_det(h)
+        assert nd == len(ref)
+        out = np.empty(nd, dtype=np.int64)
+        _lib.check(lib.sq_space_export_idx2det(h, 0, nd, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        assert np.array_equal(out, ref), key
+        # det2idx inverts idx2det; determinants outside the space map to -1 (KeyError in the reference)
+        idx = np.empty(nd, dtype=np.int64)
+        _lib.check(lib.sq_space_det2idx(h, nd, ref.ctypes.data_as(C.POINTER(C.c_int64)), idx.ctypes.data_as(C.POINTER(C.c_int64))))
+        assert np.array_equal(idx, np.arange(nd))
+        bad = np.array([0, (1 << (2 * n)) - 1, -5, 1 << (2 * n)], dtype=np.int64)
+        res = np.empty(4, dtype=np.int64)
+        _lib.check(lib.sq_space_det2idx(h, 4, bad.ctypes.data_as(C.POINTER(C.c_int64)), res.ctypes.data_as(C.POINTER(C.c_int64))))
+        assert res[2] == -1 and res[3] == -1
+        if 0 < na + nb < 2 * n:
+            assert res[0] == -1 and res[1] == -1
+        lib.sq_space_destroy(h)
+
+
+def test_space_argument_errors():
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.sq_space_create(0, 0, 0, -1, 0, -1, C.byref(h)) == _lib.SQ_ERR_INVALID
+    assert lib.sq_space_create(4, 5, 1, -1, 0, -1, C.byref(h)) == _lib.SQ_ERR_INVALID
+    assert lib.sq_space_create(4, 2, 2, -1, 3, 2, C.byref(h)) == _lib.SQ_ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(lib.sq_space_create(4, 2, 2, -1, 0, 99, C.byref(h)))
+
+
+def test_fermionic_operator_algebra(golden):
+    _, _, gops = golden
+    E = ops.Epq
+    built = {
+        "Epq_2_0": E(2, 0),
+        "Epq_1_1": E(1, 1),
+        "Epq_3_1*Epq_1_2": E(3, 1) * E(1, 2),
+        "Epq_0_1*Epq_1_0": E(0, 1) * E(1, 0),
+        "epqrs_0_1_1_2": ops.epqrs(0, 1, 1, 2),
+        "epqrs_2_2_2_2": ops.epqrs(2, 2, 2, 2),
+        "G1_1_4_AH": ops.G1(1, 4, True),
+        "G2_0_3_4_7_AH": ops.G2(0, 3, 4, 7, True),
+        "G2_0_1_6_7_AH": ops.G2(0, 1, 6, 7, True),
+        "G2_2_3_4_5_H": ops.G2(2, 3, 4, 5, False),
+        "G3_0_1_2_5_6_7_AH": ops.G3(0, 1, 2, 5, 6, 7, True),
+        "G4_0_1_2_3_4_5_6_7_AH": ops.G4(0, 1, 2, 3, 4, 5, 6, 7, True),
+        "G1_sa_0_2_AH": ops.G1_sa(0, 2, True),
+        "G2_sa_0_0_2_2_c1_AH": ops.G2_sa(0, 0, 2, 2, 1, True),
+        "G2_sa_0_0_2_3_c2_AH": ops.G2_sa(0, 0, 2, 3, 2, True),
+        "G2_sa_0_1_2_2_c3_AH": ops.G2_sa(0, 1, 2, 2, 3, True),
+        "G2_sa_0_1_2_3_c4_AH": ops.G2_sa(0, 1, 2, 3, 4, True),
+        "G2_sa_0_1_2_3_c5_AH": ops.G2_sa(0, 1, 2, 3, 5, True),
+        "commutator_E01_E12": ops.commutator(E(0, 1), E(1, 2)),
+    }
+    for name, op in built.items():
+        assert_opdict_close(op.operators, json_to_opdict(gops[name]))
+
+
+def test_algebra_agrees_with_oracle_on_random_products():
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        k = int(rng.integers(2, 7))
+        label = tuple((int(rng.integers(0, 6)), bool(rng.integers(0, 2))) for _ in range(k))
+        a = FermionicOperator({(): 1.0}) * FermionicOperator({label: 1.5})
+        assert_opdict_close(a.operators, orc.normal_order(label, 1.5))
+        assert_opdict_close(a.dagger.operators, orc.op_dagger(orc.normal_order(label, 1.5)))
+
+
+def test_hamiltonian_folding(golden):
+    arrays, _, gops = golden
+    h, g = arrays["fold_h"], arrays["fold_g"]
+    H = ops.hamiltonian_0i_0a(h, g, 1, 3)
+    assert isinstance(H, FermionicOperator)
+    folded_ref = json_to_opdict(gops["H0i0a_seed7_1_3_folded"])
+    assert len(H.operators) == gops["H0i0a_seed7_1_3_unfolded_count"]["n"]
+    assert_opdict_close(H.get_folded_operator(1, 3, 1).operators, folded_ref, 1e-12)
+    # closed-form folded integrals reproduce the folded strings: E_core + h_eff E + 1/2 g e
+    e_core, h_eff, g_act = ops.fold_hamiltonian_0i_0a(h, g, 1, 3)
+    rebuilt = FermionicOperator({(): e_core})
+    for p, q in itertools.product(range(3), repeat=2):
+        rebuilt += float(h_eff[p, q]) * ops.Epq(p, q)
+    for p, q, r, s in itertools.product(range(3), repeat=4):
+        rebuilt += (0.5 * float(g_act[p, q, r, s])) * ops.epqrs(p, q, r, s)
+    assert_opdict_close(rebuilt.operators, folded_ref, 1e-12)
+
+
+def test_hamiltonian_folding_unsymmetric_integrals():
+    rng = np.random.default_rng(9)
+    h = rng.normal(size=(5, 5))
+    g = rng.normal(size=(5, 5, 5, 5))
+    H = ops.hamiltonian_0i_0a(h, g, 2, 2)
+    folded = H.get_folded_operator(2, 2, 1).operators
+    assert_opdict_close(folded, orc.op_fold(orc.hamiltonian_0i_0a(h, g, 2, 2), 2, 2, 1), 1e-12)
+    e_core, h_eff, g_act = ops.fold_hamiltonian_0i_0a(h, g, 2, 2)
+    rebuilt = FermionicOperator({(): e_core})
+    for p, q in itertools.product(range(2), repeat=2):
+        rebuilt += float(h_eff[p, q]) * ops.Epq(p, q)
+    for p, q, r, s in itertools.product(range(2), repeat=4):
+        rebuilt += (0.5 * float(g_act[p, q, r, s])) * ops.epqrs(p, q, r, s)
+    assert_opdict_close(rebuilt.operators, folded, 1e-12)
+
+
+def _layout_from_meta(m):
+    lay = UpsStructure()
+    ansatz = m["ansatz"].lower()
+    opts = dict(m["options"])
+    n = m["num_active_orbs"]
+    args = (
+        m["active_occ_idx_shifted"],
+        m["active_unocc_idx_shifted"],
+        m["active_occ_spin_idx_shifted"],
+        m["active_unocc_spin_idx_shifted"],
+        n,
+        opts,
+    )
+    if ansatz in ("tups", "qnp"):
+        lay.create_tiled(n, opts)
+    elif ansatz in ("sdsfuccsd",):
+        lay.create_SDSfUCC(*args)
+    else:
+        lay.create_fUCC(*args)
+    return lay
+
+
+@pytest.mark.parametrize("name", ["tups44", "qnp44", "fuccsd44", "sa44", "tq44", "gsd44", "ksa44", "sds44", "sad65"])
+def test_layouts_match_reference(golden, name):
+    _, meta, _ = golden
+    m = meta[name]
+    lay = _layout_from_meta(m)
+    assert lay.excitation_operator_type == m["types"]
+    assert [list(t) for t in lay.excitation_indices] == m["indices"]
+    assert lay.n_params == len(m["types"])
+    assert lay.grad_param_R == m["grad_param_R"]
+
+
+def test_synthetic_layouts_match_reference(golden):
+    _, meta, _ = golden
+    for name in ("syn_tups_5_23", "syn_tups_6_33", "syn_qnp_6_24"):
+        m = meta[name]
+        lay = UpsStructure()
+        lay.create_tiled(m["n"], dict(m["options"]))
+        assert lay.excitation_operator_type == m["types"]
+        assert [list(t) for t in lay.excitation_indices] == m["indices"]
+    for name, opts in (
+        ("syn_gsd_6_33", {"n_layers": 1, "SAGS": True, "GpD": True, "S": True}),
+        ("syn_q56_6_33", {"n_layers": 1, "Q": True, "5": True, "6": True}),
+    ):
+        m = meta[name]
+        lay = UpsStructure()
+        lay.create_fUCC([0, 1, 2], [3, 4, 5], list(range(6)), list(range(6, 12)), 6, opts)
+        assert lay.excitation_operator_type == m["types"]
+        assert [list(t) for t in lay.excitation_indices] == m["indices"]
+
+
+def test_layout_option_errors():
+    lay = UpsStructure()
+    with pytest.raises(ValueError):
+        lay.create_tiled(4, {"n_layers": 1})  # no tiled ansatz specified
+    with pytest.raises(ValueError):
+        lay.create_tiled(4, {"do_tups": True})  # n_layers missing
+    with pytest.raises(ValueError):
+        lay.create_tiled(4, {"n_layers": 1, "do_tups": True, "bogus": 1})
+    with pytest.raises(ValueError):
+        lay.create_fUCC([0], [1], [0, 1], [2, 3], 2, {"n_layers": 1})
+
+
+def _literal_action(n, label, A, B):
+    """The reference's sequential bit-flip / popcount loop (operator_state_algebra.py:112-135) on one
+    determinant given as occupation masks (bit o = orbital o)."""
+    occ = {}
+    for o in range(n):
+        occ[2 * o] = (A >> o) & 1
+        occ[2 * o + 1] = (B >> o) & 1
+    anni = [i for i, d in label if not d]
+    crea = [i for i, d in label if d]
+    screen = [i for i in crea if i not in anni]
+    if any(occ[i] == 0 for i in anni) or any(occ[i] == 1 for i in screen):
+        return False, A, B, 0
+    phase = 0
+    for k in anni + crea:
+        occ[k] ^= 1
+        phase += sum(occ[j] for j in range(k))
+    A2 = sum(occ[2 * o] << o for o in range(n))
+    B2 = sum(occ[2 * o + 1] << o for o in range(n))
+    return True, A2, B2, 1 - 2 * (phase & 1)
+
+
+def test_closed_form_string_action_equals_literal_loop():
+    n = 5
+    lib, h = _host_space(n, 2, 3)
+    rng = np.random.default_rng(1)
+    labels = [
+        ((6, True), (2, False)),
+        ((7, True), (3, False)),
+        ((4, True), (4, False)),
+        ((9, True), (8, True), (3, False), (2, False)),
+        ((8, True), (5, True), (5, False), (0, False)),
+        ((9, True), (6, True), (2, True), (7, False), (4, False), (1, False)),
+        ((3, True), (2, False)),  # spin flip: valid action, target leaves the sector
+    ]
+    for _ in range(20):
+        k = int(rng.integers(1, 4))
+        cre = sorted(rng.choice(2 * n, size=k, replace=False).tolist(), reverse=True)
+        ann = sorted(rng.choice(2 * n, size=k, replace=False).tolist(), reverse=True)
+        labels.append(tuple((int(i), True) for i in cre) + tuple((int(i), False) for i in ann))
+    valid, tA, tB, sg = C.c_int(), C.c_uint32(), C.c_uint32(), C.c_int()
+    for label in labels:
+        flat = np.array([2 * i + (1 if d else 0) for i, d in label], dtype=np.int32)
+        for A in range(1 << n):
+            for B in range(0, 1 << n, 3):
+                _lib.check(
+                    lib.sq_debug_string_action(
+                        h, flat.ctypes.data_as(C.POINTER(C.c_int32)), len(flat), A, B,
+                        C.byref(valid), C.byref(tA), C.byref(tB), C.byref(sg),
+                    )
+                )
+                ok, A2, B2, s = _literal_action(n, label, A, B)
+                assert bool(valid.value) == ok, (label, A, B)
+                if ok:
+                    assert (tA.value, tB.value, sg.value) == (A2, B2, s), (label, A, B)
+    lib.sq_space_destroy(h)
+
+
+def test_host_only_space_refuses_kernels():
+    lib, h = _host_space(4, 2, 2)
+    lay = C.c_void_p()
+    codes = np.array([0], dtype=np.int32)
+    offs = np.array([0, 2], dtype=np.int32)
+    flat = np.array([0, 1], dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    with pytest.raises(ValueError):
+        _lib.check(lib.sq_layout_create(h, 1, p(codes), p(offs), p(flat), C.byref(lay)))
+    lib.sq_space_destroy(h)
