@@ -110,10 +110,74 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
   pt->n_src_cols = nsrcB;
   // amplitudes touched by a block containing sa_single: everything except inert x inert
   pt->touched = 2 * nsrcA_local * sp->NB + ninertA_local * 2 * nsrcB;
+  // ---- class-homogeneous work lists (tile_kernel_v2) ----
+  auto bitof = [](uint32_t code, int b) -> int { return (int)((code >> b) & 1u); };
+  std::vector<int2> colItems;
+  {
+    std::vector<int2> src, inert;
+    for (int64_t I = 0; I < sp->NB; ++I) {
+      const uint32_t c = codeB[I], cls = c & 3u;
+      if (cls == SQ_CLS_SRC) {
+        const uint32_t ip = c >> 5;
+        const int flags = bitof(c, 2) | (bitof(c, 3) << 1) | (bitof(codeB[ip], 3) << 2) | (bitof(c, 4) << 3);
+        src.push_back(make_int2((int)I, (int)(ip | ((uint32_t)flags << 27))));
+      } else if (cls == SQ_CLS_INERT) {
+        const int flags = bitof(c, 3) << 1;
+        inert.push_back(make_int2((int)I, (int)((uint32_t)flags << 27)));
+      }
+    }
+    auto pad = [](std::vector<int2>& v, size_t mult) {
+      while (v.size() % mult) v.push_back(make_int2(-1, 0));
+    };
+    pad(src, 256);
+    pad(inert, 256);
+    pt->n_colblk_src = (int)(src.size() / 256);
+    pt->n_colblk_inert = (int)(inert.size() / 256);
+    colItems = src;
+    colItems.insert(colItems.end(), inert.begin(), inert.end());
+  }
+  std::vector<int4> rowItems;
+  int sig_a = 0, sig_b = 0;   // gauge-invariant pair-double sign factors; 0 = not yet seen, 2 = mixed
+  {
+    std::vector<int4> src, inert;
+    for (int32_t I : rows) {
+      const uint32_t c = codeA[I], cls = c & 3u;
+      if (cls == SQ_CLS_SRC) {
+        const uint32_t ip = c >> 5;
+        const int flags = bitof(c, 2) | (bitof(c, 3) << 1) | (bitof(codeA[ip], 3) << 2) | (bitof(c, 4) << 3);
+        src.push_back(make_int4(I, (int)ip, flags, 0));
+        // row factor of sigma = dA * sSa * crossA(partner row)
+        const int f = (bitof(c, 4) ^ bitof(c, 2) ^ bitof(codeA[ip], 3)) ? -1 : 1;
+        sig_a = (sig_a == 0) ? f : (sig_a == f ? f : 2);
+      } else {
+        inert.push_back(make_int4(I, -1, bitof(c, 3) << 1, 0));
+      }
+    }
+    const size_t TR = 8;
+    auto pad = [&](std::vector<int4>& v) {
+      while (v.size() % TR) v.push_back(make_int4(-1, -1, 0, 0));
+    };
+    pad(src);
+    pad(inert);
+    pt->n_rowchunk_src = (int)(src.size() / TR);
+    pt->n_rowchunk_inert = (int)(inert.size() / TR);
+    rowItems = src;
+    rowItems.insert(rowItems.end(), inert.begin(), inert.end());
+  }
+  for (int64_t I = 0; I < sp->NB; ++I) {
+    const uint32_t c = codeB[I];
+    if ((c & 3u) != SQ_CLS_SRC) continue;
+    // column factor of sigma = dB * crossB(this column) * sSb
+    const int f = (bitof(c, 4) ^ bitof(c, 3) ^ bitof(c, 2)) ? -1 : 1;
+    sig_b = (sig_b == 0) ? f : (sig_b == f ? f : 2);
+  }
+  pt->sigma = (sig_a == 2 || sig_b == 2) ? 0 : ((sig_a == 0 || sig_b == 0) ? 1 : sig_a * sig_b);
   SQ_CUDA(cudaSetDevice(sp->device));
   SQ_CHECK(upload(&pt->d_codeA, codeA));
   SQ_CHECK(upload(&pt->d_codeB, codeB));
   SQ_CHECK(upload(&pt->d_rowsA, rows));
+  SQ_CHECK(upload(&pt->d_colItems, colItems));
+  SQ_CHECK(upload(&pt->d_rowItems, rowItems));
   return SQ_OK;
 }
 
@@ -335,6 +399,8 @@ extern "C" int sq_layout_destroy(sq_layout* lay) {
     cudaFree(pt.d_codeA);
     cudaFree(pt.d_codeB);
     cudaFree(pt.d_rowsA);
+    cudaFree(pt.d_colItems);
+    cudaFree(pt.d_rowItems);
   }
   for (auto& gt : lay->gens) {
     cudaFree(gt.d_srcRows);

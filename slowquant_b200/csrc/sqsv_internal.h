@@ -69,6 +69,16 @@ struct PairTables {       // tables for one spatial orbital pair (i,a)
   int64_t n_rows = 0;            // local row items
   int64_t n_src_rows = 0, n_src_cols = 0;
   int64_t touched = 0;           // amplitudes a full sa_single(+double) block touches (local rows)
+  // ---- compacted, class-homogeneous work lists for tile_kernel_v2 ----
+  // column items {ib, ibp | flags<<27}: [src columns, padded to a CTA multiple][inert columns, padded];
+  // pad entries have ib = -1.  flags: bit0 same-spin sign neg, bit1 cross neg, bit2 partner cross neg,
+  // bit3 pair-double factor neg.
+  int2* d_colItems = nullptr;
+  int n_colblk_src = 0, n_colblk_inert = 0;
+  // row items {ia, iap, flags, 0}: [src rows padded to a TILE_ROWS multiple][inert rows padded]; pad ia = -1.
+  int4* d_rowItems = nullptr;
+  int n_rowchunk_src = 0, n_rowchunk_inert = 0;
+  int sigma = 0;                 // gauge-invariant pair-double sign (+1/-1) if uniform, 0 otherwise
 };
 
 struct GenTables {        // tables for one generic excitation generator G (single string)

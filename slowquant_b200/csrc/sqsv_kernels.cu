@@ -3,6 +3,7 @@
 // along the beta-string (column) axis; sign / partner tables are 4-byte-per-string codes that stay in
 // L1/L2.  No tensor-core shapes exist on this path (it is integer address work + 2x2 rotations).
 #include <cstdio>
+#include <cstdlib>
 
 #include "sqsv_internal.h"
 
@@ -103,6 +104,140 @@ tile_kernel(double* __restrict__ C, const uint32_t* __restrict__ codeA, const ui
         row0[ibp] = x01;
         row1[ib] = x10;
         row1[ibp] = x11;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_kernel_v2: same tiles, restructured for the memory roofline.
+//   * the whole fused program is pre-multiplied on the host into ONE 4x4 matrix (src x src tiles) and two
+//     2x2 rotations (src x inert, inert x src).  Per-determinant signs are removed by a diagonal +-1 gauge
+//     (x10 -> sgA0 x10, x01 -> sgB0 x01, x11 -> sgA0 sgB1 x11), which turns every alpha/beta rotation sign
+//     into +1 and leaves one gauge-invariant sign sigma on the pair double; sigma is uniform over the space
+//     (checked on the host), so the matrix is a kernel constant.  16 DFMA per 4 amplitudes instead of a
+//     branchy step loop.
+//   * columns and rows come as compacted, class-homogeneous work lists: every CTA is src-or-inert uniform,
+//     no lane idles on a "tgt" string and inert x inert CTAs exit at once.
+//   * all loads of a CTA's row batch are issued before the first store (ROWS_PER_ITER x 4 independent
+//     8-byte loads per thread in flight).
+// ---------------------------------------------------------------------------------------------
+struct TileMatrices {
+  double m[16];        // 4x4, row-major, basis (x00, x01, x10, x11), gauge-fixed
+  double ca, sa;       // total alpha-single rotation (src row x inert column)
+  double cb, sb;       // total beta-single rotation (inert row x src column)
+};
+
+__device__ __forceinline__ double flip(double x, int neg) {
+  // multiply by +-1 through the sign bit
+  return __hiloint2double(__double2hiint(x) ^ (neg << 31), __double2loint(x));
+}
+
+#define V2_ROWS_PER_ITER 4
+
+__global__ void __launch_bounds__(TILE_THREADS)
+tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_colblk_src,
+               const int4* __restrict__ rowItems, int n_rowchunk_src, int64_t NB, int64_t row_begin,
+               const TileMatrices tm) {
+  const bool col_src = (int)blockIdx.x < n_colblk_src;
+  const bool row_src = (int)blockIdx.y < n_rowchunk_src;
+  if (!col_src && !row_src) return;
+  const int2 ci = __ldg(colItems + (int64_t)blockIdx.x * TILE_THREADS + threadIdx.x);
+  if (ci.x < 0) return;
+  const int64_t ib = ci.x;
+  const int64_t ibp = ci.y & 0x07ffffff;
+  const int cf = (int)((uint32_t)ci.y >> 27);
+  const int sSb = cf & 1, crb = (cf >> 1) & 1;
+  const int4* rit = rowItems + (int64_t)blockIdx.y * TILE_ROWS;
+
+  if (row_src && col_src) {
+#pragma unroll 1
+    for (int it = 0; it < TILE_ROWS / V2_ROWS_PER_ITER; ++it) {
+      int4 ri[V2_ROWS_PER_ITER];
+      double x00[V2_ROWS_PER_ITER], x01[V2_ROWS_PER_ITER], x10[V2_ROWS_PER_ITER], x11[V2_ROWS_PER_ITER];
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
+        if (ri[j].x >= 0) {
+          const double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
+          const double* r1 = C + ((int64_t)ri[j].y - row_begin) * NB;
+          x00[j] = r0[ib];
+          x01[j] = r0[ibp];
+          x10[j] = r1[ib];
+          x11[j] = r1[ibp];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
+        if (ri[j].x >= 0) {
+          const int rf = ri[j].z;
+          const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
+          const int g10 = sSa ^ crb;            // sgA0
+          const int g01 = sSb ^ cra;            // sgB0
+          const int g11 = g10 ^ sSb ^ crap;     // sgA0 * sgB1
+          const double y0 = x00[j], y1 = flip(x01[j], g01), y2 = flip(x10[j], g10), y3 = flip(x11[j], g11);
+          const double z0 = tm.m[0] * y0 + tm.m[1] * y1 + tm.m[2] * y2 + tm.m[3] * y3;
+          const double z1 = tm.m[4] * y0 + tm.m[5] * y1 + tm.m[6] * y2 + tm.m[7] * y3;
+          const double z2 = tm.m[8] * y0 + tm.m[9] * y1 + tm.m[10] * y2 + tm.m[11] * y3;
+          const double z3 = tm.m[12] * y0 + tm.m[13] * y1 + tm.m[14] * y2 + tm.m[15] * y3;
+          double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
+          double* r1 = C + ((int64_t)ri[j].y - row_begin) * NB;
+          r0[ib] = z0;
+          r0[ibp] = flip(z1, g01);
+          r1[ib] = flip(z2, g10);
+          r1[ibp] = flip(z3, g11);
+        }
+      }
+    }
+  } else if (row_src) {   // src row pair x inert column: alpha rotation only
+#pragma unroll 1
+    for (int it = 0; it < TILE_ROWS / V2_ROWS_PER_ITER; ++it) {
+      int4 ri[V2_ROWS_PER_ITER];
+      double x0[V2_ROWS_PER_ITER], x1[V2_ROWS_PER_ITER];
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
+        if (ri[j].x >= 0) {
+          x0[j] = C[((int64_t)ri[j].x - row_begin) * NB + ib];
+          x1[j] = C[((int64_t)ri[j].y - row_begin) * NB + ib];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
+        if (ri[j].x >= 0) {
+          const int g = (ri[j].z & 1) ^ crb;   // sSa * crossB(column)
+          const double a = x0[j], b = flip(x1[j], g);
+          C[((int64_t)ri[j].x - row_begin) * NB + ib] = tm.ca * a - tm.sa * b;
+          C[((int64_t)ri[j].y - row_begin) * NB + ib] = flip(tm.ca * b + tm.sa * a, g);
+        }
+      }
+    }
+  } else {                // inert row x src column pair: beta rotation only
+#pragma unroll 1
+    for (int it = 0; it < TILE_ROWS / V2_ROWS_PER_ITER; ++it) {
+      int4 ri[V2_ROWS_PER_ITER];
+      double x0[V2_ROWS_PER_ITER], x1[V2_ROWS_PER_ITER];
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
+        if (ri[j].x >= 0) {
+          const double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
+          x0[j] = r0[ib];
+          x1[j] = r0[ibp];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
+        if (ri[j].x >= 0) {
+          const int g = sSb ^ ((ri[j].z >> 1) & 1);   // sSb * crossA(row)
+          const double a = x0[j], b = flip(x1[j], g);
+          double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
+          r0[ib] = tm.cb * a - tm.sb * b;
+          r0[ibp] = flip(tm.cb * b + tm.sb * a, g);
+        }
       }
     }
   }
@@ -418,9 +553,71 @@ static int fill_program(const TileStep* steps, int n_steps, TileProgram* p) {
   return SQ_OK;
 }
 
+// host: multiply the step rotations into the gauge-fixed 4x4 matrix and the two total 2x2 rotations
+static void build_tile_matrices(const TileStep* steps, int n_steps, int sigma, TileMatrices* tm) {
+  double M[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  auto apply = [&](int u, int v, double c, double s) {   // rows u (src) and v (tgt) of M <- rotation * M
+    for (int k = 0; k < 4; ++k) {
+      const double a = M[u][k], b = M[v][k];
+      M[u][k] = c * a - s * b;
+      M[v][k] = c * b + s * a;
+    }
+  };
+  double tha_c = 1, tha_s = 0, thb_c = 1, thb_s = 0;
+  auto compose = [](double& C0, double& S0, double c, double s) {   // angle addition
+    const double nc = C0 * c - S0 * s, ns = S0 * c + C0 * s;
+    C0 = nc;
+    S0 = ns;
+  };
+  for (int k = 0; k < n_steps; ++k) {
+    const double c = steps[k].c, s = steps[k].s;
+    if (steps[k].kind == 0) {
+      apply(0, 2, c, s);
+      apply(1, 3, c, s);
+      compose(tha_c, tha_s, c, s);
+    } else if (steps[k].kind == 1) {
+      apply(0, 1, c, s);
+      apply(2, 3, c, s);
+      compose(thb_c, thb_s, c, s);
+    } else {
+      apply(0, 3, c, sigma * s);
+    }
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int k = 0; k < 4; ++k) tm->m[4 * r + k] = M[r][k];
+  tm->ca = tha_c;
+  tm->sa = tha_s;
+  tm->cb = thb_c;
+  tm->sb = thb_s;
+}
+
+static int g_tile_variant = -1;   // SQ_TILE_KERNEL=1 forces the step-loop kernel (debug / A-B comparison)
+
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps, double* state,
                    cudaStream_t st) {
   if (pt.n_rows == 0) return SQ_OK;
+  if (g_tile_variant < 0) {
+    const char* e = getenv("SQ_TILE_KERNEL");
+    g_tile_variant = (e && e[0] == '1') ? 1 : 2;
+  }
+  if (g_tile_variant == 2 && pt.sigma != 0) {
+    if (n_steps < 1 || n_steps > SQ_MAX_PROGRAM) {
+      sq_set_error("tile program with %d steps (max %d)", n_steps, SQ_MAX_PROGRAM);
+      return SQ_ERR_INVALID;
+    }
+    TileMatrices tm;
+    build_tile_matrices(steps, n_steps, pt.sigma, &tm);
+    bool any_single = false;
+    for (int k = 0; k < n_steps; ++k) any_single |= steps[k].kind != 2;
+    // a pair-double-only program touches src x src tiles only
+    const int gx = any_single ? pt.n_colblk_src + pt.n_colblk_inert : pt.n_colblk_src;
+    const int gy = any_single ? pt.n_rowchunk_src + pt.n_rowchunk_inert : pt.n_rowchunk_src;
+    if (gx == 0 || gy == 0) return SQ_OK;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    tile_kernel_v2<<<grid, TILE_THREADS, 0, st>>>(state, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
+                                                 pt.n_rowchunk_src, sp->NB, sp->row_begin, tm);
+    return check_launch("tile_kernel_v2");
+  }
   TileProgram prog;
   SQ_CHECK(fill_program(steps, n_steps, &prog));
   dim3 grid((unsigned)((sp->NB + TILE_THREADS - 1) / TILE_THREADS), (unsigned)((pt.n_rows + TILE_ROWS - 1) / TILE_ROWS));
