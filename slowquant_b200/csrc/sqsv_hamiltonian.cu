@@ -1,13 +1,334 @@
-// sigma-build and reduced density matrices (placeholder; filled in below)
+// sigma-build H|c> and 1-/2-RDMs from the folded integrals, without ever materialising the
+// 2n^2 + 2C(n,2)^2 + n^4 operator strings the reference loops over (operators.py:476-529 applied by
+// operator_state_algebra.py:596-628; ups_wavefunction.py:409-476 for the RDMs).
+//
+// Both are built on panels of the single-replacement matrix
+//     D[rs][J] = <J| E_rs |c>,   E_rs = a+_{r,alpha} a_{s,alpha} + a+_{r,beta} a_{s,beta}
+// (Knowles-Handy resolution): for a panel of W determinants D is an n^2 x W dense fp64 matrix, so
+//     <bra|E_pq E_rs|ket> = sum_J D^bra[qp][J] D^ket[rs][J]            (fp64 tensor-core GEMM, cuBLAS DGEMM)
+//     sigma[I] = e_core c[I] + sum_pq sum_J <I|E_pq|J> ( k_pq c[J] + 1/2 sum_rs g_pqrs D[rs][J] )
+// with k_pq = h_pq - 1/2 sum_r g_prrq.  These dense contractions are the only place this engine uses
+// tensor cores (DMMA through the library GEMM); the gather that builds D and the scatter that applies
+// E_pq are HBM/L2-bound integer-address kernels.
+#include <cublas_v2.h>
+
+#include <cmath>
+#include <cstring>
+
 #include "sqsv_internal.h"
+
+struct ERec {                 // one spin component of E_pq acting on a determinant
+  uint32_t tocc, temp;        // target screen: p occupied, q empty unless p == q      (gather form)
+  uint32_t occ, emp;          // source screen: q occupied, p empty unless p == q      (scatter form)
+  uint32_t flip;              // bits p and q of the same-spin string (0 when p == q)
+  uint32_t parS, parO;        // parity masks on the same-spin / other-spin SOURCE strings
+  int32_t s0;                 // +-1
+};
+
+struct HamWork {
+  cublasHandle_t blas = nullptr;
+  ERec* d_etab = nullptr;     // [n*n][2]  (alpha, beta)
+  double* d_D[2] = {nullptr, nullptr};
+  double* d_F = nullptr;
+  int64_t W = 0;
+  double* d_small = nullptr;  // n^4 + 2 n^2 doubles: G2 accumulator / integral matrices
+};
+
+static std::map<const sq_space*, HamWork*> g_work;
+
+static void free_work(HamWork* w) {
+  if (!w) return;
+  if (w->blas) cublasDestroy(w->blas);
+  cudaFree(w->d_etab);
+  cudaFree(w->d_D[0]);
+  cudaFree(w->d_D[1]);
+  cudaFree(w->d_F);
+  cudaFree(w->d_small);
+  delete w;
+}
+
+void sq_hamiltonian_release(const sq_space* sp) {
+  auto it = g_work.find(sp);
+  if (it != g_work.end()) {
+    free_work(it->second);
+    g_work.erase(it);
+  }
+}
+
+static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out) {
+  HamWork* w = nullptr;
+  auto it = g_work.find(sp);
+  if (it != g_work.end()) {
+    w = it->second;
+  } else {
+    w = new HamWork();
+    g_work[sp] = w;
+  }
+  const int n = sp->n_orb, n2 = n * n;
+  if (!w->blas) {
+    if (cublasCreate(&w->blas) != CUBLAS_STATUS_SUCCESS) {
+      sq_set_error("cublasCreate failed");
+      return SQ_ERR_CUDA;
+    }
+  }
+  if (!w->d_etab) {
+    std::vector<ERec> tab(2 * (size_t)n2);
+    for (int p = 0; p < n; ++p)
+      for (int q = 0; q < n; ++q)
+        for (int spin = 0; spin < 2; ++spin) {
+          int32_t label[2] = {2 * (2 * p + spin) + 1, 2 * (2 * q + spin)};
+          StringAction a;
+          SQ_CHECK(sq_make_string_action(sp, label, 2, &a));
+          ERec r;
+          if (spin == 0)
+            r = {a.toccA, a.tempA, a.occA, a.empA, a.flipA, a.parA, a.parB, a.s0};
+          else
+            r = {a.toccB, a.tempB, a.occB, a.empB, a.flipB, a.parB, a.parA, a.s0};
+          tab[2 * ((size_t)p * n + q) + spin] = r;
+        }
+    SQ_CUDA(cudaMalloc(&w->d_etab, sizeof(ERec) * tab.size()));
+    SQ_CUDA(cudaMemcpy(w->d_etab, tab.data(), sizeof(ERec) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  if (!w->W) {
+    // panel width: about 1 GiB per n^2 x W matrix, multiple of 256 determinants
+    int64_t Wmax = ((int64_t)1 << 27) / n2;
+    Wmax = (Wmax / 256) * 256;
+    if (Wmax < 256) Wmax = 256;
+    int64_t len = sp->local_len();
+    w->W = len < Wmax ? ((len + 255) / 256) * 256 : Wmax;
+    if (w->W < 256) w->W = 256;
+  }
+  const size_t pbytes = sizeof(double) * (size_t)n2 * (size_t)w->W;
+  if (!w->d_D[0]) SQ_CUDA(cudaMalloc(&w->d_D[0], pbytes));
+  if (need_second_D && !w->d_D[1]) SQ_CUDA(cudaMalloc(&w->d_D[1], pbytes));
+  if (need_F && !w->d_F) SQ_CUDA(cudaMalloc(&w->d_F, pbytes));
+  if (!w->d_small) SQ_CUDA(cudaMalloc(&w->d_small, sizeof(double) * ((size_t)n2 * n2 + 2 * (size_t)n2)));
+  *out = w;
+  return SQ_OK;
+}
+
+// D[slot][t] = <J_t| E_rs |in>, slot = r*n + s, J_t = determinant j0 + t of the local vector (gather form)
+__global__ void __launch_bounds__(256)
+build_D_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
+               const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA,
+               const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+               const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  extern __shared__ ERec sm[];
+  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256)
+    reinterpret_cast<uint32_t*>(sm)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  if (j >= len) {
+    for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  for (int slot = 0; slot < n2; ++slot) {
+    double v = 0.0;
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      const double x = IN[((int64_t)__ldg(rankA + sa) - row_begin) * NB + ib];
+      v += (par ? -ra.s0 : ra.s0) * x;
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      const double x = IN[ia_loc * NB + __ldg(rankB + sb)];
+      v += (par ? -rb.s0 : rb.s0) * x;
+    }
+    D[(int64_t)slot * W + t] = v;
+  }
+}
+
+// OUT[E_pq J] += sign * ( F[pq][t] + k[pq] * IN[J] )   for every determinant J of the panel (scatter form)
+__global__ void __launch_bounds__(256)
+scatter_E_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                 const double* __restrict__ kmat, int64_t W, int64_t j0, int64_t len,
+                 const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA,
+                 const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                 const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  extern __shared__ ERec sm[];
+  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256)
+    reinterpret_cast<uint32_t*>(sm)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j = j0 + t;
+  if (t >= W || j >= len) return;
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  const double cj = IN[j];
+  double diag = 0.0;
+  for (int slot = 0; slot < n2; ++slot) {
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    const bool va = (a & ra.occ) == ra.occ && (a & ra.emp) == 0u;
+    const bool vb = (b & rb.occ) == rb.occ && (b & rb.emp) == 0u;
+    if (!va && !vb) continue;
+    const double val = F[(int64_t)slot * W + t] + __ldg(kmat + slot) * cj;
+    if (va) {
+      const int par = (__popc(a & ra.parS) + __popc(b & ra.parO)) & 1;
+      const double sv = (par ? -ra.s0 : ra.s0) * val;
+      if (ra.flip == 0u) diag += sv;
+      else atomicAdd(OUT + ((int64_t)__ldg(rankA + (a ^ ra.flip)) - row_begin) * NB + ib, sv);
+    }
+    if (vb) {
+      const int par = (__popc(b & rb.parS) + __popc(a & rb.parO)) & 1;
+      const double sv = (par ? -rb.s0 : rb.s0) * val;
+      if (rb.flip == 0u) diag += sv;
+      else atomicAdd(OUT + ia_loc * NB + __ldg(rankB + (b ^ rb.flip)), sv);
+    }
+  }
+  atomicAdd(OUT + j, diag);
+}
+
+static int check_full_space(sq_space* sp, const char* who) {
+  if (sp->device < 0) {
+    sq_set_error("%s: host-only space (device = -1) cannot run kernels", who);
+    return SQ_ERR_INVALID;
+  }
+  if (sp->row_begin != 0 || sp->row_end != sp->NA) {
+    sq_set_error("%s: not available on an alpha-sharded vector yet", who);
+    return SQ_ERR_UNSUPPORTED;
+  }
+  return SQ_OK;
+}
+
+static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D, int64_t j0, cudaStream_t st) {
+  const int n2 = sp->n_orb * sp->n_orb;
+  const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(build_D_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  build_D_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA,
+                                                            sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("build_D_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
 
 extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, const double* g_act_host,
                         const double* in_dev, double* out_dev, void* stream) {
-  sq_set_error("sq_sigma: not built yet");
-  return SQ_ERR_UNSUPPORTED;
+  if (!sp || !h_act_host || !g_act_host || !in_dev || !out_dev) return SQ_ERR_INVALID;
+  if (in_dev == out_dev) {
+    sq_set_error("sq_sigma: in and out must not alias");
+    return SQ_ERR_INVALID;
+  }
+  SQ_CHECK(check_full_space(sp, "sq_sigma"));
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  HamWork* w = nullptr;
+  SQ_CHECK(get_work(sp, false, true, &w));
+  const int n = sp->n_orb, n2 = n * n;
+  // Gm[pq][rs] = 1/2 g_pqrs ; k_pq = h_pq - 1/2 sum_r g_prrq   (from e_pqrs = E_pq E_rs - delta_qr E_ps)
+  std::vector<double> Gm((size_t)n2 * n2), k((size_t)n2);
+  for (size_t i = 0; i < Gm.size(); ++i) Gm[i] = 0.5 * g_act_host[i];
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q) {
+      double v = h_act_host[p * n + q];
+      for (int r = 0; r < n; ++r) v -= 0.5 * g_act_host[(((size_t)p * n + r) * n + r) * n + q];
+      k[(size_t)p * n + q] = v;
+    }
+  double* d_G = w->d_small;
+  double* d_k = w->d_small + (size_t)n2 * n2;
+  SQ_CUDA(cudaMemcpyAsync(d_G, Gm.data(), sizeof(double) * Gm.size(), cudaMemcpyHostToDevice, st));
+  SQ_CUDA(cudaMemcpyAsync(d_k, k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice, st));
+  SQ_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
+  SQ_CHECK(sq_launch_scale_copy(sp, e_core, in_dev, out_dev, st));
+  cublasSetStream(w->blas, st);
+  const int64_t len = sp->local_len();
+  const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(scatter_E_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const double one = 1.0, zero = 0.0;
+  for (int64_t j0 = 0; j0 < len; j0 += w->W) {
+    SQ_CHECK(launch_build_D(sp, w, in_dev, w->d_D[0], j0, st));
+    // F (W x n2, column major, ld W) = D (W x n2) * X (n2 x n2) with X[rs][pq] = Gm[pq][rs] (Gm row-major)
+    cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, n2, n2, &one, w->d_D[0], (int)w->W,
+                                    d_G, n2, &zero, w->d_F, (int)w->W);
+    if (bs != CUBLAS_STATUS_SUCCESS) {
+      sq_set_error("sq_sigma: cublasDgemm failed (%d)", (int)bs);
+      return SQ_ERR_CUDA;
+    }
+    g_sq_launches.fetch_add(1);
+    scatter_E_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(in_dev, out_dev, w->d_F, d_k, w->W, j0, len, w->d_etab, n2,
+                                                                sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB,
+                                                                sp->row_begin);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      sq_set_error("scatter_E_kernel launch failed: %s", cudaGetErrorString(e));
+      return SQ_ERR_CUDA;
+    }
+    g_sq_launches.fetch_add(1);
+  }
+  return SQ_OK;
 }
+
 extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_dev, double* rdm1_host,
                         double* rdm2_host, void* stream) {
-  sq_set_error("sq_rdm12: not built yet");
-  return SQ_ERR_UNSUPPORTED;
+  if (!sp || !bra_dev || !ket_dev || !rdm1_host) return SQ_ERR_INVALID;
+  SQ_CHECK(check_full_space(sp, "sq_rdm12"));
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  const bool same = (bra_dev == ket_dev);
+  HamWork* w = nullptr;
+  SQ_CHECK(get_work(sp, !same && rdm2_host, false, &w));
+  const int n = sp->n_orb, n2 = n * n;
+  double* d_G2 = w->d_small;                       // [n2][n2] row-major [(q,p)][(r,s)]
+  double* d_g1 = w->d_small + (size_t)n2 * n2;     // [n2]
+  SQ_CUDA(cudaMemsetAsync(w->d_small, 0, sizeof(double) * ((size_t)n2 * n2 + 2 * (size_t)n2), st));
+  cublasSetStream(w->blas, st);
+  const int64_t len = sp->local_len();
+  const double one = 1.0;
+  for (int64_t j0 = 0; j0 < len; j0 += w->W) {
+    const int64_t wl = (len - j0 < w->W) ? len - j0 : w->W;
+    SQ_CHECK(launch_build_D(sp, w, ket_dev, w->d_D[0], j0, st));
+    // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]
+    cublasStatus_t bs = cublasDgemv(w->blas, CUBLAS_OP_T, (int)wl, n2, &one, w->d_D[0], (int)w->W, bra_dev + j0, 1, &one,
+                                    d_g1, 1);
+    if (bs != CUBLAS_STATUS_SUCCESS) {
+      sq_set_error("sq_rdm12: cublasDgemv failed (%d)", (int)bs);
+      return SQ_ERR_CUDA;
+    }
+    g_sq_launches.fetch_add(1);
+    if (rdm2_host) {
+      const double* Dbra = w->d_D[0];
+      if (!same) {
+        SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[1], j0, st));
+        Dbra = w->d_D[1];
+      }
+      // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]  ==  column-major C[b][a] = Dket^T Dbra
+      bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, n2, n2, (int)w->W, &one, w->d_D[0], (int)w->W, Dbra, (int)w->W,
+                       &one, d_G2, n2);
+      if (bs != CUBLAS_STATUS_SUCCESS) {
+        sq_set_error("sq_rdm12: cublasDgemm failed (%d)", (int)bs);
+        return SQ_ERR_CUDA;
+      }
+      g_sq_launches.fetch_add(1);
+    }
+  }
+  std::vector<double> G2h(rdm2_host ? (size_t)n2 * n2 : 0), g1h((size_t)n2);
+  SQ_CUDA(cudaMemcpyAsync(g1h.data(), d_g1, sizeof(double) * n2, cudaMemcpyDeviceToHost, st));
+  if (rdm2_host)
+    SQ_CUDA(cudaMemcpyAsync(G2h.data(), d_G2, sizeof(double) * (size_t)n2 * n2, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n2; ++i) rdm1_host[i] = g1h[i];
+  if (rdm2_host) {
+    // rdm2[p][q][r][s] = <bra|E_pq E_rs|ket> - delta_qr rdm1[p][s];  <..> = G2[(q,p)][(r,s)]
+    for (int p = 0; p < n; ++p)
+      for (int q = 0; q < n; ++q)
+        for (int r = 0; r < n; ++r)
+          for (int s = 0; s < n; ++s) {
+            double v = G2h[((size_t)(q * n + p)) * n2 + (r * n + s)];
+            if (q == r) v -= g1h[p * n + s];
+            rdm2_host[(((size_t)p * n + q) * n + r) * n + s] = v;
+          }
+  }
+  return SQ_OK;
 }

@@ -129,6 +129,7 @@ extern "C" int sq_space_destroy(sq_space* sp) {
     return SQ_OK;
   }
   cudaSetDevice(sp->device);
+  sq_hamiltonian_release(sp);
   cudaFree(sp->d_strA);
   cudaFree(sp->d_strB);
   cudaFree(sp->d_rankA);

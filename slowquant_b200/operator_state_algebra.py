@@ -344,6 +344,31 @@ def ups_gradient_sweep(
     return g, _from_device(b, b_np), _from_device(k, k_np)
 
 
+def reduced_density_matrices(bra, ket, ci_info: CI_Info, want_rdm2: bool = True):
+    r"""Active-space (transition) RDMs in one pass over the vector (replaces the n^4/4 expectation_value
+    calls of ups_wavefunction.py:409-476):
+
+        rdm1[p,q] = <bra|E_pq|ket>,   rdm2[p,q,r,s] = <bra|E_pq E_rs|ket> - delta_qr rdm1[p,s].
+
+    Returns (rdm1, rdm2 or None) as numpy arrays.
+    """
+    lib = _lib.load()
+    n = ci_info.num_active_orbs
+    k, _ = _to_device(ket, ci_info, copy=False)
+    if bra is ket:
+        b = k
+    else:
+        b, _ = _to_device(bra, ci_info, copy=False)
+    d1 = np.zeros((n, n), dtype=np.float64)
+    d2 = np.zeros((n, n, n, n), dtype=np.float64) if want_rdm2 else None
+    _lib.check(
+        lib.sq_rdm12(
+            ci_info._handle, _ptr(b), _ptr(k), d1.ctypes.data_as(_PD), d2.ctypes.data_as(_PD) if want_rdm2 else None, _stream()
+        )
+    )
+    return d1, d2
+
+
 # ---- state-averaged twins: batches [n_states, N_det] (osa.py:633-781, 827-867, 1415-1864, 2312-2976) ----
 def _map_states(fn, states):
     if isinstance(states, torch.Tensor):

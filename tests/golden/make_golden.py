@@ -294,6 +294,31 @@ def golden_synthetic_ups(out: dict, meta: dict) -> None:
     print("syn_q56 P =", lay.n_params, flush=True)
 
 
+def golden_ucc(out: dict, meta: dict) -> None:
+    """Non-factorised UCC state: expm_multiply of the dense T matrix (operator_state_algebra.py:870-896)."""
+    from slowquant.unitary_coupled_cluster.operator_state_algebra import construct_ucc_state
+    from slowquant.unitary_coupled_cluster.util import UccStructure
+
+    ci = get_indexing(0, 4, 0, 2, 2)
+    st = UccStructure()
+    st.add_sa_singles([0, 1], [2, 3])
+    st.add_sa_doubles([0, 1], [2, 3])
+    st.add_triples([0, 1, 2, 3], [4, 5, 6, 7])
+    st.add_quadruples([0, 1, 2, 3], [4, 5, 6, 7])
+    rng = np.random.default_rng(4242)
+    thetas = rng.uniform(-0.8, 0.8, st.n_params).tolist()
+    hf = np.zeros(len(ci.idx2det))
+    hf[0] = 1.0
+    out["ucc44_thetas"] = np.array(thetas)
+    out["ucc44_result"] = construct_ucc_state(hf, ci, thetas, st)
+    out["ucc44_result_dagger"] = construct_ucc_state(out["ucc44_result"], ci, thetas, st, dagger=True)
+    meta["ucc44"] = {
+        "types": list(st.excitation_operator_type),
+        "indices": [[int(x) for x in t] for t in st.excitation_indices],
+    }
+    print("ucc44 P =", st.n_params, flush=True)
+
+
 def main() -> None:
     arrays: dict = {}
     meta: dict = {}
@@ -302,6 +327,7 @@ def main() -> None:
     golden_propagate(arrays, meta)
     golden_synthetic_ups(arrays, meta)
     golden_wavefunctions(arrays, meta)
+    golden_ucc(arrays, meta)
     np.savez_compressed(os.path.join(HERE, "golden.npz"), **arrays)
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
         json.dump({"meta": meta, "operators": ops}, f, indent=0)

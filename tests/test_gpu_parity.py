@@ -271,3 +271,168 @@ def test_size_independent_properties(sq, n, ne):
     part = _layout(sq, lay.excitation_operator_type[:6], lay.excitation_indices[:6])
     w2 = sq.osa.construct_ups_state(x, info, th[:6], part)
     assert float(torch.max(torch.abs(w - w2))) < 1e-13
+
+
+def test_rdms_against_reference(sq, golden):
+    arrays, meta, _ = golden
+    from slowquant_b200.density_matrix import get_electronic_energy, get_orbital_gradient
+    from slowquant_b200.ups_wavefunction import symmetrize_rdm2_like_reference
+
+    for name in ("tups44", "fuccsd44"):
+        m = meta[name]
+        nI, nA, nV = m["num_inactive_orbs"], m["num_active_orbs"], m["num_virtual_orbs"]
+        info = sq.ci.get_indexing(nI, nA, nV, m["n_alpha"], m["n_beta"])
+        ci = arrays[f"{name}_ci"]
+        d1, d2 = sq.osa.reduced_density_matrices(ci, ci, info)
+        assert np.max(np.abs(d1 - arrays[f"{name}_rdm1"])) < 1e-12
+        assert np.max(np.abs(d2 - arrays[f"{name}_rdm2"])) < 1e-12
+        assert np.max(np.abs(symmetrize_rdm2_like_reference(d2) - arrays[f"{name}_rdm2"])) < 1e-12
+        assert abs(np.trace(d1) - (m["n_alpha"] + m["n_beta"])) < 1e-12
+        e = get_electronic_energy(arrays["h2o_h_mo"], arrays["h2o_g_mo"], nI, nA, d1, d2)
+        assert abs(e - float(arrays[f"{name}_energy_rdm"])) < 1e-10
+        assert abs(e - float(arrays[f"{name}_energy"])) < 1e-10
+    og = get_orbital_gradient(
+        arrays["h2o_h_mo"], arrays["h2o_g_mo"], arrays["tups44_kappa_idx"], 3, 4, arrays["tups44_rdm1"], arrays["tups44_rdm2"]
+    )
+    assert np.max(np.abs(og - arrays["tups44_orbital_gradient"])) < 1e-11
+
+
+def test_transition_rdm_against_oracle(sq):
+    n, na, nb = 5, 2, 3
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    info = sq.ci.get_indexing(0, n, 0, na, nb)
+    rng = np.random.default_rng(23)
+    bra = rng.normal(size=sp.num_det)
+    ket = rng.normal(size=sp.num_det)
+    d1, d2 = sq.osa.reduced_density_matrices(bra, ket, info)
+    for p, q in [(0, 0), (1, 3), (4, 2), (2, 4)]:
+        ref = orc.expectation_value(bra, [orc.Epq(p, q)], ket, sp)
+        assert abs(d1[p, q] - ref) < 1e-12
+    for p, q, r, s in [(0, 1, 1, 0), (3, 1, 2, 4), (4, 4, 2, 2), (1, 2, 2, 3), (0, 3, 4, 1)]:
+        ref = orc.expectation_value(bra, [orc.op_mul(orc.Epq(p, q), orc.Epq(r, s))], ket, sp)
+        if q == r:
+            ref -= orc.expectation_value(bra, [orc.Epq(p, s)], ket, sp)
+        assert abs(d2[p, q, r, s] - ref) < 1e-12, (p, q, r, s)
+
+
+@pytest.mark.parametrize("n,na,nb", [(6, 3, 3), (7, 4, 2), (8, 4, 4)])
+def test_sigma_against_oracle(sq, n, na, nb):
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    if n == 7:  # no permutational symmetry at all: the kernel must not assume any
+        h = rng.normal(size=(n, n))
+        g = 0.1 * rng.normal(size=(n, n, n, n))
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    info = sq.ci.get_indexing(0, n, 0, na, nb)
+    st = rng.normal(size=sp.num_det)
+    st /= np.linalg.norm(st)
+    H = hamiltonian_0i_0a(h, g, 0, n)
+    sig = sq.osa.propagate_state([H], st, info)
+    ref = orc.propagate_state([orc.hamiltonian_0i_0a(h, g, 0, n)], st, sp, threaded=True)
+    assert np.max(np.abs(sig - ref)) < 1e-11
+    e = sq.osa.expectation_value(st, [H], st, info)
+    assert abs(e - float(st @ ref)) < 1e-11
+    if n != 7:
+        d1, d2 = sq.osa.reduced_density_matrices(st, st, info)
+        e_rdm = float(np.sum(h * d1) + 0.5 * np.sum(g * d2))
+        assert abs(e - e_rdm) < 1e-10
+
+
+def test_wavefunction_object(sq, golden):
+    """WaveFunctionUPS surface on the H2O/STO-3G CAS(4,4) integrals exported from the reference run."""
+    arrays, meta, _ = golden
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    ints = ArrayIntegrals(arrays["h2o_h_mo"], arrays["h2o_g_mo"], num_elec=10)
+    eye = np.eye(arrays["h2o_h_mo"].shape[0])
+    WF = WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 2}, include_active_kappa=True)
+    m = meta["tups44"]
+    assert WF.ups_layout.excitation_operator_type == m["types"]
+    assert np.array_equal(WF.kappa_idx, arrays["tups44_kappa_idx"])
+    assert np.array_equal(WF.csf_coeffs, arrays["tups44_csf"])
+    th = arrays["tups44_thetas"].tolist()
+    WF.thetas = th
+    assert WF.thetas == th
+    assert np.max(np.abs(WF.ci_coeffs - arrays["tups44_ci"])) < TOL
+    assert abs(WF.energy_elec - float(arrays["tups44_energy"])) < 1e-10
+    assert np.max(np.abs(WF.rdm1 - arrays["tups44_rdm1"])) < 1e-12
+    assert np.max(np.abs(WF.rdm2 - arrays["tups44_rdm2"])) < 1e-12
+    params = WF.kappa + th
+    grad = WF._calc_gradient_optimization(params, True, True)
+    assert np.max(np.abs(grad - arrays["tups44_gradient"])) < 1e-10
+    e_opt = WF._calc_energy_optimization(params, True, True)
+    assert abs(e_opt - float(arrays["tups44_energy_rdm"])) < 1e-10
+    with pytest.raises(ValueError):
+        WF.thetas = th[:-1]
+    with pytest.raises(ValueError):
+        WaveFunctionUPS((4, 4), eye, ints, "nonsense")
+    # gradient is consistent with a central finite difference of the energy
+    k = 4
+    step = 1e-5
+    tp, tm = list(th), list(th)
+    tp[k] += step
+    tm[k] -= step
+    WF.thetas = tp
+    ep = WF.energy_elec
+    WF.thetas = tm
+    em = WF.energy_elec
+    assert abs((ep - em) / (2 * step) - grad[len(WF.kappa) + k]) < 1e-7
+
+
+def test_wavefunction_optimisation_reaches_reference_energy(sq, golden):
+    """Reference known answer (tests/test_unitary_product_state.py:362-394): pp-tUPS(4,4), 1 layer, on
+    H2O/STO-3G converges to -83.96387402720552 Eh (tolerance 1e-6 there)."""
+    arrays, _, _ = golden
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    ints = ArrayIntegrals(arrays["h2o_h_mo"], arrays["h2o_g_mo"], num_elec=10)
+    eye = np.eye(arrays["h2o_h_mo"].shape[0])
+    WF = WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 1, "do_pp": True})
+    WF.run_wf_optimization_1step("bfgs", orbital_optimization=False)
+    assert abs(WF.energy_elec + 83.96387402720552) < 1e-6
+
+
+def test_ucc_state_against_reference(sq, golden):
+    arrays, meta, _ = golden
+    from slowquant_b200.util import UccStructure
+
+    info = sq.ci.get_indexing(0, 4, 0, 2, 2)
+    st = UccStructure()
+    st.add_sa_singles([0, 1], [2, 3])
+    st.add_sa_doubles([0, 1], [2, 3])
+    st.add_triples([0, 1, 2, 3], [4, 5, 6, 7])
+    st.add_quadruples([0, 1, 2, 3], [4, 5, 6, 7])
+    m = meta["ucc44"]
+    assert st.excitation_operator_type == m["types"]
+    assert [list(t) for t in st.excitation_indices] == m["indices"]
+    th = arrays["ucc44_thetas"].tolist()
+    hf = np.zeros(info.num_det)
+    hf[0] = 1.0
+    res = sq.osa.construct_ucc_state(hf, info, th, st)
+    assert np.max(np.abs(res - arrays["ucc44_result"])) < 1e-12
+    back = sq.osa.construct_ucc_state(arrays["ucc44_result"], info, th, st, dagger=True)
+    assert np.max(np.abs(back - arrays["ucc44_result_dagger"])) < 1e-12
+    via_u = sq.osa.propagate_state(["U"], hf, info, th, st)
+    assert np.max(np.abs(via_u - arrays["ucc44_result"])) < 1e-12
+
+
+def test_build_operator_matrix(sq):
+    from slowquant_b200.operators import G2_sa
+
+    info = sq.ci.get_indexing(0, 4, 0, 2, 2)
+    sp = orc.get_indexing(0, 4, 0, 2, 2)
+    T = G2_sa(0, 1, 2, 3, 4, True)
+    mat = sq.osa.build_operator_matrix(T, info)
+    assert np.max(np.abs(mat + mat.T)) < 1e-15
+    v = np.random.default_rng(2).normal(size=sp.num_det)
+    ref = orc.propagate_state([orc.G2_sa(0, 1, 2, 3, 4)], v, sp, do_folding=False)
+    assert np.max(np.abs(mat @ v - ref)) < 1e-13
