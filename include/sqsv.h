@@ -115,6 +115,32 @@ int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, do
 int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                       double* bra_dev, double* ket_dev, double* grad_host, void* stream);
 
+/* ---- alpha-sharded vectors: one process per GPU, shards peer-mapped over NVLink ----------------
+ * (no counterpart in the reference, which is single-process).  The vector is split by rows
+ * (alpha strings); operators whose row pairs stay on one device run unchanged, the others rotate their
+ * tiles in place through peer pointers (the two owners of a pair split its columns).  The caller separates
+ * "exchange" operators from their neighbours with a device-wide barrier (sq_layout_needs_exchange). */
+
+/* contiguous row ranges grouped by the occupation of the first log2(world) orbitals; row_starts_out[world+1] */
+int sq_partition_prefix(int n_orb, int n_alpha, int world, int64_t* row_starts_out);
+/* declare the partition of a space created with [row_starts[rank], row_starts[rank+1]) */
+int sq_space_set_partition(sq_space* sp, int world, int rank, const int64_t* row_starts);
+/* plain cudaMalloc'ed shard (IPC-exportable), and CUDA IPC plumbing: 64-byte handles */
+int sq_dist_alloc(int device, int64_t n_doubles, double** out);
+int sq_dist_free(double* ptr);
+int sq_ipc_export(const double* ptr, unsigned char* handle64);
+int sq_ipc_import(int device, const unsigned char* handle64, double** out);
+int sq_ipc_close(double* ptr);
+/* work-list statistics of operator k on this rank: {orbital-pair id or -1, local row pairs, local inert
+ * rows, cross-device row pairs this rank works on (half the columns each), cross_global, touched amplitudes} */
+int sq_layout_op_stats(const sq_layout* lay, int k, int64_t* out6);
+/* 1 if operators [first,last) contain a row pair that spans two devices (identical on every rank) */
+int sq_layout_needs_exchange(const sq_layout* lay, int first, int last);
+/* sq_ups_apply on a sharded vector: shard_ptrs_host[r] = device pointer of rank r's shard as mapped in THIS
+ * process (own shard for r == rank).  Only orbital-pair operators (sa_single, pair double) may exchange. */
+int sq_ups_apply_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                      int dagger, double* const* shard_ptrs_host, void* stream);
+
 /* ---- generic operator application (apply_operator_serial/threaded, :53-219; propagate_state
  *      inner loop, :596-628) -------------------------------------------------------------------- */
 

@@ -65,6 +65,16 @@ def _declare(lib: C.CDLL) -> None:
             [vp, pi32, i32, C.c_uint32, C.c_uint32, C.POINTER(i32), pu32, pu32, C.POINTER(i32)],
         ),
         "sq_launch_count": (i64, []),
+        "sq_partition_prefix": (i32, [i32, i32, i32, pi64]),
+        "sq_space_set_partition": (i32, [vp, i32, i32, pi64]),
+        "sq_dist_alloc": (i32, [i32, i64, C.POINTER(vp)]),
+        "sq_dist_free": (i32, [vp]),
+        "sq_ipc_export": (i32, [vp, C.c_char_p]),
+        "sq_ipc_import": (i32, [i32, C.c_char_p, C.POINTER(vp)]),
+        "sq_ipc_close": (i32, [vp]),
+        "sq_layout_needs_exchange": (i32, [vp, i32, i32]),
+        "sq_layout_op_stats": (i32, [vp, i32, pi64]),
+        "sq_ups_apply_dist": (i32, [vp, vp, pdbl, i32, i32, i32, C.POINTER(vp), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
@@ -78,7 +88,8 @@ EXPORTED_SYMBOLS = (
     "sq_layout_attach_generator sq_layout_destroy sq_layout_num_ops sq_layout_num_launches "
     "sq_layout_touched_amplitudes sq_ups_apply "
     "sq_grad_action sq_ups_grad_sweep sq_apply_strings sq_dot sq_axpy sq_scale_copy sq_sigma sq_rdm12 "
-    "sq_debug_string_action sq_launch_count"
+    "sq_debug_string_action sq_launch_count sq_partition_prefix sq_space_set_partition sq_dist_alloc sq_dist_free "
+    "sq_ipc_export sq_ipc_import sq_ipc_close sq_layout_needs_exchange sq_ups_apply_dist sq_layout_op_stats"
 ).split()
 
 

@@ -40,8 +40,9 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
   SQ_CHECK(sq_make_string_action(sp, ld, 4, &actD));
   const uint32_t bi = 1u << i, ba = 1u << a;
   std::vector<uint32_t> codeA(sp->NA), codeB(sp->NB);
-  std::vector<int32_t> rows;
+  std::vector<int32_t> rows, crossSrc, crossTgt;
   int64_t nsrcA_local = 0, ninertA_local = 0;
+  pt->cross_global = false;
   for (int64_t I = 0; I < sp->NA; ++I) {
     const uint32_t m = sp->strA[I];
     uint32_t cls = SQ_CLS_INERT, partner = 0;
@@ -60,28 +61,38 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
     }
     code |= (uint32_t)neg_of(m, actB.parA) << 3;   // factor an alpha string gives the beta single
     codeA[I] = code;
+    if (cls == SQ_CLS_SRC && sp->world > 1 && sq_row_owner(sp, I) != sq_row_owner(sp, partner)) pt->cross_global = true;
     if (I >= sp->row_begin && I < sp->row_end) {
       if (cls == SQ_CLS_SRC) {
         if ((int64_t)partner < sp->row_begin || (int64_t)partner >= sp->row_end) {
-          sq_set_error("orbital pair (%d,%d): partner alpha row %u of row %lld is on another device", i, a,
-                       partner, (long long)I);
-          return SQ_ERR_UNSUPPORTED;
+          if (sp->world <= 1) {
+            sq_set_error("orbital pair (%d,%d): partner alpha row %u of row %lld is on another device and no "
+                         "partition is set (sq_space_set_partition)", i, a, partner, (long long)I);
+            return SQ_ERR_UNSUPPORTED;
+          }
+          crossSrc.push_back((int32_t)I);   // this rank owns the src row of a cross-device pair
+        } else {
+          rows.push_back((int32_t)I);
+          ++nsrcA_local;
         }
-        rows.push_back((int32_t)I);
-        ++nsrcA_local;
       } else if (cls == SQ_CLS_INERT) {
         rows.push_back((int32_t)I);
         ++ninertA_local;
       } else {
-        // tgt rows ride with their (local) src row
+        // tgt rows ride with their src row; if that one is remote this rank takes half of the tile's columns
         const int64_t src = sp->rankA[m ^ bi ^ ba];
         if (src < sp->row_begin || src >= sp->row_end) {
-          sq_set_error("orbital pair (%d,%d): source alpha row of row %lld is on another device", i, a, (long long)I);
-          return SQ_ERR_UNSUPPORTED;
+          if (sp->world <= 1) {
+            sq_set_error("orbital pair (%d,%d): source alpha row of row %lld is on another device and no "
+                         "partition is set (sq_space_set_partition)", i, a, (long long)I);
+            return SQ_ERR_UNSUPPORTED;
+          }
+          crossTgt.push_back((int32_t)src);
         }
       }
     }
   }
+  pt->n_cross_items = (int64_t)(crossSrc.size() + crossTgt.size());
   int64_t nsrcB = 0;
   for (int64_t I = 0; I < sp->NB; ++I) {
     const uint32_t m = sp->strB[I];
@@ -109,7 +120,7 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
   pt->n_src_rows = nsrcA_local;
   pt->n_src_cols = nsrcB;
   // amplitudes touched by a block containing sa_single: everything except inert x inert
-  pt->touched = 2 * nsrcA_local * sp->NB + ninertA_local * 2 * nsrcB;
+  pt->touched = 2 * nsrcA_local * sp->NB + ninertA_local * 2 * nsrcB + pt->n_cross_items * sp->NB;
   // ---- class-homogeneous work lists (tile_kernel_v2) ----
   auto bitof = [](uint32_t code, int b) -> int { return (int)((code >> b) & 1u); };
   std::vector<int2> colItems;
@@ -139,20 +150,31 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
   std::vector<int4> rowItems;
   int sig_a = 0, sig_b = 0;   // gauge-invariant pair-double sign factors; 0 = not yet seen, 2 = mixed
   {
+    // item = {row0 (local index on its owner), row1 (local index on its owner),
+    //         flags | owner(row0) << 8 | owner(row1) << 16, column selector (0 all, 1 even / 2 odd column CTAs)}
     std::vector<int4> src, inert;
+    const int me = sp->rank;
+    auto pair_item = [&](int32_t S, int colsel) {   // S = global index of the src row of the pair
+      const uint32_t c = codeA[S];
+      const uint32_t ip = c >> 5;
+      const int flags = bitof(c, 2) | (bitof(c, 3) << 1) | (bitof(codeA[ip], 3) << 2) | (bitof(c, 4) << 3);
+      const int o0 = sq_row_owner(sp, S), o1 = sq_row_owner(sp, ip);
+      src.push_back(make_int4((int)(S - sq_rank_start(sp, o0)), (int)((int64_t)ip - sq_rank_start(sp, o1)),
+                              flags | (o0 << 8) | (o1 << 16), colsel));
+      // row factor of sigma = dA * sSa * crossA(partner row)
+      const int f = (bitof(c, 4) ^ bitof(c, 2) ^ bitof(codeA[ip], 3)) ? -1 : 1;
+      sig_a = (sig_a == 0) ? f : (sig_a == f ? f : 2);
+    };
     for (int32_t I : rows) {
       const uint32_t c = codeA[I], cls = c & 3u;
-      if (cls == SQ_CLS_SRC) {
-        const uint32_t ip = c >> 5;
-        const int flags = bitof(c, 2) | (bitof(c, 3) << 1) | (bitof(codeA[ip], 3) << 2) | (bitof(c, 4) << 3);
-        src.push_back(make_int4(I, (int)ip, flags, 0));
-        // row factor of sigma = dA * sSa * crossA(partner row)
-        const int f = (bitof(c, 4) ^ bitof(c, 2) ^ bitof(codeA[ip], 3)) ? -1 : 1;
-        sig_a = (sig_a == 0) ? f : (sig_a == f ? f : 2);
-      } else {
-        inert.push_back(make_int4(I, -1, bitof(c, 3) << 1, 0));
-      }
+      if (cls == SQ_CLS_SRC)
+        pair_item(I, 0);
+      else
+        inert.push_back(make_int4((int)(I - sp->row_begin), -1, (bitof(c, 3) << 1) | (me << 8) | (me << 16), 0));
     }
+    // cross-device pairs: the src-row owner takes the even column CTAs, the tgt-row owner the odd ones
+    for (int32_t S : crossSrc) pair_item(S, 1);
+    for (int32_t S : crossTgt) pair_item(S, 2);
     const size_t TR = 8;
     auto pad = [&](std::vector<int4>& v) {
       while (v.size() % TR) v.push_back(make_int4(-1, -1, 0, 0));
@@ -172,6 +194,7 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
     sig_b = (sig_b == 0) ? f : (sig_b == f ? f : 2);
   }
   pt->sigma = (sig_a == 2 || sig_b == 2) ? 0 : ((sig_a == 0 || sig_b == 0) ? 1 : sig_a * sig_b);
+  if (sp->device < 0) return SQ_OK;   // host-only layout: plan / partition logic without device tables
   SQ_CUDA(cudaSetDevice(sp->device));
   SQ_CHECK(upload(&pt->d_codeA, codeA));
   SQ_CHECK(upload(&pt->d_codeB, codeB));
@@ -265,6 +288,7 @@ static int build_gen_tables(sq_space* sp, const std::vector<int>& idx, GenTables
   }
   gt->n_rows = (int64_t)srcRows.size();
   gt->n_cols_valid = nvalid;
+  if (sp->device < 0) return SQ_OK;
   SQ_CUDA(cudaSetDevice(sp->device));
   SQ_CHECK(upload(&gt->d_srcRows, srcRows));
   SQ_CHECK(upload(&gt->d_tgtRows, tgtRows));
@@ -280,10 +304,6 @@ extern "C" int sq_layout_create(sq_space* sp, int n_ops, const int32_t* exc_type
                                 const int32_t* idx_flat, sq_layout** out) {
   if (!sp || !out || n_ops < 0 || (n_ops > 0 && (!exc_type || !idx_offsets || !idx_flat))) return SQ_ERR_INVALID;
   *out = nullptr;
-  if (sp->device < 0) {
-    sq_set_error("sq_layout_create: host-only space (device = -1) cannot run kernels");
-    return SQ_ERR_INVALID;
-  }
   sq_layout* lay = new sq_layout();
   lay->sp = sp;
   lay->ops.resize(n_ops);
@@ -394,7 +414,7 @@ extern "C" int sq_layout_attach_generator(sq_layout* lay, int k, int n_strings, 
 
 extern "C" int sq_layout_destroy(sq_layout* lay) {
   if (!lay) return SQ_OK;
-  cudaSetDevice(lay->sp->device);
+  if (lay->sp->device >= 0) cudaSetDevice(lay->sp->device);
   for (auto& pt : lay->pairs) {
     cudaFree(pt.d_codeA);
     cudaFree(pt.d_codeB);
@@ -414,6 +434,24 @@ extern "C" int sq_layout_destroy(sq_layout* lay) {
 }
 
 extern "C" int sq_layout_num_ops(const sq_layout* lay) { return lay ? (int)lay->ops.size() : -1; }
+
+// work-list statistics of operator k on this rank: out6 = {orbital-pair id or -1, local row pairs,
+// local inert rows, cross-device row pairs this rank works on, cross_global, touched amplitudes}
+extern "C" int sq_layout_op_stats(const sq_layout* lay, int k, int64_t* out6) {
+  if (!lay || !out6 || k < 0 || k >= (int)lay->ops.size()) return SQ_ERR_INVALID;
+  const LayoutOp& op = lay->ops[k];
+  for (int i = 0; i < 6; ++i) out6[i] = 0;
+  out6[0] = op.pair;
+  if (op.pair >= 0) {
+    const PairTables& pt = lay->pairs[op.pair];
+    out6[1] = pt.n_src_rows;
+    out6[2] = pt.n_rows - pt.n_src_rows;
+    out6[3] = pt.n_cross_items;
+    out6[4] = pt.cross_global ? 1 : 0;
+    out6[5] = pt.touched;
+  }
+  return SQ_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // execution plan: consecutive operators on the same orbital pair fuse into one tile launch
@@ -607,8 +645,124 @@ static int run_tile(sq_space* sp, sq_layout* lay, const std::vector<int>& run, c
   return SQ_OK;
 }
 
+static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                          double* state_dev, const PeerPtrs* peers, void* stream);
+
 extern "C" int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
                             double* state_dev, void* stream) {
+  return ups_apply_impl(sp, lay, thetas_host, first, last, dagger, state_dev, nullptr, stream);
+}
+
+// ---- alpha-sharded vectors (one process per GPU; shards peer-mapped over NVLink with CUDA IPC) ----
+extern "C" int sq_space_set_partition(sq_space* sp, int world, int rank, const int64_t* row_starts) {
+  if (!sp || !row_starts || world < 1 || world > SQ_MAX_WORLD || rank < 0 || rank >= world) return SQ_ERR_INVALID;
+  if (row_starts[0] != 0 || row_starts[world] != sp->NA) {
+    sq_set_error("sq_space_set_partition: row_starts must run from 0 to %lld", (long long)sp->NA);
+    return SQ_ERR_INVALID;
+  }
+  for (int r = 0; r < world; ++r)
+    if (row_starts[r] > row_starts[r + 1]) return SQ_ERR_INVALID;
+  if (row_starts[rank] != sp->row_begin || row_starts[rank + 1] != sp->row_end) {
+    sq_set_error("sq_space_set_partition: rank %d owns rows [%lld,%lld) but the space was created for [%lld,%lld)", rank,
+                 (long long)row_starts[rank], (long long)row_starts[rank + 1], (long long)sp->row_begin,
+                 (long long)sp->row_end);
+    return SQ_ERR_INVALID;
+  }
+  sp->world = world;
+  sp->rank = rank;
+  sp->row_starts.assign(row_starts, row_starts + world + 1);
+  return SQ_OK;
+}
+
+// Default partition: alpha strings grouped by the occupation of the first log2(world) orbitals.  In
+// itertools.combinations order these groups are contiguous row ranges, and every orbital pair (p, p+1) with
+// p >= log2(world) keeps both rows of a pair on the same device.
+extern "C" int sq_partition_prefix(int n_orb, int n_alpha, int world, int64_t* row_starts_out) {
+  if (!row_starts_out || world < 1 || (world & (world - 1)) != 0 || world > SQ_MAX_WORLD) {
+    sq_set_error("sq_partition_prefix: world must be a power of two <= %d", SQ_MAX_WORLD);
+    return SQ_ERR_INVALID;
+  }
+  int k = 0;
+  while ((1 << k) < world) ++k;
+  if (k > n_orb) return SQ_ERR_INVALID;
+  auto binom = [](int n, int r) -> int64_t {
+    if (r < 0 || r > n) return 0;
+    long double v = 1;
+    for (int i = 1; i <= r; ++i) v = v * (n - r + i) / i;
+    return (int64_t)(v + 0.5L);
+  };
+  // lexicographic order of sorted index tuples: prefix patterns with an occupied early orbital come first,
+  // i.e. prefix bit patterns (orbital 0 = most significant) in DEcreasing numeric order
+  int64_t acc = 0;
+  row_starts_out[0] = 0;
+  for (int g = 0; g < world; ++g) {
+    const int pattern = world - 1 - g;
+    const int occ = __builtin_popcount((unsigned)pattern);
+    acc += binom(n_orb - k, n_alpha - occ);
+    row_starts_out[g + 1] = acc;
+  }
+  return SQ_OK;
+}
+
+extern "C" int sq_dist_alloc(int device, int64_t n_doubles, double** out) {
+  if (!out || n_doubles < 0) return SQ_ERR_INVALID;
+  SQ_CUDA(cudaSetDevice(device));
+  // at least one element so that the allocation has a valid IPC handle even for an empty shard
+  SQ_CUDA(cudaMalloc(out, sizeof(double) * (size_t)(n_doubles > 0 ? n_doubles : 1)));
+  return SQ_OK;
+}
+
+extern "C" int sq_dist_free(double* ptr) {
+  if (ptr) SQ_CUDA(cudaFree(ptr));
+  return SQ_OK;
+}
+
+extern "C" int sq_ipc_export(const double* ptr, unsigned char* handle64) {
+  if (!ptr || !handle64) return SQ_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  SQ_CUDA(cudaIpcGetMemHandle(&h, const_cast<double*>(ptr)));
+  memcpy(handle64, &h, 64);
+  return SQ_OK;
+}
+
+extern "C" int sq_ipc_import(int device, const unsigned char* handle64, double** out) {
+  if (!handle64 || !out) return SQ_ERR_INVALID;
+  SQ_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  SQ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *out = (double*)p;
+  return SQ_OK;
+}
+
+extern "C" int sq_ipc_close(double* ptr) {
+  if (ptr) SQ_CUDA(cudaIpcCloseMemHandle(ptr));
+  return SQ_OK;
+}
+
+// 1 if some row pair of the runs in [first,last) spans two devices: every rank must then separate these
+// operators from their neighbours by a device-wide barrier (same answer on every rank).
+extern "C" int sq_layout_needs_exchange(const sq_layout* lay, int first, int last) {
+  if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
+  for (int k = first; k < last; ++k) {
+    const LayoutOp& op = lay->ops[k];
+    if (op.pair >= 0 && lay->pairs[op.pair].cross_global) return 1;
+  }
+  return 0;
+}
+
+extern "C" int sq_ups_apply_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                                 int dagger, double* const* shard_ptrs_host, void* stream) {
+  if (!sp || !shard_ptrs_host) return SQ_ERR_INVALID;
+  PeerPtrs peers;
+  for (int r = 0; r < SQ_MAX_WORLD; ++r) peers.p[r] = (r < sp->world) ? shard_ptrs_host[r] : nullptr;
+  return ups_apply_impl(sp, lay, thetas_host, first, last, dagger, peers.p[sp->rank], &peers, stream);
+}
+
+static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                          double* state_dev, const PeerPtrs* peers, void* stream) {
   if (!sp || !lay || lay->sp != sp || !state_dev) return SQ_ERR_INVALID;
   const int P = (int)lay->ops.size();
   if (first < 0 || last > P || first > last || (first < last && !thetas_host)) {
@@ -616,6 +770,10 @@ extern "C" int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_h
     return SQ_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (sp->device < 0) {
+    sq_set_error("sq_ups_apply: host-only space (device = -1) cannot run kernels");
+    return SQ_ERR_INVALID;
+  }
   SQ_CUDA(cudaSetDevice(sp->device));
   std::vector<int> order;
   exec_order(first, last, dagger, &order);
@@ -627,7 +785,7 @@ extern "C" int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_h
       TileStep steps[SQ_MAX_PROGRAM];
       int step_op[SQ_MAX_PROGRAM], n_steps = 0;
       SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
-      SQ_CHECK(sq_launch_tile(sp, lay->pairs[op.pair], steps, n_steps, state_dev, st));
+      SQ_CHECK(sq_launch_tile(sp, lay->pairs[op.pair], steps, n_steps, state_dev, peers, st));
     } else if (op.null_op) {
       continue;
     } else if (op.gen >= 0) {

@@ -79,7 +79,12 @@ struct PairTables {       // tables for one spatial orbital pair (i,a)
   int4* d_rowItems = nullptr;
   int n_rowchunk_src = 0, n_rowchunk_inert = 0;
   int sigma = 0;                 // gauge-invariant pair-double sign (+1/-1) if uniform, 0 otherwise
+  bool cross_global = false;     // some row pair of this orbital pair spans two devices (same answer on every rank)
+  int64_t n_cross_items = 0;     // cross-device row pairs this rank works on (half of the columns each)
 };
+
+#define SQ_MAX_WORLD 16
+struct PeerPtrs { double* p[SQ_MAX_WORLD]; };   // base pointer of the vector shard on every rank (peer-mapped)
 
 struct GenTables {        // tables for one generic excitation generator G (single string)
   StringAction act;
@@ -95,6 +100,8 @@ struct sq_space {
   int n_orb, n_alpha, n_beta, device;
   int64_t NA, NB, ndet;
   int64_t row_begin, row_end;       // local alpha rows
+  int world = 1, rank = 0;          // alpha-row partition over devices (sq_space_set_partition)
+  std::vector<int64_t> row_starts;  // [world + 1]; rank r owns rows [row_starts[r], row_starts[r+1])
   uint64_t binom[SQ_MAX_ORB + 2][SQ_MAX_ORB + 2];
   std::vector<uint32_t> strA, strB; // occupation masks in itertools.combinations order
   std::vector<int32_t> rankA, rankB;  // mask -> string index (-1 if wrong electron count); 2^n entries
@@ -133,6 +140,16 @@ struct sq_layout {
   std::map<std::vector<int>, int> gen_index;
 };
 
+static inline int sq_row_owner(const sq_space* sp, int64_t row) {
+  if (sp->world <= 1) return sp->rank;
+  int r = 0;
+  while (r + 1 < sp->world && row >= sp->row_starts[r + 1]) ++r;
+  return r;
+}
+static inline int64_t sq_rank_start(const sq_space* sp, int r) {
+  return sp->world <= 1 ? sp->row_begin : sp->row_starts[r];
+}
+
 // host helpers (sqsv_space.cu)
 int sq_rank_mask(const sq_space* sp, int spin, uint32_t mask);   // -1 if not in list
 int sq_make_string_action(const sq_space* sp, const int32_t* ops, int n_ops, StringAction* out);
@@ -143,7 +160,7 @@ int sq_ensure_partial(sq_space* sp, int64_t n);
 // kernel launchers (sqsv_kernels.cu)
 struct TileStep { int kind; double c, s; };   // kind: 0 alpha-rot, 1 beta-rot, 2 pair-double rot
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
-                   double* state, cudaStream_t st);
+                   double* state, const PeerPtrs* peers, cudaStream_t st);
 int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                         double* bra, double* ket, double* grad_out_host, cudaStream_t st);
 int sq_launch_gen_rot(sq_space* sp, const GenTables& gt, double c, double s, double* state,

@@ -135,10 +135,23 @@ __device__ __forceinline__ double flip(double x, int neg) {
 
 #define V2_ROWS_PER_ITER 4
 
+// Row pointers: a row item names the owner rank of each of its two rows; `bases` holds the peer-mapped
+// base pointer of every rank's shard (NVLink P2P), so a tile whose rows live on two GPUs is rotated in
+// place by plain loads/stores on local + remote memory.  On one GPU both owners are rank 0.
+__device__ __forceinline__ double* rowp0(const PeerPtrs& b, const int4& ri, int64_t NB) {
+  return b.p[(ri.z >> 8) & 0xff] + (int64_t)ri.x * NB;
+}
+__device__ __forceinline__ double* rowp1(const PeerPtrs& b, const int4& ri, int64_t NB) {
+  return b.p[(ri.z >> 16) & 0xff] + (int64_t)ri.y * NB;
+}
+// pad entries have x < 0; cross-device pairs are split between the two owners by column-CTA parity (w = 1 / 2)
+__device__ __forceinline__ bool item_on(const int4& ri) {
+  return ri.x >= 0 && (ri.w == 0 || (int)(blockIdx.x & 1u) == ri.w - 1);
+}
+
 __global__ void __launch_bounds__(TILE_THREADS)
-tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_colblk_src,
-               const int4* __restrict__ rowItems, int n_rowchunk_src, int64_t NB, int64_t row_begin,
-               const TileMatrices tm) {
+tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_colblk_src,
+               const int4* __restrict__ rowItems, int n_rowchunk_src, int64_t NB, const TileMatrices tm) {
   const bool col_src = (int)blockIdx.x < n_colblk_src;
   const bool row_src = (int)blockIdx.y < n_rowchunk_src;
   if (!col_src && !row_src) return;
@@ -159,9 +172,9 @@ tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (ri[j].x >= 0) {
-          const double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
-          const double* r1 = C + ((int64_t)ri[j].y - row_begin) * NB;
+        if (item_on(ri[j])) {
+          const double* r0 = rowp0(bases, ri[j], NB);
+          const double* r1 = rowp1(bases, ri[j], NB);
           x00[j] = r0[ib];
           x01[j] = r0[ibp];
           x10[j] = r1[ib];
@@ -170,7 +183,7 @@ tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_
       }
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (ri[j].x >= 0) {
+        if (item_on(ri[j])) {
           const int rf = ri[j].z;
           const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
           const int g10 = sSa ^ crb;            // sgA0
@@ -181,8 +194,8 @@ tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_
           const double z1 = tm.m[4] * y0 + tm.m[5] * y1 + tm.m[6] * y2 + tm.m[7] * y3;
           const double z2 = tm.m[8] * y0 + tm.m[9] * y1 + tm.m[10] * y2 + tm.m[11] * y3;
           const double z3 = tm.m[12] * y0 + tm.m[13] * y1 + tm.m[14] * y2 + tm.m[15] * y3;
-          double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
-          double* r1 = C + ((int64_t)ri[j].y - row_begin) * NB;
+          double* r0 = rowp0(bases, ri[j], NB);
+          double* r1 = rowp1(bases, ri[j], NB);
           r0[ib] = z0;
           r0[ibp] = flip(z1, g01);
           r1[ib] = flip(z2, g10);
@@ -199,18 +212,18 @@ tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (ri[j].x >= 0) {
-          x0[j] = C[((int64_t)ri[j].x - row_begin) * NB + ib];
-          x1[j] = C[((int64_t)ri[j].y - row_begin) * NB + ib];
+        if (item_on(ri[j])) {
+          x0[j] = rowp0(bases, ri[j], NB)[ib];
+          x1[j] = rowp1(bases, ri[j], NB)[ib];
         }
       }
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (ri[j].x >= 0) {
+        if (item_on(ri[j])) {
           const int g = (ri[j].z & 1) ^ crb;   // sSa * crossB(column)
           const double a = x0[j], b = flip(x1[j], g);
-          C[((int64_t)ri[j].x - row_begin) * NB + ib] = tm.ca * a - tm.sa * b;
-          C[((int64_t)ri[j].y - row_begin) * NB + ib] = flip(tm.ca * b + tm.sa * a, g);
+          rowp0(bases, ri[j], NB)[ib] = tm.ca * a - tm.sa * b;
+          rowp1(bases, ri[j], NB)[ib] = flip(tm.ca * b + tm.sa * a, g);
         }
       }
     }
@@ -223,18 +236,18 @@ tile_kernel_v2(double* __restrict__ C, const int2* __restrict__ colItems, int n_
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (ri[j].x >= 0) {
-          const double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
+        if (item_on(ri[j])) {
+          const double* r0 = rowp0(bases, ri[j], NB);
           x0[j] = r0[ib];
           x1[j] = r0[ibp];
         }
       }
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (ri[j].x >= 0) {
+        if (item_on(ri[j])) {
           const int g = sSb ^ ((ri[j].z >> 1) & 1);   // sSb * crossA(row)
           const double a = x0[j], b = flip(x1[j], g);
-          double* r0 = C + ((int64_t)ri[j].x - row_begin) * NB;
+          double* r0 = rowp0(bases, ri[j], NB);
           r0[ib] = tm.cb * a - tm.sb * b;
           r0[ibp] = flip(tm.cb * b + tm.sb * a, g);
         }
@@ -594,13 +607,21 @@ static void build_tile_matrices(const TileStep* steps, int n_steps, int sigma, T
 static int g_tile_variant = -1;   // SQ_TILE_KERNEL=1 forces the step-loop kernel (debug / A-B comparison)
 
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps, double* state,
-                   cudaStream_t st) {
-  if (pt.n_rows == 0) return SQ_OK;
+                   const PeerPtrs* peers, cudaStream_t st) {
+  if (pt.n_rows == 0 && pt.n_cross_items == 0) return SQ_OK;
   if (g_tile_variant < 0) {
     const char* e = getenv("SQ_TILE_KERNEL");
     g_tile_variant = (e && e[0] == '1') ? 1 : 2;
   }
-  if (g_tile_variant == 2 && pt.sigma != 0) {
+  if (pt.n_cross_items > 0 && (!peers || pt.sigma == 0)) {
+    sq_set_error("orbital pair (%d,%d) pairs alpha rows on different devices: use sq_ups_apply_dist with peer-mapped "
+                 "shards", pt.i, pt.a);
+    return SQ_ERR_UNSUPPORTED;
+  }
+  if ((g_tile_variant == 2 || peers) && pt.sigma != 0) {
+    PeerPtrs bases;
+    for (int r = 0; r < SQ_MAX_WORLD; ++r) bases.p[r] = peers ? peers->p[r] : nullptr;
+    bases.p[sp->rank] = state;
     if (n_steps < 1 || n_steps > SQ_MAX_PROGRAM) {
       sq_set_error("tile program with %d steps (max %d)", n_steps, SQ_MAX_PROGRAM);
       return SQ_ERR_INVALID;
@@ -614,8 +635,8 @@ int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, in
     const int gy = any_single ? pt.n_rowchunk_src + pt.n_rowchunk_inert : pt.n_rowchunk_src;
     if (gx == 0 || gy == 0) return SQ_OK;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    tile_kernel_v2<<<grid, TILE_THREADS, 0, st>>>(state, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
-                                                 pt.n_rowchunk_src, sp->NB, sp->row_begin, tm);
+    tile_kernel_v2<<<grid, TILE_THREADS, 0, st>>>(bases, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
+                                                 pt.n_rowchunk_src, sp->NB, tm);
     return check_launch("tile_kernel_v2");
   }
   TileProgram prog;

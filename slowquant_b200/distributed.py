@@ -1,0 +1,208 @@
+"""Alpha-string-sharded CI vectors over the GPUs of one node (one process per GPU).
+
+The reference is single-process; this is the scaling axis the north star asks for: the
+N_alpha x N_beta coefficient matrix is split by rows.  Rows are grouped by the occupation of the first
+log2(G) orbitals, which in itertools.combinations order are contiguous ranges, so every tUPS brick on an
+orbital pair (p, p+1) with p >= log2(G) is purely local.  The remaining bricks pair rows that live on two
+GPUs; their tiles are rotated in place through CUDA-IPC peer mappings over NVLink (the two owners split
+the columns of each pair), with a stream-ordered NCCL barrier before and after such an operator.  Scalars
+(dots, norms) are reduced with ``all_reduce``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from slowquant_b200 import _lib
+from slowquant_b200 import operator_state_algebra as osa
+from slowquant_b200.ci_spaces import CI_Info
+
+
+def partition_prefix(n_orb: int, n_alpha: int, world: int) -> np.ndarray:
+    """Row ranges of the prefix-class partition: rank r owns rows [starts[r], starts[r+1])."""
+    lib = _lib.load()
+    out = np.zeros(world + 1, dtype=np.int64)
+    _lib.check(lib.sq_partition_prefix(n_orb, n_alpha, world, out.ctypes.data_as(C.POINTER(C.c_int64))))
+    return out
+
+
+class ShardedSpace:
+    """CI space whose vector is sharded by alpha string over the ranks of a process group."""
+
+    def __init__(
+        self,
+        num_inactive_orbs: int,
+        num_active_orbs: int,
+        num_virtual_orbs: int,
+        num_active_elec_alpha: int,
+        num_active_elec_beta: int,
+        device: int | None = None,
+        rank: int | None = None,
+        world: int | None = None,
+    ) -> None:
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.row_starts = partition_prefix(num_active_orbs, num_active_elec_alpha, self.world)
+        rb, re = int(self.row_starts[self.rank]), int(self.row_starts[self.rank + 1])
+        self.ci_info = CI_Info(
+            num_inactive_orbs,
+            num_active_orbs,
+            num_virtual_orbs,
+            num_active_elec_alpha,
+            num_active_elec_beta,
+            device=device,
+            row_range=(rb, re),
+        )
+        lib = _lib.load()
+        _lib.check(
+            lib.sq_space_set_partition(
+                self.ci_info._handle, self.world, self.rank, self.row_starts.ctypes.data_as(C.POINTER(C.c_int64))
+            )
+        )
+        self.row_begin, self.row_end = rb, re
+        self.local_len = self.ci_info.local_len
+        self._barrier_token = None
+
+    # ---- shards -------------------------------------------------------------------------------
+    def alloc_state(self, zero: bool = True) -> "ShardedState":
+        return ShardedState(self, zero)
+
+    def barrier(self) -> None:
+        """Stream-ordered device-wide barrier (tiny NCCL all-reduce on the current stream)."""
+        if self.world == 1:
+            return
+        if self._barrier_token is None:
+            self._barrier_token = torch.zeros(1, dtype=torch.float32, device=torch.device("cuda", self.ci_info.device))
+        dist.all_reduce(self._barrier_token)
+
+    def exchange_plan(self, wf_struct, first: int, last: int, dagger: bool) -> list[tuple[int, int, bool]]:
+        """Split operators [first,last) into maximal ranges (f, l, needs_exchange) in execution order."""
+        lib = _lib.load()
+        lay = osa.compile_layout(self.ci_info, wf_struct)
+        flags = [bool(lib.sq_layout_needs_exchange(lay, k, k + 1)) for k in range(first, last)]
+        types, idx = wf_struct.excitation_operator_type, wf_struct.excitation_indices
+        pair_key = []
+        for k in range(first, last):
+            t, ind = types[k], idx[k]
+            if t == "sa_single":
+                pair_key.append((int(ind[0]), int(ind[1])))
+            elif t == "double" and len(ind) == 4 and ind[0] % 2 == 0 and ind[1] == ind[0] + 1 and ind[2] % 2 == 0 and ind[3] == ind[2] + 1:
+                pair_key.append((int(ind[0]) // 2, int(ind[2]) // 2))
+            else:
+                pair_key.append(None)
+        order = list(range(last - first))
+        if dagger:
+            order.reverse()
+        plan: list[tuple[int, int, bool]] = []
+        cur: list[int] = []
+        for j in order:
+            # operators on the same orbital pair stay together (they fuse into one launch);
+            # an exchange operator never shares a range with a different pair
+            if cur and (flags[j] != flags[cur[-1]] or (flags[j] and pair_key[j] != pair_key[cur[-1]])):
+                plan.append((first + min(cur), first + max(cur) + 1, flags[cur[0]]))
+                cur = []
+            cur.append(j)
+        if cur:
+            plan.append((first + min(cur), first + max(cur) + 1, flags[cur[0]]))
+        return plan
+
+
+class ShardedState:
+    """One rank's shard of a CI vector plus the peer mappings of all other shards."""
+
+    def __init__(self, space: ShardedSpace, zero: bool = True) -> None:
+        lib = _lib.load()
+        self.space = space
+        dev = space.ci_info.device
+        ptr = C.c_void_p()
+        _lib.check(lib.sq_dist_alloc(dev, space.local_len, C.byref(ptr)))
+        self._ptr = ptr
+        n = space.local_len
+
+        class _Iface:
+            __cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+
+        self._iface = _Iface()
+        self.local = torch.as_tensor(self._iface, device=torch.device("cuda", dev))[:n]
+        if zero:
+            self.local.zero_()
+        self._peer_ptrs = (C.c_void_p * space.world)()
+        self._peer_ptrs[space.rank] = ptr.value
+        self._opened: list[C.c_void_p] = []
+        if space.world > 1:
+            handle = C.create_string_buffer(64)
+            _lib.check(lib.sq_ipc_export(ptr, handle))
+            gathered: list = [None] * space.world
+            dist.all_gather_object(gathered, bytes(handle.raw))
+            for r in range(space.world):
+                if r == space.rank:
+                    continue
+                p = C.c_void_p()
+                _lib.check(lib.sq_ipc_import(dev, gathered[r], C.byref(p)))
+                self._peer_ptrs[r] = p.value
+                self._opened.append(p)
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def close(self) -> None:
+        lib = _lib.load()
+        if self.space.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+        for p in self._opened:
+            lib.sq_ipc_close(p)
+        self._opened = []
+        if self._ptr:
+            self.local = None
+            lib.sq_dist_free(self._ptr)
+            self._ptr = None
+
+    # convenience: fill the local shard from a full-length host vector / gather the full vector
+    def set_from_full(self, full: np.ndarray) -> None:
+        sp = self.space
+        nb = sp.ci_info.num_beta_strings
+        self.local.copy_(torch.from_numpy(np.ascontiguousarray(full[sp.row_begin * nb : sp.row_end * nb])))
+
+    def set_determinant(self, index: int) -> None:
+        sp = self.space
+        nb = sp.ci_info.num_beta_strings
+        self.local.zero_()
+        lo, hi = sp.row_begin * nb, sp.row_end * nb
+        if lo <= index < hi:
+            self.local[index - lo] = 1.0
+
+
+def construct_ups_state_sharded(
+    state: ShardedState, thetas: Sequence[float], ups_struct, dagger: bool = False, first: int = 0, last: int | None = None
+) -> None:
+    """In place: state <- U state (or U^dagger state) on the sharded vector (osa.py:963-1412 semantics)."""
+    lib = _lib.load()
+    sp = state.space
+    n_ops = len(ups_struct.excitation_operator_type)
+    last = n_ops if last is None else last
+    lay = osa.compile_layout(sp.ci_info, ups_struct)
+    th = osa._thetas_array(thetas, n_ops)
+    thp = th.ctypes.data_as(C.POINTER(C.c_double))
+    for f, l, exchange in sp.exchange_plan(ups_struct, first, last, dagger):
+        if exchange:
+            sp.barrier()
+        _lib.check(
+            lib.sq_ups_apply_dist(sp.ci_info._handle, lay, thp, f, l, 1 if dagger else 0, state._peer_ptrs, osa._stream())
+        )
+        if exchange:
+            sp.barrier()
+
+
+def dot_sharded(a: ShardedState, b: ShardedState) -> float:
+    """<a|b> over all shards."""
+    sp = a.space
+    local = osa._dot(a.local, b.local, sp.ci_info) if sp.local_len else 0.0
+    if sp.world == 1:
+        return local
+    t = torch.tensor([local], dtype=torch.float64, device=a.local.device)
+    dist.all_reduce(t)
+    return float(t.item())

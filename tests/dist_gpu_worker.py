@@ -1,0 +1,77 @@
+"""torchrun worker: alpha-sharded tUPS/QNP state construction on N GPUs checked against the single-GPU
+engine (each rank recomputes the full vector on its own GPU and compares its shard).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/dist_gpu_worker.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from slowquant_b200 import operator_state_algebra as osa
+    from slowquant_b200.ci_spaces import get_indexing
+    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded
+    from slowquant_b200.util import UpsStructure
+
+    worst = 0.0
+    cases = [(8, 4, 4, 2, False), (9, 4, 5, 2, True), (10, 5, 5, 2, False), (12, 6, 6, 1, False)]
+    for n, na, nb, L, qnp in cases:
+        sp = ShardedSpace(0, n, 0, na, nb, device=local_rank)
+        info = get_indexing(0, n, 0, na, nb, device=local_rank)
+        lay = UpsStructure()
+        lay.create_tiled(n, {"n_layers": L, "do_qnp": True} if qnp else {"n_layers": L, "do_tups": True})
+        rng = np.random.default_rng(1000 + n)       # same stream on every rank
+        th = rng.uniform(-np.pi, np.pi, lay.n_params)
+        full = rng.normal(size=info.num_det)
+        full /= np.linalg.norm(full)
+        ref = osa.construct_ups_state(full, info, th, lay)
+        ref_d = osa.construct_ups_state(full, info, th, lay, dagger=True)
+        nbs = info.num_beta_strings
+        lo, hi = sp.row_begin * nbs, sp.row_end * nbs
+        st = sp.alloc_state()
+        st.set_from_full(full)
+        construct_ups_state_sharded(st, th, lay)
+        torch.cuda.synchronize()
+        err = float(np.max(np.abs(st.local.cpu().numpy() - ref[lo:hi]))) if hi > lo else 0.0
+        nrm = dot_sharded(st, st)
+        st.set_from_full(full)
+        construct_ups_state_sharded(st, th, lay, dagger=True)
+        torch.cuda.synchronize()
+        err_d = float(np.max(np.abs(st.local.cpu().numpy() - ref_d[lo:hi]))) if hi > lo else 0.0
+        # HF determinant start
+        st.set_determinant(0)
+        hf = np.zeros(info.num_det)
+        hf[0] = 1.0
+        ref_hf = osa.construct_ups_state(hf, info, th, lay)
+        construct_ups_state_sharded(st, th, lay)
+        torch.cuda.synchronize()
+        err_hf = float(np.max(np.abs(st.local.cpu().numpy() - ref_hf[lo:hi]))) if hi > lo else 0.0
+        st.close()
+        e = torch.tensor([err, err_d, err_hf, abs(nrm - 1.0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"CAS({na + nb},{n}) L={L} world={world}: max|diff| fwd {e[0]:.2e} dagger {e[1]:.2e} hf {e[2]:.2e} "
+                  f"|norm-1| {e[3]:.2e}", flush=True)
+        worst = max(worst, float(e.max()))
+    dist.barrier()
+    dist.destroy_process_group()
+    if worst > 1e-12:
+        print("DIST_CHECK_FAILED", worst, flush=True)
+        sys.exit(1)
+    if rank == 0:
+        print("DIST_CHECK_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""Host-side logic of the alpha-sharded path, exercised with world_size-2/4 gloo process groups on CPU:
+partition, per-rank work lists, the exchange plan (identical on every rank) and complete, non-overlapping
+coverage of every orbital-pair tile.  No kernels run (host-only spaces, device = -1)."""
+import ctypes as C
+import os
+import socket
+from math import comb
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from slowquant_b200 import _lib
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank: int, world: int, port: int, n: int, na: int, nb: int, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from slowquant_b200.distributed import ShardedSpace
+        from slowquant_b200.util import UpsStructure
+
+        sp = ShardedSpace(0, n, 0, na, nb, device=-1, rank=rank, world=world)
+        lay = UpsStructure()
+        lay.create_tiled(n, {"n_layers": 1, "do_tups": True})
+        plan = sp.exchange_plan(lay, 0, lay.n_params, False)
+        plan_d = sp.exchange_plan(lay, 0, lay.n_params, True)
+        lib = _lib.load()
+        handle = __import__("slowquant_b200.operator_state_algebra", fromlist=["x"]).compile_layout(sp.ci_info, lay)
+        stats = []
+        for k in range(lay.n_params):
+            out = np.zeros(6, dtype=np.int64)
+            _lib.check(lib.sq_layout_op_stats(handle, k, out.ctypes.data_as(C.POINTER(C.c_int64))))
+            stats.append(out.tolist())
+        mine = {"rank": rank, "rows": (sp.row_begin, sp.row_end), "plan": plan, "plan_d": plan_d, "stats": stats}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            ret["all"] = gathered
+            ret["types"] = list(lay.excitation_operator_type)
+            ret["indices"] = [tuple(t) for t in lay.excitation_indices]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,na,nb", [(2, 6, 3, 3), (4, 7, 3, 4), (2, 5, 2, 2)])
+def test_sharded_work_lists_cover_every_tile(world, n, na, nb):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, na, nb, ret), nprocs=world, join=True)
+    allr = sorted(ret["all"], key=lambda d: d["rank"])
+    # partition: contiguous, complete, prefix classes
+    assert allr[0]["rows"][0] == 0 and allr[-1]["rows"][1] == comb(n, na)
+    for a, b in zip(allr[:-1], allr[1:]):
+        assert a["rows"][1] == b["rows"][0]
+    # the exchange plan is the same on every rank, covers all operators, in order
+    for key in ("plan", "plan_d"):
+        for d in allr[1:]:
+            assert d[key] == allr[0][key]
+    plan = allr[0]["plan"]
+    assert plan[0][0] == 0 and plan[-1][1] == len(ret["types"])
+    for (f0, l0, _), (f1, l1, _) in zip(plan[:-1], plan[1:]):
+        assert l0 == f1
+    assert [(f, l) for f, l, _ in allr[0]["plan_d"]] == [(f, l) for f, l, _ in plan[::-1]]
+    k_bits = world.bit_length() - 1
+    for k, (t, idx) in enumerate(zip(ret["types"], ret["indices"])):
+        p = idx[0] if t == "sa_single" else idx[0] // 2
+        crosses = p < k_bits           # pair (p, p+1) changes the occupation of the first log2(world) orbitals
+        for d in allr:
+            assert bool(d["stats"][k][4]) == crosses, (k, t, idx)
+        in_exchange_range = any(f <= k < l and x for f, l, x in plan)
+        assert in_exchange_range == crosses
+        # coverage: every (src,tgt) row pair is worked on either by one rank entirely, or by two ranks that
+        # split its columns; every inert row by exactly its owner
+        n_pairs = comb(n - 2, na - 1)
+        n_inert = comb(n, na) - 2 * n_pairs
+        local_pairs = sum(d["stats"][k][1] for d in allr)
+        cross_items = sum(d["stats"][k][3] for d in allr)
+        assert cross_items % 2 == 0
+        assert local_pairs + cross_items // 2 == n_pairs
+        assert sum(d["stats"][k][2] for d in allr) == n_inert
+        if not crosses:
+            assert cross_items == 0
+        # touched amplitudes add up to the single-device count
+        nbeta = comb(n, nb)
+        nsrc_b = comb(n - 2, nb - 1)
+        assert sum(d["stats"][k][5] for d in allr) == 2 * n_pairs * nbeta + n_inert * 2 * nsrc_b
+
+
+def test_partition_prefix_matches_string_order():
+    from slowquant_b200.distributed import partition_prefix
+
+    lib = _lib.load()
+    for n, na, world in [(6, 3, 2), (7, 3, 4), (8, 4, 8), (5, 1, 4)]:
+        starts = partition_prefix(n, na, world)
+        h = C.c_void_p()
+        _lib.check(lib.sq_space_create(n, na, na, -1, 0, -1, C.byref(h)))
+        NA = lib.sq_space_num_strings(h, 0)
+        masks = np.empty(NA, dtype=np.uint32)
+        _lib.check(lib.sq_space_export_strings(h, 0, masks.ctypes.data_as(C.POINTER(C.c_uint32))))
+        k = world.bit_length() - 1
+        prefix = masks & ((1 << k) - 1)
+        for r in range(world):
+            block = prefix[starts[r] : starts[r + 1]]
+            assert len(set(block.tolist())) <= 1, "a rank's rows must share the occupation of the first orbitals"
+        assert starts[-1] == NA
+        lib.sq_space_destroy(h)
+    with pytest.raises(ValueError):
+        partition_prefix(6, 3, 3)

@@ -270,6 +270,12 @@ def test_host_only_space_refuses_kernels():
     offs = np.array([0, 2], dtype=np.int32)
     flat = np.array([0, 1], dtype=np.int32)
     p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    # a host-only layout exists for planning (work lists, exchange plan) ...
+    _lib.check(lib.sq_layout_create(h, 1, p(codes), p(offs), p(flat), C.byref(lay)))
+    assert lib.sq_layout_num_launches(lay, 0, 1) == 1
+    # ... but no kernel may run on it
+    th = np.array([0.1])
     with pytest.raises(ValueError):
-        _lib.check(lib.sq_layout_create(h, 1, p(codes), p(offs), p(flat), C.byref(lay)))
+        _lib.check(lib.sq_ups_apply(h, lay, th.ctypes.data_as(C.POINTER(C.c_double)), 0, 1, 0, C.c_void_p(8), None))
+    lib.sq_layout_destroy(lay)
     lib.sq_space_destroy(h)
