@@ -66,6 +66,7 @@ class ShardedSpace:
         self.row_begin, self.row_end = rb, re
         self.local_len = self.ci_info.local_len
         self._barrier_token = None
+        self._plans: dict = {}
 
     # ---- shards -------------------------------------------------------------------------------
     def alloc_state(self, zero: bool = True) -> "ShardedState":
@@ -187,14 +188,23 @@ def construct_ups_state_sharded(
     lay = osa.compile_layout(sp.ci_info, ups_struct)
     th = osa._thetas_array(thetas, n_ops)
     thp = th.ctypes.data_as(C.POINTER(C.c_double))
-    for f, l, exchange in sp.exchange_plan(ups_struct, first, last, dagger):
-        if exchange:
+    key = (id(ups_struct), n_ops, first, last, bool(dagger))
+    plan = sp._plans.get(key)
+    if plan is None:
+        plan = sp.exchange_plan(ups_struct, first, last, dagger)
+        sp._plans[key] = plan
+    # a device-wide barrier separates an exchange range from its neighbours on both sides: before it every
+    # rank must have finished writing its own rows, after it the remote writes must have landed
+    prev_exchange = False
+    for f, l, exchange in plan:
+        if exchange or prev_exchange:
             sp.barrier()
         _lib.check(
             lib.sq_ups_apply_dist(sp.ci_info._handle, lay, thp, f, l, 1 if dagger else 0, state._peer_ptrs, osa._stream())
         )
-        if exchange:
-            sp.barrier()
+        prev_exchange = exchange
+    if prev_exchange:
+        sp.barrier()
 
 
 def dot_sharded(a: ShardedState, b: ShardedState) -> float:
