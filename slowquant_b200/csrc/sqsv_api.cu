@@ -866,17 +866,33 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
   exec_order(first, last, 0, &order);
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, plan_th.data(), &runs);
+  // every launch writes its <bra|T|ket> values into a device array; ONE copy back at the end of the sweep
+  std::vector<int> slot_op;   // layout operator each device slot belongs to
   for (auto& run : runs) {
+    const LayoutOp& op = lay->ops[run[0]];
+    if (is_tile_op(op)) {
+      for (int k : run)
+        for (int s = 0; s < tile_steps_of(lay->ops[k]); ++s) slot_op.push_back(k);
+    } else if (!op.null_op && op.gen >= 0) {
+      slot_op.push_back(run[0]);
+    }
+  }
+  double* d_grad = nullptr;
+  if (!slot_op.empty()) SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st));
+  int status = SQ_OK;
+  size_t slot = 0;
+  for (auto& run : runs) {
+    if (status != SQ_OK) break;
     const LayoutOp& op = lay->ops[run[0]];
     if (is_tile_op(op)) {
       TileStep steps[SQ_MAX_PROGRAM];
       int step_op[SQ_MAX_PROGRAM], n_steps = 0;
-      SQ_CHECK(run_tile(sp, lay, run, thetas_host, 0, steps, &n_steps, step_op));
+      status = run_tile(sp, lay, run, thetas_host, 0, steps, &n_steps, step_op);
+      if (status != SQ_OK) break;
       for (int s = 0; s < n_steps; ++s)
         if (std::fabs(thetas_host[step_op[s]]) < 1e-28) { steps[s].c = 1.0; steps[s].s = 0.0; }
-      double g[SQ_MAX_PROGRAM];
-      SQ_CHECK(sq_launch_tile_grad(sp, lay->pairs[op.pair], steps, n_steps, bra_dev, ket_dev, g, st));
-      for (int s = 0; s < n_steps; ++s) grad_host[step_op[s] - first] += 2.0 * g[s];
+      status = sq_launch_tile_grad(sp, lay->pairs[op.pair], steps, n_steps, bra_dev, ket_dev, d_grad + slot, st);
+      slot += n_steps;
     } else if (op.null_op) {
       continue;
     } else if (op.gen >= 0) {
@@ -884,26 +900,37 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
       double th = thetas_host[k];
       double c = std::cos(th), s = std::sin(th);
       if (std::fabs(th) < 1e-28) { c = 1.0; s = 0.0; }
-      double g = 0.0;
-      SQ_CHECK(sq_launch_gen_grad(sp, lay->gens[op.gen], c, s, bra_dev, ket_dev, &g, st));
-      grad_host[k - first] = 2.0 * g;
+      status = sq_launch_gen_grad(sp, lay->gens[op.gen], c, s, bra_dev, ket_dev, d_grad + slot, st);
+      slot += 1;
     } else if (op.multi) {
       const int k = run[0];
-      SQ_CHECK(sq_ensure_work(sp, 2));
-      SQ_CHECK(sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, ket_dev, sp->d_work[2], 0, st));
+      status = sq_ensure_work(sp, 2);
+      if (status == SQ_OK) status = sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, ket_dev, sp->d_work[2], 0, st);
       double g = 0.0;
-      SQ_CHECK(sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st));
+      if (status == SQ_OK) status = sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st);
       grad_host[k - first] = 2.0 * g;
-      if (std::fabs(thetas_host[k]) >= 1e-28) {
-        SQ_CHECK(sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st));
-        SQ_CHECK(sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st));
+      if (status == SQ_OK && std::fabs(thetas_host[k]) >= 1e-28) {
+        status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st);
+        if (status == SQ_OK) status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st);
       }
     } else {
       sq_set_error("sq_ups_grad_sweep: operator %d has no generator", run[0]);
-      return SQ_ERR_INVALID;
+      status = SQ_ERR_INVALID;
     }
   }
-  return SQ_OK;
+  if (status == SQ_OK && !slot_op.empty()) {
+    std::vector<double> g(slot_op.size());
+    cudaError_t e = cudaMemcpyAsync(g.data(), d_grad, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      sq_set_error("sq_ups_grad_sweep: %s", cudaGetErrorString(e));
+      status = SQ_ERR_CUDA;
+    } else {
+      for (size_t i = 0; i < g.size(); ++i) grad_host[slot_op[i] - first] += 2.0 * g[i];
+    }
+  }
+  if (d_grad) cudaFreeAsync(d_grad, st);
+  return status;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -368,6 +368,129 @@ tile_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, const uint3
   block_reduce_store<SQ_MAX_PROGRAM>(acc, partial, (int64_t)blockIdx.y * gridDim.x + blockIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// tile_grad_kernel_v2: the fused gradient step on the compacted work lists of tile_kernel_v2.
+// In the gauge-fixed basis every alpha/beta generator element is +1 (sigma on the pair double), so
+//   <bra|T_step|ket> = sum_tiles sum_pairs (b_tgt k_src - b_src k_tgt)
+// without per-element sign arithmetic; bra and ket tiles are rotated in registers right after.
+// ---------------------------------------------------------------------------------------------
+struct GradProgram {
+  int n;
+  int kind[SQ_MAX_PROGRAM];
+  double c[SQ_MAX_PROGRAM];
+  double s[SQ_MAX_PROGRAM];   // pair-double entries already carry sigma
+  double sig[SQ_MAX_PROGRAM]; // generator element of the step in the gauge-fixed basis (+1, or sigma)
+};
+
+#define G2_ROWS_PER_ITER 2
+
+__device__ __forceinline__ void grad_pair(double& bs, double& bt, double& ks, double& kt, double c, double s, double sig,
+                                          double& acc) {
+  acc += sig * (bt * ks - bs * kt);
+  rot(bs, bt, c, s);
+  rot(ks, kt, c, s);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+tile_grad_kernel_v2(double* __restrict__ BRA, double* __restrict__ KET, const int2* __restrict__ colItems,
+                    int n_colblk_src, const int4* __restrict__ rowItems, int n_rowchunk_src, int64_t NB,
+                    const GradProgram gp, double* __restrict__ partial) {
+  double acc[SQ_MAX_PROGRAM];
+#pragma unroll
+  for (int k = 0; k < SQ_MAX_PROGRAM; ++k) acc[k] = 0.0;
+  const bool col_src = (int)blockIdx.x < n_colblk_src;
+  const bool row_src = (int)blockIdx.y < n_rowchunk_src;
+  const int2 ci = __ldg(colItems + (int64_t)blockIdx.x * TILE_THREADS + threadIdx.x);
+  if ((col_src || row_src) && ci.x >= 0) {
+    const int64_t ib = ci.x;
+    const int64_t ibp = ci.y & 0x07ffffff;
+    const int cf = (int)((uint32_t)ci.y >> 27);
+    const int sSb = cf & 1, crb = (cf >> 1) & 1;
+    const int4* rit = rowItems + (int64_t)blockIdx.y * TILE_ROWS;
+    if (row_src && col_src) {
+#pragma unroll 1
+      for (int it = 0; it < TILE_ROWS / G2_ROWS_PER_ITER; ++it) {
+        int4 ri[G2_ROWS_PER_ITER];
+        double b[G2_ROWS_PER_ITER][4], k[G2_ROWS_PER_ITER][4];
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * G2_ROWS_PER_ITER + j);
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (ri[j].x >= 0) {
+            const int64_t o0 = (int64_t)ri[j].x * NB, o1 = (int64_t)ri[j].y * NB;
+            b[j][0] = BRA[o0 + ib]; b[j][1] = BRA[o0 + ibp]; b[j][2] = BRA[o1 + ib]; b[j][3] = BRA[o1 + ibp];
+            k[j][0] = KET[o0 + ib]; k[j][1] = KET[o0 + ibp]; k[j][2] = KET[o1 + ib]; k[j][3] = KET[o1 + ibp];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (ri[j].x >= 0) {
+            const int rf = ri[j].z;
+            const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
+            const int g10 = sSa ^ crb, g01 = sSb ^ cra, g11 = g10 ^ sSb ^ crap;
+            b[j][1] = flip(b[j][1], g01); b[j][2] = flip(b[j][2], g10); b[j][3] = flip(b[j][3], g11);
+            k[j][1] = flip(k[j][1], g01); k[j][2] = flip(k[j][2], g10); k[j][3] = flip(k[j][3], g11);
+#pragma unroll
+            for (int s = 0; s < SQ_MAX_PROGRAM; ++s) {
+              if (s >= gp.n) break;
+              const double c = gp.c[s], sn = gp.s[s], sg = gp.sig[s];
+              if (gp.kind[s] == 0) {
+                grad_pair(b[j][0], b[j][2], k[j][0], k[j][2], c, sn, sg, acc[s]);
+                grad_pair(b[j][1], b[j][3], k[j][1], k[j][3], c, sn, sg, acc[s]);
+              } else if (gp.kind[s] == 1) {
+                grad_pair(b[j][0], b[j][1], k[j][0], k[j][1], c, sn, sg, acc[s]);
+                grad_pair(b[j][2], b[j][3], k[j][2], k[j][3], c, sn, sg, acc[s]);
+              } else {
+                grad_pair(b[j][0], b[j][3], k[j][0], k[j][3], c, sn, sg, acc[s]);
+              }
+            }
+            const int64_t o0 = (int64_t)ri[j].x * NB, o1 = (int64_t)ri[j].y * NB;
+            BRA[o0 + ib] = b[j][0]; BRA[o0 + ibp] = flip(b[j][1], g01);
+            BRA[o1 + ib] = flip(b[j][2], g10); BRA[o1 + ibp] = flip(b[j][3], g11);
+            KET[o0 + ib] = k[j][0]; KET[o0 + ibp] = flip(k[j][1], g01);
+            KET[o1 + ib] = flip(k[j][2], g10); KET[o1 + ibp] = flip(k[j][3], g11);
+          }
+        }
+      }
+    } else {
+      // 2-amplitude tiles: (src row pair x inert column) feels only alpha steps, (inert row x src column pair) only beta
+      const int want = row_src ? 0 : 1;
+#pragma unroll 1
+      for (int it = 0; it < TILE_ROWS / G2_ROWS_PER_ITER; ++it) {
+        int4 ri[G2_ROWS_PER_ITER];
+        double b0[G2_ROWS_PER_ITER], b1[G2_ROWS_PER_ITER], k0[G2_ROWS_PER_ITER], k1[G2_ROWS_PER_ITER];
+        int64_t i0[G2_ROWS_PER_ITER], i1[G2_ROWS_PER_ITER];
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * G2_ROWS_PER_ITER + j);
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (ri[j].x >= 0) {
+            i0[j] = (int64_t)ri[j].x * NB + ib;
+            i1[j] = row_src ? (int64_t)ri[j].y * NB + ib : (int64_t)ri[j].x * NB + ibp;
+            b0[j] = BRA[i0[j]]; b1[j] = BRA[i1[j]]; k0[j] = KET[i0[j]]; k1[j] = KET[i1[j]];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (ri[j].x >= 0) {
+            const int g = row_src ? ((ri[j].z & 1) ^ crb) : (sSb ^ ((ri[j].z >> 1) & 1));
+            b1[j] = flip(b1[j], g);
+            k1[j] = flip(k1[j], g);
+#pragma unroll
+            for (int s = 0; s < SQ_MAX_PROGRAM; ++s) {
+              if (s >= gp.n) break;
+              if (gp.kind[s] == want) grad_pair(b0[j], b1[j], k0[j], k1[j], gp.c[s], gp.s[s], 1.0, acc[s]);
+            }
+            BRA[i0[j]] = b0[j]; BRA[i1[j]] = flip(b1[j], g);
+            KET[i0[j]] = k0[j]; KET[i1[j]] = flip(k1[j], g);
+          }
+        }
+      }
+    }
+  }
+  block_reduce_store<SQ_MAX_PROGRAM>(acc, partial, (int64_t)blockIdx.y * gridDim.x + blockIdx.x);
+}
+
 // sum partial[b*NS + k] over b for each k (one block per k, fixed order -> deterministic)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partial, int64_t nblocks,
                                                              int ns, double* __restrict__ out, double scale) {
@@ -658,10 +781,45 @@ static int finish_partials(sq_space* sp, int64_t nblocks, int ns, double scale, 
   return SQ_OK;
 }
 
+// d_out: DEVICE array of n_steps doubles receiving <bra|T_step|ket> (no host synchronisation here; the
+// sweep copies the whole gradient back once at its end)
 int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps, double* bra,
-                        double* ket, double* grad_out_host, cudaStream_t st) {
-  for (int k = 0; k < n_steps; ++k) grad_out_host[k] = 0.0;
+                        double* ket, double* d_out, cudaStream_t st) {
+  SQ_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n_steps, st));
+  if (pt.n_cross_items > 0) {
+    sq_set_error("gradient sweep: orbital pair (%d,%d) pairs rows on different devices (not supported yet)", pt.i, pt.a);
+    return SQ_ERR_UNSUPPORTED;
+  }
   if (pt.n_rows == 0) return SQ_OK;
+  if (g_tile_variant < 0) {
+    const char* e = getenv("SQ_TILE_KERNEL");
+    g_tile_variant = (e && e[0] == '1') ? 1 : 2;
+  }
+  if (n_steps < 1 || n_steps > SQ_MAX_PROGRAM) {
+    sq_set_error("tile program with %d steps (max %d)", n_steps, SQ_MAX_PROGRAM);
+    return SQ_ERR_INVALID;
+  }
+  if (g_tile_variant == 2 && pt.sigma != 0) {
+    GradProgram gp;
+    gp.n = n_steps;
+    for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
+      const bool on = k < n_steps;
+      gp.kind[k] = on ? steps[k].kind : -1;
+      const double sig = (on && steps[k].kind == 2) ? (double)pt.sigma : 1.0;
+      gp.c[k] = on ? steps[k].c : 1.0;
+      gp.s[k] = on ? sig * steps[k].s : 0.0;
+      gp.sig[k] = sig;
+    }
+    dim3 grid((unsigned)(pt.n_colblk_src + pt.n_colblk_inert), (unsigned)(pt.n_rowchunk_src + pt.n_rowchunk_inert));
+    const int64_t nblocks = (int64_t)grid.x * grid.y;
+    SQ_CHECK(sq_ensure_partial(sp, nblocks * SQ_MAX_PROGRAM + SQ_MAX_PROGRAM));
+    // the work lists hold row indices relative to the shard start, so the kernel takes the shard base pointers
+    tile_grad_kernel_v2<<<grid, TILE_THREADS, 0, st>>>(bra, ket, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
+                                                      pt.n_rowchunk_src, sp->NB, gp, sp->d_partial);
+    SQ_CHECK(check_launch("tile_grad_kernel_v2"));
+    reduce_partials_kernel<<<n_steps, 256, 0, st>>>(sp->d_partial, nblocks, SQ_MAX_PROGRAM, d_out, 1.0);
+    return check_launch("reduce_partials_kernel");
+  }
   TileProgram prog;
   SQ_CHECK(fill_program(steps, n_steps, &prog));
   dim3 grid((unsigned)((sp->NB + TILE_THREADS - 1) / TILE_THREADS), (unsigned)((pt.n_rows + TILE_ROWS - 1) / TILE_ROWS));
@@ -670,10 +828,8 @@ int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* step
   tile_grad_kernel<<<grid, TILE_THREADS, 0, st>>>(bra, ket, pt.d_codeA, pt.d_codeB, pt.d_rowsA, pt.n_rows, sp->NB,
                                                  sp->row_begin, prog, sp->d_partial);
   SQ_CHECK(check_launch("tile_grad_kernel"));
-  double tmp[SQ_MAX_PROGRAM];
-  SQ_CHECK(finish_partials(sp, nblocks, SQ_MAX_PROGRAM, 1.0, tmp, st));
-  for (int k = 0; k < n_steps; ++k) grad_out_host[k] = tmp[k];
-  return SQ_OK;
+  reduce_partials_kernel<<<n_steps, 256, 0, st>>>(sp->d_partial, nblocks, SQ_MAX_PROGRAM, d_out, 1.0);
+  return check_launch("reduce_partials_kernel");
 }
 
 int sq_launch_gen_rot(sq_space* sp, const GenTables& gt, double c, double s, double* state, cudaStream_t st) {
@@ -694,8 +850,8 @@ int sq_launch_gen_apply(sq_space* sp, const GenTables& gt, const double* in, dou
 }
 
 int sq_launch_gen_grad(sq_space* sp, const GenTables& gt, double c, double s, double* bra, double* ket,
-                       double* grad_out_host, cudaStream_t st) {
-  grad_out_host[0] = 0.0;
+                       double* d_out, cudaStream_t st) {
+  SQ_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
   if (gt.n_rows == 0 || gt.n_cols_valid == 0) return SQ_OK;
   dim3 grid((unsigned)((sp->NB + TILE_THREADS - 1) / TILE_THREADS), (unsigned)((gt.n_rows + TILE_ROWS - 1) / TILE_ROWS));
   const int64_t nblocks = (int64_t)grid.x * grid.y;
@@ -703,7 +859,8 @@ int sq_launch_gen_grad(sq_space* sp, const GenTables& gt, double c, double s, do
   gen_grad_kernel<<<grid, TILE_THREADS, 0, st>>>(bra, ket, gt.d_srcRows, gt.d_tgtRows, gt.d_sgnRows, gt.n_rows,
                                                 gt.d_colCode, sp->NB, sp->row_begin, c, s, sp->d_partial);
   SQ_CHECK(check_launch("gen_grad_kernel"));
-  return finish_partials(sp, nblocks, 1, 1.0, grad_out_host, st);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(sp->d_partial, nblocks, 1, d_out, 1.0);
+  return check_launch("reduce_partials_kernel");
 }
 
 int sq_launch_gather(sq_space* sp, const std::vector<StringAction>& strings, const std::vector<double>& coeffs,
