@@ -317,6 +317,25 @@ def golden_ucc(out: dict, meta: dict) -> None:
         "indices": [[int(x) for x in t] for t in st.excitation_indices],
     }
     print("ucc44 P =", st.n_params, flush=True)
+    # wave-function object: H2O/STO-3G UCCSD(4,4) at fixed thetas (energy, RDMs, finite-difference theta gradient)
+    from slowquant.unitary_coupled_cluster.ucc_wavefunction import WaveFunctionUCC
+
+    SQobj = _h2o()
+    WF = WaveFunctionUCC((4, 4), SQobj.hartree_fock.mo_coeff, SQobj, "SD")
+    th = np.random.default_rng(99).uniform(-0.4, 0.4, len(WF.thetas)).tolist()
+    WF.thetas = th
+    out["uccwf_thetas"] = np.array(th)
+    out["uccwf_ci"] = np.array(WF.ci_coeffs)
+    out["uccwf_energy"] = np.array(WF.energy_elec)
+    out["uccwf_rdm1"] = np.array(WF.rdm1)
+    out["uccwf_rdm2"] = np.array(WF.rdm2)
+    WF._old_opt_parameters = np.zeros(len(th)) + 10**20
+    out["uccwf_gradient"] = WF._calc_gradient_optimization(th, True, False)
+    meta["uccwf"] = {
+        "types": list(WF.ucc_layout.excitation_operator_type),
+        "indices": [[int(x) for x in t] for t in WF.ucc_layout.excitation_indices],
+    }
+    print("uccwf P =", len(th), "E =", WF.energy_elec, flush=True)
 
 
 def main() -> None:

@@ -436,3 +436,115 @@ def test_build_operator_matrix(sq):
     v = np.random.default_rng(2).normal(size=sp.num_det)
     ref = orc.propagate_state([orc.G2_sa(0, 1, 2, 3, 4)], v, sp, do_folding=False)
     assert np.max(np.abs(mat @ v - ref)) < 1e-13
+
+
+def test_config2_n2_ccpvdz_cas1010(sq):
+    """BASELINE.json config 2: N2 / cc-pVDZ oo-tUPS CAS(10,10), 63 504 determinants, real integrals exported
+    from a run of the reference (tests/golden/make_golden_n2.py): state, energy (string and RDM paths),
+    1-/2-RDM, orbital gradient (236 kappa), theta gradient."""
+    import os
+
+    from conftest import ROOT
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    d = np.load(os.path.join(ROOT, "tests", "golden", "golden_n2.npz"))
+    nI, nA, nV, na, nb = (int(x) for x in d["dims"])
+    N, M = nI + nA + nV, nI + nA
+    g = np.zeros((N, N, N, N))
+    g[:, :M, :M, :M] = d["g_npqr"]
+    g[:M, :, :M, :M] = d["g_pnqr"]
+    WF = WaveFunctionUPS((10, 10), np.eye(N), ArrayIntegrals(d["h_mo"], g, num_elec=14), "tUPS", {"n_layers": 2})
+    assert (WF.num_inactive_orbs, WF.num_active_orbs, WF.num_virtual_orbs) == (nI, nA, nV)
+    assert WF.num_det == 63504
+    assert np.array_equal(WF.kappa_idx, d["kappa_idx"])
+    th = d["thetas"].tolist()
+    WF.thetas = th
+    ci = WF.ci_coeffs
+    ref_ci = np.zeros(WF.num_det)
+    ref_ci[d["ci_nonzero_idx"]] = d["ci_nonzero_val"]
+    assert np.max(np.abs(ci - ref_ci)) < 1e-13
+    assert abs(WF.energy_elec - float(d["energy_strings"])) < 1e-10
+    assert np.max(np.abs(WF.rdm1 - d["rdm1"])) < 1e-11
+    assert np.max(np.abs(WF.rdm2 - d["rdm2"])) < 1e-11
+    from slowquant_b200.density_matrix import get_electronic_energy, get_orbital_gradient
+
+    e_rdm = get_electronic_energy(WF.h_mo, WF.g_mo, nI, nA, WF.rdm1, WF.rdm2)
+    assert abs(e_rdm - float(d["energy_rdm"])) < 1e-10
+    og = get_orbital_gradient(WF.h_mo, WF.g_mo, WF.kappa_idx, nI, nA, WF.rdm1, WF.rdm2)
+    assert np.max(np.abs(og - d["orbital_gradient"])) < 1e-10
+    tg = WF._calc_gradient_optimization(th, True, False)
+    assert np.max(np.abs(tg - d["theta_gradient"])) < 1e-10
+
+
+def test_config3_fuccsd_against_oracle_and_invariants(sq):
+    """BASELINE.json config 3 shape (fUCCSD: all singles then all doubles through the generic Givens kernel):
+    a 60-operator slice against the oracle at CAS(10,10), and invariants of the full 3381-operator ansatz at
+    CAS(14,14) (11.8M determinants): unit norm, adjoint round trip, E_sigma == E_RDM, Tr rdm1 = N_e."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    # (a) oracle slice
+    n, ne = 10, 5
+    lay = sq.UpsStructure()
+    occ_s, unocc_s = list(range(2 * ne)), list(range(2 * ne, 2 * n))
+    lay.create_fUCC(list(range(ne)), list(range(ne, n)), occ_s, unocc_s, n, {"n_layers": 1, "S": True, "D": True})
+    pick = list(range(0, 30)) + list(range(lay.n_params - 30, lay.n_params))
+    types = [lay.excitation_operator_type[k] for k in pick]
+    idx = [lay.excitation_indices[k] for k in pick]
+    rng = np.random.default_rng(31)
+    th = rng.uniform(-1.0, 1.0, len(pick))
+    sp = orc.get_indexing(0, n, 0, ne, ne)
+    info = sq.ci.get_indexing(0, n, 0, ne, ne)
+    st = rng.normal(size=sp.num_det)
+    st /= np.linalg.norm(st)
+    ref = orc.construct_ups_state(st, sp, th, types, idx, threaded=True)
+    res = sq.osa.construct_ups_state(st, info, th.tolist(), _layout(sq, types, idx))
+    assert np.max(np.abs(res - ref)) < 1e-12
+    # (b) full ansatz at CAS(14,14)
+    n, ne = 14, 7
+    lay = sq.UpsStructure()
+    lay.create_fUCC(list(range(ne)), list(range(ne, n)), list(range(2 * ne)), list(range(2 * ne, 2 * n)), n,
+                    {"n_layers": 1, "S": True, "D": True})
+    assert lay.n_params == 3381 and lay.excitation_operator_type.count("single") == 98
+    info = sq.ci.get_indexing(0, n, 0, ne, ne)
+    th = (0.05 * np.random.default_rng(14).uniform(-1, 1, lay.n_params)).tolist()
+    dev = torch.device("cuda", info.device)
+    hf = torch.zeros(info.num_det, dtype=torch.float64, device=dev)
+    hf[0] = 1.0
+    psi = sq.osa.construct_ups_state(hf, info, th, lay)
+    assert abs(float(torch.linalg.norm(psi)) - 1.0) < 1e-12
+    back = sq.osa.construct_ups_state(psi, info, th, lay, dagger=True)
+    assert float(torch.max(torch.abs(back - hf))) < 1e-12
+    rng = np.random.default_rng(2024)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    e = sq.osa.expectation_value(psi, [hamiltonian_0i_0a(h, g, 0, n)], psi, info)
+    d1, d2 = sq.osa.reduced_density_matrices(psi, psi, info)
+    assert abs(np.trace(d1) - 2 * ne) < 1e-11
+    assert abs(e - float(np.sum(h * d1) + 0.5 * np.sum(g * d2))) < 1e-10
+    assert np.max(np.abs(d2 - d2.transpose(2, 3, 0, 1))) < 1e-12
+
+
+def test_ucc_wavefunction_object(sq, golden):
+    """WaveFunctionUCC surface (ucc_wavefunction.py): UCCSD(4,4) on the H2O integrals at fixed thetas."""
+    arrays, meta, _ = golden
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ucc_wavefunction import WaveFunctionUCC
+
+    ints = ArrayIntegrals(arrays["h2o_h_mo"], arrays["h2o_g_mo"], num_elec=10)
+    WF = WaveFunctionUCC((4, 4), np.eye(arrays["h2o_h_mo"].shape[0]), ints, "SD")
+    assert WF.ucc_layout.excitation_operator_type == meta["uccwf"]["types"]
+    assert [list(t) for t in WF.ucc_layout.excitation_indices] == meta["uccwf"]["indices"]
+    th = arrays["uccwf_thetas"].tolist()
+    WF.thetas = th
+    assert np.max(np.abs(WF.ci_coeffs - arrays["uccwf_ci"])) < 1e-12
+    assert abs(WF.energy_elec - float(arrays["uccwf_energy"])) < 1e-10
+    assert np.max(np.abs(WF.rdm1 - arrays["uccwf_rdm1"])) < 1e-11
+    assert np.max(np.abs(WF.rdm2 - arrays["uccwf_rdm2"])) < 1e-11
+    # forward finite differences with step sqrt(eps): the reference's own numbers carry ~1e-7 noise
+    grad = WF._calc_gradient_optimization(th, True, False)
+    assert np.max(np.abs(grad - arrays["uccwf_gradient"])) < 5e-6

@@ -58,7 +58,7 @@ def grad():
 
 
 gth = timed("theta gradient sweep", grad)
-k = 3
+k = lay.n_params - 2
 step = 1e-5
 tp, tm = th.copy(), th.copy()
 tp[k] += step
@@ -67,4 +67,27 @@ cp = osa.construct_ups_state(csf, info, tp, lay)
 cm = osa.construct_ups_state(csf, info, tm, lay)
 ep = osa.expectation_value(cp, [H], cp, info)
 em = osa.expectation_value(cm, [H], cm, info)
-print("grad[3] =", gth[k], " finite diff =", (ep - em) / (2 * step))
+print(f"grad[{k}] =", gth[k], " finite diff =", (ep - em) / (2 * step))
+
+from slowquant_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+h_lay = osa.compile_layout(info, lay)
+touched = lib.sq_layout_touched_amplitudes(h_lay, 0, lay.n_params)
+bra = osa.construct_ups_state(sig, info, th, lay, dagger=True)
+
+
+def sweep_only():
+    b = bra.clone()
+    k_ = csf.clone()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    osa.ups_gradient_sweep(b, k_, info, th, lay)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+best = min(sweep_only() for _ in range(3))
+# ups_gradient_sweep copies its inputs (2 x 16 B/amplitude extra); subtract nothing, report as is
+print(f"gradient sweep (incl. input copies): {best*1e3:.1f} ms; algorithmic 32 B x touched = {32*touched/1e9:.2f} GB "
+      f"-> {32*touched/best/1e9:.0f} GB/s")
