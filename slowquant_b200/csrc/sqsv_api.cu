@@ -2,9 +2,13 @@
 // sweep, generic operator application.  See include/sqsv.h for the reference functions each replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "sqsv_internal.h"
+
+int sq_build_quad_tables(sq_space* sp, const PairTables& p1, const PairTables& p2, int pair1, int pair2, QuadTables* qt);
+void sq_free_quad_tables(QuadTables* qt);
 
 // ---------------------------------------------------------------------------------------------
 // table construction
@@ -194,6 +198,8 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
     sig_b = (sig_b == 0) ? f : (sig_b == f ? f : 2);
   }
   pt->sigma = (sig_a == 2 || sig_b == 2) ? 0 : ((sig_a == 0 || sig_b == 0) ? 1 : sig_a * sig_b);
+  pt->h_codeA = codeA;
+  pt->h_codeB = codeB;
   if (sp->device < 0) return SQ_OK;   // host-only layout: plan / partition logic without device tables
   SQ_CUDA(cudaSetDevice(sp->device));
   SQ_CHECK(upload(&pt->d_codeA, codeA));
@@ -422,6 +428,7 @@ extern "C" int sq_layout_destroy(sq_layout* lay) {
     cudaFree(pt.d_colItems);
     cudaFree(pt.d_rowItems);
   }
+  for (auto& kv : lay->quads) sq_free_quad_tables(&kv.second);
   for (auto& gt : lay->gens) {
     cudaFree(gt.d_srcRows);
     cudaFree(gt.d_tgtRows);
@@ -501,15 +508,66 @@ static void exec_order(int first, int last, int dagger, std::vector<int>* order)
     for (int k = last - 1; k >= first; --k) order->push_back(k);
 }
 
-extern "C" int sq_layout_num_launches(const sq_layout* lay, int first, int last) {
+// ---- quad fusion: two consecutive bricks on disjoint orbital pairs in one sweep (sqsv_quad.cu) ----
+int sq_build_quad_tables(sq_space* sp, const PairTables& p1, const PairTables& p2, int pair1, int pair2, QuadTables* qt);
+void sq_free_quad_tables(QuadTables* qt);
+
+static bool quad_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SQ_QUAD");   // SQ_QUAD=0 disables the fusion (A/B comparison, debugging)
+    const char* t = getenv("SQ_TILE_KERNEL");
+    v = ((e && e[0] == '0') || (t && t[0] == '1')) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int get_quad(sq_layout* lay, int pA, int pB, const QuadTables** out) {
+  *out = nullptr;
+  if (pA < 0 || pB < 0 || pA == pB) return SQ_OK;
+  auto key = std::make_pair(pA, pB);
+  auto it = lay->quads.find(key);
+  if (it == lay->quads.end()) {
+    QuadTables qt;
+    SQ_CHECK(sq_build_quad_tables(lay->sp, lay->pairs[pA], lay->pairs[pB], pA, pB, &qt));
+    it = lay->quads.emplace(key, qt).first;
+  }
+  *out = &it->second;
+  return SQ_OK;
+}
+
+// launches of a run list after quad fusion: entry = (run index, partner run index or -1)
+static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<std::pair<int, int>>* out) {
+  out->clear();
+  for (size_t ri = 0; ri < runs.size(); ++ri) {
+    const LayoutOp& op = lay->ops[runs[ri][0]];
+    if (is_tile_op(op) && ri + 1 < runs.size() && is_tile_op(lay->ops[runs[ri + 1][0]]) && quad_enabled()) {
+      const QuadTables* qt = nullptr;
+      SQ_CHECK(get_quad(lay, op.pair, lay->ops[runs[ri + 1][0]].pair, &qt));
+      if (qt && qt->ok) {
+        out->push_back({(int)ri, (int)ri + 1});
+        ++ri;
+        continue;
+      }
+    }
+    out->push_back({(int)ri, -1});
+  }
+  return SQ_OK;
+}
+
+extern "C" int sq_layout_num_launches(const sq_layout* lay_c, int first, int last) {
+  sq_layout* lay = const_cast<sq_layout*>(lay_c);
   if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
   std::vector<double> th(lay->ops.size(), 1.0);
   std::vector<int> order;
   exec_order(first, last, 0, &order);
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, th.data(), &runs);
+  std::vector<std::pair<int, int>> launches;
+  if (plan_launches(lay, runs, &launches) != SQ_OK) return -1;
   int n = 0;
-  for (auto& r : runs) {
+  for (auto& l : launches) {
+    const std::vector<int>& r = runs[l.first];
     const LayoutOp& op = lay->ops[r[0]];
     if (is_tile_op(op)) n += 1;
     else if (op.gen >= 0) n += 1;
@@ -523,18 +581,24 @@ extern "C" int sq_layout_num_launches(const sq_layout* lay, int first, int last)
 
 // amplitudes read+written by the launches of ops [first,last): the algorithmic traffic of sq_ups_apply is
 // 16 bytes (one fp64 read + one fp64 write) per touched amplitude per launch.
-extern "C" int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last) {
+extern "C" int64_t sq_layout_touched_amplitudes(const sq_layout* lay_c, int first, int last) {
+  sq_layout* lay = const_cast<sq_layout*>(lay_c);
   if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
   std::vector<double> th(lay->ops.size(), 1.0);
   std::vector<int> order;
   exec_order(first, last, 0, &order);
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, th.data(), &runs);
+  std::vector<std::pair<int, int>> launches;
+  if (plan_launches(lay, runs, &launches) != SQ_OK) return -1;
   const sq_space* sp = lay->sp;
   int64_t total = 0;
-  for (auto& r : runs) {
+  for (auto& l : launches) {
+    const std::vector<int>& r = runs[l.first];
     const LayoutOp& op = lay->ops[r[0]];
-    if (is_tile_op(op)) {
+    if (l.second >= 0) {
+      total += lay->quads[{op.pair, lay->ops[runs[l.second][0]].pair}].touched;
+    } else if (is_tile_op(op)) {
       const PairTables& pt = lay->pairs[op.pair];
       bool has_single = false;
       for (int k : r) has_single |= !lay->ops[k].pair_double;
@@ -779,12 +843,28 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
   exec_order(first, last, dagger, &order);
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, thetas_host, &runs);
-  for (auto& run : runs) {
+  for (size_t ri = 0; ri < runs.size(); ++ri) {
+    auto& run = runs[ri];
     const LayoutOp& op = lay->ops[run[0]];
     if (is_tile_op(op)) {
       TileStep steps[SQ_MAX_PROGRAM];
       int step_op[SQ_MAX_PROGRAM], n_steps = 0;
       SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
+      // two consecutive bricks on disjoint orbital pairs commute: one sweep for both (sqsv_quad.cu)
+      if (ri + 1 < runs.size() && is_tile_op(lay->ops[runs[ri + 1][0]]) && quad_enabled()) {
+        const int pA = op.pair, pB = lay->ops[runs[ri + 1][0]].pair;
+        const QuadTables* qt = nullptr;
+        SQ_CHECK(get_quad(lay, pA, pB, &qt));
+        if (qt && qt->ok) {
+          TileStep steps2[SQ_MAX_PROGRAM];
+          int step_op2[SQ_MAX_PROGRAM], n_steps2 = 0;
+          SQ_CHECK(run_tile(sp, lay, runs[ri + 1], thetas_host, dagger, steps2, &n_steps2, step_op2));
+          SQ_CHECK(sq_launch_quad(sp, *qt, steps, n_steps, lay->pairs[pA].sigma, steps2, n_steps2, lay->pairs[pB].sigma,
+                                  state_dev, st));
+          ++ri;
+          continue;
+        }
+      }
       SQ_CHECK(sq_launch_tile(sp, lay->pairs[op.pair], steps, n_steps, state_dev, peers, st));
     } else if (op.null_op) {
       continue;

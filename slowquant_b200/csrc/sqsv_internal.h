@@ -65,6 +65,7 @@ struct PairTables {       // tables for one spatial orbital pair (i,a)
   int i, a;
   uint32_t* d_codeA = nullptr;   // [NA]
   uint32_t* d_codeB = nullptr;   // [NB]
+  std::vector<uint32_t> h_codeA, h_codeB;   // host copies (quad work lists are derived from them)
   int32_t* d_rowsA = nullptr;    // alpha rows that are src or inert (tgt rows ride with their src)
   int64_t n_rows = 0;            // local row items
   int64_t n_src_rows = 0, n_src_cols = 0;
@@ -81,6 +82,22 @@ struct PairTables {       // tables for one spatial orbital pair (i,a)
   int sigma = 0;                 // gauge-invariant pair-double sign (+1/-1) if uniform, 0 otherwise
   bool cross_global = false;     // some row pair of this orbital pair spans two devices (same answer on every rank)
   int64_t n_cross_items = 0;     // cross-device row pairs this rank works on (half of the columns each)
+};
+
+// Work lists for TWO commuting bricks (disjoint orbital pairs P1, P2) applied in one sweep.  A string is
+// active (src/tgt) or inert in each pair; its group holds 1, 2 or 4 strings (index a = a1*2 + a2, a_k = 0 src /
+// 1 tgt in pair k).  Lists are sorted by group type t = 2*active(P1) + active(P2) in the order 3,2,1,0 and
+// padded per type, so every CTA is type-homogeneous in rows and in columns.
+struct QuadTables {
+  bool ok = false;               // false: flags are not pair-local for this combination -> no quad fusion
+  int pair1 = -1, pair2 = -1;
+  int4* d_colIdx = nullptr;      // 4 string indices per column group (-1 = absent / pad)
+  int* d_colFlags = nullptr;     // bits 0-2: sSb1, crb1(b1=0 or inert), crbp1 ; bits 4-6: same for pair 2
+  int4* d_rowIdx = nullptr;      // row indices relative to the shard start
+  int* d_rowFlags = nullptr;     // bits 0-2: sSa1, cra1, crap1 ; bits 4-6: pair 2
+  int colblk_end[4] = {0, 0, 0, 0};    // cumulative CTA counts after types 3,2,1,0
+  int rowchunk_end[4] = {0, 0, 0, 0};
+  int64_t touched = 0;
 };
 
 #define SQ_MAX_WORLD 16
@@ -138,6 +155,7 @@ struct sq_layout {
   std::map<std::pair<int, int>, int> pair_index;
   std::vector<GenTables> gens;
   std::map<std::vector<int>, int> gen_index;
+  std::map<std::pair<int, int>, QuadTables> quads;   // built lazily per (pair1, pair2)
 };
 
 static inline int sq_row_owner(const sq_space* sp, int64_t row) {
@@ -161,6 +179,8 @@ int sq_ensure_partial(sq_space* sp, int64_t n);
 struct TileStep { int kind; double c, s; };   // kind: 0 alpha-rot, 1 beta-rot, 2 pair-double rot
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                    double* state, const PeerPtrs* peers, cudaStream_t st);
+int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, int n1, int sigma1,
+                   const TileStep* steps2, int n2, int sigma2, double* state, cudaStream_t st);
 int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                         double* bra, double* ket, double* grad_out_host, cudaStream_t st);
 int sq_launch_gen_rot(sq_space* sp, const GenTables& gt, double c, double s, double* state,
