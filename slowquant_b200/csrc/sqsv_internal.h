@@ -119,6 +119,8 @@ struct sq_space {
   int64_t row_begin, row_end;       // local alpha rows
   int world = 1, rank = 0;          // alpha-row partition over devices (sq_space_set_partition)
   std::vector<int64_t> row_starts;  // [world + 1]; rank r owns rows [row_starts[r], row_starts[r+1])
+  unsigned long long* d_peer_tab = nullptr;             // device table of shard base pointers (cross-device tiles)
+  unsigned long long peer_shadow[16] = {0};             // last uploaded table
   uint64_t binom[SQ_MAX_ORB + 2][SQ_MAX_ORB + 2];
   std::vector<uint32_t> strA, strB; // occupation masks in itertools.combinations order
   std::vector<int32_t> rankA, rankB;  // mask -> string index (-1 if wrong electron count); 2^n entries

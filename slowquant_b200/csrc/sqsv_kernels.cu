@@ -2,8 +2,10 @@
 // bandwidth: amplitudes are read and written exactly once per launch with fully coalesced 8-byte lanes
 // along the beta-string (column) axis; sign / partner tables are 4-byte-per-string codes that stay in
 // L1/L2.  No tensor-core shapes exist on this path (it is integer address work + 2x2 rotations).
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "sqsv_internal.h"
 
@@ -138,19 +140,34 @@ __device__ __forceinline__ double flip(double x, int neg) {
 // Row pointers: a row item names the owner rank of each of its two rows; `bases` holds the peer-mapped
 // base pointer of every rank's shard (NVLink P2P), so a tile whose rows live on two GPUs is rotated in
 // place by plain loads/stores on local + remote memory.  On one GPU both owners are rank 0.
-__device__ __forceinline__ double* rowp0(const PeerPtrs& b, const int4& ri, int64_t NB) {
-  return b.p[(ri.z >> 8) & 0xff] + (int64_t)ri.x * NB;
+// PEER = false (one GPU, or a sharded operator whose pairs are all local): rows are offsets from the local
+// shard.  PEER = true: the owner's base pointer comes from a 16-entry device table (an indexed kernel-parameter
+// array would be spilled to local memory).
+template <bool PEER>
+struct Bases {
+  double* C;
+  const unsigned long long* tab;
+};
+template <bool PEER>
+__device__ __forceinline__ double* rowp0(const Bases<PEER>& b, const int4& ri, int64_t NB) {
+  if (PEER) return reinterpret_cast<double*>(__ldg(b.tab + ((ri.z >> 8) & 0xff))) + (int64_t)ri.x * NB;
+  return b.C + (int64_t)ri.x * NB;
 }
-__device__ __forceinline__ double* rowp1(const PeerPtrs& b, const int4& ri, int64_t NB) {
-  return b.p[(ri.z >> 16) & 0xff] + (int64_t)ri.y * NB;
+template <bool PEER>
+__device__ __forceinline__ double* rowp1(const Bases<PEER>& b, const int4& ri, int64_t NB) {
+  if (PEER) return reinterpret_cast<double*>(__ldg(b.tab + ((ri.z >> 16) & 0xff))) + (int64_t)ri.y * NB;
+  return b.C + (int64_t)ri.y * NB;
 }
 // pad entries have x < 0; cross-device pairs are split between the two owners by column-CTA parity (w = 1 / 2)
+template <bool PEER>
 __device__ __forceinline__ bool item_on(const int4& ri) {
-  return ri.x >= 0 && (ri.w == 0 || (int)(blockIdx.x & 1u) == ri.w - 1);
+  if (PEER) return ri.x >= 0 && (ri.w == 0 || (int)(blockIdx.x & 1u) == ri.w - 1);
+  return ri.x >= 0;
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(TILE_THREADS)
-tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_colblk_src,
+tile_kernel_v2(const Bases<PEER> bases, const int2* __restrict__ colItems, int n_colblk_src,
                const int4* __restrict__ rowItems, int n_rowchunk_src, int64_t NB, const TileMatrices tm) {
   const bool col_src = (int)blockIdx.x < n_colblk_src;
   const bool row_src = (int)blockIdx.y < n_rowchunk_src;
@@ -172,7 +189,7 @@ tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_co
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (item_on(ri[j])) {
+        if (item_on<PEER>(ri[j])) {
           const double* r0 = rowp0(bases, ri[j], NB);
           const double* r1 = rowp1(bases, ri[j], NB);
           x00[j] = r0[ib];
@@ -183,7 +200,7 @@ tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_co
       }
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (item_on(ri[j])) {
+        if (item_on<PEER>(ri[j])) {
           const int rf = ri[j].z;
           const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
           const int g10 = sSa ^ crb;            // sgA0
@@ -212,14 +229,14 @@ tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_co
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (item_on(ri[j])) {
+        if (item_on<PEER>(ri[j])) {
           x0[j] = rowp0(bases, ri[j], NB)[ib];
           x1[j] = rowp1(bases, ri[j], NB)[ib];
         }
       }
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (item_on(ri[j])) {
+        if (item_on<PEER>(ri[j])) {
           const int g = (ri[j].z & 1) ^ crb;   // sSa * crossB(column)
           const double a = x0[j], b = flip(x1[j], g);
           rowp0(bases, ri[j], NB)[ib] = tm.ca * a - tm.sa * b;
@@ -236,7 +253,7 @@ tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_co
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * V2_ROWS_PER_ITER + j);
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (item_on(ri[j])) {
+        if (item_on<PEER>(ri[j])) {
           const double* r0 = rowp0(bases, ri[j], NB);
           x0[j] = r0[ib];
           x1[j] = r0[ibp];
@@ -244,7 +261,7 @@ tile_kernel_v2(const PeerPtrs bases, const int2* __restrict__ colItems, int n_co
       }
 #pragma unroll
       for (int j = 0; j < V2_ROWS_PER_ITER; ++j) {
-        if (item_on(ri[j])) {
+        if (item_on<PEER>(ri[j])) {
           const int g = sSb ^ ((ri[j].z >> 1) & 1);   // sSb * crossA(row)
           const double a = x0[j], b = flip(x1[j], g);
           double* r0 = rowp0(bases, ri[j], NB);
@@ -742,9 +759,22 @@ int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, in
     return SQ_ERR_UNSUPPORTED;
   }
   if ((g_tile_variant == 2 || peers) && pt.sigma != 0) {
-    PeerPtrs bases;
-    for (int r = 0; r < SQ_MAX_WORLD; ++r) bases.p[r] = peers ? peers->p[r] : nullptr;
-    bases.p[sp->rank] = state;
+    const bool use_peers = peers && pt.n_cross_items > 0;
+    if (use_peers) {
+      // (re)upload the 16-entry base-pointer table only when it changes; the staging words are pinned, so the
+      // stream is drained before they are overwritten
+      unsigned long long tab[SQ_MAX_WORLD];
+      for (int r = 0; r < SQ_MAX_WORLD; ++r) tab[r] = (unsigned long long)(uintptr_t)peers->p[r];
+      tab[sp->rank] = (unsigned long long)(uintptr_t)state;
+      if (!sp->d_peer_tab) SQ_CUDA(cudaMalloc(&sp->d_peer_tab, sizeof(tab)));
+      if (memcmp(tab, sp->peer_shadow, sizeof(tab)) != 0) {
+        SQ_CUDA(cudaStreamSynchronize(st));
+        unsigned long long* stage = reinterpret_cast<unsigned long long*>(sp->h_pinned + 4096 - SQ_MAX_WORLD);
+        memcpy(stage, tab, sizeof(tab));
+        memcpy(sp->peer_shadow, tab, sizeof(tab));
+        SQ_CUDA(cudaMemcpyAsync(sp->d_peer_tab, stage, sizeof(tab), cudaMemcpyHostToDevice, st));
+      }
+    }
     if (n_steps < 1 || n_steps > SQ_MAX_PROGRAM) {
       sq_set_error("tile program with %d steps (max %d)", n_steps, SQ_MAX_PROGRAM);
       return SQ_ERR_INVALID;
@@ -758,8 +788,15 @@ int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, in
     const int gy = any_single ? pt.n_rowchunk_src + pt.n_rowchunk_inert : pt.n_rowchunk_src;
     if (gx == 0 || gy == 0) return SQ_OK;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    tile_kernel_v2<<<grid, TILE_THREADS, 0, st>>>(bases, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
-                                                 pt.n_rowchunk_src, sp->NB, tm);
+    if (use_peers) {
+      Bases<true> bases{state, sp->d_peer_tab};
+      tile_kernel_v2<true><<<grid, TILE_THREADS, 0, st>>>(bases, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
+                                                         pt.n_rowchunk_src, sp->NB, tm);
+    } else {
+      Bases<false> bases{state, nullptr};
+      tile_kernel_v2<false><<<grid, TILE_THREADS, 0, st>>>(bases, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems,
+                                                          pt.n_rowchunk_src, sp->NB, tm);
+    }
     return check_launch("tile_kernel_v2");
   }
   TileProgram prog;

@@ -135,6 +135,7 @@ extern "C" int sq_space_destroy(sq_space* sp) {
   cudaFree(sp->d_rankA);
   cudaFree(sp->d_rankB);
   cudaFree(sp->d_partial);
+  cudaFree(sp->d_peer_tab);
   for (int i = 0; i < 3; ++i) cudaFree(sp->d_work[i]);
   if (sp->h_pinned) cudaFreeHost(sp->h_pinned);
   delete sp;
