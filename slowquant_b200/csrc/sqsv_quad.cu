@@ -12,10 +12,13 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cuda_pipeline.h>
+
 #include "sqsv_internal.h"
 
 #define QUAD_THREADS 128
-#define QUAD_ROWS 4
+#define QUAD_ROWS 8
+#define QUAD_STAGES 3
 
 struct QuadMats {
   double m1[16], m2[16];   // gauge-fixed 4x4 brick matrices, basis (x00, x01, x10, x11) = (row, column) index in the pair
@@ -41,9 +44,31 @@ __device__ __forceinline__ void rot2(double& a, double& b, double c, double s, i
 }
 
 // R1/R2: the row group is active in pair 1 / 2; C1/C2: same for the column group
+// Asynchronous tile fetch: every thread copies the amplitudes of ITS tile into its private slots of a shared
+// memory stage with cp.async (8 bytes each).  Nothing is held in registers while the loads are in flight, so
+// several row groups per thread can be outstanding at once (deep memory-level parallelism at ~70 registers),
+// and because a thread only ever reads back its own slots no block-wide barrier is needed.
+template <bool R1, bool R2, bool C1, bool C2>
+__device__ __forceinline__ void quad_issue(const double* __restrict__ C, int64_t NB, const int4 rw, const int4 cl,
+                                           double* __restrict__ sm) {
+  constexpr int NR1 = R1 ? 2 : 1, NR2 = R2 ? 2 : 1, NC1 = C1 ? 2 : 1, NC2 = C2 ? 2 : 1;
+#pragma unroll
+  for (int a1 = 0; a1 < NR1; ++a1)
+#pragma unroll
+    for (int a2 = 0; a2 < NR2; ++a2) {
+      const double* row = C + (int64_t)comp(rw, a1 * 2 + a2) * NB;
+#pragma unroll
+      for (int b1 = 0; b1 < NC1; ++b1)
+#pragma unroll
+        for (int b2 = 0; b2 < NC2; ++b2)
+          __pipeline_memcpy_async(sm + (((a1 * NR2 + a2) * NC1 + b1) * NC2 + b2) * QUAD_THREADS,
+                                  row + comp(cl, b1 * 2 + b2), sizeof(double));
+    }
+}
+
 template <bool R1, bool R2, bool C1, bool C2>
 __device__ __forceinline__ void quad_tile(double* __restrict__ C, int64_t NB, const int4 rw, const int rf, const int4 cl,
-                                          const int cf, const QuadMats& qm) {
+                                          const int cf, const QuadMats& qm, const double* __restrict__ sm) {
   constexpr int NR1 = R1 ? 2 : 1, NR2 = R2 ? 2 : 1, NC1 = C1 ? 2 : 1, NC2 = C2 ? 2 : 1;
   double x[NR1][NR2][NC1][NC2];
   int64_t ro[NR1][NR2];
@@ -63,7 +88,7 @@ __device__ __forceinline__ void quad_tile(double* __restrict__ C, int64_t NB, co
 #pragma unroll
       for (int b1 = 0; b1 < NC1; ++b1)
 #pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2) x[a1][a2][b1][b2] = C[ro[a1][a2] + co[b1][b2]];
+        for (int b2 = 0; b2 < NC2; ++b2) x[a1][a2][b1][b2] = sm[(((a1 * NR2 + a2) * NC1 + b1) * NC2 + b2) * QUAD_THREADS];
   // ---- brick 1: acts on (a1, b1) for every (a2, b2) ----
   {
     const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
@@ -142,11 +167,27 @@ template <bool R1, bool R2, bool C1, bool C2>
 __device__ __forceinline__ void quad_rows(double* __restrict__ C, int64_t NB, const int4* __restrict__ rowIdx,
                                           const int* __restrict__ rowFlags, int64_t r0, const int4 cl, const int cf,
                                           const QuadMats& qm) {
+  extern __shared__ double quad_smem[];
+  double* mine = quad_smem + threadIdx.x;   // slot s of stage t lives at mine[(t * 16 + s) * QUAD_THREADS]
+  // software pipeline over the CTA's row groups: QUAD_STAGES - 1 fetches are always in flight
+#pragma unroll
+  for (int j = 0; j < QUAD_STAGES - 1; ++j) {
+    const int4 rw = __ldg(rowIdx + r0 + j);
+    if (rw.x >= 0) quad_issue<R1, R2, C1, C2>(C, NB, rw, cl, mine + (j % QUAD_STAGES) * 16 * QUAD_THREADS);
+    __pipeline_commit();
+  }
 #pragma unroll 1
   for (int j = 0; j < QUAD_ROWS; ++j) {
+    const int jn = j + QUAD_STAGES - 1;
+    if (jn < QUAD_ROWS) {
+      const int4 rn = __ldg(rowIdx + r0 + jn);
+      if (rn.x >= 0) quad_issue<R1, R2, C1, C2>(C, NB, rn, cl, mine + (jn % QUAD_STAGES) * 16 * QUAD_THREADS);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(QUAD_STAGES - 1);   // the fetch of row group j has landed
     const int4 rw = __ldg(rowIdx + r0 + j);
     if (rw.x < 0) continue;
-    quad_tile<R1, R2, C1, C2>(C, NB, rw, __ldg(rowFlags + r0 + j), cl, cf, qm);
+    quad_tile<R1, R2, C1, C2>(C, NB, rw, __ldg(rowFlags + r0 + j), cl, cf, qm, mine + (j % QUAD_STAGES) * 16 * QUAD_THREADS);
   }
 }
 
@@ -364,7 +405,14 @@ int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, i
                    qt.rowchunk_end[0], qt.rowchunk_end[1], qt.rowchunk_end[2], qt.rowchunk_end[3]};
   if (qb.c0 == 0 || qb.r0 == 0) return SQ_OK;
   dim3 grid((unsigned)qb.c0, (unsigned)qb.r0);
-  quad_kernel<<<grid, QUAD_THREADS, 0, st>>>(state, qt.d_colIdx, qt.d_colFlags, qt.d_rowIdx, qt.d_rowFlags, sp->NB, qb, qm);
+  const size_t smem = sizeof(double) * QUAD_STAGES * 16 * QUAD_THREADS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  quad_kernel<<<grid, QUAD_THREADS, smem, st>>>(state, qt.d_colIdx, qt.d_colFlags, qt.d_rowIdx, qt.d_rowFlags, sp->NB, qb,
+                                               qm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     sq_set_error("quad_kernel launch failed: %s", cudaGetErrorString(e));
