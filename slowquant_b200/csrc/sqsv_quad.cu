@@ -17,7 +17,7 @@
 #include "sqsv_internal.h"
 
 #define QUAD_THREADS 128
-#define QUAD_ROWS 8
+#define QUAD_ROWS 16
 #define QUAD_STAGES 3
 
 struct QuadMats {
@@ -169,25 +169,38 @@ __device__ __forceinline__ void quad_rows(double* __restrict__ C, int64_t NB, co
                                           const QuadMats& qm) {
   extern __shared__ double quad_smem[];
   double* mine = quad_smem + threadIdx.x;   // slot s of stage t lives at mine[(t * 16 + s) * QUAD_THREADS]
-  // software pipeline over the CTA's row groups: QUAD_STAGES - 1 fetches are always in flight
+  // A stage always carries 16 amplitudes per thread: one 4x4 tile, two 2x4 tiles, ... eight 1x2 tiles, so
+  // the small tile shapes keep as many bytes in flight as the big one.
+  constexpr int TILE = (R1 ? 2 : 1) * (R2 ? 2 : 1) * (C1 ? 2 : 1) * (C2 ? 2 : 1);
+  constexpr int G = (16 / TILE > 8) ? 8 : 16 / TILE;     // row groups per stage
+  constexpr int NB_ = QUAD_ROWS / G;                     // batches per CTA
+  auto issue_batch = [&](int b) {
+    double* st = mine + (b % QUAD_STAGES) * 16 * QUAD_THREADS;
 #pragma unroll
-  for (int j = 0; j < QUAD_STAGES - 1; ++j) {
-    const int4 rw = __ldg(rowIdx + r0 + j);
-    if (rw.x >= 0) quad_issue<R1, R2, C1, C2>(C, NB, rw, cl, mine + (j % QUAD_STAGES) * 16 * QUAD_THREADS);
+    for (int g = 0; g < G; ++g) {
+      const int4 rw = __ldg(rowIdx + r0 + b * G + g);
+      if (rw.x >= 0) quad_issue<R1, R2, C1, C2>(C, NB, rw, cl, st + g * TILE * QUAD_THREADS);
+    }
+  };
+  // software pipeline over the batches: QUAD_STAGES - 1 fetches are always in flight
+#pragma unroll
+  for (int b = 0; b < QUAD_STAGES - 1; ++b) {
+    if (b < NB_) issue_batch(b);
     __pipeline_commit();
   }
 #pragma unroll 1
-  for (int j = 0; j < QUAD_ROWS; ++j) {
-    const int jn = j + QUAD_STAGES - 1;
-    if (jn < QUAD_ROWS) {
-      const int4 rn = __ldg(rowIdx + r0 + jn);
-      if (rn.x >= 0) quad_issue<R1, R2, C1, C2>(C, NB, rn, cl, mine + (jn % QUAD_STAGES) * 16 * QUAD_THREADS);
-    }
+  for (int b = 0; b < NB_; ++b) {
+    const int bn = b + QUAD_STAGES - 1;
+    if (bn < NB_) issue_batch(bn);
     __pipeline_commit();
-    __pipeline_wait_prior(QUAD_STAGES - 1);   // the fetch of row group j has landed
-    const int4 rw = __ldg(rowIdx + r0 + j);
-    if (rw.x < 0) continue;
-    quad_tile<R1, R2, C1, C2>(C, NB, rw, __ldg(rowFlags + r0 + j), cl, cf, qm, mine + (j % QUAD_STAGES) * 16 * QUAD_THREADS);
+    __pipeline_wait_prior(QUAD_STAGES - 1);   // the fetch of batch b has landed
+    const double* st = mine + (b % QUAD_STAGES) * 16 * QUAD_THREADS;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int4 rw = __ldg(rowIdx + r0 + b * G + g);
+      if (rw.x < 0) continue;
+      quad_tile<R1, R2, C1, C2>(C, NB, rw, __ldg(rowFlags + r0 + b * G + g), cl, cf, qm, st + g * TILE * QUAD_THREADS);
+    }
   }
 }
 
