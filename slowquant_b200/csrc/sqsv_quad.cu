@@ -9,6 +9,12 @@
 // brick 2, and writes it back.  One read + one write of the vector for SIX ansatz operators; almost no
 // amplitude is inert in both pairs, so the 32-byte sectors that an isolated high-orbital brick drags along
 // without using are used here.
+//
+// Data movement: a batch always carries 16 amplitudes per thread (one 4x4 tile, two 2x4 tiles, ... eight
+// 1x2 tiles), all loads of a batch are issued before the first store.  QUAD_ASYNC = 1 fetches through
+// cp.async into per-thread shared-memory slots with a multi-stage pipeline instead of registers; on B200
+// the 8-byte LDGSTS path turned out to be issue-limited (~8 cycles per warp instruction), so plain LDG is the
+// default.
 #include <cstdio>
 #include <cstdlib>
 
@@ -16,7 +22,20 @@
 
 #include "sqsv_internal.h"
 
+#ifndef QUAD_ASYNC
+#define QUAD_ASYNC 0
+#endif
+#if QUAD_ASYNC
 #define QUAD_THREADS 128
+#define QUAD_MINBLOCKS 1
+#else
+#ifndef QUAD_THREADS
+#define QUAD_THREADS 256
+#endif
+#ifndef QUAD_MINBLOCKS
+#define QUAD_MINBLOCKS 3     // <= 85 registers per thread -> 24 resident warps per SM
+#endif
+#endif
 #define QUAD_ROWS 16
 #define QUAD_STAGES 3
 
@@ -43,52 +62,70 @@ __device__ __forceinline__ void rot2(double& a, double& b, double c, double s, i
   b = qflip(c * y + s * x, g);
 }
 
-// R1/R2: the row group is active in pair 1 / 2; C1/C2: same for the column group
-// Asynchronous tile fetch: every thread copies the amplitudes of ITS tile into its private slots of a shared
-// memory stage with cp.async (8 bytes each).  Nothing is held in registers while the loads are in flight, so
-// several row groups per thread can be outstanding at once (deep memory-level parallelism at ~70 registers),
-// and because a thread only ever reads back its own slots no block-wide barrier is needed.
+// R1/R2: the row group is active in pair 1 / 2; C1/C2: same for the column group.
+// Flat tile index: ((a1 * NR2 + a2) * NC1 + b1) * NC2 + b2.
 template <bool R1, bool R2, bool C1, bool C2>
-__device__ __forceinline__ void quad_issue(const double* __restrict__ C, int64_t NB, const int4 rw, const int4 cl,
-                                           double* __restrict__ sm) {
-  constexpr int NR1 = R1 ? 2 : 1, NR2 = R2 ? 2 : 1, NC1 = C1 ? 2 : 1, NC2 = C2 ? 2 : 1;
+struct Shape {
+  static constexpr int NR1 = R1 ? 2 : 1, NR2 = R2 ? 2 : 1, NC1 = C1 ? 2 : 1, NC2 = C2 ? 2 : 1;
+  static constexpr int TILE = NR1 * NR2 * NC1 * NC2;
+  static constexpr int G = (16 / TILE > 8) ? 8 : 16 / TILE;   // row groups per batch
+  __device__ static constexpr int at(int a1, int a2, int b1, int b2) { return ((a1 * NR2 + a2) * NC1 + b1) * NC2 + b2; }
+};
+
+template <bool R1, bool R2, bool C1, bool C2>
+__device__ __forceinline__ void quad_load(const double* __restrict__ C, int64_t NB, const int4 rw, const int4 cl,
+                                          double* __restrict__ x) {
+  using S = Shape<R1, R2, C1, C2>;
 #pragma unroll
-  for (int a1 = 0; a1 < NR1; ++a1)
+  for (int a1 = 0; a1 < S::NR1; ++a1)
 #pragma unroll
-    for (int a2 = 0; a2 < NR2; ++a2) {
+    for (int a2 = 0; a2 < S::NR2; ++a2) {
       const double* row = C + (int64_t)comp(rw, a1 * 2 + a2) * NB;
 #pragma unroll
-      for (int b1 = 0; b1 < NC1; ++b1)
+      for (int b1 = 0; b1 < S::NC1; ++b1)
 #pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2)
-          __pipeline_memcpy_async(sm + (((a1 * NR2 + a2) * NC1 + b1) * NC2 + b2) * QUAD_THREADS,
-                                  row + comp(cl, b1 * 2 + b2), sizeof(double));
+        for (int b2 = 0; b2 < S::NC2; ++b2) x[S::at(a1, a2, b1, b2)] = row[comp(cl, b1 * 2 + b2)];
     }
 }
 
 template <bool R1, bool R2, bool C1, bool C2>
-__device__ __forceinline__ void quad_tile(double* __restrict__ C, int64_t NB, const int4 rw, const int rf, const int4 cl,
-                                          const int cf, const QuadMats& qm, const double* __restrict__ sm) {
-  constexpr int NR1 = R1 ? 2 : 1, NR2 = R2 ? 2 : 1, NC1 = C1 ? 2 : 1, NC2 = C2 ? 2 : 1;
-  double x[NR1][NR2][NC1][NC2];
-  int64_t ro[NR1][NR2];
-  int64_t co[NC1][NC2];
+__device__ __forceinline__ void quad_issue(const double* __restrict__ C, int64_t NB, const int4 rw, const int4 cl,
+                                           double* __restrict__ sm) {
+  using S = Shape<R1, R2, C1, C2>;
 #pragma unroll
-  for (int a1 = 0; a1 < NR1; ++a1)
+  for (int a1 = 0; a1 < S::NR1; ++a1)
 #pragma unroll
-    for (int a2 = 0; a2 < NR2; ++a2) ro[a1][a2] = (int64_t)comp(rw, a1 * 2 + a2) * NB;
+    for (int a2 = 0; a2 < S::NR2; ++a2) {
+      const double* row = C + (int64_t)comp(rw, a1 * 2 + a2) * NB;
 #pragma unroll
-  for (int b1 = 0; b1 < NC1; ++b1)
+      for (int b1 = 0; b1 < S::NC1; ++b1)
 #pragma unroll
-    for (int b2 = 0; b2 < NC2; ++b2) co[b1][b2] = comp(cl, b1 * 2 + b2);
+        for (int b2 = 0; b2 < S::NC2; ++b2)
+          __pipeline_memcpy_async(sm + S::at(a1, a2, b1, b2) * QUAD_THREADS, row + comp(cl, b1 * 2 + b2), sizeof(double));
+    }
+}
+
+template <bool R1, bool R2, bool C1, bool C2>
+__device__ __forceinline__ void quad_store(double* __restrict__ C, int64_t NB, const int4 rw, const int4 cl,
+                                           const double* __restrict__ x) {
+  using S = Shape<R1, R2, C1, C2>;
 #pragma unroll
-  for (int a1 = 0; a1 < NR1; ++a1)
+  for (int a1 = 0; a1 < S::NR1; ++a1)
 #pragma unroll
-    for (int a2 = 0; a2 < NR2; ++a2)
+    for (int a2 = 0; a2 < S::NR2; ++a2) {
+      double* row = C + (int64_t)comp(rw, a1 * 2 + a2) * NB;
 #pragma unroll
-      for (int b1 = 0; b1 < NC1; ++b1)
+      for (int b1 = 0; b1 < S::NC1; ++b1)
 #pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2) x[a1][a2][b1][b2] = sm[(((a1 * NR2 + a2) * NC1 + b1) * NC2 + b2) * QUAD_THREADS];
+        for (int b2 = 0; b2 < S::NC2; ++b2) row[comp(cl, b1 * 2 + b2)] = x[S::at(a1, a2, b1, b2)];
+    }
+}
+
+// both bricks on a tile held in registers
+template <bool R1, bool R2, bool C1, bool C2>
+__device__ __forceinline__ void quad_apply(double* __restrict__ x, const int rf, const int cf, const QuadMats& qm) {
+  using S = Shape<R1, R2, C1, C2>;
+  constexpr int H1 = S::NR1 - 1, H2 = S::NR2 - 1, K1 = S::NC1 - 1, K2 = S::NC2 - 1;   // index of the "tgt" member (0 if inert)
   // ---- brick 1: acts on (a1, b1) for every (a2, b2) ----
   {
     const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
@@ -96,29 +133,29 @@ __device__ __forceinline__ void quad_tile(double* __restrict__ C, int64_t NB, co
     if (R1 && C1) {
       const int g10 = sSa ^ crb, g01 = sSb ^ cra, g11 = g10 ^ sSb ^ crap;
 #pragma unroll
-      for (int a2 = 0; a2 < NR2; ++a2)
+      for (int a2 = 0; a2 < S::NR2; ++a2)
 #pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2) {
-          double y0 = x[0][a2][0][b2], y1 = qflip(x[0][a2][NC1 - 1][b2], g01), y2 = qflip(x[NR1 - 1][a2][0][b2], g10),
-                 y3 = qflip(x[NR1 - 1][a2][NC1 - 1][b2], g11);
+        for (int b2 = 0; b2 < S::NC2; ++b2) {
+          double y0 = x[S::at(0, a2, 0, b2)], y1 = qflip(x[S::at(0, a2, K1, b2)], g01),
+                 y2 = qflip(x[S::at(H1, a2, 0, b2)], g10), y3 = qflip(x[S::at(H1, a2, K1, b2)], g11);
           mat4(qm.m1, y0, y1, y2, y3);
-          x[0][a2][0][b2] = y0;
-          x[0][a2][NC1 - 1][b2] = qflip(y1, g01);
-          x[NR1 - 1][a2][0][b2] = qflip(y2, g10);
-          x[NR1 - 1][a2][NC1 - 1][b2] = qflip(y3, g11);
+          x[S::at(0, a2, 0, b2)] = y0;
+          x[S::at(0, a2, K1, b2)] = qflip(y1, g01);
+          x[S::at(H1, a2, 0, b2)] = qflip(y2, g10);
+          x[S::at(H1, a2, K1, b2)] = qflip(y3, g11);
         }
     } else if (R1) {
-      const int g = sSa ^ crb;   // alpha single on an inert column
+      const int g = sSa ^ crb;   // alpha single on a column that is inert in pair 1
 #pragma unroll
-      for (int a2 = 0; a2 < NR2; ++a2)
+      for (int a2 = 0; a2 < S::NR2; ++a2)
 #pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2) rot2(x[0][a2][0][b2], x[NR1 - 1][a2][0][b2], qm.ca1, qm.sa1, g);
+        for (int b2 = 0; b2 < S::NC2; ++b2) rot2(x[S::at(0, a2, 0, b2)], x[S::at(H1, a2, 0, b2)], qm.ca1, qm.sa1, g);
     } else if (C1) {
-      const int g = sSb ^ cra;   // beta single on an inert row
+      const int g = sSb ^ cra;   // beta single on a row that is inert in pair 1
 #pragma unroll
-      for (int a2 = 0; a2 < NR2; ++a2)
+      for (int a2 = 0; a2 < S::NR2; ++a2)
 #pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2) rot2(x[0][a2][0][b2], x[0][a2][NC1 - 1][b2], qm.cb1, qm.sb1, g);
+        for (int b2 = 0; b2 < S::NC2; ++b2) rot2(x[S::at(0, a2, 0, b2)], x[S::at(0, a2, K1, b2)], qm.cb1, qm.sb1, g);
     }
   }
   // ---- brick 2: acts on (a2, b2) for every (a1, b1) ----
@@ -128,52 +165,42 @@ __device__ __forceinline__ void quad_tile(double* __restrict__ C, int64_t NB, co
     if (R2 && C2) {
       const int g10 = sSa ^ crb, g01 = sSb ^ cra, g11 = g10 ^ sSb ^ crap;
 #pragma unroll
-      for (int a1 = 0; a1 < NR1; ++a1)
+      for (int a1 = 0; a1 < S::NR1; ++a1)
 #pragma unroll
-        for (int b1 = 0; b1 < NC1; ++b1) {
-          double y0 = x[a1][0][b1][0], y1 = qflip(x[a1][0][b1][NC2 - 1], g01), y2 = qflip(x[a1][NR2 - 1][b1][0], g10),
-                 y3 = qflip(x[a1][NR2 - 1][b1][NC2 - 1], g11);
+        for (int b1 = 0; b1 < S::NC1; ++b1) {
+          double y0 = x[S::at(a1, 0, b1, 0)], y1 = qflip(x[S::at(a1, 0, b1, K2)], g01),
+                 y2 = qflip(x[S::at(a1, H2, b1, 0)], g10), y3 = qflip(x[S::at(a1, H2, b1, K2)], g11);
           mat4(qm.m2, y0, y1, y2, y3);
-          x[a1][0][b1][0] = y0;
-          x[a1][0][b1][NC2 - 1] = qflip(y1, g01);
-          x[a1][NR2 - 1][b1][0] = qflip(y2, g10);
-          x[a1][NR2 - 1][b1][NC2 - 1] = qflip(y3, g11);
+          x[S::at(a1, 0, b1, 0)] = y0;
+          x[S::at(a1, 0, b1, K2)] = qflip(y1, g01);
+          x[S::at(a1, H2, b1, 0)] = qflip(y2, g10);
+          x[S::at(a1, H2, b1, K2)] = qflip(y3, g11);
         }
     } else if (R2) {
       const int g = sSa ^ crb;
 #pragma unroll
-      for (int a1 = 0; a1 < NR1; ++a1)
+      for (int a1 = 0; a1 < S::NR1; ++a1)
 #pragma unroll
-        for (int b1 = 0; b1 < NC1; ++b1) rot2(x[a1][0][b1][0], x[a1][NR2 - 1][b1][0], qm.ca2, qm.sa2, g);
+        for (int b1 = 0; b1 < S::NC1; ++b1) rot2(x[S::at(a1, 0, b1, 0)], x[S::at(a1, H2, b1, 0)], qm.ca2, qm.sa2, g);
     } else if (C2) {
       const int g = sSb ^ cra;
 #pragma unroll
-      for (int a1 = 0; a1 < NR1; ++a1)
+      for (int a1 = 0; a1 < S::NR1; ++a1)
 #pragma unroll
-        for (int b1 = 0; b1 < NC1; ++b1) rot2(x[a1][0][b1][0], x[a1][0][b1][NC2 - 1], qm.cb2, qm.sb2, g);
+        for (int b1 = 0; b1 < S::NC1; ++b1) rot2(x[S::at(a1, 0, b1, 0)], x[S::at(a1, 0, b1, K2)], qm.cb2, qm.sb2, g);
     }
   }
-#pragma unroll
-  for (int a1 = 0; a1 < NR1; ++a1)
-#pragma unroll
-    for (int a2 = 0; a2 < NR2; ++a2)
-#pragma unroll
-      for (int b1 = 0; b1 < NC1; ++b1)
-#pragma unroll
-        for (int b2 = 0; b2 < NC2; ++b2) C[ro[a1][a2] + co[b1][b2]] = x[a1][a2][b1][b2];
 }
 
 template <bool R1, bool R2, bool C1, bool C2>
 __device__ __forceinline__ void quad_rows(double* __restrict__ C, int64_t NB, const int4* __restrict__ rowIdx,
                                           const int* __restrict__ rowFlags, int64_t r0, const int4 cl, const int cf,
                                           const QuadMats& qm) {
+  using S = Shape<R1, R2, C1, C2>;
+  constexpr int TILE = S::TILE, G = S::G, NBATCH = QUAD_ROWS / G;
+#if QUAD_ASYNC
   extern __shared__ double quad_smem[];
   double* mine = quad_smem + threadIdx.x;   // slot s of stage t lives at mine[(t * 16 + s) * QUAD_THREADS]
-  // A stage always carries 16 amplitudes per thread: one 4x4 tile, two 2x4 tiles, ... eight 1x2 tiles, so
-  // the small tile shapes keep as many bytes in flight as the big one.
-  constexpr int TILE = (R1 ? 2 : 1) * (R2 ? 2 : 1) * (C1 ? 2 : 1) * (C2 ? 2 : 1);
-  constexpr int G = (16 / TILE > 8) ? 8 : 16 / TILE;     // row groups per stage
-  constexpr int NB_ = QUAD_ROWS / G;                     // batches per CTA
   auto issue_batch = [&](int b) {
     double* st = mine + (b % QUAD_STAGES) * 16 * QUAD_THREADS;
 #pragma unroll
@@ -182,31 +209,52 @@ __device__ __forceinline__ void quad_rows(double* __restrict__ C, int64_t NB, co
       if (rw.x >= 0) quad_issue<R1, R2, C1, C2>(C, NB, rw, cl, st + g * TILE * QUAD_THREADS);
     }
   };
-  // software pipeline over the batches: QUAD_STAGES - 1 fetches are always in flight
 #pragma unroll
   for (int b = 0; b < QUAD_STAGES - 1; ++b) {
-    if (b < NB_) issue_batch(b);
+    if (b < NBATCH) issue_batch(b);
     __pipeline_commit();
   }
 #pragma unroll 1
-  for (int b = 0; b < NB_; ++b) {
+  for (int b = 0; b < NBATCH; ++b) {
     const int bn = b + QUAD_STAGES - 1;
-    if (bn < NB_) issue_batch(bn);
+    if (bn < NBATCH) issue_batch(bn);
     __pipeline_commit();
-    __pipeline_wait_prior(QUAD_STAGES - 1);   // the fetch of batch b has landed
+    __pipeline_wait_prior(QUAD_STAGES - 1);
     const double* st = mine + (b % QUAD_STAGES) * 16 * QUAD_THREADS;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int4 rw = __ldg(rowIdx + r0 + b * G + g);
       if (rw.x < 0) continue;
-      quad_tile<R1, R2, C1, C2>(C, NB, rw, __ldg(rowFlags + r0 + b * G + g), cl, cf, qm, st + g * TILE * QUAD_THREADS);
+      double x[TILE];
+#pragma unroll
+      for (int k = 0; k < TILE; ++k) x[k] = st[(g * TILE + k) * QUAD_THREADS];
+      quad_apply<R1, R2, C1, C2>(x, __ldg(rowFlags + r0 + b * G + g), cf, qm);
+      quad_store<R1, R2, C1, C2>(C, NB, rw, cl, x);
     }
   }
+#else
+#pragma unroll 1
+  for (int b = 0; b < NBATCH; ++b) {
+    int4 rw[G];
+    double x[G][TILE];
+#pragma unroll
+    for (int g = 0; g < G; ++g) rw[g] = __ldg(rowIdx + r0 + b * G + g);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (rw[g].x >= 0) quad_load<R1, R2, C1, C2>(C, NB, rw[g], cl, x[g]);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (rw[g].x >= 0) {
+        quad_apply<R1, R2, C1, C2>(x[g], __ldg(rowFlags + r0 + b * G + g), cf, qm);
+        quad_store<R1, R2, C1, C2>(C, NB, rw[g], cl, x[g]);
+      }
+  }
+#endif
 }
 
 struct QuadBounds { int c3, c2, c1, c0; int r3, r2, r1, r0; };   // cumulative CTA / row-chunk counts per type
 
-__global__ void __launch_bounds__(QUAD_THREADS)
+__global__ void __launch_bounds__(QUAD_THREADS, QUAD_MINBLOCKS)
 quad_kernel(double* __restrict__ C, const int4* __restrict__ colIdx, const int* __restrict__ colFlags,
             const int4* __restrict__ rowIdx, const int* __restrict__ rowFlags, int64_t NB, const QuadBounds qb,
             const QuadMats qm) {
@@ -418,12 +466,16 @@ int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, i
                    qt.rowchunk_end[0], qt.rowchunk_end[1], qt.rowchunk_end[2], qt.rowchunk_end[3]};
   if (qb.c0 == 0 || qb.r0 == 0) return SQ_OK;
   dim3 grid((unsigned)qb.c0, (unsigned)qb.r0);
+#if QUAD_ASYNC
   const size_t smem = sizeof(double) * QUAD_STAGES * 16 * QUAD_THREADS;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
+#else
+  const size_t smem = 0;
+#endif
   quad_kernel<<<grid, QUAD_THREADS, smem, st>>>(state, qt.d_colIdx, qt.d_colFlags, qt.d_rowIdx, qt.d_rowFlags, sp->NB, qb,
                                                qm);
   cudaError_t e = cudaGetLastError();
