@@ -51,6 +51,8 @@ def _declare(lib: C.CDLL) -> None:
         "sq_layout_num_ops": (i32, [vp]),
         "sq_layout_num_launches": (i32, [vp, i32, i32]),
         "sq_layout_touched_amplitudes": (i64, [vp, i32, i32]),
+        "sq_layout_plan_stats": (i32, [vp, i32, i32, pi64]),
+        "sq_set_option": (i32, [C.c_char_p, C.c_char_p]),
         "sq_ups_apply": (i32, [vp, vp, pdbl, i32, i32, i32, vp, vp]),
         "sq_grad_action": (i32, [vp, vp, i32, vp, vp, vp]),
         "sq_ups_grad_sweep": (i32, [vp, vp, pdbl, i32, i32, vp, vp, pdbl, vp]),
@@ -86,7 +88,7 @@ EXPORTED_SYMBOLS = (
     "sq_last_error sq_version sq_space_create sq_space_destroy sq_space_num_det sq_space_num_strings "
     "sq_space_local_rows sq_space_export_strings sq_space_export_idx2det sq_space_det2idx sq_layout_create "
     "sq_layout_attach_generator sq_layout_destroy sq_layout_num_ops sq_layout_num_launches "
-    "sq_layout_touched_amplitudes sq_ups_apply "
+    "sq_layout_touched_amplitudes sq_layout_plan_stats sq_set_option sq_ups_apply "
     "sq_grad_action sq_ups_grad_sweep sq_apply_strings sq_dot sq_axpy sq_scale_copy sq_sigma sq_rdm12 "
     "sq_debug_string_action sq_launch_count sq_partition_prefix sq_space_set_partition sq_dist_alloc sq_dist_free "
     "sq_ipc_export sq_ipc_import sq_ipc_close sq_layout_needs_exchange sq_ups_apply_dist sq_layout_op_stats"

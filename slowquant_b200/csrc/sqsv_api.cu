@@ -2,6 +2,7 @@
 // sweep, generic operator application.  See include/sqsv.h for the reference functions each replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -429,6 +430,7 @@ extern "C" int sq_layout_destroy(sq_layout* lay) {
     cudaFree(pt.d_rowItems);
   }
   for (auto& kv : lay->quads) sq_free_quad_tables(&kv.second);
+  for (auto& kv : lay->wins) sq_free_win_tables(kv.second);
   for (auto& gt : lay->gens) {
     cudaFree(gt.d_srcRows);
     cudaFree(gt.d_tgtRows);
@@ -536,45 +538,255 @@ static int get_quad(sq_layout* lay, int pA, int pB, const QuadTables** out) {
   return SQ_OK;
 }
 
-// launches of a run list after quad fusion: entry = (run index, partner run index or -1)
-static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<std::pair<int, int>>* out) {
+// ---- launch plan: window sweeps (sqsv_win.cu), quad fusion, single bricks, generic operators ----
+// A run is one brick (consecutive operators on one orbital pair) or one non-tile operator.  Bricks on disjoint
+// orbital pairs commute (even products of ladder operators on disjoint spin orbitals), so a brick may be
+// executed early if it commutes with every not-yet-executed run in front of it.  The planner repeatedly takes
+// the window that can absorb the most such bricks; non-tile operators are barriers.
+struct Launch {
+  int kind = 0;                 // 0 single run (tile / generic / sa_double / null), 1 quad (2 runs), 2 window sweep
+  std::vector<int> runs;        // run indices in execution order
+  const WinTables* wt = nullptr;
+  const QuadTables* qt = nullptr;
+};
+
+struct WinConfig {
+  bool enabled = true;
+  int widths[4] = {8, 6, 4, 0};  // alpha window widths tried
+  int k_run = 16;                // beta suffixes per CTA for "run" windows (power of two <= 16)
+  int max_block = 12;            // beta "block" windows reach the last orbital when n - b0 <= max_block
+  int smem_kb = 100;             // largest tile admitted
+  int min_suffix = 6;            // run windows need at least this many suffix orbitals
+  int max_bricks = SQ_WIN_MAX_BRICKS;
+  int min_bricks = 3;            // smaller groups go to the tile / quad kernels
+};
+
+static void parse_win_config(const char* e, WinConfig* cfg) {
+  // "0" disables, "1" / "" restores the defaults, otherwise
+  // "w1:w2:w3,k_run,max_block,smem_kb,min_suffix,max_bricks,min_bricks" (trailing fields optional)
+  *cfg = WinConfig();
+  if (!e || !e[0] || (e[0] == '1' && e[1] == 0)) return;
+  if (e[0] == '0' && e[1] == 0) {
+    cfg->enabled = false;
+    return;
+  }
+  int w[3] = {0, 0, 0}, v[6] = {cfg->k_run, cfg->max_block, cfg->smem_kb, cfg->min_suffix, cfg->max_bricks, cfg->min_bricks};
+  const int got = sscanf(e, "%d:%d:%d,%d,%d,%d,%d,%d,%d", &w[0], &w[1], &w[2], &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+  if (got >= 3) {
+    for (int i = 0; i < 3; ++i) cfg->widths[i] = w[i];
+    cfg->k_run = std::max(1, std::min(v[0], 16));
+    cfg->max_block = v[1];
+    cfg->smem_kb = v[2];
+    cfg->min_suffix = v[3];
+    cfg->max_bricks = std::max(1, std::min(v[4], SQ_WIN_MAX_BRICKS));
+    cfg->min_bricks = std::max(1, v[5]);
+  }
+}
+
+static WinConfig& win_config() {
+  static WinConfig cfg;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    parse_win_config(getenv("SQ_WIN"), &cfg);
+    const char* t = getenv("SQ_TILE_KERNEL");
+    if (t && t[0] == '1') cfg.enabled = false;
+  }
+  return cfg;
+}
+
+// run-time switches for A/B comparisons and tests: name "win" takes the SQ_WIN syntax
+extern "C" int sq_set_option(const char* name, const char* value) {
+  if (!name) return SQ_ERR_INVALID;
+  if (strcmp(name, "win") == 0) {
+    parse_win_config(value, &win_config());
+    return SQ_OK;
+  }
+  sq_set_error("sq_set_option: unknown option '%s'", name);
+  return SQ_ERR_INVALID;
+}
+
+struct WinCand {
+  int a0, Ha, b0, Hb, K;
+  size_t smem;
+  bool dead = false;
+};
+
+static void win_candidates(const sq_space* sp, std::vector<WinCand>* out) {
   out->clear();
-  for (size_t ri = 0; ri < runs.size(); ++ri) {
-    const LayoutOp& op = lay->ops[runs[ri][0]];
-    if (is_tile_op(op) && ri + 1 < runs.size() && is_tile_op(lay->ops[runs[ri + 1][0]]) && quad_enabled()) {
-      const QuadTables* qt = nullptr;
-      SQ_CHECK(get_quad(lay, op.pair, lay->ops[runs[ri + 1][0]].pair, &qt));
-      if (qt && qt->ok) {
-        out->push_back({(int)ri, (int)ri + 1});
-        ++ri;
-        continue;
+  const WinConfig& cfg = win_config();
+  if (!cfg.enabled) return;
+  const int n = sp->n_orb;
+  for (int wi = 0; wi < 3; ++wi) {
+    int Ha = cfg.widths[wi];
+    if (Ha <= 1) continue;
+    if (Ha > n) Ha = n;
+    bool dup = false;
+    for (int wj = 0; wj < wi; ++wj) dup |= (std::min(cfg.widths[wj], n) == Ha);
+    if (dup) continue;
+    for (int a0 = 0; a0 + Ha <= n; ++a0) {
+      const size_t ra = (size_t)sq_win_max_class(n, sp->n_alpha, a0, Ha);
+      if (n - a0 <= cfg.max_block) {   // block window on the beta side
+        WinCand c{a0, Ha, a0, n - a0, 1, 0};
+        c.smem = 8 * ra * (size_t)sq_win_max_class(n, sp->n_beta, c.b0, c.Hb);
+        if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
+      }
+      if (n - (a0 + Ha) >= cfg.min_suffix) {
+        WinCand c{a0, Ha, a0, Ha, cfg.k_run, 0};
+        c.smem = 8 * ra * (size_t)sq_win_max_class(n, sp->n_beta, c.b0, c.Hb) * (size_t)c.K;
+        while (c.K > 2 && c.smem > (size_t)cfg.smem_kb * 1024) {
+          c.K >>= 1;
+          c.smem >>= 1;
+        }
+        if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
       }
     }
-    out->push_back({(int)ri, -1});
+  }
+}
+
+static uint32_t run_orbitals(const sq_layout* lay, const std::vector<int>& run) {
+  const LayoutOp& op = lay->ops[run[0]];
+  if (!is_tile_op(op)) return 0xffffffffu;
+  const PairTables& pt = lay->pairs[op.pair];
+  return (1u << pt.i) | (1u << pt.a);
+}
+
+static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out) {
+  out->clear();
+  sq_space* sp = lay->sp;
+  const WinConfig& cfg = win_config();
+  const int m = (int)runs.size();
+  std::vector<WinCand> cands;
+  win_candidates(sp, &cands);
+  std::vector<char> done(m, 0);
+  std::vector<uint32_t> orb(m);
+  std::vector<int> pair(m);
+  for (int t = 0; t < m; ++t) {
+    orb[t] = run_orbitals(lay, runs[t]);
+    pair[t] = lay->ops[runs[t][0]].pair;
+  }
+  auto simulate = [&](const WinCand& c, int head, std::vector<int>* sel) {
+    sel->clear();
+    uint32_t blocked = 0;
+    const int wlo = std::max(c.a0, c.b0), whi = std::min(c.a0 + c.Ha, c.b0 + c.Hb);
+    const uint32_t full = ((whi >= 32) ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u);
+    for (int t = head; t < m && (int)sel->size() < cfg.max_bricks; ++t) {
+      if (done[t]) continue;
+      if (pair[t] < 0) break;   // barrier
+      if (!(orb[t] & blocked) && sq_win_pair_ok(lay, pair[t], c.a0, c.Ha, c.b0, c.Hb)) sel->push_back(t);
+      else blocked |= orb[t];
+      if ((blocked & full) == full) break;
+    }
+  };
+  int head = 0;
+  std::vector<int> sel, best;
+  while (head < m) {
+    if (done[head]) { ++head; continue; }
+    if (pair[head] >= 0) {
+      // best window for the current front
+      for (;;) {
+        int bi = -1;
+        best.clear();
+        for (size_t ci = 0; ci < cands.size(); ++ci) {
+          if (cands[ci].dead) continue;
+          simulate(cands[ci], head, &sel);
+          if (sel.size() > best.size() || (sel.size() == best.size() && bi >= 0 && !sel.empty() && cands[ci].smem < cands[bi].smem)) {
+            best = sel;
+            bi = (int)ci;
+          }
+        }
+        if (bi < 0 || (int)best.size() < cfg.min_bricks) { best.clear(); break; }
+        const WinTables* wt = nullptr;
+        const WinCand& c = cands[bi];
+        SQ_CHECK(sq_get_win(sp, lay, c.a0, c.Ha, c.b0, c.Hb, c.K, &wt));
+        if (!wt || !wt->ok) { cands[bi].dead = true; continue; }
+        Launch l;
+        l.kind = 2;
+        l.runs = best;
+        l.wt = wt;
+        out->push_back(l);
+        for (int t : best) done[t] = 1;
+        break;
+      }
+      if (!best.empty()) continue;
+      // no window: the front brick alone, or fused with the next pending brick when they commute (quad kernel)
+      int nxt = head + 1;
+      while (nxt < m && done[nxt]) ++nxt;
+      if (nxt < m && pair[nxt] >= 0 && quad_enabled()) {
+        const QuadTables* qt = nullptr;
+        SQ_CHECK(get_quad(lay, pair[head], pair[nxt], &qt));
+        if (qt && qt->ok) {
+          Launch l;
+          l.kind = 1;
+          l.runs = {head, nxt};
+          l.qt = qt;
+          out->push_back(l);
+          done[head] = done[nxt] = 1;
+          continue;
+        }
+      }
+    }
+    Launch l;
+    l.kind = 0;
+    l.runs = {head};
+    out->push_back(l);
+    done[head] = 1;
   }
   return SQ_OK;
+}
+
+static int launch_cost(const sq_layout* lay, const std::vector<std::vector<int>>& runs, const Launch& l, int* n_kernels,
+                       int64_t* touched) {
+  const sq_space* sp = lay->sp;
+  const std::vector<int>& r = runs[l.runs[0]];
+  const LayoutOp& op = lay->ops[r[0]];
+  *n_kernels = 0;
+  *touched = 0;
+  if (l.kind == 2) {
+    *n_kernels = 1;
+    *touched = l.wt->touched;
+  } else if (l.kind == 1) {
+    *n_kernels = 1;
+    *touched = l.qt->touched;
+  } else if (is_tile_op(op)) {
+    const PairTables& pt = lay->pairs[op.pair];
+    bool has_single = false;
+    for (int k : r) has_single |= !lay->ops[k].pair_double;
+    *n_kernels = 1;
+    *touched = has_single ? pt.touched : 2 * pt.n_src_rows * pt.n_src_cols;
+  } else if (op.null_op) {
+  } else if (op.gen >= 0) {
+    *n_kernels = 1;
+    *touched = 2 * lay->gens[op.gen].n_rows * lay->gens[op.gen].n_cols_valid;
+  } else if (op.multi) {
+    static const int napp[5] = {2, 4, 4, 8, 10};
+    // each power: gather (read + write) and axpy (2 reads + write) over the whole vector
+    *n_kernels = 2 * napp[op.type - SQ_EXC_SA_DOUBLE_1];
+    *touched = (int64_t)napp[op.type - SQ_EXC_SA_DOUBLE_1] * 3 * sp->local_len();
+  }
+  return SQ_OK;
+}
+
+static int plan_range(sq_layout* lay, int first, int last, std::vector<std::vector<int>>* runs, std::vector<Launch>* launches) {
+  std::vector<double> th(lay->ops.size(), 1.0);
+  std::vector<int> order;
+  exec_order(first, last, 0, &order);
+  plan_runs(lay, order, th.data(), runs);
+  return plan_launches(lay, *runs, launches);
 }
 
 extern "C" int sq_layout_num_launches(const sq_layout* lay_c, int first, int last) {
   sq_layout* lay = const_cast<sq_layout*>(lay_c);
   if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
-  std::vector<double> th(lay->ops.size(), 1.0);
-  std::vector<int> order;
-  exec_order(first, last, 0, &order);
   std::vector<std::vector<int>> runs;
-  plan_runs(lay, order, th.data(), &runs);
-  std::vector<std::pair<int, int>> launches;
-  if (plan_launches(lay, runs, &launches) != SQ_OK) return -1;
+  std::vector<Launch> launches;
+  if (plan_range(lay, first, last, &runs, &launches) != SQ_OK) return -1;
   int n = 0;
   for (auto& l : launches) {
-    const std::vector<int>& r = runs[l.first];
-    const LayoutOp& op = lay->ops[r[0]];
-    if (is_tile_op(op)) n += 1;
-    else if (op.gen >= 0) n += 1;
-    else if (op.multi) {
-      static const int napp[5] = {2, 4, 4, 8, 10};
-      n += 2 * napp[op.type - SQ_EXC_SA_DOUBLE_1];
-    }
+    int nk;
+    int64_t t;
+    launch_cost(lay, runs, l, &nk, &t);
+    n += nk;
   }
   return n;
 }
@@ -584,34 +796,50 @@ extern "C" int sq_layout_num_launches(const sq_layout* lay_c, int first, int las
 extern "C" int64_t sq_layout_touched_amplitudes(const sq_layout* lay_c, int first, int last) {
   sq_layout* lay = const_cast<sq_layout*>(lay_c);
   if (!lay || first < 0 || last > (int)lay->ops.size() || first > last) return -1;
-  std::vector<double> th(lay->ops.size(), 1.0);
-  std::vector<int> order;
-  exec_order(first, last, 0, &order);
   std::vector<std::vector<int>> runs;
-  plan_runs(lay, order, th.data(), &runs);
-  std::vector<std::pair<int, int>> launches;
-  if (plan_launches(lay, runs, &launches) != SQ_OK) return -1;
-  const sq_space* sp = lay->sp;
+  std::vector<Launch> launches;
+  if (plan_range(lay, first, last, &runs, &launches) != SQ_OK) return -1;
   int64_t total = 0;
   for (auto& l : launches) {
-    const std::vector<int>& r = runs[l.first];
-    const LayoutOp& op = lay->ops[r[0]];
-    if (l.second >= 0) {
-      total += lay->quads[{op.pair, lay->ops[runs[l.second][0]].pair}].touched;
-    } else if (is_tile_op(op)) {
-      const PairTables& pt = lay->pairs[op.pair];
-      bool has_single = false;
-      for (int k : r) has_single |= !lay->ops[k].pair_double;
-      total += has_single ? pt.touched : 2 * pt.n_src_rows * pt.n_src_cols;
-    } else if (op.gen >= 0) {
-      total += 2 * lay->gens[op.gen].n_rows * lay->gens[op.gen].n_cols_valid;
-    } else if (op.multi) {
-      static const int napp[5] = {2, 4, 4, 8, 10};
-      // each power: gather (read + write) and axpy (2 reads + write) over the whole vector
-      total += (int64_t)napp[op.type - SQ_EXC_SA_DOUBLE_1] * 3 * sp->local_len();
-    }
+    int nk;
+    int64_t t;
+    launch_cost(lay, runs, l, &nk, &t);
+    total += t;
   }
   return total;
+}
+
+// plan summary for tools / tests: out[0] = launches, out[1] = window sweeps, out[2] = bricks inside window sweeps,
+// out[3] = quad launches, out[4] = single-brick launches, out[5] = other launches
+extern "C" int sq_layout_plan_stats(const sq_layout* lay_c, int first, int last, int64_t* out6) {
+  sq_layout* lay = const_cast<sq_layout*>(lay_c);
+  if (!lay || !out6 || first < 0 || last > (int)lay->ops.size() || first > last) return SQ_ERR_INVALID;
+  std::vector<std::vector<int>> runs;
+  std::vector<Launch> launches;
+  SQ_CHECK(plan_range(lay, first, last, &runs, &launches));
+  for (int i = 0; i < 6; ++i) out6[i] = 0;
+  for (auto& l : launches) {
+    ++out6[0];
+    if (l.kind == 2) { ++out6[1]; out6[2] += (int64_t)l.runs.size(); }
+    else if (l.kind == 1) ++out6[3];
+    else if (is_tile_op(lay->ops[runs[l.runs[0]][0]])) ++out6[4];
+    else ++out6[5];
+  }
+  if (getenv("SQ_PLAN_DEBUG")) {
+    for (auto& l : launches) {
+      if (l.kind == 2) {
+        fprintf(stderr, "win a[%d,%d) b[%d,%d) K=%d smem=%zu :", l.wt->A.w0, l.wt->A.w0 + l.wt->A.H, l.wt->B.w0,
+                l.wt->B.w0 + l.wt->B.H, l.wt->K, l.wt->smem);
+        for (int t : l.runs) fprintf(stderr, " (%d,%d)", lay->pairs[lay->ops[runs[t][0]].pair].i, lay->pairs[lay->ops[runs[t][0]].pair].a);
+        fprintf(stderr, "\n");
+      } else if (l.kind == 1) {
+        fprintf(stderr, "quad\n");
+      } else {
+        fprintf(stderr, "single\n");
+      }
+    }
+  }
+  return SQ_OK;
 }
 
 // closed forms of exp(theta T) for the spin-adapted doubles (operator_state_algebra.py:1086-1409):
@@ -843,28 +1071,65 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
   exec_order(first, last, dagger, &order);
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, thetas_host, &runs);
-  for (size_t ri = 0; ri < runs.size(); ++ri) {
-    auto& run = runs[ri];
+  std::vector<Launch> launches;
+  SQ_CHECK(plan_launches(lay, runs, &launches));
+  static const bool timing = getenv("SQ_LAUNCH_TIMING") != nullptr;   // debug: per-launch device time on stderr
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+  if (timing) {
+    cudaEventCreate(&tev0);
+    cudaEventCreate(&tev1);
+  }
+  struct TimingScope {
+    cudaEvent_t a, b;
+    cudaStream_t st;
+    const Launch* l;
+    TimingScope(cudaEvent_t a_, cudaEvent_t b_, cudaStream_t st_, const Launch* l_) : a(a_), b(b_), st(st_), l(l_) {
+      if (a) cudaEventRecord(a, st);
+    }
+    ~TimingScope() {
+      if (!a) return;
+      cudaEventRecord(b, st);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      if (l->kind == 2)
+        fprintf(stderr, "launch win a[%d,%d) b[%d,%d) K=%d smem=%zu grid=%dx%d bricks=%zu : %.3f ms\n", l->wt->A.w0,
+                l->wt->A.w0 + l->wt->A.H, l->wt->B.w0, l->wt->B.w0 + l->wt->B.H, l->wt->K, l->wt->smem, l->wt->B.n_groups,
+                l->wt->A.n_groups, l->runs.size(), ms);
+      else
+        fprintf(stderr, "launch kind=%d : %.3f ms\n", l->kind, ms);
+    }
+  };
+  for (const Launch& l : launches) {
+    TimingScope tscope(tev0, tev1, st, &l);
+    auto& run = runs[l.runs[0]];
     const LayoutOp& op = lay->ops[run[0]];
-    if (is_tile_op(op)) {
-      TileStep steps[SQ_MAX_PROGRAM];
-      int step_op[SQ_MAX_PROGRAM], n_steps = 0;
-      SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
-      // two consecutive bricks on disjoint orbital pairs commute: one sweep for both (sqsv_quad.cu)
-      if (ri + 1 < runs.size() && is_tile_op(lay->ops[runs[ri + 1][0]]) && quad_enabled()) {
-        const int pA = op.pair, pB = lay->ops[runs[ri + 1][0]].pair;
-        const QuadTables* qt = nullptr;
-        SQ_CHECK(get_quad(lay, pA, pB, &qt));
-        if (qt && qt->ok) {
-          TileStep steps2[SQ_MAX_PROGRAM];
-          int step_op2[SQ_MAX_PROGRAM], n_steps2 = 0;
-          SQ_CHECK(run_tile(sp, lay, runs[ri + 1], thetas_host, dagger, steps2, &n_steps2, step_op2));
-          SQ_CHECK(sq_launch_quad(sp, *qt, steps, n_steps, lay->pairs[pA].sigma, steps2, n_steps2, lay->pairs[pB].sigma,
-                                  state_dev, st));
-          ++ri;
-          continue;
-        }
+    TileStep steps[SQ_MAX_PROGRAM];
+    int step_op[SQ_MAX_PROGRAM], n_steps = 0;
+    if (l.kind == 2) {
+      // window sweep: the rotation steps of every brick; the launcher folds them into constant matrices
+      int pair_idx[SQ_WIN_MAX_BRICKS], nst[SQ_WIN_MAX_BRICKS];
+      TileStep wsteps[SQ_WIN_MAX_BRICKS][SQ_MAX_PROGRAM];
+      const TileStep* sptr[SQ_WIN_MAX_BRICKS];
+      int nb = 0;
+      for (int t : l.runs) {
+        SQ_CHECK(run_tile(sp, lay, runs[t], thetas_host, dagger, wsteps[nb], &nst[nb], step_op));
+        pair_idx[nb] = lay->ops[runs[t][0]].pair;
+        sptr[nb] = wsteps[nb];
+        ++nb;
       }
+      SQ_CHECK(sq_launch_win(sp, *l.wt, pair_idx, sptr, nst, nb, state_dev, st));
+    } else if (l.kind == 1) {
+      // two bricks on disjoint orbital pairs commute: one sweep for both (sqsv_quad.cu)
+      const int pA = op.pair, pB = lay->ops[runs[l.runs[1]][0]].pair;
+      SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
+      TileStep steps2[SQ_MAX_PROGRAM];
+      int step_op2[SQ_MAX_PROGRAM], n_steps2 = 0;
+      SQ_CHECK(run_tile(sp, lay, runs[l.runs[1]], thetas_host, dagger, steps2, &n_steps2, step_op2));
+      SQ_CHECK(sq_launch_quad(sp, *l.qt, steps, n_steps, lay->pairs[pA].sigma, steps2, n_steps2, lay->pairs[pB].sigma,
+                              state_dev, st));
+    } else if (is_tile_op(op)) {
+      SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
       SQ_CHECK(sq_launch_tile(sp, lay->pairs[op.pair], steps, n_steps, state_dev, peers, st));
     } else if (op.null_op) {
       continue;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
 #include <atomic>
 #include <map>
 #include <string>
@@ -158,6 +159,7 @@ struct sq_layout {
   std::vector<GenTables> gens;
   std::map<std::vector<int>, int> gen_index;
   std::map<std::pair<int, int>, QuadTables> quads;   // built lazily per (pair1, pair2)
+  std::map<std::array<int, 5>, struct WinTables*> wins;   // built lazily per (a0, Ha, b0, Hb, K) (sqsv_win.cu)
 };
 
 static inline int sq_row_owner(const sq_space* sp, int64_t row) {
@@ -179,6 +181,44 @@ int sq_ensure_partial(sq_space* sp, int64_t n);
 
 // kernel launchers (sqsv_kernels.cu)
 struct TileStep { int kind; double c, s; };   // kind: 0 alpha-rot, 1 beta-rot, 2 pair-double rot
+// one brick (fused program on one orbital pair) in the gauge-fixed tile basis (x00, x01, x10, x11)
+struct TileMatrices {
+  double m[16];        // 4x4, row-major
+  double ca, sa;       // total alpha-single rotation (src row x inert column)
+  double cb, sb;       // total beta-single rotation (inert row x src column)
+};
+void sq_build_tile_matrices(const TileStep* steps, int n_steps, int sigma, TileMatrices* tm);
+// same with explicit signs of the alpha single, beta single and pair double generators
+void sq_build_tile_matrices3(const TileStep* steps, int n_steps, int ea, int eb, int ed, TileMatrices* tm);
+
+// Tables of the window kernel (sqsv_win.cu): one orbital window per spin, see the header of that file.
+#define SQ_WIN_MAX_BRICKS 16
+struct WinSide {
+  int w0 = 0, H = 0;
+  int ncls = 0, LT = 0, n_groups = 0, max_cnt = 0;
+  int2* d_groups = nullptr;
+  int* d_delta = nullptr;
+  uint32_t* d_gbits = nullptr;
+  int* d_cnt = nullptr;
+  uint32_t* d_items = nullptr;
+  int2* d_itemcnt = nullptr;
+};
+struct WinTables {
+  bool ok = false;
+  int K = 1, logK = 0;             // consecutive beta suffixes per CTA
+  WinSide A, B;
+  std::vector<int> pair_local;     // layout pair index -> pair id inside the window tables, -1 if unusable
+  std::vector<int8_t> eps;         // [3 * local pair] constant signs of Ta, Tb, pair double in the window gauge
+  size_t smem = 0;                 // dynamic shared memory per CTA (largest tile + staged tables)
+  int tile_doubles = 0;            // doubles of the largest tile
+  int64_t touched = 0;             // amplitudes per launch (the whole local vector)
+};
+int sq_win_max_class(int n, int ne, int w0, int H);
+bool sq_win_pair_ok(const sq_layout* lay, int pair, int a0, int Ha, int b0, int Hb);
+int sq_get_win(sq_space* sp, sq_layout* lay, int a0, int Ha, int b0, int Hb, int K, const WinTables** out);
+void sq_free_win_tables(WinTables* wt);
+int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
+                  int n_bricks, double* state, cudaStream_t st);
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                    double* state, const PeerPtrs* peers, cudaStream_t st);
 int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, int n1, int sigma1,

@@ -124,12 +124,6 @@ tile_kernel(double* __restrict__ C, const uint32_t* __restrict__ codeA, const ui
 //   * all loads of a CTA's row batch are issued before the first store (ROWS_PER_ITER x 4 independent
 //     8-byte loads per thread in flight).
 // ---------------------------------------------------------------------------------------------
-struct TileMatrices {
-  double m[16];        // 4x4, row-major, basis (x00, x01, x10, x11), gauge-fixed
-  double ca, sa;       // total alpha-single rotation (src row x inert column)
-  double cb, sb;       // total beta-single rotation (inert row x src column)
-};
-
 __device__ __forceinline__ double flip(double x, int neg) {
   // multiply by +-1 through the sign bit
   return __hiloint2double(__double2hiint(x) ^ (neg << 31), __double2loint(x));
@@ -707,7 +701,11 @@ static int fill_program(const TileStep* steps, int n_steps, TileProgram* p) {
 }
 
 // host: multiply the step rotations into the gauge-fixed 4x4 matrix and the two total 2x2 rotations
-static void build_tile_matrices(const TileStep* steps, int n_steps, int sigma, TileMatrices* tm) {
+void sq_build_tile_matrices(const TileStep* steps, int n_steps, int sigma, TileMatrices* tm) {
+  sq_build_tile_matrices3(steps, n_steps, 1, 1, sigma, tm);
+}
+
+void sq_build_tile_matrices3(const TileStep* steps, int n_steps, int ea, int eb, int ed, TileMatrices* tm) {
   double M[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
   auto apply = [&](int u, int v, double c, double s) {   // rows u (src) and v (tgt) of M <- rotation * M
     for (int k = 0; k < 4; ++k) {
@@ -725,15 +723,15 @@ static void build_tile_matrices(const TileStep* steps, int n_steps, int sigma, T
   for (int k = 0; k < n_steps; ++k) {
     const double c = steps[k].c, s = steps[k].s;
     if (steps[k].kind == 0) {
-      apply(0, 2, c, s);
-      apply(1, 3, c, s);
-      compose(tha_c, tha_s, c, s);
+      apply(0, 2, c, ea * s);
+      apply(1, 3, c, ea * s);
+      compose(tha_c, tha_s, c, ea * s);
     } else if (steps[k].kind == 1) {
-      apply(0, 1, c, s);
-      apply(2, 3, c, s);
-      compose(thb_c, thb_s, c, s);
+      apply(0, 1, c, eb * s);
+      apply(2, 3, c, eb * s);
+      compose(thb_c, thb_s, c, eb * s);
     } else {
-      apply(0, 3, c, sigma * s);
+      apply(0, 3, c, ed * s);
     }
   }
   for (int r = 0; r < 4; ++r)
@@ -780,7 +778,7 @@ int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, in
       return SQ_ERR_INVALID;
     }
     TileMatrices tm;
-    build_tile_matrices(steps, n_steps, pt.sigma, &tm);
+    sq_build_tile_matrices(steps, n_steps, pt.sigma, &tm);
     bool any_single = false;
     for (int k = 0; k < n_steps; ++k) any_single |= steps[k].kind != 2;
     // a pair-double-only program touches src x src tiles only

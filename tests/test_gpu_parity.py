@@ -549,3 +549,52 @@ def test_ucc_wavefunction_object(sq, golden):
     # ours are quantised in units of 2 ulp(E)/step ~ 1.9e-6, so agreement is only meaningful to a few units
     grad = WF._calc_gradient_optimization(th, True, False)
     assert np.max(np.abs(grad - arrays["uccwf_gradient"])) < 3e-5
+
+
+WIN_VARIANTS = ["1", "8:6:4,16,12,100,6,16,3", "6:4:0,16,8,60,2,16,2", "4:0:0,8,4,40,1,5,2", "8:0:0,4,12,200,4,16,1",
+                "6:0:0,16,0,100,0,7,1", "5:3:0,2,12,100,3,16,2"]
+
+
+@pytest.mark.parametrize("n,na,nb,L,qnp", [(8, 4, 4, 3, False), (9, 4, 5, 2, True), (12, 6, 6, 3, False), (13, 6, 5, 2, False)])
+def test_window_sweeps_equal_single_brick_launches(sq, n, na, nb, L, qnp):
+    """Every window configuration of the planner (alpha/beta windows, run and block modes, brick caps) gives
+    the state of the one-brick-per-launch path; at small sizes that path is also checked against the oracle."""
+    import ctypes as C
+
+    lib = sq.lib.load()
+    types, idx, th, rng = _seeded_case(n, na, nb, L, 500 + n, qnp=qnp)
+    info = sq.ci.get_indexing(0, n, 0, na, nb)
+    lay = _layout(sq, types, idx)
+    handle = sq.osa.compile_layout(info, lay)
+    dev = torch.device("cuda", info.device)
+    x = torch.randn(info.num_det, dtype=torch.float64, device=dev)
+    x /= torch.linalg.norm(x)
+    try:
+        sq.lib.check(lib.sq_set_option(b"win", b"0"))
+        ref = sq.osa.construct_ups_state(x, info, th.tolist(), lay)
+        ref_d = sq.osa.construct_ups_state(x, info, th.tolist(), lay, dagger=True)
+        if n <= 9:
+            sp = orc.get_indexing(0, n, 0, na, nb)
+            o = orc.construct_ups_state(x.cpu().numpy(), sp, th, types, idx, threaded=True)
+            assert np.max(np.abs(ref.cpu().numpy() - o)) < TOL
+        used = 0
+        for cfg in WIN_VARIANTS:
+            sq.lib.check(lib.sq_set_option(b"win", cfg.encode()))
+            stats = (C.c_int64 * 6)()
+            sq.lib.check(lib.sq_layout_plan_stats(handle, 0, len(types), stats))
+            used += int(stats[1])
+            res = sq.osa.construct_ups_state(x, info, th.tolist(), lay)
+            assert float(torch.max(torch.abs(res - ref))) < 1e-13, cfg
+            res_d = sq.osa.construct_ups_state(x, info, th.tolist(), lay, dagger=True)
+            assert float(torch.max(torch.abs(res_d - ref_d))) < 1e-13, cfg
+            # a sub-range of the circuit (propagate_unitary-style first/last)
+            k0, k1 = 2, len(types) - 1
+            part = _layout(sq, types[k0:k1], idx[k0:k1])
+            sq.lib.check(lib.sq_set_option(b"win", b"0"))
+            ref_p = sq.osa.construct_ups_state(x, info, th[k0:k1].tolist(), part)
+            sq.lib.check(lib.sq_set_option(b"win", cfg.encode()))
+            res_p = sq.osa.construct_ups_state(x, info, th[k0:k1].tolist(), part)
+            assert float(torch.max(torch.abs(res_p - ref_p))) < 1e-13, cfg
+        assert used > 0, "no window sweep was planned"
+    finally:
+        sq.lib.check(lib.sq_set_option(b"win", b"1"))
