@@ -102,7 +102,7 @@ int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last);
  * single-brick launches, other launches}.  (No reference counterpart: the reference applies one operator per pass.) */
 int sq_layout_plan_stats(const sq_layout* lay, int first, int last, int64_t* out6);
 /* run-time switch of the launch planner (A/B comparisons, tests): name "win", value "0" (window sweeps off),
- * "1" (defaults) or "w1:w2:w3,k_run,max_block,smem_kb,min_suffix,max_bricks,min_bricks" */
+ * "1" (defaults) or "w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks" */
 int sq_set_option(const char* name, const char* value);
 
 /* ---- unitary product state (construct_ups_state, operator_state_algebra.py:963-1412;

@@ -543,43 +543,35 @@ static int get_quad(sq_layout* lay, int pA, int pB, const QuadTables** out) {
 // orbital pairs commute (even products of ladder operators on disjoint spin orbitals), so a brick may be
 // executed early if it commutes with every not-yet-executed run in front of it.  The planner repeatedly takes
 // the window that can absorb the most such bricks; non-tile operators are barriers.
-struct Launch {
-  int kind = 0;                 // 0 single run (tile / generic / sa_double / null), 1 quad (2 runs), 2 window sweep
-  std::vector<int> runs;        // run indices in execution order
-  const WinTables* wt = nullptr;
-  const QuadTables* qt = nullptr;
-};
+
+static int g_plan_version = 0;   // bumped by sq_set_option: cached plans of older versions are dropped
 
 struct WinConfig {
   bool enabled = true;
-  int widths[4] = {8, 6, 4, 0};  // alpha window widths tried
-  int k_run = 16;                // beta suffixes per CTA for "run" windows (power of two <= 16)
-  int max_block = 12;            // beta "block" windows reach the last orbital when n - b0 <= max_block
-  int smem_kb = 100;             // largest tile admitted
-  int min_suffix = 6;            // run windows need at least this many suffix orbitals
+  int widths[3] = {6, 5, 4};     // window widths tried (orbitals)
+  int smem_kb = 72;              // largest batch admitted (3 CTAs per SM)
+  int min_suffix = 3;            // windows below the top one need at least this many orbitals above them
   int max_bricks = SQ_WIN_MAX_BRICKS;
-  int min_bricks = 3;            // smaller groups go to the tile / quad kernels
+  int min_bricks = 3;            // smaller isolated groups go to the tile / quad kernels
 };
 
 static void parse_win_config(const char* e, WinConfig* cfg) {
   // "0" disables, "1" / "" restores the defaults, otherwise
-  // "w1:w2:w3,k_run,max_block,smem_kb,min_suffix,max_bricks,min_bricks" (trailing fields optional)
+  // "w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks" (trailing fields optional)
   *cfg = WinConfig();
   if (!e || !e[0] || (e[0] == '1' && e[1] == 0)) return;
   if (e[0] == '0' && e[1] == 0) {
     cfg->enabled = false;
     return;
   }
-  int w[3] = {0, 0, 0}, v[6] = {cfg->k_run, cfg->max_block, cfg->smem_kb, cfg->min_suffix, cfg->max_bricks, cfg->min_bricks};
-  const int got = sscanf(e, "%d:%d:%d,%d,%d,%d,%d,%d,%d", &w[0], &w[1], &w[2], &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+  int w[3] = {0, 0, 0}, v[4] = {cfg->smem_kb, cfg->min_suffix, cfg->max_bricks, cfg->min_bricks};
+  const int got = sscanf(e, "%d:%d:%d,%d,%d,%d,%d", &w[0], &w[1], &w[2], &v[0], &v[1], &v[2], &v[3]);
   if (got >= 3) {
     for (int i = 0; i < 3; ++i) cfg->widths[i] = w[i];
-    cfg->k_run = std::max(1, std::min(v[0], 16));
-    cfg->max_block = v[1];
-    cfg->smem_kb = v[2];
-    cfg->min_suffix = v[3];
-    cfg->max_bricks = std::max(1, std::min(v[4], SQ_WIN_MAX_BRICKS));
-    cfg->min_bricks = std::max(1, v[5]);
+    cfg->smem_kb = v[0];
+    cfg->min_suffix = v[1];
+    cfg->max_bricks = std::max(1, std::min(v[2], SQ_WIN_MAX_BRICKS));
+    cfg->min_bricks = std::max(1, v[3]);
   }
 }
 
@@ -600,6 +592,7 @@ extern "C" int sq_set_option(const char* name, const char* value) {
   if (!name) return SQ_ERR_INVALID;
   if (strcmp(name, "win") == 0) {
     parse_win_config(value, &win_config());
+    ++g_plan_version;
     return SQ_OK;
   }
   sq_set_error("sq_set_option: unknown option '%s'", name);
@@ -607,7 +600,7 @@ extern "C" int sq_set_option(const char* name, const char* value) {
 }
 
 struct WinCand {
-  int a0, Ha, b0, Hb, K;
+  int w0, H;
   size_t smem;
   bool dead = false;
 };
@@ -618,28 +611,20 @@ static void win_candidates(const sq_space* sp, std::vector<WinCand>* out) {
   if (!cfg.enabled) return;
   const int n = sp->n_orb;
   for (int wi = 0; wi < 3; ++wi) {
-    int Ha = cfg.widths[wi];
-    if (Ha <= 1) continue;
-    if (Ha > n) Ha = n;
+    int H = cfg.widths[wi];
+    if (H <= 1) continue;
+    if (H > n) H = n;
     bool dup = false;
-    for (int wj = 0; wj < wi; ++wj) dup |= (std::min(cfg.widths[wj], n) == Ha);
+    for (int wj = 0; wj < wi; ++wj) dup |= (std::min(cfg.widths[wj], n) == H);
     if (dup) continue;
-    for (int a0 = 0; a0 + Ha <= n; ++a0) {
-      const size_t ra = (size_t)sq_win_max_class(n, sp->n_alpha, a0, Ha);
-      if (n - a0 <= cfg.max_block) {   // block window on the beta side
-        WinCand c{a0, Ha, a0, n - a0, 1, 0};
-        c.smem = 8 * ra * (size_t)sq_win_max_class(n, sp->n_beta, c.b0, c.Hb);
-        if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
-      }
-      if (n - (a0 + Ha) >= cfg.min_suffix) {
-        WinCand c{a0, Ha, a0, Ha, cfg.k_run, 0};
-        c.smem = 8 * ra * (size_t)sq_win_max_class(n, sp->n_beta, c.b0, c.Hb) * (size_t)c.K;
-        while (c.K > 2 && c.smem > (size_t)cfg.smem_kb * 1024) {
-          c.K >>= 1;
-          c.smem >>= 1;
-        }
-        if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
-      }
+    for (int w0 = 0; w0 + H <= n; ++w0) {
+      const int suffix = n - w0 - H;
+      if (suffix != 0 && suffix < cfg.min_suffix) continue;   // short suffix runs would not coalesce
+      WinCand c{w0, H, 0};
+      // work lists are bounded by (strings per side)^2; the exact size comes with the tables
+      const int ma = sq_win_max_class(n, sp->n_alpha, w0, H), mb = sq_win_max_class(n, sp->n_beta, w0, H);
+      c.smem = sq_win_smem_bytes(ma, mb, ma, mb, (ma * mb) / 8 + 1, (ma * mb) / 3 + 1, 8);
+      if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
     }
   }
 }
@@ -651,7 +636,27 @@ static uint32_t run_orbitals(const sq_layout* lay, const std::vector<int>& run) 
   return (1u << pt.i) | (1u << pt.a);
 }
 
+
+static int plan_launches_uncached(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out);
+
+// plans are cached on the layout (the beam search costs tens of milliseconds for a 720-operator circuit)
 static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out) {
+  if (lay->plan_version != g_plan_version) {
+    lay->plans.clear();
+    lay->plan_version = g_plan_version;
+  }
+  for (auto& pc : lay->plans)
+    if (pc.runs == runs) {
+      *out = pc.launches;
+      return SQ_OK;
+    }
+  SQ_CHECK(plan_launches_uncached(lay, runs, out));
+  if (lay->plans.size() >= 16) lay->plans.erase(lay->plans.begin());
+  lay->plans.push_back({runs, *out});
+  return SQ_OK;
+}
+
+static int plan_launches_uncached(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out) {
   out->clear();
   sq_space* sp = lay->sp;
   const WinConfig& cfg = win_config();
@@ -668,62 +673,41 @@ static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& ru
   auto simulate = [&](const WinCand& c, int head, std::vector<int>* sel) {
     sel->clear();
     uint32_t blocked = 0;
-    const int wlo = std::max(c.a0, c.b0), whi = std::min(c.a0 + c.Ha, c.b0 + c.Hb);
+    const int wlo = c.w0, whi = c.w0 + c.H;
     const uint32_t full = ((whi >= 32) ? 0xffffffffu : ((1u << whi) - 1u)) & ~((1u << wlo) - 1u);
     for (int t = head; t < m && (int)sel->size() < cfg.max_bricks; ++t) {
       if (done[t]) continue;
       if (pair[t] < 0) break;   // barrier
-      if (!(orb[t] & blocked) && sq_win_pair_ok(lay, pair[t], c.a0, c.Ha, c.b0, c.Hb)) sel->push_back(t);
+      if (!(orb[t] & blocked) && sq_win_pair_ok(lay, pair[t], c.w0, c.H)) sel->push_back(t);
       else blocked |= orb[t];
       if ((blocked & full) == full) break;
     }
   };
-  int head = 0;
-  std::vector<int> sel, best;
-  while (head < m) {
-    if (done[head]) { ++head; continue; }
-    if (pair[head] >= 0) {
-      // best window for the current front
-      for (;;) {
-        int bi = -1;
-        best.clear();
-        for (size_t ci = 0; ci < cands.size(); ++ci) {
-          if (cands[ci].dead) continue;
-          simulate(cands[ci], head, &sel);
-          if (sel.size() > best.size() || (sel.size() == best.size() && bi >= 0 && !sel.empty() && cands[ci].smem < cands[bi].smem)) {
-            best = sel;
-            bi = (int)ci;
-          }
-        }
-        if (bi < 0 || (int)best.size() < cfg.min_bricks) { best.clear(); break; }
-        const WinTables* wt = nullptr;
-        const WinCand& c = cands[bi];
-        SQ_CHECK(sq_get_win(sp, lay, c.a0, c.Ha, c.b0, c.Hb, c.K, &wt));
-        if (!wt || !wt->ok) { cands[bi].dead = true; continue; }
+  // usable candidates (tables are built once per layout and window)
+  for (WinCand& c : cands) {
+    bool any = false;
+    for (int t = 0; t < m && !any; ++t) any = pair[t] >= 0 && sq_win_pair_ok(lay, pair[t], c.w0, c.H);
+    if (!any) { c.dead = true; continue; }
+    const WinTables* wt = nullptr;
+    SQ_CHECK(sq_get_win(sp, lay, c.w0, c.H, &wt));
+    if (!wt || !wt->ok) c.dead = true;
+  }
+  auto emit_single = [&](int head, bool front) -> int {
+    // one brick alone; the front brick (everything before it executed) may be fused with the next pending brick
+    // when they commute (quad kernel)
+    int nxt = head + 1;
+    while (nxt < m && done[nxt]) ++nxt;
+    if (front && pair[head] >= 0 && nxt < m && pair[nxt] >= 0 && quad_enabled()) {
+      const QuadTables* qt = nullptr;
+      SQ_CHECK(get_quad(lay, pair[head], pair[nxt], &qt));
+      if (qt && qt->ok) {
         Launch l;
-        l.kind = 2;
-        l.runs = best;
-        l.wt = wt;
+        l.kind = 1;
+        l.runs = {head, nxt};
+        l.qt = qt;
         out->push_back(l);
-        for (int t : best) done[t] = 1;
-        break;
-      }
-      if (!best.empty()) continue;
-      // no window: the front brick alone, or fused with the next pending brick when they commute (quad kernel)
-      int nxt = head + 1;
-      while (nxt < m && done[nxt]) ++nxt;
-      if (nxt < m && pair[nxt] >= 0 && quad_enabled()) {
-        const QuadTables* qt = nullptr;
-        SQ_CHECK(get_quad(lay, pair[head], pair[nxt], &qt));
-        if (qt && qt->ok) {
-          Launch l;
-          l.kind = 1;
-          l.runs = {head, nxt};
-          l.qt = qt;
-          out->push_back(l);
-          done[head] = done[nxt] = 1;
-          continue;
-        }
+        done[head] = done[nxt] = 1;
+        return SQ_OK;
       }
     }
     Launch l;
@@ -731,6 +715,95 @@ static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& ru
     l.runs = {head};
     out->push_back(l);
     done[head] = 1;
+    return SQ_OK;
+  };
+  // Beam search over window sequences for every stretch of bricks between two barriers: a state is the set of
+  // executed runs; one step = one sweep (the window with its greedy closure of executable bricks).  States of
+  // equal depth are ranked by the number of executed bricks.
+  struct Node {
+    std::vector<char> done;
+    int head, parent, cand, n_done;
+    std::vector<int> sel;
+  };
+  const int BEAM = 24;
+  int head = 0;
+  std::vector<int> sel;
+  while (head < m) {
+    if (done[head]) { ++head; continue; }
+    bool coverable = false;
+    if (pair[head] >= 0)
+      for (const WinCand& c : cands) coverable |= !c.dead && sq_win_pair_ok(lay, pair[head], c.w0, c.H);
+    if (!coverable) { SQ_CHECK(emit_single(head, true)); continue; }
+    int seg_end = head;   // bricks up to the next barrier
+    while (seg_end < m && pair[seg_end] >= 0) ++seg_end;
+    std::vector<Node> nodes;
+    nodes.push_back({done, head, -1, -1, 0, {}});
+    std::vector<int> frontier = {0};
+    int goal = -1;
+    while (goal < 0) {
+      std::vector<int> next;
+      std::map<std::vector<char>, int> seen;
+      for (int ni : frontier) {
+        std::vector<char> cur = nodes[ni].done;   // copy: nodes may reallocate
+        int h = nodes[ni].head;
+        while (h < seg_end && cur[h]) ++h;
+        if (h >= seg_end) { goal = ni; break; }
+        done.swap(cur);   // simulate() reads `done`
+        bool head_covered = false;
+        std::vector<std::pair<int, std::vector<int>>> moves;
+        for (size_t ci = 0; ci < cands.size(); ++ci) {
+          if (cands[ci].dead) continue;
+          simulate(cands[ci], h, &sel);
+          while (!sel.empty() && sel.back() >= seg_end) sel.pop_back();
+          if (sel.empty()) continue;
+          head_covered |= (sel[0] == h);
+          moves.push_back({(int)ci, sel});
+        }
+        done.swap(cur);
+        if (!head_covered) moves.push_back({-1, std::vector<int>{h}});   // a brick no window takes: single launch
+        for (auto& mv : moves) {
+          std::vector<char> d2 = cur;
+          for (int t : mv.second) d2[t] = 1;
+          if (seen.count(d2)) continue;
+          seen[d2] = 1;
+          nodes.push_back({d2, h, ni, mv.first, nodes[ni].n_done + (int)mv.second.size(), mv.second});
+          next.push_back((int)nodes.size() - 1);
+        }
+      }
+      if (goal >= 0) break;
+      std::sort(next.begin(), next.end(), [&](int a, int b) {
+        return nodes[a].n_done != nodes[b].n_done ? nodes[a].n_done > nodes[b].n_done : nodes[a].head > nodes[b].head;
+      });
+      if ((int)next.size() > BEAM) next.resize(BEAM);
+      frontier.swap(next);
+      if (frontier.empty()) {
+        sq_set_error("launch planner: no progress");
+        return SQ_ERR_INVALID;
+      }
+    }
+    std::vector<int> path;
+    for (int ni = goal; nodes[ni].parent >= 0; ni = nodes[ni].parent) path.push_back(ni);
+    std::reverse(path.begin(), path.end());
+    // a short window sweep pays two extra gauge sweeps unless a neighbouring launch is a window sweep as well
+    std::vector<char> as_win(path.size(), 0);
+    for (size_t k = 0; k < path.size(); ++k) as_win[k] = nodes[path[k]].cand >= 0 && (int)nodes[path[k]].sel.size() >= cfg.min_bricks;
+    for (size_t k = 0; k < path.size(); ++k)
+      if (!as_win[k] && nodes[path[k]].cand >= 0 && ((k > 0 && as_win[k - 1]) || (k + 1 < path.size() && as_win[k + 1]))) as_win[k] = 2;
+    for (size_t k = 0; k < path.size(); ++k) {
+      const Node& nd = nodes[path[k]];
+      if (as_win[k]) {
+        Launch l;
+        l.kind = 2;
+        l.runs = nd.sel;
+        SQ_CHECK(sq_get_win(sp, lay, cands[nd.cand].w0, cands[nd.cand].H, &l.wt));
+        out->push_back(l);
+        for (int t : nd.sel) done[t] = 1;
+      } else {
+        for (int t : nd.sel)
+          if (!done[t]) SQ_CHECK(emit_single(t, false));
+      }
+    }
+    head = seg_end;
   }
   return SQ_OK;
 }
@@ -782,13 +855,15 @@ extern "C" int sq_layout_num_launches(const sq_layout* lay_c, int first, int las
   std::vector<Launch> launches;
   if (plan_range(lay, first, last, &runs, &launches) != SQ_OK) return -1;
   int n = 0;
+  bool in_gauge = false;
   for (auto& l : launches) {
     int nk;
     int64_t t;
     launch_cost(lay, runs, l, &nk, &t);
     n += nk;
+    if ((l.kind == 2) != in_gauge) { ++n; in_gauge = !in_gauge; }
   }
-  return n;
+  return n + (in_gauge ? 1 : 0);
 }
 
 // amplitudes read+written by the launches of ops [first,last): the algorithmic traffic of sq_ups_apply is
@@ -800,13 +875,15 @@ extern "C" int64_t sq_layout_touched_amplitudes(const sq_layout* lay_c, int firs
   std::vector<Launch> launches;
   if (plan_range(lay, first, last, &runs, &launches) != SQ_OK) return -1;
   int64_t total = 0;
+  bool in_gauge = false;
   for (auto& l : launches) {
     int nk;
     int64_t t;
     launch_cost(lay, runs, l, &nk, &t);
     total += t;
+    if ((l.kind == 2) != in_gauge) { total += lay->sp->local_len(); in_gauge = !in_gauge; }   // gauge sweep
   }
-  return total;
+  return total + (in_gauge ? lay->sp->local_len() : 0);
 }
 
 // plan summary for tools / tests: out[0] = launches, out[1] = window sweeps, out[2] = bricks inside window sweeps,
@@ -828,8 +905,7 @@ extern "C" int sq_layout_plan_stats(const sq_layout* lay_c, int first, int last,
   if (getenv("SQ_PLAN_DEBUG")) {
     for (auto& l : launches) {
       if (l.kind == 2) {
-        fprintf(stderr, "win a[%d,%d) b[%d,%d) K=%d smem=%zu :", l.wt->A.w0, l.wt->A.w0 + l.wt->A.H, l.wt->B.w0,
-                l.wt->B.w0 + l.wt->B.H, l.wt->K, l.wt->smem);
+        fprintf(stderr, "win [%d,%d) smem=%zu :", l.wt->w0, l.wt->w0 + l.wt->H, l.wt->smem);
         for (int t : l.runs) fprintf(stderr, " (%d,%d)", lay->pairs[lay->ops[runs[t][0]].pair].i, lay->pairs[lay->ops[runs[t][0]].pair].a);
         fprintf(stderr, "\n");
       } else if (l.kind == 1) {
@@ -1093,14 +1169,19 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
       float ms = 0;
       cudaEventElapsedTime(&ms, a, b);
       if (l->kind == 2)
-        fprintf(stderr, "launch win a[%d,%d) b[%d,%d) K=%d smem=%zu grid=%dx%d bricks=%zu : %.3f ms\n", l->wt->A.w0,
-                l->wt->A.w0 + l->wt->A.H, l->wt->B.w0, l->wt->B.w0 + l->wt->B.H, l->wt->K, l->wt->smem, l->wt->B.n_groups,
-                l->wt->A.n_groups, l->runs.size(), ms);
+        fprintf(stderr, "launch win [%d,%d) smem=%zu grid=%dx%d bricks=%zu : %.3f ms\n", l->wt->w0, l->wt->w0 + l->wt->H,
+                l->wt->smem, l->wt->n_chunks_b, l->wt->n_groups_a, l->runs.size(), ms);
       else
         fprintf(stderr, "launch kind=%d : %.3f ms\n", l->kind, ms);
     }
   };
+  // window sweeps work in the sign-free gauge (sqsv_win.cu); every other kernel in the reference's sign convention
+  bool in_gauge = false;
   for (const Launch& l : launches) {
+    if ((l.kind == 2) != in_gauge) {
+      SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
+      in_gauge = !in_gauge;
+    }
     TimingScope tscope(tev0, tev1, st, &l);
     auto& run = runs[l.runs[0]];
     const LayoutOp& op = lay->ops[run[0]];
@@ -1148,6 +1229,7 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
       return SQ_ERR_INVALID;
     }
   }
+  if (in_gauge) SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
   return SQ_OK;
 }
 

@@ -126,6 +126,7 @@ struct sq_space {
   std::vector<uint32_t> strA, strB; // occupation masks in itertools.combinations order
   std::vector<int32_t> rankA, rankB;  // mask -> string index (-1 if wrong electron count); 2^n entries
   uint32_t *d_strA = nullptr, *d_strB = nullptr;
+  uint32_t* d_gwordB = nullptr;     // gauge words of the beta strings (sqsv_win.cu), built lazily
   int32_t *d_rankA = nullptr, *d_rankB = nullptr;
   // reduction scratch
   double* d_partial = nullptr;
@@ -151,6 +152,18 @@ struct LayoutOp {
   GenOp* multi = nullptr;
 };
 
+// one kernel launch of the plan of sq_ups_apply (sqsv_api.cu)
+struct Launch {
+  int kind = 0;                 // 0 single run (tile / generic / sa_double / null), 1 quad (2 runs), 2 window sweep
+  std::vector<int> runs;        // run indices in execution order
+  const struct WinTables* wt = nullptr;
+  const struct QuadTables* qt = nullptr;
+};
+struct PlanCache {
+  std::vector<std::vector<int>> runs;
+  std::vector<Launch> launches;
+};
+
 struct sq_layout {
   sq_space* sp;
   std::vector<LayoutOp> ops;
@@ -159,7 +172,9 @@ struct sq_layout {
   std::vector<GenTables> gens;
   std::map<std::vector<int>, int> gen_index;
   std::map<std::pair<int, int>, QuadTables> quads;   // built lazily per (pair1, pair2)
-  std::map<std::array<int, 5>, struct WinTables*> wins;   // built lazily per (a0, Ha, b0, Hb, K) (sqsv_win.cu)
+  std::vector<PlanCache> plans;   // launch plans by run structure (sqsv_api.cu)
+  int plan_version = 0;
+  std::map<std::array<int, 5>, struct WinTables*> wins;   // built lazily per (w0, H) (sqsv_win.cu)
 };
 
 static inline int sq_row_owner(const sq_space* sp, int64_t row) {
@@ -191,31 +206,28 @@ void sq_build_tile_matrices(const TileStep* steps, int n_steps, int sigma, TileM
 // same with explicit signs of the alpha single, beta single and pair double generators
 void sq_build_tile_matrices3(const TileStep* steps, int n_steps, int ea, int eb, int ed, TileMatrices* tm);
 
-// Tables of the window kernel (sqsv_win.cu): one orbital window per spin, see the header of that file.
+// Tables of the window kernel (sqsv_win.cu): one orbital window [w0, w0+H), see the header of that file.
 #define SQ_WIN_MAX_BRICKS 16
-struct WinSide {
-  int w0 = 0, H = 0;
-  int ncls = 0, LT = 0, n_groups = 0, max_cnt = 0;
-  int2* d_groups = nullptr;
-  int* d_delta = nullptr;
-  uint32_t* d_gbits = nullptr;
-  int* d_cnt = nullptr;
-  uint32_t* d_items = nullptr;
-  int2* d_itemcnt = nullptr;
-};
 struct WinTables {
   bool ok = false;
-  int K = 1, logK = 0;             // consecutive beta suffixes per CTA
-  WinSide A, B;
+  int w0 = 0, H = 0;
+  int LTA = 0, LTB = 0, max_a = 0, max_b = 0, lanes_j = 0;
+  int n_groups_a = 0, n_chunks_b = 0;
+  int maxQ = 0, maxS = 0, tile_doubles = 0;
+  int2 *d_groupsA = nullptr, *d_clsA = nullptr, *d_chunksB = nullptr, *d_clsB = nullptr;
+  int *d_deltaA = nullptr, *d_deltaB = nullptr, *d_gbaseB = nullptr;
+  uint32_t* d_lists = nullptr;
+  int4* d_listidx = nullptr;
   std::vector<int> pair_local;     // layout pair index -> pair id inside the window tables, -1 if unusable
   std::vector<int8_t> eps;         // [3 * local pair] constant signs of Ta, Tb, pair double in the window gauge
-  size_t smem = 0;                 // dynamic shared memory per CTA (largest tile + staged tables)
-  int tile_doubles = 0;            // doubles of the largest tile
+  size_t smem = 0;                 // dynamic shared memory per CTA with SQ_WIN_MAX_BRICKS bricks
   int64_t touched = 0;             // amplitudes per launch (the whole local vector)
 };
 int sq_win_max_class(int n, int ne, int w0, int H);
-bool sq_win_pair_ok(const sq_layout* lay, int pair, int a0, int Ha, int b0, int Hb);
-int sq_get_win(sq_space* sp, sq_layout* lay, int a0, int Ha, int b0, int Hb, int K, const WinTables** out);
+size_t sq_win_smem_bytes(int max_a, int max_b, int lta, int ltb, int maxQ, int maxS, int n_bricks);
+int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st);
+bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H);
+int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** out);
 void sq_free_win_tables(WinTables* wt);
 int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
                   int n_bricks, double* state, cudaStream_t st);

@@ -131,6 +131,7 @@ extern "C" int sq_space_destroy(sq_space* sp) {
   cudaSetDevice(sp->device);
   sq_hamiltonian_release(sp);
   cudaFree(sp->d_strA);
+  cudaFree(sp->d_gwordB);
   cudaFree(sp->d_strB);
   cudaFree(sp->d_rankA);
   cudaFree(sp->d_rankB);

@@ -1,23 +1,32 @@
 // "window" kernel: a whole group of bricks in ONE read + ONE write of the CI vector, through shared memory.
 //
-// Pick an orbital window [w0, w0+H) per spin.  A string is (prefix on orbitals < w0, window part, suffix on
-// orbitals >= w0+H).  An operator whose orbitals all lie inside the window never changes prefix or suffix,
-// conserves the electron count e_w of the window part, and its fermionic sign depends on window bits only.
+// Pick an orbital window [w0, w0+H) (the same for both spins).  A string is (prefix on orbitals < w0, window part,
+// suffix on orbitals >= w0+H).  An operator whose orbitals all lie inside the window never changes prefix or
+// suffix, conserves the electron count e_w of the window part, and its fermionic sign depends on window bits only.
 // Hence the coefficient matrix C[Ia][Ib] decomposes into independent tiles
-//     (alpha prefix, alpha suffix; beta prefix, beta suffix)  x  (C(Ha,e_wa) rows) x (C(Hb,e_wb) columns)
+//     (alpha prefix, alpha suffix; beta prefix, beta suffix)  x  (C(H,e_wa) rows) x (C(H,e_wb) columns)
 // and EVERY brick inside the window maps each tile onto itself.  In itertools.combinations order
 //     I(prefix, w, suffix) = start(prefix) + off_{e_rem}(w) + rank(suffix),
 // so the rows/columns of a tile sit at base + delta[class][j] (class = (electrons left after the prefix, e_w),
 // j = rank of the window part), and consecutive suffixes of the same (prefix, e_w) are consecutive indices.
-//   * beta "run" windows (large suffix): a CTA takes K consecutive suffixes, so every tile column is a
-//     contiguous K-double run in memory (K = 16 -> 128 B);
-//   * beta "block" windows (the window reaches the last orbital): delta[j] = j, the tile columns are one
-//     contiguous segment.
-// A CTA loads its tile (rows need no contiguity: one row is one coalesced stream), applies up to
-// SQ_WIN_MAX_BRICKS bricks on it in shared memory with the gauge-fixed 4x4 / 2x2 matrices of tile_kernel_v2,
-// and stores it back.  The commutation-aware planner of sqsv_api.cu chooses windows and brick groups; a tUPS
-// layer at n = 16 needs ~3 sweeps of the vector (often fewer, bricks of the next layer ride along) instead of
-// 15 (tile_kernel_v2) or 8 (quad_kernel).
+//
+// A CTA works on a BATCH of G = 16 tiles with the same alpha rows and the same beta class:
+//   * "run" windows (a beta suffix exists): the 16 tiles are 16 consecutive beta suffixes, i.e. every tile column is
+//     a contiguous 128-byte run in memory;
+//   * the "block" window (the window reaches the last orbital): the 16 tiles are 16 beta prefixes of one class, each
+//     with contiguous columns.
+// The batch index g is the fastest index in shared memory (tile[row][col][g], padded to 17), so the 16 lanes of a
+// half-warp work on the SAME (row item, column item) of 16 tiles: every data access is bank-conflict free and every
+// table look-up is uniform.  Brick work comes as ready-made lists per (orbital pair, e_wa, e_wb) built on the host:
+// quad entries {r, r', c, c'} (4x4 update) and single entries (2x2 rotation), fetched one brick ahead.
+//
+// Sign-free gauge.  The reference orders spin orbitals a0 b0 a1 b1 ...; re-ordering them as (all alpha)(all beta)
+// multiplies determinant |A,B> by D(A,B) = (-1)^{#{(p,q): p in A, q in B, q < p}}.  In that gauge every
+// nearest-neighbour hop p <-> p+1 of either spin and the pair double carry a constant sign (checked on the host
+// per pair, folded into the brick matrices), so a brick is ONE constant 4x4 matrix / 2x2 rotation for all tiles.
+// The window-local part of D is applied when a tile is loaded and again when it is stored.
+//
+// The commutation-aware planner of sqsv_api.cu chooses windows and brick groups.
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -28,15 +37,26 @@
 
 #define WIN_THREADS 256
 #define WIN_WARPS (WIN_THREADS / 32)
+#define WIN_G 16                      // tiles per CTA
+#define WIN_GP 17                     // padded batch stride in shared memory
+#define WIN_SLOTS (WIN_THREADS / WIN_G)
 
-struct WinSideDev {
-  const int2* groups;      // alpha: {first row (shard-relative), class}; beta: {first column, class | n_suffix << 16}
-  const int* delta;        // [ncls][LT] offset of window string j from the group base
-  const uint32_t* gbits;   // [ncls][LT] gauge word of window string j: alpha = occupation mask, beta = parity-prefix mask
-  const int* cnt;          // [ncls] number of window strings
-  const uint32_t* items;   // [n_pairs][ncls][LT] work items of a brick: src strings first, then inert ones
-  const int2* itemcnt;     // [n_pairs][ncls] {n_src, n_inert}
-  int LT, ncls;
+struct WinDev {
+  // alpha side
+  const int2* groupsA;     // {first row (shard-relative), class}
+  const int2* clsA;        // [ncls] {number of window strings, e_w}
+  const int* deltaA;       // [ncls][LTA] offset of window string j from the group base
+  // beta side
+  const int2* chunksB;     // {chunk id, class | tiles in the batch << 16}
+  const int* gbaseB;       // [chunk][WIN_G] first column of every tile of the batch
+  const int2* clsB;
+  const int* deltaB;
+  // brick work lists
+  const uint32_t* lists;   // quad entries jr | jr' << 8 | jc << 16 | jc' << 24, then single entries jr0 | jc0 << 8 | jr1 << 16 | jc1 << 24
+  const int4* listidx;     // [pair][e_wa][e_wb] {offset, n_quad, n_alpha_single, n_beta_single}
+  int LTA, LTB, H1;        // H1 = H + 1
+  int lanes_j;             // top window: the tiles of a batch are far apart, global accesses run along the columns
+  int tile_doubles, maxQ, maxS;
 };
 
 struct WinBrick {
@@ -49,20 +69,6 @@ struct WinProgram {
   WinBrick br[SQ_WIN_MAX_BRICKS];
 };
 
-__device__ __forceinline__ double wflip(double x, int neg) {
-  return __hiloint2double(__double2hiint(x) ^ (neg << 31), __double2loint(x));
-}
-
-// item code: bits 9:0 window string j, 19:10 partner j' (src only)
-#define IT_J(c) ((int)((c)&1023u))
-#define IT_JP(c) ((int)(((c) >> 10) & 1023u))
-
-// tile data is touched once per sweep: keep it out of L1 so that the (small, hot) window tables stay there
-__device__ __forceinline__ double ldg_stream(const double* p) {
-  double v;
-  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
@@ -72,215 +78,211 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __device__ __forceinline__ void stg_stream(double* p, double v) {
   asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+__device__ __forceinline__ double lds64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 
-// Sign-free gauge.  The reference orders spin orbitals a0 b0 a1 b1 ...; re-ordering them as (all alpha)(all beta)
-// multiplies determinant |A,B> by D(A,B) = (-1)^{#{(p,q): p in A, q in B, q < p}}.  In that gauge every
-// nearest-neighbour hop p <-> p+1 of either spin and the pair double carry a constant sign (checked on the host
-// per pair, folded into the brick matrices), so a brick is ONE constant 4x4 matrix / 2x2 rotation for all tiles.
-// The window-local part of D is applied when a tile is loaded and again when it is stored.
-//
-// Brick work inside a tile, flat over the CTA's threads (one item per thread per step):
-//   (src row item) x (src column item) x k : 4x4 on {r,r'} x {c,c'}
-//   (src row item) x (inert column)    x k : alpha single on {r,r'} x {c}
-//   (inert row)    x (src column item) x k : beta single on {r} x {c,c'}
-// Shared memory: [tile Rn x LD doubles][beta delta, beta gauge words: LTB each][alpha delta, alpha gauge words:
-// LTA each][brick items, double buffered: 2 x (LTA + LTB)].  All table reads inside the loops are LDS: the tables
-// of a CTA's classes are staged once, the item lists of brick b+1 are fetched while brick b is computed.
-template <int LOGK>
+// The vector is in the sign-free gauge (gauge_kernel) while window sweeps run, so the kernel is sign-free:
+// load the batch, apply the bricks, store the batch.
+// Shared memory: [tile: Rn x Wn x 17 doubles][beta delta: LTB][alpha delta: LTA][batch bases: 16][list headers: int4 x
+// SQ_WIN_MAX_BRICKS][per brick: maxQ uint2 quad entries + maxS uint32 single entries, BYTE offsets in 16-bit fields].
+// Global round trips per CTA: class tables + list headers, then (tile copies in flight) the list entries, then the
+// stores.
 __global__ void __launch_bounds__(WIN_THREADS, 3)
-win_kernel(double* __restrict__ C, int64_t NB, const WinSideDev A, const WinSideDev B, const WinProgram P, int tile_doubles) {
-  constexpr int K = 1 << LOGK;
+win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_constant__ WinProgram P) {
   extern __shared__ double tile[];
-  int* const sdB = reinterpret_cast<int*>(tile + tile_doubles);
-  uint32_t* const sgB = reinterpret_cast<uint32_t*>(sdB + B.LT);
-  int* const sdA = reinterpret_cast<int*>(sgB + B.LT);
-  uint32_t* const sgA = reinterpret_cast<uint32_t*>(sdA + A.LT);
-  uint32_t* const sitems = sgA + A.LT;
-  const int ITS = A.LT + B.LT;   // words per item buffer: [alpha items LTA][beta items LTB]
-  const int2 ga = __ldg(A.groups + blockIdx.y), gb = __ldg(B.groups + blockIdx.x);
-  const int clsA = ga.y, clsB = gb.y & 0xffff, kcnt = gb.y >> 16;
-  const int Rn = __ldg(A.cnt + clsA), Wn = __ldg(B.cnt + clsB);
-  const int LD = Wn << LOGK;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* const base = C + gb.x;
+  int* const sdB = reinterpret_cast<int*>(tile + W.tile_doubles);
+  int* const sdA = sdB + W.LTB;
+  int* const sbase = sdA + W.LTA;
+  int4* const shdr = reinterpret_cast<int4*>(sbase + WIN_G);             // 16-byte aligned (host pads the table sizes)
+  uint2* const qall = reinterpret_cast<uint2*>(shdr + SQ_WIN_MAX_BRICKS);
+  const int per_brick = 2 * W.maxQ + W.maxS;                             // words per brick: quads first, then singles
 
-  int lp = P.pair[0];
-  int2 nA = __ldg(A.itemcnt + lp * A.ncls + clsA), nB = __ldg(B.itemcnt + lp * B.ncls + clsB);
-  for (int t = threadIdx.x; t < Wn; t += WIN_THREADS) {
-    sdB[t] = __ldg(B.delta + clsB * B.LT + t);
-    sgB[t] = __ldg(B.gbits + clsB * B.LT + t);
-  }
-  for (int t = threadIdx.x; t < Rn; t += WIN_THREADS) {
-    sdA[t] = __ldg(A.delta + clsA * A.LT + t);
-    sgA[t] = __ldg(A.gbits + clsA * A.LT + t);
-  }
-  for (int t = threadIdx.x; t < ITS; t += WIN_THREADS)
-    sitems[t] = (t < A.LT) ? __ldg(A.items + (size_t)(lp * A.ncls + clsA) * A.LT + t)
-                           : __ldg(B.items + (size_t)(lp * B.ncls + clsB) * B.LT + (t - A.LT));
+  const int2 ga = __ldg(W.groupsA + blockIdx.y), gb = __ldg(W.chunksB + blockIdx.x);
+  const int clsA = ga.y, clsB = gb.y & 0xffff, kcnt = gb.y >> 16;
+  const int2 ca2 = __ldg(W.clsA + clsA), cb2 = __ldg(W.clsB + clsB);
+  const int Rn = ca2.x, Wn = cb2.x;
+  const int RS = Wn * WIN_GP;               // row stride (doubles)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = threadIdx.x & (WIN_G - 1), slot = threadIdx.x / WIN_G;
+
+  // ---- round trip 1: class tables and list headers ----
+  for (int t = threadIdx.x; t < Wn; t += WIN_THREADS) sdB[t] = __ldg(W.deltaB + clsB * W.LTB + t);
+  for (int t = threadIdx.x; t < Rn; t += WIN_THREADS) sdA[t] = __ldg(W.deltaA + clsA * W.LTA + t);
+  if (threadIdx.x < WIN_G) sbase[threadIdx.x] = __ldg(W.gbaseB + gb.x * WIN_G + threadIdx.x);
+  if (threadIdx.x >= 32 && (int)threadIdx.x < 32 + P.n)
+    shdr[threadIdx.x - 32] = __ldg(W.listidx + (P.pair[threadIdx.x - 32] * W.H1 + ca2.y) * W.H1 + cb2.y);
   __syncthreads();
 
-  // the whole tile is requested at once with 8-byte async copies (no registers in between: the CTA has its full
-  // tile in flight), then the gauge sign is applied in shared memory
+  // ---- round trip 2: the whole batch with 8-byte async copies, and (meanwhile) the list entries ----
   const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tile);
-  for (int r = warp; r < Rn; r += WIN_WARPS) {
-    const double* src = base + (int64_t)(ga.x + sdA[r]) * NB;
-    const uint32_t dst = tb + (uint32_t)(r * LD) * 8u;
+  if (W.lanes_j) {
+    const int NX = kcnt * Wn;
+    const float invW = 1.0f / (float)Wn;
+    for (int r = warp; r < Rn; r += WIN_WARPS) {
+      const double* src = C + (int64_t)(ga.x + sdA[r]) * NB;
+      const uint32_t dst = tb + (uint32_t)(r * RS) * 8u;
+      for (int x = lane; x < NX; x += 32) {
+        const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
+        cp_async8(dst + (uint32_t)(j * WIN_GP + gg) * 8u, src + sbase[gg] + sdB[j]);
+      }
+    }
+  } else {
+    const int myb = sbase[g];
+    for (int r = warp; r < Rn; r += WIN_WARPS) {
+      const double* src = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
+      const uint32_t dst = tb + (uint32_t)(r * RS + g) * 8u;
+      if (g < kcnt) {
 #pragma unroll 4
-    for (int x = lane; x < LD; x += 32) {
-      const int j = x >> LOGK, k = x & (K - 1);
-      if (LOGK == 0 || k < kcnt) cp_async8(dst + (uint32_t)x * 8u, src + sdB[j] + k);
+        for (int j = lane >> 4; j < Wn; j += 2) cp_async8(dst + (uint32_t)(j * WIN_GP) * 8u, src + sdB[j]);
+      }
+    }
+  }
+  {
+    // one entry per thread and brick (maxQ + maxS <= WIN_THREADS): all loads first, then scale to byte offsets
+    uint32_t raw[SQ_WIN_MAX_BRICKS];
+#pragma unroll
+    for (int b = 0; b < SQ_WIN_MAX_BRICKS; ++b) {
+      raw[b] = 0u;
+      if (b < P.n) {
+        const int4 li = shdr[b];
+        if ((int)threadIdx.x < li.y + li.z + li.w) raw[b] = __ldg(W.lists + li.x + threadIdx.x);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < SQ_WIN_MAX_BRICKS; ++b) {
+      if (b < P.n) {
+        const int4 li = shdr[b];
+        const int t = threadIdx.x;
+        const uint32_t w = raw[b];
+        uint32_t* dst = reinterpret_cast<uint32_t*>(qall) + b * per_brick;
+        if (t < li.y) {
+          const uint32_t r0 = (w & 255u) * RS, r1 = ((w >> 8) & 255u) * RS, c0 = ((w >> 16) & 255u) * WIN_GP, c1 = (w >> 24) * WIN_GP;
+          reinterpret_cast<uint2*>(dst)[t] = make_uint2((r0 | (r1 << 16)) << 3, (c0 | (c1 << 16)) << 3);
+        } else if (t < li.y + li.z + li.w) {
+          const uint32_t o0 = (w & 255u) * RS + ((w >> 8) & 255u) * WIN_GP, o1 = ((w >> 16) & 255u) * RS + (w >> 24) * WIN_GP;
+          dst[2 * W.maxQ + (t - li.y)] = (o0 | (o1 << 16)) << 3;
+        }
+      }
     }
   }
   cp_async_wait_all();
-  __syncthreads();
-  for (int r = warp; r < Rn; r += WIN_WARPS) {
-    const uint32_t wa = sgA[r];
-    double* dst = tile + r * LD;
-    for (int x = lane; x < LD; x += 32)
-      if (__popc(wa & sgB[x >> LOGK]) & 1) dst[x] = -dst[x];
-  }
 
-  // Brick loop, column-stationary: a thread owns one column lane (column item x k) and walks down the row items,
-  // so the per-item work is one LDS of the packed row offsets, four address adds and the 4x4 / 2x2 update.
-  // Threads [0,TS) take the src column lanes (4x4 with src rows, beta single with inert rows), threads [TS,256)
-  // the inert column lanes (alpha single with src rows); TS follows the work ratio in whole warps.
+  // ---- bricks ----
+  const uint32_t tgb = tb + (uint32_t)g * 8u;
+  const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
   for (int b = 0; b < P.n; ++b) {
-    const uint32_t* itA = sitems + (b & 1) * ITS;
-    const uint32_t* itB = itA + A.LT;
-    const int nRS = nA.x, nRI = nA.y, nCS = nB.x, nCI = nB.y;
-    const int NS = nCS << LOGK, NI = nCI << LOGK;
-    // fetch the next brick's scalars and item lists now; they are parked in the other buffer after the loops
-    uint32_t nxt[3] = {0u, 0u, 0u};
-    const bool more = b + 1 < P.n;
-    if (more) {
-      lp = P.pair[b + 1];
-      nA = __ldg(A.itemcnt + lp * A.ncls + clsA);
-      nB = __ldg(B.itemcnt + lp * B.ncls + clsB);
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int t = threadIdx.x + q * WIN_THREADS;
-        if (t < ITS)
-          nxt[q] = (t < A.LT) ? __ldg(A.items + (size_t)(lp * A.ncls + clsA) * A.LT + t)
-                              : __ldg(B.items + (size_t)(lp * B.ncls + clsB) * B.LT + (t - A.LT));
+    __syncthreads();   // convergent: every thread of the CTA, also the lanes of unused tiles
+    if (g >= kcnt) continue;
+    const int4 hd = shdr[b];
+    const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
+    const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
+    const WinBrick& br = P.br[b];
+    if (slot < nQ) {   // 4x4 entries, two per step: all loads before the first store
+      int e = slot;
+      for (; e + WIN_SLOTS < nQ; e += 2 * WIN_SLOTS) {
+        uint32_t ux, uy, vx, vy;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(ql + (uint32_t)(e + WIN_SLOTS) * 8u));
+        const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
+        const uint32_t b0 = tgb + (vx & 0xffffu), b1 = tgb + (vx >> 16), d0 = vy & 0xffffu, d1 = vy >> 16;
+        const double y0 = lds64(a0 + c0), y1 = lds64(a0 + c1), y2 = lds64(a1 + c0), y3 = lds64(a1 + c1);
+        const double z0 = lds64(b0 + d0), z1 = lds64(b0 + d1), z2 = lds64(b1 + d0), z3 = lds64(b1 + d1);
+        sts64(a0 + c0, br.m[0] * y0 + br.m[1] * y1 + br.m[2] * y2 + br.m[3] * y3);
+        sts64(a0 + c1, br.m[4] * y0 + br.m[5] * y1 + br.m[6] * y2 + br.m[7] * y3);
+        sts64(a1 + c0, br.m[8] * y0 + br.m[9] * y1 + br.m[10] * y2 + br.m[11] * y3);
+        sts64(a1 + c1, br.m[12] * y0 + br.m[13] * y1 + br.m[14] * y2 + br.m[15] * y3);
+        sts64(b0 + d0, br.m[0] * z0 + br.m[1] * z1 + br.m[2] * z2 + br.m[3] * z3);
+        sts64(b0 + d1, br.m[4] * z0 + br.m[5] * z1 + br.m[6] * z2 + br.m[7] * z3);
+        sts64(b1 + d0, br.m[8] * z0 + br.m[9] * z1 + br.m[10] * z2 + br.m[11] * z3);
+        sts64(b1 + d1, br.m[12] * z0 + br.m[13] * z1 + br.m[14] * z2 + br.m[15] * z3);
+      }
+      if (e < nQ) {
+        uint32_t ux, uy;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
+        const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
+        const double y0 = lds64(a0 + c0), y1 = lds64(a0 + c1), y2 = lds64(a1 + c0), y3 = lds64(a1 + c1);
+        sts64(a0 + c0, br.m[0] * y0 + br.m[1] * y1 + br.m[2] * y2 + br.m[3] * y3);
+        sts64(a0 + c1, br.m[4] * y0 + br.m[5] * y1 + br.m[6] * y2 + br.m[7] * y3);
+        sts64(a1 + c0, br.m[8] * y0 + br.m[9] * y1 + br.m[10] * y2 + br.m[11] * y3);
+        sts64(a1 + c1, br.m[12] * y0 + br.m[13] * y1 + br.m[14] * y2 + br.m[15] * y3);
       }
     }
-    const int ws = NS * (2 * nRS + nRI), wi = NI * nRS;
-    int TS = WIN_THREADS;
-    if (wi > 0) {
-      TS = ws > 0 ? ((int)((float)(WIN_THREADS / 32) * (float)ws / (float)(ws + wi) + 0.5f)) * 32 : 0;
-      TS = ws > 0 ? min(max(TS, 32), WIN_THREADS - 32) : 0;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < TS) {
-      if (NS > 0) {
-        const int CS = min(NS, TS);
-        const int RG = TS / CS;
-        const int rg = (int)(((float)threadIdx.x + 0.5f) / (float)CS);
-        const int cl0 = threadIdx.x - rg * CS;
-        if (rg < RG) {
-          double m[16];
+    if (slot < nS) {   // 2x2 entries: alpha singles first, then beta singles; four per step
+      int e = slot;
+      for (; e + 3 * WIN_SLOTS < nS; e += 4 * WIN_SLOTS) {
+        uint32_t o0[4], o1[4];
+        double y0[4], y1[4];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) m[e] = P.br[b].m[e];
-          const double cbt = P.br[b].cb, sbt = P.br[b].sb;
-          for (int cl = cl0; cl < NS; cl += CS) {
-            const int k = cl & (K - 1);
-            if (LOGK != 0 && k >= kcnt) continue;
-            const uint32_t cw = itB[cl >> LOGK];
-            const int c = (IT_J(cw) << LOGK) + k, cp = (IT_JP(cw) << LOGK) + k;
-            int ri = rg;
-            for (; ri + RG < nRS; ri += 2 * RG) {   // two src row items per step, loads before stores
-              const uint32_t w0 = itA[ri], w1 = itA[ri + RG];
-              const int a0 = IT_J(w0) * LD, a1 = IT_JP(w0) * LD, b0 = IT_J(w1) * LD, b1 = IT_JP(w1) * LD;
-              const double y0 = tile[a0 + c], y1 = tile[a0 + cp], y2 = tile[a1 + c], y3 = tile[a1 + cp];
-              const double z0 = tile[b0 + c], z1 = tile[b0 + cp], z2 = tile[b1 + c], z3 = tile[b1 + cp];
-              tile[a0 + c] = m[0] * y0 + m[1] * y1 + m[2] * y2 + m[3] * y3;
-              tile[a0 + cp] = m[4] * y0 + m[5] * y1 + m[6] * y2 + m[7] * y3;
-              tile[a1 + c] = m[8] * y0 + m[9] * y1 + m[10] * y2 + m[11] * y3;
-              tile[a1 + cp] = m[12] * y0 + m[13] * y1 + m[14] * y2 + m[15] * y3;
-              tile[b0 + c] = m[0] * z0 + m[1] * z1 + m[2] * z2 + m[3] * z3;
-              tile[b0 + cp] = m[4] * z0 + m[5] * z1 + m[6] * z2 + m[7] * z3;
-              tile[b1 + c] = m[8] * z0 + m[9] * z1 + m[10] * z2 + m[11] * z3;
-              tile[b1 + cp] = m[12] * z0 + m[13] * z1 + m[14] * z2 + m[15] * z3;
-            }
-            if (ri < nRS) {
-              const uint32_t w0 = itA[ri];
-              const int a0 = IT_J(w0) * LD, a1 = IT_JP(w0) * LD;
-              const double y0 = tile[a0 + c], y1 = tile[a0 + cp], y2 = tile[a1 + c], y3 = tile[a1 + cp];
-              tile[a0 + c] = m[0] * y0 + m[1] * y1 + m[2] * y2 + m[3] * y3;
-              tile[a0 + cp] = m[4] * y0 + m[5] * y1 + m[6] * y2 + m[7] * y3;
-              tile[a1 + c] = m[8] * y0 + m[9] * y1 + m[10] * y2 + m[11] * y3;
-              tile[a1 + cp] = m[12] * y0 + m[13] * y1 + m[14] * y2 + m[15] * y3;
-            }
-            // inert rows: beta single on (c, c')
-            ri = rg;
-            for (; ri + RG < nRI; ri += 2 * RG) {
-              const int a0 = IT_J(itA[nRS + ri]) * LD, b0 = IT_J(itA[nRS + ri + RG]) * LD;
-              const double y0 = tile[a0 + c], y1 = tile[a0 + cp], z0 = tile[b0 + c], z1 = tile[b0 + cp];
-              tile[a0 + c] = cbt * y0 - sbt * y1;
-              tile[a0 + cp] = cbt * y1 + sbt * y0;
-              tile[b0 + c] = cbt * z0 - sbt * z1;
-              tile[b0 + cp] = cbt * z1 + sbt * z0;
-            }
-            if (ri < nRI) {
-              const int a0 = IT_J(itA[nRS + ri]) * LD;
-              const double y0 = tile[a0 + c], y1 = tile[a0 + cp];
-              tile[a0 + c] = cbt * y0 - sbt * y1;
-              tile[a0 + cp] = cbt * y1 + sbt * y0;
-            }
-          }
+        for (int t = 0; t < 4; ++t) {
+          uint32_t u;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)(e + t * WIN_SLOTS) * 4u));
+          o0[t] = tgb + (u & 0xffffu);
+          o1[t] = tgb + (u >> 16);
+          y0[t] = lds64(o0[t]);
+          y1[t] = lds64(o1[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const bool al = e + t * WIN_SLOTS < nSa;
+          const double c = al ? br.ca : br.cb, s = al ? br.sa : br.sb;
+          sts64(o0[t], c * y0[t] - s * y1[t]);
+          sts64(o1[t], c * y1[t] + s * y0[t]);
         }
       }
-    } else if (NI > 0 && nRS > 0) {
-      const int TI = WIN_THREADS - TS, t = threadIdx.x - TS;
-      const int CS = min(NI, TI);
-      const int RG = TI / CS;
-      const int rg = (int)(((float)t + 0.5f) / (float)CS);
-      const int cl0 = t - rg * CS;
-      if (rg < RG) {
-        const double ca = P.br[b].ca, sa = P.br[b].sa;
-        for (int cl = cl0; cl < NI; cl += CS) {
-          const int k = cl & (K - 1);
-          if (LOGK != 0 && k >= kcnt) continue;
-          const int c = (IT_J(itB[nCS + (cl >> LOGK)]) << LOGK) + k;
-          int ri = rg;
-          for (; ri + RG < nRS; ri += 2 * RG) {
-            const uint32_t w0 = itA[ri], w1 = itA[ri + RG];
-            const int a0 = IT_J(w0) * LD + c, a1 = IT_JP(w0) * LD + c, b0 = IT_J(w1) * LD + c, b1 = IT_JP(w1) * LD + c;
-            const double y0 = tile[a0], y1 = tile[a1], z0 = tile[b0], z1 = tile[b1];
-            tile[a0] = ca * y0 - sa * y1;
-            tile[a1] = ca * y1 + sa * y0;
-            tile[b0] = ca * z0 - sa * z1;
-            tile[b1] = ca * z1 + sa * z0;
-          }
-          if (ri < nRS) {
-            const uint32_t w0 = itA[ri];
-            const int a0 = IT_J(w0) * LD + c, a1 = IT_JP(w0) * LD + c;
-            const double y0 = tile[a0], y1 = tile[a1];
-            tile[a0] = ca * y0 - sa * y1;
-            tile[a1] = ca * y1 + sa * y0;
-          }
-        }
-      }
-    }
-    if (more) {
-      uint32_t* dst = sitems + ((b + 1) & 1) * ITS;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int t = threadIdx.x + q * WIN_THREADS;
-        if (t < ITS) dst[t] = nxt[q];
+      for (; e < nS; e += WIN_SLOTS) {
+        uint32_t u;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
+        const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16);
+        const bool al = e < nSa;
+        const double c = al ? br.ca : br.cb, s = al ? br.sa : br.sb;
+        const double y0 = lds64(o0), y1 = lds64(o1);
+        sts64(o0, c * y0 - s * y1);
+        sts64(o1, c * y1 + s * y0);
       }
     }
   }
   __syncthreads();
 
-  for (int r = warp; r < Rn; r += WIN_WARPS) {
-    double* dstg = base + (int64_t)(ga.x + sdA[r]) * NB;
-    const uint32_t wa = sgA[r];
-    const double* srct = tile + r * LD;
+  // ---- store ----
+  if (W.lanes_j) {
+    const int NX = kcnt * Wn;
+    const float invW = 1.0f / (float)Wn;
+    for (int r = warp; r < Rn; r += WIN_WARPS) {
+      double* dst = C + (int64_t)(ga.x + sdA[r]) * NB;
+      const double* srct = tile + r * RS;
+      for (int x = lane; x < NX; x += 32) {
+        const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
+        stg_stream(dst + sbase[gg] + sdB[j], srct[j * WIN_GP + gg]);
+      }
+    }
+  } else if (g < kcnt) {
+    const int myb = sbase[g];
+    for (int r = warp; r < Rn; r += WIN_WARPS) {
+      double* dst = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
+      const double* srct = tile + r * RS + g;
 #pragma unroll 4
-    for (int x = lane; x < LD; x += 32) {
-      const int j = x >> LOGK, k = x & (K - 1);
-      if (LOGK == 0 || k < kcnt) stg_stream(dstg + sdB[j] + k, wflip(srct[x], __popc(wa & sgB[j]) & 1));
+      for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * WIN_GP]);
+    }
+  }
+}
+
+// x[Ia][Ib] *= D(A,B) = (-1)^{popc(A & gword(B))}: into / out of the sign-free gauge (its own inverse)
+__global__ void __launch_bounds__(256)
+gauge_kernel(double* __restrict__ C, int64_t NB, int64_t n_rows, int64_t row_begin, const uint32_t* __restrict__ strA,
+             const uint32_t* __restrict__ gwordB) {
+  const int64_t ib = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (ib >= NB) return;
+  const uint32_t gw = __ldg(gwordB + ib);
+  const int64_t r0 = (int64_t)blockIdx.y * 32, r1 = min(r0 + 32, n_rows);
+  for (int64_t r = r0; r < r1; ++r) {
+    const uint32_t a = __ldg(strA + row_begin + r);
+    if (__popc(a & gw) & 1) {
+      double* p = C + r * NB + ib;
+      *p = -*p;
     }
   }
 }
@@ -299,14 +301,6 @@ static int win_upload(T** d, const std::vector<T>& v) {
   return SQ_OK;
 }
 
-struct SideHost {
-  std::vector<int2> groups;
-  std::vector<int> delta, cnt;
-  std::vector<uint32_t> items, gbits;
-  std::vector<int2> itemcnt;
-  int ncls = 0, LT = 0, max_cnt = 0;
-};
-
 // gauge words (global orbital positions): alpha = occupation mask of the window part; beta = mask whose bit p is
 // the parity of the beta window electrons on orbitals < p.  D(A,B) = parity(popc(alpha word & beta word)).
 static inline uint32_t gauge_beta_word(uint32_t mB) {
@@ -318,6 +312,7 @@ static inline uint32_t gauge_beta_word(uint32_t mB) {
   return w;
 }
 static inline int gauge_bit(uint32_t mA, uint32_t mB) { return __builtin_popcount(mA & gauge_beta_word(mB)) & 1; }
+
 
 // largest tile dimension of a window of H orbitals starting at w0 (n orbitals, ne electrons of this spin)
 int sq_win_max_class(int n, int ne, int w0, int H) {
@@ -332,16 +327,26 @@ int sq_win_max_class(int n, int ne, int w0, int H) {
   return best;
 }
 
+
+struct SideHost {
+  std::vector<int2> groups;          // alpha: {first row, class}; beta: {chunk id, class | tiles << 16}
+  std::vector<int> gbase;            // beta: [chunk][WIN_G]
+  std::vector<int2> cls;             // {count, e_w}
+  std::vector<int> delta;
+  std::vector<std::vector<uint32_t>> wl;   // window parts per electron count, combination order
+  int ncls = 0, LT = 0, max_cnt = 0;
+};
+
 // Tables of one spin.  Returns false (no error) when the window cannot be used with this space / partition.
-static bool build_side(const sq_space* sp, const sq_layout* lay, int spin, int w0, int H, int K, const std::vector<int>& pairs,
-                       SideHost* out) {
+static bool build_side(const sq_space* sp, int spin, int w0, int H, SideHost* out) {
   const std::vector<uint32_t>& strs = spin ? sp->strB : sp->strA;
   const int ne = spin ? sp->n_beta : sp->n_alpha;
   const int64_t lo = spin ? 0 : sp->row_begin, hi = spin ? sp->NB : sp->row_end;
-  if (H < 1 || H > 12 || w0 < 0 || w0 + H > sp->n_orb) return false;
+  if (H < 1 || H > 8 || w0 < 0 || w0 + H > sp->n_orb) return false;
+  const bool block = (w0 + H == sp->n_orb);   // no suffix: batches are made of prefixes
   const uint32_t wmask = (1u << H) - 1u, wbits = wmask << w0, premask = (1u << w0) - 1u;
-  // window parts per electron count, in combination order (a lower orbital occupied sorts first)
-  std::vector<std::vector<uint32_t>> wl(H + 1);
+  std::vector<std::vector<uint32_t>>& wl = out->wl;
+  wl.assign(H + 1, {});
   for (uint32_t w = 0; w <= wmask; ++w) wl[__builtin_popcount(w)].push_back(w);
   std::vector<int> pos(wmask + 1, 0);
   int LT = 1;
@@ -349,12 +354,12 @@ static bool build_side(const sq_space* sp, const sq_layout* lay, int spin, int w
     std::sort(wl[e].begin(), wl[e].end(), [](uint32_t a, uint32_t b) {
       const uint32_t d = a ^ b;
       if (!d) return false;
-      return (a & (d & (0u - d))) != 0;
+      return (a & (d & (0u - d))) != 0;   // a lower orbital occupied sorts first
     });
     for (size_t j = 0; j < wl[e].size(); ++j) pos[wl[e][j]] = (int)j;
     LT = std::max(LT, (int)wl[e].size());
   }
-  if (LT > 1023) return false;
+  if (LT > 255) return false;   // list entries hold 8-bit string ranks
   // pass 1: groups = strings sharing prefix and suffix
   struct G {
     int64_t base;
@@ -401,113 +406,77 @@ static bool build_side(const sq_space* sp, const sq_layout* lay, int spin, int w
   }
   for (int& d : delta)
     if (d == INT_MIN) d = 0;
-  out->cnt.resize(ncls);
+  out->cls.resize(ncls);
   out->max_cnt = 0;
   for (int c = 0; c < ncls; ++c) {
-    out->cnt[c] = (int)wl[cls_ew[c]].size();
-    out->max_cnt = std::max(out->max_cnt, out->cnt[c]);
+    out->cls[c] = make_int2((int)wl[cls_ew[c]].size(), cls_ew[c]);
+    out->max_cnt = std::max(out->max_cnt, out->cls[c].x);
   }
-  // groups / chunks of K consecutive suffixes
   std::vector<int> order(gs.size());
   for (size_t i = 0; i < gs.size(); ++i) order[i] = (int)i;
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return gs[a].base < gs[b].base; });
   std::vector<int2> groups;
   if (spin == 0) {
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return gs[a].base < gs[b].base; });
     for (int i : order) groups.push_back(make_int2((int)(gs[i].base - sp->row_begin), gs[i].cls));
-    std::stable_sort(groups.begin(), groups.end(), [&](const int2& a, const int2& b) { return out->cnt[a.y] > out->cnt[b.y]; });
+    std::stable_sort(groups.begin(), groups.end(), [&](const int2& a, const int2& b) { return out->cls[a.y].x > out->cls[b.y].x; });
   } else {
+    // batches of up to WIN_G tiles of one class, in memory order (consecutive suffixes of one prefix are
+    // consecutive columns, so most lanes of a batch read neighbouring addresses)
+    (void)block;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+      return gs[a].cls != gs[b].cls ? gs[a].cls < gs[b].cls : gs[a].base < gs[b].base;
+    });
     size_t i = 0;
     while (i < order.size()) {
       const G& g0 = gs[order[i]];
       int c = 1;
-      while (c < K && i + c < order.size()) {
+      while (c < WIN_G && i + c < order.size()) {
         const G& g1 = gs[order[i + c]];
-        if (g1.pre != g0.pre || g1.e_w != g0.e_w || g1.base != g0.base + c) break;
+        if (g1.cls != g0.cls) break;
         ++c;
       }
-      groups.push_back(make_int2((int)g0.base, g0.cls | (c << 16)));
+      const int chunk = (int)(out->gbase.size() / WIN_G);
+      for (int t = 0; t < WIN_G; ++t) out->gbase.push_back(t < c ? (int)gs[order[i + t]].base : 0);
+      groups.push_back(make_int2(chunk, g0.cls | (c << 16)));
       i += c;
     }
     std::stable_sort(groups.begin(), groups.end(), [&](const int2& a, const int2& b) {
-      return out->cnt[a.y & 0xffff] * (a.y >> 16) > out->cnt[b.y & 0xffff] * (b.y >> 16);
+      return out->cls[a.y & 0xffff].x * (a.y >> 16) > out->cls[b.y & 0xffff].x * (b.y >> 16);
     });
   }
-  // brick work items (signs live in the gauge, see win_kernel)
-  std::vector<uint32_t> items(pairs.size() * (size_t)ncls * LT, 0u);
-  std::vector<int2> itemcnt(pairs.size() * (size_t)ncls, make_int2(0, 0));
-  for (size_t lp = 0; lp < pairs.size(); ++lp) {
-    const PairTables& pt = lay->pairs[pairs[lp]];
-    const uint32_t bi = 1u << pt.i, ba = 1u << pt.a;
-    if (!(bi & wbits) || !(ba & wbits)) return false;
-    for (int c = 0; c < ncls; ++c) {
-      const std::vector<uint32_t>& w = wl[cls_ew[c]];
-      uint32_t* dst = items.data() + (lp * (size_t)ncls + c) * LT;
-      int nS = 0, nI = 0;
-      for (size_t j = 0; j < w.size(); ++j) {
-        const uint32_t m = w[j] << w0;
-        if ((m & bi) && !(m & ba)) dst[nS++] = (uint32_t)j | ((uint32_t)pos[(m ^ bi ^ ba) >> w0] << 10);
-      }
-      for (size_t j = 0; j < w.size(); ++j) {
-        const uint32_t m = w[j] << w0;
-        if (((m & bi) != 0) == ((m & ba) != 0)) dst[nS + nI++] = (uint32_t)j;
-      }
-      itemcnt[lp * (size_t)ncls + c] = make_int2(nS, nI);
-    }
-  }
-  std::vector<uint32_t> gbits((size_t)ncls * LT, 0u);
-  for (int c = 0; c < ncls; ++c) {
-    const std::vector<uint32_t>& w = wl[cls_ew[c]];
-    for (size_t j = 0; j < w.size(); ++j) gbits[(size_t)c * LT + j] = spin ? gauge_beta_word(w[j] << w0) : (w[j] << w0);
-  }
-  out->gbits.swap(gbits);
   out->groups.swap(groups);
   out->delta.swap(delta);
-  out->items.swap(items);
-  out->itemcnt.swap(itemcnt);
   out->ncls = ncls;
   out->LT = LT;
   return true;
 }
 
-static int upload_side(const SideHost& h, int w0, int H, WinSide* s) {
-  s->w0 = w0;
-  s->H = H;
-  s->ncls = h.ncls;
-  s->LT = h.LT;
-  s->n_groups = (int)h.groups.size();
-  s->max_cnt = h.max_cnt;
-  SQ_CHECK(win_upload(&s->d_groups, h.groups));
-  SQ_CHECK(win_upload(&s->d_delta, h.delta));
-  SQ_CHECK(win_upload(&s->d_gbits, h.gbits));
-  SQ_CHECK(win_upload(&s->d_cnt, h.cnt));
-  SQ_CHECK(win_upload(&s->d_items, h.items));
-  SQ_CHECK(win_upload(&s->d_itemcnt, h.itemcnt));
-  return SQ_OK;
-}
-
-static void free_side(WinSide* s) {
-  cudaFree(s->d_groups);
-  cudaFree(s->d_delta);
-  cudaFree(s->d_gbits);
-  cudaFree(s->d_cnt);
-  cudaFree(s->d_items);
-  cudaFree(s->d_itemcnt);
-}
-
 void sq_free_win_tables(WinTables* wt) {
   if (!wt) return;
-  free_side(&wt->A);
-  free_side(&wt->B);
+  cudaFree(wt->d_groupsA);
+  cudaFree(wt->d_clsA);
+  cudaFree(wt->d_deltaA);
+  cudaFree(wt->d_chunksB);
+  cudaFree(wt->d_gbaseB);
+  cudaFree(wt->d_clsB);
+  cudaFree(wt->d_deltaB);
+  cudaFree(wt->d_lists);
+  cudaFree(wt->d_listidx);
   delete wt;
 }
 
-// pairs of the layout that the window kernel can take: both orbitals inside both windows, uniform gauge sign,
-// no row pair spanning two devices
-bool sq_win_pair_ok(const sq_layout* lay, int pair, int a0, int Ha, int b0, int Hb) {
+// pairs of the layout that the window kernel can take: nearest-neighbour orbitals inside the window (their signs
+// vanish in the window gauge), no row pair spanning two devices
+bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H) {
   const PairTables& pt = lay->pairs[pair];
   const int lo = std::min(pt.i, pt.a), hi = std::max(pt.i, pt.a);
-  // nearest-neighbour pairs only: their signs vanish in the window gauge
-  return hi == lo + 1 && lo >= a0 && hi < a0 + Ha && lo >= b0 && hi < b0 + Hb && !pt.cross_global && pt.n_cross_items == 0;
+  return hi == lo + 1 && lo >= w0 && hi < w0 + H && !pt.cross_global && pt.n_cross_items == 0;
+}
+
+size_t sq_win_smem_bytes(int max_a, int max_b, int lta, int ltb, int maxQ, int maxS, int n_bricks) {
+  const size_t tile = sizeof(double) * (((size_t)max_a * (size_t)max_b * WIN_GP + 1) & ~(size_t)1);
+  const size_t tabs = 4 * (size_t)(ltb + lta + WIN_G + 4 * SQ_WIN_MAX_BRICKS);   // tile_doubles is even: 16-byte aligned
+  return tile + tabs + (size_t)n_bricks * ((size_t)maxQ * 8 + (size_t)maxS * 4);
 }
 
 // Signs of Ta, Tb and the pair double of orbital pair (i,a) in the window gauge, checked over every pair of
@@ -561,10 +530,10 @@ static bool gauge_signs(const sq_space* sp, const PairTables& pt, int a0, int Ha
   return true;
 }
 
-// Tables for alpha window [a0,a0+Ha) and beta window [b0,b0+Hb) with K consecutive beta suffixes per CTA;
-// cached on the layout.  (*out)->ok is false when the combination is unusable.
-int sq_get_win(sq_space* sp, sq_layout* lay, int a0, int Ha, int b0, int Hb, int K, const WinTables** out) {
-  const std::array<int, 5> key = {a0, Ha, b0, Hb, K};
+
+// Tables for the window [w0, w0+H); cached on the layout.  (*out)->ok is false when the window is unusable.
+int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** out) {
+  const std::array<int, 5> key = {w0, H, 0, 0, 0};
   auto it = lay->wins.find(key);
   if (it != lay->wins.end()) {
     *out = it->second;
@@ -573,19 +542,17 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int a0, int Ha, int b0, int Hb, int
   WinTables* wt = new WinTables();
   lay->wins[key] = wt;
   *out = wt;
-  wt->K = K;
-  wt->logK = 0;
-  while ((1 << wt->logK) < K) ++wt->logK;
-  if ((1 << wt->logK) != K || wt->logK > 4) return SQ_OK;
+  wt->w0 = w0;
+  wt->H = H;
   if (sp->world > 1) {
     int k = 0;
     while ((1 << k) < sp->world) ++k;
-    if (a0 < k) return SQ_OK;   // alpha prefixes would straddle devices
+    if (w0 < k) return SQ_OK;   // alpha prefixes would straddle devices
   }
   wt->pair_local.assign(lay->pairs.size(), -1);
   std::vector<int> pairs;
   for (size_t p = 0; p < lay->pairs.size(); ++p)
-    if (sq_win_pair_ok(lay, (int)p, a0, Ha, b0, Hb)) {
+    if (sq_win_pair_ok(lay, (int)p, w0, H)) {
       wt->pair_local[p] = (int)pairs.size();
       pairs.push_back((int)p);
     }
@@ -593,52 +560,94 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int a0, int Ha, int b0, int Hb, int
   // constant signs of the three generators of every pair in the window gauge
   wt->eps.assign(3 * pairs.size(), 1);
   for (size_t lp = 0; lp < pairs.size(); ++lp)
-    if (!gauge_signs(sp, lay->pairs[pairs[lp]], a0, Ha, b0, Hb, &wt->eps[3 * lp])) return SQ_OK;
+    if (!gauge_signs(sp, lay->pairs[pairs[lp]], w0, H, w0, H, &wt->eps[3 * lp])) return SQ_OK;
   SideHost hA, hB;
-  if (!build_side(sp, lay, 0, a0, Ha, 1, pairs, &hA)) return SQ_OK;
-  if (!build_side(sp, lay, 1, b0, Hb, K, pairs, &hB)) return SQ_OK;
+  if (!build_side(sp, 0, w0, H, &hA)) return SQ_OK;
+  if (!build_side(sp, 1, w0, H, &hB)) return SQ_OK;
   if (hA.groups.size() > 65535 || hB.groups.empty() || hA.groups.empty()) return SQ_OK;
-  if (hA.LT + hB.LT > 3 * WIN_THREADS) return SQ_OK;   // item lists are fetched 3 words per thread
-  wt->tile_doubles = hA.max_cnt * hB.max_cnt * K;
-  wt->smem = sizeof(double) * (size_t)wt->tile_doubles + 4 * (size_t)(2 * hB.LT + 2 * hA.LT + 2 * (hA.LT + hB.LT));
-  if (wt->smem > 220 * 1024) return SQ_OK;
+  // work lists per (pair, e_wa, e_wb)
+  const int H1 = H + 1;
+  std::vector<uint32_t> lists;
+  std::vector<int4> listidx(pairs.size() * (size_t)H1 * H1, make_int4(0, 0, 0, 0));
+  int maxQ = 1, maxS = 1;
+  for (size_t lp = 0; lp < pairs.size(); ++lp) {
+    const PairTables& pt = lay->pairs[pairs[lp]];
+    const uint32_t bi = 1u << (pt.i - w0), ba = 1u << (pt.a - w0);
+    // per electron count: src strings (j, j') and inert strings of this pair
+    std::vector<std::vector<std::pair<int, int>>> src(H1);
+    std::vector<std::vector<int>> inert(H1);
+    for (int e = 0; e <= H; ++e) {
+      const std::vector<uint32_t>& w = hA.wl[e];
+      std::unordered_map<uint32_t, int> pos;
+      for (size_t j = 0; j < w.size(); ++j) pos[w[j]] = (int)j;
+      for (size_t j = 0; j < w.size(); ++j) {
+        const uint32_t m = w[j];
+        if ((m & bi) && !(m & ba)) src[e].push_back({(int)j, pos[m ^ bi ^ ba]});
+        else if (((m & bi) != 0) == ((m & ba) != 0)) inert[e].push_back((int)j);
+      }
+    }
+    for (int ea = 0; ea <= H; ++ea)
+      for (int eb = 0; eb <= H; ++eb) {
+        int4 idx = make_int4((int)lists.size(), 0, 0, 0);
+        for (auto& r : src[ea])
+          for (auto& c : src[eb]) {
+            lists.push_back((uint32_t)r.first | ((uint32_t)r.second << 8) | ((uint32_t)c.first << 16) | ((uint32_t)c.second << 24));
+            ++idx.y;
+          }
+        for (auto& r : src[ea])       // alpha single: (r, c) <-> (r', c), c inert
+          for (int c : inert[eb]) {
+            lists.push_back((uint32_t)r.first | ((uint32_t)c << 8) | ((uint32_t)r.second << 16) | ((uint32_t)c << 24));
+            ++idx.z;
+          }
+        for (int r : inert[ea])       // beta single: (r, c) <-> (r, c'), r inert
+          for (auto& c : src[eb]) {
+            lists.push_back((uint32_t)r | ((uint32_t)c.first << 8) | ((uint32_t)r << 16) | ((uint32_t)c.second << 24));
+            ++idx.w;
+          }
+        listidx[(lp * H1 + ea) * H1 + eb] = idx;
+        maxQ = std::max(maxQ, idx.y);
+        maxS = std::max(maxS, idx.z + idx.w);
+      }
+  }
+  if ((size_t)hA.max_cnt * hB.max_cnt * WIN_GP * 8 > 65535) return SQ_OK;   // 16-bit byte offsets inside a batch
+  if (maxQ + maxS > WIN_THREADS) return SQ_OK;   // the kernel fetches one list entry per thread and brick
+  maxS = (maxS + 1) & ~1;   // every brick's list area stays 8-byte aligned
+  wt->maxQ = maxQ;
+  wt->maxS = maxS;
+  wt->tile_doubles = (hA.max_cnt * hB.max_cnt * WIN_GP + 1) & ~1;   // even: the tables behind the tile stay 16-byte aligned
+  wt->LTA = (hA.LT + 3) & ~3;   // multiples of 4 words: the headers behind the tables stay 16-byte aligned
+  wt->LTB = (hB.LT + 3) & ~3;
+  if (sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS) > 220 * 1024) return SQ_OK;
+  // the device tables use the padded leading dimensions
+  auto repad = [](std::vector<int>& v, int ncls, int lt_old, int lt_new) {
+    std::vector<int> o((size_t)ncls * lt_new, 0);
+    for (int c = 0; c < ncls; ++c)
+      for (int j = 0; j < lt_old; ++j) o[(size_t)c * lt_new + j] = v[(size_t)c * lt_old + j];
+    v.swap(o);
+  };
+  repad(hA.delta, hA.ncls, hA.LT, wt->LTA);
+  repad(hB.delta, hB.ncls, hB.LT, wt->LTB);
+  wt->smem = sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS);
+  wt->max_a = hA.max_cnt;
+  wt->max_b = hB.max_cnt;
+  wt->lanes_j = (w0 + H == sp->n_orb) ? 1 : 0;
+  wt->n_groups_a = (int)hA.groups.size();
+  wt->n_chunks_b = (int)hB.groups.size();
   wt->touched = sp->local_len();
   if (sp->device >= 0) {
     SQ_CUDA(cudaSetDevice(sp->device));
-    SQ_CHECK(upload_side(hA, a0, Ha, &wt->A));
-    SQ_CHECK(upload_side(hB, b0, Hb, &wt->B));
-  } else {   // host-only space: plan / partition logic without device tables
-    wt->A.w0 = a0; wt->A.H = Ha; wt->A.n_groups = (int)hA.groups.size();
-    wt->B.w0 = b0; wt->B.H = Hb; wt->B.n_groups = (int)hB.groups.size();
+    SQ_CHECK(win_upload(&wt->d_groupsA, hA.groups));
+    SQ_CHECK(win_upload(&wt->d_clsA, hA.cls));
+    SQ_CHECK(win_upload(&wt->d_deltaA, hA.delta));
+    SQ_CHECK(win_upload(&wt->d_chunksB, hB.groups));
+    SQ_CHECK(win_upload(&wt->d_gbaseB, hB.gbase));
+    SQ_CHECK(win_upload(&wt->d_clsB, hB.cls));
+    SQ_CHECK(win_upload(&wt->d_deltaB, hB.delta));
+    SQ_CHECK(win_upload(&wt->d_lists, lists));
+    SQ_CHECK(win_upload(&wt->d_listidx, listidx));
   }
   wt->ok = true;
   return SQ_OK;
-}
-
-static WinSideDev side_dev(const WinSide& s) {
-  WinSideDev d;
-  d.groups = s.d_groups;
-  d.delta = s.d_delta;
-  d.gbits = s.d_gbits;
-  d.cnt = s.d_cnt;
-  d.items = s.d_items;
-  d.itemcnt = s.d_itemcnt;
-  d.LT = s.LT;
-  d.ncls = s.ncls;
-  return d;
-}
-
-template <int LOGK>
-static cudaError_t launch_win_k(dim3 grid, size_t smem, cudaStream_t st, double* state, int64_t NB, const WinSideDev& A,
-                                const WinSideDev& B, const WinProgram& P, int tile_doubles) {
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(win_kernel<LOGK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = smem;
-  }
-  win_kernel<LOGK><<<grid, WIN_THREADS, smem, st>>>(state, NB, A, B, P, tile_doubles);
-  return cudaGetLastError();
 }
 
 // bricks[k] = (layout pair index, rotation steps of the fused program); every pair must be usable in `wt`
@@ -663,18 +672,48 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
     P.br[k].ca = tm.ca; P.br[k].sa = tm.sa; P.br[k].cb = tm.cb; P.br[k].sb = tm.sb;
   }
   for (int k = n_bricks; k < SQ_WIN_MAX_BRICKS; ++k) P.pair[k] = 0;
-  const dim3 grid((unsigned)wt.B.n_groups, (unsigned)wt.A.n_groups);
-  const WinSideDev A = side_dev(wt.A), B = side_dev(wt.B);
+  WinDev W;
+  W.groupsA = wt.d_groupsA; W.clsA = wt.d_clsA; W.deltaA = wt.d_deltaA;
+  W.chunksB = wt.d_chunksB; W.gbaseB = wt.d_gbaseB; W.clsB = wt.d_clsB; W.deltaB = wt.d_deltaB;
+  W.lists = wt.d_lists; W.listidx = wt.d_listidx;
+  W.LTA = wt.LTA; W.LTB = wt.LTB; W.H1 = wt.H + 1;
+  W.lanes_j = wt.lanes_j;
+  W.tile_doubles = wt.tile_doubles; W.maxQ = wt.maxQ; W.maxS = wt.maxS;
+  const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks);
+  const dim3 grid((unsigned)wt.n_chunks_b, (unsigned)wt.n_groups_a);
   cudaError_t e = cudaSuccess;
-  switch (wt.logK) {
-    case 0: e = launch_win_k<0>(grid, wt.smem, st, state, sp->NB, A, B, P, wt.tile_doubles); break;
-    case 1: e = launch_win_k<1>(grid, wt.smem, st, state, sp->NB, A, B, P, wt.tile_doubles); break;
-    case 2: e = launch_win_k<2>(grid, wt.smem, st, state, sp->NB, A, B, P, wt.tile_doubles); break;
-    case 3: e = launch_win_k<3>(grid, wt.smem, st, state, sp->NB, A, B, P, wt.tile_doubles); break;
-    default: e = launch_win_k<4>(grid, wt.smem, st, state, sp->NB, A, B, P, wt.tile_doubles); break;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    e = cudaFuncSetAttribute(win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) attr = smem;
+  }
+  if (e == cudaSuccess) {
+    win_kernel<<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P);
+    e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
     sq_set_error("win_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+// Multiply the local vector by the sign-free gauge D (an involution).  The beta gauge words live on the space.
+int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st) {
+  if (!sp->d_gwordB) {
+    std::vector<uint32_t> gw((size_t)sp->NB);
+    for (int64_t I = 0; I < sp->NB; ++I) gw[I] = gauge_beta_word(sp->strB[I]);
+    SQ_CUDA(cudaMalloc(&sp->d_gwordB, sizeof(uint32_t) * gw.size()));
+    SQ_CUDA(cudaMemcpy(sp->d_gwordB, gw.data(), sizeof(uint32_t) * gw.size(), cudaMemcpyHostToDevice));
+  }
+  const int64_t n_rows = sp->row_end - sp->row_begin;
+  if (n_rows == 0) return SQ_OK;
+  const dim3 grid((unsigned)((sp->NB + 255) / 256), (unsigned)((n_rows + 31) / 32));
+  gauge_kernel<<<grid, 256, 0, st>>>(state, sp->NB, n_rows, sp->row_begin, sp->d_strA, sp->d_gwordB);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("gauge_kernel launch failed: %s", cudaGetErrorString(e));
     return SQ_ERR_CUDA;
   }
   g_sq_launches.fetch_add(1);

@@ -551,8 +551,8 @@ def test_ucc_wavefunction_object(sq, golden):
     assert np.max(np.abs(grad - arrays["uccwf_gradient"])) < 3e-5
 
 
-WIN_VARIANTS = ["1", "8:6:4,16,12,100,6,16,3", "6:4:0,16,8,60,2,16,2", "4:0:0,8,4,40,1,5,2", "8:0:0,4,12,200,4,16,1",
-                "6:0:0,16,0,100,0,7,1", "5:3:0,2,12,100,3,16,2"]
+WIN_VARIANTS = ["1", "6:5:4,72,5,16,3", "6:4:0,60,2,16,2", "4:0:0,40,1,5,2", "5:0:0,200,4,16,1", "6:0:0,100,0,7,1",
+                "5:3:0,100,3,16,2", "8:7:3,220,0,9,1"]
 
 
 @pytest.mark.parametrize("n,na,nb,L,qnp", [(8, 4, 4, 3, False), (9, 4, 5, 2, True), (12, 6, 6, 3, False), (13, 6, 5, 2, False)])

@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "window or tups_against" 2>&1 | tail -3
-SQ_LAUNCH_TIMING=1 python tools/win_scan.py --layers 4 --reps 1 "1" 2>&1 | tail -7
-python tools/win_scan.py "1" "8:6:4,16,12,100,6,8,3" "8:0:0,16,12,100,6,16,3" "8:0:0,16,12,100,6,10,3"  "8:0:0,16,12,100,6,7,3" 2>&1 | tail -5
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
+timeout 200 python tools/win_scan.py "0" "1" "6:5:4,72,4,16,3" "6:5:4,72,3,16,3" "6:5:4,72,4,12,3" 2>&1 | tail -5
+SQ_WIN="6:5:4,72,4,16,3" SQ_LAUNCH_TIMING=1 timeout 100 python tools/win_scan.py --layers 4 --reps 1 "6:5:4,72,4,16,3" 2>&1 | tail -12

@@ -4,7 +4,7 @@
     python tools/win_scan.py [--cas 16] [--layers 16] [--reps 3] cfg1 cfg2 ...
 
 cfg uses the SQ_WIN syntax ("0" = no window sweeps, "1" = defaults,
-"w1:w2:w3,k_run,max_block,smem_kb,min_suffix,max_bricks,min_bricks").  Prints ms per step, launches, window
+"w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks").  Prints ms per step, launches, window
 sweeps, bricks inside windows, ms per launch and layers/s.
 """
 import argparse
