@@ -623,7 +623,7 @@ static void win_candidates(const sq_space* sp, std::vector<WinCand>* out) {
       WinCand c{w0, H, 0};
       // work lists are bounded by (strings per side)^2; the exact size comes with the tables
       const int ma = sq_win_max_class(n, sp->n_alpha, w0, H), mb = sq_win_max_class(n, sp->n_beta, w0, H);
-      c.smem = sq_win_smem_bytes(ma, mb, ma, mb, (ma * mb) / 8 + 1, (ma * mb) / 3 + 1, 8);
+      c.smem = sq_win_smem_bytes(ma, mb, suffix ? 16 : 18, ma, mb, (ma * mb) / 8 + 1, (ma * mb) / 3 + 1, 8);
       if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
     }
   }

@@ -38,8 +38,7 @@
 #define WIN_THREADS 256
 #define WIN_WARPS (WIN_THREADS / 32)
 #define WIN_G 16                      // tiles per CTA
-#define WIN_GP 17                     // padded batch stride in shared memory
-#define WIN_SLOTS (WIN_THREADS / WIN_G)
+#define WIN_SLOTS (WIN_THREADS / (WIN_G / 2))   // a thread works on two tiles (128-bit shared-memory accesses)
 
 struct WinDev {
   // alpha side
@@ -56,6 +55,7 @@ struct WinDev {
   const int4* listidx;     // [pair][e_wa][e_wb] {offset, n_quad, n_alpha_single, n_beta_single}
   int LTA, LTB, H1;        // H1 = H + 1
   int lanes_j;             // top window: the tiles of a batch are far apart, global accesses run along the columns
+  int gp;                  // batch stride in shared memory: 16, or 18 for the top window (column-wise copies)
   int tile_doubles, maxQ, maxS;
 };
 
@@ -84,6 +84,14 @@ __device__ __forceinline__ double lds64(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ double2 lds128(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
 
 // The vector is in the sign-free gauge (gauge_kernel) while window sweeps run, so the kernel is sign-free:
 // load the batch, apply the bricks, store the batch.
@@ -105,9 +113,10 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
   const int clsA = ga.y, clsB = gb.y & 0xffff, kcnt = gb.y >> 16;
   const int2 ca2 = __ldg(W.clsA + clsA), cb2 = __ldg(W.clsB + clsB);
   const int Rn = ca2.x, Wn = cb2.x;
-  const int RS = Wn * WIN_GP;               // row stride (doubles)
+  const int GP = W.gp;
+  const int RS = Wn * GP;                   // row stride (doubles)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = threadIdx.x & (WIN_G - 1), slot = threadIdx.x / WIN_G;
+  const int g = threadIdx.x & (WIN_G - 1);
 
   // ---- round trip 1: class tables and list headers ----
   for (int t = threadIdx.x; t < Wn; t += WIN_THREADS) sdB[t] = __ldg(W.deltaB + clsB * W.LTB + t);
@@ -127,7 +136,7 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
       const uint32_t dst = tb + (uint32_t)(r * RS) * 8u;
       for (int x = lane; x < NX; x += 32) {
         const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
-        cp_async8(dst + (uint32_t)(j * WIN_GP + gg) * 8u, src + sbase[gg] + sdB[j]);
+        cp_async8(dst + (uint32_t)(j * GP + gg) * 8u, src + sbase[gg] + sdB[j]);
       }
     }
   } else {
@@ -137,7 +146,7 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
       const uint32_t dst = tb + (uint32_t)(r * RS + g) * 8u;
       if (g < kcnt) {
 #pragma unroll 4
-        for (int j = lane >> 4; j < Wn; j += 2) cp_async8(dst + (uint32_t)(j * WIN_GP) * 8u, src + sdB[j]);
+        for (int j = lane >> 4; j < Wn; j += 2) cp_async8(dst + (uint32_t)(j * GP) * 8u, src + sdB[j]);
       }
     }
   }
@@ -160,10 +169,10 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
         const uint32_t w = raw[b];
         uint32_t* dst = reinterpret_cast<uint32_t*>(qall) + b * per_brick;
         if (t < li.y) {
-          const uint32_t r0 = (w & 255u) * RS, r1 = ((w >> 8) & 255u) * RS, c0 = ((w >> 16) & 255u) * WIN_GP, c1 = (w >> 24) * WIN_GP;
+          const uint32_t r0 = (w & 255u) * RS, r1 = ((w >> 8) & 255u) * RS, c0 = ((w >> 16) & 255u) * GP, c1 = (w >> 24) * GP;
           reinterpret_cast<uint2*>(dst)[t] = make_uint2((r0 | (r1 << 16)) << 3, (c0 | (c1 << 16)) << 3);
         } else if (t < li.y + li.z + li.w) {
-          const uint32_t o0 = (w & 255u) * RS + ((w >> 8) & 255u) * WIN_GP, o1 = ((w >> 16) & 255u) * RS + (w >> 24) * WIN_GP;
+          const uint32_t o0 = (w & 255u) * RS + ((w >> 8) & 255u) * GP, o1 = ((w >> 16) & 255u) * RS + (w >> 24) * GP;
           dst[2 * W.maxQ + (t - li.y)] = (o0 | (o1 << 16)) << 3;
         }
       }
@@ -172,76 +181,61 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
   cp_async_wait_all();
 
   // ---- bricks ----
-  const uint32_t tgb = tb + (uint32_t)g * 8u;
+  // 8 lanes x 2 tiles per work-list entry (32 entries in flight per CTA); every shared-memory access moves 16 bytes
+  const int g2 = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const bool on = 2 * g2 < kcnt;   // an odd batch computes one unused tile along (its lanes are never stored to memory)
+  const uint32_t tgb = tb + (uint32_t)g2 * 16u;
   const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
   for (int b = 0; b < P.n; ++b) {
     __syncthreads();   // convergent: every thread of the CTA, also the lanes of unused tiles
-    if (g >= kcnt) continue;
+    if (!on) continue;
     const int4 hd = shdr[b];
     const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
     const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
     const WinBrick& br = P.br[b];
-    if (slot < nQ) {   // 4x4 entries, two per step: all loads before the first store
-      int e = slot;
-      for (; e + WIN_SLOTS < nQ; e += 2 * WIN_SLOTS) {
-        uint32_t ux, uy, vx, vy;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(ql + (uint32_t)(e + WIN_SLOTS) * 8u));
-        const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
-        const uint32_t b0 = tgb + (vx & 0xffffu), b1 = tgb + (vx >> 16), d0 = vy & 0xffffu, d1 = vy >> 16;
-        const double y0 = lds64(a0 + c0), y1 = lds64(a0 + c1), y2 = lds64(a1 + c0), y3 = lds64(a1 + c1);
-        const double z0 = lds64(b0 + d0), z1 = lds64(b0 + d1), z2 = lds64(b1 + d0), z3 = lds64(b1 + d1);
-        sts64(a0 + c0, br.m[0] * y0 + br.m[1] * y1 + br.m[2] * y2 + br.m[3] * y3);
-        sts64(a0 + c1, br.m[4] * y0 + br.m[5] * y1 + br.m[6] * y2 + br.m[7] * y3);
-        sts64(a1 + c0, br.m[8] * y0 + br.m[9] * y1 + br.m[10] * y2 + br.m[11] * y3);
-        sts64(a1 + c1, br.m[12] * y0 + br.m[13] * y1 + br.m[14] * y2 + br.m[15] * y3);
-        sts64(b0 + d0, br.m[0] * z0 + br.m[1] * z1 + br.m[2] * z2 + br.m[3] * z3);
-        sts64(b0 + d1, br.m[4] * z0 + br.m[5] * z1 + br.m[6] * z2 + br.m[7] * z3);
-        sts64(b1 + d0, br.m[8] * z0 + br.m[9] * z1 + br.m[10] * z2 + br.m[11] * z3);
-        sts64(b1 + d1, br.m[12] * z0 + br.m[13] * z1 + br.m[14] * z2 + br.m[15] * z3);
-      }
-      if (e < nQ) {
-        uint32_t ux, uy;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
-        const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
-        const double y0 = lds64(a0 + c0), y1 = lds64(a0 + c1), y2 = lds64(a1 + c0), y3 = lds64(a1 + c1);
-        sts64(a0 + c0, br.m[0] * y0 + br.m[1] * y1 + br.m[2] * y2 + br.m[3] * y3);
-        sts64(a0 + c1, br.m[4] * y0 + br.m[5] * y1 + br.m[6] * y2 + br.m[7] * y3);
-        sts64(a1 + c0, br.m[8] * y0 + br.m[9] * y1 + br.m[10] * y2 + br.m[11] * y3);
-        sts64(a1 + c1, br.m[12] * y0 + br.m[13] * y1 + br.m[14] * y2 + br.m[15] * y3);
-      }
+    for (int e = slot; e < nQ; e += WIN_SLOTS) {   // 4x4 entries
+      uint32_t ux, uy;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
+      const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
+      const double2 y0 = lds128(a0 + c0), y1 = lds128(a0 + c1), y2 = lds128(a1 + c0), y3 = lds128(a1 + c1);
+      double2 z;
+      z.x = br.m[0] * y0.x + br.m[1] * y1.x + br.m[2] * y2.x + br.m[3] * y3.x;
+      z.y = br.m[0] * y0.y + br.m[1] * y1.y + br.m[2] * y2.y + br.m[3] * y3.y;
+      sts128(a0 + c0, z);
+      z.x = br.m[4] * y0.x + br.m[5] * y1.x + br.m[6] * y2.x + br.m[7] * y3.x;
+      z.y = br.m[4] * y0.y + br.m[5] * y1.y + br.m[6] * y2.y + br.m[7] * y3.y;
+      sts128(a0 + c1, z);
+      z.x = br.m[8] * y0.x + br.m[9] * y1.x + br.m[10] * y2.x + br.m[11] * y3.x;
+      z.y = br.m[8] * y0.y + br.m[9] * y1.y + br.m[10] * y2.y + br.m[11] * y3.y;
+      sts128(a1 + c0, z);
+      z.x = br.m[12] * y0.x + br.m[13] * y1.x + br.m[14] * y2.x + br.m[15] * y3.x;
+      z.y = br.m[12] * y0.y + br.m[13] * y1.y + br.m[14] * y2.y + br.m[15] * y3.y;
+      sts128(a1 + c1, z);
     }
-    if (slot < nS) {   // 2x2 entries: alpha singles first, then beta singles; four per step
+    {   // 2x2 entries: alpha singles first, then beta singles; two per step
       int e = slot;
-      for (; e + 3 * WIN_SLOTS < nS; e += 4 * WIN_SLOTS) {
-        uint32_t o0[4], o1[4];
-        double y0[4], y1[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint32_t u;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)(e + t * WIN_SLOTS) * 4u));
-          o0[t] = tgb + (u & 0xffffu);
-          o1[t] = tgb + (u >> 16);
-          y0[t] = lds64(o0[t]);
-          y1[t] = lds64(o1[t]);
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const bool al = e + t * WIN_SLOTS < nSa;
-          const double c = al ? br.ca : br.cb, s = al ? br.sa : br.sb;
-          sts64(o0[t], c * y0[t] - s * y1[t]);
-          sts64(o1[t], c * y1[t] + s * y0[t]);
-        }
+      for (; e + WIN_SLOTS < nS; e += 2 * WIN_SLOTS) {
+        uint32_t u, v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sl + (uint32_t)(e + WIN_SLOTS) * 4u));
+        const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16), p0 = tgb + (v & 0xffffu), p1 = tgb + (v >> 16);
+        const double2 y0 = lds128(o0), y1 = lds128(o1), w0 = lds128(p0), w1 = lds128(p1);
+        const bool al = e < nSa, bl = e + WIN_SLOTS < nSa;
+        const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb, c2 = bl ? br.ca : br.cb, s2 = bl ? br.sa : br.sb;
+        sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
+        sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
+        sts128(p0, make_double2(c2 * w0.x - s2 * w1.x, c2 * w0.y - s2 * w1.y));
+        sts128(p1, make_double2(c2 * w1.x + s2 * w0.x, c2 * w1.y + s2 * w0.y));
       }
-      for (; e < nS; e += WIN_SLOTS) {
+      if (e < nS) {
         uint32_t u;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
         const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16);
         const bool al = e < nSa;
-        const double c = al ? br.ca : br.cb, s = al ? br.sa : br.sb;
-        const double y0 = lds64(o0), y1 = lds64(o1);
-        sts64(o0, c * y0 - s * y1);
-        sts64(o1, c * y1 + s * y0);
+        const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb;
+        const double2 y0 = lds128(o0), y1 = lds128(o1);
+        sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
+        sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
       }
     }
   }
@@ -256,7 +250,7 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
       const double* srct = tile + r * RS;
       for (int x = lane; x < NX; x += 32) {
         const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
-        stg_stream(dst + sbase[gg] + sdB[j], srct[j * WIN_GP + gg]);
+        stg_stream(dst + sbase[gg] + sdB[j], srct[j * GP + gg]);
       }
     }
   } else if (g < kcnt) {
@@ -265,7 +259,7 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
       double* dst = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
       const double* srct = tile + r * RS + g;
 #pragma unroll 4
-      for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * WIN_GP]);
+      for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * GP]);
     }
   }
 }
@@ -473,8 +467,8 @@ bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H) {
   return hi == lo + 1 && lo >= w0 && hi < w0 + H && !pt.cross_global && pt.n_cross_items == 0;
 }
 
-size_t sq_win_smem_bytes(int max_a, int max_b, int lta, int ltb, int maxQ, int maxS, int n_bricks) {
-  const size_t tile = sizeof(double) * (((size_t)max_a * (size_t)max_b * WIN_GP + 1) & ~(size_t)1);
+size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int lta, int ltb, int maxQ, int maxS, int n_bricks) {
+  const size_t tile = sizeof(double) * (size_t)max_a * (size_t)max_b * (size_t)gp;
   const size_t tabs = 4 * (size_t)(ltb + lta + WIN_G + 4 * SQ_WIN_MAX_BRICKS);   // tile_doubles is even: 16-byte aligned
   return tile + tabs + (size_t)n_bricks * ((size_t)maxQ * 8 + (size_t)maxS * 4);
 }
@@ -609,15 +603,17 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
         maxS = std::max(maxS, idx.z + idx.w);
       }
   }
-  if ((size_t)hA.max_cnt * hB.max_cnt * WIN_GP * 8 > 65535) return SQ_OK;   // 16-bit byte offsets inside a batch
+  wt->lanes_j = (w0 + H == sp->n_orb) ? 1 : 0;
+  wt->gp = wt->lanes_j ? 18 : 16;   // even: 16-byte aligned tile pairs; 18 spreads the column-wise copies over the banks
+  if ((size_t)hA.max_cnt * hB.max_cnt * wt->gp * 8 > 65535) return SQ_OK;   // 16-bit byte offsets inside a batch
   if (maxQ + maxS > WIN_THREADS) return SQ_OK;   // the kernel fetches one list entry per thread and brick
   maxS = (maxS + 1) & ~1;   // every brick's list area stays 8-byte aligned
   wt->maxQ = maxQ;
   wt->maxS = maxS;
-  wt->tile_doubles = (hA.max_cnt * hB.max_cnt * WIN_GP + 1) & ~1;   // even: the tables behind the tile stay 16-byte aligned
+  wt->tile_doubles = hA.max_cnt * hB.max_cnt * wt->gp;   // even
   wt->LTA = (hA.LT + 3) & ~3;   // multiples of 4 words: the headers behind the tables stay 16-byte aligned
   wt->LTB = (hB.LT + 3) & ~3;
-  if (sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS) > 220 * 1024) return SQ_OK;
+  if (sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->gp, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS) > 220 * 1024) return SQ_OK;
   // the device tables use the padded leading dimensions
   auto repad = [](std::vector<int>& v, int ncls, int lt_old, int lt_new) {
     std::vector<int> o((size_t)ncls * lt_new, 0);
@@ -627,10 +623,9 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
   };
   repad(hA.delta, hA.ncls, hA.LT, wt->LTA);
   repad(hB.delta, hB.ncls, hB.LT, wt->LTB);
-  wt->smem = sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS);
+  wt->smem = sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->gp, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS);
   wt->max_a = hA.max_cnt;
   wt->max_b = hB.max_cnt;
-  wt->lanes_j = (w0 + H == sp->n_orb) ? 1 : 0;
   wt->n_groups_a = (int)hA.groups.size();
   wt->n_chunks_b = (int)hB.groups.size();
   wt->touched = sp->local_len();
@@ -678,8 +673,9 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
   W.lists = wt.d_lists; W.listidx = wt.d_listidx;
   W.LTA = wt.LTA; W.LTB = wt.LTB; W.H1 = wt.H + 1;
   W.lanes_j = wt.lanes_j;
+  W.gp = wt.gp;
   W.tile_doubles = wt.tile_doubles; W.maxQ = wt.maxQ; W.maxS = wt.maxS;
-  const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks);
+  const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.gp, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks);
   const dim3 grid((unsigned)wt.n_chunks_b, (unsigned)wt.n_groups_a);
   cudaError_t e = cudaSuccess;
   static size_t attr = 0;
