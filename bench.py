@@ -8,8 +8,11 @@ the resident 165 636 900-amplitude fp64 CI vector.  `value` = layers/s with the 
 `e2e` = the same through the public `construct_ups_state(numpy_state, ...)` call with pinned HOST buffers
 (H2D of the state + D2H of the result inside the timed region).  One JSON line is printed by rank 0.
 
-N > 1 (torchrun): the CAS(16,16) vector fits one GPU, so ranks run independent replicas of the workload
-(different theta sets, as RotoSolve / finite-difference columns do) -- weak scaling, no data-path collective.
+N > 1 (torchrun): the CAS(16,16) vector fits one GPU, so by default the ranks run independent replicas of the
+workload (different theta sets, as RotoSolve shifts / finite-difference columns do) -- weak scaling, no data-path
+collective.  --mode sharded (default when the vector exceeds 64 GB, e.g. --cas 20) shards ONE vector by alpha string
+over the N GPUs: local bricks stay on the GPU, bricks that pair rows of two GPUs rotate their tiles through NVLink
+peer memory (strong scaling).
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP over all host
 cores) on a bounded sample of the same workload; /root/reference itself is pure Python + numba and does
@@ -42,11 +45,18 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cas", type=int, default=16, help="active orbitals n; CAS(n,n)")
     ap.add_argument("--layers", type=int, default=16)
-    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
-                    help="N > 1: one alpha-sharded vector (strong scaling, default) or independent replicas (weak)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"],
+                    help="N > 1: independent replicas (weak scaling; auto while the vector fits one GPU) or one "
+                    "alpha-sharded vector (strong scaling; auto when 8*N_det > 64 GB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+def vector_bytes(n: int) -> float:
+    from math import comb
+
+    return 8.0 * comb(n, n // 2) ** 2
 
 
 def workload_name(n: int, L: int) -> str:
@@ -313,6 +323,13 @@ def run_ours(args) -> None:
         launch_ms = ms_max / max(launches, 1)
         bytes_per_launch = 16.0 * touched_per_step / max(launches_per_step, 1)
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+            if n == 16 and plan[1]:
+                with open(os.path.join(ROOT, "profiles", "r1_win_kernel_traffic.json")) as f:
+                    traffic = float(json.load(f)["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
         roofline = {
             "kernel": "win_kernel (one read + one write of the vector per sweep; %.1f bricks = %.1f ansatz operators per sweep)"
             % (plan[2] / max(plan[1], 1), 3.0 * plan[2] / max(plan[1], 1)) if plan[1] else "tile/quad kernels (one or two bricks per launch)",
@@ -322,7 +339,8 @@ def run_ours(args) -> None:
             "peak_source": peak_src,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_source": "ncu --set full capture of win_kernel, profiles/r1_win_kernel_ncu_full_summary.csv" if traffic else None,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "avg_launch_ms": launch_ms,
             "full_sweep_equiv_GBps": 16.0 * info.num_det / (launch_ms * 1e-3) / 1e9,
@@ -403,6 +421,13 @@ def run_sharded(args) -> None:
     touched_per_step = int(lib.sq_layout_touched_amplitudes(handle, 0, P))
     plan = sp.exchange_plan(lay, 0, P, False)
     n_exchange = sum(1 for _, _, x in plan if x)
+    import ctypes as C
+
+    pstats = [0] * 6   # launch plan summed over the operator ranges of the exchange plan
+    for first, last, _ in plan:
+        one = (C.c_int64 * 6)()
+        _lib.check(lib.sq_layout_plan_stats(handle, first, last, one))
+        pstats = [a + int(b) for a, b in zip(pstats, one)]
     st = sp.alloc_state()
     st.set_determinant(0)
 
@@ -485,14 +510,14 @@ def run_sharded(args) -> None:
                 "l2_policy": "inputs larger than L2" if 8 * sp.local_len > 126e6 else "per-GPU shard may fit L2 (strong scaling of a fixed vector)",
                 "parallelism": f"one vector sharded by alpha string over {world} GPUs (prefix-class row partition); "
                 f"{n_exchange} of {len(plan)} operator ranges per step exchange tiles over NVLink peer memory, the rest are local",
-                "fusion": "%d launches per step: %d window sweeps holding %d bricks (3 operators each), %d quad, %d single-brick, "
-                "2 gauge sweeps" % (launches_per_step, plan[1], plan[2], plan[3], plan[4]),
+                "fusion": "per rank and step: %d window sweeps holding %d bricks (3 operators each), %d quad, %d single-brick launches"
+                % (pstats[1], pstats[2], pstats[3], pstats[4]),
             },
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "kernel": "tile_kernel_v2 (per-GPU average over local and NVLink-exchange bricks)",
+                "kernel": "win_kernel on the local operator ranges, tile_kernel_v2 over NVLink peer memory on the exchange ranges (per-GPU average)",
                 "bound": "hbm",
                 "achieved": achieved,
                 "peak": peak,
@@ -514,7 +539,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args)
-    elif world > 1 and args.mode == "sharded":
+    elif world > 1 and (args.mode == "sharded" or (args.mode == "auto" and vector_bytes(args.cas) > 64e9)):
         run_sharded(args)
     else:
         run_ours(args)
