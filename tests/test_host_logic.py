@@ -279,3 +279,59 @@ def test_host_only_space_refuses_kernels():
         _lib.check(lib.sq_ups_apply(h, lay, th.ctypes.data_as(C.POINTER(C.c_double)), 0, 1, 0, C.c_void_p(8), None))
     lib.sq_layout_destroy(lay)
     lib.sq_space_destroy(h)
+
+
+def _tups_layout(lib, h, n, L):
+    from slowquant_b200.util import UpsStructure
+
+    lay = UpsStructure()
+    lay.create_tiled(n, {"n_layers": L, "do_tups": True})
+    codes = np.array([_lib.EXC_CODES[t] for t in lay.excitation_operator_type], dtype=np.int32)
+    offs = np.zeros(len(codes) + 1, dtype=np.int32)
+    flat = []
+    for k, idx in enumerate(lay.excitation_indices):
+        flat.extend(int(x) for x in idx)
+        offs[k + 1] = len(flat)
+    flat = np.asarray(flat, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    handle = C.c_void_p()
+    _lib.check(lib.sq_layout_create(h, len(codes), p(codes), p(offs), p(flat), C.byref(handle)))
+    return handle, len(codes)
+
+
+def test_launch_planner_on_host_only_space():
+    """The commutation-aware planner (window sweeps) is pure host logic: every brick is executed exactly once,
+    a tUPS circuit needs far fewer sweeps than bricks, and the run-time switch turns the window sweeps off."""
+    n, L = 12, 6
+    lib, h = _host_space(n, n // 2, n // 2)
+    lay, P = _tups_layout(lib, h, n, L)
+    stats = (C.c_int64 * 6)()
+    try:
+        _lib.check(lib.sq_set_option(b"win", b"1"))
+        _lib.check(lib.sq_layout_plan_stats(lay, 0, P, stats))
+        launches, sweeps, bricks_in, quads, singles, other = (int(x) for x in stats)
+        n_bricks = (n - 1) * L
+        assert other == 0
+        assert bricks_in + 2 * quads + singles == n_bricks          # every brick exactly once
+        assert sweeps > 0 and launches == sweeps + quads + singles
+        assert launches <= n_bricks // 4                               # >= 4 bricks per launch on average
+        # kernel launches = plan launches + the two gauge sweeps around the window sweeps
+        assert lib.sq_layout_num_launches(lay, 0, P) == launches + 2
+        # amplitudes read+written: every sweep touches the whole vector
+        ndet = int(lib.sq_space_num_det(h))
+        assert lib.sq_layout_touched_amplitudes(lay, 0, P) >= (sweeps + 2) * ndet
+        # a sub-range and a single operator: isolated bricks do not pay gauge sweeps
+        assert lib.sq_layout_num_launches(lay, 0, 1) == 1
+        _lib.check(lib.sq_set_option(b"win", b"0"))
+        _lib.check(lib.sq_layout_plan_stats(lay, 0, P, stats))
+        assert int(stats[1]) == 0 and 2 * int(stats[3]) + int(stats[4]) == n_bricks
+        # narrower windows, brick cap 4
+        _lib.check(lib.sq_set_option(b"win", b"4:3:0,72,2,4,2"))
+        _lib.check(lib.sq_layout_plan_stats(lay, 0, P, stats))
+        assert int(stats[2]) + 2 * int(stats[3]) + int(stats[4]) == n_bricks
+        assert int(stats[1]) > 0 and int(stats[2]) <= 4 * int(stats[1])
+        assert lib.sq_set_option(b"nonsense", b"1") == _lib.SQ_ERR_INVALID
+    finally:
+        _lib.check(lib.sq_set_option(b"win", b"1"))
+        lib.sq_layout_destroy(lay)
+        lib.sq_space_destroy(h)
