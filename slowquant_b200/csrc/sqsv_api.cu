@@ -549,7 +549,7 @@ static int g_plan_version = 0;   // bumped by sq_set_option: cached plans of old
 struct WinConfig {
   bool enabled = true;
   int widths[3] = {6, 5, 4};     // window widths tried (orbitals)
-  int smem_kb = 72;              // largest batch admitted (3 CTAs per SM)
+  int smem_kb = 72;              // largest CTA footprint admitted (3 CTAs per SM)
   int min_suffix = 3;            // windows below the top one need at least this many orbitals above them
   int max_bricks = SQ_WIN_MAX_BRICKS;
   int min_bricks = 3;            // smaller isolated groups go to the tile / quad kernels
@@ -623,7 +623,7 @@ static void win_candidates(const sq_space* sp, std::vector<WinCand>* out) {
       WinCand c{w0, H, 0};
       // work lists are bounded by (strings per side)^2; the exact size comes with the tables
       const int ma = sq_win_max_class(n, sp->n_alpha, w0, H), mb = sq_win_max_class(n, sp->n_beta, w0, H);
-      c.smem = sq_win_smem_bytes(ma, mb, suffix ? 16 : 18, ma, mb, (ma * mb) / 8 + 1, (ma * mb) / 3 + 1, 8);
+      c.smem = sq_win_smem_bytes(ma, mb, suffix ? 16 : 18, 1, ma, mb, (ma * mb) / 8 + 1, (ma * mb) / 3 + 1, 8);
       if (c.smem <= (size_t)cfg.smem_kb * 1024) out->push_back(c);
     }
   }
@@ -1170,7 +1170,7 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
       cudaEventElapsedTime(&ms, a, b);
       if (l->kind == 2)
         fprintf(stderr, "launch win [%d,%d) smem=%zu grid=%dx%d bricks=%zu : %.3f ms\n", l->wt->w0, l->wt->w0 + l->wt->H,
-                l->wt->smem, l->wt->n_chunks_b, l->wt->n_groups_a, l->runs.size(), ms);
+                l->wt->smem, l->wt->n_ranges_b, l->wt->n_groups_a, l->runs.size(), ms);
       else
         fprintf(stderr, "launch kind=%d : %.3f ms\n", l->kind, ms);
     }

@@ -212,10 +212,10 @@ struct WinTables {
   bool ok = false;
   int w0 = 0, H = 0;
   int LTA = 0, LTB = 0, max_a = 0, max_b = 0, lanes_j = 0, gp = 16;
-  int n_groups_a = 0, n_chunks_b = 0;
+  int n_groups_a = 0, n_chunks_b = 0, n_ranges_b = 0, nbuf = 1;
   int maxQ = 0, maxS = 0, tile_doubles = 0;
-  int2 *d_groupsA = nullptr, *d_clsA = nullptr, *d_chunksB = nullptr, *d_clsB = nullptr;
-  int *d_deltaA = nullptr, *d_deltaB = nullptr, *d_gbaseB = nullptr;
+  int2 *d_groupsA = nullptr, *d_clsA = nullptr, *d_chunksB = nullptr, *d_clsB = nullptr, *d_rangesB = nullptr;
+  int *d_deltaA = nullptr, *d_deltaB = nullptr, *d_gbaseB = nullptr, *d_rchunks = nullptr;
   uint32_t* d_lists = nullptr;
   int4* d_listidx = nullptr;
   std::vector<int> pair_local;     // layout pair index -> pair id inside the window tables, -1 if unusable
@@ -224,7 +224,7 @@ struct WinTables {
   int64_t touched = 0;             // amplitudes per launch (the whole local vector)
 };
 int sq_win_max_class(int n, int ne, int w0, int H);
-size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int lta, int ltb, int maxQ, int maxS, int n_bricks);
+size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int nbuf, int lta, int ltb, int maxQ, int maxS, int n_bricks);
 int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st);
 bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H);
 int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** out);

@@ -48,6 +48,8 @@ struct WinDev {
   // beta side
   const int2* chunksB;     // {chunk id, class | tiles in the batch << 16}
   const int* gbaseB;       // [chunk][WIN_G] first column of every tile of the batch
+  const int2* rangesB;     // {first entry of rchunks, batches}: the batches of one CTA (all of one class)
+  const int* rchunks;      // chunk ids ordered by class
   const int2* clsB;
   const int* deltaB;
   // brick work lists
@@ -93,24 +95,32 @@ __device__ __forceinline__ void sts128(uint32_t a, double2 v) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
 
+#define WIN_RMAX 16   // batches per CTA (one range of the beta chunks of one class)
+
 // The vector is in the sign-free gauge (gauge_kernel) while window sweeps run, so the kernel is sign-free:
-// load the batch, apply the bricks, store the batch.
-// Shared memory: [tile: Rn x Wn x 17 doubles][beta delta: LTB][alpha delta: LTA][batch bases: 16][list headers: int4 x
-// SQ_WIN_MAX_BRICKS][per brick: maxQ uint2 quad entries + maxS uint32 single entries, BYTE offsets in 16-bit fields].
-// Global round trips per CTA: class tables + list headers, then (tile copies in flight) the list entries, then the
-// stores.
-__global__ void __launch_bounds__(WIN_THREADS, 3)
+// load a batch, apply the bricks, store the batch.  A CTA owns one alpha group and a RANGE of up to WIN_RMAX beta
+// batches of one class: class tables and work lists are staged once, and with NBUF = 2 the copies of the next batch
+// are in flight while the bricks of the current one run (the top window, whose padded tile leaves room for one buffer
+// only at three CTAs per SM, runs with NBUF = 1).
+// Shared memory: [NBUF tiles: Rn x Wn x gp doubles][beta delta: LTB][alpha delta: LTA][batch bases: WIN_RMAX x 16]
+// [tiles per batch: WIN_RMAX][list headers: int4 x SQ_WIN_MAX_BRICKS][per brick: maxQ uint2 quad entries + maxS uint32
+// single entries, BYTE offsets in 16-bit fields].
+template <int NBUF>
+__global__ void __launch_bounds__(WIN_THREADS, NBUF == 2 ? 2 : 3)
 win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_constant__ WinProgram P) {
   extern __shared__ double tile[];
-  int* const sdB = reinterpret_cast<int*>(tile + W.tile_doubles);
+  int* const sdB = reinterpret_cast<int*>(tile + NBUF * W.tile_doubles);
   int* const sdA = sdB + W.LTB;
-  int* const sbase = sdA + W.LTA;
-  int4* const shdr = reinterpret_cast<int4*>(sbase + WIN_G);             // 16-byte aligned (host pads the table sizes)
+  int* const sbase = sdA + W.LTA;                                        // [batch][16]
+  int* const skcnt = sbase + WIN_RMAX * WIN_G;                           // [batch]
+  int4* const shdr = reinterpret_cast<int4*>(skcnt + WIN_RMAX);          // 16-byte aligned (host pads the table sizes)
   uint2* const qall = reinterpret_cast<uint2*>(shdr + SQ_WIN_MAX_BRICKS);
   const int per_brick = 2 * W.maxQ + W.maxS;                             // words per brick: quads first, then singles
 
-  const int2 ga = __ldg(W.groupsA + blockIdx.y), gb = __ldg(W.chunksB + blockIdx.x);
-  const int clsA = ga.y, clsB = gb.y & 0xffff, kcnt = gb.y >> 16;
+  const int2 ga = __ldg(W.groupsA + blockIdx.y);
+  const int2 rg = __ldg(W.rangesB + blockIdx.x);                         // {first entry of rchunks, batches}
+  const int n_items = rg.y;
+  const int clsA = ga.y, clsB = __ldg(W.chunksB + __ldg(W.rchunks + rg.x)).y & 0xffff;
   const int2 ca2 = __ldg(W.clsA + clsA), cb2 = __ldg(W.clsB + clsB);
   const int Rn = ca2.x, Wn = cb2.x;
   const int GP = W.gp;
@@ -118,38 +128,49 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = threadIdx.x & (WIN_G - 1);
 
-  // ---- round trip 1: class tables and list headers ----
+  // ---- round trip 1: class tables, batch bases, list headers ----
   for (int t = threadIdx.x; t < Wn; t += WIN_THREADS) sdB[t] = __ldg(W.deltaB + clsB * W.LTB + t);
   for (int t = threadIdx.x; t < Rn; t += WIN_THREADS) sdA[t] = __ldg(W.deltaA + clsA * W.LTA + t);
-  if (threadIdx.x < WIN_G) sbase[threadIdx.x] = __ldg(W.gbaseB + gb.x * WIN_G + threadIdx.x);
-  if (threadIdx.x >= 32 && (int)threadIdx.x < 32 + P.n)
-    shdr[threadIdx.x - 32] = __ldg(W.listidx + (P.pair[threadIdx.x - 32] * W.H1 + ca2.y) * W.H1 + cb2.y);
+  if ((int)threadIdx.x < n_items * WIN_G) {
+    const int2 ch = __ldg(W.chunksB + __ldg(W.rchunks + rg.x + (threadIdx.x >> 4)));
+    sbase[threadIdx.x] = __ldg(W.gbaseB + ch.x * WIN_G + g);
+    if (g == 0) skcnt[threadIdx.x >> 4] = ch.y >> 16;
+  }
+  if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + P.n)
+    shdr[threadIdx.x - 128] = __ldg(W.listidx + (P.pair[threadIdx.x - 128] * W.H1 + ca2.y) * W.H1 + cb2.y);
   __syncthreads();
 
-  // ---- round trip 2: the whole batch with 8-byte async copies, and (meanwhile) the list entries ----
-  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tile);
-  if (W.lanes_j) {
-    const int NX = kcnt * Wn;
-    const float invW = 1.0f / (float)Wn;
-    for (int r = warp; r < Rn; r += WIN_WARPS) {
-      const double* src = C + (int64_t)(ga.x + sdA[r]) * NB;
-      const uint32_t dst = tb + (uint32_t)(r * RS) * 8u;
-      for (int x = lane; x < NX; x += 32) {
-        const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
-        cp_async8(dst + (uint32_t)(j * GP + gg) * 8u, src + sbase[gg] + sdB[j]);
+  const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(tile);
+  // the whole batch is requested at once with 8-byte async copies
+  auto issue_loads = [&](int it) {
+    const uint32_t tb = tb0 + (uint32_t)((it % NBUF) * W.tile_doubles) * 8u;
+    const int kcnt = skcnt[it];
+    const int* sb = sbase + it * WIN_G;
+    if (W.lanes_j) {
+      const int NX = kcnt * Wn;
+      const float invW = 1.0f / (float)Wn;
+      for (int r = warp; r < Rn; r += WIN_WARPS) {
+        const double* src = C + (int64_t)(ga.x + sdA[r]) * NB;
+        const uint32_t dst = tb + (uint32_t)(r * RS) * 8u;
+        for (int x = lane; x < NX; x += 32) {
+          const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
+          cp_async8(dst + (uint32_t)(j * GP + gg) * 8u, src + sb[gg] + sdB[j]);
+        }
       }
-    }
-  } else {
-    const int myb = sbase[g];
-    for (int r = warp; r < Rn; r += WIN_WARPS) {
-      const double* src = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
-      const uint32_t dst = tb + (uint32_t)(r * RS + g) * 8u;
-      if (g < kcnt) {
+    } else if (g < kcnt) {
+      const int myb = sb[g];
+      for (int r = warp; r < Rn; r += WIN_WARPS) {
+        const double* src = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
+        const uint32_t dst = tb + (uint32_t)(r * RS + g) * 8u;
 #pragma unroll 4
         for (int j = lane >> 4; j < Wn; j += 2) cp_async8(dst + (uint32_t)(j * GP) * 8u, src + sdB[j]);
       }
     }
-  }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ---- round trip 2: the first batch, and (meanwhile) the list entries ----
+  issue_loads(0);
   {
     // one entry per thread and brick (maxQ + maxS <= WIN_THREADS): all loads first, then scale to byte offsets
     uint32_t raw[SQ_WIN_MAX_BRICKS];
@@ -178,88 +199,101 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
       }
     }
   }
-  cp_async_wait_all();
 
-  // ---- bricks ----
   // 8 lanes x 2 tiles per work-list entry (32 entries in flight per CTA); every shared-memory access moves 16 bytes
   const int g2 = threadIdx.x & 7, slot = threadIdx.x >> 3;
-  const bool on = 2 * g2 < kcnt;   // an odd batch computes one unused tile along (its lanes are never stored to memory)
-  const uint32_t tgb = tb + (uint32_t)g2 * 16u;
   const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
-  for (int b = 0; b < P.n; ++b) {
-    __syncthreads();   // convergent: every thread of the CTA, also the lanes of unused tiles
-    if (!on) continue;
-    const int4 hd = shdr[b];
-    const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
-    const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
-    const WinBrick& br = P.br[b];
-    for (int e = slot; e < nQ; e += WIN_SLOTS) {   // 4x4 entries
-      uint32_t ux, uy;
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
-      const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
-      const double2 y0 = lds128(a0 + c0), y1 = lds128(a0 + c1), y2 = lds128(a1 + c0), y3 = lds128(a1 + c1);
-      double2 z;
-      z.x = br.m[0] * y0.x + br.m[1] * y1.x + br.m[2] * y2.x + br.m[3] * y3.x;
-      z.y = br.m[0] * y0.y + br.m[1] * y1.y + br.m[2] * y2.y + br.m[3] * y3.y;
-      sts128(a0 + c0, z);
-      z.x = br.m[4] * y0.x + br.m[5] * y1.x + br.m[6] * y2.x + br.m[7] * y3.x;
-      z.y = br.m[4] * y0.y + br.m[5] * y1.y + br.m[6] * y2.y + br.m[7] * y3.y;
-      sts128(a0 + c1, z);
-      z.x = br.m[8] * y0.x + br.m[9] * y1.x + br.m[10] * y2.x + br.m[11] * y3.x;
-      z.y = br.m[8] * y0.y + br.m[9] * y1.y + br.m[10] * y2.y + br.m[11] * y3.y;
-      sts128(a1 + c0, z);
-      z.x = br.m[12] * y0.x + br.m[13] * y1.x + br.m[14] * y2.x + br.m[15] * y3.x;
-      z.y = br.m[12] * y0.y + br.m[13] * y1.y + br.m[14] * y2.y + br.m[15] * y3.y;
-      sts128(a1 + c1, z);
-    }
-    {   // 2x2 entries: alpha singles first, then beta singles; two per step
-      int e = slot;
-      for (; e + WIN_SLOTS < nS; e += 2 * WIN_SLOTS) {
-        uint32_t u, v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sl + (uint32_t)(e + WIN_SLOTS) * 4u));
-        const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16), p0 = tgb + (v & 0xffffu), p1 = tgb + (v >> 16);
-        const double2 y0 = lds128(o0), y1 = lds128(o1), w0 = lds128(p0), w1 = lds128(p1);
-        const bool al = e < nSa, bl = e + WIN_SLOTS < nSa;
-        const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb, c2 = bl ? br.ca : br.cb, s2 = bl ? br.sa : br.sb;
-        sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
-        sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
-        sts128(p0, make_double2(c2 * w0.x - s2 * w1.x, c2 * w0.y - s2 * w1.y));
-        sts128(p1, make_double2(c2 * w1.x + s2 * w0.x, c2 * w1.y + s2 * w0.y));
-      }
-      if (e < nS) {
-        uint32_t u;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
-        const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16);
-        const bool al = e < nSa;
-        const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb;
-        const double2 y0 = lds128(o0), y1 = lds128(o1);
-        sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
-        sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
-      }
-    }
-  }
-  __syncthreads();
+  for (int it = 0; it < n_items; ++it) {
+    const int kcnt = skcnt[it];
+    const uint32_t tb = tb0 + (uint32_t)((it % NBUF) * W.tile_doubles) * 8u;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // batch `it` has landed; every thread is done with the stores of batch it - 1
+    if (NBUF == 2 && it + 1 < n_items) issue_loads(it + 1);   // into the other buffer, in flight during the bricks
 
-  // ---- store ----
-  if (W.lanes_j) {
-    const int NX = kcnt * Wn;
-    const float invW = 1.0f / (float)Wn;
-    for (int r = warp; r < Rn; r += WIN_WARPS) {
-      double* dst = C + (int64_t)(ga.x + sdA[r]) * NB;
-      const double* srct = tile + r * RS;
-      for (int x = lane; x < NX; x += 32) {
-        const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
-        stg_stream(dst + sbase[gg] + sdB[j], srct[j * GP + gg]);
+    // ---- bricks ----
+    const bool on = 2 * g2 < kcnt;   // an odd batch computes one unused tile along (its lanes are never stored to memory)
+    const uint32_t tgb = tb + (uint32_t)g2 * 16u;
+    for (int b = 0; b < P.n; ++b) {
+      if (b) __syncthreads();   // convergent: every thread of the CTA, also the lanes of unused tiles
+      if (!on) continue;
+      const int4 hd = shdr[b];
+      const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
+      const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
+      const WinBrick& br = P.br[b];
+      for (int e = slot; e < nQ; e += WIN_SLOTS) {   // 4x4 entries
+        uint32_t ux, uy;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
+        const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
+        const double2 y0 = lds128(a0 + c0), y1 = lds128(a0 + c1), y2 = lds128(a1 + c0), y3 = lds128(a1 + c1);
+        double2 z;
+        z.x = br.m[0] * y0.x + br.m[1] * y1.x + br.m[2] * y2.x + br.m[3] * y3.x;
+        z.y = br.m[0] * y0.y + br.m[1] * y1.y + br.m[2] * y2.y + br.m[3] * y3.y;
+        sts128(a0 + c0, z);
+        z.x = br.m[4] * y0.x + br.m[5] * y1.x + br.m[6] * y2.x + br.m[7] * y3.x;
+        z.y = br.m[4] * y0.y + br.m[5] * y1.y + br.m[6] * y2.y + br.m[7] * y3.y;
+        sts128(a0 + c1, z);
+        z.x = br.m[8] * y0.x + br.m[9] * y1.x + br.m[10] * y2.x + br.m[11] * y3.x;
+        z.y = br.m[8] * y0.y + br.m[9] * y1.y + br.m[10] * y2.y + br.m[11] * y3.y;
+        sts128(a1 + c0, z);
+        z.x = br.m[12] * y0.x + br.m[13] * y1.x + br.m[14] * y2.x + br.m[15] * y3.x;
+        z.y = br.m[12] * y0.y + br.m[13] * y1.y + br.m[14] * y2.y + br.m[15] * y3.y;
+        sts128(a1 + c1, z);
+      }
+      {   // 2x2 entries: alpha singles first, then beta singles; two per step
+        int e = slot;
+        for (; e + WIN_SLOTS < nS; e += 2 * WIN_SLOTS) {
+          uint32_t u, v;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sl + (uint32_t)(e + WIN_SLOTS) * 4u));
+          const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16), p0 = tgb + (v & 0xffffu), p1 = tgb + (v >> 16);
+          const double2 y0 = lds128(o0), y1 = lds128(o1), w0 = lds128(p0), w1 = lds128(p1);
+          const bool al = e < nSa, bl = e + WIN_SLOTS < nSa;
+          const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb, c2 = bl ? br.ca : br.cb, s2 = bl ? br.sa : br.sb;
+          sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
+          sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
+          sts128(p0, make_double2(c2 * w0.x - s2 * w1.x, c2 * w0.y - s2 * w1.y));
+          sts128(p1, make_double2(c2 * w1.x + s2 * w0.x, c2 * w1.y + s2 * w0.y));
+        }
+        if (e < nS) {
+          uint32_t u;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
+          const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16);
+          const bool al = e < nSa;
+          const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb;
+          const double2 y0 = lds128(o0), y1 = lds128(o1);
+          sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
+          sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
+        }
       }
     }
-  } else if (g < kcnt) {
-    const int myb = sbase[g];
-    for (int r = warp; r < Rn; r += WIN_WARPS) {
-      double* dst = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
-      const double* srct = tile + r * RS + g;
+    __syncthreads();
+
+    // ---- store ----
+    const int* sb = sbase + it * WIN_G;
+    const double* tbuf = tile + (it % NBUF) * W.tile_doubles;
+    if (W.lanes_j) {
+      const int NX = kcnt * Wn;
+      const float invW = 1.0f / (float)Wn;
+      for (int r = warp; r < Rn; r += WIN_WARPS) {
+        double* dst = C + (int64_t)(ga.x + sdA[r]) * NB;
+        const double* srct = tbuf + r * RS;
+        for (int x = lane; x < NX; x += 32) {
+          const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
+          stg_stream(dst + sb[gg] + sdB[j], srct[j * GP + gg]);
+        }
+      }
+    } else if (g < kcnt) {
+      const int myb = sb[g];
+      for (int r = warp; r < Rn; r += WIN_WARPS) {
+        double* dst = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
+        const double* srct = tbuf + r * RS + g;
 #pragma unroll 4
-      for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * GP]);
+        for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * GP]);
+      }
+    }
+    if (NBUF == 1 && it + 1 < n_items) {
+      __syncthreads();   // the single buffer is free again
+      issue_loads(it + 1);
     }
   }
 }
@@ -452,6 +486,8 @@ void sq_free_win_tables(WinTables* wt) {
   cudaFree(wt->d_deltaA);
   cudaFree(wt->d_chunksB);
   cudaFree(wt->d_gbaseB);
+  cudaFree(wt->d_rangesB);
+  cudaFree(wt->d_rchunks);
   cudaFree(wt->d_clsB);
   cudaFree(wt->d_deltaB);
   cudaFree(wt->d_lists);
@@ -467,10 +503,10 @@ bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H) {
   return hi == lo + 1 && lo >= w0 && hi < w0 + H && !pt.cross_global && pt.n_cross_items == 0;
 }
 
-size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int lta, int ltb, int maxQ, int maxS, int n_bricks) {
-  const size_t tile = sizeof(double) * (size_t)max_a * (size_t)max_b * (size_t)gp;
-  const size_t tabs = 4 * (size_t)(ltb + lta + WIN_G + 4 * SQ_WIN_MAX_BRICKS);   // tile_doubles is even: 16-byte aligned
-  return tile + tabs + (size_t)n_bricks * ((size_t)maxQ * 8 + (size_t)maxS * 4);
+size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int nbuf, int lta, int ltb, int maxQ, int maxS, int n_bricks) {
+  const size_t tile = sizeof(double) * (size_t)max_a * (size_t)max_b * (size_t)gp;   // even number of doubles
+  const size_t tabs = 4 * (size_t)(ltb + lta + WIN_RMAX * WIN_G + WIN_RMAX + 4 * SQ_WIN_MAX_BRICKS);
+  return (size_t)nbuf * tile + tabs + (size_t)n_bricks * ((size_t)maxQ * 8 + (size_t)maxS * 4);
 }
 
 // Signs of Ta, Tb and the pair double of orbital pair (i,a) in the window gauge, checked over every pair of
@@ -559,6 +595,40 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
   if (!build_side(sp, 0, w0, H, &hA)) return SQ_OK;
   if (!build_side(sp, 1, w0, H, &hB)) return SQ_OK;
   if (hA.groups.size() > 65535 || hB.groups.empty() || hA.groups.empty()) return SQ_OK;
+  // ranges of up to WIN_RMAX batches of one class per CTA; heavy ranges first
+  std::vector<int> rchunks;
+  std::vector<int2> ranges;
+  {
+    std::vector<int> order(hB.groups.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (hB.groups[a].y & 0xffff) < (hB.groups[b].y & 0xffff); });
+    size_t i = 0;
+    while (i < order.size()) {
+      const int cls = hB.groups[order[i]].y & 0xffff;
+      size_t j = i;
+      while (j < order.size() && (hB.groups[order[j]].y & 0xffff) == cls) ++j;
+      static int rmax = 0;
+      if (!rmax) {
+        const char* e = getenv("SQ_WIN_RANGE");   // batches per CTA, 1..WIN_RMAX
+        rmax = e ? std::max(1, std::min(atoi(e), WIN_RMAX)) : 8;   // 8 measured as good as 16, 4 is 2 % slower, 1 is 16 % slower
+      }
+      const int n = (int)(j - i), parts = (n + rmax - 1) / rmax;
+      for (int q = 0; q < parts; ++q) {
+        const int b0 = (int)((int64_t)n * q / parts), b1 = (int)((int64_t)n * (q + 1) / parts);
+        ranges.push_back(make_int2((int)rchunks.size(), b1 - b0));
+        for (int t = b0; t < b1; ++t) rchunks.push_back(order[i + t]);
+      }
+      i = j;
+    }
+    std::stable_sort(ranges.begin(), ranges.end(), [&](const int2& a, const int2& b) {
+      auto weight = [&](const int2& r) {
+        int w = 0;
+        for (int t = 0; t < r.y; ++t) w += hB.groups[rchunks[r.x + t]].y >> 16;
+        return w * hB.cls[hB.groups[rchunks[r.x]].y & 0xffff].x;
+      };
+      return weight(a) > weight(b);
+    });
+  }
   // work lists per (pair, e_wa, e_wb)
   const int H1 = H + 1;
   std::vector<uint32_t> lists;
@@ -613,7 +683,13 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
   wt->tile_doubles = hA.max_cnt * hB.max_cnt * wt->gp;   // even
   wt->LTA = (hA.LT + 3) & ~3;   // multiples of 4 words: the headers behind the tables stay 16-byte aligned
   wt->LTB = (hB.LT + 3) & ~3;
-  if (sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->gp, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS) > 220 * 1024) return SQ_OK;
+  {
+    // one tile buffer and three CTAs per SM measured faster than two buffers (next batch in flight during the bricks)
+    // and two CTAs per SM; SQ_WIN_NBUF=2 selects the latter for experiments
+    const char* nb = getenv("SQ_WIN_NBUF");
+    wt->nbuf = (nb && nb[0] == '2' && !wt->lanes_j) ? 2 : 1;
+  }
+  if (sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->gp, wt->nbuf, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS) > 220 * 1024) return SQ_OK;
   // the device tables use the padded leading dimensions
   auto repad = [](std::vector<int>& v, int ncls, int lt_old, int lt_new) {
     std::vector<int> o((size_t)ncls * lt_new, 0);
@@ -623,11 +699,12 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
   };
   repad(hA.delta, hA.ncls, hA.LT, wt->LTA);
   repad(hB.delta, hB.ncls, hB.LT, wt->LTB);
-  wt->smem = sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->gp, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS);
+  wt->smem = sq_win_smem_bytes(hA.max_cnt, hB.max_cnt, wt->gp, wt->nbuf, wt->LTA, wt->LTB, maxQ, maxS, SQ_WIN_MAX_BRICKS);
   wt->max_a = hA.max_cnt;
   wt->max_b = hB.max_cnt;
   wt->n_groups_a = (int)hA.groups.size();
   wt->n_chunks_b = (int)hB.groups.size();
+  wt->n_ranges_b = (int)ranges.size();
   wt->touched = sp->local_len();
   if (sp->device >= 0) {
     SQ_CUDA(cudaSetDevice(sp->device));
@@ -636,6 +713,8 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
     SQ_CHECK(win_upload(&wt->d_deltaA, hA.delta));
     SQ_CHECK(win_upload(&wt->d_chunksB, hB.groups));
     SQ_CHECK(win_upload(&wt->d_gbaseB, hB.gbase));
+    SQ_CHECK(win_upload(&wt->d_rangesB, ranges));
+    SQ_CHECK(win_upload(&wt->d_rchunks, rchunks));
     SQ_CHECK(win_upload(&wt->d_clsB, hB.cls));
     SQ_CHECK(win_upload(&wt->d_deltaB, hB.delta));
     SQ_CHECK(win_upload(&wt->d_lists, lists));
@@ -669,22 +748,24 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
   for (int k = n_bricks; k < SQ_WIN_MAX_BRICKS; ++k) P.pair[k] = 0;
   WinDev W;
   W.groupsA = wt.d_groupsA; W.clsA = wt.d_clsA; W.deltaA = wt.d_deltaA;
-  W.chunksB = wt.d_chunksB; W.gbaseB = wt.d_gbaseB; W.clsB = wt.d_clsB; W.deltaB = wt.d_deltaB;
+  W.chunksB = wt.d_chunksB; W.gbaseB = wt.d_gbaseB; W.rangesB = wt.d_rangesB; W.rchunks = wt.d_rchunks; W.clsB = wt.d_clsB; W.deltaB = wt.d_deltaB;
   W.lists = wt.d_lists; W.listidx = wt.d_listidx;
   W.LTA = wt.LTA; W.LTB = wt.LTB; W.H1 = wt.H + 1;
   W.lanes_j = wt.lanes_j;
   W.gp = wt.gp;
   W.tile_doubles = wt.tile_doubles; W.maxQ = wt.maxQ; W.maxS = wt.maxS;
-  const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.gp, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks);
-  const dim3 grid((unsigned)wt.n_chunks_b, (unsigned)wt.n_groups_a);
+  const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.gp, wt.nbuf, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks);
+  const dim3 grid((unsigned)wt.n_ranges_b, (unsigned)wt.n_groups_a);
   cudaError_t e = cudaSuccess;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    e = cudaFuncSetAttribute(win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) attr = smem;
+  static size_t attr[3] = {0, 0, 0};
+  if (smem > 48 * 1024 && smem > attr[wt.nbuf]) {
+    e = wt.nbuf == 2 ? cudaFuncSetAttribute(win_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(win_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) attr[wt.nbuf] = smem;
   }
   if (e == cudaSuccess) {
-    win_kernel<<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P);
+    if (wt.nbuf == 2) win_kernel<2><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P);
+    else win_kernel<1><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {

@@ -551,7 +551,7 @@ def test_ucc_wavefunction_object(sq, golden):
     assert np.max(np.abs(grad - arrays["uccwf_gradient"])) < 3e-5
 
 
-WIN_VARIANTS = ["1", "6:5:4,72,5,16,3", "6:4:0,60,2,16,2", "4:0:0,40,1,5,2", "5:0:0,200,4,16,1", "6:0:0,100,0,7,1",
+WIN_VARIANTS = ["1", "6:5:4,113,5,16,3", "6:5:4,72,5,16,3", "6:4:0,60,2,16,2", "4:0:0,40,1,5,2", "5:0:0,200,4,16,1", "6:0:0,100,0,7,1",
                 "5:3:0,100,3,16,2", "8:7:3,220,0,9,1"]
 
 
