@@ -335,3 +335,24 @@ def test_launch_planner_on_host_only_space():
         _lib.check(lib.sq_set_option(b"win", b"1"))
         lib.sq_layout_destroy(lay)
         lib.sq_space_destroy(h)
+
+
+def test_lr_orbital_blocks_match_reference():
+    """RDM-only linear-response orbital blocks (reference density_matrix.py:233-563) against outputs of the reference
+    itself on seeded random h, g, x, rdm1, rdm2 (tests/golden/make_golden_lr.py), incl. no-inactive / no-virtual spaces."""
+    from slowquant_b200 import density_matrix as dm
+
+    gold = np.load(f"{ROOT}/tests/golden/golden_lr.npz")
+    for case in range(3):
+        pre = f"c{case}_"
+        nI, nA, nV, n_exc = (int(x) for x in gold[pre + "dims"])
+        h, g, x = gold[pre + "h"], gold[pre + "g"], gold[pre + "x"]
+        rdm1, rdm2, kappa, resp = gold[pre + "rdm1"], gold[pre + "rdm2"], gold[pre + "kappa"], gold[pre + "resp"]
+        kd = kappa[:, ::-1].copy()
+        assert np.max(np.abs(dm.get_orbital_gradient_response(h, g, kappa, nI, nA, rdm1, rdm2) - gold[pre + "grad_response"])) < 1e-11
+        assert np.max(np.abs(dm.get_orbital_response_metric_sigma(kappa, nI, nA, rdm1) - gold[pre + "metric_sigma"])) < 1e-13
+        for s in range(4):
+            assert abs(dm.get_orbital_response_vector_norm(kappa, nI, nA, rdm1, resp, s, n_exc) - gold[pre + "vector_norm"][s]) < 1e-11
+            assert abs(dm.get_orbital_response_property_gradient(x, kappa, nI, nA, rdm1, resp, s, n_exc) - gold[pre + "property_gradient"][s]) < 1e-11
+        assert np.max(np.abs(dm.get_orbital_response_hessian_block(h, g, kd, kappa, nI, nA, rdm1, rdm2) - gold[pre + "hessian_A"])) < 1e-10
+        assert np.max(np.abs(dm.get_orbital_response_hessian_block(h, g, kd, kd, nI, nA, rdm1, rdm2) - gold[pre + "hessian_B"])) < 1e-10
