@@ -101,7 +101,8 @@ int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last);
 /* launch plan of ops [first,last): out6 = {launches, window sweeps, bricks inside window sweeps, quad launches,
  * single-brick launches, other launches}.  (No reference counterpart: the reference applies one operator per pass.) */
 int sq_layout_plan_stats(const sq_layout* lay, int first, int last, int64_t* out6);
-/* run-time switch of the launch planner (A/B comparisons, tests): name "win", value "0" (window sweeps off),
+/* run-time switches (A/B comparisons, tests).  name "wingrad": "1" routes sq_ups_grad_sweep through the window kernel
+ * (default "0": one brick per launch).  name "win": launch planner of sq_ups_apply, value "0" (window sweeps off),
  * "1" (defaults) or "w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks" */
 int sq_set_option(const char* name, const char* value);
 

@@ -545,6 +545,7 @@ static int get_quad(sq_layout* lay, int pA, int pB, const QuadTables** out) {
 // the window that can absorb the most such bricks; non-tile operators are barriers.
 
 static int g_plan_version = 0;   // bumped by sq_set_option: cached plans of older versions are dropped
+static int g_win_grad = 0;       // sq_set_option("wingrad", "1"): gradient sweep through the window kernel
 
 struct WinConfig {
   bool enabled = true;
@@ -593,6 +594,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
   if (strcmp(name, "win") == 0) {
     parse_win_config(value, &win_config());
     ++g_plan_version;
+    return SQ_OK;
+  }
+  if (strcmp(name, "wingrad") == 0) {
+    g_win_grad = (value && value[0] == '1') ? 1 : 0;
     return SQ_OK;
   }
   sq_set_error("sq_set_option: unknown option '%s'", name);
@@ -1294,57 +1299,109 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, plan_th.data(), &runs);
   // every launch writes its <bra|T|ket> values into a device array; ONE copy back at the end of the sweep
-  std::vector<int> slot_op;   // layout operator each device slot belongs to
-  for (auto& run : runs) {
-    const LayoutOp& op = lay->ops[run[0]];
+  std::vector<int> slot_op;            // layout operator each device slot belongs to
+  std::vector<int> run_slot0(runs.size(), -1);
+  for (size_t ri = 0; ri < runs.size(); ++ri) {
+    const LayoutOp& op = lay->ops[runs[ri][0]];
     if (is_tile_op(op)) {
-      for (int k : run)
+      run_slot0[ri] = (int)slot_op.size();
+      for (int k : runs[ri])
         for (int s = 0; s < tile_steps_of(lay->ops[k]); ++s) slot_op.push_back(k);
     } else if (!op.null_op && op.gen >= 0) {
-      slot_op.push_back(run[0]);
+      run_slot0[ri] = (int)slot_op.size();
+      slot_op.push_back(runs[ri][0]);
     }
   }
   double* d_grad = nullptr;
-  if (!slot_op.empty()) SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st));
+  if (!slot_op.empty()) {
+    SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st));
+    SQ_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * slot_op.size(), st));
+  }
+  // the same launch plan as sq_ups_apply: bricks of a window sweep are differentiated and applied inside the sweep
+  // (commuting bricks may be reordered: <bra|T_k|ket> does not change); quad launches run as two single bricks
+  std::vector<Launch> launches;
   int status = SQ_OK;
-  size_t slot = 0;
-  for (auto& run : runs) {
+  if (g_win_grad) {
+    status = plan_launches(lay, runs, &launches);
+  } else {
+    // default: one fused brick per launch (tile_grad_kernel_v2 runs at 0.7 of the HBM roofline; the window gradient
+    // kernel is correct but not yet faster per brick)
+    launches.resize(runs.size());
+    for (size_t ri = 0; ri < runs.size(); ++ri) launches[ri].runs = {(int)ri};
+  }
+  bool in_gauge = false;
+  auto set_gauge = [&](bool want) -> int {
+    if (want == in_gauge) return SQ_OK;
+    SQ_CHECK(sq_launch_gauge(sp, bra_dev, st));
+    SQ_CHECK(sq_launch_gauge(sp, ket_dev, st));
+    in_gauge = want;
+    return SQ_OK;
+  };
+  auto tile_program = [&](const std::vector<int>& run, TileStep* steps, int* n_steps) -> int {
+    int step_op[SQ_MAX_PROGRAM];
+    SQ_CHECK(run_tile(sp, lay, run, thetas_host, 0, steps, n_steps, step_op));
+    for (int s = 0; s < *n_steps; ++s)
+      if (std::fabs(thetas_host[step_op[s]]) < 1e-28) { steps[s].c = 1.0; steps[s].s = 0.0; }
+    return SQ_OK;
+  };
+  for (const Launch& l : launches) {
     if (status != SQ_OK) break;
-    const LayoutOp& op = lay->ops[run[0]];
-    if (is_tile_op(op)) {
-      TileStep steps[SQ_MAX_PROGRAM];
-      int step_op[SQ_MAX_PROGRAM], n_steps = 0;
-      status = run_tile(sp, lay, run, thetas_host, 0, steps, &n_steps, step_op);
+    if (l.kind == 2) {
+      status = set_gauge(true);
       if (status != SQ_OK) break;
-      for (int s = 0; s < n_steps; ++s)
-        if (std::fabs(thetas_host[step_op[s]]) < 1e-28) { steps[s].c = 1.0; steps[s].s = 0.0; }
-      status = sq_launch_tile_grad(sp, lay->pairs[op.pair], steps, n_steps, bra_dev, ket_dev, d_grad + slot, st);
-      slot += n_steps;
-    } else if (op.null_op) {
-      continue;
-    } else if (op.gen >= 0) {
-      const int k = run[0];
-      double th = thetas_host[k];
-      double c = std::cos(th), s = std::sin(th);
-      if (std::fabs(th) < 1e-28) { c = 1.0; s = 0.0; }
-      status = sq_launch_gen_grad(sp, lay->gens[op.gen], c, s, bra_dev, ket_dev, d_grad + slot, st);
-      slot += 1;
-    } else if (op.multi) {
-      const int k = run[0];
-      status = sq_ensure_work(sp, 2);
-      if (status == SQ_OK) status = sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, ket_dev, sp->d_work[2], 0, st);
-      double g = 0.0;
-      if (status == SQ_OK) status = sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st);
-      grad_host[k - first] = 2.0 * g;
-      if (status == SQ_OK && std::fabs(thetas_host[k]) >= 1e-28) {
-        status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st);
-        if (status == SQ_OK) status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st);
+      int pair_idx[SQ_WIN_MAX_BRICKS], nst[SQ_WIN_MAX_BRICKS], slot0[SQ_WIN_MAX_BRICKS];
+      TileStep wsteps[SQ_WIN_MAX_BRICKS][SQ_MAX_PROGRAM];
+      const TileStep* sptr[SQ_WIN_MAX_BRICKS];
+      int nb = 0;
+      for (int t : l.runs) {
+        status = tile_program(runs[t], wsteps[nb], &nst[nb]);
+        if (status != SQ_OK) break;
+        pair_idx[nb] = lay->ops[runs[t][0]].pair;
+        slot0[nb] = run_slot0[t];
+        sptr[nb] = wsteps[nb];
+        ++nb;
       }
-    } else {
-      sq_set_error("sq_ups_grad_sweep: operator %d has no generator", run[0]);
-      status = SQ_ERR_INVALID;
+      if (status == SQ_OK) status = sq_launch_win_grad(sp, *l.wt, pair_idx, sptr, nst, slot0, nb, bra_dev, ket_dev, d_grad, st);
+      continue;
+    }
+    status = set_gauge(false);
+    if (status != SQ_OK) break;
+    for (int t : l.runs) {
+      if (status != SQ_OK) break;
+      const std::vector<int>& run = runs[t];
+      const LayoutOp& op = lay->ops[run[0]];
+      if (is_tile_op(op)) {
+        TileStep steps[SQ_MAX_PROGRAM];
+        int n_steps = 0;
+        status = tile_program(run, steps, &n_steps);
+        if (status != SQ_OK) break;
+        status = sq_launch_tile_grad(sp, lay->pairs[op.pair], steps, n_steps, bra_dev, ket_dev, d_grad + run_slot0[t], st);
+      } else if (op.null_op) {
+        continue;
+      } else if (op.gen >= 0) {
+        const int k = run[0];
+        double th = thetas_host[k];
+        double c = std::cos(th), s = std::sin(th);
+        if (std::fabs(th) < 1e-28) { c = 1.0; s = 0.0; }
+        status = sq_launch_gen_grad(sp, lay->gens[op.gen], c, s, bra_dev, ket_dev, d_grad + run_slot0[t], st);
+      } else if (op.multi) {
+        const int k = run[0];
+        status = sq_ensure_work(sp, 2);
+        if (status == SQ_OK) status = sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, ket_dev, sp->d_work[2], 0, st);
+        double g = 0.0;
+        if (status == SQ_OK) status = sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st);
+        grad_host[k - first] = 2.0 * g;
+        if (status == SQ_OK && std::fabs(thetas_host[k]) >= 1e-28) {
+          status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st);
+          if (status == SQ_OK) status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st);
+        }
+      } else {
+        sq_set_error("sq_ups_grad_sweep: operator %d has no generator", run[0]);
+        status = SQ_ERR_INVALID;
+      }
     }
   }
+  if (status == SQ_OK) status = set_gauge(false);
   if (status == SQ_OK && !slot_op.empty()) {
     std::vector<double> g(slot_op.size());
     cudaError_t e = cudaMemcpyAsync(g.data(), d_grad, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, st);

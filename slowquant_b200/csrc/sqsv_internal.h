@@ -229,6 +229,8 @@ int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st);
 bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H);
 int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** out);
 void sq_free_win_tables(WinTables* wt);
+int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
+                       const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, cudaStream_t st);
 int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
                   int n_bricks, double* state, cudaStream_t st);
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,

@@ -298,6 +298,242 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gradient sweep on windows: the same batches for TWO vectors (bra, ket).  For every rotation step k of every brick
+// (reference ups_wavefunction.py:1114-1138) accumulate <bra|T_k|ket> on the current tiles, then rotate both vectors.
+// A work-list entry is closed under all steps of its brick (alpha rotation: rows r,r'; beta rotation: columns c,c';
+// pair double: (r,c) <-> (r',c')), so an entry stays in registers for the whole brick.  Reordering commuting bricks
+// leaves every <bra|T_k|ket> unchanged (the moved operators commute with T_k and act on both vectors).
+// ---------------------------------------------------------------------------------------------
+struct WinGradBrick {
+  int n;                        // rotation steps
+  int kind[SQ_MAX_PROGRAM];     // 0 alpha rotation, 1 beta rotation, 2 pair double; bit 4: T has sign -1 in the window gauge
+  double c[SQ_MAX_PROGRAM], s[SQ_MAX_PROGRAM];   // s carries the sign
+  int slot0;                    // first output slot of this brick's steps
+};
+struct WinGradProgram {
+  int n;
+  int pair[SQ_WIN_MAX_BRICKS];
+  WinGradBrick br[SQ_WIN_MAX_BRICKS];
+};
+
+__device__ __forceinline__ void grot(double& xs, double& xt, double c, double s) {
+  const double a = xs, b = xt;
+  xs = c * a - s * b;
+  xt = c * b + s * a;
+}
+
+// Shared memory: [bra tile][ket tile][accumulators: SQ_WIN_MAX_BRICKS x SQ_MAX_PROGRAM doubles][tables as win_kernel]
+__global__ void __launch_bounds__(WIN_THREADS, 2)
+win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, const WinDev W,
+                const __grid_constant__ WinGradProgram P, double* __restrict__ grad_out) {
+  extern __shared__ double tile[];
+  const int TD = W.tile_doubles;
+  double* const sacc = tile + 2 * TD;
+  int* const sdB = reinterpret_cast<int*>(sacc + SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM);
+  int* const sdA = sdB + W.LTB;
+  int* const sbase = sdA + W.LTA;
+  int* const skcnt = sbase + WIN_RMAX * WIN_G;
+  int4* const shdr = reinterpret_cast<int4*>(skcnt + WIN_RMAX);
+  uint2* const qall = reinterpret_cast<uint2*>(shdr + SQ_WIN_MAX_BRICKS);
+  const int per_brick = 2 * W.maxQ + W.maxS;
+
+  const int2 ga = __ldg(W.groupsA + blockIdx.y);
+  const int2 rg = __ldg(W.rangesB + blockIdx.x);
+  const int n_items = rg.y;
+  const int clsA = ga.y, clsB = __ldg(W.chunksB + __ldg(W.rchunks + rg.x)).y & 0xffff;
+  const int2 ca2 = __ldg(W.clsA + clsA), cb2 = __ldg(W.clsB + clsB);
+  const int Rn = ca2.x, Wn = cb2.x;
+  const int GP = W.gp;
+  const int RS = Wn * GP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = threadIdx.x & (WIN_G - 1), slot = threadIdx.x >> 4;
+
+  for (int t = threadIdx.x; t < Wn; t += WIN_THREADS) sdB[t] = __ldg(W.deltaB + clsB * W.LTB + t);
+  for (int t = threadIdx.x; t < Rn; t += WIN_THREADS) sdA[t] = __ldg(W.deltaA + clsA * W.LTA + t);
+  if ((int)threadIdx.x < n_items * WIN_G) {
+    const int2 ch = __ldg(W.chunksB + __ldg(W.rchunks + rg.x + (threadIdx.x >> 4)));
+    sbase[threadIdx.x] = __ldg(W.gbaseB + ch.x * WIN_G + g);
+    if (g == 0) skcnt[threadIdx.x >> 4] = ch.y >> 16;
+  }
+  if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + P.n)
+    shdr[threadIdx.x - 128] = __ldg(W.listidx + (P.pair[threadIdx.x - 128] * W.H1 + ca2.y) * W.H1 + cb2.y);
+  if (threadIdx.x < SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM) sacc[threadIdx.x] = 0.0;
+  __syncthreads();
+
+  const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(tile);
+  auto issue_loads = [&](int it) {
+    const int kcnt = skcnt[it];
+    const int* sb = sbase + it * WIN_G;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double* C = v ? KET : BRA;
+      const uint32_t tb = tb0 + (uint32_t)(v * TD) * 8u;
+      if (W.lanes_j) {
+        const int NX = kcnt * Wn;
+        const float invW = 1.0f / (float)Wn;
+        for (int r = warp; r < Rn; r += WIN_WARPS) {
+          const double* src = C + (int64_t)(ga.x + sdA[r]) * NB;
+          const uint32_t dst = tb + (uint32_t)(r * RS) * 8u;
+          for (int x = lane; x < NX; x += 32) {
+            const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
+            cp_async8(dst + (uint32_t)(j * GP + gg) * 8u, src + sb[gg] + sdB[j]);
+          }
+        }
+      } else if (g < kcnt) {
+        const int myb = sb[g];
+        for (int r = warp; r < Rn; r += WIN_WARPS) {
+          const double* src = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
+          const uint32_t dst = tb + (uint32_t)(r * RS + g) * 8u;
+#pragma unroll 4
+          for (int j = lane >> 4; j < Wn; j += 2) cp_async8(dst + (uint32_t)(j * GP) * 8u, src + sdB[j]);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_loads(0);
+  {
+    uint32_t raw[SQ_WIN_MAX_BRICKS];
+#pragma unroll
+    for (int b = 0; b < SQ_WIN_MAX_BRICKS; ++b) {
+      raw[b] = 0u;
+      if (b < P.n) {
+        const int4 li = shdr[b];
+        if ((int)threadIdx.x < li.y + li.z + li.w) raw[b] = __ldg(W.lists + li.x + threadIdx.x);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < SQ_WIN_MAX_BRICKS; ++b) {
+      if (b < P.n) {
+        const int4 li = shdr[b];
+        const int t = threadIdx.x;
+        const uint32_t w = raw[b];
+        uint32_t* dst = reinterpret_cast<uint32_t*>(qall) + b * per_brick;
+        if (t < li.y) {
+          const uint32_t r0 = (w & 255u) * RS, r1 = ((w >> 8) & 255u) * RS, c0 = ((w >> 16) & 255u) * GP, c1 = (w >> 24) * GP;
+          reinterpret_cast<uint2*>(dst)[t] = make_uint2((r0 | (r1 << 16)) << 3, (c0 | (c1 << 16)) << 3);
+        } else if (t < li.y + li.z + li.w) {
+          const uint32_t o0 = (w & 255u) * RS + ((w >> 8) & 255u) * GP, o1 = ((w >> 16) & 255u) * RS + (w >> 24) * GP;
+          dst[2 * W.maxQ + (t - li.y)] = (o0 | (o1 << 16)) << 3;
+        }
+      }
+    }
+  }
+
+  const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
+  const uint32_t kofs = (uint32_t)TD * 8u;   // ket tile behind the bra tile
+  for (int it = 0; it < n_items; ++it) {
+    const int kcnt = skcnt[it];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const bool on = g < kcnt;
+    const uint32_t tg = tb0 + (uint32_t)g * 8u;   // one tile per thread, 16 lanes per entry
+    for (int b = 0; b < P.n; ++b) {
+      if (b) __syncthreads();
+      const WinGradBrick& br = P.br[b];
+      double acc[SQ_MAX_PROGRAM];
+#pragma unroll
+      for (int k = 0; k < SQ_MAX_PROGRAM; ++k) acc[k] = 0.0;
+      if (on) {
+        const int4 hd = shdr[b];
+        const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
+        const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
+        for (int e = slot; e < nQ; e += WIN_THREADS / WIN_G) {
+          uint32_t ux, uy;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
+          const uint32_t a0 = tg + (ux & 0xffffu), a1 = tg + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
+          double b00 = lds64(a0 + c0), b01 = lds64(a0 + c1), b10 = lds64(a1 + c0), b11 = lds64(a1 + c1);
+          double k00 = lds64(a0 + c0 + kofs), k01 = lds64(a0 + c1 + kofs), k10 = lds64(a1 + c0 + kofs), k11 = lds64(a1 + c1 + kofs);
+#pragma unroll
+          for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
+            if (k >= br.n) break;
+            const int kind = br.kind[k] & 3;
+            const double c = br.c[k], sn = br.s[k];
+            if (kind == 0) {
+              acc[k] += (b10 * k00 - b00 * k10) + (b11 * k01 - b01 * k11);
+              grot(b00, b10, c, sn); grot(b01, b11, c, sn); grot(k00, k10, c, sn); grot(k01, k11, c, sn);
+            } else if (kind == 1) {
+              acc[k] += (b01 * k00 - b00 * k01) + (b11 * k10 - b10 * k11);
+              grot(b00, b01, c, sn); grot(b10, b11, c, sn); grot(k00, k01, c, sn); grot(k10, k11, c, sn);
+            } else {
+              acc[k] += b11 * k00 - b00 * k11;
+              grot(b00, b11, c, sn); grot(k00, k11, c, sn);
+            }
+          }
+          sts64(a0 + c0, b00); sts64(a0 + c1, b01); sts64(a1 + c0, b10); sts64(a1 + c1, b11);
+          sts64(a0 + c0 + kofs, k00); sts64(a0 + c1 + kofs, k01); sts64(a1 + c0 + kofs, k10); sts64(a1 + c1 + kofs, k11);
+        }
+        for (int e = slot; e < nS; e += WIN_THREADS / WIN_G) {
+          uint32_t u;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
+          const uint32_t o0 = tg + (u & 0xffffu), o1 = tg + (u >> 16);
+          const int want = e < nSa ? 0 : 1;   // alpha singles see the alpha rotations only, beta singles the beta ones
+          double b0 = lds64(o0), b1 = lds64(o1), k0 = lds64(o0 + kofs), k1 = lds64(o1 + kofs);
+#pragma unroll
+          for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
+            if (k >= br.n) break;
+            if ((br.kind[k] & 3) != want) continue;
+            acc[k] += b1 * k0 - b0 * k1;
+            grot(b0, b1, br.c[k], br.s[k]);
+            grot(k0, k1, br.c[k], br.s[k]);
+          }
+          sts64(o0, b0); sts64(o1, b1); sts64(o0 + kofs, k0); sts64(o1 + kofs, k1);
+        }
+      }
+      // block-level sum of the step values of this brick (all lanes take part in the shuffles)
+#pragma unroll
+      for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
+        if (k >= br.n) break;
+        double v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0 && v != 0.0) atomicAdd(sacc + b * SQ_MAX_PROGRAM + k, v);
+      }
+    }
+    __syncthreads();
+    // ---- store both vectors ----
+    const int* sb = sbase + it * WIN_G;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      double* C = v ? KET : BRA;
+      const double* tbuf = tile + v * TD;
+      if (W.lanes_j) {
+        const int NX = kcnt * Wn;
+        const float invW = 1.0f / (float)Wn;
+        for (int r = warp; r < Rn; r += WIN_WARPS) {
+          double* dst = C + (int64_t)(ga.x + sdA[r]) * NB;
+          const double* srct = tbuf + r * RS;
+          for (int x = lane; x < NX; x += 32) {
+            const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
+            stg_stream(dst + sb[gg] + sdB[j], srct[j * GP + gg]);
+          }
+        }
+      } else if (g < kcnt) {
+        const int myb = sb[g];
+        for (int r = warp; r < Rn; r += WIN_WARPS) {
+          double* dst = C + (int64_t)(ga.x + sdA[r]) * NB + myb;
+          const double* srct = tbuf + r * RS + g;
+#pragma unroll 4
+          for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * GP]);
+        }
+      }
+    }
+    if (it + 1 < n_items) {
+      __syncthreads();
+      issue_loads(it + 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM) {
+    const int b = threadIdx.x / SQ_MAX_PROGRAM, k = threadIdx.x - b * SQ_MAX_PROGRAM;
+    if (b < P.n && k < P.br[b].n) {
+      const double v = sacc[threadIdx.x];
+      if (v != 0.0) atomicAdd(grad_out + P.br[b].slot0 + k, (P.br[b].kind[k] & 16) ? -v : v);
+    }
+  }
+}
+
 // x[Ia][Ib] *= D(A,B) = (-1)^{popc(A & gword(B))}: into / out of the sign-free gauge (its own inverse)
 __global__ void __launch_bounds__(256)
 gauge_kernel(double* __restrict__ C, int64_t NB, int64_t n_rows, int64_t row_begin, const uint32_t* __restrict__ strA,
@@ -770,6 +1006,65 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
   }
   if (e != cudaSuccess) {
     sq_set_error("win_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+// Gradient sweep of a window launch: out[slot0[k] + step] += <bra|T_step|ket> for every rotation step of brick k
+// (evaluated before that step), then both vectors are rotated.  Both vectors must be in the sign-free gauge.
+int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
+                       const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, cudaStream_t st) {
+  if (!wt.ok || n_bricks < 1 || n_bricks > SQ_WIN_MAX_BRICKS) {
+    sq_set_error("window gradient launch with %d bricks (max %d) or without tables", n_bricks, SQ_WIN_MAX_BRICKS);
+    return SQ_ERR_INVALID;
+  }
+  WinGradProgram P;
+  memset(&P, 0, sizeof(P));
+  P.n = n_bricks;
+  for (int k = 0; k < n_bricks; ++k) {
+    const int lp = wt.pair_local[pair_idx[k]];
+    if (lp < 0 || n_steps[k] < 1 || n_steps[k] > SQ_MAX_PROGRAM) {
+      sq_set_error("window gradient launch: orbital pair %d is outside the window or has a bad program", pair_idx[k]);
+      return SQ_ERR_INVALID;
+    }
+    P.pair[k] = lp;
+    WinGradBrick& b = P.br[k];
+    b.n = n_steps[k];
+    b.slot0 = slot0[k];
+    for (int q = 0; q < n_steps[k]; ++q) {
+      const int kind = steps[k][q].kind;
+      const int eps = wt.eps[3 * lp + kind];   // sign of T_alpha / T_beta / T_double in the window gauge
+      b.kind[q] = kind | (eps < 0 ? 16 : 0);
+      b.c[q] = steps[k][q].c;
+      b.s[q] = eps * steps[k][q].s;
+    }
+  }
+  WinDev W;
+  W.groupsA = wt.d_groupsA; W.clsA = wt.d_clsA; W.deltaA = wt.d_deltaA;
+  W.chunksB = wt.d_chunksB; W.gbaseB = wt.d_gbaseB; W.rangesB = wt.d_rangesB; W.rchunks = wt.d_rchunks; W.clsB = wt.d_clsB; W.deltaB = wt.d_deltaB;
+  W.lists = wt.d_lists; W.listidx = wt.d_listidx;
+  W.LTA = wt.LTA; W.LTB = wt.LTB; W.H1 = wt.H + 1;
+  W.lanes_j = wt.lanes_j;
+  W.gp = wt.gp;
+  W.tile_doubles = wt.tile_doubles; W.maxQ = wt.maxQ; W.maxS = wt.maxS;
+  const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.gp, 2, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks) +
+                      sizeof(double) * SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(win_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      sq_set_error("win_grad_kernel: cannot get %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return SQ_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  const dim3 grid((unsigned)wt.n_ranges_b, (unsigned)wt.n_groups_a);
+  win_grad_kernel<<<grid, WIN_THREADS, smem, st>>>(bra, ket, sp->NB, W, P, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("win_grad_kernel launch failed: %s", cudaGetErrorString(e));
     return SQ_ERR_CUDA;
   }
   g_sq_launches.fetch_add(1);

@@ -598,3 +598,42 @@ def test_window_sweeps_equal_single_brick_launches(sq, n, na, nb, L, qnp):
         assert used > 0, "no window sweep was planned"
     finally:
         sq.lib.check(lib.sq_set_option(b"win", b"1"))
+
+
+@pytest.mark.parametrize("n,na,nb,L,qnp", [(8, 4, 4, 2, False), (9, 5, 4, 2, True), (12, 6, 6, 2, False)])
+def test_window_gradient_sweep(sq, n, na, nb, L, qnp):
+    """theta-gradient sweep through the window kernel (bricks differentiated inside the sweeps, commuting bricks
+    reordered) against the one-brick-per-launch path; at small sizes that path is checked against the oracle's
+    literal loop of ups_wavefunction.py:1114-1138.  Includes a zero theta (gradient without rotation)."""
+    lib = sq.lib.load()
+    types, idx, th, rng = _seeded_case(n, na, nb, L, 900 + n, qnp=qnp)
+    th[3] = 0.0
+    info = sq.ci.get_indexing(0, n, 0, na, nb)
+    lay = _layout(sq, types, idx)
+    dev = torch.device("cuda", info.device)
+    bra = torch.randn(info.num_det, dtype=torch.float64, device=dev)
+    ket = torch.randn(info.num_det, dtype=torch.float64, device=dev)
+    bra /= torch.linalg.norm(bra)
+    ket /= torch.linalg.norm(ket)
+    try:
+        sq.lib.check(lib.sq_set_option(b"wingrad", b"0"))
+        g0, b0, k0 = sq.osa.ups_gradient_sweep(bra, ket, info, th.tolist(), lay)
+        if n <= 9:
+            sp = orc.get_indexing(0, n, 0, na, nb)
+            b_np, k_np = bra.cpu().numpy().copy(), ket.cpu().numpy().copy()
+            gr = np.zeros(len(types))
+            for k in range(len(types)):   # the literal loop of ups_wavefunction.py:1114-1138
+                gr[k] = 2.0 * float(b_np @ orc.get_grad_action(k_np, k, sp, types, idx))
+                b_np = orc.propagate_unitary(b_np, k, sp, th, types, idx)
+                k_np = orc.propagate_unitary(k_np, k, sp, th, types, idx)
+            assert np.max(np.abs(g0 - gr)) < 1e-11
+            assert np.max(np.abs(k0.cpu().numpy() - k_np)) < TOL
+        sq.lib.check(lib.sq_set_option(b"wingrad", b"1"))
+        for cfg in ("1", "5:4:0,72,2,16,2", "6:0:0,100,0,4,1"):
+            sq.lib.check(lib.sq_set_option(b"win", cfg.encode()))
+            g1, b1, k1 = sq.osa.ups_gradient_sweep(bra, ket, info, th.tolist(), lay)
+            assert np.max(np.abs(g1 - g0)) < 1e-12, cfg
+            assert float(torch.max(torch.abs(b1 - b0))) < 1e-13 and float(torch.max(torch.abs(k1 - k0))) < 1e-13, cfg
+    finally:
+        sq.lib.check(lib.sq_set_option(b"win", b"1"))
+        sq.lib.check(lib.sq_set_option(b"wingrad", b"0"))
