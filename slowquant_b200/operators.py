@@ -264,3 +264,86 @@ def one_elec_op_0i_0a(ints_mo: np.ndarray, num_inactive_orbs: int, num_active_or
             if abs(ints_mo[p, q]) > 10**-14:
                 op += float(ints_mo[p, q]) * Epq(p, q)
     return op
+
+
+def _inactive_virtual_changes(p: int, q: int, r: int, s: int, num_inactive_orbs: int, virtual_start: int) -> tuple[int, int]:
+    """(net inactive changes, virtual indices) of e_pqrs, counted as operators.py:562-591: every inactive index
+    counts once, and every create/annihilate pair on the same inactive orbital ((p,q), (r,s), (p,s), (q,r)) gives two back."""
+    idx = (p, q, r, s)
+    n_virt = sum(1 for x in idx if x >= virtual_start)
+    n_inact = sum(1 for x in idx if x < num_inactive_orbs)
+    for x, y in ((p, q), (r, s), (p, s), (q, r)):
+        if x == y and x < num_inactive_orbs:
+            n_inact -= 2
+    return n_inact, n_virt
+
+
+def _hamiltonian_ni_na(
+    h_mo: np.ndarray, g_mo: np.ndarray, num_inactive_orbs: int, num_active_orbs: int, num_virtual_orbs: int, level: int
+) -> FermionicOperator:
+    num_orbs = num_inactive_orbs + num_active_orbs + num_virtual_orbs
+    virtual_start = num_inactive_orbs + num_active_orbs
+    H = FermionicOperator({})
+    for p in range(num_orbs):
+        for q in range(num_orbs):
+            if level == 1:
+                if p >= virtual_start and q >= virtual_start:
+                    continue
+                if p < num_inactive_orbs and q < num_inactive_orbs and p != q:
+                    continue
+            if abs(h_mo[p, q]) > 10**-14:
+                H += float(h_mo[p, q]) * Epq(p, q)
+    for p in range(num_orbs):
+        for q in range(num_orbs):
+            for r in range(num_orbs):
+                for s in range(num_orbs):
+                    if abs(g_mo[p, q, r, s]) <= 10**-14:
+                        continue
+                    n_inact, n_virt = _inactive_virtual_changes(p, q, r, s, num_inactive_orbs, virtual_start)
+                    if n_virt > level or n_inact > level:
+                        continue
+                    H += (1 / 2 * float(g_mo[p, q, r, s])) * epqrs(p, q, r, s)
+    return H
+
+
+def hamiltonian_1i_1a(
+    h_mo: np.ndarray, g_mo: np.ndarray, num_inactive_orbs: int, num_active_orbs: int, num_virtual_orbs: int
+) -> FermionicOperator:
+    """Hamiltonian terms with at most one inactive and one virtual change (operators.py:532-598): the operator
+    that multiplies ONE orbital-rotation generator in the linear-response blocks."""
+    return _hamiltonian_ni_na(h_mo, g_mo, num_inactive_orbs, num_active_orbs, num_virtual_orbs, 1)
+
+
+def hamiltonian_2i_2a(
+    h_mo: np.ndarray, g_mo: np.ndarray, num_inactive_orbs: int, num_active_orbs: int, num_virtual_orbs: int
+) -> FermionicOperator:
+    """Hamiltonian terms with at most two inactive and two virtual changes (operators.py:601-663)."""
+    return _hamiltonian_ni_na(h_mo, g_mo, num_inactive_orbs, num_active_orbs, num_virtual_orbs, 2)
+
+
+def one_elec_op_full_space(ints_mo: np.ndarray, num_orbs: int) -> FermionicOperator:
+    r""":math:`\sum_{pq} o_{pq} E_{pq}` over all orbitals (operators.py:666-684)."""
+    op = FermionicOperator({})
+    for p in range(num_orbs):
+        for q in range(num_orbs):
+            if abs(ints_mo[p, q]) > 10**-14:
+                op += float(ints_mo[p, q]) * Epq(p, q)
+    return op
+
+
+def one_elec_op_1i_1a(
+    ints_mo: np.ndarray, num_inactive_orbs: int, num_active_orbs: int, num_virtual_orbs: int
+) -> FermionicOperator:
+    """One-electron operator with at most one inactive/virtual change (operators.py:711-737)."""
+    num_orbs = num_inactive_orbs + num_active_orbs + num_virtual_orbs
+    virtual_start = num_inactive_orbs + num_active_orbs
+    op = FermionicOperator({})
+    for p in range(num_orbs):
+        for q in range(num_orbs):
+            if p >= virtual_start and q >= virtual_start:
+                continue
+            if p < num_inactive_orbs and q < num_inactive_orbs and p != q:
+                continue
+            if abs(ints_mo[p, q]) > 10**-14:
+                op += float(ints_mo[p, q]) * Epq(p, q)
+    return op

@@ -1,0 +1,87 @@
+"""Config 1 (BASELINE.json configs[0]): tUPS energy + naive linear response on the CUDA path, at the FIXED
+(theta, c_mo) exported from the reference run (tests/golden/make_golden_config1.py).  Compared element-wise:
+ci_coeffs, rdm1, rdm2, energy, the LR matrices A / B / Sigma, excitation energies, excited-state norms and
+oscillator strengths; LiH also against the literals of the reference's own test_ups_naivelr
+(tests/test_unitary_product_state.py:35-61).  Tolerances: amplitudes 1e-12, energies / RDM / matrix elements 1e-10
+(north_star), eigenvalues 1e-8 (generalised eigenproblem of a matrix pair known to 1e-13)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+LIH_ENERGIES = [0.129476, 0.178749, 0.178749, 0.604681, 0.646707, 0.740632, 0.740632, 1.002914,
+                2.074822, 2.137193, 2.137193, 2.455191, 2.954372]
+LIH_OSC = [0.049920, 0.241184, 0.241184, 0.158045, 0.166539, 0.010379, 0.010379, 0.006256,
+           0.062386, 0.128862, 0.128862, 0.046007, 0.003904]
+
+
+@pytest.fixture(scope="module")
+def g1():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_config1.npz"))
+
+
+def _wavefunction(g, name, options):
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    pre = name + "_"
+    ints = ArrayIntegrals(g[pre + "h_ao"], g[pre + "eri_ao"], int(g[pre + "num_elec"]), dipole=tuple(g[pre + "dipole_ao"]))
+    cas = tuple(int(x) for x in g[pre + "cas"])
+    WF = WaveFunctionUPS(cas, g[pre + "c_mo"], ints, "tUPS", ansatz_options=dict(options), include_active_kappa=True)
+    WF.thetas = g[pre + "thetas"].tolist()
+    return WF
+
+
+@pytest.mark.parametrize(
+    "name,options", [("lih", {"n_layers": 1, "skip_last_singles": True}), ("h2o", {"n_layers": 3})]
+)
+def test_tups_energy_and_naive_linear_response(g1, name, options):
+    from slowquant_b200 import _lib
+    from slowquant_b200.linear_response.naive import LinearResponse
+
+    pre = name + "_"
+    WF = _wavefunction(g1, name, options)
+    assert np.max(np.abs(WF.h_mo - g1[pre + "h_mo"])) < 1e-11
+    assert np.max(np.abs(WF.g_mo - g1[pre + "g_mo"])) < 1e-11
+    assert np.max(np.abs(WF.ci_coeffs - g1[pre + "ci"])) < 1e-12
+    assert abs(WF.energy_elec - float(g1[pre + "energy"])) < 1e-10
+    assert np.max(np.abs(WF.rdm1 - g1[pre + "rdm1"])) < 1e-10
+    assert np.max(np.abs(WF.rdm2 - g1[pre + "rdm2"])) < 1e-10
+    before = _lib.load().sq_launch_count()
+    LR = LinearResponse(WF, excitations="SD")
+    assert _lib.load().sq_launch_count() > before, "the LR build launched no CUDA kernels"
+    assert [len(LR.G_ops), len(LR.q_ops)] == [int(x) for x in g1[pre + "num_G_q"]]
+    for key in ("A", "B", "Sigma", "Delta"):
+        assert np.max(np.abs(getattr(LR, key) - g1[pre + key])) < 1e-10, key
+    LR.calc_excitation_energies()
+    assert np.max(np.abs(LR.excitation_energies - g1[pre + "excitation_energies"])) < 1e-8
+    assert np.max(np.abs(LR.get_excited_state_norm() - g1[pre + "norms"])) < 1e-8
+    osc = LR.get_oscillator_strength()
+    assert np.max(np.abs(osc - g1[pre + "oscillator_strengths"])) < 1e-8
+    # transition dipoles are defined up to the sign of each eigenvector
+    assert np.max(np.abs(np.abs(LR.get_transition_dipole()) - np.abs(g1[pre + "transition_dipoles"]))) < 1e-7
+    if name == "lih":
+        assert np.max(np.abs(LR.excitation_energies - np.array(LIH_ENERGIES))) < 1e-4
+        assert np.max(np.abs(osc - np.array(LIH_OSC))) < 1e-3
+    else:
+        # lowest roots of the H2O tUPS(4,4) L=3 naive LR
+        assert np.max(np.abs(LR.excitation_energies[:5] - np.array([0.42592102, 0.52387332, 0.58068225, 0.69052476, 0.91356175]))) < 1e-7
+
+
+def test_naive_lr_refuses_an_unconverged_wave_function(g1):
+    """naive.py:89-92: max|<[G, H]>| > 1e-3 raises."""
+    from slowquant_b200.linear_response.naive import LinearResponse
+
+    WF = _wavefunction(g1, "h2o", {"n_layers": 3})
+    th = WF.thetas
+    th[1] += 0.2
+    WF.thetas = th
+    with pytest.raises(ValueError, match="Large Gradient"):
+        LinearResponse(WF, excitations="SD")
