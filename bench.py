@@ -50,6 +50,7 @@ def parse_args():
                     "alpha-sharded vector (strong scaling; auto when 8*N_det > 64 GB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the energy / RDM / theta-gradient timings")
     return ap.parse_args()
 
 
@@ -217,6 +218,96 @@ def run_reference(args) -> None:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
+    """The rest of north_star's "energy + gradient" at the same CAS, timed with CUDA events on the resident state:
+    sigma build H|psi> (ups_wavefunction.py:770-784), 1-/2-RDM (ups_wavefunction.py:409-476) and the reverse
+    theta-gradient sweep (ups_wavefunction.py:1114-1138: per operator g_k = 2<bra|T_k|ket>, then both vectors <- U_k).
+    Algorithmic bytes of the sweep: 32 B x touched amplitudes per operator (read + write of bra and ket)."""
+    import torch
+
+    from slowquant_b200 import _lib
+    from slowquant_b200 import operator_state_algebra as osa
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    lib = _lib.load()
+    n = info.num_active_orbs
+    P = lay.n_params
+    rng = np.random.default_rng(2024)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    H = hamiltonian_0i_0a(h, g, 0, n)
+    peak, _ = measured_peak()
+
+    def timed(fn, reps=2):
+        best, res = None, None
+        for _ in range(reps + 1):  # first pass is the warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            res = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best, res
+
+    ms_sigma, sig = timed(lambda: osa.propagate_state([H], state, info))
+    energy = float(torch.dot(state, sig))
+    ms_rdm, (d1, d2) = timed(lambda: osa.reduced_density_matrices(state, state, info))
+    e_rdm = float(np.sum(h * d1) + 0.5 * np.sum(g * d2))
+    handle = osa.compile_layout(info, lay)
+    # the sweep runs one launch per brick [sa_single, double, sa_single] on an orbital pair (p, p+1); a brick touches the
+    # amplitudes whose alpha or beta string has exactly one of the two orbitals occupied (SURVEY 8d: 78.2 % at n = 16)
+    from math import comb
+
+    na, nb = info.num_active_elec_alpha, info.num_active_elec_beta
+    inert_a = 1.0 - 2.0 * comb(n - 2, na - 1) / comb(n, na)
+    inert_b = 1.0 - 2.0 * comb(n - 2, nb - 1) / comb(n, nb)
+    touched = (P // 3) * (1.0 - inert_a * inert_b) * info.num_det
+    bra = osa.construct_ups_state(sig, info, thetas, lay, dagger=True)   # U^d H|psi>
+    ket = torch.zeros_like(state)
+    ket[0] = 1.0
+    g_out = np.zeros(P)
+    import ctypes as C
+
+    PD = C.POINTER(C.c_double)
+    th = np.ascontiguousarray(thetas, dtype=np.float64)
+
+    def sweep():
+        b, k = bra.clone(), ket.clone()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        _lib.check(lib.sq_ups_grad_sweep(info._handle, handle, th.ctypes.data_as(PD), 0, P, C.c_void_p(b.data_ptr()), C.c_void_p(k.data_ptr()),
+                                         g_out.ctypes.data_as(PD), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    sweep()
+    ms_sweep = min(sweep() for _ in range(2))
+    sweep_gbs = 32.0 * touched / (ms_sweep * 1e-3) / 1e9
+    return {
+        "sigma_ms": ms_sigma,
+        "rdm12_ms": ms_rdm,
+        "energy_sigma": energy,
+        "energy_rdm": e_rdm,
+        "energy_diff": energy - e_rdm,
+        "trace_rdm1": float(np.trace(d1)),
+        "gradient_sweep_ms": ms_sweep,
+        "gradient_sweep_ms_per_operator": ms_sweep / P,
+        "gradient_sweep_ms_per_brick": ms_sweep / (P // 3),
+        "gradient_sweep_algorithmic_GBps": sweep_gbs,
+        "gradient_sweep_frac_of_measured_hbm_peak": sweep_gbs / peak,
+        "gradient_norm": float(np.linalg.norm(g_out)),
+        "note": "synthetic symmetric integrals (default_rng(2024)); sigma/RDM are DGEMM-bound (D-panel + cuBLAS fp64), the sweep is HBM-bound",
+    }
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -316,7 +407,43 @@ def run_ours(args) -> None:
             "steps": n_e2e,
             "norm_check": float(np.linalg.norm(out)),
         }
+        # the batch call of the same API (construct_ups_state_SA on [S, N_det] host states: RotoSolve shifts, state-averaged
+        # ensembles): copies of neighbouring states overlap the kernels on three streams
+        try:
+            from slowquant_b200.operator_state_algebra import construct_ups_state_SA
+
+            S = 4
+            batch_in = torch.zeros((S, info.num_det), dtype=torch.float64).pin_memory()
+            batch_in[:, 0] = 1.0
+            outb = construct_ups_state_SA(batch_in.numpy(), info, thetas, lay)  # warm-up: streams, and the page-locked result block the timed call reuses
+            del outb
+            barrier()
+            t0 = time.perf_counter()
+            outb = construct_ups_state_SA(batch_in.numpy(), info, thetas, lay)
+            torch.cuda.synchronize()
+            dtb = time.perf_counter() - t0
+            t3 = torch.tensor([dtb], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            e2e["batched"] = {
+                "value": world * L * S / float(t3.item()),
+                "unit": UNIT,
+                "states_per_call": S,
+                "api": "construct_ups_state_SA(host_states[S, N_det]) -- H2D of state k+1 and D2H of state k-1 overlap the kernels of state k",
+                "norm_check": float(np.linalg.norm(outb[S - 1])),
+                "max_diff_vs_single_call": float(np.max(np.abs(outb[S - 1] - out))),
+            }
+            del outb, batch_in
+        except Exception as exc:  # an extra, never a gate
+            e2e["batched"] = {"error": repr(exc)}
         del out, host_in, np_in
+
+    extras = None
+    if not args.no_extras and world == 1:
+        try:
+            extras = energy_gradient_extras(info, lay, thetas, state, dev)
+        except Exception as exc:  # extras never gate the headline line
+            extras = {"error": repr(exc)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -382,6 +509,7 @@ def run_ours(args) -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
             "state_norm": norm,
+            "energy_gradient": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

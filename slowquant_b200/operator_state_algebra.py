@@ -387,11 +387,64 @@ def expectation_value_SA(bra, operators, ket, ci_info, thetas=None, wf_struct=No
     return val / len(bra)
 
 
+def _pipelined_host_batch(states, ci_info: CI_Info, run_inplace) -> np.ndarray:
+    """``out[k] = run_inplace(states[k])`` for a batch of HOST vectors ``[S, N_det]``.
+
+    Three device buffers rotate through three streams: while the kernels of state k run on the caller's stream, the
+    H2D copy of state k+1 and the D2H copy of state k-1 are in flight (PCIe is full duplex), so a batch costs
+    max(copy, compute) per state instead of their sum.  Copies overlap only for page-locked input; pageable input is
+    staged by the driver and merely loses the overlap.  The result is a fresh page-locked array.
+    """
+    dev = _device_of(ci_info)
+    src = torch.from_numpy(np.ascontiguousarray(states, dtype=np.float64))
+    S, N = src.shape
+    if N != ci_info.local_len:
+        raise ValueError(f"states have {N} elements, the CI space holds {ci_info.local_len}")
+    out = torch.empty((S, N), dtype=torch.float64, pin_memory=True)
+    nb = min(S, 3)
+    bufs = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(nb)]
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(nb)]
+    ev_done = [torch.cuda.Event() for _ in range(nb)]
+    ev_out = [torch.cuda.Event() for _ in range(nb)]
+    s_in.wait_stream(main)
+    for k in range(S):
+        b = k % nb
+        with torch.cuda.stream(s_in):
+            if k >= nb:
+                s_in.wait_event(ev_out[b])      # the buffer is free once its previous result has left
+            bufs[b].copy_(src[k], non_blocking=True)
+            ev_in[b].record(s_in)
+        main.wait_event(ev_in[b])
+        run_inplace(bufs[b])                    # launches on the caller's (current) stream
+        ev_done[b].record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[b])
+            out[k].copy_(bufs[b], non_blocking=True)
+            ev_out[b].record(s_out)
+    s_out.synchronize()
+    for buf in bufs:                            # the side streams used the buffers: tell the caching allocator
+        buf.record_stream(s_in)
+        buf.record_stream(s_out)
+    return out.numpy()
+
+
 def construct_ups_state_SA(state, ci_info, thetas, ups_struct, dagger=False):
+    """Batch twin of construct_ups_state (osa.py:1415-1864); host batches are stream-pipelined."""
+    if not isinstance(state, torch.Tensor) and len(state) > 1:
+        n = len(ups_struct.excitation_operator_type)
+        return _pipelined_host_batch(state, ci_info, lambda t: _ups_apply_inplace(t, ci_info, thetas, ups_struct, 0, n, dagger))
     return _map_states(lambda s: construct_ups_state(s, ci_info, thetas, ups_struct, dagger), state)
 
 
 def propagate_unitary_SA(state, idx, ci_info, thetas, ups_struct):
+    """Batch twin of propagate_unitary (osa.py:2312-2754); host batches are stream-pipelined."""
+    n = len(ups_struct.excitation_operator_type)
+    if not 0 <= idx < n:
+        raise IndexError(f"unitary index {idx} out of range for {n} operators")
+    if not isinstance(state, torch.Tensor) and len(state) > 1:
+        return _pipelined_host_batch(state, ci_info, lambda t: _ups_apply_inplace(t, ci_info, thetas, ups_struct, idx, idx + 1, False))
     return _map_states(lambda s: propagate_unitary(s, idx, ci_info, thetas, ups_struct), state)
 
 

@@ -389,6 +389,9 @@ class WaveFunctionUPS:
 
         The optimiser loop is host control flow; every energy / gradient evaluation runs on the device.
         """
+        if optimizer_name.lower() in ("rotosolve", "cobyla", "cobyqa"):
+            self._run_optimizer_by_name(optimizer_name, orbital_optimization, tol, maxiter)
+            return
         method = {"bfgs": "BFGS", "l-bfgs-b": "L-BFGS-B", "slsqp": "SLSQP"}.get(optimizer_name.lower())
         if method is None:
             raise ValueError(f"Unknown optimizer: {optimizer_name}")
@@ -407,3 +410,58 @@ class WaveFunctionUPS:
             self.kappa = list(res.x[:nk])
         self.thetas = list(res.x[nk:])
         self._energy_elec = None
+
+    def _run_optimizer_by_name(self, optimizer_name: str, orbital_optimization: bool, tol: float, maxiter: int) -> None:
+        """RotoSolve / gradient-free SciPy methods through the Optimizers front end (ups_wavefunction.py:934-1017)."""
+        from functools import partial
+
+        from slowquant_b200.optimizers import Optimizers
+
+        if optimizer_name.lower() == "rotosolve" and orbital_optimization and len(self.kappa) != 0:
+            raise ValueError("Cannot use RotoSolve together with orbital optimization in the one-step solver.")
+        theta_opt = len(self.thetas) > 0 or not orbital_optimization
+        energy = partial(self._calc_energy_optimization, theta_optimization=theta_opt, kappa_optimization=orbital_optimization)
+        gradient = partial(self._calc_gradient_optimization, theta_optimization=theta_opt, kappa_optimization=orbital_optimization)
+        parameters = (self.kappa if orbital_optimization else []) + (self.thetas if theta_opt else [])
+        optimizer = Optimizers(
+            energy, optimizer_name, grad=gradient, maxiter=maxiter, tol=tol, energy_eval_callback=lambda: self.num_energy_evals
+        )
+        self._old_opt_parameters = np.zeros(len(parameters)) + 10**20
+        self._E_opt_old = 0.0
+        extra = None
+        if optimizer_name.lower() == "rotosolve":
+            extra = {
+                "R": self.ups_layout.grad_param_R,
+                "param_names": self.ups_layout.param_names,
+                "f_rotosolve_optimized": self._calc_energy_rotosolve_optimization,
+            }
+        res = optimizer.minimize(parameters, extra_options=extra)
+        nk = len(self.kappa_idx) if orbital_optimization else 0
+        if orbital_optimization:
+            self.kappa = list(res.x[:nk])
+        self.thetas = list(res.x[nk:])
+        self._energy_elec = None
+
+    def _calc_energy_rotosolve_optimization(self, parameters: list[float], theta_diffs: list[float], theta_idx: int) -> list[float]:
+        """Energies at all shifted values of theta[theta_idx] (ups_wavefunction.py:1144-1194), device resident.
+
+        The reference propagates operator by operator through its `_SA` kernels; here the prefix
+        U_{idx-1}..U_0|CSF> is built once, and every shift is one single-unitary launch plus ONE fused
+        sq_ups_apply over the whole remaining operator range (window sweeps), a sigma build and a dot.
+        """
+        th = np.asarray(parameters, dtype=np.float64).copy()
+        n = len(th)
+        prefix = self._csf_dev.clone()
+        if theta_idx > 0:
+            osa._ups_apply_inplace(prefix, self.ci_info, th, self.ups_layout, 0, theta_idx, False)
+        H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
+        energies = []
+        for shift in theta_diffs:
+            th_s = th.copy()
+            th_s[theta_idx] = shift
+            ket = prefix.clone()
+            osa._ups_apply_inplace(ket, self.ci_info, th_s, self.ups_layout, theta_idx, n, False)
+            Hket = osa.propagate_state([H], ket, self.ci_info)
+            energies.append(osa._dot(Hket, ket, self.ci_info))
+        self.num_energy_evals += len(energies)
+        return energies

@@ -80,8 +80,35 @@ def test_naive_lr_refuses_an_unconverged_wave_function(g1):
     from slowquant_b200.linear_response.naive import LinearResponse
 
     WF = _wavefunction(g1, "h2o", {"n_layers": 3})
-    th = WF.thetas
-    th[1] += 0.2
-    WF.thetas = th
+    WF.thetas = [t + 0.1 for t in WF.thetas]
     with pytest.raises(ValueError, match="Large Gradient"):
         LinearResponse(WF, excitations="SD")
+
+
+def test_rotosolve_energies_and_optimisation(g1):
+    """_calc_energy_rotosolve_optimization (ups_wavefunction.py:1144-1194) and a 3-sweep RotoSolve run
+    (optimizers.py:166-270) on H2O/STO-3G tUPS(4,4) against the reference's outputs (golden_rotosolve.npz)."""
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    gr = np.load(os.path.join(ROOT, "tests", "golden", "golden_rotosolve.npz"))
+    g0 = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+    ints = ArrayIntegrals(g0["h2o_h_mo"], g0["h2o_g_mo"], num_elec=10)
+    eye = np.eye(g0["h2o_h_mo"].shape[0])
+    WF = WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 2}, include_active_kappa=True)
+    th = g0["tups44_thetas"].tolist()
+    evals0 = WF.num_energy_evals
+    for idx in (0, 4, len(th) - 1):
+        shifts = gr[f"rs_idx{idx}_shifts"].tolist()
+        e = WF._calc_energy_rotosolve_optimization(th, shifts, idx)
+        assert np.max(np.abs(np.array(e) - gr[f"rs_idx{idx}_energies"])) < 1e-10, idx
+    assert WF.num_energy_evals > evals0
+    WF1 = WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 2})
+    WF1.thetas = gr["opt_start_thetas"].tolist()
+    assert abs(WF1.energy_elec - float(gr["opt_start_energy"])) < 1e-10
+    WF1.run_wf_optimization_1step("rotosolve", False, maxiter=3)
+    # thetas the energy does not depend on are fixed by rounding noise (see make_golden_rotosolve.py): compare the energy
+    assert abs(WF1.energy_elec - float(gr["opt_energy"])) < 1e-8
+    assert WF1.energy_elec < float(gr["opt_start_energy"]) - 1e-3
+    with pytest.raises(ValueError):
+        WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 1}, include_active_kappa=True).run_wf_optimization_1step("rotosolve", True)

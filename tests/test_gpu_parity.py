@@ -637,3 +637,42 @@ def test_window_gradient_sweep(sq, n, na, nb, L, qnp):
     finally:
         sq.lib.check(lib.sq_set_option(b"win", b"1"))
         sq.lib.check(lib.sq_set_option(b"wingrad", b"0"))
+
+
+def test_state_averaged_twins(sq):
+    """`_SA` batch functions (osa.py:633-781, 827-867, 1415-1864, 2312-2976) on [n_states, N_det] batches: host batches
+    take the stream-pipelined path, device batches the per-state path; both against the oracle state by state."""
+    n, na, nb = 8, 4, 4
+    info = sq.ci.get_indexing(0, n, 0, na, nb)
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    lay = sq.UpsStructure()
+    lay.create_tiled(n, {"n_layers": 2, "do_tups": True})
+    rng = np.random.default_rng(99)
+    th = rng.uniform(-np.pi, np.pi, lay.n_params)
+    S = 5  # more states than pipeline buffers
+    states = rng.normal(size=(S, info.num_det))
+    states /= np.linalg.norm(states, axis=1)[:, None]
+    keep = states.copy()
+    ref = np.array([orc.construct_ups_state(s, sp, th, lay.excitation_operator_type, lay.excitation_indices) for s in states])
+    out = sq.osa.construct_ups_state_SA(states, info, th.tolist(), lay)
+    assert out.shape == ref.shape and np.max(np.abs(out - ref)) < TOL
+    assert np.array_equal(states, keep), "inputs must not be modified"
+    out_dev = sq.osa.construct_ups_state_SA(torch.from_numpy(states).cuda(), info, th.tolist(), lay)
+    assert isinstance(out_dev, torch.Tensor) and np.max(np.abs(out_dev.cpu().numpy() - ref)) < TOL
+    back = sq.osa.construct_ups_state_SA(out, info, th.tolist(), lay, dagger=True)
+    assert np.max(np.abs(back - states)) < TOL
+    one = sq.osa.construct_ups_state_SA(states[:1], info, th.tolist(), lay)
+    assert one.shape == (1, info.num_det) and np.max(np.abs(one[0] - ref[0])) < TOL
+    k = 4
+    ref_u = np.array([orc.propagate_unitary(s, k, sp, th, lay.excitation_operator_type, lay.excitation_indices) for s in states])
+    assert np.max(np.abs(sq.osa.propagate_unitary_SA(states, k, info, th.tolist(), lay) - ref_u)) < TOL
+    ref_g = np.array([orc.get_grad_action(s, k, sp, lay.excitation_operator_type, lay.excitation_indices) for s in states])
+    assert np.max(np.abs(sq.osa.get_grad_action_SA(states, k, info, lay) - ref_g)) < TOL
+    from slowquant_b200 import operators as mops
+
+    op = mops.Epq(1, 2) * mops.Epq(5, 3) + 0.3 * mops.Epq(0, 6)
+    ref_p = np.array([orc.propagate_state([dict(op.operators)], s, sp) for s in states])
+    got_p = sq.osa.propagate_state_SA([op], states, info)
+    assert np.max(np.abs(got_p - ref_p)) < TOL
+    ev = sq.osa.expectation_value_SA(states, [op], states, info)
+    assert abs(ev - float(np.mean([s @ r for s, r in zip(states, ref_p)]))) < 1e-12
