@@ -61,3 +61,72 @@ def panel_from_rows(op: FermionicOperator, rows: torch.Tensor, ci_info: CI_Info)
 def gram(P: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
     """G[i, j] = <P_i|Q_j>  (one DGEMM over the determinant index)."""
     return P @ Q.T
+
+
+def apply_unitary_rows(rows: torch.Tensor, index_info, dagger: bool) -> None:
+    """rows[k] <- U rows[k] (or U^dagger) in place for every vector of a panel: the "U" / "Ud" elements of the
+    reference's operator lists (osa.py:525-552) with the ansatz of ``index_info = (ci_info, thetas, layout)``."""
+    ci_info, thetas, layout = index_info
+    from slowquant_b200.util import UccStructure
+
+    if rows.dim() == 1:
+        rows = rows.unsqueeze(0)
+    if isinstance(layout, UccStructure):
+        for k in range(rows.shape[0]):
+            rows[k].copy_(osa.construct_ucc_state(rows[k], ci_info, thetas, layout, dagger=dagger))
+        return
+    n = len(layout.excitation_operator_type)
+    for k in range(rows.shape[0]):
+        osa._ups_apply_inplace(rows[k], ci_info, thetas, layout, 0, n, dagger)
+
+
+def orbital_blocks(lr) -> None:
+    """q-q blocks of A, B, Sigma from the RDMs and the orbital-gradient guard, shared by every LR parametrisation
+    (naive.py:42-54, 93-123 and the identical code in projected.py / statetransfer.py)."""
+    import numpy as np
+
+    from slowquant_b200.density_matrix import (
+        get_orbital_gradient_response,
+        get_orbital_response_hessian_block,
+        get_orbital_response_metric_sigma,
+    )
+
+    wf = lr.wf
+    nq = len(lr.q_ops)
+    if nq == 0:
+        return
+    nI, nA = wf.num_inactive_orbs, wf.num_active_orbs
+    k, kd = wf.kappa_no_activeactive_idx, wf.kappa_no_activeactive_idx_dagger
+    grad = get_orbital_gradient_response(wf.h_mo, wf.g_mo, k, nI, nA, wf.rdm1, wf.rdm2)
+    print("idx, max(abs(grad orb)):", np.argmax(np.abs(grad)), np.max(np.abs(grad)))
+    if np.max(np.abs(grad)) > 10**-3:
+        raise ValueError("Large Gradient detected in q of ", np.max(np.abs(grad)))
+    lr.A[:nq, :nq] = get_orbital_response_hessian_block(wf.h_mo, wf.g_mo, kd, k, nI, nA, wf.rdm1, wf.rdm2)
+    lr.B[:nq, :nq] = get_orbital_response_hessian_block(wf.h_mo, wf.g_mo, kd, kd, nI, nA, wf.rdm1, wf.rdm2)
+    lr.Sigma[:nq, :nq] = get_orbital_response_metric_sigma(k, nI, nA, wf.rdm1)
+
+
+def check_active_gradient(grad) -> None:
+    import numpy as np
+
+    if len(grad) != 0:
+        print("idx, max(abs(grad active)):", np.argmax(np.abs(grad)), np.max(np.abs(grad)))
+        if np.max(np.abs(grad)) > 10**-3:
+            raise ValueError("Large Gradient detected in G of ", np.max(np.abs(grad)))
+
+
+def mirror_lower(M: torch.Tensor):
+    """The reference evaluates val(i, j) for i >= j only and stores it in [i, j] and [j, i]."""
+    return (torch.tril(M) + torch.tril(M, -1).T).cpu().numpy()
+
+
+def orbital_property_part(lr, mu, state_number: int, number_excitations: int) -> float:
+    from slowquant_b200.density_matrix import get_orbital_response_property_gradient
+
+    if len(lr.q_ops) == 0:
+        return 0.0
+    wf = lr.wf
+    return get_orbital_response_property_gradient(
+        mu, wf.kappa_no_activeactive_idx, wf.num_inactive_orbs, wf.num_active_orbs, wf.rdm1, lr.normed_response_vectors,
+        state_number, number_excitations,
+    )

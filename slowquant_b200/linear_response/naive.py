@@ -17,12 +17,6 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from slowquant_b200.density_matrix import (
-    get_orbital_gradient_response,
-    get_orbital_response_hessian_block,
-    get_orbital_response_metric_sigma,
-    get_orbital_response_property_gradient,
-)
 from slowquant_b200.integral_manager import one_electron_integral_transform
 from slowquant_b200.linear_response import _panels as pn
 from slowquant_b200.linear_response._symbolic import SectorSplit
@@ -30,12 +24,6 @@ from slowquant_b200.linear_response.lr_baseclass import LinearResponseBaseClass
 from slowquant_b200.operators import one_elec_op_0i_0a
 from slowquant_b200.ucc_wavefunction import WaveFunctionUCC
 from slowquant_b200.ups_wavefunction import WaveFunctionUPS
-
-
-def _mirror_lower(M: torch.Tensor) -> np.ndarray:
-    """The reference evaluates val(i, j) for i >= j only and stores it in [i, j] and [j, i] (naive.py:239, 272)."""
-    L = torch.tril(M)
-    return (L + torch.tril(M, -1).T).cpu().numpy()
 
 
 class LinearResponse(LinearResponseBaseClass):
@@ -47,11 +35,7 @@ class LinearResponse(LinearResponseBaseClass):
         nI, nA = wf.num_inactive_orbs, wf.num_active_orbs
         print("Gs", nG)
         print("qs", nq)
-        if nq != 0:
-            grad = get_orbital_gradient_response(wf.h_mo, wf.g_mo, wf.kappa_no_activeactive_idx, nI, nA, wf.rdm1, wf.rdm2)
-            print("idx, max(abs(grad orb)):", np.argmax(np.abs(grad)), np.max(np.abs(grad)))
-            if np.max(np.abs(grad)) > 10**-3:
-                raise ValueError("Large Gradient detected in q of ", np.max(np.abs(grad)))
+        pn.orbital_blocks(self)                                         # guard + q-q blocks (naive.py:42-54, 93-123)
         # ---- panels (device resident) ----
         psi = pn.state_on_device(wf.ci_coeffs, ci_info)
         H0 = pn.apply(self.H_0i_0a, psi, ci_info)                       # H|0>
@@ -63,16 +47,7 @@ class LinearResponse(LinearResponseBaseClass):
         if nG != 0:
             hg = (Gk @ H0).cpu().numpy()
             hgd = (Gdk @ H0).cpu().numpy()
-            grad = np.concatenate([hg - hgd, hg - hgd])
-            print("idx, max(abs(grad active)):", np.argmax(np.abs(grad)), np.max(np.abs(grad)))
-            if np.max(np.abs(grad)) > 10**-3:
-                raise ValueError("Large Gradient detected in G of ", np.max(np.abs(grad)))
-        # ---- q-q blocks (naive.py:93-123) ----
-        if nq != 0:
-            k, kd = wf.kappa_no_activeactive_idx, wf.kappa_no_activeactive_idx_dagger
-            self.A[:nq, :nq] = get_orbital_response_hessian_block(wf.h_mo, wf.g_mo, kd, k, nI, nA, wf.rdm1, wf.rdm2)
-            self.B[:nq, :nq] = get_orbital_response_hessian_block(wf.h_mo, wf.g_mo, kd, kd, nI, nA, wf.rdm1, wf.rdm2)
-            self.Sigma[:nq, :nq] = get_orbital_response_metric_sigma(k, nI, nA, wf.rdm1)
+            pn.check_active_gradient(np.concatenate([hg - hgd, hg - hgd]))
         # ---- q-G blocks (naive.py:124-194) ----
         if nq != 0 and nG != 0:
             H1 = SectorSplit(self.H_1i_1a, nI, nA)   # only the strings of H that can survive the fold are multiplied
@@ -109,9 +84,9 @@ class LinearResponse(LinearResponseBaseClass):
             A_GG = g(Gk, HG) + g(Gdk, HGd) - 0.5 * (g(Gk, GH) + g(Gdk, GdH) + g(GdH, Gdk) + g(GH, Gk))
             B_GG = g(Gk, HGd) - g(Gk, GdH) - g(Gdk, GH) + g(Gdk, HG)
             S_GG = g(Gk, Gk) - g(Gdk, Gdk)
-            self.A[nq:, nq:] = _mirror_lower(A_GG)
-            self.B[nq:, nq:] = _mirror_lower(B_GG)
-            self.Sigma[nq:, nq:] = _mirror_lower(S_GG)
+            self.A[nq:, nq:] = pn.mirror_lower(A_GG)
+            self.B[nq:, nq:] = pn.mirror_lower(B_GG)
+            self.Sigma[nq:, nq:] = pn.mirror_lower(S_GG)
 
     def get_transition_dipole(self) -> np.ndarray:
         """<0|[mu, O_n]|0> for every excited state (naive.py:306-429); the active part for all states at once:
@@ -134,10 +109,6 @@ class LinearResponse(LinearResponseBaseClass):
             mud_ket = pn.apply(mu_op.dagger, self._psi, ci_info)
             active = (transfer @ mud_ket - transfer_d @ mu_ket).cpu().numpy()  # <0|mu T|0> - <0|T mu|0>
             for state_number in range(number_excitations):
-                q_part = 0.0
-                if len(self.q_ops) != 0:
-                    q_part = get_orbital_response_property_gradient(
-                        mu, wf.kappa_no_activeactive_idx, nI, nA, wf.rdm1, self.normed_response_vectors, state_number, number_excitations
-                    )
+                q_part = pn.orbital_property_part(self, mu, state_number, number_excitations)
                 transition_dipoles[state_number, axis] = q_part + active[state_number]
         return transition_dipoles

@@ -112,3 +112,23 @@ def test_rotosolve_energies_and_optimisation(g1):
     assert WF1.energy_elec < float(gr["opt_start_energy"]) - 1e-3
     with pytest.raises(ValueError):
         WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 1}, include_active_kappa=True).run_wf_optimization_1step("rotosolve", True)
+
+
+@pytest.mark.parametrize("variant,tag", [("projected", "proj"), ("statetransfer", "st")])
+@pytest.mark.parametrize("name,options", [("lih", {"n_layers": 1, "skip_last_singles": True}), ("h2o", {"n_layers": 3})])
+def test_projected_and_statetransfer_linear_response(g1, name, options, variant, tag):
+    """linear_response/projected.py and statetransfer.py ("U" / "Ud" operator lists run through the fused unitary
+    kernels) against the reference's matrices at the same fixed (theta, c_mo) (golden_lr_variants.npz)."""
+    import importlib
+
+    gv = np.load(os.path.join(ROOT, "tests", "golden", "golden_lr_variants.npz"))
+    mod = importlib.import_module("slowquant_b200.linear_response." + variant)
+    WF = _wavefunction(g1, name, options)
+    LR = mod.LinearResponse(WF, excitations="SD")
+    pre = f"{name}_{tag}_"
+    for key in ("A", "B", "Sigma", "Delta"):
+        assert np.max(np.abs(getattr(LR, key) - gv[pre + key])) < 1e-10, key
+    LR.calc_excitation_energies()
+    assert np.max(np.abs(LR.excitation_energies - gv[pre + "excitation_energies"])) < 1e-8
+    assert np.max(np.abs(LR.get_excited_state_norm() - gv[pre + "norms"])) < 1e-8
+    assert np.max(np.abs(LR.get_oscillator_strength() - gv[pre + "oscillator_strengths"])) < 1e-8
