@@ -160,7 +160,143 @@ def get_indexing(
     )
 
 
-def get_indexing_extended(*args, **kwargs):
-    """Extended (CAS + singles/doubles) spaces of ci_spaces.py:119-259 are not a product of string lists;
-    they are outside the round-1 scope."""
-    raise NotImplementedError("extended CI spaces are not available in the B200 engine yet")
+# ---- extended spaces (ci_spaces.py:119-341) --------------------------------------------------------------------
+def generate_singles(num_inactive_orbs: int, num_virtual_orbs: int):
+    """(inactive occupation, virtual occupation) after at most one electron left the inactive orbitals and at most one
+    entered the virtual orbitals, in the order of ci_spaces.py:262-294 (hole index outer, particle index inner, "no
+    change" last in both loops)."""
+    for i in range(num_inactive_orbs + 1):
+        inactive = [1] * num_inactive_orbs
+        if i != num_inactive_orbs:
+            inactive[i] = 0
+        for j in range(num_virtual_orbs + 1):
+            virtual = [0] * num_virtual_orbs
+            if j != num_virtual_orbs:
+                virtual[j] = 1
+            yield inactive, virtual
+
+
+def generate_doubles(num_inactive_orbs: int, num_virtual_orbs: int):
+    """Same with up to two holes and up to two particles (ci_spaces.py:297-341)."""
+    nI, nV = num_inactive_orbs, num_virtual_orbs
+    for i in range(nI + 1):
+        for i2 in range(min(i + 1, nI), nI + 1):
+            inactive = [1] * nI
+            for h in (i, i2):
+                if h != nI:
+                    inactive[h] = 0
+            for j in range(nV + 1):
+                for j2 in range(min(j + 1, nV), nV + 1):
+                    virtual = [0] * nV
+                    for q in (j, j2):
+                        if q != nV:
+                            virtual[q] = 1
+                    yield inactive, virtual
+
+
+def _sector_strings(inactive: list[int], virtual: list[int], num_active_orbs: int, n_active_elec: int, shift: int) -> np.ndarray:
+    """All strings (inactive pattern | any active string with n_active_elec electrons | virtual pattern) as int64 masks
+    already spread to the interleaved determinant layout (orbital 0 = most significant bit pair; shift 1 = alpha, 0 = beta),
+    active part in itertools.combinations order (ci_spaces.py:56-73)."""
+    import itertools
+
+    N = len(inactive) + num_active_orbs + len(virtual)
+    fixed = 0
+    for p, occ in enumerate(inactive):
+        if occ:
+            fixed |= 1 << (2 * (N - 1 - p) + shift)
+    for v, occ in enumerate(virtual):
+        if occ:
+            fixed |= 1 << (2 * (N - 1 - (len(inactive) + num_active_orbs + v)) + shift)
+    out = []
+    if n_active_elec < 0:  # nothing to iterate (ci_spaces.py:66-68)
+        return np.zeros(0, dtype=np.int64)
+    for comb in itertools.combinations(range(num_active_orbs), n_active_elec):
+        m = fixed
+        for a in comb:
+            m |= 1 << (2 * (N - 1 - (len(inactive) + a)) + shift)
+        out.append(m)
+    return np.asarray(out, dtype=np.int64)
+
+
+def extended_idx2det(
+    num_inactive_orbs: int, num_active_orbs: int, num_virtual_orbs: int, num_active_elec_alpha: int, num_active_elec_beta: int, order: int
+) -> np.ndarray:
+    """Determinant list of the extended space in the reference's order (ci_spaces.py:142-247): the CAS block, then alpha
+    sectors x reference beta, reference alpha x beta sectors and (order 2) single alpha x single beta sectors; alpha outer,
+    beta inner inside a block; determinants already present are skipped."""
+    if order > 2:
+        raise ValueError("Excitation order needs to be <= 2")
+    nI, nA, nV = num_inactive_orbs, num_active_orbs, num_virtual_orbs
+    singles = list(generate_singles(nI, nV))
+    doubles = list(generate_doubles(nI, nV)) if order == 2 else []
+
+    def strings(sector, n_elec, shift):
+        inactive, virtual = sector
+        return _sector_strings(inactive, virtual, nA, int(n_elec - sum(virtual) + nI - sum(inactive)), shift)
+
+    reference = ([1] * nI, [0] * nV)
+    ref_a = strings(reference, num_active_elec_alpha, 1)
+    ref_b = strings(reference, num_active_elec_beta, 0)
+    blocks = [(ref_a, ref_b)]
+    for sector in singles + doubles:
+        blocks.append((strings(sector, num_active_elec_alpha, 1), ref_b))
+    for sector in singles + doubles:
+        blocks.append((ref_a, strings(sector, num_active_elec_beta, 0)))
+    if order == 2:
+        for sa in singles:
+            a_str = strings(sa, num_active_elec_alpha, 1)
+            for sb in singles:
+                blocks.append((a_str, strings(sb, num_active_elec_beta, 0)))
+    dets = np.concatenate([(a[:, None] | b[None, :]).ravel() for a, b in blocks if a.size and b.size])
+    _, first = np.unique(dets, return_index=True)
+    return dets[np.sort(first)]
+
+
+class ExtendedCI_Info:
+    """CAS + singles(/doubles) into the inactive and virtual orbitals (ci_spaces.py:119-259), attribute for attribute.
+
+    The determinant list is not a product of string lists, but it is a union of (alpha sector) x (beta sector) blocks of the
+    product space of ALL orbitals with ``nI + n_alpha`` / ``nI + n_beta`` electrons.  The engine therefore keeps a private
+    *parent* product space (every kernel works there unchanged) and this object holds the embedding: vectors of the
+    extended space are scattered into parent vectors, operated on, and gathered back, which is exactly the reference's
+    "skip what leaves the space" (``do_unsafe=True``) -- and a KeyError otherwise, when anything landed outside.
+    Like the reference's version (it scans a Python list per determinant, ci_spaces.py:173), this is for small spaces.
+    """
+
+    is_extended = True
+
+    def __init__(self, nI: int, nA: int, nV: int, n_alpha: int, n_beta: int, order: int, device: int | None = None) -> None:
+        N = nI + nA + nV
+        self.num_inactive_orbs = 0
+        self.num_active_orbs = N
+        self.num_virtual_orbs = 0
+        self.num_active_elec_alpha = n_alpha + nI
+        self.num_active_elec_beta = n_beta + nI
+        self.space_extension_offset = nI
+        self.idx2det = extended_idx2det(nI, nA, nV, n_alpha, n_beta, order)
+        self.num_det = int(self.idx2det.size)
+        self.local_len = self.num_det
+        self.det2idx = {int(d): i for i, d in enumerate(self.idx2det)}
+        self.parent = CI_Info(0, N, 0, n_alpha + nI, n_beta + nI, device=device)
+        self.parent.space_extension_offset = nI          # ansatz indices are shifted in the parent space too
+        self.device = self.parent.device
+        self.embedding = self.parent.det2idx.lookup_many(self.idx2det)      # parent index of every determinant
+        if np.any(self.embedding < 0):
+            raise RuntimeError("extended determinant outside its parent product space")
+        self._layouts = self.parent._layouts
+
+
+def get_indexing_extended(
+    num_inactive_orbs: int,
+    num_active_orbs: int,
+    num_virtual_orbs: int,
+    num_active_elec_alpha: int,
+    num_active_elec_beta: int,
+    order: int,
+    device: int | None = None,
+) -> ExtendedCI_Info:
+    """Same call as ci_spaces.py:119-126 (+ optional ``device``; -1 = host-only integer tables)."""
+    return ExtendedCI_Info(
+        num_inactive_orbs, num_active_orbs, num_virtual_orbs, num_active_elec_alpha, num_active_elec_beta, order, device
+    )

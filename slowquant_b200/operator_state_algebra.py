@@ -69,6 +69,47 @@ def _ptr(t: torch.Tensor) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+# ---- extended (non-product) spaces: embed into the parent product space, operate, project back ----------------
+def _is_extended(ci_info) -> bool:
+    return getattr(ci_info, "is_extended", False)
+
+
+def _embedding(ci_info) -> tuple[torch.Tensor, torch.Tensor]:
+    """(parent index of every determinant of the extended space, 0/1 mask over the parent vector), device resident."""
+    cached = getattr(ci_info, "_embed_dev", None)
+    if cached is None:
+        dev = _device_of(ci_info)
+        idx = torch.from_numpy(np.ascontiguousarray(ci_info.embedding, dtype=np.int64)).to(dev)
+        mask = torch.zeros(ci_info.parent.local_len, dtype=torch.float64, device=dev)
+        mask[idx] = 1.0
+        cached = ci_info._embed_dev = (idx, mask)
+    return cached
+
+
+def _embed(state, ci_info) -> tuple[torch.Tensor, bool]:
+    """Scatter a vector of the extended space into a zero-filled parent vector."""
+    sub, was_numpy = _to_device(state, ci_info, copy=False)
+    idx, _ = _embedding(ci_info)
+    full = torch.zeros(ci_info.parent.local_len, dtype=torch.float64, device=sub.device)
+    full[idx] = sub
+    return full, was_numpy
+
+
+def _restrict(full: torch.Tensor, ci_info) -> torch.Tensor:
+    return full[_embedding(ci_info)[0]]
+
+
+def _project(full: torch.Tensor, ci_info, do_unsafe: bool) -> torch.Tensor:
+    """Zero whatever left the extended space: the reference's do_unsafe=True skips such determinants string by string
+    (osa.py:131-135), which is this projection; without do_unsafe it raises KeyError."""
+    _, mask = _embedding(ci_info)
+    if not do_unsafe:
+        leak = float(torch.max(torch.abs(full * (1.0 - mask))))
+        if leak > 0.0:
+            raise KeyError("operator maps a determinant outside the CI space (pass do_unsafe=True to skip such terms)")
+    return full * mask
+
+
 def encode_operator(op: FermionicOperator) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Flatten a FermionicOperator into (ops_flat, offsets, coeffs); entry = 2*spin_orbital + dagger."""
     labels = op.operators
@@ -205,6 +246,10 @@ def _ups_apply_inplace(
 # ---- public surface -----------------------------------------------------------------------------
 def construct_ups_state(state, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, dagger: bool = False):
     r"""Apply the unitary product :math:`U_N \dots U_0` (or its adjoint) to `state` (osa.py:963-1412)."""
+    if _is_extended(ci_info):  # the ansatz acts inside every inactive/virtual sector: the space is closed under U
+        full, was_numpy = _embed(state, ci_info)
+        _ups_apply_inplace(full, ci_info.parent, thetas, ups_struct, 0, len(ups_struct.excitation_operator_type), dagger)
+        return _from_device(_restrict(full, ci_info), was_numpy)
     t, was_numpy = _to_device(state, ci_info)
     _ups_apply_inplace(t, ci_info, thetas, ups_struct, 0, len(ups_struct.excitation_operator_type), dagger)
     return _from_device(t, was_numpy)
@@ -215,6 +260,10 @@ def propagate_unitary(state, idx: int, ci_info: CI_Info, thetas: Sequence[float]
     n = len(ups_struct.excitation_operator_type)
     if not 0 <= idx < n:
         raise IndexError(f"unitary index {idx} out of range for {n} operators")
+    if _is_extended(ci_info):
+        full, was_numpy = _embed(state, ci_info)
+        _ups_apply_inplace(full, ci_info.parent, thetas, ups_struct, idx, idx + 1, False)
+        return _from_device(_restrict(full, ci_info), was_numpy)
     t, was_numpy = _to_device(state, ci_info)
     _ups_apply_inplace(t, ci_info, thetas, ups_struct, idx, idx + 1, False)
     return _from_device(t, was_numpy)
@@ -225,6 +274,9 @@ def get_grad_action(state, idx: int, ci_info: CI_Info, ups_struct: UpsStructure)
     n = len(ups_struct.excitation_operator_type)
     if not 0 <= idx < n:
         raise IndexError(f"operator index {idx} out of range for {n} operators")
+    if _is_extended(ci_info):
+        full, was_numpy = _embed(state, ci_info)
+        return _from_device(_restrict(get_grad_action(full, idx, ci_info.parent, ups_struct), ci_info), was_numpy)
     lib = _lib.load()
     lay = compile_layout(ci_info, ups_struct)
     t, was_numpy = _to_device(state, ci_info, copy=False)
@@ -237,6 +289,9 @@ def construct_ucc_state(state, ci_info: CI_Info, thetas: Sequence[float], ucc_st
     """exp(T - T^dagger)|state> for the non-factorised UCC (osa.py:870-896), matrix free."""
     from slowquant_b200.ucc_state import expm_multiply_operator, get_ucc_T
 
+    if _is_extended(ci_info):
+        full, was_numpy = _embed(state, ci_info)
+        return _from_device(_restrict(construct_ucc_state(full, ci_info.parent, thetas, ucc_struct, dagger), ci_info), was_numpy)
     T = get_ucc_T(thetas, ucc_struct, ci_info.space_extension_offset)
     t, was_numpy = _to_device(state, ci_info, copy=False)
     out = expm_multiply_operator(T, t, ci_info, -1.0 if dagger else 1.0)
@@ -259,6 +314,13 @@ def propagate_state(
     """
     if len(operators) == 0:
         return np.copy(state) if not isinstance(state, torch.Tensor) else state.clone()
+    if _is_extended(ci_info):
+        cur, was_numpy = _embed(state, ci_info)
+        for op in operators[::-1]:
+            cur = propagate_state([op], cur, ci_info.parent, thetas, wf_struct, do_folding=do_folding, do_unsafe=do_unsafe)
+            if not isinstance(op, str):
+                cur = _project(cur, ci_info, do_unsafe)
+        return _from_device(_restrict(cur, ci_info), was_numpy)
     cur, was_numpy = _to_device(state, ci_info)
     tmp = None
     for op in operators[::-1]:
@@ -297,6 +359,8 @@ def propagate_state(
 
 
 def _dot(a: torch.Tensor, b: torch.Tensor, ci_info: CI_Info) -> float:
+    if _is_extended(ci_info):
+        return float(torch.dot(a, b))
     lib = _lib.load()
     out = C.c_double(0.0)
     _lib.check(lib.sq_dot(ci_info._handle, _ptr(a), _ptr(b), C.byref(out), _stream()))
@@ -457,6 +521,12 @@ def build_operator_matrix(op: FermionicOperator, ci_info: CI_Info, do_unsafe: bo
     n = ci_info.num_det
     dev = _device_of(ci_info)
     mat = np.zeros((n, n), dtype=np.float64)
+    if _is_extended(ci_info):
+        for j in range(n):
+            unit = torch.zeros(n, dtype=torch.float64, device=dev)
+            unit[j] = 1.0
+            mat[:, j] = propagate_state([op], unit, ci_info, do_folding=False, do_unsafe=do_unsafe).cpu().numpy()
+        return mat
     unit = torch.zeros(n, dtype=torch.float64, device=dev)
     out = torch.empty_like(unit)
     for j in range(n):

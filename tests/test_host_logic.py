@@ -356,3 +356,26 @@ def test_lr_orbital_blocks_match_reference():
             assert abs(dm.get_orbital_response_property_gradient(x, kappa, nI, nA, rdm1, resp, s, n_exc) - gold[pre + "property_gradient"][s]) < 1e-11
         assert np.max(np.abs(dm.get_orbital_response_hessian_block(h, g, kd, kappa, nI, nA, rdm1, rdm2) - gold[pre + "hessian_A"])) < 1e-10
         assert np.max(np.abs(dm.get_orbital_response_hessian_block(h, g, kd, kd, nI, nA, rdm1, rdm2) - gold[pre + "hessian_B"])) < 1e-10
+
+
+def test_extended_space_tables_bit_exact():
+    """get_indexing_extended (ci_spaces.py:119-259): idx2det bit-exact against the reference's lists for seven spaces
+    (orders 1 and 2, empty inactive / virtual spaces, unequal spin counts), det2idx, and the embedding into the parent
+    product space of all orbitals (host-only space, device = -1)."""
+    from slowquant_b200.ci_spaces import extended_idx2det, get_indexing_extended
+
+    g = np.load(f"{ROOT}/tests/golden/golden_extended.npz")
+    for k, sp in enumerate(g["spaces"]):
+        sp = tuple(int(x) for x in sp)
+        ref = g[f"idx2det_{k}"]
+        assert np.array_equal(extended_idx2det(*sp), ref), sp
+        ci = get_indexing_extended(*sp, device=-1)
+        nI, nA, nV, na, nb, _ = sp
+        assert (ci.num_inactive_orbs, ci.num_active_orbs, ci.num_virtual_orbs) == (0, nI + nA + nV, 0)
+        assert (ci.num_active_elec_alpha, ci.num_active_elec_beta) == (na + nI, nb + nI)
+        assert ci.space_extension_offset == nI and ci.num_det == len(ref)
+        assert all(ci.det2idx[int(d)] == i for i, d in enumerate(ref))
+        assert np.array_equal(ci.parent.idx2det[ci.embedding], ref)      # same determinants, parent numbering
+        assert len(set(ci.embedding.tolist())) == len(ref)
+    with pytest.raises(ValueError):
+        extended_idx2det(1, 2, 1, 1, 1, 3)
