@@ -412,7 +412,7 @@ def run_ours(args) -> None:
         try:
             from slowquant_b200.operator_state_algebra import construct_ups_state_SA
 
-            S = 4
+            S = 6
             batch_in = torch.zeros((S, info.num_det), dtype=torch.float64).pin_memory()
             batch_in[:, 0] = 1.0
             outb = construct_ups_state_SA(batch_in.numpy(), info, thetas, lay)  # warm-up: streams, and the page-locked result block the timed call reuses

@@ -114,11 +114,12 @@ def test_rotosolve_energies_and_optimisation(g1):
         WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 1}, include_active_kappa=True).run_wf_optimization_1step("rotosolve", True)
 
 
-@pytest.mark.parametrize("variant,tag", [("projected", "proj"), ("statetransfer", "st")])
+@pytest.mark.parametrize("variant,tag", [("projected", "proj"), ("statetransfer", "st"), ("selfconsistent", "sc")])
 @pytest.mark.parametrize("name,options", [("lih", {"n_layers": 1, "skip_last_singles": True}), ("h2o", {"n_layers": 3})])
-def test_projected_and_statetransfer_linear_response(g1, name, options, variant, tag):
-    """linear_response/projected.py and statetransfer.py ("U" / "Ud" operator lists run through the fused unitary
-    kernels) against the reference's matrices at the same fixed (theta, c_mo) (golden_lr_variants.npz)."""
+def test_projected_statetransfer_selfconsistent_linear_response(g1, name, options, variant, tag):
+    """linear_response/projected.py, statetransfer.py ("U" / "Ud" operator lists run through the fused unitary kernels)
+    and selfconsistent.py (extended CI space, do_unsafe operators) against the reference's matrices at the same fixed
+    (theta, c_mo) (golden_lr_variants.npz)."""
     import importlib
 
     gv = np.load(os.path.join(ROOT, "tests", "golden", "golden_lr_variants.npz"))
