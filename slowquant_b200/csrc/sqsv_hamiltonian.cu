@@ -37,6 +37,19 @@ struct HamWork {
 
 static std::map<const sq_space*, HamWork*> g_work;
 
+// The E_pq table is read uniformly by every thread (same slot at the same time).  Default: a shared-memory copy staged
+// per CTA (four broadcast LDS.128 per slot and thread).  A per-device constant-memory copy (uniform LDC loads) is kept
+// behind sq_set_option("etab", "const") as the measured alternative: at CAS(16,16) it is SLOWER for the sigma build
+// (557 ms against 521 ms; RDMs unchanged), i.e. the LSU pressure of the panel kernels (profiles/
+// r1_energy_kernels_ncu_summary.csv: data pipe 62-77 %) comes from the scattered beta gathers, not from the table reads.
+// One constant table per device at a time: it is rebound when another space runs (after draining the device).
+#define SQ_ETAB_CONST_ORBS 24
+__constant__ ERec c_etab[2 * SQ_ETAB_CONST_ORBS * SQ_ETAB_CONST_ORBS];
+static std::map<int, const sq_space*> g_etab_owner;   // device -> space whose table sits in c_etab
+static int g_etab_const = 0;                          // sq_set_option("etab", "const") selects the constant table
+
+void sq_hamiltonian_set_etab_mode(int use_const) { g_etab_const = use_const ? 1 : 0; }
+
 static void free_work(HamWork* w) {
   if (!w) return;
   if (w->blas) cublasDestroy(w->blas);
@@ -50,6 +63,8 @@ static void free_work(HamWork* w) {
 }
 
 void sq_hamiltonian_release(const sq_space* sp) {
+  for (auto& kv : g_etab_owner)
+    if (kv.second == sp) kv.second = nullptr;
   auto it = g_work.find(sp);
   if (it != g_work.end()) {
     free_work(it->second);
@@ -111,15 +126,24 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
 }
 
 // D[slot][t] = <J_t| E_rs |in>, slot = r*n + s, J_t = determinant j0 + t of the local vector (gather form)
+// table access: CONST = the per-device constant copy (uniform loads), otherwise a shared-memory copy staged per CTA
+template <bool CONST>
+__device__ __forceinline__ const ERec* stage_etab(const ERec* __restrict__ etab, int n2) {
+  if (CONST) return c_etab;
+  extern __shared__ ERec sm[];
+  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256)
+    reinterpret_cast<uint32_t*>(sm)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
+  __syncthreads();
+  return sm;
+}
+
+template <bool CONST>
 __global__ void __launch_bounds__(256)
 build_D_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
                const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA,
                const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
                const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
-  extern __shared__ ERec sm[];
-  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256)
-    reinterpret_cast<uint32_t*>(sm)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
-  __syncthreads();
+  const ERec* sm = stage_etab<CONST>(etab, n2);
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (t >= W) return;
   const int64_t j = j0 + t;
@@ -150,16 +174,14 @@ build_D_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W,
 
 // Symmetrised panel for integrals with g_pqrs = g_pqsr: Dsym[slot(r,s)][t] = <J_t| E_rs + E_sr |in> for r > s and
 // <J_t| E_rr |in> for r = s, slot(r,s) = r (r + 1) / 2 + s  -- n (n + 1) / 2 rows instead of n^2.
+template <bool CONST>
 __global__ void __launch_bounds__(256)
 build_Dsym_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
                   const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ strA,
                   const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
                   const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
-  extern __shared__ ERec sm[];
   const int n2 = n * n;
-  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256)
-    reinterpret_cast<uint32_t*>(sm)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
-  __syncthreads();
+  const ERec* sm = stage_etab<CONST>(etab, n2);
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (t >= W) return;
   const int64_t j = j0 + t;
@@ -191,16 +213,14 @@ build_Dsym_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t
 }
 
 // OUT[E_pq J] += sign * ( F[pq][t] + k[pq] * IN[J] )   for every determinant J of the panel (scatter form)
+template <bool CONST>
 __global__ void __launch_bounds__(256)
 scatter_E_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
                  const double* __restrict__ kmat, const int* __restrict__ frow, int64_t W, int64_t j0, int64_t len,
                  const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA,
                  const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
                  const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
-  extern __shared__ ERec sm[];
-  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256)
-    reinterpret_cast<uint32_t*>(sm)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
-  __syncthreads();
+  const ERec* sm = stage_etab<CONST>(etab, n2);
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t j = j0 + t;
   if (t >= W || j >= len) return;
@@ -242,13 +262,37 @@ static int check_full_space(sq_space* sp, const char* who) {
   return SQ_OK;
 }
 
-static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D, int64_t j0, cudaStream_t st) {
+// Make c_etab hold this space's table (no-op when it already does); *use_const = false -> shared-memory kernels.
+static int bind_etab(sq_space* sp, HamWork* w, cudaStream_t st, bool* use_const) {
+  const int n = sp->n_orb;
+  *use_const = g_etab_const && n <= SQ_ETAB_CONST_ORBS;
+  if (!*use_const) return SQ_OK;
+  const sq_space*& owner = g_etab_owner[sp->device];
+  if (owner != sp) {
+    if (owner) SQ_CUDA(cudaDeviceSynchronize());   // kernels of the previous owner may still be reading the table
+    SQ_CUDA(cudaMemcpyToSymbolAsync(c_etab, w->d_etab, sizeof(ERec) * 2 * (size_t)n * n, 0, cudaMemcpyDeviceToDevice, st));
+    owner = sp;
+  }
+  return SQ_OK;
+}
+
+template <typename K>
+static void allow_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D, int64_t j0, cudaStream_t st, bool use_const) {
   const int n2 = sp->n_orb * sp->n_orb;
-  const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(build_D_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  build_D_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA,
-                                                            sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  const unsigned grid = (unsigned)(w->W / 256);
+  if (use_const) {
+    build_D_kernel<true><<<grid, 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA, sp->d_strB,
+                                               sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  } else {
+    const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+    allow_smem(build_D_kernel<false>, smem);
+    build_D_kernel<false><<<grid, 256, smem, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA, sp->d_strB,
+                                                   sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     sq_set_error("build_D_kernel launch failed: %s", cudaGetErrorString(e));
@@ -322,16 +366,23 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   SQ_CHECK(sq_launch_scale_copy(sp, e_core, in_dev, out_dev, st));
   cublasSetStream(w->blas, st);
   const int64_t len = sp->local_len();
-  const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(scatter_E_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(build_Dsym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  bool use_const = false;
+  SQ_CHECK(bind_etab(sp, w, st, &use_const));
+  const size_t smem = use_const ? 0 : sizeof(ERec) * 2 * (size_t)n2;
+  if (!use_const) {
+    allow_smem(scatter_E_kernel<false>, smem);
+    allow_smem(build_Dsym_kernel<false>, smem);
   }
+  const unsigned grid = (unsigned)(w->W / 256);
   const double one = 1.0, zero = 0.0;
   for (int64_t j0 = 0; j0 < len; j0 += w->W) {
     if (sym) {
-      build_Dsym_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(in_dev, w->d_D[0], w->W, j0, len, w->d_etab, n, sp->d_strA,
-                                                                   sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+      if (use_const)
+        build_Dsym_kernel<true><<<grid, 256, 0, st>>>(in_dev, w->d_D[0], w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                      sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+      else
+        build_Dsym_kernel<false><<<grid, 256, smem, st>>>(in_dev, w->d_D[0], w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                          sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) {
         sq_set_error("build_Dsym_kernel launch failed: %s", cudaGetErrorString(e));
@@ -339,7 +390,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       }
       g_sq_launches.fetch_add(1);
     } else {
-      SQ_CHECK(launch_build_D(sp, w, in_dev, w->d_D[0], j0, st));
+      SQ_CHECK(launch_build_D(sp, w, in_dev, w->d_D[0], j0, st, use_const));
     }
     // F (W x nrow, column major, ld W) = D (W x nrow) * X (nrow x nrow) with X[rs][pq] = Gm[pq][rs] (Gm row-major)
     cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, nrow, nrow, &one, w->d_D[0], (int)w->W,
@@ -349,9 +400,12 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       return SQ_ERR_CUDA;
     }
     g_sq_launches.fetch_add(1);
-    scatter_E_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(in_dev, out_dev, w->d_F, d_k, w->d_frow, w->W, j0, len,
-                                                                w->d_etab, n2, sp->d_strA, sp->d_strB, sp->d_rankA,
-                                                                sp->d_rankB, sp->NB, sp->row_begin);
+    if (use_const)
+      scatter_E_kernel<true><<<grid, 256, 0, st>>>(in_dev, out_dev, w->d_F, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
+                                                   sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+    else
+      scatter_E_kernel<false><<<grid, 256, smem, st>>>(in_dev, out_dev, w->d_F, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
+                                                       sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       sq_set_error("scatter_E_kernel launch failed: %s", cudaGetErrorString(e));
@@ -376,23 +430,31 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
   double* d_g1 = w->d_small + (size_t)n2 * n2;     // [n2]
   SQ_CUDA(cudaMemsetAsync(w->d_small, 0, sizeof(double) * ((size_t)n2 * n2 + 2 * (size_t)n2), st));
   cublasSetStream(w->blas, st);
+  bool use_const = false;
+  SQ_CHECK(bind_etab(sp, w, st, &use_const));
   const int64_t len = sp->local_len();
   const double one = 1.0;
+  const int n_elec = sp->n_alpha + sp->n_beta;
+  // With the 2-RDM accumulator at hand, rdm1 needs no pass of its own: sum_r E_rr = N on this space, so
+  // <bra|E_pq|ket> = (1/N) sum_r <bra|E_pq E_rr|ket>  (saves one GEMV sweep over every panel).
+  const bool rdm1_from_G2 = rdm2_host && n_elec > 0;
   for (int64_t j0 = 0; j0 < len; j0 += w->W) {
     const int64_t wl = (len - j0 < w->W) ? len - j0 : w->W;
-    SQ_CHECK(launch_build_D(sp, w, ket_dev, w->d_D[0], j0, st));
-    // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]
-    cublasStatus_t bs = cublasDgemv(w->blas, CUBLAS_OP_T, (int)wl, n2, &one, w->d_D[0], (int)w->W, bra_dev + j0, 1, &one,
-                                    d_g1, 1);
-    if (bs != CUBLAS_STATUS_SUCCESS) {
-      sq_set_error("sq_rdm12: cublasDgemv failed (%d)", (int)bs);
-      return SQ_ERR_CUDA;
+    SQ_CHECK(launch_build_D(sp, w, ket_dev, w->d_D[0], j0, st, use_const));
+    cublasStatus_t bs = CUBLAS_STATUS_SUCCESS;
+    if (!rdm1_from_G2) {
+      // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]
+      bs = cublasDgemv(w->blas, CUBLAS_OP_T, (int)wl, n2, &one, w->d_D[0], (int)w->W, bra_dev + j0, 1, &one, d_g1, 1);
+      if (bs != CUBLAS_STATUS_SUCCESS) {
+        sq_set_error("sq_rdm12: cublasDgemv failed (%d)", (int)bs);
+        return SQ_ERR_CUDA;
+      }
+      g_sq_launches.fetch_add(1);
     }
-    g_sq_launches.fetch_add(1);
     if (rdm2_host) {
       const double* Dbra = w->d_D[0];
       if (!same) {
-        SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[1], j0, st));
+        SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[1], j0, st, use_const));
         Dbra = w->d_D[1];
       }
       // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]  ==  column-major C[b][a] = Dket^T Dbra
@@ -411,6 +473,14 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
   if (rdm2_host)
     SQ_CUDA(cudaMemcpyAsync(G2h.data(), d_G2, sizeof(double) * (size_t)n2 * n2, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(cudaStreamSynchronize(st));
+  if (rdm1_from_G2) {
+    for (int p = 0; p < n; ++p)
+      for (int q = 0; q < n; ++q) {
+        double v = 0.0;
+        for (int r = 0; r < n; ++r) v += G2h[((size_t)(q * n + p)) * n2 + (r * n + r)];
+        g1h[(size_t)p * n + q] = v / n_elec;
+      }
+  }
   for (int i = 0; i < n2; ++i) rdm1_host[i] = g1h[i];
   if (rdm2_host) {
     // rdm2[p][q][r][s] = <bra|E_pq E_rs|ket> - delta_qr rdm1[p][s];  <..> = G2[(q,p)][(r,s)]
