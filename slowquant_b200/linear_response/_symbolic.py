@@ -59,3 +59,46 @@ class SectorSplit:
             if part is not None:
                 out += piece * part
         return out
+
+    def sandwich(self, left: FermionicOperator, right: FermionicOperator) -> FermionicOperator:
+        """Fold-surviving part of ``left * op * right``."""
+        out = FermionicOperator({})
+        for sl, pl in self._split(left).items():
+            for sr, pr in self._split(right).items():
+                net: dict[int, int] = {}
+                for i, c in sl + sr:
+                    net[i] = net.get(i, 0) + c
+                need = tuple(sorted((i, -c) for i, c in net.items() if c != 0))
+                part = self.parts.get(need)
+                if part is not None:
+                    out += pl * part * pr
+        return out
+
+
+def projected_orbital_blocks(lr, H_2i_2a: FermionicOperator, psi, ci_info) -> None:
+    """q-q blocks of the projected parametrisations (allprojected.py:86-112, projected_statetransfer.py:82-104):
+    A = <0|q_I^d H q_J|0> - E <0|q_I^d q_J|0>, Sigma = <0|q_I^d q_J|0>, B = 0, every expectation value over a product
+    folded onto the active space (only the strings of ``hamiltonian_2i_2a`` that can survive the fold are multiplied)."""
+    import torch
+
+    from slowquant_b200.linear_response import _panels as pn
+
+    wf = lr.wf
+    nq = len(lr.q_ops)
+    if nq == 0:
+        return
+    H2 = SectorSplit(H_2i_2a, wf.num_inactive_orbs, wf.num_active_orbs)
+    E = wf.energy_elec
+    tmp = torch.empty_like(psi)
+    lr.A[:nq, :nq] = 0.0
+    lr.B[:nq, :nq] = 0.0
+    lr.Sigma[:nq, :nq] = 0.0
+    q_dag = [q.dagger for q in lr.q_ops]
+    for j, qJ in enumerate(lr.q_ops):
+        for i in range(j, nq):
+            pn.apply_into(H2.sandwich(q_dag[i], qJ), psi, tmp, ci_info)
+            hqq = float(torch.dot(psi, tmp))
+            pn.apply_into(q_dag[i] * qJ, psi, tmp, ci_info)
+            qq = float(torch.dot(psi, tmp))
+            lr.A[i, j] = lr.A[j, i] = hqq - qq * E
+            lr.Sigma[i, j] = lr.Sigma[j, i] = qq

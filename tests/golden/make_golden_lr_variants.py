@@ -1,5 +1,5 @@
-"""Golden matrices for the projected, state-transfer and self-consistent linear-response parametrisations (reference
-linear_response/projected.py, statetransfer.py, selfconsistent.py), produced by RUNNING THE REFERENCE in the build container at the FIXED
+"""Golden matrices for the projected, state-transfer, self-consistent, all-state-transfer, all-self-consistent, all-projected and projected state-transfer linear-response parametrisations (reference
+linear_response/projected.py, statetransfer.py, selfconsistent.py, allstatetransfer.py, allselfconsistent.py, allprojected.py, projected_statetransfer.py), produced by RUNNING THE REFERENCE in the build container at the FIXED
 converged (theta, c_mo) of golden_config1.npz (no re-optimisation):
 
     python tests/golden/make_golden_lr_variants.py        ->  tests/golden/golden_lr_variants.npz
@@ -22,7 +22,11 @@ sys.path.insert(0, stub)
 sys.path.insert(0, "/root/reference")
 
 import slowquant.SlowQuant as sq  # noqa: E402
+import slowquant.unitary_coupled_cluster.linear_response.allprojected as allprojlr  # noqa: E402
+import slowquant.unitary_coupled_cluster.linear_response.allselfconsistent as allsclr  # noqa: E402
+import slowquant.unitary_coupled_cluster.linear_response.allstatetransfer as allstlr  # noqa: E402
 import slowquant.unitary_coupled_cluster.linear_response.projected as projlr  # noqa: E402
+import slowquant.unitary_coupled_cluster.linear_response.projected_statetransfer as projstlr  # noqa: E402
 import slowquant.unitary_coupled_cluster.linear_response.selfconsistent as sclr  # noqa: E402
 import slowquant.unitary_coupled_cluster.linear_response.statetransfer as stlr  # noqa: E402
 from slowquant.unitary_coupled_cluster.ups_wavefunction import WaveFunctionUPS  # noqa: E402
@@ -53,7 +57,7 @@ for name, (geom, cas, options) in MOLECULES.items():
     WF = WaveFunctionUPS(cas, g1[name + "_c_mo"], SQobj, "tUPS", ansatz_options=dict(options), include_active_kappa=True)
     WF.thetas = g1[name + "_thetas"].tolist()
     assert abs(WF.energy_elec - float(g1[name + "_energy"])) < 1e-9
-    for tag, mod in (("proj", projlr), ("st", stlr), ("sc", sclr)):
+    for tag, mod in (("proj", projlr), ("st", stlr), ("sc", sclr), ("allst", allstlr), ("allsc", allsclr), ("allproj", allprojlr), ("projst", projstlr)):
         LR = mod.LinearResponse(WF, excitations="SD")
         LR.calc_excitation_energies()
         pre = f"{name}_{tag}_"

@@ -114,12 +114,24 @@ def test_rotosolve_energies_and_optimisation(g1):
         WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 1}, include_active_kappa=True).run_wf_optimization_1step("rotosolve", True)
 
 
-@pytest.mark.parametrize("variant,tag", [("projected", "proj"), ("statetransfer", "st"), ("selfconsistent", "sc")])
+@pytest.mark.parametrize(
+    "variant,tag",
+    [
+        ("projected", "proj"),
+        ("statetransfer", "st"),
+        ("selfconsistent", "sc"),
+        ("allstatetransfer", "allst"),
+        ("allselfconsistent", "allsc"),
+        ("allprojected", "allproj"),
+        ("projected_statetransfer", "projst"),
+    ],
+)
 @pytest.mark.parametrize("name,options", [("lih", {"n_layers": 1, "skip_last_singles": True}), ("h2o", {"n_layers": 3})])
-def test_projected_statetransfer_selfconsistent_linear_response(g1, name, options, variant, tag):
+def test_linear_response_parametrisations(g1, name, options, variant, tag):
     """linear_response/projected.py, statetransfer.py ("U" / "Ud" operator lists run through the fused unitary kernels)
-    and selfconsistent.py (extended CI space, do_unsafe operators) against the reference's matrices at the same fixed
-    (theta, c_mo) (golden_lr_variants.npz)."""
+    selfconsistent.py / allstatetransfer.py / allselfconsistent.py (extended CI spaces, do_unsafe operators) and
+    allprojected.py / projected_statetransfer.py (folded q^d H q products) against the reference's matrices at the same
+    fixed (theta, c_mo) (golden_lr_variants.npz)."""
     import importlib
 
     gv = np.load(os.path.join(ROOT, "tests", "golden", "golden_lr_variants.npz"))
@@ -133,3 +145,31 @@ def test_projected_statetransfer_selfconsistent_linear_response(g1, name, option
     assert np.max(np.abs(LR.excitation_energies - gv[pre + "excitation_energies"])) < 1e-8
     assert np.max(np.abs(LR.get_excited_state_norm() - gv[pre + "norms"])) < 1e-8
     assert np.max(np.abs(LR.get_oscillator_strength() - gv[pre + "oscillator_strengths"])) < 1e-8
+
+
+def test_all_statetransfer_reference_literals(g1):
+    """The reference's own all-ST test (tests/test_unitary_product_state.py:64-128: LiH/STO-3G, UCCSD-optimised orbitals,
+    tUPS(2,2) L=1, excitation energies and oscillator strengths +-1e-3), re-run end to end on the CUDA path: orbital
+    optimisation with WaveFunctionUCC, theta optimisation with WaveFunctionUPS, then the all-ST response."""
+    import contextlib
+    import io
+
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.linear_response.allstatetransfer import LinearResponse
+    from slowquant_b200.ucc_wavefunction import WaveFunctionUCC
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    gl = np.load(os.path.join(ROOT, "tests", "golden", "golden_lih167.npz"))
+    ints = ArrayIntegrals(gl["h_ao"], gl["eri_ao"], 4, dipole=tuple(gl["dipole_ao"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        WF = WaveFunctionUCC((2, 2), gl["c_mo_rhf"], ints, "SD")
+        WF.run_wf_optimization_1step("BFGS", True)
+        WF2 = WaveFunctionUPS((2, 2), WF.c_mo, ints, "tUPS", ansatz_options={"n_layers": 1})
+        WF2.run_wf_optimization_1step("BFGS", False)
+        LR = LinearResponse(WF2, excitations="SD")
+        LR.calc_excitation_energies()
+        osc = LR.get_oscillator_strength()
+    solutions = np.array([0.1851181, 0.24715136, 0.24715136, 0.6230648, 0.85960395, 2.07752209, 2.13720198, 2.13720198, 2.55113802])
+    assert np.allclose(LR.excitation_energies, solutions, atol=1e-3)
+    ref_osc = [0.06668878, 0.33360367, 0.33360367, 0.30588158, 0.02569977, 0.06690658, 0.13411942, 0.13411942, 0.04689274]
+    assert np.max(np.abs(osc - np.array(ref_osc))) < 1e-3
