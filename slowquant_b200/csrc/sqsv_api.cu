@@ -600,6 +600,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     g_win_grad = (value && value[0] == '1') ? 1 : 0;
     return SQ_OK;
   }
+  if (strcmp(name, "pipeline") == 0) {   // sigma / RDM panels: "1" (default) overlaps gather, DGEMM and scatter of neighbouring panels
+    sq_hamiltonian_set_pipeline(!(value && value[0] == '0'));
+    return SQ_OK;
+  }
   if (strcmp(name, "etab") == 0) {   // E_pq table of the sigma / RDM panel kernels: "smem" (default) or "const"
     sq_hamiltonian_set_etab_mode(value && strcmp(value, "const") == 0);
     return SQ_OK;

@@ -28,8 +28,11 @@ struct ERec {                 // one spin component of E_pq acting on a determin
 struct HamWork {
   cublasHandle_t blas = nullptr;
   ERec* d_etab = nullptr;     // [n*n][2]  (alpha, beta)
-  double* d_D[2] = {nullptr, nullptr};
-  double* d_F = nullptr;
+  double* d_D[4] = {nullptr, nullptr, nullptr, nullptr};   // ket panels (two in flight), bra panels (two in flight)
+  double* d_F[2] = {nullptr, nullptr};
+  // panel pipeline: gather, GEMM and scatter of neighbouring panels overlap on three internal streams
+  cudaStream_t s_build = nullptr, s_gemm = nullptr, s_scat = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_built[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr}, ev_scat[2] = {nullptr, nullptr};
   int64_t W = 0;
   double* d_small = nullptr;  // n^4 + 2 n^2 doubles: G2 accumulator / integral matrices
   int* d_frow = nullptr;      // [n^2] row of F for every (p,q)
@@ -50,13 +53,25 @@ static int g_etab_const = 0;                          // sq_set_option("etab", "
 
 void sq_hamiltonian_set_etab_mode(int use_const) { g_etab_const = use_const ? 1 : 0; }
 
+// sq_set_option("pipeline", "0"): one panel at a time on the caller's stream (the pre-pipeline behaviour, for A/B runs)
+static int g_panel_pipeline = 1;
+void sq_hamiltonian_set_pipeline(int on) { g_panel_pipeline = on ? 1 : 0; }
+
 static void free_work(HamWork* w) {
   if (!w) return;
   if (w->blas) cublasDestroy(w->blas);
   cudaFree(w->d_etab);
-  cudaFree(w->d_D[0]);
-  cudaFree(w->d_D[1]);
-  cudaFree(w->d_F);
+  for (double* p : w->d_D) cudaFree(p);
+  for (double* p : w->d_F) cudaFree(p);
+  if (w->s_build) cudaStreamDestroy(w->s_build);
+  if (w->s_gemm) cudaStreamDestroy(w->s_gemm);
+  if (w->s_scat) cudaStreamDestroy(w->s_scat);
+  if (w->ev_start) cudaEventDestroy(w->ev_start);
+  for (int b = 0; b < 2; ++b) {
+    if (w->ev_built[b]) cudaEventDestroy(w->ev_built[b]);
+    if (w->ev_gemm[b]) cudaEventDestroy(w->ev_gemm[b]);
+    if (w->ev_scat[b]) cudaEventDestroy(w->ev_scat[b]);
+  }
   cudaFree(w->d_small);
   cudaFree(w->d_frow);
   delete w;
@@ -116,9 +131,24 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
     if (w->W < 256) w->W = 256;
   }
   const size_t pbytes = sizeof(double) * (size_t)n2 * (size_t)w->W;
-  if (!w->d_D[0]) SQ_CUDA(cudaMalloc(&w->d_D[0], pbytes));
-  if (need_second_D && !w->d_D[1]) SQ_CUDA(cudaMalloc(&w->d_D[1], pbytes));
-  if (need_F && !w->d_F) SQ_CUDA(cudaMalloc(&w->d_F, pbytes));
+  const int64_t n_panels = (sp->local_len() + w->W - 1) / w->W;
+  const int depth = (g_panel_pipeline && n_panels > 1) ? 2 : 1;   // panels in flight
+  for (int b = 0; b < depth; ++b) {
+    if (!w->d_D[b]) SQ_CUDA(cudaMalloc(&w->d_D[b], pbytes));
+    if (need_second_D && !w->d_D[2 + b]) SQ_CUDA(cudaMalloc(&w->d_D[2 + b], pbytes));
+    if (need_F && !w->d_F[b]) SQ_CUDA(cudaMalloc(&w->d_F[b], pbytes));
+  }
+  if (!w->s_build) {
+    SQ_CUDA(cudaStreamCreateWithFlags(&w->s_build, cudaStreamNonBlocking));
+    SQ_CUDA(cudaStreamCreateWithFlags(&w->s_gemm, cudaStreamNonBlocking));
+    SQ_CUDA(cudaStreamCreateWithFlags(&w->s_scat, cudaStreamNonBlocking));
+    SQ_CUDA(cudaEventCreateWithFlags(&w->ev_start, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+      SQ_CUDA(cudaEventCreateWithFlags(&w->ev_built[b], cudaEventDisableTiming));
+      SQ_CUDA(cudaEventCreateWithFlags(&w->ev_gemm[b], cudaEventDisableTiming));
+      SQ_CUDA(cudaEventCreateWithFlags(&w->ev_scat[b], cudaEventDisableTiming));
+    }
+  }
   if (!w->d_small) SQ_CUDA(cudaMalloc(&w->d_small, sizeof(double) * ((size_t)n2 * n2 + 2 * (size_t)n2)));
   if (!w->d_frow) SQ_CUDA(cudaMalloc(&w->d_frow, sizeof(int) * (size_t)n2));
   *out = w;
@@ -375,14 +405,31 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   }
   const unsigned grid = (unsigned)(w->W / 256);
   const double one = 1.0, zero = 0.0;
-  for (int64_t j0 = 0; j0 < len; j0 += w->W) {
+  // Three-stage pipeline over the panels: while the DGEMM of panel k runs on the tensor cores, the gather of panel k+1
+  // and the scatter of panel k-1 (both address-bound) run beside it.  Two D and two F panels are in flight; with
+  // pipeline off (or a single panel) all three stages are issued on the caller's stream.
+  const bool piped = g_panel_pipeline && w->d_D[1] && w->d_F[1];
+  cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st, s_scat = piped ? w->s_scat : st;
+  if (piped) {
+    SQ_CUDA(cudaEventRecord(w->ev_start, st));
+    SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_start, 0));
+    SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_start, 0));
+    SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_start, 0));
+  }
+  cublasSetStream(w->blas, s_gemm);
+  int64_t ip = 0;
+  for (int64_t j0 = 0; j0 < len; j0 += w->W, ++ip) {
+    const int b = piped ? (int)(ip & 1) : 0;
+    double* Dp = w->d_D[b];
+    double* Fp = w->d_F[b];
+    if (piped && ip >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // D[b] is free once GEMM k-2 has read it
     if (sym) {
       if (use_const)
-        build_Dsym_kernel<true><<<grid, 256, 0, st>>>(in_dev, w->d_D[0], w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
-                                                      sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+        build_Dsym_kernel<true><<<grid, 256, 0, s_build>>>(in_dev, Dp, w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                           sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
       else
-        build_Dsym_kernel<false><<<grid, 256, smem, st>>>(in_dev, w->d_D[0], w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
-                                                          sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+        build_Dsym_kernel<false><<<grid, 256, smem, s_build>>>(in_dev, Dp, w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                               sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) {
         sq_set_error("build_Dsym_kernel launch failed: %s", cudaGetErrorString(e));
@@ -390,28 +437,44 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       }
       g_sq_launches.fetch_add(1);
     } else {
-      SQ_CHECK(launch_build_D(sp, w, in_dev, w->d_D[0], j0, st, use_const));
+      SQ_CHECK(launch_build_D(sp, w, in_dev, Dp, j0, s_build, use_const));
+    }
+    if (piped) {
+      SQ_CUDA(cudaEventRecord(w->ev_built[b], s_build));
+      SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_built[b], 0));
+      if (ip >= 2) SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_scat[b], 0));             // F[b] is free once scatter k-2 has read it
     }
     // F (W x nrow, column major, ld W) = D (W x nrow) * X (nrow x nrow) with X[rs][pq] = Gm[pq][rs] (Gm row-major)
-    cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, nrow, nrow, &one, w->d_D[0], (int)w->W,
-                                    d_G, nrow, &zero, w->d_F, (int)w->W);
+    cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, nrow, nrow, &one, Dp, (int)w->W,
+                                    d_G, nrow, &zero, Fp, (int)w->W);
     if (bs != CUBLAS_STATUS_SUCCESS) {
       sq_set_error("sq_sigma: cublasDgemm failed (%d)", (int)bs);
       return SQ_ERR_CUDA;
     }
     g_sq_launches.fetch_add(1);
+    if (piped) {
+      SQ_CUDA(cudaEventRecord(w->ev_gemm[b], s_gemm));
+      SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_gemm[b], 0));
+    }
     if (use_const)
-      scatter_E_kernel<true><<<grid, 256, 0, st>>>(in_dev, out_dev, w->d_F, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
-                                                   sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-    else
-      scatter_E_kernel<false><<<grid, 256, smem, st>>>(in_dev, out_dev, w->d_F, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
+      scatter_E_kernel<true><<<grid, 256, 0, s_scat>>>(in_dev, out_dev, Fp, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
                                                        sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+    else
+      scatter_E_kernel<false><<<grid, 256, smem, s_scat>>>(in_dev, out_dev, Fp, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
+                                                           sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       sq_set_error("scatter_E_kernel launch failed: %s", cudaGetErrorString(e));
       return SQ_ERR_CUDA;
     }
     g_sq_launches.fetch_add(1);
+    if (piped) SQ_CUDA(cudaEventRecord(w->ev_scat[b], s_scat));
+  }
+  if (piped) {   // the caller's stream continues after the last scatter (which is after everything else)
+    SQ_CUDA(cudaEventRecord(w->ev_start, s_scat));
+    SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
+    SQ_CUDA(cudaEventRecord(w->ev_start, s_build));
+    SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
   }
   return SQ_OK;
 }
@@ -438,13 +501,35 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
   // With the 2-RDM accumulator at hand, rdm1 needs no pass of its own: sum_r E_rr = N on this space, so
   // <bra|E_pq|ket> = (1/N) sum_r <bra|E_pq E_rr|ket>  (saves one GEMV sweep over every panel).
   const bool rdm1_from_G2 = rdm2_host && n_elec > 0;
-  for (int64_t j0 = 0; j0 < len; j0 += w->W) {
+  // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
+  const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
+  cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
+  if (piped) {
+    SQ_CUDA(cudaEventRecord(w->ev_start, st));
+    SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_start, 0));
+    SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_start, 0));
+  }
+  cublasSetStream(w->blas, s_gemm);
+  int64_t k = 0;
+  for (int64_t j0 = 0; j0 < len; j0 += w->W, ++k) {
     const int64_t wl = (len - j0 < w->W) ? len - j0 : w->W;
-    SQ_CHECK(launch_build_D(sp, w, ket_dev, w->d_D[0], j0, st, use_const));
+    const int b = piped ? (int)(k & 1) : 0;
+    double* Dket = w->d_D[b];
+    if (piped && k >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // panels b are free once GEMM k-2 is done
+    SQ_CHECK(launch_build_D(sp, w, ket_dev, Dket, j0, s_build, use_const));
+    const double* Dbra = Dket;
+    if (rdm2_host && !same) {
+      SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[2 + b], j0, s_build, use_const));
+      Dbra = w->d_D[2 + b];
+    }
+    if (piped) {
+      SQ_CUDA(cudaEventRecord(w->ev_built[b], s_build));
+      SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_built[b], 0));
+    }
     cublasStatus_t bs = CUBLAS_STATUS_SUCCESS;
     if (!rdm1_from_G2) {
       // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]
-      bs = cublasDgemv(w->blas, CUBLAS_OP_T, (int)wl, n2, &one, w->d_D[0], (int)w->W, bra_dev + j0, 1, &one, d_g1, 1);
+      bs = cublasDgemv(w->blas, CUBLAS_OP_T, (int)wl, n2, &one, Dket, (int)w->W, bra_dev + j0, 1, &one, d_g1, 1);
       if (bs != CUBLAS_STATUS_SUCCESS) {
         sq_set_error("sq_rdm12: cublasDgemv failed (%d)", (int)bs);
         return SQ_ERR_CUDA;
@@ -452,14 +537,9 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
       g_sq_launches.fetch_add(1);
     }
     if (rdm2_host) {
-      const double* Dbra = w->d_D[0];
-      if (!same) {
-        SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[1], j0, st, use_const));
-        Dbra = w->d_D[1];
-      }
       // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]  ==  column-major C[b][a] = Dket^T Dbra
       // (cublasDsyrk would do half the flops for bra == ket but runs 3 x slower than DGEMM at n^2 = 256, k = 5e5)
-      bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, n2, n2, (int)w->W, &one, w->d_D[0], (int)w->W, Dbra, (int)w->W,
+      bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, n2, n2, (int)w->W, &one, Dket, (int)w->W, Dbra, (int)w->W,
                        &one, d_G2, n2);
       if (bs != CUBLAS_STATUS_SUCCESS) {
         sq_set_error("sq_rdm12: cublasDgemm failed (%d)", (int)bs);
@@ -467,6 +547,13 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
       }
       g_sq_launches.fetch_add(1);
     }
+    if (piped) SQ_CUDA(cudaEventRecord(w->ev_gemm[b], s_gemm));
+  }
+  if (piped) {
+    SQ_CUDA(cudaEventRecord(w->ev_start, s_gemm));
+    SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
+    SQ_CUDA(cudaEventRecord(w->ev_start, s_build));
+    SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
   }
   std::vector<double> G2h(rdm2_host ? (size_t)n2 * n2 : 0), g1h((size_t)n2);
   SQ_CUDA(cudaMemcpyAsync(g1h.data(), d_g1, sizeof(double) * n2, cudaMemcpyDeviceToHost, st));

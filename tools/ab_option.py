@@ -1,4 +1,5 @@
-"""A/B of the E_pq table placement in the sigma / RDM panel kernels (constant vs shared memory) at a given CAS."""
+"""A/B of a run-time switch of the sigma / RDM path at a given CAS:  python tools/ab_option.py [n] [option] [value_a] [value_b]
+(defaults: 16 pipeline 0 1; e.g. `16 etab smem const`).  Prints timings of both settings (twice) and the result differences."""
 import sys
 import time
 
@@ -12,6 +13,9 @@ from slowquant_b200.ci_spaces import get_indexing  # noqa: E402
 from slowquant_b200.operators import hamiltonian_0i_0a  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+opt = (sys.argv[2] if len(sys.argv) > 2 else "pipeline").encode()
+va = (sys.argv[3] if len(sys.argv) > 3 else "0").encode()
+vb = (sys.argv[4] if len(sys.argv) > 4 else "1").encode()
 ne = n // 2
 info = get_indexing(0, n, 0, ne, ne)
 rng = np.random.default_rng(2024)
@@ -27,8 +31,8 @@ ci = torch.randn(info.num_det, dtype=torch.float64, device=dev)
 ci /= torch.linalg.norm(ci)
 lib = _lib.load()
 res = {}
-for mode in (b"smem", b"const", b"smem", b"const"):
-    lib.sq_set_option(b"etab", mode)
+for mode in (va, vb, va, vb):
+    lib.sq_set_option(opt, mode)
     for label, fn in (("sigma", lambda: osa.propagate_state([H], ci, info)), ("rdm12", lambda: osa.reduced_density_matrices(ci, ci, info))):
         fn()
         torch.cuda.synchronize()
@@ -36,9 +40,9 @@ for mode in (b"smem", b"const", b"smem", b"const"):
         out = fn()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        print(f"CAS({n},{n}) etab={mode.decode():5s} {label:6s} {dt*1e3:9.1f} ms", flush=True)
+        print(f"CAS({n},{n}) {opt.decode()}={mode.decode():5s} {label:6s} {dt*1e3:9.1f} ms", flush=True)
         res[(mode, label)] = out
-s0, s1 = res[(b"smem", "sigma")], res[(b"const", "sigma")]
-print("sigma max|const - smem| =", float(torch.max(torch.abs(s0 - s1))), " |sigma| =", float(torch.linalg.norm(s0)))
-(d1a, d2a), (d1b, d2b) = res[(b"smem", "rdm12")], res[(b"const", "rdm12")]
+s0, s1 = res[(va, "sigma")], res[(vb, "sigma")]
+print("sigma max|b - a| =", float(torch.max(torch.abs(s0 - s1))), " |sigma| =", float(torch.linalg.norm(s0)))
+(d1a, d2a), (d1b, d2b) = res[(va, "rdm12")], res[(vb, "rdm12")]
 print("rdm1 diff", float(np.max(np.abs(d1a - d1b))), "rdm2 diff", float(np.max(np.abs(d2a - d2b))), "tr", float(np.trace(d1b)))
