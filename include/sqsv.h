@@ -105,7 +105,10 @@ int sq_layout_plan_stats(const sq_layout* lay, int first, int last, int64_t* out
  * (default "0": one brick per launch).  name "win": launch planner of sq_ups_apply, value "0" (window sweeps off),
  * "1" (defaults) or "w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks".  name "etab": E_pq table of the sigma / RDM
  * panel kernels in shared memory ("smem", default) or constant memory ("const").  name "pipeline": "1" (default) overlaps
- * the gather, DGEMM and scatter of neighbouring sigma / RDM panels on internal streams, "0" runs one panel at a time */
+ * the gather, DGEMM and scatter of neighbouring sigma / RDM panels on internal streams, "0" runs one panel at a time.  name "rows": "0" (default) determinant-per-thread gather /
+ * scatter kernels, "1" row-per-CTA kernels with the row staged in shared memory (measured slower; "rows_cfg" =
+ * "threads,chunks" sets their geometry).  name "panel": determinants per
+ * panel for spaces that build their panels afterwards ("0": about 1 GiB per panel) */
 int sq_set_option(const char* name, const char* value);
 
 /* ---- unitary product state (construct_ups_state, operator_state_algebra.py:963-1412;

@@ -600,6 +600,20 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     g_win_grad = (value && value[0] == '1') ? 1 : 0;
     return SQ_OK;
   }
+  if (strcmp(name, "panel") == 0) {   // determinants per sigma / RDM panel for spaces created afterwards ("0": default)
+    sq_hamiltonian_set_panel_width(value ? atoll(value) : 0);
+    return SQ_OK;
+  }
+  if (strcmp(name, "rows_cfg") == 0) {   // "threads,chunks" of the row kernels (chunks 0: automatic)
+    int t = 1024, c = 0;
+    if (value) sscanf(value, "%d,%d", &t, &c);
+    sq_hamiltonian_set_rows_cfg(t, c);
+    return SQ_OK;
+  }
+  if (strcmp(name, "rows") == 0) {   // sigma / RDM panel kernels: "0" (default) determinant-per-thread, "1" row-per-CTA (slower, kept as evidence)
+    sq_hamiltonian_set_rows_mode(value && value[0] == '1');
+    return SQ_OK;
+  }
   if (strcmp(name, "pipeline") == 0) {   // sigma / RDM panels: "1" (default) overlaps gather, DGEMM and scatter of neighbouring panels
     sq_hamiltonian_set_pipeline(!(value && value[0] == '0'));
     return SQ_OK;

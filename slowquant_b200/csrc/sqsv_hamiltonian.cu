@@ -28,6 +28,9 @@ struct ERec {                 // one spin component of E_pq acting on a determin
 struct HamWork {
   cublasHandle_t blas = nullptr;
   ERec* d_etab = nullptr;     // [n*n][2]  (alpha, beta)
+  std::vector<ERec> h_etab;
+  uint32_t* d_tabG = nullptr; // [n*n][NB] beta gather table of the row kernels (build_D_rows_kernel)
+  uint32_t* d_tabS = nullptr; // [n*n][NB] beta scatter table (scatter_E_rows_kernel)
   double* d_D[4] = {nullptr, nullptr, nullptr, nullptr};   // ket panels (two in flight), bra panels (two in flight)
   double* d_F[2] = {nullptr, nullptr};
   // panel pipeline: gather, GEMM and scatter of neighbouring panels overlap on three internal streams
@@ -56,11 +59,17 @@ void sq_hamiltonian_set_etab_mode(int use_const) { g_etab_const = use_const ? 1 
 // sq_set_option("pipeline", "0"): one panel at a time on the caller's stream (the pre-pipeline behaviour, for A/B runs)
 static int g_panel_pipeline = 1;
 void sq_hamiltonian_set_pipeline(int on) { g_panel_pipeline = on ? 1 : 0; }
+// sq_set_option("panel", "<determinants>"): panel width of spaces that have not built their panels yet (tests use it to get
+// several panels at small CAS); "0" restores the 1 GiB default
+static int64_t g_panel_width = 0;
+void sq_hamiltonian_set_panel_width(long long w) { g_panel_width = w > 0 ? (int64_t)w : 0; }
 
 static void free_work(HamWork* w) {
   if (!w) return;
   if (w->blas) cublasDestroy(w->blas);
   cudaFree(w->d_etab);
+  cudaFree(w->d_tabG);
+  cudaFree(w->d_tabS);
   for (double* p : w->d_D) cudaFree(p);
   for (double* p : w->d_F) cudaFree(p);
   if (w->s_build) cudaStreamDestroy(w->s_build);
@@ -86,6 +95,9 @@ void sq_hamiltonian_release(const sq_space* sp) {
     g_work.erase(it);
   }
 }
+
+static bool rows_kernels_fit(const sq_space* sp);
+static int build_beta_tables(sq_space* sp, HamWork* w);
 
 static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out) {
   HamWork* w = nullptr;
@@ -120,10 +132,12 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
         }
     SQ_CUDA(cudaMalloc(&w->d_etab, sizeof(ERec) * tab.size()));
     SQ_CUDA(cudaMemcpy(w->d_etab, tab.data(), sizeof(ERec) * tab.size(), cudaMemcpyHostToDevice));
+    w->h_etab = tab;
   }
+  if (g_rows_kernels && rows_kernels_fit(sp) && !w->d_tabG) SQ_CHECK(build_beta_tables(sp, w));
   if (!w->W) {
     // panel width: about 1 GiB per n^2 x W matrix, multiple of 256 determinants
-    int64_t Wmax = ((int64_t)1 << 27) / n2;
+    int64_t Wmax = g_panel_width > 0 ? g_panel_width : ((int64_t)1 << 27) / n2;
     Wmax = (Wmax / 256) * 256;
     if (Wmax < 256) Wmax = 256;
     int64_t len = sp->local_len();
@@ -280,6 +294,208 @@ scatter_E_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const 
   atomicAdd(OUT + j, diag);
 }
 
+// ---- row kernels (measured alternative, off by default) ---------------------------------------------------------------
+// Idea: the beta partner of column ib under E_rs and its sign do not depend on the row, so they can be tabulated once per
+// space as one 32-bit word per (rs, ib) and read coalesced; and all beta partners of a row lie in that row, so a CTA that
+// owns (part of) ONE row can keep the row in shared memory -- the gather reads it there, the scatter accumulates there
+// (shared-memory atomics) and flushes once; the alpha part becomes uniform per CTA.  Same arithmetic per element, parity
+// tested against the determinant-per-thread kernels (test_sigma_and_rdm_kernel_variants_agree).
+// Measured at CAS(16,16) (profiles/r1_ab_rows_kernels_cas16.txt): SLOWER -- sigma 576 ms against 468 ms, RDMs 759 ms against
+// 729 ms with 1024 threads per CTA, worse with fewer.  A 103 KB row allows two CTAs per SM and a panel of ~41 rows gives
+// few CTAs, while the determinant-per-thread kernels run 64 warps per SM and find the row in L1 anyway (consecutive CTAs
+// work on the same row).  Kept behind sq_set_option("rows", "1") with its geometry knob ("rows_cfg") as the evidence.
+#define SQ_TINV 0x3FFFFFFFu   // table word: [29:0] partner column (SQ_TINV: none), bit 30 beta-string sign, bit 31 alpha-op parity of b
+struct RowU {
+  int32_t row;      // alpha partner row under this slot, -1 if the slot does not act on the row's alpha string
+  uint32_t bits;    // bit 0: alpha sign (string part and s0); bit 1: parity of the alpha string under the BETA operator
+};
+static int g_rows_kernels = 0;
+static int g_rows_threads = 1024, g_rows_ch = 0;   // CTA size and column chunks per row (0: one wave of two CTAs per SM)
+void sq_hamiltonian_set_rows_mode(int on) { g_rows_kernels = on ? 1 : 0; }
+void sq_hamiltonian_set_rows_cfg(int threads, int ch) {
+  g_rows_threads = (threads >= 32 && threads <= 1024) ? (threads / 32) * 32 : 1024;
+  g_rows_ch = ch > 0 ? ch : 0;
+}
+
+static size_t rows_smem(const sq_space* sp) {
+  const size_t n2 = (size_t)sp->n_orb * sp->n_orb;
+  return sizeof(double) * (size_t)sp->NB + sizeof(RowU) * n2 + sizeof(double) * n2 + sizeof(int) * n2;
+}
+static bool rows_kernels_fit(const sq_space* sp) { return rows_smem(sp) <= 200 * 1024 && sp->NB < (int64_t)SQ_TINV; }
+
+static int build_beta_tables(sq_space* sp, HamWork* w) {
+  const int n = sp->n_orb, n2 = n * n;
+  const int64_t NB = sp->NB;
+  std::vector<uint32_t> tg((size_t)n2 * NB), ts((size_t)n2 * NB);
+  for (int slot = 0; slot < n2; ++slot) {
+    const ERec ra = w->h_etab[2 * (size_t)slot], rb = w->h_etab[2 * (size_t)slot + 1];
+    for (int64_t ib = 0; ib < NB; ++ib) {
+      const uint32_t b = sp->strB[ib];
+      const uint32_t apar = (uint32_t)(__builtin_popcount(b & ra.parO) & 1) << 31;
+      uint32_t g = SQ_TINV, sc = SQ_TINV;
+      if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {           // gather form: b is the target, sb the source
+        const uint32_t sb = b ^ rb.flip;
+        const uint32_t sgn = (uint32_t)((__builtin_popcount(sb & rb.parS) & 1) ^ (rb.s0 < 0 ? 1 : 0));
+        g = (uint32_t)sp->rankB[sb] | (sgn << 30);
+      }
+      if ((b & rb.occ) == rb.occ && (b & rb.emp) == 0u) {              // scatter form: b is the source
+        const uint32_t sgn = (uint32_t)((__builtin_popcount(b & rb.parS) & 1) ^ (rb.s0 < 0 ? 1 : 0));
+        sc = (uint32_t)sp->rankB[b ^ rb.flip] | (sgn << 30);
+      }
+      tg[(size_t)slot * NB + ib] = g | apar;
+      ts[(size_t)slot * NB + ib] = sc | apar;
+    }
+  }
+  SQ_CUDA(cudaMalloc(&w->d_tabG, sizeof(uint32_t) * tg.size()));
+  SQ_CUDA(cudaMalloc(&w->d_tabS, sizeof(uint32_t) * ts.size()));
+  SQ_CUDA(cudaMemcpy(w->d_tabG, tg.data(), sizeof(uint32_t) * tg.size(), cudaMemcpyHostToDevice));
+  SQ_CUDA(cudaMemcpy(w->d_tabS, ts.data(), sizeof(uint32_t) * ts.size(), cudaMemcpyHostToDevice));
+  return SQ_OK;
+}
+
+// CTA = (row ia, column chunk): D[slot][t] for the determinants of that chunk that fall into the panel [j0, jend)
+template <bool SYM>
+__global__ void __launch_bounds__(1024)
+build_D_rows_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t jend,
+                    const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ strA,
+                    const int32_t* __restrict__ rankA, const uint32_t* __restrict__ tabG, int64_t NB, int64_t ia_first,
+                    int CH) {
+  extern __shared__ double rowsm[];                 // the row's NB amplitudes, then the per-slot alpha records
+  const int n2 = n * n;
+  RowU* u = reinterpret_cast<RowU*>(rowsm + NB);
+  const int64_t ia = ia_first + blockIdx.x / CH;
+  const int ch = blockIdx.x % CH;
+  const uint32_t a = __ldg(strA + ia);
+  for (int slot = threadIdx.x; slot < n2; slot += blockDim.x) {
+    const ERec ra = etab[2 * slot], rb = etab[2 * slot + 1];
+    RowU r;
+    r.row = -1;
+    r.bits = 0u;
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      r.row = __ldg(rankA + sa);
+      r.bits = (uint32_t)((__popc(sa & ra.parS) & 1) ^ (ra.s0 < 0 ? 1 : 0));
+    }
+    r.bits |= (uint32_t)(__popc(a & rb.parO) & 1) << 1;
+    u[slot] = r;
+  }
+  const double* row = IN + ia * NB;
+  for (int64_t i = threadIdx.x; i < NB; i += blockDim.x) rowsm[i] = row[i];
+  __syncthreads();
+  const int64_t c0 = NB * ch / CH, c1 = NB * (ch + 1) / CH;
+  for (int64_t ib = c0 + threadIdx.x; ib < c1; ib += blockDim.x) {
+    const int64_t j = ia * NB + ib;
+    if (j < j0 || j >= jend) continue;
+    const int64_t t = j - j0;
+    auto elem = [&](int slot) -> double {
+      const uint32_t e = __ldg(tabG + (int64_t)slot * NB + ib);
+      const RowU r = u[slot];
+      double v = 0.0;
+      if (r.row >= 0) {
+        const double x = IN[(int64_t)r.row * NB + ib];
+        v += ((r.bits ^ (e >> 31)) & 1u) ? -x : x;
+      }
+      const uint32_t idx = e & SQ_TINV;
+      if (idx != SQ_TINV) {
+        const double x = rowsm[idx];
+        v += (((e >> 30) ^ (r.bits >> 1)) & 1u) ? -x : x;
+      }
+      return v;
+    };
+    if (SYM) {
+      int slot = 0;
+      for (int r = 0; r < n; ++r)
+        for (int q = 0; q <= r; ++q, ++slot)
+          D[(int64_t)slot * W + t] = (r == q) ? elem(r * n + r) : elem(r * n + q) + elem(q * n + r);
+    } else {
+      for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = elem(slot);
+    }
+  }
+}
+
+// CTA = (row ia, column chunk): OUT[E_pq J] += sign (F[pq][t] + k[pq] IN[J]); beta targets accumulate in the shared row
+__global__ void __launch_bounds__(1024)
+scatter_E_rows_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                      const double* __restrict__ kmat, const int* __restrict__ frow, int64_t W, int64_t j0, int64_t jend,
+                      const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA,
+                      const int32_t* __restrict__ rankA, const uint32_t* __restrict__ tabS, int64_t NB, int64_t ia_first,
+                      int CH) {
+  extern __shared__ double acc[];                   // NB accumulators, alpha records, k_pq, F rows
+  RowU* u = reinterpret_cast<RowU*>(acc + NB);
+  double* ks = reinterpret_cast<double*>(u + n2);
+  int* fr = reinterpret_cast<int*>(ks + n2);
+  const int64_t ia = ia_first + blockIdx.x / CH;
+  const int ch = blockIdx.x % CH;
+  const uint32_t a = __ldg(strA + ia);
+  for (int slot = threadIdx.x; slot < n2; slot += blockDim.x) {
+    const ERec ra = etab[2 * slot], rb = etab[2 * slot + 1];
+    RowU r;
+    r.row = -1;
+    r.bits = 0u;
+    if ((a & ra.occ) == ra.occ && (a & ra.emp) == 0u) {
+      r.row = __ldg(rankA + (a ^ ra.flip));
+      r.bits = (uint32_t)((__popc(a & ra.parS) & 1) ^ (ra.s0 < 0 ? 1 : 0));
+    }
+    r.bits |= (uint32_t)(__popc(a & rb.parO) & 1) << 1;
+    u[slot] = r;
+    ks[slot] = kmat[slot];
+    fr[slot] = frow[slot];
+  }
+  for (int64_t i = threadIdx.x; i < NB; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const int64_t c0 = NB * ch / CH, c1 = NB * (ch + 1) / CH;
+  for (int64_t ib = c0 + threadIdx.x; ib < c1; ib += blockDim.x) {
+    const int64_t j = ia * NB + ib;
+    if (j < j0 || j >= jend) continue;
+    const int64_t t = j - j0;
+    const double cj = IN[j];
+    double diag = 0.0;
+    for (int slot = 0; slot < n2; ++slot) {
+      const uint32_t e = __ldg(tabS + (int64_t)slot * NB + ib);
+      const RowU r = u[slot];
+      const uint32_t idx = e & SQ_TINV;
+      if (r.row < 0 && idx == SQ_TINV) continue;
+      const double val = F[(int64_t)fr[slot] * W + t] + ks[slot] * cj;
+      if (r.row >= 0) {
+        const double sv = ((r.bits ^ (e >> 31)) & 1u) ? -val : val;
+        if (r.row == ia) diag += sv;
+        else atomicAdd(OUT + (int64_t)r.row * NB + ib, sv);
+      }
+      if (idx != SQ_TINV) {
+        const double sv = (((e >> 30) ^ (r.bits >> 1)) & 1u) ? -val : val;
+        if ((int64_t)idx == ib) diag += sv;
+        else atomicAdd(acc + idx, sv);
+      }
+    }
+    atomicAdd(acc + ib, diag);
+  }
+  __syncthreads();
+  double* orow = OUT + ia * NB;
+  for (int64_t i = threadIdx.x; i < NB; i += blockDim.x) {
+    const double v = acc[i];
+    if (v != 0.0) atomicAdd(orow + i, v);
+  }
+}
+
+// launch geometry of the row kernels for the panel [j0, j0 + W)
+struct RowGrid {
+  int64_t ia_first, jend;
+  int CH;
+  unsigned grid;
+};
+static RowGrid row_grid(const sq_space* sp, const HamWork* w, int64_t j0) {
+  RowGrid g;
+  const int64_t len = sp->local_len();
+  g.jend = (j0 + w->W < len) ? j0 + w->W : len;
+  g.ia_first = j0 / sp->NB;
+  const int64_t ia_last = (g.jend - 1) / sp->NB;
+  const int64_t nrows = ia_last - g.ia_first + 1;
+  int ch = g_rows_ch > 0 ? g_rows_ch : (int)((2 * 148) / nrows);   // default: two CTAs per SM (103 KB row at CAS(16,16)), one wave
+  g.CH = ch < 1 ? 1 : (ch > 64 ? 64 : ch);
+  g.grid = (unsigned)(nrows * g.CH);
+  return g;
+}
+
 static int check_full_space(sq_space* sp, const char* who) {
   if (sp->device < 0) {
     sq_set_error("%s: host-only space (device = -1) cannot run kernels", who);
@@ -311,25 +527,82 @@ static void allow_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D, int64_t j0, cudaStream_t st, bool use_const) {
-  const int n2 = sp->n_orb * sp->n_orb;
-  const unsigned grid = (unsigned)(w->W / 256);
-  if (use_const) {
-    build_D_kernel<true><<<grid, 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA, sp->d_strB,
-                                               sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-  } else {
-    const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
-    allow_smem(build_D_kernel<false>, smem);
-    build_D_kernel<false><<<grid, 256, smem, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA, sp->d_strB,
-                                                   sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-  }
+static int launch_error(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    sq_set_error("build_D_kernel launch failed: %s", cudaGetErrorString(e));
+    sq_set_error("%s launch failed: %s", what, cudaGetErrorString(e));
     return SQ_ERR_CUDA;
   }
   g_sq_launches.fetch_add(1);
   return SQ_OK;
+}
+
+// D panel of [j0, j0 + W): n^2 rows, or the n (n + 1) / 2 symmetrised rows when sym
+static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D, int64_t j0, cudaStream_t st, bool use_const,
+                          bool sym = false) {
+  const int n = sp->n_orb, n2 = n * n;
+  if (g_rows_kernels && w->d_tabG) {
+    const RowGrid g = row_grid(sp, w, j0);
+    const size_t smem = rows_smem(sp);
+    if (g.jend - j0 < w->W)   // last panel: the GEMM reads all W columns, the kernel writes only the live ones
+      SQ_CUDA(cudaMemsetAsync(D, 0, sizeof(double) * (size_t)(sym ? n * (n + 1) / 2 : n2) * (size_t)w->W, st));
+    if (sym) {
+      allow_smem(build_D_rows_kernel<true>, smem);
+      build_D_rows_kernel<true><<<g.grid, g_rows_threads, smem, st>>>(in, D, w->W, j0, g.jend, w->d_etab, n, sp->d_strA, sp->d_rankA,
+                                                           w->d_tabG, sp->NB, g.ia_first, g.CH);
+    } else {
+      allow_smem(build_D_rows_kernel<false>, smem);
+      build_D_rows_kernel<false><<<g.grid, g_rows_threads, smem, st>>>(in, D, w->W, j0, g.jend, w->d_etab, n, sp->d_strA, sp->d_rankA,
+                                                            w->d_tabG, sp->NB, g.ia_first, g.CH);
+    }
+    return launch_error("build_D_rows_kernel");
+  }
+  const unsigned grid = (unsigned)(w->W / 256);
+  const size_t smem = use_const ? 0 : sizeof(ERec) * 2 * (size_t)n2;
+  if (sym) {
+    if (use_const) {
+      build_Dsym_kernel<true><<<grid, 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                    sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+    } else {
+      allow_smem(build_Dsym_kernel<false>, smem);
+      build_Dsym_kernel<false><<<grid, 256, smem, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                        sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+    }
+    return launch_error("build_Dsym_kernel");
+  }
+  if (use_const) {
+    build_D_kernel<true><<<grid, 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA, sp->d_strB,
+                                               sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  } else {
+    allow_smem(build_D_kernel<false>, smem);
+    build_D_kernel<false><<<grid, 256, smem, st>>>(in, D, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA, sp->d_strB,
+                                                   sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  }
+  return launch_error("build_D_kernel");
+}
+
+static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* out, const double* F, const double* d_k,
+                            int64_t j0, cudaStream_t st, bool use_const) {
+  const int n2 = sp->n_orb * sp->n_orb;
+  if (g_rows_kernels && w->d_tabS) {
+    const RowGrid g = row_grid(sp, w, j0);
+    const size_t smem = rows_smem(sp);
+    allow_smem(scatter_E_rows_kernel, smem);
+    scatter_E_rows_kernel<<<g.grid, g_rows_threads, smem, st>>>(in, out, F, d_k, w->d_frow, w->W, j0, g.jend, w->d_etab, n2, sp->d_strA,
+                                                     sp->d_rankA, w->d_tabS, sp->NB, g.ia_first, g.CH);
+    return launch_error("scatter_E_rows_kernel");
+  }
+  const unsigned grid = (unsigned)(w->W / 256);
+  if (use_const) {
+    scatter_E_kernel<true><<<grid, 256, 0, st>>>(in, out, F, d_k, w->d_frow, w->W, j0, sp->local_len(), w->d_etab, n2, sp->d_strA,
+                                                 sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  } else {
+    const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+    allow_smem(scatter_E_kernel<false>, smem);
+    scatter_E_kernel<false><<<grid, 256, smem, st>>>(in, out, F, d_k, w->d_frow, w->W, j0, sp->local_len(), w->d_etab, n2,
+                                                     sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  }
+  return launch_error("scatter_E_kernel");
 }
 
 extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, const double* g_act_host,
@@ -398,12 +671,6 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   const int64_t len = sp->local_len();
   bool use_const = false;
   SQ_CHECK(bind_etab(sp, w, st, &use_const));
-  const size_t smem = use_const ? 0 : sizeof(ERec) * 2 * (size_t)n2;
-  if (!use_const) {
-    allow_smem(scatter_E_kernel<false>, smem);
-    allow_smem(build_Dsym_kernel<false>, smem);
-  }
-  const unsigned grid = (unsigned)(w->W / 256);
   const double one = 1.0, zero = 0.0;
   // Three-stage pipeline over the panels: while the DGEMM of panel k runs on the tensor cores, the gather of panel k+1
   // and the scatter of panel k-1 (both address-bound) run beside it.  Two D and two F panels are in flight; with
@@ -423,22 +690,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     double* Dp = w->d_D[b];
     double* Fp = w->d_F[b];
     if (piped && ip >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // D[b] is free once GEMM k-2 has read it
-    if (sym) {
-      if (use_const)
-        build_Dsym_kernel<true><<<grid, 256, 0, s_build>>>(in_dev, Dp, w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
-                                                           sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-      else
-        build_Dsym_kernel<false><<<grid, 256, smem, s_build>>>(in_dev, Dp, w->W, j0, len, w->d_etab, n, sp->d_strA, sp->d_strB,
-                                                               sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) {
-        sq_set_error("build_Dsym_kernel launch failed: %s", cudaGetErrorString(e));
-        return SQ_ERR_CUDA;
-      }
-      g_sq_launches.fetch_add(1);
-    } else {
-      SQ_CHECK(launch_build_D(sp, w, in_dev, Dp, j0, s_build, use_const));
-    }
+    SQ_CHECK(launch_build_D(sp, w, in_dev, Dp, j0, s_build, use_const, sym));
     if (piped) {
       SQ_CUDA(cudaEventRecord(w->ev_built[b], s_build));
       SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_built[b], 0));
@@ -456,18 +708,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       SQ_CUDA(cudaEventRecord(w->ev_gemm[b], s_gemm));
       SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_gemm[b], 0));
     }
-    if (use_const)
-      scatter_E_kernel<true><<<grid, 256, 0, s_scat>>>(in_dev, out_dev, Fp, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
-                                                       sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-    else
-      scatter_E_kernel<false><<<grid, 256, smem, s_scat>>>(in_dev, out_dev, Fp, d_k, w->d_frow, w->W, j0, len, w->d_etab, n2,
-                                                           sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      sq_set_error("scatter_E_kernel launch failed: %s", cudaGetErrorString(e));
-      return SQ_ERR_CUDA;
-    }
-    g_sq_launches.fetch_add(1);
+    SQ_CHECK(launch_scatter_E(sp, w, in_dev, out_dev, Fp, d_k, j0, s_scat, use_const));
     if (piped) SQ_CUDA(cudaEventRecord(w->ev_scat[b], s_scat));
   }
   if (piped) {   // the caller's stream continues after the last scatter (which is after everything else)

@@ -191,6 +191,9 @@ static inline int64_t sq_rank_start(const sq_space* sp, int r) {
 int sq_rank_mask(const sq_space* sp, int spin, uint32_t mask);   // -1 if not in list
 int sq_make_string_action(const sq_space* sp, const int32_t* ops, int n_ops, StringAction* out);
 void sq_hamiltonian_release(const sq_space* sp);   // frees sigma / RDM panels (sqsv_hamiltonian.cu)
+void sq_hamiltonian_set_panel_width(long long w);  // determinants per panel for spaces that build their panels later (0: 1 GiB)
+void sq_hamiltonian_set_rows_cfg(int threads, int ch);  // CTA size / column chunks per row of the row kernels
+void sq_hamiltonian_set_rows_mode(int on);         // row-per-CTA panel kernels (default on) or determinant-per-thread
 void sq_hamiltonian_set_pipeline(int on);          // sigma / RDM panel pipeline over internal streams (default on)
 void sq_hamiltonian_set_etab_mode(int use_const);  // E_pq table in constant (1) or shared (0) memory
 int sq_ensure_work(sq_space* sp, int which);

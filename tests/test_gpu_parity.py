@@ -676,3 +676,50 @@ def test_state_averaged_twins(sq):
     assert np.max(np.abs(got_p - ref_p)) < TOL
     ev = sq.osa.expectation_value_SA(states, [op], states, info)
     assert abs(ev - float(np.mean([s @ r for s, r in zip(states, ref_p)]))) < 1e-12
+
+
+def test_sigma_and_rdm_kernel_variants_agree(sq):
+    """The sigma / RDM path has run-time variants (sq_set_option): row-per-CTA or determinant-per-thread panel kernels,
+    E table in shared or constant memory, panels pipelined over internal streams or one at a time.  With small panels (so
+    that several panels, a partial last panel and rows split between panels all occur) every variant must give the oracle's
+    sigma vector and identical RDMs."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    lib = sq.lib.load()
+    n, na, nb = 8, 4, 3
+    rng = np.random.default_rng(7)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    g_unsym = g + 0.05 * rng.normal(size=(n, n, n, n))      # takes the general n^2 path
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    state = rng.normal(size=sp.num_det)
+    state /= np.linalg.norm(state)
+    refs = {}
+    for name, gg in (("sym", g), ("unsym", g_unsym)):
+        refs[name] = orc.propagate_state([orc.hamiltonian_0i_0a(h, gg, 0, n)], state, sp)
+    results = []
+    other = rng.normal(size=sp.num_det)
+    try:
+        for rows, etab, pipe in ((b"1", b"smem", b"1"), (b"1", b"smem", b"0"), (b"0", b"smem", b"1"), (b"0", b"const", b"0")):
+            lib.sq_set_option(b"panel", b"768")            # 3920 determinants -> 6 panels, the last one partial
+            lib.sq_set_option(b"rows", rows)
+            lib.sq_set_option(b"etab", etab)
+            lib.sq_set_option(b"pipeline", pipe)
+            info = sq.ci.get_indexing(0, n, 0, na, nb)      # a fresh space picks up the panel width
+            for name, gg in (("sym", g), ("unsym", g_unsym)):
+                out = sq.osa.propagate_state([hamiltonian_0i_0a(h, gg, 0, n)], state, info)
+                assert np.max(np.abs(out - refs[name])) < 1e-11, (rows, etab, pipe, name)
+            d1, d2 = sq.osa.reduced_density_matrices(state, state, info)
+            t1, t2 = sq.osa.reduced_density_matrices(other, state, info)
+            results.append((d1, d2, t1, t2))
+            assert abs(np.trace(d1) - (na + nb)) < 1e-12
+    finally:
+        for name, val in ((b"panel", b"0"), (b"rows", b"0"), (b"etab", b"smem"), (b"pipeline", b"1")):
+            lib.sq_set_option(name, val)
+    for other in results[1:]:
+        for x, y in zip(results[0], other):
+            assert np.max(np.abs(x - y)) < 1e-12
