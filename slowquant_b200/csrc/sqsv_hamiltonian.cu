@@ -96,6 +96,7 @@ void sq_hamiltonian_release(const sq_space* sp) {
   }
 }
 
+static int g_rows_kernels = 0;   // sq_set_option("rows", "1"): row-per-CTA panel kernels (see "row kernels" below)
 static bool rows_kernels_fit(const sq_space* sp);
 static int build_beta_tables(sq_space* sp, HamWork* w);
 
@@ -309,7 +310,6 @@ struct RowU {
   int32_t row;      // alpha partner row under this slot, -1 if the slot does not act on the row's alpha string
   uint32_t bits;    // bit 0: alpha sign (string part and s0); bit 1: parity of the alpha string under the BETA operator
 };
-static int g_rows_kernels = 0;
 static int g_rows_threads = 1024, g_rows_ch = 0;   // CTA size and column chunks per row (0: one wave of two CTAs per SM)
 void sq_hamiltonian_set_rows_mode(int on) { g_rows_kernels = on ? 1 : 0; }
 void sq_hamiltonian_set_rows_cfg(int threads, int ch) {
