@@ -410,6 +410,8 @@ def run_ours(args) -> None:
         # the batch call of the same API (construct_ups_state_SA on [S, N_det] host states: RotoSolve shifts, state-averaged
         # ensembles): copies of neighbouring states overlap the kernels on three streams
         try:
+            if world > 1:
+                raise RuntimeError("skipped for N > 1 (one pinned batch per rank)")
             from slowquant_b200.operator_state_algebra import construct_ups_state_SA
 
             S = 6
@@ -476,6 +478,22 @@ def run_ours(args) -> None:
             # per-operator HBM roofline
             "per_operator_algorithm_GBps": 16.0 * info.num_det * P * args.steps / (ms_max * 1e-3) / 1e9,
         }
+        # the roofline that actually binds win_kernel: every brick moves its touched amplitudes through shared memory
+        # once (LDS + STS, 16 B each); peak = 128 B per clock and SM (B300_MICROARCH.md) at the sampled SM clock
+        if plan[1]:
+            from math import comb
+
+            inert = 1.0 - 2.0 * comb(n - 2, ne - 1) / comb(n, ne)
+            smem_bytes = 16.0 * plan[2] * (1.0 - inert * inert) * info.num_det * args.steps
+            smem_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965) * 1e6 / 1e9
+            roofline["shared_memory"] = {
+                "bound": "shared memory bandwidth (brick phases of win_kernel)",
+                "achieved": smem_bytes / (ms_max * 1e-3) / 1e9,
+                "peak": smem_peak,
+                "unit": "GB/s",
+                "frac": smem_bytes / (ms_max * 1e-3) / 1e9 / smem_peak,
+                "note": "whole-step average including the HBM phases of every sweep; ncu: LSU data pipe 70-75 % over the kernel",
+            }
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -433,6 +433,71 @@ def reduced_density_matrices(bra, ket, ci_info: CI_Info, want_rdm2: bool = True)
     return d1, d2
 
 
+def higher_reduced_density_matrices(state, ci_info: CI_Info, rdm1: np.ndarray, rdm2: np.ndarray, want_rdm4: bool = True):
+    r"""Active-space 3- and 4-RDMs of one state (replaces the n^6 / n^8 ``expectation_value`` loops of
+    ups_wavefunction.py:478-754).
+
+    One panel ``W[(a,b),(c,d)] = E_ab E_cd |psi>`` (n^2 + n^4 gather launches) carries both: with ``D[(a,b)] = E_ab|psi>``
+
+        <E_pq E_rs E_tu>      = D[(q,p)] . W[(r,s),(t,u)]                 (one GEMM  n^2 x N_det x n^4)
+        <E_pq E_rs E_tu E_mn> = W[(s,r),(q,p)] . W[(t,u),(m,n)]           (one Gram matrix  n^4 x N_det x n^4)
+
+    followed by the contraction terms of the reference (:517-524, :575-606) as index-placement einsums with the
+    (mirrored) rdm1 / rdm2.  Small active spaces only: the panel holds n^4 vectors.
+    """
+    from slowquant_b200.operators import Epq
+
+    n = ci_info.num_active_orbs
+    psi, _ = _to_device(state, ci_info, copy=False)
+    ndet = psi.numel()
+    if 8.0 * n**4 * ndet > 16e9:
+        raise MemoryError(f"rdm3/rdm4 panel needs {8.0 * n**4 * ndet / 1e9:.1f} GB; implemented for small active spaces only")
+    E = [[Epq(a, b) for b in range(n)] for a in range(n)]
+    D = torch.empty((n * n, ndet), dtype=torch.float64, device=psi.device)
+    for a in range(n):
+        for b in range(n):
+            _apply_operator(E[a][b], psi, D[a * n + b], ci_info, False)
+    W = torch.empty((n * n, n * n, ndet), dtype=torch.float64, device=psi.device)
+    for a in range(n):
+        for b in range(n):
+            for cd in range(n * n):
+                _apply_operator(E[a][b], D[cd], W[a * n + b, cd], ci_info, False)
+    Wf = W.reshape(n**4, ndet)
+    # R3[(q,p),(r,s),(t,u)] -> [p,q,r,s,t,u]
+    R3 = (D @ Wf.T).cpu().numpy().reshape(n, n, n, n, n, n).transpose(1, 0, 2, 3, 4, 5)
+    I = np.eye(n)
+    G1, G2 = np.asarray(rdm1), np.asarray(rdm2)
+    rdm3 = (
+        R3
+        - np.einsum("ts,pqru->pqrstu", I, G2)
+        - np.einsum("rq,pstu->pqrstu", I, G2)
+        - np.einsum("tq,purs->pqrstu", I, G2)
+        - np.einsum("ts,rq,pu->pqrstu", I, I, G1)
+    )
+    if not want_rdm4:
+        return rdm3, None
+    # R4[(s,r),(q,p),(t,u),(m,n)] -> [p,q,r,s,t,u,m,n]
+    R4 = (Wf @ Wf.T).cpu().numpy().reshape(n, n, n, n, n, n, n, n).transpose(3, 2, 1, 0, 4, 5, 6, 7)
+    rdm4 = (
+        R4
+        - np.einsum("rq,pstumn->pqrstumn", I, rdm3)
+        - np.einsum("tq,pursmn->pqrstumn", I, rdm3)
+        - np.einsum("mq,pnrstu->pqrstumn", I, rdm3)
+        - np.einsum("mu,pqrstn->pqrstumn", I, rdm3)
+        - np.einsum("ts,pqrumn->pqrstumn", I, rdm3)
+        - np.einsum("ms,pqrntu->pqrstumn", I, rdm3)
+        - np.einsum("mu,rq,pstn->pqrstumn", I, I, G2)
+        - np.einsum("mu,tq,pnrs->pqrstumn", I, I, G2)
+        - np.einsum("ts,mu,pqrn->pqrstumn", I, I, G2)
+        - np.einsum("ts,rq,pumn->pqrstumn", I, I, G2)
+        - np.einsum("ts,mq,pnru->pqrstumn", I, I, G2)
+        - np.einsum("ms,rq,pntu->pqrstumn", I, I, G2)
+        - np.einsum("ms,tq,purn->pqrstumn", I, I, G2)
+        - np.einsum("mu,ts,rq,pn->pqrstumn", I, I, I, G1)
+    )
+    return rdm3, rdm4
+
+
 # ---- state-averaged twins: batches [n_states, N_det] (osa.py:633-781, 827-867, 1415-1864, 2312-2976) ----
 def _map_states(fn, states):
     if isinstance(states, torch.Tensor):

@@ -60,6 +60,7 @@ class WaveFunctionUCC(WaveFunctionUPS):
         if len(theta) != len(self._thetas):
             raise ValueError(f"Expected {len(self._thetas)} theta1 values got {len(theta)}")
         self._rdm1 = self._rdm2 = None
+        self._rdm3 = self._rdm4 = None
         self._energy_elec = None
         self._thetas = [float(x) for x in theta]
         self._ci_dev = osa.construct_ucc_state(self._csf_dev, self.ci_info, self._thetas, self.ucc_layout)

@@ -262,6 +262,7 @@ class WaveFunctionUPS:
         if len(theta_vals) != len(self._thetas):
             raise ValueError(f"Expected {len(self._thetas)} theta1 values got {len(theta_vals)}")
         self._rdm1 = self._rdm2 = None
+        self._rdm3 = self._rdm4 = None
         self._energy_elec = None
         self._thetas = [float(x) for x in theta_vals]
         self._ci_dev = osa.construct_ups_state(self._csf_dev, self.ci_info, self._thetas, self.ups_layout)
@@ -279,6 +280,7 @@ class WaveFunctionUPS:
         self._ci_dev = torch.as_tensor(np.asarray(value, dtype=np.float64)).to(dev).clone()
         self._ci_host = None
         self._rdm1 = self._rdm2 = None
+        self._rdm3 = self._rdm4 = None
         self._energy_elec = None
 
     @property
@@ -330,6 +332,26 @@ class WaveFunctionUPS:
         if self._rdm2 is None:
             self._build_rdms(True)
         return self._rdm2
+
+    def _build_higher_rdms(self, want_rdm4: bool) -> None:
+        d3, d4 = osa.higher_reduced_density_matrices(self._ci_dev, self.ci_info, self.rdm1, self.rdm2, want_rdm4=want_rdm4)
+        self._rdm3 = d3
+        if want_rdm4:
+            self._rdm4 = d4
+
+    @property
+    def rdm3(self) -> np.ndarray:
+        """Three-electron RDM in the active space (ups_wavefunction.py:478-545)."""
+        if getattr(self, "_rdm3", None) is None:
+            self._build_higher_rdms(False)
+        return self._rdm3
+
+    @property
+    def rdm4(self) -> np.ndarray:
+        """Four-electron RDM in the active space (ups_wavefunction.py:547-754)."""
+        if getattr(self, "_rdm4", None) is None:
+            self._build_higher_rdms(True)
+        return self._rdm4
 
     @property
     def energy_elec(self) -> float:

@@ -723,3 +723,36 @@ def test_sigma_and_rdm_kernel_variants_agree(sq):
     for other in results[1:]:
         for x, y in zip(results[0], other):
             assert np.max(np.abs(x - y)) < 1e-12
+
+
+def test_rdm3_rdm4_against_reference(sq, golden):
+    """rdm3 / rdm4 (ups_wavefunction.py:478-754) from the E E|psi> panel against the reference's loops: CAS(4,4) rdm3,
+    CAS(4,3) rdm3 + rdm4, and CAS(2,3) where both must vanish (every contraction term has to cancel)."""
+    import os
+
+    from conftest import ROOT
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    arrays, _, _ = golden
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_rdm34.npz"))
+    ints = ArrayIntegrals(arrays["h2o_h_mo"], arrays["h2o_g_mo"], num_elec=10)
+    eye = np.eye(arrays["h2o_h_mo"].shape[0])
+    WF = WaveFunctionUPS((4, 4), eye, ints, "tUPS", {"n_layers": 2}, include_active_kappa=True)
+    WF.thetas = arrays["tups44_thetas"].tolist()
+    assert np.max(np.abs(WF.rdm3 - g["cas44_rdm3"])) < 1e-10
+    # partial trace: sum_t Gamma3[pq rs tt] = (N - 2) Gamma2[pq rs]
+    assert np.max(np.abs(np.einsum("pqrstt->pqrs", WF.rdm3) - 2 * WF.rdm2)) < 1e-10
+    WF3 = WaveFunctionUPS((4, 3), eye, ints, "tUPS", {"n_layers": 2}, include_active_kappa=True)
+    WF3.thetas = g["cas43_thetas"].tolist()
+    assert np.max(np.abs(WF3.rdm3 - g["cas43_rdm3"])) < 1e-10
+    assert np.max(np.abs(WF3.rdm4 - g["cas43_rdm4"])) < 1e-10
+    assert np.max(np.abs(np.einsum("pqrstumm->pqrstu", WF3.rdm4) - 1 * WF3.rdm3)) < 1e-10
+    WF2 = WaveFunctionUPS((2, 3), eye, ints, "tUPS", {"n_layers": 2}, include_active_kappa=True)
+    WF2.thetas = g["cas23_thetas"].tolist()
+    assert np.max(np.abs(WF2.ci_coeffs - g["cas23_ci"])) < TOL
+    assert np.max(np.abs(WF2.rdm3)) < 1e-12 and np.max(np.abs(WF2.rdm4)) < 1e-12
+    assert np.max(np.abs(WF2.rdm3 - g["cas23_rdm3"])) < 1e-12 and np.max(np.abs(WF2.rdm4 - g["cas23_rdm4"])) < 1e-12
+    th = WF3.thetas
+    WF3.thetas = [t + 0.1 for t in th]      # the setter drops the cached higher RDMs
+    assert np.max(np.abs(WF3.rdm3 - g["cas43_rdm3"])) > 1e-4
