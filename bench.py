@@ -438,6 +438,38 @@ def run_ours(args) -> None:
             del outb, batch_in
         except Exception as exc:  # an extra, never a gate
             e2e["batched"] = {"error": repr(exc)}
+        # the call an optimiser makes: `WF.thetas = x` on a WaveFunctionUPS whose reference state is resident (H2D: the
+        # parameters; D2H: one amplitude as the completion fence) -- what a user pays per state construction when the
+        # vector never has to leave the device
+        try:
+            if world > 1:
+                raise RuntimeError("skipped for N > 1")
+            from slowquant_b200.integral_manager import ArrayIntegrals
+            from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+            rng_i = np.random.default_rng(2024)
+            h_syn = rng_i.normal(size=(n, n))
+            g_syn = np.zeros((n, n, n, n))
+            WF = WaveFunctionUPS((n, n), np.eye(n), ArrayIntegrals(h_syn + h_syn.T, g_syn, num_elec=n), "tUPS", {"n_layers": L}, device=local_rank)
+            th_list = thetas.tolist()
+            WF.thetas = th_list
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                WF.thetas = th_list
+                probe = float(WF.ci_coeffs_device[0].item())
+            dtw = time.perf_counter() - t0
+            e2e["wavefunction_setter"] = {
+                "value": L * n_e2e / dtw,
+                "unit": UNIT,
+                "api": "WaveFunctionUPS.thetas = x (reference state resident on the device), one amplitude read back",
+                "h2d_bytes_per_step": int(8 * P),
+                "d2h_bytes_per_step": 8,
+                "probe": probe,
+            }
+            del WF
+        except Exception as exc:  # an extra, never a gate
+            e2e["wavefunction_setter"] = {"error": repr(exc)}
         del out, host_in, np_in
 
     extras = None

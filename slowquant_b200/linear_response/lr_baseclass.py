@@ -26,31 +26,22 @@ class LinearResponseBaseClass:
             self.index_info = (self.wf.ci_info, self.wf.thetas, self.wf.ups_layout)
         else:
             raise ValueError(f"Got incompatible wave function type, {type(self.wf)}")
-        self.G_ops: list[FermionicOperator] = []
-        self.q_ops: list[FermionicOperator] = []
-        excitations = excitations.lower()
         occ, unocc = self.wf.active_occ_idx, self.wf.active_unocc_idx
         occ_s, unocc_s = self.wf.active_occ_spin_idx, self.wf.active_unocc_spin_idx
+        # excitation pools by the letters of `excitations`; the iterators yield (a, i, b, j, ...) = particle, hole, ...
+        # and the operator factories take all holes first, then all particles (lr_baseclass.py:61-91)
+        spin_orbital_pools = (("t", iterate_t3, G3), ("q", iterate_t4, G4), ("5", iterate_t5, G5), ("6", iterate_t6, G6))
+        excitations = excitations.lower()
+        self.G_ops: list[FermionicOperator] = []
         if "s" in excitations:
-            for a, i, _ in iterate_t1_sa(occ, unocc):
-                self.G_ops.append(G1_sa(i, a))
+            self.G_ops += [G1_sa(i, a) for a, i, _ in iterate_t1_sa(occ, unocc)]
         if "d" in excitations:
-            for a, i, b, j, _, op_type in iterate_t2_sa(occ, unocc):
-                self.G_ops.append(G2_sa(i, j, a, b, op_type))
-        if "t" in excitations:
-            for a, i, b, j, c, k in iterate_t3(occ_s, unocc_s):
-                self.G_ops.append(G3(i, j, k, a, b, c))
-        if "q" in excitations:
-            for a, i, b, j, c, k, d, l in iterate_t4(occ_s, unocc_s):
-                self.G_ops.append(G4(i, j, k, l, a, b, c, d))
-        if "5" in excitations:
-            for a, i, b, j, c, k, d, l, e, m in iterate_t5(occ_s, unocc_s):
-                self.G_ops.append(G5(i, j, k, l, m, a, b, c, d, e))
-        if "6" in excitations:
-            for a, i, b, j, c, k, d, l, e, m, f, n in iterate_t6(occ_s, unocc_s):
-                self.G_ops.append(G6(i, j, k, l, m, n, a, b, c, d, e, f))
-        for p, q in self.wf.kappa_no_activeactive_idx:
-            self.q_ops.append(G1_sa(int(p), int(q)))
+            self.G_ops += [G2_sa(i, j, a, b, case) for a, i, b, j, _, case in iterate_t2_sa(occ, unocc)]
+        for letter, iterator, factory in spin_orbital_pools:
+            if letter in excitations:
+                for idx in iterator(occ_s, unocc_s):
+                    self.G_ops.append(factory(*idx[1::2], *idx[0::2]))
+        self.q_ops: list[FermionicOperator] = [G1_sa(int(p), int(q)) for p, q in self.wf.kappa_no_activeactive_idx]
         num_parameters = len(self.G_ops) + len(self.q_ops)
         self.A = np.zeros((num_parameters, num_parameters))
         self.B = np.zeros((num_parameters, num_parameters))
@@ -79,29 +70,21 @@ class LinearResponseBaseClass:
         sorting = np.argsort(eigval)
         self.excitation_energies = np.real(eigval[sorting][size:])
         self.response_vectors = np.real(eigvec[:, sorting][:, size:])
-        self.normed_response_vectors = np.zeros_like(self.response_vectors)
-        self.num_q = len(self.q_ops)
-        self.num_G = size - self.num_q
-        nq, nG = self.num_q, self.num_G
-        self.Z_q = self.response_vectors[:nq, :]
-        self.Z_G = self.response_vectors[nq : nq + nG, :]
-        self.Y_q = self.response_vectors[nq + nG : 2 * nq + nG]
-        self.Y_G = self.response_vectors[2 * nq + nG :]
-        self.Z_q_normed = np.zeros_like(self.Z_q)
-        self.Z_G_normed = np.zeros_like(self.Z_G)
-        self.Y_q_normed = np.zeros_like(self.Y_q)
-        self.Y_G_normed = np.zeros_like(self.Y_G)
+        self.num_q = nq = len(self.q_ops)
+        self.num_G = nG = size - nq
+        # rows of a response vector: [Z_q, Z_G, Y_q, Y_G]
+        bounds = np.cumsum([0, nq, nG, nq, nG])
+        self.Z_q, self.Z_G, self.Y_q, self.Y_G = (self.response_vectors[bounds[k] : bounds[k + 1]] for k in range(4))
         norms = self.get_excited_state_norm()
+        scale = np.zeros_like(norms)
         for state_number, norm in enumerate(norms):
-            if norm < 10**-10:
+            if norm < 10**-10:    # such a state keeps zero normalised vectors (lr_baseclass.py:150-153)
                 print(f"WARNING: State number {state_number} could not be normalized. Norm of {norm}.")
-                continue
-            scale = (1 / norm) ** 0.5
-            self.Z_q_normed[:, state_number] = self.Z_q[:, state_number] * scale
-            self.Z_G_normed[:, state_number] = self.Z_G[:, state_number] * scale
-            self.Y_q_normed[:, state_number] = self.Y_q[:, state_number] * scale
-            self.Y_G_normed[:, state_number] = self.Y_G[:, state_number] * scale
-            self.normed_response_vectors[:, state_number] = self.response_vectors[:, state_number] * scale
+            else:
+                scale[state_number] = (1 / norm) ** 0.5
+        self.normed_response_vectors = self.response_vectors * scale[None, :]
+        self.Z_q_normed, self.Z_G_normed = self.Z_q * scale[None, :], self.Z_G * scale[None, :]
+        self.Y_q_normed, self.Y_G_normed = self.Y_q * scale[None, :], self.Y_G * scale[None, :]
 
     def get_excited_state_norm(self) -> np.ndarray:
         """Z^T S Z - Y^T S Y with the q-q and G-G diagonal blocks of the metric (lr_baseclass.py:168-188)."""
