@@ -127,6 +127,15 @@ int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, do
 int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                       double* bra_dev, double* ket_dev, double* grad_host, void* stream);
 
+/* Energy and theta gradient of a unitary product state in one call (_calc_energy_optimization /
+ * _calc_gradient_optimization, ups_wavefunction.py:1019-1142): psi = U(theta) ref, *energy_host = <psi|H|psi> with H given by
+ * the folded integrals of sq_sigma, grad_host[k] = dE/dtheta_k by the reverse sweep (skipped when grad_host is NULL).
+ * work_ket_dev / work_bra_dev: two vectors of the state's length, distinct from ref_dev; on return work_ket_dev holds
+ * psi when grad_host is NULL and the swept reference state otherwise. */
+int sq_ups_energy_grad(sq_space* sp, sq_layout* lay, const double* thetas_host, double e_core,
+                       const double* h_act_host, const double* g_act_host, const double* ref_dev,
+                       double* work_ket_dev, double* work_bra_dev, double* energy_host, double* grad_host, void* stream);
+
 /* ---- alpha-sharded vectors: one process per GPU, shards peer-mapped over NVLink ----------------
  * (no counterpart in the reference, which is single-process).  The vector is split by rows
  * (alpha strings); operators whose row pairs stay on one device run unchanged, the others rotate their

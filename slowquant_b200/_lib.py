@@ -56,6 +56,7 @@ def _declare(lib: C.CDLL) -> None:
         "sq_ups_apply": (i32, [vp, vp, pdbl, i32, i32, i32, vp, vp]),
         "sq_grad_action": (i32, [vp, vp, i32, vp, vp, vp]),
         "sq_ups_grad_sweep": (i32, [vp, vp, pdbl, i32, i32, vp, vp, pdbl, vp]),
+        "sq_ups_energy_grad": (i32, [vp, vp, pdbl, dbl, pdbl, pdbl, vp, vp, vp, pdbl, pdbl, vp]),
         "sq_apply_strings": (i32, [vp, i32, pi32, pi32, pdbl, vp, vp, i32, i32, vp]),
         "sq_dot": (i32, [vp, vp, vp, pdbl, vp]),
         "sq_axpy": (i32, [vp, dbl, vp, vp, vp]),
@@ -89,7 +90,7 @@ EXPORTED_SYMBOLS = (
     "sq_space_local_rows sq_space_export_strings sq_space_export_idx2det sq_space_det2idx sq_layout_create "
     "sq_layout_attach_generator sq_layout_destroy sq_layout_num_ops sq_layout_num_launches "
     "sq_layout_touched_amplitudes sq_layout_plan_stats sq_set_option sq_ups_apply "
-    "sq_grad_action sq_ups_grad_sweep sq_apply_strings sq_dot sq_axpy sq_scale_copy sq_sigma sq_rdm12 "
+    "sq_grad_action sq_ups_grad_sweep sq_ups_energy_grad sq_apply_strings sq_dot sq_axpy sq_scale_copy sq_sigma sq_rdm12 "
     "sq_debug_string_action sq_launch_count sq_partition_prefix sq_space_set_partition sq_dist_alloc sq_dist_free "
     "sq_ipc_export sq_ipc_import sq_ipc_close sq_layout_needs_exchange sq_ups_apply_dist sq_layout_op_stats"
 ).split()

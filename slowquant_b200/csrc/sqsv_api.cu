@@ -1462,6 +1462,34 @@ extern "C" int sq_apply_strings(sq_space* sp, int n_strings, const int32_t* ops_
   return sq_launch_gather(sp, acts, cf, in_dev, out_dev, accumulate, (cudaStream_t)stream);
 }
 
+// Energy and theta gradient in one call (ups_wavefunction.py:1019-1142 with the state path of :345-365):
+//   |psi> = U(theta)|ref>,  E = <psi|H|psi>,  g_k = 2 <bra_k|T_k|ket_k>  (reverse sweep of :1114-1138 started from
+//   bra = U^d H|psi>, ket = |ref>).  The caller supplies two work vectors of the state's length.
+extern "C" int sq_ups_energy_grad(sq_space* sp, sq_layout* lay, const double* thetas_host, double e_core,
+                                  const double* h_act_host, const double* g_act_host, const double* ref_dev,
+                                  double* work_ket_dev, double* work_bra_dev, double* energy_host, double* grad_host,
+                                  void* stream) {
+  if (!sp || !lay || lay->sp != sp || !thetas_host || !h_act_host || !g_act_host || !ref_dev || !work_ket_dev ||
+      !work_bra_dev || !energy_host)
+    return SQ_ERR_INVALID;
+  if (work_ket_dev == work_bra_dev || work_ket_dev == ref_dev || work_bra_dev == ref_dev) {
+    sq_set_error("sq_ups_energy_grad: the reference state and the two work vectors must be distinct");
+    return SQ_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  const int P = (int)lay->ops.size();
+  const size_t bytes = sizeof(double) * (size_t)sp->local_len();
+  SQ_CUDA(cudaMemcpyAsync(work_ket_dev, ref_dev, bytes, cudaMemcpyDeviceToDevice, st));
+  SQ_CHECK(sq_ups_apply(sp, lay, thetas_host, 0, P, 0, work_ket_dev, stream));                       // |psi>
+  SQ_CHECK(sq_sigma(sp, e_core, h_act_host, g_act_host, work_ket_dev, work_bra_dev, stream));        // H|psi>
+  SQ_CHECK(sq_dot(sp, work_ket_dev, work_bra_dev, energy_host, stream));
+  if (!grad_host) return SQ_OK;
+  SQ_CHECK(sq_ups_apply(sp, lay, thetas_host, 0, P, 1, work_bra_dev, stream));                       // U^d H|psi>
+  SQ_CUDA(cudaMemcpyAsync(work_ket_dev, ref_dev, bytes, cudaMemcpyDeviceToDevice, st));
+  return sq_ups_grad_sweep(sp, lay, thetas_host, 0, P, work_bra_dev, work_ket_dev, grad_host, stream);
+}
+
 extern "C" int sq_dot(sq_space* sp, const double* a_dev, const double* b_dev, double* out_host, void* stream) {
   if (!sp || !a_dev || !b_dev || !out_host) return SQ_ERR_INVALID;
   SQ_CUDA(cudaSetDevice(sp->device));

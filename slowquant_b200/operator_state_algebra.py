@@ -408,6 +408,31 @@ def ups_gradient_sweep(
     return g, _from_device(b, b_np), _from_device(k, k_np)
 
 
+def ups_energy_and_gradient(
+    ref_state, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, hamiltonian: ActiveSpaceHamiltonian,
+    want_gradient: bool = True,
+) -> tuple[float, np.ndarray | None]:
+    r"""Energy and analytic theta gradient of :math:`U(\theta)|\text{ref}\rangle` in ONE library call
+    (``sq_ups_energy_grad``: state construction, sigma build, adjoint sweep and the fused reverse gradient sweep of
+    ups_wavefunction.py:1019-1142 stay on the device; only the scalar and the gradient come back)."""
+    lib = _lib.load()
+    lay = compile_layout(ci_info, ups_struct)
+    n = len(ups_struct.excitation_operator_type)
+    th = _thetas_array(thetas, n)
+    ref, _ = _to_device(ref_state, ci_info, copy=False)
+    e_core, h_eff, g_act = hamiltonian.folded_integrals()
+    ket, bra = torch.empty_like(ref), torch.empty_like(ref)
+    energy = C.c_double(0.0)
+    grad = np.zeros(n, dtype=np.float64) if want_gradient else None
+    _lib.check(
+        lib.sq_ups_energy_grad(
+            ci_info._handle, lay, th.ctypes.data_as(_PD), e_core, h_eff.ctypes.data_as(_PD), g_act.ctypes.data_as(_PD),
+            _ptr(ref), _ptr(ket), _ptr(bra), C.byref(energy), grad.ctypes.data_as(_PD) if want_gradient else None, _stream(),
+        )
+    )
+    return float(energy.value), grad
+
+
 def reduced_density_matrices(bra, ket, ci_info: CI_Info, want_rdm2: bool = True):
     r"""Active-space (transition) RDMs in one pass over the vector (replaces the n^4/4 expectation_value
     calls of ups_wavefunction.py:409-476):

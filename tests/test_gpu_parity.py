@@ -756,3 +756,28 @@ def test_rdm3_rdm4_against_reference(sq, golden):
     th = WF3.thetas
     WF3.thetas = [t + 0.1 for t in th]      # the setter drops the cached higher RDMs
     assert np.max(np.abs(WF3.rdm3 - g["cas43_rdm3"])) > 1e-4
+
+
+def test_fused_energy_gradient_call(sq, golden):
+    """sq_ups_energy_grad (one C-ABI call for _calc_energy_optimization + _calc_gradient_optimization,
+    ups_wavefunction.py:1019-1142) against the reference's energy and analytic theta gradient on H2O tUPS(4,4) and
+    fUCCSD(4,4) (sa-free generic excitations), and against the separately composed calls."""
+    arrays, meta, _ = golden
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.operators import hamiltonian_0i_0a
+    from slowquant_b200.ups_wavefunction import WaveFunctionUPS
+
+    ints = ArrayIntegrals(arrays["h2o_h_mo"], arrays["h2o_g_mo"], num_elec=10)
+    eye = np.eye(arrays["h2o_h_mo"].shape[0])
+    for name, ansatz, options in (("tups44", "tUPS", {"n_layers": 2}), ("fuccsd44", "fUCCSD", {})):
+        WF = WaveFunctionUPS((4, 4), eye, ints, ansatz, dict(options), include_active_kappa=(name == "tups44"))
+        th = arrays[f"{name}_thetas"].tolist()
+        H = hamiltonian_0i_0a(WF.h_mo, WF.g_mo, WF.num_inactive_orbs, WF.num_active_orbs)
+        E, g = sq.osa.ups_energy_and_gradient(WF.csf_coeffs, WF.ci_info, th, WF.ups_layout, H)
+        assert abs(E - float(arrays[f"{name}_energy"])) < 1e-10
+        ref_grad = WF._calc_gradient_optimization(th, True, False)
+        assert np.max(np.abs(g - ref_grad)) < 1e-11
+        ref = arrays[f"{name}_gradient"]              # reference: [kappa..., theta...] when active kappa is included
+        assert np.max(np.abs(g - ref[len(ref) - len(g) :])) < 1e-10
+        E2, g2 = sq.osa.ups_energy_and_gradient(torch.from_numpy(WF.csf_coeffs).cuda(), WF.ci_info, th, WF.ups_layout, H, want_gradient=False)
+        assert g2 is None and abs(E2 - E) < 1e-13
