@@ -161,6 +161,11 @@ int sq_layout_needs_exchange(const sq_layout* lay, int first, int last);
  * process (own shard for r == rank).  Only orbital-pair operators (sa_single, pair double) may exchange. */
 int sq_ups_apply_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                       int dagger, double* const* shard_ptrs_host, void* stream);
+/* 1-/2-RDM contributions of THIS rank's rows of alpha-sharded vectors (same definitions as sq_rdm12; the caller sums the
+ * ranks' results, e.g. with an all-reduce).  *_ptrs_host[r] = base pointer of rank r's shard as mapped into this process;
+ * alpha partners on other ranks are read in place over NVLink.  All ranks must have finished writing their shards. */
+int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host,
+                  double* rdm1_host, double* rdm2_host, void* stream);
 
 /* ---- generic operator application (apply_operator_serial/threaded, :53-219; propagate_state
  *      inner loop, :596-628) -------------------------------------------------------------------- */

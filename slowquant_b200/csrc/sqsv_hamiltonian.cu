@@ -217,6 +217,51 @@ build_D_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W,
   }
 }
 
+// Alpha-sharded vector: the beta partner of a determinant lies in its own (local) row, the alpha partner in another row
+// that may belong to another GPU; it is read in place through the peer-mapped shard of its owner (NVLink), the same
+// mechanism the brick kernel uses for exchange operators.  rows [row_starts[r], row_starts[r+1]) live on rank r.
+struct PeerView {
+  const double* p[SQ_MAX_WORLD];
+  int64_t row_starts[SQ_MAX_WORLD + 1];
+  int world;
+};
+__global__ void __launch_bounds__(256)
+build_D_peer_kernel(PeerView pv, const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
+                    const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA,
+                    const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                    const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  const ERec* sm = stage_etab<false>(etab, n2);
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  if (j >= len) {
+    for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  for (int slot = 0; slot < n2; ++slot) {
+    double v = 0.0;
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      const int64_t gr = __ldg(rankA + sa);          // global row of the alpha partner
+      int o = 0;
+      while (o + 1 < pv.world && gr >= pv.row_starts[o + 1]) ++o;
+      const double x = pv.p[o][(gr - pv.row_starts[o]) * NB + ib];
+      v += (par ? -ra.s0 : ra.s0) * x;
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      const double x = IN[ia_loc * NB + __ldg(rankB + sb)];
+      v += (par ? -rb.s0 : rb.s0) * x;
+    }
+    D[(int64_t)slot * W + t] = v;
+  }
+}
+
 // Symmetrised panel for integrals with g_pqrs = g_pqsr: Dsym[slot(r,s)][t] = <J_t| E_rs + E_sr |in> for r > s and
 // <J_t| E_rr |in> for r = s, slot(r,s) = r (r + 1) / 2 + s  -- n (n + 1) / 2 rows instead of n^2.
 template <bool CONST>
@@ -539,8 +584,16 @@ static int launch_error(const char* what) {
 
 // D panel of [j0, j0 + W): n^2 rows, or the n (n + 1) / 2 symmetrised rows when sym
 static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D, int64_t j0, cudaStream_t st, bool use_const,
-                          bool sym = false) {
+                          bool sym = false, const PeerView* pv = nullptr) {
   const int n = sp->n_orb, n2 = n * n;
+  if (pv) {   // alpha-sharded vector: general n^2 panel, alpha partners through peer memory
+    const size_t smem_p = sizeof(ERec) * 2 * (size_t)n2;
+    allow_smem(build_D_peer_kernel, smem_p);
+    build_D_peer_kernel<<<(unsigned)(w->W / 256), 256, smem_p, st>>>(*pv, in, D, w->W, j0, sp->local_len(), w->d_etab, n2,
+                                                                     sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB,
+                                                                     sp->row_begin);
+    return launch_error("build_D_peer_kernel");
+  }
   if (g_rows_kernels && w->d_tabG) {
     const RowGrid g = row_grid(sp, w, j0);
     const size_t smem = rows_smem(sp);
@@ -720,10 +773,44 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   return SQ_OK;
 }
 
+static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev, const PeerView* pv_bra,
+                      const PeerView* pv_ket, double* rdm1_host, double* rdm2_host, void* stream);
+
 extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_dev, double* rdm1_host,
                         double* rdm2_host, void* stream) {
   if (!sp || !bra_dev || !ket_dev || !rdm1_host) return SQ_ERR_INVALID;
   SQ_CHECK(check_full_space(sp, "sq_rdm12"));
+  return rdm12_impl(sp, bra_dev, ket_dev, nullptr, nullptr, rdm1_host, rdm2_host, stream);
+}
+
+// This rank's PARTIAL sums over its rows of an alpha-sharded vector (the caller adds the ranks' results: everything is
+// linear in the partial sums).  *_ptrs_host[r] = base pointer of rank r's shard as mapped into this process.
+extern "C" int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host,
+                             double* rdm1_host, double* rdm2_host, void* stream) {
+  if (!sp || !bra_ptrs_host || !ket_ptrs_host || !rdm1_host) return SQ_ERR_INVALID;
+  if (sp->device < 0) return SQ_ERR_INVALID;
+  if (sp->world < 1 || sp->world > SQ_MAX_WORLD || (int)sp->row_starts.size() != sp->world + 1) {
+    sq_set_error("sq_rdm12_dist: the space has no row partition (sq_space_set_partition)");
+    return SQ_ERR_INVALID;
+  }
+  PeerView pb, pk;
+  pb.world = pk.world = sp->world;
+  for (int r = 0; r < SQ_MAX_WORLD; ++r) {
+    pb.p[r] = r < sp->world ? bra_ptrs_host[r] : nullptr;
+    pk.p[r] = r < sp->world ? ket_ptrs_host[r] : nullptr;
+  }
+  for (int r = 0; r <= SQ_MAX_WORLD; ++r) pb.row_starts[r] = pk.row_starts[r] = r <= sp->world ? sp->row_starts[r] : sp->row_starts[sp->world];
+  const int n = sp->n_orb, n2 = n * n;
+  if (sp->local_len() == 0) {   // a rank without rows contributes nothing
+    for (int i = 0; i < n2; ++i) rdm1_host[i] = 0.0;
+    if (rdm2_host) for (size_t i = 0; i < (size_t)n2 * n2; ++i) rdm2_host[i] = 0.0;
+    return SQ_OK;
+  }
+  return rdm12_impl(sp, pb.p[sp->rank], pk.p[sp->rank], &pb, &pk, rdm1_host, rdm2_host, stream);
+}
+
+static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev, const PeerView* pv_bra,
+                      const PeerView* pv_ket, double* rdm1_host, double* rdm2_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SQ_CUDA(cudaSetDevice(sp->device));
   const bool same = (bra_dev == ket_dev);
@@ -757,10 +844,10 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
     const int b = piped ? (int)(k & 1) : 0;
     double* Dket = w->d_D[b];
     if (piped && k >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // panels b are free once GEMM k-2 is done
-    SQ_CHECK(launch_build_D(sp, w, ket_dev, Dket, j0, s_build, use_const));
+    SQ_CHECK(launch_build_D(sp, w, ket_dev, Dket, j0, s_build, use_const, false, pv_ket));
     const double* Dbra = Dket;
     if (rdm2_host && !same) {
-      SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[2 + b], j0, s_build, use_const));
+      SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[2 + b], j0, s_build, use_const, false, pv_bra));
       Dbra = w->d_D[2 + b];
     }
     if (piped) {

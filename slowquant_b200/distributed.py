@@ -216,3 +216,40 @@ def dot_sharded(a: ShardedState, b: ShardedState) -> float:
     t = torch.tensor([local], dtype=torch.float64, device=a.local.device)
     dist.all_reduce(t)
     return float(t.item())
+
+
+def rdm12_sharded(bra: ShardedState, ket: ShardedState, want_rdm2: bool = True) -> tuple[np.ndarray, np.ndarray | None]:
+    """Active-space (transition) 1-/2-RDMs of alpha-sharded vectors: every rank contracts the determinants of its own rows
+    (alpha partners that live on another GPU are read in place through the peer mappings, ``sq_rdm12_dist``), the n^2 + n^4
+    partial sums are added with one all-reduce."""
+    lib = _lib.load()
+    sp = ket.space
+    n = sp.ci_info.num_active_orbs
+    d1 = np.zeros((n, n), dtype=np.float64)
+    d2 = np.zeros((n, n, n, n), dtype=np.float64) if want_rdm2 else None
+    PD = C.POINTER(C.c_double)
+    sp.barrier()        # every shard is complete before anybody reads it remotely
+    _lib.check(
+        lib.sq_rdm12_dist(
+            sp.ci_info._handle, bra._peer_ptrs, ket._peer_ptrs, d1.ctypes.data_as(PD), d2.ctypes.data_as(PD) if want_rdm2 else None,
+            osa._stream(),
+        )
+    )
+    sp.barrier()        # ... and nobody changes a shard while a neighbour may still be reading it
+    if sp.world > 1:
+        dev = ket.local.device
+        parts = [d1] if d2 is None else [d1, d2]
+        flat = torch.from_numpy(np.concatenate([p.ravel() for p in parts])).to(dev)
+        dist.all_reduce(flat)
+        flat = flat.cpu().numpy()
+        d1 = flat[: n * n].reshape(n, n)
+        if d2 is not None:
+            d2 = flat[n * n :].reshape(n, n, n, n)
+    return d1, d2
+
+
+def energy_sharded(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0) -> float:
+    r""":math:`\langle\Psi|H|\Psi\rangle = E_\text{core} + \sum h_{pq}\Gamma^1_{pq} + \tfrac12\sum g_{pqrs}\Gamma^2_{pqrs}` of a sharded vector
+    from its RDMs (the RDM route of ups_wavefunction.py:1041-1050 / density_matrix.py:139-178 in the active space)."""
+    d1, d2 = rdm12_sharded(state, state)
+    return float(e_core + np.sum(np.asarray(h_act) * d1) + 0.5 * np.sum(np.asarray(g_act) * d2))

@@ -21,7 +21,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     from slowquant_b200 import operator_state_algebra as osa
     from slowquant_b200.ci_spaces import get_indexing
-    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded
+    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded, energy_sharded, rdm12_sharded
     from slowquant_b200.util import UpsStructure
 
     worst = 0.0
@@ -57,12 +57,26 @@ def main():
         construct_ups_state_sharded(st, th, lay)
         torch.cuda.synchronize()
         err_hf = float(np.max(np.abs(st.local.cpu().numpy() - ref_hf[lo:hi]))) if hi > lo else 0.0
+        # RDMs and energy of the sharded vector (and a transition RDM between two sharded vectors) vs the single-GPU engine
+        d1_ref, d2_ref = osa.reduced_density_matrices(ref_hf, ref_hf, info)
+        d1, d2 = rdm12_sharded(st, st)
+        err_rdm = max(float(np.max(np.abs(d1 - d1_ref))), float(np.max(np.abs(d2 - d2_ref))))
+        h_syn = rng.normal(size=(n, n))
+        g_syn = 0.1 * rng.normal(size=(n, n, n, n))
+        e_ref = float(np.sum(h_syn * d1_ref) + 0.5 * np.sum(g_syn * d2_ref))
+        err_rdm = max(err_rdm, abs(energy_sharded(st, h_syn, g_syn) - e_ref))
+        st2 = sp.alloc_state()
+        st2.set_from_full(full)
+        t1_ref, t2_ref = osa.reduced_density_matrices(full, ref_hf, info)
+        t1, t2 = rdm12_sharded(st2, st)
+        err_rdm = max(err_rdm, float(np.max(np.abs(t1 - t1_ref))), float(np.max(np.abs(t2 - t2_ref))))
+        st2.close()
         st.close()
-        e = torch.tensor([err, err_d, err_hf, abs(nrm - 1.0)], dtype=torch.float64, device="cuda")
+        e = torch.tensor([err, err_d, err_hf, abs(nrm - 1.0), err_rdm], dtype=torch.float64, device="cuda")
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(f"CAS({na + nb},{n}) L={L} world={world}: max|diff| fwd {e[0]:.2e} dagger {e[1]:.2e} hf {e[2]:.2e} "
-                  f"|norm-1| {e[3]:.2e}", flush=True)
+                  f"|norm-1| {e[3]:.2e} rdm/energy {e[4]:.2e}", flush=True)
         worst = max(worst, float(e.max()))
     dist.barrier()
     dist.destroy_process_group()

@@ -2,6 +2,11 @@
 (norm conservation, U^dagger U = 1 round trip back to the HF determinant) plus timing.
 
     python -m torch.distributed.run --nproc-per-node 8 tools/sharded_check.py 20 2
+    python -m torch.distributed.run --nproc-per-node 2 tools/sharded_check.py 18 2 energy
+
+With a third argument "energy": also <H> of the sharded vector from its RDMs (synthetic symmetric integrals), checked at
+the Hartree-Fock determinant against the closed form 2 sum_i h_ii + sum_ij (2 g_iijj - g_ijji), with Tr Gamma1 = N_e and
+sum_pq Gamma2[ppqq] = N_e (N_e - 1) on the correlated state.
 """
 import os
 import sys
@@ -21,7 +26,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
-    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded
+    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded, rdm12_sharded
     from slowquant_b200.util import UpsStructure
 
     ne = n // 2
@@ -46,6 +51,34 @@ def main():
     dist.barrier()
     dt = time.perf_counter() - t0
     norm2 = dot_sharded(st, st) ** 0.5
+    if len(sys.argv) > 3 and sys.argv[3] == "energy":
+        rng = np.random.default_rng(2024)
+        A = rng.normal(size=(n, n))
+        h = A + A.T
+        B = 0.1 * rng.normal(size=(n, n, n, n))
+        g = B + B.transpose(1, 0, 2, 3)
+        g = g + g.transpose(0, 1, 3, 2)
+        g = g + g.transpose(2, 3, 0, 1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        d1, d2 = rdm12_sharded(st, st)
+        t_rdm = time.perf_counter() - t0
+        energy = float(np.sum(h * d1) + 0.5 * np.sum(g * d2))
+        hf = sp.alloc_state()
+        hf.set_determinant(0)
+        h1, h2 = rdm12_sharded(hf, hf)
+        hf.close()
+        e_hf = float(np.sum(h * h1) + 0.5 * np.sum(g * h2))
+        occ = range(ne)
+        e_hf_exact = sum(2 * h[i, i] for i in occ) + sum(2 * g[i, i, j, j] - g[i, j, j, i] for i in occ for j in occ)
+        if rank == 0:
+            print(
+                f"CAS({n},{n}) world={world} sharded 1-/2-RDM: {t_rdm:.2f} s;  E = {energy:.12f};  Tr G1 = {np.trace(d1):.12f} "
+                f"(N_e = {2 * ne});  sum G2[ppqq] = {np.einsum('ppqq->', d2):.10f} (N_e (N_e - 1) = {2 * ne * (2 * ne - 1)});  "
+                f"E_HF {e_hf:.12f} vs closed form {e_hf_exact:.12f} (diff {e_hf - e_hf_exact:.2e})",
+                flush=True,
+            )
     # undo both applications: must return to the HF determinant
     construct_ups_state_sharded(st, th, lay, dagger=True)
     construct_ups_state_sharded(st, th, lay, dagger=True)
