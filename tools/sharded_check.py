@@ -51,7 +51,7 @@ def main():
     dist.barrier()
     dt = time.perf_counter() - t0
     norm2 = dot_sharded(st, st) ** 0.5
-    if len(sys.argv) > 3 and sys.argv[3] == "energy":
+    if len(sys.argv) > 3 and sys.argv[3] in ("energy", "energy-nohf"):
         rng = np.random.default_rng(2024)
         A = rng.normal(size=(n, n))
         h = A + A.T
@@ -65,18 +65,22 @@ def main():
         d1, d2 = rdm12_sharded(st, st)
         t_rdm = time.perf_counter() - t0
         energy = float(np.sum(h * d1) + 0.5 * np.sum(g * d2))
-        hf = sp.alloc_state()
-        hf.set_determinant(0)
-        h1, h2 = rdm12_sharded(hf, hf)
-        hf.close()
-        e_hf = float(np.sum(h * h1) + 0.5 * np.sum(g * h2))
-        occ = range(ne)
-        e_hf_exact = sum(2 * h[i, i] for i in occ) + sum(2 * g[i, i, j, j] - g[i, j, j, i] for i in occ for j in occ)
+        hf_msg = ""
+        if sys.argv[3] == "energy":     # second vector + second RDM pass; "energy-nohf" skips it
+            hf = sp.alloc_state()
+            hf.set_determinant(0)
+            h1, h2 = rdm12_sharded(hf, hf)
+            hf.close()
+            e_hf = float(np.sum(h * h1) + 0.5 * np.sum(g * h2))
+            occ = range(ne)
+            e_hf_exact = sum(2 * h[i, i] for i in occ) + sum(2 * g[i, i, j, j] - g[i, j, j, i] for i in occ for j in occ)
+            hf_msg = f";  E_HF {e_hf:.12f} vs closed form {e_hf_exact:.12f} (diff {e_hf - e_hf_exact:.2e})"
         if rank == 0:
+            sym = float(np.max(np.abs(d1 - d1.T)))
             print(
                 f"CAS({n},{n}) world={world} sharded 1-/2-RDM: {t_rdm:.2f} s;  E = {energy:.12f};  Tr G1 = {np.trace(d1):.12f} "
                 f"(N_e = {2 * ne});  sum G2[ppqq] = {np.einsum('ppqq->', d2):.10f} (N_e (N_e - 1) = {2 * ne * (2 * ne - 1)});  "
-                f"E_HF {e_hf:.12f} vs closed form {e_hf_exact:.12f} (diff {e_hf - e_hf_exact:.2e})",
+                f"max|G1 - G1^T| = {sym:.1e}" + hf_msg,
                 flush=True,
             )
     # undo both applications: must return to the HF determinant
