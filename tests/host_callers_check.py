@@ -1,0 +1,136 @@
+"""Subprocess body of tests/test_host_callers.py: host logic of the engine's callers on the oracle-backed stand-in
+(tests/host_standin.py), against the reference goldens.  Prints one line per check and HOST_CALLERS_OK at the end."""
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import host_standin  # noqa: E402  (patches slowquant_b200 in this process)
+
+import slowquant_b200.linear_response._panels as pn  # noqa: E402
+import slowquant_b200.operator_state_algebra as osa  # noqa: E402
+import slowquant_b200.sa_ups_wavefunction as sam  # noqa: E402
+from slowquant_b200 import operators as mops  # noqa: E402
+from slowquant_b200.ci_spaces import get_indexing_extended  # noqa: E402
+from slowquant_b200.integral_manager import ArrayIntegrals  # noqa: E402
+from slowquant_b200.ups_wavefunction import WaveFunctionUPS  # noqa: E402
+from slowquant_b200.util import UpsStructure  # noqa: E402
+
+pn.torch = sam.torch = host_standin.TorchProxy()
+G = os.path.join(HERE, "golden")
+worst = {}
+
+
+def record(name, value, tol):
+    value = float(value)
+    print(f"{name:48s} {value:9.2e}  (tol {tol:.0e})", flush=True)
+    worst[name] = (value, tol)
+
+
+def d(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+
+# ---- linear response: all eight parametrisations on LiH tUPS(2,2) (and naive on H2O tUPS(4,4) with "h2o") ----
+if which in ("all", "lr", "h2o"):
+    g1 = np.load(os.path.join(G, "golden_config1.npz"))
+    gv = np.load(os.path.join(G, "golden_lr_variants.npz"))
+    systems = [("lih", {"n_layers": 1, "skip_last_singles": True})] + ([("h2o", {"n_layers": 3})] if which == "h2o" else [])
+    variants = [("naive", "naive"), ("proj", "projected"), ("st", "statetransfer"), ("sc", "selfconsistent"), ("allst", "allstatetransfer"),
+                ("allsc", "allselfconsistent"), ("allproj", "allprojected"), ("projst", "projected_statetransfer")]
+    for name, options in systems:
+        pre = name + "_"
+        ints = ArrayIntegrals(g1[pre + "h_ao"], g1[pre + "eri_ao"], int(g1[pre + "num_elec"]), dipole=tuple(g1[pre + "dipole_ao"]))
+        WF = WaveFunctionUPS(tuple(int(x) for x in g1[pre + "cas"]), g1[pre + "c_mo"], ints, "tUPS", dict(options), include_active_kappa=True)
+        WF.thetas = g1[pre + "thetas"].tolist()
+        record(f"{name} energy", abs(WF.energy_elec - float(g1[pre + "energy"])), 1e-10)
+        for tag, modname in variants:
+            keys = ("A", "B", "Sigma", "Delta", "excitation_energies", "norms", "oscillator_strengths")
+            gold = {k: (g1[pre + k] if tag == "naive" else gv[f"{name}_{tag}_{k}"]) for k in keys}
+            mod = importlib.import_module("slowquant_b200.linear_response." + modname)
+            mod.torch = host_standin.TorchProxy()
+            with contextlib.redirect_stdout(io.StringIO()):
+                LR = mod.LinearResponse(WF, "SD")
+                LR.calc_excitation_energies()
+                osc = LR.get_oscillator_strength()
+            record(f"{name} {modname} A/B/Sigma/Delta", max(d(getattr(LR, k), gold[k]) for k in ("A", "B", "Sigma", "Delta")), 1e-10)
+            record(f"{name} {modname} excitation energies", d(LR.excitation_energies, gold["excitation_energies"]), 1e-8)
+            record(f"{name} {modname} norms / osc. strengths", max(d(LR.get_excited_state_norm(), gold["norms"]), d(osc, gold["oscillator_strengths"])), 1e-8)
+
+# ---- state-averaged UPS at the reference's parameters ----
+if which in ("all", "saups"):
+    g = np.load(os.path.join(G, "golden_saups.npz"))
+    s2 = 2 ** (-1 / 2)
+    cases = {
+        "h2": (([[1], [s2, -s2], [1]], [["1100"], ["1001", "0110"], ["0011"]]), {"n_layers": 1, "skip_last_singles": True}),
+        "h3": (([[1], [s2, -s2], [s2, -s2]], [["110000"], ["100100", "011000"], ["100001", "010010"]]), {"n_layers": 2, "skip_last_singles": True}),
+    }
+    for name, (states, options) in cases.items():
+        pre = name + "_"
+        ints = ArrayIntegrals(g[pre + "h_ao"], g[pre + "eri_ao"], int(g[pre + "num_elec"]), dipole=tuple(g[pre + "dipole_ao"]))
+        WF = sam.WaveFunctionSAUPS(tuple(int(x) for x in g[pre + "cas"]), g[pre + "c_mo"], ints, states, "tUPS", dict(options), include_active_kappa=True)
+        WF.thetas = g[pre + "thetas"].tolist()
+        record(f"saups {name} ci / rdm1 / rdm2", max(d(WF.ci_coeffs, g[pre + "ci"]), d(WF.rdm1, g[pre + "rdm1"]), d(WF.rdm2, g[pre + "rdm2"])), 1e-10)
+        record(f"saups {name} energies", max(abs(WF.sa_energy - float(g[pre + "sa_energy"])), d(WF.energy_states, g[pre + "energy_states"])), 1e-10)
+        record(f"saups {name} oscillator strengths", d(WF.get_oscillator_strenghts(), g[pre + "oscillator_strengths"]), 1e-9)
+        th = g[pre + "pert_thetas"].tolist()
+        params = [0.0] * len(WF.kappa_idx) + th
+        WF._old_opt_parameters = np.zeros(len(params)) + 10**20
+        e = WF._calc_energy_optimization(params, True, True)
+        grad = WF._calc_gradient_optimization(params, True, True)
+        record(f"saups {name} energy / gradient at perturbed theta", max(abs(e - float(g[pre + "pert_energy"])), d(grad, g[pre + "pert_gradient"])), 1e-10)
+        roto = WF._calc_energy_rotosolve_optimization(th, g[pre + "rs_shifts"].tolist(), int(g[pre + "rs_idx"]))
+        record(f"saups {name} rotosolve energies", d(roto, g[pre + "rs_energies"]), 1e-10)
+
+# ---- extended spaces: embedding, projection (do_unsafe), operator lists ----
+if which in ("all", "extended"):
+    g = np.load(os.path.join(G, "golden_extended.npz"))
+    for tag in ("a", "b"):
+        pre = tag + "_"
+        sp = tuple(int(x) for x in g[pre + "space"])
+        nI, nA, nV = sp[:3]
+        ci = get_indexing_extended(*sp)
+        lay = UpsStructure()
+        lay.create_tiled(nA, {"n_layers": int(g[pre + "n_layers"]), "do_tups": True})
+        th, state = g[pre + "thetas"].tolist(), g[pre + "state"]
+        q = mops.G1_sa(0, nI + nA + nV - 1)
+        E = mops.Epq(nI, nI + 1) * mops.Epq(nI + 1, nI) + 0.5 * mops.Epq(nI, nI)
+        errs = [
+            d(osa.construct_ups_state(state, ci, th, lay), g[pre + "U_state"]),
+            d(osa.construct_ups_state(state, ci, th, lay, dagger=True), g[pre + "Ud_state"]),
+            d(osa.propagate_unitary(state, 3, ci, th, lay), g[pre + "unitary3"]),
+            d(osa.get_grad_action(state, 1, ci, lay), g[pre + "grad1"]),
+            d(osa.propagate_state([q.dagger, q], state, ci, do_unsafe=True), g[pre + "qd_q_state"]),
+            d(osa.propagate_state(["U", q], state, ci, th, lay, do_unsafe=True), g[pre + "U_q_state"]),
+            abs(osa.expectation_value(state, ["Ud", E, "U"], state, ci, th, lay) - float(g[pre + "expval"])),
+        ]
+        record(f"extended space {tag}", max(errs), 1e-12)
+        raised = False
+        try:
+            osa.propagate_state([q], state, ci)
+        except KeyError:
+            raised = True
+        record(f"extended space {tag} KeyError as the reference", float(raised != bool(int(g[pre + "q_raises"]))), 0.5)
+
+# ---- rdm3 / rdm4 contractions ----
+if which in ("all", "rdm34"):
+    g0 = np.load(os.path.join(G, "golden.npz"))
+    g = np.load(os.path.join(G, "golden_rdm34.npz"))
+    ints = ArrayIntegrals(g0["h2o_h_mo"], g0["h2o_g_mo"], num_elec=10)
+    eye = np.eye(g0["h2o_h_mo"].shape[0])
+    WF3 = WaveFunctionUPS((4, 3), eye, ints, "tUPS", {"n_layers": 2}, include_active_kappa=True)
+    WF3.thetas = g["cas43_thetas"].tolist()
+    record("rdm3 / rdm4 CAS(4,3)", max(d(WF3.rdm3, g["cas43_rdm3"]), d(WF3.rdm4, g["cas43_rdm4"])), 1e-10)
+
+bad = {k: v for k, v in worst.items() if not v[0] <= v[1]}
+if bad:
+    print("HOST_CALLERS_FAILED", bad, flush=True)
+    sys.exit(1)
+print("HOST_CALLERS_OK", len(worst), "checks", flush=True)
