@@ -14,7 +14,6 @@ one ``[n_states, N_det]`` fp64 matrix; every state shares the ansatz unitary, so
 from __future__ import annotations
 
 from collections.abc import Sequence
-from functools import partial
 from typing import Any
 
 import numpy as np
@@ -25,7 +24,6 @@ from slowquant_b200 import operator_state_algebra as osa
 from slowquant_b200.density_matrix import get_orbital_gradient
 from slowquant_b200.integral_manager import one_electron_integral_transform
 from slowquant_b200.operators import hamiltonian_0i_0a, one_elec_op_0i_0a
-from slowquant_b200.optimizers import Optimizers
 from slowquant_b200.ups_wavefunction import WaveFunctionUPS, symmetrize_rdm2_like_reference
 
 _SA_ANSATZE = ("tups", "qnp", "fucc", "ksafupccgsd", "safuccsd", "ksasdsfupccgsd")
@@ -267,26 +265,6 @@ class WaveFunctionSAUPS(WaveFunctionUPS):
         self.num_energy_evals += self.num_states
         return energies
 
-    def _optimizer(self, name: str, theta: bool, kappa: bool, tol: float, maxiter: int, silent: bool = False) -> Optimizers:
-        return Optimizers(
-            partial(self._calc_energy_optimization, theta_optimization=theta, kappa_optimization=kappa),
-            name,
-            grad=partial(self._calc_gradient_optimization, theta_optimization=theta, kappa_optimization=kappa),
-            maxiter=maxiter,
-            tol=tol,
-            is_silent=silent,
-            energy_eval_callback=lambda: self.num_energy_evals,
-        )
-
-    def _rotosolve_options(self, name: str):
-        if name.lower() != "rotosolve":
-            return None
-        return {
-            "R": self.ups_layout.grad_param_R,
-            "param_names": self.ups_layout.param_names,
-            "f_rotosolve_optimized": self._calc_energy_rotosolve_optimization,
-        }
-
     def run_wf_optimization_1step(self, optimizer_name: str, orbital_optimization: bool = False, tol: float = 1e-10, maxiter: int = 1000) -> None:
         """sa_ups_wavefunction.py:640-739."""
         if optimizer_name.lower() == "rotosolve" and orbital_optimization and len(self.kappa) != 0:
@@ -307,33 +285,8 @@ class WaveFunctionSAUPS(WaveFunctionUPS):
         self._do_state_ci()
         self._sa_energy = res.fun
 
-    def run_wf_optimization_2step(
-        self, optimizer_name: str, orbital_optimization: bool = False, tol: float = 1e-10, maxiter: int = 1000,
-        is_silent_subiterations: bool = False,
-    ) -> None:
-        """Alternating ansatz / orbital optimisation (sa_ups_wavefunction.py:517-638)."""
-        e_old = 1e12
-        res = None
-        for _ in range(int(maxiter)):
-            optimizer = self._optimizer(optimizer_name, True, False, tol, maxiter, is_silent_subiterations)
-            self._old_opt_parameters = np.zeros(len(self._thetas)) + 10**20
-            self._E_opt_old = 0.0
-            res = optimizer.minimize(self.thetas, extra_options=self._rotosolve_options(optimizer_name))
-            self.thetas = res.x.tolist()
-            if not (orbital_optimization and len(self.kappa) != 0):
-                if orbital_optimization:
-                    print("WARNING: No orbital optimization performed, because there is no non-redundant orbital parameters")
-                break
-            optimizer = self._optimizer("l-bfgs-b", False, True, tol, maxiter, is_silent_subiterations)
-            self._old_opt_parameters = np.zeros(len(self.kappa_idx)) + 10**20
-            self._E_opt_old = 0.0
-            res = optimizer.minimize([0.0] * len(self.kappa_idx))
-            for i in range(len(self._kappa)):
-                self._kappa[i] = 0.0
-                self._kappa_old[i] = 0.0
-            e_new = res.fun
-            if abs(e_new - e_old) < tol:
-                break
-            e_old = e_new
+    def _finish_optimization(self, energy: float) -> None:
+        """After the shared two-step driver (ups_wavefunction.run_wf_optimization_2step): subspace diagonalisation, then
+        the state-averaged energy of the optimiser (sa_ups_wavefunction.py:636-638)."""
         self._do_state_ci()
-        self._sa_energy = res.fun
+        self._sa_energy = energy

@@ -433,6 +433,88 @@ class WaveFunctionUPS:
         self.thetas = list(res.x[nk:])
         self._energy_elec = None
 
+    # ---- pieces shared by the one- and two-step drivers (and by the state-averaged subclass) ----
+    def _optimizer(self, name: str, theta: bool, kappa: bool, tol: float, maxiter: int, silent: bool = False):
+        from functools import partial
+
+        from slowquant_b200.optimizers import Optimizers
+
+        return Optimizers(
+            partial(self._calc_energy_optimization, theta_optimization=theta, kappa_optimization=kappa),
+            name,
+            grad=partial(self._calc_gradient_optimization, theta_optimization=theta, kappa_optimization=kappa),
+            maxiter=maxiter,
+            tol=tol,
+            is_silent=silent,
+            energy_eval_callback=lambda: self.num_energy_evals,
+        )
+
+    def _rotosolve_options(self, name: str):
+        if name.lower() != "rotosolve":
+            return None
+        return {
+            "R": self.ups_layout.grad_param_R,
+            "param_names": self.ups_layout.param_names,
+            "f_rotosolve_optimized": self._calc_energy_rotosolve_optimization,
+        }
+
+    def _finish_optimization(self, energy: float) -> None:
+        self._energy_elec = energy
+
+    def run_wf_optimization_2step(
+        self, optimizer_name: str, orbital_optimization: bool = False, tol: float = 1e-10, maxiter: int = 1000,
+        is_silent_subiterations: bool = False,
+    ) -> None:
+        """Alternate ansatz (theta) and orbital (kappa, L-BFGS-B) optimisations until the energy stops changing
+        (ups_wavefunction.py:799-918; sa_ups_wavefunction.py:517-638 for the state-averaged class)."""
+        import time
+
+        print("### Parameters information:")
+        if orbital_optimization:
+            print(f"### Number kappa: {len(self.kappa)}")
+        print(f"### Number theta: {self.ups_layout.n_params}")
+        print("Full optimization")
+        print("Iteration # | Iteration time [s] | Electronic energy [Hartree] | Energy measurement #")
+        e_old = 1e12
+        res = None
+        for full_iter in range(int(maxiter)):
+            full_start = time.time()
+            optimizer = self._optimizer(optimizer_name, True, False, tol, maxiter, is_silent_subiterations)
+            self._old_opt_parameters = np.zeros(len(self._thetas)) + 10**20
+            self._E_opt_old = 0.0
+            res = optimizer.minimize(self.thetas, extra_options=self._rotosolve_options(optimizer_name))
+            self.thetas = res.x.tolist()
+            if not (orbital_optimization and len(self.kappa) != 0):
+                # without orbital parameters the ansatz optimisation already is the answer
+                if orbital_optimization:
+                    print("WARNING: No orbital optimization performed, because there is no non-redundant orbital parameters.")
+                break
+            optimizer = self._optimizer("l-bfgs-b", False, True, tol, maxiter, is_silent_subiterations)
+            self._old_opt_parameters = np.zeros(len(self.kappa_idx)) + 10**20
+            self._E_opt_old = 0.0
+            res = optimizer.minimize([0.0] * len(self.kappa_idx))
+            for i in range(len(self._kappa)):   # the expansion point has moved with every evaluation (kappa setter)
+                self._kappa[i] = 0.0
+                self._kappa_old[i] = 0.0
+            e_new = res.fun
+            print(f"{str(full_iter + 1).center(11)} | {f'{time.time() - full_start:7.2f}'.center(18)} | {f'{e_new:3.12f}'.center(27)} | {str(self.num_energy_evals).center(11)}")
+            if abs(e_new - e_old) < tol:
+                break
+            e_old = e_new
+        self._finish_optimization(res.fun)
+
+    def check_orthonormality(self, overlap_integral: np.ndarray) -> None:
+        """Print max|C^T S C - 1| (ups_wavefunction.py:756-768)."""
+        S_ortho = one_electron_integral_transform(self.c_mo, overlap_integral)
+        print("Max ortho-normal diff:", np.max(np.abs(S_ortho - np.identity(len(S_ortho)))))
+
+    def _get_hamiltonian(self, qiskit_form: bool = False):
+        """Energy Hamiltonian folded onto the active space as explicit strings (ups_wavefunction.py:786-797)."""
+        if qiskit_form:
+            raise NotImplementedError("the Qiskit form belongs to the Qiskit interface, which is outside this engine's scope")
+        H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
+        return H.get_folded_operator(self.num_inactive_orbs, self.num_active_orbs, self.num_virtual_orbs)
+
     def _run_optimizer_by_name(self, optimizer_name: str, orbital_optimization: bool, tol: float, maxiter: int) -> None:
         """RotoSolve / gradient-free SciPy methods through the Optimizers front end (ups_wavefunction.py:934-1017)."""
         from functools import partial

@@ -129,6 +129,29 @@ if which in ("all", "rdm34"):
     WF3.thetas = g["cas43_thetas"].tolist()
     record("rdm3 / rdm4 CAS(4,3)", max(d(WF3.rdm3, g["cas43_rdm3"]), d(WF3.rdm4, g["cas43_rdm4"])), 1e-10)
 
+# ---- two-step optimisation drivers (host control flow around the engine) ----
+if which in ("all", "opt2"):
+    g1 = np.load(os.path.join(G, "golden_config1.npz"))
+    ints = ArrayIntegrals(g1["lih_h_ao"], g1["lih_eri_ao"], int(g1["lih_num_elec"]), dipole=tuple(g1["lih_dipole_ao"]))
+    WF = WaveFunctionUPS((2, 2), g1["lih_c_mo_rhf"], ints, "tUPS", {"n_layers": 1, "skip_last_singles": True}, include_active_kappa=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        WF.run_wf_optimization_2step("BFGS", True, is_silent_subiterations=True)
+        WF.check_orthonormality(np.linalg.inv(g1["lih_c_mo_rhf"] @ g1["lih_c_mo_rhf"].T))
+    # the reference's ONE-step optimisation of the same wave function (golden_config1) reaches the same minimum
+    record("UPS two-step energy vs reference one-step minimum", abs(WF.energy_elec - float(g1["lih_energy"])), 1e-7)
+    H = WF._get_hamiltonian()
+    record("_get_hamiltonian expectation value", abs(osa.expectation_value(WF.ci_coeffs, [H], WF.ci_coeffs, WF.ci_info, do_folding=False) - WF.energy_elec), 1e-10)
+    g = np.load(os.path.join(G, "golden_saups.npz"))
+    s2 = 2 ** (-1 / 2)
+    states = ([[1], [s2, -s2], [s2, -s2]], [["110000"], ["100100", "011000"], ["100001", "010010"]])
+    ints = ArrayIntegrals(g["h3_h_ao"], g["h3_eri_ao"], int(g["h3_num_elec"]), dipole=tuple(g["h3_dipole_ao"]))
+    WS = sam.WaveFunctionSAUPS((2, 3), g["h3_c_mo"], ints, states, "tUPS", {"n_layers": 2, "skip_last_singles": True}, include_active_kappa=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        WS.run_wf_optimization_2step("BFGS", True, is_silent_subiterations=True)
+    # tests/test_unitary_product_state.py:238-242
+    record("SA-UPS two-step excitation energies (reference literals)", d(WS.excitation_energies, [0.838466, 0.838466]), 1e-6)
+    record("SA-UPS two-step oscillator strengths (reference literals)", d(WS.get_oscillator_strenghts(), [0.7569, 0.7569]), 1e-3)
+
 bad = {k: v for k, v in worst.items() if not v[0] <= v[1]}
 if bad:
     print("HOST_CALLERS_FAILED", bad, flush=True)
