@@ -101,3 +101,14 @@ def test_saups_input_validation(gs):
         WaveFunctionSAUPS((2, 2), c, ints, ([[1]], [["1100"]]), "tUPS", {"n_layers": 1, "do_pp": True})
     with pytest.raises(ValueError, match="unknown ansatz"):
         WaveFunctionSAUPS((2, 2), c, ints, ([[1]], [["1100"]]), "fUCCSD")
+
+
+def test_saups_h3_two_step_optimisation_reaches_reference_literals(gs):
+    """tests/test_unitary_product_state.py:201-242 (two-step driver, started from the reference's converged orbitals)."""
+    WF = _wf(gs, "h3")
+    with contextlib.redirect_stdout(io.StringIO()):
+        WF.run_wf_optimization_2step("BFGS", True, is_silent_subiterations=True)
+    assert abs(WF.excitation_energies[0] - 0.838466) < 1e-6
+    assert abs(WF.excitation_energies[1] - 0.838466) < 1e-6
+    osc = WF.get_oscillator_strenghts()
+    assert abs(osc[0] - 0.7569) < 1e-3 and abs(osc[1] - 0.7569) < 1e-3
