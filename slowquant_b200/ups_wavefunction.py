@@ -452,6 +452,8 @@ class WaveFunctionUPS:
     def _rotosolve_options(self, name: str):
         if name.lower() != "rotosolve":
             return None
+        if self.ups_layout is None:
+            raise ValueError("RotoSolve needs a product ansatz (it is not defined for the non-factorised UCC)")
         return {
             "R": self.ups_layout.grad_param_R,
             "param_names": self.ups_layout.param_names,
@@ -472,7 +474,7 @@ class WaveFunctionUPS:
         print("### Parameters information:")
         if orbital_optimization:
             print(f"### Number kappa: {len(self.kappa)}")
-        print(f"### Number theta: {self.ups_layout.n_params}")
+        print(f"### Number theta: {len(self._thetas)}")
         print("Full optimization")
         print("Iteration # | Iteration time [s] | Electronic energy [Hartree] | Energy measurement #")
         e_old = 1e12

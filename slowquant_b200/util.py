@@ -7,7 +7,7 @@ the orderings are restated with itertools instead of nested index loops.
 from __future__ import annotations
 
 import itertools
-from collections.abc import Generator, Sequence
+from collections.abc import Sequence
 from typing import Any
 
 
