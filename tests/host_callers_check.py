@@ -129,6 +129,26 @@ if which in ("all", "rdm34"):
     WF3.thetas = g["cas43_thetas"].tolist()
     record("rdm3 / rdm4 CAS(4,3)", max(d(WF3.rdm3, g["cas43_rdm3"]), d(WF3.rdm4, g["cas43_rdm4"])), 1e-10)
 
+# ---- UCC wave function + linear response (UccStructure path of the "U" / "Ud" panels) ----
+if which in ("all", "ucc"):
+    from slowquant_b200.ucc_wavefunction import WaveFunctionUCC
+
+    g = np.load(os.path.join(G, "golden_h4_ucc.npz"))
+    ints = ArrayIntegrals(g["h_ao"], g["eri_ao"], 4, dipole=tuple(g["dipole_ao"]))
+    WF = WaveFunctionUCC((4, 4), g["c_mo_rhf"], ints, "SD")
+    WF.thetas = g["thetas"].tolist()
+    record("ucc H4 ci / energy", max(d(WF.ci_coeffs, g["ci"]), abs(WF.energy_elec - float(g["energy"]))), 1e-10)
+    for tag, modname in (("naive", "naive"), ("sc", "selfconsistent")):
+        mod = importlib.import_module("slowquant_b200.linear_response." + modname)
+        mod.torch = host_standin.TorchProxy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            LR = mod.LinearResponse(WF, "SD")
+            LR.calc_excitation_energies()
+            osc = LR.get_oscillator_strength()
+        record(f"ucc H4 {modname} A/B/Sigma/Delta", max(d(getattr(LR, k), g[f"{tag}_{k}"]) for k in ("A", "B", "Sigma", "Delta")), 1e-9)
+        record(f"ucc H4 {modname} excitation energies", d(LR.excitation_energies, g[f"{tag}_excitation_energies"]), 1e-8)
+        record(f"ucc H4 {modname} oscillator strengths", d(osc, g[f"{tag}_oscillator_strengths"]), 1e-7)
+
 # ---- two-step optimisation drivers (host control flow around the engine) ----
 if which in ("all", "opt2"):
     g1 = np.load(os.path.join(G, "golden_config1.npz"))

@@ -87,3 +87,28 @@ def reduced_density_matrices(bra, ket, ci, want_rdm2=True):
                         d2[p,q,r,s] = Eb[p][q] @ E[r][s] - (d1[p,s] if q == r else 0.0)
     return d1, d2
 osa.reduced_density_matrices = reduced_density_matrices
+
+
+# matrix-free exp(T)|state> of ucc_state.py -> dense matrix of T from the oracle + scipy (small spaces only)
+import scipy.sparse.linalg  # noqa: E402
+
+import slowquant_b200.ucc_state as _ucc_state  # noqa: E402
+import slowquant_b200.ucc_wavefunction as _ucc_wf  # noqa: E402
+
+
+def expm_multiply_operator(T, state, ci_info, scale=1.0):
+    n = state.numel()
+    sp = space_of(ci_info)
+    M = np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        M[:, j] = orc.propagate_state([dict(T.operators)], e, sp, do_folding=False)
+    return torch.from_numpy(np.asarray(scipy.sparse.linalg.expm_multiply(scale * M, state.numpy())))
+
+
+_ucc_state.expm_multiply_operator = expm_multiply_operator
+_ucc_wf.expm_multiply_operator = expm_multiply_operator
+for _m in (_ucc_state, _ucc_wf):
+    if hasattr(_m, "torch"):
+        _m.torch = TorchProxy()

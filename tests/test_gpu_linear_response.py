@@ -173,3 +173,38 @@ def test_all_statetransfer_reference_literals(g1):
     assert np.allclose(LR.excitation_energies, solutions, atol=1e-3)
     ref_osc = [0.06668878, 0.33360367, 0.33360367, 0.30588158, 0.02569977, 0.06690658, 0.13411942, 0.13411942, 0.04689274]
     assert np.max(np.abs(osc - np.array(ref_osc))) < 1e-3
+
+
+def test_ucc_wavefunction_linear_response(g1):
+    """The reference's UCC + LR test (tests/test_unitary_coupled_cluster.py:281-363: H4/STO-3G UCCSD(4,4), naive and
+    self-consistent LR) at the reference's converged thetas: the "U"/"Ud" panels go through the matrix-free exponential of
+    the non-factorised UCC; matrices element-wise against the reference, spectra also against the literals of its test."""
+    import contextlib
+    import io
+
+    from slowquant_b200.integral_manager import ArrayIntegrals
+    from slowquant_b200.linear_response import naive, selfconsistent
+    from slowquant_b200.ucc_wavefunction import WaveFunctionUCC
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_h4_ucc.npz"))
+    ints = ArrayIntegrals(g["h_ao"], g["eri_ao"], 4, dipole=tuple(g["dipole_ao"]))
+    WF = WaveFunctionUCC((4, 4), g["c_mo_rhf"], ints, "SD")
+    WF.thetas = g["thetas"].tolist()
+    assert np.max(np.abs(WF.ci_coeffs - g["ci"])) < 1e-10
+    assert abs(WF.energy_elec - float(g["energy"])) < 1e-10
+    literals = {
+        "naive": [0.162961, 0.418771, 0.550513, 0.585337, 0.600209, 0.602964, 0.680440, 0.705532, 0.805980, 0.843321,
+                  0.923462, 1.189881, 1.512350, 1.515402],
+        "sc": [0.162962, 0.385979, 0.516725, 0.585337, 0.600210, 0.602570, 0.671853, 0.705532, 0.805981, 0.843321,
+               0.923462, 1.189882, 1.512350, 1.515402],
+    }
+    for tag, mod in (("naive", naive), ("sc", selfconsistent)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            LR = mod.LinearResponse(WF, excitations="SD")
+            LR.calc_excitation_energies()
+            osc = LR.get_oscillator_strength()
+        for key in ("A", "B", "Sigma", "Delta"):
+            assert np.max(np.abs(getattr(LR, key) - g[f"{tag}_{key}"])) < 1e-9, (tag, key)
+        assert np.max(np.abs(LR.excitation_energies - g[f"{tag}_excitation_energies"])) < 1e-8
+        assert np.max(np.abs(osc - g[f"{tag}_oscillator_strengths"])) < 1e-7
+        assert np.max(np.abs(LR.excitation_energies - np.array(literals[tag]))) < 1e-5
