@@ -379,3 +379,17 @@ def test_extended_space_tables_bit_exact():
         assert len(set(ci.embedding.tolist())) == len(ref)
     with pytest.raises(ValueError):
         extended_idx2det(1, 2, 1, 1, 1, 3)
+
+
+def test_runtime_switches_are_known():
+    """sq_set_option: every switch named in include/sqsv.h is accepted, anything else is an error (host call, no kernel)."""
+    lib = _lib.load()
+    for name, value in (
+        (b"win", b"1"), (b"wingrad", b"0"), (b"pipeline", b"1"), (b"etab", b"smem"), (b"rows", b"0"), (b"rows_cfg", b"1024,0"),
+        (b"panel", b"0"),
+    ):
+        assert lib.sq_set_option(name, value) == 0, name
+    assert lib.sq_set_option(b"no-such-switch", b"1") != 0
+    header = open(f"{ROOT}/include/sqsv.h").read()
+    for name in ("win", "wingrad", "pipeline", "etab", "rows", "rows_cfg", "panel"):
+        assert f'"{name}"' in header, f"switch {name} is not documented in include/sqsv.h"
