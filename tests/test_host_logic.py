@@ -393,3 +393,23 @@ def test_runtime_switches_are_known():
     header = open(f"{ROOT}/include/sqsv.h").read()
     for name in ("win", "wingrad", "pipeline", "etab", "rows", "rows_cfg", "panel"):
         assert f'"{name}"' in header, f"switch {name} is not documented in include/sqsv.h"
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys,
+    at a small CAS so that it finishes in seconds."""
+    import json
+    import subprocess
+    import sys
+
+    res = subprocess.run(
+        [sys.executable, f"{ROOT}/bench.py", "--impl", "reference", "--cas", "8", "--layers", "2", "--steps", "1", "--warmup", "0"],
+        capture_output=True, text=True, timeout=300,
+    )
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "layers/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["dtype"] == "f64" and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
