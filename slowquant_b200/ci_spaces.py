@@ -135,6 +135,21 @@ class CI_Info:
             pass
 
 
+def generate_spin_strings(num_orbs: int, num_elec: int):
+    """All occupation lists with `num_elec` ones in `num_orbs` places, in the order of the engine's string tables
+    (= ``itertools.combinations`` order, ci_spaces.py:56-73).  Host helper; the tables themselves are built inside
+    libsqsv (``sq_space_create``) and exported by ``CI_Info.strings``."""
+    import itertools
+
+    if num_elec < 0:
+        return
+    for occupied in itertools.combinations(range(num_orbs), num_elec):
+        string = [0] * num_orbs
+        for o in occupied:
+            string[o] = 1
+        yield string
+
+
 def get_indexing(
     num_inactive_orbs: int,
     num_active_orbs: int,

@@ -625,3 +625,103 @@ def build_operator_matrix(op: FermionicOperator, ci_info: CI_Info, do_unsafe: bo
         _apply_operator(op, unit, out, ci_info, do_unsafe)
         mat[:, j] = out.cpu().numpy()
     return mat
+
+
+# ---- the reference's per-string entry points (osa.py:33-410) ----------------------------------------
+# The reference's propagate_state hands every ladder string to a numba kernel together with its idx2det / det2idx
+# tables.  On the engine the per-string loop lives inside ``sq_apply_strings``; these wrappers keep the reference's
+# names, argument order and in-place accumulation for code that calls the kernels directly.  The CI space is
+# recovered from the ``det2idx`` view (``ci_info.det2idx``), the only table the engine needs.
+def bitcount(x: int) -> int:
+    """Number of set bits (osa.py:33-50; the kernels use ``__popc``)."""
+    return int(x).bit_count() if x > 0 else 0
+
+
+def get_ucc_T(thetas: Sequence[float], ucc_struct: UccStructure, offset: int = 0) -> FermionicOperator:
+    """T = sum_k theta_k (G_k - G_k^dagger) (osa.py:899-960)."""
+    from slowquant_b200.ucc_state import get_ucc_T as _get_ucc_T
+
+    return _get_ucc_T(thetas, ucc_struct, offset)
+
+
+def _space_of_tables(det2idx) -> CI_Info:
+    info = getattr(det2idx, "_info", None)
+    if info is None:
+        raise TypeError(
+            "det2idx must be the det2idx view of a slowquant_b200 CI_Info (the engine addresses determinants by "
+            f"string rank, not through a hash map); got {type(det2idx)}"
+        )
+    return info
+
+
+def _string_operator(kind: str, a_string, n_first: int, screen, factor: float) -> FermionicOperator:
+    """One-string FermionicOperator from the index arrays the reference's kernels take.
+
+    serial kernels (osa.py:610-612):   a_string = anni_idx + create_idx, screen = creators not also annihilated
+    threaded kernels (osa.py:577-579): a_string = create_idx + anni_idx, screen = annihilators not also created
+    Both split a label into its creators and annihilators in label order, so the label (creators, annihilators)
+    reproduces exactly these arrays."""
+    a_string = [int(x) for x in np.asarray(a_string).ravel()]
+    if kind == "serial":
+        anni, create = a_string[:n_first], a_string[n_first:]
+        expect = [c for c in create if c not in anni]
+    else:
+        create, anni = a_string[:n_first], a_string[n_first:]
+        expect = [a for a in anni if a not in create]
+    if sorted(int(x) for x in np.asarray(screen).ravel()) != sorted(expect):
+        raise ValueError("screening indices do not belong to a_string (expected the arrays propagate_state builds)")
+    label = tuple((c, True) for c in create) + tuple((a, False) for a in anni)
+    return FermionicOperator({label: float(factor)})
+
+
+def _accumulate_string(op: FermionicOperator, state, det2idx, do_unsafe: bool, tmp_state, batched: bool):
+    ci_info = _space_of_tables(det2idx)
+    fn = propagate_state_SA if batched else propagate_state
+    out = fn([op], state, ci_info, do_folding=False, do_unsafe=bool(do_unsafe))
+    if isinstance(tmp_state, torch.Tensor):
+        tmp_state += out if isinstance(out, torch.Tensor) else torch.from_numpy(np.asarray(out)).to(tmp_state.device)
+    else:
+        tmp_state += out.cpu().numpy() if isinstance(out, torch.Tensor) else out
+    return tmp_state
+
+
+def apply_operator_serial(
+    state, a_string, create_screen, anni_idx, num_active_orbs, parity_check, idx2det, det2idx, do_unsafe, tmp_state, factor
+):
+    """tmp_state += factor * string|state> for one ladder string (osa.py:53-136).  ``parity_check`` / ``idx2det`` /
+    ``num_active_orbs`` are accepted for signature compatibility; signs come from the closed form of DESIGN.md §2."""
+    op = _string_operator("serial", a_string, len(np.asarray(anni_idx).ravel()), create_screen, factor)
+    return _accumulate_string(op, state, det2idx, do_unsafe, tmp_state, batched=False)
+
+
+def apply_operator_threaded(
+    state, a_string, create_idx, anni_screen, num_active_orbs, parity_check, idx2det, det2idx, do_unsafe, tmp_state, factor
+):
+    """Gather-form twin of apply_operator_serial (osa.py:139-219); same result."""
+    op = _string_operator("threaded", a_string, len(np.asarray(create_idx).ravel()), anni_screen, factor)
+    return _accumulate_string(op, state, det2idx, do_unsafe, tmp_state, batched=False)
+
+
+def apply_operator_SA_serial(
+    state, a_string, create_screen, anni_idx, num_active_orbs, parity_check, idx2det, det2idx, do_unsafe, tmp_state, factor
+):
+    """Batch twin on ``state[n_states, N_det]`` (osa.py:282-348)."""
+    op = _string_operator("serial", a_string, len(np.asarray(anni_idx).ravel()), create_screen, factor)
+    return _accumulate_string(op, state, det2idx, do_unsafe, tmp_state, batched=True)
+
+
+def apply_operator_SA_threaded(
+    state, a_string, create_idx, anni_screen, num_active_orbs, parity_check, idx2det, det2idx, do_unsafe, tmp_state, factor
+):
+    """Batch twin of apply_operator_threaded (osa.py:351-410)."""
+    op = _string_operator("threaded", a_string, len(np.asarray(create_idx).ravel()), anni_screen, factor)
+    return _accumulate_string(op, state, det2idx, do_unsafe, tmp_state, batched=True)
+
+
+def add_operator_matrix(
+    op_mat, a_string, create_screen, anni_idx, num_active_orbs, parity_check, idx2det, det2idx, do_unsafe, factor
+):
+    """op_mat[tgt, src] += factor * sign for one ladder string (osa.py:222-279).  Small spaces only."""
+    op = _string_operator("serial", a_string, len(np.asarray(anni_idx).ravel()), create_screen, factor)
+    op_mat += build_operator_matrix(op, _space_of_tables(det2idx), do_unsafe=bool(do_unsafe))
+    return op_mat

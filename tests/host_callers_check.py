@@ -119,6 +119,52 @@ if which in ("all", "extended"):
             raised = True
         record(f"extended space {tag} KeyError as the reference", float(raised != bool(int(g[pre + "q_raises"]))), 0.5)
 
+# ---- the reference's per-string kernels (osa.py:33-410) and generate_spin_strings, against reference outputs ----
+if which in ("all", "strings"):
+    from slowquant_b200.ci_spaces import generate_spin_strings, get_indexing
+
+    g = np.load(os.path.join(G, "golden_strings.npz"))
+    nI, nA, nV, na, nb = (int(x) for x in g["space"])
+    ci = get_indexing(nI, nA, nV, na, nb)
+    record("strings: idx2det bit-exact", float(not np.array_equal(ci.idx2det, g["idx2det"])), 0.5)
+    record("strings: bitcount", float(any(osa.bitcount(int(x)) != int(y) for x, y in zip(g["bitcount_in"], g["bitcount_out"]))), 0.5)
+    bad_strings = 0
+    for n, k in ((5, 3), (5, 1), (4, 0), (3, 3)):
+        bad_strings += not np.array_equal(np.array(list(generate_spin_strings(n, k)), dtype=np.int64).reshape(-1, n), g[f"strings_{n}_{k}"])
+    bad_strings += list(generate_spin_strings(3, -1)) != []
+    masks = [sum(b << o for o, b in enumerate(s_)) for s_ in generate_spin_strings(nA, na)]
+    bad_strings += not np.array_equal(np.array(masks, dtype=np.uint32), ci.strings(0))
+    record("strings: generate_spin_strings == reference == engine tables", float(bad_strings), 0.5)
+    pc, st, sts = g["parity_check"], g["state"], g["states"]
+    errs = {"serial": 0.0, "threaded": 0.0, "sa_serial": 0.0, "sa_threaded": 0.0, "matrix": 0.0}
+    for c in range(int(g["n_cases"])):
+        pre = f"c{c}_"
+        f = float(g[pre + "factor"])
+        t = g["tmp0"].copy()
+        r = osa.apply_operator_serial(st, g[pre + "a_serial"], g[pre + "create_screen"], g[pre + "anni_idx"], nA, pc, ci.idx2det, ci.det2idx, False, t, f)
+        assert r is t  # accumulates in place and returns tmp_state, as the reference
+        errs["serial"] = max(errs["serial"], d(r, g[pre + "serial"]))
+        r = osa.apply_operator_threaded(st, g[pre + "a_threaded"], g[pre + "create_idx"], g[pre + "anni_screen"], nA, pc, ci.idx2det, ci.det2idx, False, g["tmp0"].copy(), f)
+        errs["threaded"] = max(errs["threaded"], d(r, g[pre + "threaded"]))
+        r = osa.apply_operator_SA_serial(sts, g[pre + "a_serial"], g[pre + "create_screen"], g[pre + "anni_idx"], nA, pc, ci.idx2det, ci.det2idx, False, g["tmps0"].copy(), f)
+        errs["sa_serial"] = max(errs["sa_serial"], d(r, g[pre + "sa_serial"]))
+        r = osa.apply_operator_SA_threaded(sts, g[pre + "a_threaded"], g[pre + "create_idx"], g[pre + "anni_screen"], nA, pc, ci.idx2det, ci.det2idx, False, g["tmps0"].copy(), f)
+        errs["sa_threaded"] = max(errs["sa_threaded"], d(r, g[pre + "sa_threaded"]))
+        r = osa.add_operator_matrix(np.zeros((len(st), len(st))), g[pre + "a_serial"], g[pre + "create_screen"], g[pre + "anni_idx"], nA, pc, ci.idx2det, ci.det2idx, False, f)
+        errs["matrix"] = max(errs["matrix"], d(r, g[pre + "matrix"]))
+    for k, v in errs.items():
+        record(f"strings: apply_operator / add_operator_matrix [{k}]", v, 1e-14)
+    raised = 0
+    try:
+        osa.apply_operator_serial(st, g["c0_a_serial"], g["c0_create_screen"], g["c0_anni_idx"], nA, pc, ci.idx2det, {}, False, g["tmp0"].copy(), 1.0)
+    except TypeError:
+        raised += 1
+    try:
+        osa.apply_operator_serial(st, g["c0_a_serial"], g["c0_anni_idx"], g["c0_anni_idx"], nA, pc, ci.idx2det, ci.det2idx, False, g["tmp0"].copy(), 1.0)
+    except ValueError:
+        raised += 1
+    record("strings: foreign det2idx -> TypeError, inconsistent screen -> ValueError", float(raised != 2), 0.5)
+
 # ---- rdm3 / rdm4 contractions ----
 if which in ("all", "rdm34"):
     g0 = np.load(os.path.join(G, "golden.npz"))

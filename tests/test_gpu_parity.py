@@ -781,3 +781,36 @@ def test_fused_energy_gradient_call(sq, golden):
         assert np.max(np.abs(g - ref[len(ref) - len(g) :])) < 1e-10
         E2, g2 = sq.osa.ups_energy_and_gradient(torch.from_numpy(WF.csf_coeffs).cuda(), WF.ci_info, th, WF.ups_layout, H, want_gradient=False)
         assert g2 is None and abs(E2 - E) < 1e-13
+
+
+def test_per_string_kernels_against_reference_outputs(sq):
+    """The reference's per-string entry points (osa.py:33-410: apply_operator_serial / _threaded, their _SA twins,
+    add_operator_matrix) through the gather kernel, on CAS(4,5) with 3 alpha / 1 beta electrons, against outputs of the
+    reference's numba kernels (tests/golden/make_golden_strings.py): host arrays accumulate in place like the reference,
+    device tensors stay resident."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_strings.npz"))
+    nI, nA, nV, na, nb = (int(x) for x in g["space"])
+    info = sq.ci.get_indexing(nI, nA, nV, na, nb)
+    assert np.array_equal(info.idx2det, g["idx2det"])
+    osa, pc, st, sts = sq.osa, g["parity_check"], g["state"], g["states"]
+    dev_state = torch.from_numpy(st).cuda()
+    for c in range(int(g["n_cases"])):
+        pre = f"c{c}_"
+        f = float(g[pre + "factor"])
+        ser = (g[pre + "a_serial"], g[pre + "create_screen"], g[pre + "anni_idx"], nA, pc, info.idx2det, info.det2idx, False)
+        thr = (g[pre + "a_threaded"], g[pre + "create_idx"], g[pre + "anni_screen"], nA, pc, info.idx2det, info.det2idx, False)
+        tmp = g["tmp0"].copy()
+        out = osa.apply_operator_serial(st, *ser, tmp, f)
+        assert out is tmp and np.max(np.abs(out - g[pre + "serial"])) < 1e-14
+        assert np.max(np.abs(osa.apply_operator_threaded(st, *thr, g["tmp0"].copy(), f) - g[pre + "threaded"])) < 1e-14
+        assert np.max(np.abs(osa.apply_operator_SA_serial(sts, *ser, g["tmps0"].copy(), f) - g[pre + "sa_serial"])) < 1e-14
+        assert np.max(np.abs(osa.apply_operator_SA_threaded(sts, *thr, g["tmps0"].copy(), f) - g[pre + "sa_threaded"])) < 1e-14
+        n = len(st)
+        assert np.max(np.abs(osa.add_operator_matrix(np.zeros((n, n)), *ser, f) - g[pre + "matrix"])) < 1e-14
+        dev_tmp = torch.from_numpy(g["tmp0"]).cuda()
+        dev_out = osa.apply_operator_serial(dev_state, *ser, dev_tmp, f)
+        assert dev_out is dev_tmp and dev_out.is_cuda
+        assert float(torch.max(torch.abs(dev_out.cpu() - torch.from_numpy(g[pre + "serial"])))) < 1e-14
+    assert [osa.bitcount(int(x)) for x in g["bitcount_in"]] == [int(x) for x in g["bitcount_out"]]
