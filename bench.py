@@ -137,13 +137,10 @@ _CPU_CACHE: dict = {}
 
 
 def cpu_sample(n: int) -> dict:
-    """Time ONE exp(theta T) rotation (the pair `double` of the first tUPS brick: 6 string passes +
-    the numpy closed form, reference osa.py:1043-1085) on the dense CAS(n,n) vector with the oracle's
-    OpenMP restatement of apply_operator_threaded (osa.py:139-219), and scale to one layer.
-
-    One tUPS layer on n orbitals has (n-1) bricks [sa_single, double, sa_single]; an sa_single is two such
-    rotations in sequence (alpha then beta, osa.py:1009-1042), so a layer costs 5(n-1) rotations.
-    """
+    """Time ONE tUPS brick -- [sa_single, double, sa_single] on orbitals (0,1): 5 exp(theta T) rotations (an sa_single
+    is an alpha and a beta rotation in sequence, osa.py:1009-1042), 6 string passes + the numpy closed form each
+    (reference osa.py:1002-1085) -- on the dense CAS(n,n) vector with the oracle's OpenMP restatement of
+    apply_operator_threaded (osa.py:139-219), and scale to one layer = (n-1) bricks (util.py:694-745)."""
     from oracle import sq_oracle as orc
 
     cores = os.cpu_count() or 1
@@ -157,22 +154,25 @@ def cpu_sample(n: int) -> dict:
         _CPU_CACHE[n] = (sp, state)
     sp, state = _CPU_CACHE[n]
     types, idx = orc.tiled_layout(n, 1)
-    assert types[1] == "double"
+    assert list(types[:3]) == ["sa_single", "double", "sa_single"]
     t0 = time.perf_counter()
-    orc.construct_ups_state(state, sp, [0.7], types[1:2], idx[1:2], threaded=True)
+    orc.construct_ups_state(state, sp, [0.7, -0.4, 0.3], types[0:3], idx[0:3], threaded=True)
     dt = time.perf_counter() - t0
-    rotations_per_layer = 5 * (n - 1)
-    layer_s = dt * rotations_per_layer
+    layer_s = dt * BRICKS_PER_LAYER(n)
     return {
         "value": 1.0 / layer_s,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
-        "sample": f"1 of the {rotations_per_layer} exp(theta T) rotations of one tUPS layer (pair double of the first "
-        f"brick, 6 string passes) on the dense CAS({n},{n}) vector ({sp.num_det} determinants): {dt:.2f} s, "
-        f"scaled x{rotations_per_layer} to one layer",
+        "sample": f"1 of the {BRICKS_PER_LAYER(n)} bricks of one tUPS layer ([sa_single, double, sa_single] on orbitals 0,1 = 3 "
+        f"ansatz operators = 5 rotations, 30 string passes) on the dense CAS({n},{n}) vector ({sp.num_det} determinants): "
+        f"{dt:.2f} s, scaled x{BRICKS_PER_LAYER(n)} to one layer",
         "seconds_per_sample": dt,
     }
+
+
+def BRICKS_PER_LAYER(n: int) -> int:
+    return n - 1
 
 
 def run_reference(args) -> None:
@@ -180,7 +180,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     n, L = args.cas, args.layers
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):  # one untimed pass (page faults, OpenMP pool); more would only burn host minutes
         cpu_sample(n)
     t_total = 0.0
     res = None
@@ -188,7 +188,7 @@ def run_reference(args) -> None:
         res = cpu_sample(n)
         t_total += res["seconds_per_sample"]
     mean_sample = t_total / max(args.steps, 1)
-    layer_s = mean_sample * 5 * (n - 1)
+    layer_s = mean_sample * BRICKS_PER_LAYER(n)
     value = 1.0 / layer_s
     cpu = dict(res)
     cpu["value"] = value
@@ -207,7 +207,7 @@ def run_reference(args) -> None:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(n, L), "step_is": "bounded sample: one exp(theta T) rotation, scaled to L layers"},
+        "config": {"workload": workload_name(n, L), "step_is": "bounded sample: one tUPS brick (3 operators, 5 rotations), scaled to L layers; at most one untimed warm-up sample"},
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
