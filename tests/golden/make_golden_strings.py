@@ -6,7 +6,7 @@ generate_spin_strings (ci_spaces.py:56-73), produced by RUNNING THE REFERENCE in
 
 Space CAS(4,5) with 3 alpha / 1 beta electrons (unequal spin counts on purpose).  Every case stores the index arrays
 exactly as the reference's propagate_state builds them (osa.py:560-612), the factor, and the kernel's output for a
-seeded state accumulated onto a seeded, non-zero tmp_state.
+seeded state accumulated onto a seeded, non-zero tmp_state.  Also idx2det of degenerate spaces (edge_*).
 """
 from __future__ import annotations
 
@@ -72,6 +72,12 @@ for c, label in enumerate(labels):
     out[pre + "matrix"] = rosa.add_operator_matrix(
         np.zeros((N, N)), a_ser, i64(create_screen), i64(anni), nA, parity_check, ci.idx2det, ci.det2idx, False, factor)
     assert np.array_equal(out[pre + "serial"], out[pre + "threaded"])
+
+# degenerate spaces (no electrons of one spin, a full spin string, one orbital, empty space): idx2det bit-exact targets
+EDGE = [(3, 0, 2), (3, 2, 0), (3, 3, 3), (1, 1, 0), (1, 0, 0), (4, 4, 1), (6, 0, 0), (5, 0, 5), (2, 1, 1)]
+out["edge_spaces"] = np.array(EDGE, dtype=np.int64)
+for n, a, b in EDGE:
+    out[f"edge_idx2det_{n}_{a}_{b}"] = np.array(get_indexing(0, n, 0, a, b).idx2det, dtype=np.int64)
 
 np.savez_compressed(os.path.join(HERE, "golden_strings.npz"), **out)
 print("wrote golden_strings.npz:", len(labels), "strings,", N, "determinants")

@@ -60,6 +60,27 @@ def test_idx2det_and_det2idx_bit_exact(golden):
         lib.sq_space_destroy(h)
 
 
+def test_degenerate_spaces_bit_exact():
+    """Spaces with no electrons of one spin, a full spin string, a single orbital or no electrons at all (one string per
+    empty / full spin, ci_spaces.py:56-73 yields exactly one list for k = 0) against the reference's idx2det."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_strings.npz"))
+    for n, na, nb in g["edge_spaces"]:
+        n, na, nb = int(n), int(na), int(nb)
+        lib, h = _host_space(n, na, nb)
+        ref = g[f"edge_idx2det_{n}_{na}_{nb}"]
+        nd = lib.sq_space_num_det(h)
+        assert nd == len(ref), (n, na, nb)
+        out = np.empty(nd, dtype=np.int64)
+        _lib.check(lib.sq_space_export_idx2det(h, 0, nd, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        assert np.array_equal(out, ref), (n, na, nb)
+        idx = np.empty(nd, dtype=np.int64)
+        _lib.check(lib.sq_space_det2idx(h, nd, ref.ctypes.data_as(C.POINTER(C.c_int64)), idx.ctypes.data_as(C.POINTER(C.c_int64))))
+        assert np.array_equal(idx, np.arange(nd))
+        lib.sq_space_destroy(h)
+
+
 def test_space_argument_errors():
     lib = _lib.load()
     h = C.c_void_p()
