@@ -167,6 +167,15 @@ int sq_ups_apply_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, i
 int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host,
                   double* rdm1_host, double* rdm2_host, void* stream);
 
+/* H|in> of an alpha-sharded vector (the string path of energy_elec, ups_wavefunction.py:770-784, and the sigma vector
+ * behind the theta gradient, :1091-1112), accumulated: every rank treats the determinants of ITS rows as sources, reads
+ * their alpha partners in place over NVLink and adds the images that belong to another rank's rows into that rank's
+ * out shard with system-scope atomics through the peer mapping.  Protocol: every rank sets out = e_core * in on its
+ * shard, barrier, every rank calls sq_sigma_dist, stream synchronise, barrier.  *_ptrs_host[r] = base pointer of rank
+ * r's shard as mapped into this process; in and out must not alias.  No symmetry of g is assumed. */
+int sq_sigma_dist(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
+                  double* const* out_ptrs_host, void* stream);
+
 /* ---- generic operator application (apply_operator_serial/threaded, :53-219; propagate_state
  *      inner loop, :596-628) -------------------------------------------------------------------- */
 

@@ -910,3 +910,123 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   }
   return SQ_OK;
 }
+
+// ---- sigma of an alpha-sharded vector ----------------------------------------------------------------------------------
+// Same Knowles-Handy panels as sq_sigma (general n^2 path: no symmetry of g assumed), one rank = the determinants of its
+// own rows as SOURCES: D is gathered with alpha partners read over NVLink (build_D_peer_kernel, as in sq_rdm12_dist),
+// F = 1/2 g D is a local DGEMM, and E_pq-images whose alpha row lives on another GPU are accumulated in place in the
+// owner's shard with system-scope fp64 atomics through the peer mapping -- the exchange step is inside the scatter
+// kernel, there is no transpose.  Several GPUs (and the owner itself) may add to one element concurrently, hence
+// atomicAdd_system for EVERY accumulation into OUT, local ones included.
+struct PeerViewRW {
+  double* p[SQ_MAX_WORLD];
+  int64_t row_starts[SQ_MAX_WORLD + 1];
+  int world;
+};
+__global__ void __launch_bounds__(256)
+scatter_E_peer_kernel(PeerViewRW pvo, const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                      const double* __restrict__ kmat, int64_t W, int64_t j0, int64_t len, const ERec* __restrict__ etab, int n2,
+                      const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                      const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  const ERec* sm = stage_etab<false>(etab, n2);
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j = j0 + t;
+  if (t >= W || j >= len) return;
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  const double cj = IN[j];
+  double diag = 0.0;
+  for (int slot = 0; slot < n2; ++slot) {
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    const bool va = (a & ra.occ) == ra.occ && (a & ra.emp) == 0u;
+    const bool vb = (b & rb.occ) == rb.occ && (b & rb.emp) == 0u;
+    if (!va && !vb) continue;
+    const double val = F[(int64_t)slot * W + t] + __ldg(kmat + slot) * cj;
+    if (va) {
+      const int par = (__popc(a & ra.parS) + __popc(b & ra.parO)) & 1;
+      const double sv = (par ? -ra.s0 : ra.s0) * val;
+      if (ra.flip == 0u) {
+        diag += sv;
+      } else {
+        const int64_t gr = __ldg(rankA + (a ^ ra.flip));   // global row of the image; its owner may be another GPU
+        int o = 0;
+        while (o + 1 < pvo.world && gr >= pvo.row_starts[o + 1]) ++o;
+        atomicAdd_system(pvo.p[o] + (gr - pvo.row_starts[o]) * NB + ib, sv);
+      }
+    }
+    if (vb) {
+      const int par = (__popc(b & rb.parS) + __popc(a & rb.parO)) & 1;
+      const double sv = (par ? -rb.s0 : rb.s0) * val;
+      if (rb.flip == 0u) diag += sv;
+      else atomicAdd_system(OUT + ia_loc * NB + __ldg(rankB + (b ^ rb.flip)), sv);
+    }
+  }
+  atomicAdd_system(OUT + j, diag);
+}
+
+// out (all shards) += sum_pq k_pq E_pq |in> + 1/2 sum_pqrs g_pqrs E_pq E_rs |in> restricted to THIS rank's source rows.
+// Protocol (the caller's, slowquant_b200/distributed.py::sigma_sharded): every rank sets its out shard to e_core * in,
+// barrier, every rank calls sq_sigma_dist, stream synchronise, barrier -- then out holds H|in>.
+extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
+                             double* const* out_ptrs_host, void* stream) {
+  if (!sp || !h_act_host || !g_act_host || !in_ptrs_host || !out_ptrs_host) return SQ_ERR_INVALID;
+  if (sp->device < 0) return SQ_ERR_INVALID;
+  if (sp->world < 1 || sp->world > SQ_MAX_WORLD || (int)sp->row_starts.size() != sp->world + 1) {
+    sq_set_error("sq_sigma_dist: the space has no row partition (sq_space_set_partition)");
+    return SQ_ERR_INVALID;
+  }
+  PeerView pin;
+  PeerViewRW pout;
+  pin.world = pout.world = sp->world;
+  for (int r = 0; r < SQ_MAX_WORLD; ++r) {
+    pin.p[r] = r < sp->world ? in_ptrs_host[r] : nullptr;
+    pout.p[r] = r < sp->world ? out_ptrs_host[r] : nullptr;
+    if (r < sp->world && (!pin.p[r] || !pout.p[r] || pin.p[r] == pout.p[r])) {
+      sq_set_error("sq_sigma_dist: missing or aliased shard pointer for rank %d", r);
+      return SQ_ERR_INVALID;
+    }
+  }
+  for (int r = 0; r <= SQ_MAX_WORLD; ++r)
+    pin.row_starts[r] = pout.row_starts[r] = r <= sp->world ? sp->row_starts[r] : sp->row_starts[sp->world];
+  const int64_t len = sp->local_len();
+  if (len == 0) return SQ_OK;   // a rank without rows has no sources
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  HamWork* w = nullptr;
+  SQ_CHECK(get_work(sp, false, true, &w));
+  const int n = sp->n_orb, n2 = n * n;
+  std::vector<double> k((size_t)n2), Gm((size_t)n2 * n2);
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q) {
+      double v = h_act_host[p * n + q];
+      for (int r = 0; r < n; ++r) v -= 0.5 * g_act_host[(((size_t)p * n + r) * n + r) * n + q];
+      k[(size_t)p * n + q] = v;
+    }
+  for (size_t i = 0; i < Gm.size(); ++i) Gm[i] = 0.5 * g_act_host[i];
+  double* d_G = w->d_small;
+  double* d_k = w->d_small + (size_t)n2 * n2;
+  SQ_CUDA(cudaMemcpyAsync(d_G, Gm.data(), sizeof(double) * Gm.size(), cudaMemcpyHostToDevice, st));
+  SQ_CUDA(cudaMemcpyAsync(d_k, k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice, st));
+  SQ_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
+  cublasSetStream(w->blas, st);
+  const double* in_dev = pin.p[sp->rank];
+  double* out_dev = pout.p[sp->rank];
+  const double one = 1.0, zero = 0.0;
+  const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+  allow_smem(scatter_E_peer_kernel, smem);
+  for (int64_t j0 = 0; j0 < len; j0 += w->W) {   // one stream: gather -> DGEMM -> scatter per panel
+    SQ_CHECK(launch_build_D(sp, w, in_dev, w->d_D[0], j0, st, false, false, &pin));
+    cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, n2, n2, &one, w->d_D[0], (int)w->W, d_G, n2,
+                                    &zero, w->d_F[0], (int)w->W);
+    if (bs != CUBLAS_STATUS_SUCCESS) {
+      sq_set_error("sq_sigma_dist: cublasDgemm failed (%d)", (int)bs);
+      return SQ_ERR_CUDA;
+    }
+    g_sq_launches.fetch_add(1);
+    scatter_E_peer_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(pout, in_dev, out_dev, w->d_F[0], d_k, w->W, j0, len, w->d_etab,
+                                                                     n2, sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB,
+                                                                     sp->row_begin);
+    SQ_CHECK(launch_error("scatter_E_peer_kernel"));
+  }
+  return SQ_OK;
+}

@@ -253,3 +253,40 @@ def energy_sharded(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_
     from its RDMs (the RDM route of ups_wavefunction.py:1041-1050 / density_matrix.py:139-178 in the active space)."""
     d1, d2 = rdm12_sharded(state, state)
     return float(e_core + np.sum(np.asarray(h_act) * d1) + 0.5 * np.sum(np.asarray(g_act) * d2))
+
+
+def sigma_sharded(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0, out: ShardedState | None = None) -> ShardedState:
+    r""":math:`H|\Psi\rangle` of an alpha-sharded vector as a new sharded vector (the string route of
+    ups_wavefunction.py:770-784 / :1091-1112 in the active space; ``h_act`` / ``g_act`` are the folded active integrals of
+    ``operators.fold_hamiltonian_0i_0a``).  Every rank treats the determinants of its rows as sources (``sq_sigma_dist``):
+    alpha partners on other GPUs are read over NVLink, images in other GPUs' rows are added there with system-scope
+    atomics; no transpose, no collective besides the two barriers.
+
+    STATUS: written in a session without GPU time -- compiled for sm_100a, not yet run; its parity test
+    (tests/test_gpu_distributed.py::test_sharded_sigma_matches_single_gpu) is opt-in (SQ_RUN_UNVERIFIED=1) until then."""
+    lib = _lib.load()
+    sp = state.space
+    n = sp.ci_info.num_active_orbs
+    h = np.ascontiguousarray(h_act, dtype=np.float64).reshape(n, n)
+    g = np.ascontiguousarray(g_act, dtype=np.float64).reshape(n, n, n, n)
+    if out is None:
+        out = sp.alloc_state(zero=False)
+    if out is state:
+        raise ValueError("sigma_sharded: out must not be the input state")
+    torch.mul(state.local, float(e_core), out=out.local)
+    torch.cuda.synchronize()
+    sp.barrier()        # every out shard is initialised and every in shard complete before remote reads / atomics start
+    PD = C.POINTER(C.c_double)
+    _lib.check(lib.sq_sigma_dist(sp.ci_info._handle, h.ctypes.data_as(PD), g.ctypes.data_as(PD), state._peer_ptrs, out._peer_ptrs, osa._stream()))
+    torch.cuda.synchronize()
+    sp.barrier()        # all remote contributions have landed
+    return out
+
+
+def energy_sharded_sigma(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0) -> float:
+    r""":math:`\langle\Psi|H|\Psi\rangle` of a sharded vector through :func:`sigma_sharded` and one all-reduced dot."""
+    sig = sigma_sharded(state, h_act, g_act, e_core)
+    try:
+        return dot_sharded(state, sig)
+    finally:
+        sig.close()
