@@ -290,3 +290,71 @@ def energy_sharded_sigma(state: ShardedState, h_act: np.ndarray, g_act: np.ndarr
         return dot_sharded(state, sig)
     finally:
         sig.close()
+
+
+# ---- theta gradient of a sharded vector ---------------------------------------------------------------------------------
+# The single-GPU path fuses g_k = 2 <bra|T_k|ket> with the two rotations in one kernel (sq_ups_grad_sweep).  For vectors that
+# only exist sharded, the same reference loop (ups_wavefunction.py:1114-1138) is composed from the sharded primitives:
+# <bra|T_k|ket> is the derivative at x = 0 of f(x) = <bra|exp(x T_k)|ket>, a trigonometric polynomial whose frequencies are
+# the (integer) |eigenvalues| of the anti-Hermitian generator, so it is EXACTLY a weighted sum of 2R rotated overlaps
+# (general parameter-shift rule for equidistant frequencies).  Correct first, not fast: 2R single-operator sweeps + dots per
+# parameter; a peer-memory variant of the fused gradient kernel is the next step.
+_AMPLITUDE_FREQUENCIES = {
+    # largest |eigenvalue| of T_k (spectra verified against the reference's generators)
+    "sa_single": 2,        # T_alpha + T_beta, commuting, each with spectrum {0, +-i}  (osa.py:1003-1042)
+    "single": 1, "double": 1, "triple": 1, "quadruple": 1, "quintuple": 1, "sextuple": 1,   # G - G^dagger: {0, +-i}
+    "sa_double_1": 1,
+}
+
+
+def shift_rule(R: int) -> tuple[np.ndarray, np.ndarray]:
+    """Points x_mu and weights w_mu with f'(0) = sum_mu w_mu f(x_mu) for every f(x) = sum_{|l| <= R} c_l exp(i l x)."""
+    mu = np.arange(1, 2 * R + 1)
+    x = (2 * mu - 1) * np.pi / (2 * R)
+    w = (-1.0) ** (mu - 1) / (4 * R * np.sin(x / 2) ** 2)
+    return x, w
+
+
+def energy_and_theta_gradient_sharded(
+    reference: ShardedState, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0
+) -> tuple[float, np.ndarray]:
+    r"""Energy and :math:`\partial E/\partial\theta_k` of :math:`U(\theta)|\text{reference}\rangle` on an alpha-sharded
+    vector (the theta part of ``_calc_gradient_optimization``, ups_wavefunction.py:1091-1138).  ``reference`` is not modified.
+
+    STATUS: composition of GPU-verified sharded primitives with ``sigma_sharded`` (first GPU run pending, see there); the
+    shift-rule arithmetic is checked on the CPU against the oracle's literal gradient loop (tests/test_distributed_host.py)."""
+    sp = reference.space
+    types = list(ups_struct.excitation_operator_type)
+    P = len(types)
+    th = osa._thetas_array(thetas, P)
+    for t in types:
+        if t not in _AMPLITUDE_FREQUENCIES:
+            raise NotImplementedError(f"theta gradient of sharded vectors: no shift rule for operator type {t}")
+    ket = sp.alloc_state(zero=False)
+    ket.local.copy_(reference.local)
+    construct_ups_state_sharded(ket, th, ups_struct)
+    bra = sigma_sharded(ket, h_act, g_act, e_core)
+    energy = dot_sharded(ket, bra)
+    construct_ups_state_sharded(bra, th, ups_struct, dagger=True)
+    ket.local.copy_(reference.local)
+    tmp = sp.alloc_state(zero=False)
+    grad = np.zeros(P)
+    probe = np.zeros(P)
+    try:
+        for k in range(P):
+            xs, ws = shift_rule(_AMPLITUDE_FREQUENCIES[types[k]])
+            acc = 0.0
+            for x, w in zip(xs, ws):
+                tmp.local.copy_(ket.local)
+                probe[k] = x
+                construct_ups_state_sharded(tmp, probe, ups_struct, first=k, last=k + 1)
+                acc += w * dot_sharded(bra, tmp)
+            probe[k] = 0.0
+            grad[k] = 2.0 * acc
+            construct_ups_state_sharded(bra, th, ups_struct, first=k, last=k + 1)
+            construct_ups_state_sharded(ket, th, ups_struct, first=k, last=k + 1)
+    finally:
+        tmp.close()
+        bra.close()
+        ket.close()
+    return energy, grad

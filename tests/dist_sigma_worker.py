@@ -21,7 +21,10 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     from slowquant_b200 import operator_state_algebra as osa
     from slowquant_b200.ci_spaces import get_indexing
-    from slowquant_b200.distributed import ShardedSpace, energy_sharded, energy_sharded_sigma, sigma_sharded
+    from slowquant_b200.distributed import (
+        ShardedSpace, energy_and_theta_gradient_sharded, energy_sharded, energy_sharded_sigma, sigma_sharded,
+    )
+    from slowquant_b200.util import UpsStructure
     from slowquant_b200.operators import hamiltonian_0i_0a
 
     worst = 0.0
@@ -53,10 +56,24 @@ def main():
         e_rdm = energy_sharded(st, h, g, e_core)
         err_e = max(abs(e_sig - e_ref), abs(e_sig - e_rdm)) / max(1.0, abs(e_ref))
         st.close()
-        e = torch.tensor([err, err_e], dtype=torch.float64, device="cuda")
+        # energy + theta gradient of U(theta)|HF> on the sharded vector (shift-rule composition) vs the fused single-GPU call
+        err_g = 0.0
+        if n <= 9:
+            lay = UpsStructure()
+            lay.create_tiled(n, {"n_layers": 1, "do_tups": True})
+            th = rng.uniform(-np.pi, np.pi, lay.n_params)
+            hf = np.zeros(info.num_det)
+            hf[0] = 1.0
+            e1, g1 = osa.ups_energy_and_gradient(hf, info, th, lay, hamiltonian_0i_0a(h, g, 0, n))
+            ref_st = sp.alloc_state()
+            ref_st.set_determinant(0)
+            e2, g2 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0)
+            ref_st.close()
+            err_g = max(abs(e1 - e2), float(np.max(np.abs(g1 - g2)))) / max(1.0, abs(e1))
+        e = torch.tensor([err, max(err_e, err_g)], dtype=torch.float64, device="cuda")
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"CAS({na + nb},{n}) world={world} symmetric={symmetric}: sigma rel. max|diff| {e[0]:.2e}, energy {e[1]:.2e}", flush=True)
+            print(f"CAS({na + nb},{n}) world={world} symmetric={symmetric}: sigma rel. max|diff| {e[0]:.2e}, energy / theta gradient {e[1]:.2e}", flush=True)
         worst = max(worst, float(e.max()))
     dist.barrier()
     dist.destroy_process_group()

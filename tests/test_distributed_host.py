@@ -117,3 +117,56 @@ def test_partition_prefix_matches_string_order():
         lib.sq_space_destroy(h)
     with pytest.raises(ValueError):
         partition_prefix(6, 3, 3)
+
+
+def test_shift_rule_is_exact_on_trigonometric_polynomials():
+    from slowquant_b200.distributed import shift_rule
+
+    rng = np.random.default_rng(5)
+    for R in (1, 2, 3, 4):
+        l = np.arange(-R, R + 1)
+        c = rng.normal(size=2 * R + 1) + 1j * rng.normal(size=2 * R + 1)
+        x, w = shift_rule(R)
+        assert len(x) == 2 * R
+        fprime = sum(wi * np.sum(c * np.exp(1j * l * xi)) for xi, wi in zip(x, w))
+        assert abs(fprime - np.sum(1j * l * c)) < 1e-13
+
+
+@pytest.mark.parametrize("layout", ["tups", "qnp", "generic"])
+def test_sharded_gradient_composition_equals_literal_loop(layout):
+    """The arithmetic of distributed.energy_and_theta_gradient_sharded -- g_k = 2 sum_mu w_mu <bra|exp(x_mu T_k)|ket> with the
+    frequency table _AMPLITUDE_FREQUENCIES, then both vectors advanced by U_k -- on the oracle's CPU primitives, against
+    the oracle's restatement of the reference's gradient loop (ups_wavefunction.py:1091-1138, get_grad_action per step)."""
+    from oracle import sq_oracle as orc
+    from slowquant_b200.distributed import _AMPLITUDE_FREQUENCIES, shift_rule
+
+    rng = np.random.default_rng(11)
+    n, na, nb = 4, 2, 2
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    if layout == "generic":
+        types = ["single", "sa_single", "double", "sa_double_1", "double", "single", "sa_single"]
+        idx = [(0, 4), (1, 3), (0, 1, 4, 5), (0, 1, 2, 3), (2, 3, 6, 7), (3, 7), (0, 2)]
+    else:
+        types, idx = orc.tiled_layout(n, 2, do_qnp=(layout == "qnp"))
+    P = len(types)
+    th = rng.uniform(-np.pi, np.pi, P)
+    th[1] = 0.0                                        # a zero angle: gradient without rotation
+    h = rng.normal(size=(n, n))
+    g = 0.1 * rng.normal(size=(n, n, n, n))
+    h, g = h + h.T, g + g.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    csf = rng.normal(size=sp.num_det)
+    csf /= np.linalg.norm(csf)
+    ref = orc.theta_gradient(csf, th, types, idx, h, g, sp)
+    ci = orc.construct_ups_state(csf, sp, th, types, idx)
+    bra = orc.propagate_state([orc.hamiltonian_0i_0a(h, g, 0, n)], ci, sp)
+    bra = orc.construct_ups_state(bra, sp, th, types, idx, dagger=True)
+    ket = csf.copy()
+    grad = np.zeros(P)
+    for k in range(P):
+        xs, ws = shift_rule(_AMPLITUDE_FREQUENCIES[types[k]])
+        grad[k] = 2.0 * sum(w * (bra @ orc.construct_ups_state(ket, sp, [x], types[k : k + 1], idx[k : k + 1])) for x, w in zip(xs, ws))
+        bra = orc.construct_ups_state(bra, sp, th[k : k + 1], types[k : k + 1], idx[k : k + 1])
+        ket = orc.construct_ups_state(ket, sp, th[k : k + 1], types[k : k + 1], idx[k : k + 1])
+    assert np.max(np.abs(grad - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
