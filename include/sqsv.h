@@ -101,6 +101,10 @@ int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last);
 /* launch plan of ops [first,last): out6 = {launches, window sweeps, bricks inside window sweeps, quad launches,
  * single-brick launches, other launches}.  (No reference counterpart: the reference applies one operator per pass.) */
 int sq_layout_plan_stats(const sq_layout* lay, int first, int last, int64_t* out6);
+/* the plan itself (planner tests): operators of [first,last) in execution order (dagger != 0: the reversed circuit) and the
+ * launch each one rides in; thetas_host may be NULL (all active; |theta| < 1e-28 is skipped as in sq_ups_apply). */
+int sq_layout_plan_export(const sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                          int32_t* ops_out, int32_t* launch_out, int cap, int* n_out);
 /* run-time switches (A/B comparisons, tests).  name "wingrad": "1" routes sq_ups_grad_sweep through the window kernel
  * (default "0": one brick per launch).  name "win": launch planner of sq_ups_apply, value "0" (window sweeps off),
  * "1" (defaults) or "w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks".  name "etab": E_pq table of the sigma / RDM

@@ -945,6 +945,37 @@ extern "C" int sq_layout_plan_stats(const sq_layout* lay_c, int first, int last,
   return SQ_OK;
 }
 
+// the plan itself, for tests of the planner: operators of [first,last) in EXECUTION order (dagger: reversed circuit) with the
+// index of the launch each one rides in.  thetas_host may be NULL (all operators active) -- zero angles are skipped as in
+// sq_ups_apply.  Returns SQ_ERR_INVALID if cap is too small; *n_out = number of entries.
+extern "C" int sq_layout_plan_export(const sq_layout* lay_c, const double* thetas_host, int first, int last, int dagger,
+                                     int32_t* ops_out, int32_t* launch_out, int cap, int* n_out) {
+  sq_layout* lay = const_cast<sq_layout*>(lay_c);
+  if (!lay || !ops_out || !launch_out || !n_out || first < 0 || last > (int)lay->ops.size() || first > last) return SQ_ERR_INVALID;
+  std::vector<double> th(lay->ops.size(), 1.0);
+  if (thetas_host)
+    for (size_t k = 0; k < th.size(); ++k) th[k] = thetas_host[k];
+  std::vector<int> order;
+  exec_order(first, last, dagger ? 1 : 0, &order);
+  std::vector<std::vector<int>> runs;
+  std::vector<Launch> launches;
+  plan_runs(lay, order, th.data(), &runs);
+  SQ_CHECK(plan_launches(lay, runs, &launches));
+  int n = 0, li = 0;
+  for (auto& l : launches) {
+    for (int t : l.runs)
+      for (int k : runs[t]) {
+        if (n >= cap) return SQ_ERR_INVALID;
+        ops_out[n] = k;
+        launch_out[n] = li;
+        ++n;
+      }
+    ++li;
+  }
+  *n_out = n;
+  return SQ_OK;
+}
+
 // closed forms of exp(theta T) for the spin-adapted doubles (operator_state_algebra.py:1086-1409):
 // out += sum_m w_m(theta) T^m out with the reference's coefficient tables.
 static int sa_double_poly(sq_space* sp, const GenOp& g, int type, double theta, double* state, cudaStream_t st) {

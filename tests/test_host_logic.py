@@ -358,6 +358,93 @@ def test_launch_planner_on_host_only_space():
         lib.sq_space_destroy(h)
 
 
+def _layout_handle(lib, h, lay):
+    codes = np.array([_lib.EXC_CODES[t] for t in lay.excitation_operator_type], dtype=np.int32)
+    offs = np.zeros(len(codes) + 1, dtype=np.int32)
+    flat = []
+    for k, idx in enumerate(lay.excitation_indices):
+        flat.extend(int(x) for x in idx)
+        offs[k + 1] = len(flat)
+    flat = np.asarray(flat, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    handle = C.c_void_p()
+    _lib.check(lib.sq_layout_create(h, len(codes), p(codes), p(offs), p(flat), C.byref(handle)))
+    return handle
+
+
+def _spatial_orbitals(exc_type, idx):
+    return {int(x) for x in idx} if exc_type.startswith("sa_") else {int(x) // 2 for x in idx}
+
+
+@pytest.mark.parametrize(
+    "n,na,nb,options,win",
+    [
+        (8, 4, 4, {"n_layers": 5, "do_tups": True}, b"1"),
+        (10, 5, 5, {"n_layers": 7, "do_qnp": True}, b"1"),
+        (11, 5, 6, {"n_layers": 4, "do_tups": True, "skip_last_singles": True}, b"1"),
+        (12, 6, 6, {"n_layers": 9, "do_tups": True}, b"1"),
+        (12, 6, 6, {"n_layers": 5, "do_tups": True}, b"4:3:0,72,2,4,2"),
+        (9, 4, 5, {"n_layers": 6, "do_tups": True}, b"0"),
+    ],
+)
+def test_launch_plan_is_a_valid_reordering(n, na, nb, options, win):
+    """The planner may only move an operator past operators it commutes with.  Export the plan (sq_layout_plan_export) and check,
+    for forward and adjoint circuits, full ranges, sub-ranges and with some angles exactly zero: (1) every active operator runs
+    exactly once, skipped ones (|theta| < 1e-28, osa.py:998) never; (2) any two operators that share a spatial orbital keep the
+    order of the circuit (reversed for the adjoint); (3) launches are contiguous in the exported order."""
+    from slowquant_b200.util import UpsStructure
+
+    lib, h = _host_space(n, na, nb)
+    ups = UpsStructure()
+    ups.create_tiled(n, dict(options))
+    # a few generic operators in the middle: they split the circuit into stretches the planner treats separately
+    P0 = ups.n_params
+    types, idxs = list(ups.excitation_operator_type), [tuple(i) for i in ups.excitation_indices]
+    mid = P0 // 2
+    types[mid:mid] = ["single", "double"]
+    idxs[mid:mid] = [(0, 2 * (n - 1)), (0, 1, 2 * (n - 2), 2 * (n - 1) + 1)]
+    ups.excitation_operator_type, ups.excitation_indices, ups.n_params = types, idxs, len(types)
+    lay = _layout_handle(lib, h, ups)
+    P = len(types)
+    orbs = [_spatial_orbitals(t, i) for t, i in zip(types, idxs)]
+    rng = np.random.default_rng(n * 100 + P)
+    ops_out = np.empty(P, dtype=np.int32)
+    launch_out = np.empty(P, dtype=np.int32)
+    n_out = C.c_int(0)
+    pi32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    try:
+        _lib.check(lib.sq_set_option(b"win", win))
+        for first, last, zero_some in ((0, P, False), (0, P, True), (3, P - 5, False), (mid - 7, mid + 9, True)):
+            th = rng.uniform(-np.pi, np.pi, P)
+            if zero_some:
+                th[rng.choice(P, size=P // 6, replace=False)] = 0.0
+            for dagger in (0, 1):
+                _lib.check(
+                    lib.sq_layout_plan_export(
+                        lay, th.ctypes.data_as(C.POINTER(C.c_double)), first, last, dagger, pi32(ops_out), pi32(launch_out), P, C.byref(n_out)
+                    )
+                )
+                m = n_out.value
+                planned = ops_out[:m].tolist()
+                active = [k for k in range(first, last) if abs(th[k]) >= 1e-28]
+                assert sorted(planned) == active                                   # (1)
+                pos = {k: i for i, k in enumerate(planned)}
+                for a_i, ka in enumerate(active):                                  # (2)
+                    for kb in active[a_i + 1 :]:
+                        if orbs[ka] & orbs[kb]:
+                            assert (pos[ka] < pos[kb]) == (not dagger), (ka, kb, dagger, types[ka], types[kb])
+                la = launch_out[:m]
+                assert np.all(np.diff(la) >= 0) and (m == 0 or la[0] == 0)         # (3)
+                if win == b"1" and n >= 10 and (first, last) == (0, P) and not zero_some:
+                    # the check above is not vacuous: the plan is time-skewed (not the circuit order) and fuses many operators
+                    assert planned != (active if not dagger else active[::-1]) and int(la[-1]) + 1 < m // 6
+        assert lib.sq_layout_plan_export(lay, None, 0, P, 0, pi32(ops_out), pi32(launch_out), 3, C.byref(n_out)) == _lib.SQ_ERR_INVALID
+    finally:
+        _lib.check(lib.sq_set_option(b"win", b"1"))
+        lib.sq_layout_destroy(lay)
+        lib.sq_space_destroy(h)
+
+
 def test_lr_orbital_blocks_match_reference():
     """RDM-only linear-response orbital blocks (reference density_matrix.py:233-563) against outputs of the reference
     itself on seeded random h, g, x, rdm1, rdm2 (tests/golden/make_golden_lr.py), incl. no-inactive / no-virtual spaces."""
