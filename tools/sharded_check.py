@@ -6,7 +6,8 @@
 
 With a third argument "energy": also <H> of the sharded vector from its RDMs (synthetic symmetric integrals), checked at
 the Hartree-Fock determinant against the closed form 2 sum_i h_ii + sum_ij (2 g_iijj - g_ijji), with Tr Gamma1 = N_e and
-sum_pq Gamma2[ppqq] = N_e (N_e - 1) on the correlated state.
+sum_pq Gamma2[ppqq] = N_e (N_e - 1) on the correlated state.  A fourth argument "sigma" adds <H> through the sharded sigma
+vector (sq_sigma_dist), which must agree with the RDM route.
 """
 import os
 import sys
@@ -83,6 +84,17 @@ def main():
                 f"max|G1 - G1^T| = {sym:.1e}" + hf_msg,
                 flush=True,
             )
+    if len(sys.argv) > 3 and sys.argv[3] in ("energy", "energy-nohf") and len(sys.argv) > 4 and sys.argv[4] == "sigma":
+        # <H> once more through H|psi> (sq_sigma_dist: peer gathers + NVLink atomics) -- must equal the RDM route
+        from slowquant_b200.distributed import energy_sharded_sigma
+
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        e_sig = energy_sharded_sigma(st, h, g)
+        t_sig = time.perf_counter() - t0
+        if rank == 0:
+            print(f"CAS({n},{n}) world={world} sharded sigma + dot: {t_sig:.2f} s;  E_sigma = {e_sig:.12f} (E_sigma - E_RDM = {e_sig - energy:.2e})", flush=True)
     # undo both applications: must return to the HF determinant
     construct_ups_state_sharded(st, th, lay, dagger=True)
     construct_ups_state_sharded(st, th, lay, dagger=True)
