@@ -112,7 +112,8 @@ int sq_layout_plan_export(const sq_layout* lay, const double* thetas_host, int f
  * the gather, DGEMM and scatter of neighbouring sigma / RDM panels on internal streams, "0" runs one panel at a time.  name "rows": "0" (default) determinant-per-thread gather /
  * scatter kernels, "1" row-per-CTA kernels with the row staged in shared memory (measured slower; "rows_cfg" =
  * "threads,chunks" sets their geometry).  name "panel": determinants per
- * panel for spaces that build their panels afterwards ("0": about 1 GiB per panel) */
+ * panel for spaces that build their panels afterwards ("0": about 1 GiB per panel).  name "rdm_tri": "1" builds the symmetric
+ * Gram matrix of sq_rdm12 with bra == ket from three half-size DGEMMs (3/4 of the flops), "0" (default) from one DGEMM. */
 int sq_set_option(const char* name, const char* value);
 
 /* ---- unitary product state (construct_ups_state, operator_state_algebra.py:963-1412;

@@ -618,6 +618,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_pipeline(!(value && value[0] == '0'));
     return SQ_OK;
   }
+  if (strcmp(name, "rdm_tri") == 0) {   // RDMs with bra == ket: "1" three half-size DGEMMs (3/4 of the flops), "0" (default) one DGEMM
+    sq_hamiltonian_set_rdm_tri(value && value[0] == '1');
+    return SQ_OK;
+  }
   if (strcmp(name, "etab") == 0) {   // E_pq table of the sigma / RDM panel kernels: "smem" (default) or "const"
     sq_hamiltonian_set_etab_mode(value && strcmp(value, "const") == 0);
     return SQ_OK;

@@ -59,6 +59,11 @@ void sq_hamiltonian_set_etab_mode(int use_const) { g_etab_const = use_const ? 1 
 // sq_set_option("pipeline", "0"): one panel at a time on the caller's stream (the pre-pipeline behaviour, for A/B runs)
 static int g_panel_pipeline = 1;
 void sq_hamiltonian_set_pipeline(int on) { g_panel_pipeline = on ? 1 : 0; }
+// sq_set_option("rdm_tri", "1"): for bra == ket the Gram matrix D D^T is symmetric -- compute the two diagonal half blocks and ONE
+// off-diagonal block (three DGEMMs of n^2/2 x n^2/2 x W: 3/4 of the flops) and mirror the fourth on the host.  Candidate for the
+// next GPU visit (cublasDsyrk was measured 3 x slower than DGEMM here); off by default until it is measured.
+static int g_rdm_tri = 0;
+void sq_hamiltonian_set_rdm_tri(int on) { g_rdm_tri = on ? 1 : 0; }
 // sq_set_option("panel", "<determinants>"): panel width of spaces that have not built their panels yet (tests use it to get
 // several panels at small CAS); "0" restores the 1 GiB default
 static int64_t g_panel_width = 0;
@@ -829,6 +834,7 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   // With the 2-RDM accumulator at hand, rdm1 needs no pass of its own: sum_r E_rr = N on this space, so
   // <bra|E_pq|ket> = (1/N) sum_r <bra|E_pq E_rr|ket>  (saves one GEMV sweep over every panel).
   const bool rdm1_from_G2 = rdm2_host && n_elec > 0;
+  const bool tri = g_rdm_tri && same && rdm2_host && n2 >= 2;   // symmetric Gram matrix: three of the four half blocks
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -867,8 +873,21 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     if (rdm2_host) {
       // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]  ==  column-major C[b][a] = Dket^T Dbra
       // (cublasDsyrk would do half the flops for bra == ket but runs 3 x slower than DGEMM at n^2 = 256, k = 5e5)
-      bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, n2, n2, (int)w->W, &one, Dket, (int)w->W, Dbra, (int)w->W,
-                       &one, d_G2, n2);
+      if (tri) {
+        // column-major C (ld n2): blocks (rows i0.., cols j0..) = Dket[:, i0..]^T Dbra[:, j0..]; block (hb.., 0..) is skipped
+        const int hb = n2 / 2, rb = n2 - hb;
+        bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, hb, hb, (int)w->W, &one, Dket, (int)w->W, Dbra, (int)w->W, &one, d_G2, n2);
+        if (bs == CUBLAS_STATUS_SUCCESS)
+          bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, hb, rb, (int)w->W, &one, Dket, (int)w->W, Dbra + (size_t)hb * w->W,
+                           (int)w->W, &one, d_G2 + (size_t)hb * n2, n2);
+        if (bs == CUBLAS_STATUS_SUCCESS)
+          bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, rb, rb, (int)w->W, &one, Dket + (size_t)hb * w->W, (int)w->W,
+                           Dbra + (size_t)hb * w->W, (int)w->W, &one, d_G2 + hb + (size_t)hb * n2, n2);
+        g_sq_launches.fetch_add(2);
+      } else {
+        bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, n2, n2, (int)w->W, &one, Dket, (int)w->W, Dbra, (int)w->W,
+                         &one, d_G2, n2);
+      }
       if (bs != CUBLAS_STATUS_SUCCESS) {
         sq_set_error("sq_rdm12: cublasDgemm failed (%d)", (int)bs);
         return SQ_ERR_CUDA;
@@ -888,6 +907,11 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   if (rdm2_host)
     SQ_CUDA(cudaMemcpyAsync(G2h.data(), d_G2, sizeof(double) * (size_t)n2 * n2, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(cudaStreamSynchronize(st));
+  if (tri) {   // the skipped block: column-major C[i][j], i >= hb > j, equals C[j][i]; row-major G2h[a][b] holds C[b][a]
+    const int hb = n2 / 2;
+    for (int a = 0; a < hb; ++a)
+      for (int b = hb; b < n2; ++b) G2h[(size_t)a * n2 + b] = G2h[(size_t)b * n2 + a];
+  }
   if (rdm1_from_G2) {
     for (int p = 0; p < n; ++p)
       for (int q = 0; q < n; ++q) {

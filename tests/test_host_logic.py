@@ -494,12 +494,12 @@ def test_runtime_switches_are_known():
     lib = _lib.load()
     for name, value in (
         (b"win", b"1"), (b"wingrad", b"0"), (b"pipeline", b"1"), (b"etab", b"smem"), (b"rows", b"0"), (b"rows_cfg", b"1024,0"),
-        (b"panel", b"0"),
+        (b"panel", b"0"), (b"rdm_tri", b"0"),
     ):
         assert lib.sq_set_option(name, value) == 0, name
     assert lib.sq_set_option(b"no-such-switch", b"1") != 0
     header = open(f"{ROOT}/include/sqsv.h").read()
-    for name in ("win", "wingrad", "pipeline", "etab", "rows", "rows_cfg", "panel"):
+    for name in ("win", "wingrad", "pipeline", "etab", "rows", "rows_cfg", "panel", "rdm_tri"):
         assert f'"{name}"' in header, f"switch {name} is not documented in include/sqsv.h"
 
 
