@@ -184,10 +184,15 @@ def run_reference(args) -> None:
         cpu_sample(n)
     t_total = 0.0
     res = None
-    for _ in range(args.steps):
+    timed = 0
+    budget_s = 150.0   # host time for the timed samples: the whole arm has to end within a few minutes whatever K is
+    for _ in range(max(args.steps, 1)):
         res = cpu_sample(n)
         t_total += res["seconds_per_sample"]
-    mean_sample = t_total / max(args.steps, 1)
+        timed += 1
+        if t_total + res["seconds_per_sample"] > budget_s:
+            break
+    mean_sample = t_total / timed
     layer_s = mean_sample * BRICKS_PER_LAYER(n)
     value = 1.0 / layer_s
     cpu = dict(res)
@@ -211,6 +216,7 @@ def run_reference(args) -> None:
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "samples_timed": timed,   # == steps unless the 150 s host-time budget ended the loop earlier (the samples are identical)
     }
     print(json.dumps(line), flush=True)
 
