@@ -108,7 +108,8 @@ int sq_layout_plan_export(const sq_layout* lay, const double* thetas_host, int f
 /* run-time switches (A/B comparisons, tests).  name "wingrad": "1" routes sq_ups_grad_sweep through the window kernel
  * (default "0": one brick per launch).  name "win": launch planner of sq_ups_apply, value "0" (window sweeps off),
  * "1" (defaults) or "w1:w2:w3,smem_kb,min_suffix,max_bricks,min_bricks".  name "etab": E_pq table of the sigma / RDM
- * panel kernels in shared memory ("smem", default) or constant memory ("const").  name "pipeline": "1" (default) overlaps
+ * panel kernels in shared memory ("smem", default), constant memory ("const"), or no table at all ("alu": the record of E_pq is
+ * computed from (p,q) with uniform integer instructions).  name "pipeline": "1" (default) overlaps
  * the gather, DGEMM and scatter of neighbouring sigma / RDM panels on internal streams, "0" runs one panel at a time.  name "rows": "0" (default) determinant-per-thread gather /
  * scatter kernels, "1" row-per-CTA kernels with the row staged in shared memory (measured slower; "rows_cfg" =
  * "threads,chunks" sets their geometry).  name "panel": determinants per
@@ -215,6 +216,9 @@ int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_dev, double*
  * sign = phase of :127-134. */
 int sq_debug_string_action(const sq_space* sp, const int32_t* ops, int n_ops, uint32_t A, uint32_t B,
                            int* valid, uint32_t* tgtA, uint32_t* tgtB, int* sign);
+/* number of (p, q, spin) for which the table-free record of E_pq (sq_set_option("etab", "alu")) differs from the table the
+ * sigma / RDM panel kernels use (built from the closed-form string action above); must be 0. */
+int sq_debug_etab_closed_form(const sq_space* sp, int* n_mismatch);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 /* number of kernels this library has launched since load (all spaces) */

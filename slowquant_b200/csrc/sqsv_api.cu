@@ -624,6 +624,7 @@ extern "C" int sq_set_option(const char* name, const char* value) {
   }
   if (strcmp(name, "etab") == 0) {   // E_pq table of the sigma / RDM panel kernels: "smem" (default) or "const"
     sq_hamiltonian_set_etab_mode(value && strcmp(value, "const") == 0);
+    sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
     return SQ_OK;
   }
   sq_set_error("sq_set_option: unknown option '%s'", name);

@@ -55,6 +55,27 @@ static std::map<int, const sq_space*> g_etab_owner;   // device -> space whose t
 static int g_etab_const = 0;                          // sq_set_option("etab", "const") selects the constant table
 
 void sq_hamiltonian_set_etab_mode(int use_const) { g_etab_const = use_const ? 1 : 0; }
+// sq_set_option("etab", "alu"): no table at all.  The (p,q) loops of the panel kernels are uniform across the CTA, so the record
+// of E_pq -- two single-bit masks, two interval masks, a sign -- is a handful of uniform-datapath integer instructions instead of
+// four 16-byte shared-memory loads per (p,q) and warp (the panel kernels are LSU-bound: 62-77 % LSU data pipe,
+// profiles/r1_energy_kernels_ncu_summary.csv).  Closed form of sq_make_string_action for the label [a+_p a_q] of one spin (checked
+// entry by entry against the table on the host: sq_debug_etab_closed_form, tests/test_host_logic.py).  Candidate for the next GPU visit,
+// off by default until measured.
+static int g_etab_alu = 0;
+void sq_hamiltonian_set_etab_alu(int on) { g_etab_alu = on ? 1 : 0; }
+__host__ __device__ __forceinline__ ERec erec_closed(int p, int q, int spin) {
+  const uint32_t bp = 1u << p, bq = 1u << q;
+  ERec r;
+  r.tocc = bp;                  // target: p occupied ...
+  r.temp = bq & ~bp;            // ... q empty unless p == q
+  r.occ = bq;                   // source: q occupied ...
+  r.emp = bp & ~bq;             // ... p empty unless p == q
+  r.flip = bp ^ bq;
+  r.parS = (bp - 1u) ^ (bq - 1u);                                       // same-spin orbitals in [min, max)
+  r.parO = spin ? (((bp << 1) - 1u) ^ ((bq << 1) - 1u)) : r.parS;       // other spin: (min, max] for beta, [min, max) for alpha
+  r.s0 = q < p ? -1 : 1;
+  return r;
+}
 
 // sq_set_option("pipeline", "0"): one panel at a time on the caller's stream (the pre-pipeline behaviour, for A/B runs)
 static int g_panel_pipeline = 1;
@@ -345,6 +366,112 @@ scatter_E_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const 
   atomicAdd(OUT + j, diag);
 }
 
+// ---- table-free variants (sq_set_option("etab", "alu")): same arithmetic, records from erec_closed ----------------------------------
+__global__ void __launch_bounds__(256)
+build_D_alu_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len, int n,
+                   const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                   const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int n2 = n * n;
+  if (j >= len) {
+    for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  int slot = 0;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q, ++slot) {
+      double v = 0.0;
+      const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+      if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+        const uint32_t sa = a ^ ra.flip;
+        const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+        const double x = IN[((int64_t)__ldg(rankA + sa) - row_begin) * NB + ib];
+        v += (par ? -ra.s0 : ra.s0) * x;
+      }
+      if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+        const uint32_t sb = b ^ rb.flip;
+        const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+        const double x = IN[ia_loc * NB + __ldg(rankB + sb)];
+        v += (par ? -rb.s0 : rb.s0) * x;
+      }
+      D[(int64_t)slot * W + t] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+build_Dsym_alu_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len, int n,
+                      const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                      const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < nS; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  auto elem = [&](int p, int q) -> double {
+    double v = 0.0;
+    const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      v += (par ? -ra.s0 : ra.s0) * IN[((int64_t)__ldg(rankA + sa) - row_begin) * NB + ib];
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      v += (par ? -rb.s0 : rb.s0) * IN[ia_loc * NB + __ldg(rankB + sb)];
+    }
+    return v;
+  };
+  int slot = 0;
+  for (int r = 0; r < n; ++r)
+    for (int q = 0; q <= r; ++q, ++slot) D[(int64_t)slot * W + t] = (r == q) ? elem(r, r) : elem(r, q) + elem(q, r);
+}
+
+__global__ void __launch_bounds__(256)
+scatter_E_alu_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                     const double* __restrict__ kmat, const int* __restrict__ frow, int64_t W, int64_t j0, int64_t len, int n,
+                     const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                     const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j = j0 + t;
+  if (t >= W || j >= len) return;
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  const double cj = IN[j];
+  double diag = 0.0;
+  int slot = 0;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q, ++slot) {
+      const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+      const bool va = (a & ra.occ) == ra.occ && (a & ra.emp) == 0u;
+      const bool vb = (b & rb.occ) == rb.occ && (b & rb.emp) == 0u;
+      if (!va && !vb) continue;
+      const double val = F[(int64_t)__ldg(frow + slot) * W + t] + __ldg(kmat + slot) * cj;   // frow: row of F that holds (p,q)
+      if (va) {
+        const int par = (__popc(a & ra.parS) + __popc(b & ra.parO)) & 1;
+        const double sv = (par ? -ra.s0 : ra.s0) * val;
+        if (ra.flip == 0u) diag += sv;
+        else atomicAdd(OUT + ((int64_t)__ldg(rankA + (a ^ ra.flip)) - row_begin) * NB + ib, sv);
+      }
+      if (vb) {
+        const int par = (__popc(b & rb.parS) + __popc(a & rb.parO)) & 1;
+        const double sv = (par ? -rb.s0 : rb.s0) * val;
+        if (rb.flip == 0u) diag += sv;
+        else atomicAdd(OUT + ia_loc * NB + __ldg(rankB + (b ^ rb.flip)), sv);
+      }
+    }
+  atomicAdd(OUT + j, diag);
+}
+
 // ---- row kernels (measured alternative, off by default) ---------------------------------------------------------------
 // Idea: the beta partner of column ib under E_rs and its sign do not depend on the row, so they can be tabulated once per
 // space as one 32-bit word per (rs, ib) and read coalesced; and all beta partners of a row lie in that row, so a CTA that
@@ -599,6 +726,16 @@ static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D,
                                                                      sp->row_begin);
     return launch_error("build_D_peer_kernel");
   }
+  if (g_etab_alu) {   // table-free records (candidate, off by default)
+    const unsigned grid_a = (unsigned)(w->W / 256);
+    if (sym)
+      build_Dsym_alu_kernel<<<grid_a, 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), n, sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB,
+                                                     sp->NB, sp->row_begin);
+    else
+      build_D_alu_kernel<<<grid_a, 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), n, sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB,
+                                                  sp->NB, sp->row_begin);
+    return launch_error("build_D_alu_kernel");
+  }
   if (g_rows_kernels && w->d_tabG) {
     const RowGrid g = row_grid(sp, w, j0);
     const size_t smem = rows_smem(sp);
@@ -642,6 +779,11 @@ static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D,
 static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* out, const double* F, const double* d_k,
                             int64_t j0, cudaStream_t st, bool use_const) {
   const int n2 = sp->n_orb * sp->n_orb;
+  if (g_etab_alu) {   // table-free records (candidate, off by default)
+    scatter_E_alu_kernel<<<(unsigned)(w->W / 256), 256, 0, st>>>(in, out, F, d_k, w->d_frow, w->W, j0, sp->local_len(), sp->n_orb,
+                                                                 sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+    return launch_error("scatter_E_alu_kernel");
+  }
   if (g_rows_kernels && w->d_tabS) {
     const RowGrid g = row_grid(sp, w, j0);
     const size_t smem = rows_smem(sp);
@@ -1134,5 +1276,30 @@ extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const doubl
                                                                      sp->row_begin);
     SQ_CHECK(launch_error("scatter_E_peer_kernel"));
   }
+  return SQ_OK;
+}
+
+// Host check of erec_closed against the table get_work builds from sq_make_string_action (works on host-only spaces).
+extern "C" int sq_debug_etab_closed_form(const sq_space* sp, int* n_mismatch) {
+  if (!sp || !n_mismatch) return SQ_ERR_INVALID;
+  const int n = sp->n_orb;
+  int bad = 0;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q)
+      for (int spin = 0; spin < 2; ++spin) {
+        int32_t label[2] = {2 * (2 * p + spin) + 1, 2 * (2 * q + spin)};
+        StringAction a;
+        SQ_CHECK(sq_make_string_action(sp, label, 2, &a));
+        ERec r;
+        if (spin == 0)
+          r = {a.toccA, a.tempA, a.occA, a.empA, a.flipA, a.parA, a.parB, a.s0};
+        else
+          r = {a.toccB, a.tempB, a.occB, a.empB, a.flipB, a.parB, a.parA, a.s0};
+        const ERec c = erec_closed(p, q, spin);
+        if (r.tocc != c.tocc || r.temp != c.temp || r.occ != c.occ || r.emp != c.emp || r.flip != c.flip || r.parS != c.parS ||
+            r.parO != c.parO || r.s0 != c.s0)
+          ++bad;
+      }
+  *n_mismatch = bad;
   return SQ_OK;
 }

@@ -195,6 +195,7 @@ void sq_hamiltonian_set_panel_width(long long w);  // determinants per panel for
 void sq_hamiltonian_set_rows_cfg(int threads, int ch);  // CTA size / column chunks per row of the row kernels
 void sq_hamiltonian_set_rows_mode(int on);         // row-per-CTA panel kernels (default on) or determinant-per-thread
 void sq_hamiltonian_set_pipeline(int on);          // sigma / RDM panel pipeline over internal streams (default on)
+void sq_hamiltonian_set_etab_alu(int on);          // panel kernels without an E_pq table (records computed from (p,q); default off)
 void sq_hamiltonian_set_rdm_tri(int on);           // RDMs with bra == ket: three half-size DGEMMs instead of one (default off)
 void sq_hamiltonian_set_etab_mode(int use_const);  // E_pq table in constant (1) or shared (0) memory
 int sq_ensure_work(sq_space* sp, int which);

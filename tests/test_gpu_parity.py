@@ -845,3 +845,44 @@ def test_rdm_triangle_variant_agrees(sq):
     assert np.max(np.abs(d1 - e1)) < 1e-12 and np.max(np.abs(d2 - e2)) < 1e-12
     assert np.max(np.abs(t1 - u1)) < 1e-12 and np.max(np.abs(t2 - u2)) < 1e-12
     assert abs(np.trace(e1) - (na + nb)) < 1e-12
+
+
+@pytest.mark.skipif(
+    __import__("os").environ.get("SQ_RUN_UNVERIFIED") != "1",
+    reason="the table-free panel kernels (etab=alu) were written without GPU time (compiled, never run): opt in with SQ_RUN_UNVERIFIED=1",
+)
+def test_table_free_panel_kernels_agree(sq):
+    """sq_set_option("etab", "alu"): sigma (symmetric and unsymmetric integrals) against the oracle and RDMs / transition RDMs
+    against the table kernels, with small panels (several panels, a partial last one)."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    lib = sq.lib.load()
+    n, na, nb = 8, 4, 3
+    rng = np.random.default_rng(7)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    g_unsym = g + 0.05 * rng.normal(size=(n, n, n, n))
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    state = rng.normal(size=sp.num_det)
+    state /= np.linalg.norm(state)
+    other = rng.normal(size=sp.num_det)
+    results = []
+    try:
+        for etab in (b"smem", b"alu"):
+            lib.sq_set_option(b"panel", b"768")
+            lib.sq_set_option(b"etab", etab)
+            info = sq.ci.get_indexing(0, n, 0, na, nb)
+            for gg in (g, g_unsym):
+                ref = orc.propagate_state([orc.hamiltonian_0i_0a(h, gg, 0, n)], state, sp)
+                out = sq.osa.propagate_state([hamiltonian_0i_0a(h, gg, 0, n)], state, info)
+                assert np.max(np.abs(out - ref)) < 1e-11, etab
+            results.append(sq.osa.reduced_density_matrices(state, state, info) + sq.osa.reduced_density_matrices(other, state, info))
+    finally:
+        lib.sq_set_option(b"panel", b"0")
+        lib.sq_set_option(b"etab", b"smem")
+    for x, y in zip(*results):
+        assert np.max(np.abs(x - y)) < 1e-12

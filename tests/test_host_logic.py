@@ -489,12 +489,24 @@ def test_extended_space_tables_bit_exact():
         extended_idx2det(1, 2, 1, 1, 1, 3)
 
 
+def test_table_free_E_records_equal_the_table():
+    """sq_set_option("etab", "alu"): the record of E_pq the table-free panel kernels compute from (p, q, spin) equals, field by
+    field, the table entry built from the closed-form string action (which test_closed_form_string_action_equals_literal_loop
+    pins to the reference's flip / popcount loop), for every (p, q, spin) of several active-space sizes."""
+    for n, na, nb in [(2, 1, 1), (5, 3, 1), (8, 4, 4), (16, 8, 8), (20, 10, 10), (26, 2, 2)]:
+        lib, h = _host_space(n, na, nb)
+        bad = C.c_int(-1)
+        _lib.check(lib.sq_debug_etab_closed_form(h, C.byref(bad)))
+        assert bad.value == 0, (n, bad.value)
+        lib.sq_space_destroy(h)
+
+
 def test_runtime_switches_are_known():
     """sq_set_option: every switch named in include/sqsv.h is accepted, anything else is an error (host call, no kernel)."""
     lib = _lib.load()
     for name, value in (
         (b"win", b"1"), (b"wingrad", b"0"), (b"pipeline", b"1"), (b"etab", b"smem"), (b"rows", b"0"), (b"rows_cfg", b"1024,0"),
-        (b"panel", b"0"), (b"rdm_tri", b"0"),
+        (b"panel", b"0"), (b"rdm_tri", b"0"), (b"etab", b"alu"), (b"etab", b"smem"),
     ):
         assert lib.sq_set_option(name, value) == 0, name
     assert lib.sq_set_option(b"no-such-switch", b"1") != 0

@@ -10,6 +10,9 @@ SQ_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_distributed.py -
 echo "unverified rc=$?"; tail -15 $out/${tag}_unverified.log
 SQ_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "rdm_triangle" > $out/${tag}_rdm_tri.log 2>&1
 echo "rdm_tri rc=$?"; tail -5 $out/${tag}_rdm_tri.log
+SQ_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "table_free" > $out/${tag}_etab_alu.log 2>&1
+echo "etab alu rc=$?"; tail -5 $out/${tag}_etab_alu.log
+timeout 300 python tools/ab_option.py 16 etab smem alu > $out/${tag}_ab_etab_alu.txt 2>&1; tail -12 $out/${tag}_ab_etab_alu.txt
 timeout 300 python tools/ab_option.py 16 rdm_tri 0 1 > $out/${tag}_ab_rdm_tri.txt 2>&1; tail -12 $out/${tag}_ab_rdm_tri.txt
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "per_string" > $out/${tag}_strings.log 2>&1
 echo "per-string rc=$?"; tail -5 $out/${tag}_strings.log
