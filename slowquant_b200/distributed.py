@@ -316,10 +316,15 @@ def shift_rule(R: int) -> tuple[np.ndarray, np.ndarray]:
 
 
 def energy_and_theta_gradient_sharded(
-    reference: ShardedState, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0
+    reference: ShardedState, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0,
+    fused_local: bool = True,
 ) -> tuple[float, np.ndarray]:
     r"""Energy and :math:`\partial E/\partial\theta_k` of :math:`U(\theta)|\text{reference}\rangle` on an alpha-sharded
     vector (the theta part of ``_calc_gradient_optimization``, ups_wavefunction.py:1091-1138).  ``reference`` is not modified.
+
+    Stretches of bricks whose row pairs are all local (on G GPUs: every pair (p, p+1) with p >= log2 G) go through the fused
+    single-GPU gradient kernels on the shards plus one all-reduce per stretch; operators that pair rows of two GPUs use the
+    shift rule (``fused_local=False``: shift rule everywhere).
 
     STATUS: composition of GPU-verified sharded primitives with ``sigma_sharded`` (first GPU run pending, see there); the
     shift-rule arithmetic is checked on the CPU against the oracle's literal gradient loop (tests/test_distributed_host.py)."""
@@ -340,19 +345,44 @@ def energy_and_theta_gradient_sharded(
     tmp = sp.alloc_state(zero=False)
     grad = np.zeros(P)
     probe = np.zeros(P)
+    lib = _lib.load()
+    lay = osa.compile_layout(sp.ci_info, ups_struct)
+    PD = C.POINTER(C.c_double)
+    idx = ups_struct.excitation_indices
+
+    def brick_operator(k: int) -> bool:   # sa_single / pair double on neighbouring orbitals: the fused tile kernels take these
+        t, ind = types[k], idx[k]
+        if t == "sa_single":
+            return True
+        return t == "double" and len(ind) == 4 and ind[0] % 2 == 0 and ind[1] == ind[0] + 1 and ind[2] % 2 == 0 and ind[3] == ind[2] + 1
+
     try:
-        for k in range(P):
-            xs, ws = shift_rule(_AMPLITUDE_FREQUENCIES[types[k]])
-            acc = 0.0
-            for x, w in zip(xs, ws):
-                tmp.local.copy_(ket.local)
-                probe[k] = x
-                construct_ups_state_sharded(tmp, probe, ups_struct, first=k, last=k + 1)
-                acc += w * dot_sharded(bra, tmp)
-            probe[k] = 0.0
-            grad[k] = 2.0 * acc
-            construct_ups_state_sharded(bra, th, ups_struct, first=k, last=k + 1)
-            construct_ups_state_sharded(ket, th, ups_struct, first=k, last=k + 1)
+        for f, l, exchange in sp.exchange_plan(ups_struct, 0, P, False):
+            if not exchange and fused_local and all(brick_operator(k) for k in range(f, l)):
+                # every row pair of these operators is local: the fused single-GPU sweep (g_k and both rotations in one kernel
+                # per brick, sq_ups_grad_sweep) runs on the shards; <bra|T_k|ket> is a sum over rows -> one all-reduce
+                part = np.zeros(l - f, dtype=np.float64)
+                if sp.local_len:
+                    _lib.check(lib.sq_ups_grad_sweep(sp.ci_info._handle, lay, th.ctypes.data_as(PD), f, l, osa._ptr(bra.local),
+                                                     osa._ptr(ket.local), part.ctypes.data_as(PD), osa._stream()))
+                if sp.world > 1:
+                    t = torch.from_numpy(part).to(ket.local.device)
+                    dist.all_reduce(t)
+                    part = t.cpu().numpy()
+                grad[f:l] = part
+                continue
+            for k in range(f, l):   # operators that pair rows of two GPUs (or that the tile kernels do not take): shift rule
+                xs, ws = shift_rule(_AMPLITUDE_FREQUENCIES[types[k]])
+                acc = 0.0
+                for x, w in zip(xs, ws):
+                    tmp.local.copy_(ket.local)
+                    probe[k] = x
+                    construct_ups_state_sharded(tmp, probe, ups_struct, first=k, last=k + 1)
+                    acc += w * dot_sharded(bra, tmp)
+                probe[k] = 0.0
+                grad[k] = 2.0 * acc
+                construct_ups_state_sharded(bra, th, ups_struct, first=k, last=k + 1)
+                construct_ups_state_sharded(ket, th, ups_struct, first=k, last=k + 1)
     finally:
         tmp.close()
         bra.close()

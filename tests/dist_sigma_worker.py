@@ -67,9 +67,10 @@ def main():
             e1, g1 = osa.ups_energy_and_gradient(hf, info, th, lay, hamiltonian_0i_0a(h, g, 0, n))
             ref_st = sp.alloc_state()
             ref_st.set_determinant(0)
-            e2, g2 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0)
+            e2, g2 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0)                       # fused local stretches
+            e3, g3 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0, fused_local=False)    # shift rule everywhere
             ref_st.close()
-            err_g = max(abs(e1 - e2), float(np.max(np.abs(g1 - g2)))) / max(1.0, abs(e1))
+            err_g = max(abs(e1 - e2), abs(e1 - e3), float(np.max(np.abs(g1 - g2))), float(np.max(np.abs(g1 - g3)))) / max(1.0, abs(e1))
         e = torch.tensor([err, max(err_e, err_g)], dtype=torch.float64, device="cuda")
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         if rank == 0:
