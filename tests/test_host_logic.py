@@ -445,6 +445,46 @@ def test_launch_plan_is_a_valid_reordering(n, na, nb, options, win):
         lib.sq_space_destroy(h)
 
 
+@pytest.mark.parametrize("n,na,nb,L,qnp", [(6, 3, 3, 4, False), (7, 3, 4, 3, True), (8, 4, 4, 3, False)])
+def test_launch_plan_order_gives_the_same_state(n, na, nb, L, qnp):
+    """Numerical twin of test_launch_plan_is_a_valid_reordering: applying the operators one by one in the ORDER OF THE PLAN
+    (oracle, CPU) gives the state of the circuit order -- forward and adjoint, with some angles zero."""
+    from slowquant_b200.util import UpsStructure
+
+    lib, h = _host_space(n, na, nb)
+    ups = UpsStructure()
+    ups.create_tiled(n, {"n_layers": L, "do_qnp": True} if qnp else {"n_layers": L, "do_tups": True})
+    lay = _layout_handle(lib, h, ups)
+    P = ups.n_params
+    types, idxs = list(ups.excitation_operator_type), [tuple(int(x) for x in i) for i in ups.excitation_indices]
+    rng = np.random.default_rng(90 + n)
+    th = rng.uniform(-np.pi, np.pi, P)
+    th[rng.choice(P, size=P // 8, replace=False)] = 0.0
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    state = rng.normal(size=sp.num_det)
+    state /= np.linalg.norm(state)
+    ops_out = np.empty(P, dtype=np.int32)
+    launch_out = np.empty(P, dtype=np.int32)
+    n_out = C.c_int(0)
+    pi32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    try:
+        _lib.check(lib.sq_set_option(b"win", b"1"))
+        for dagger in (False, True):
+            ref = orc.construct_ups_state(state, sp, th, types, idxs, dagger=dagger)
+            _lib.check(
+                lib.sq_layout_plan_export(lay, th.ctypes.data_as(C.POINTER(C.c_double)), 0, P, int(dagger), pi32(ops_out), pi32(launch_out), P, C.byref(n_out))
+            )
+            cur = state.copy()
+            for k in ops_out[: n_out.value]:
+                k = int(k)
+                cur = orc.construct_ups_state(cur, sp, th[k : k + 1], types[k : k + 1], idxs[k : k + 1], dagger=dagger)
+            assert np.max(np.abs(cur - ref)) < 1e-13
+            assert int(launch_out[n_out.value - 1]) + 1 < n_out.value        # the plan fuses operators
+    finally:
+        lib.sq_layout_destroy(lay)
+        lib.sq_space_destroy(h)
+
+
 def test_lr_orbital_blocks_match_reference():
     """RDM-only linear-response orbital blocks (reference density_matrix.py:233-563) against outputs of the reference
     itself on seeded random h, g, x, rdm1, rdm2 (tests/golden/make_golden_lr.py), incl. no-inactive / no-virtual spaces."""
