@@ -315,6 +315,28 @@ def shift_rule(R: int) -> tuple[np.ndarray, np.ndarray]:
     return x, w
 
 
+def gradient_segments(plan: list[tuple[int, int, bool]], ups_struct, fused_local: bool = True) -> list[tuple[int, int, bool]]:
+    """Split the exchange plan of a circuit into (first, last, fused) stretches for the sharded theta gradient: ``fused`` = every
+    row pair is local AND every operator is a brick operator (sa_single, or a pair double (2p, 2p+1, 2q, 2q+1)) that the fused
+    tile gradient kernels take; everything else is differentiated with the shift rule, one operator at a time."""
+    types, idx = ups_struct.excitation_operator_type, ups_struct.excitation_indices
+
+    def brick_operator(k: int) -> bool:
+        t, ind = types[k], idx[k]
+        if t == "sa_single":
+            return True
+        return t == "double" and len(ind) == 4 and ind[0] % 2 == 0 and ind[1] == ind[0] + 1 and ind[2] % 2 == 0 and ind[3] == ind[2] + 1
+
+    out: list[tuple[int, int, bool]] = []
+    for f, l, exchange in plan:
+        fused = bool(fused_local and not exchange and all(brick_operator(k) for k in range(f, l)))
+        if out and out[-1][2] == fused and out[-1][1] == f and fused:
+            out[-1] = (out[-1][0], l, True)      # neighbouring fused stretches: one sweep, one all-reduce
+        else:
+            out.append((f, l, fused))
+    return out
+
+
 def energy_and_theta_gradient_sharded(
     reference: ShardedState, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0,
     fused_local: bool = True,
@@ -348,17 +370,10 @@ def energy_and_theta_gradient_sharded(
     lib = _lib.load()
     lay = osa.compile_layout(sp.ci_info, ups_struct)
     PD = C.POINTER(C.c_double)
-    idx = ups_struct.excitation_indices
-
-    def brick_operator(k: int) -> bool:   # sa_single / pair double on neighbouring orbitals: the fused tile kernels take these
-        t, ind = types[k], idx[k]
-        if t == "sa_single":
-            return True
-        return t == "double" and len(ind) == 4 and ind[0] % 2 == 0 and ind[1] == ind[0] + 1 and ind[2] % 2 == 0 and ind[3] == ind[2] + 1
 
     try:
-        for f, l, exchange in sp.exchange_plan(ups_struct, 0, P, False):
-            if not exchange and fused_local and all(brick_operator(k) for k in range(f, l)):
+        for f, l, fused in gradient_segments(sp.exchange_plan(ups_struct, 0, P, False), ups_struct, fused_local):
+            if fused:
                 # every row pair of these operators is local: the fused single-GPU sweep (g_k and both rotations in one kernel
                 # per brick, sq_ups_grad_sweep) runs on the shards; <bra|T_k|ket> is a sum over rows -> one all-reduce
                 part = np.zeros(l - f, dtype=np.float64)

@@ -170,3 +170,28 @@ def test_sharded_gradient_composition_equals_literal_loop(layout):
         bra = orc.construct_ups_state(bra, sp, th[k : k + 1], types[k : k + 1], idx[k : k + 1])
         ket = orc.construct_ups_state(ket, sp, th[k : k + 1], types[k : k + 1], idx[k : k + 1])
     assert np.max(np.abs(grad - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_gradient_segments_cover_the_circuit_once():
+    """distributed.gradient_segments: the stretches tile [0, P) in order; only local stretches made of brick operators are fused;
+    fused_local=False sends everything to the shift rule."""
+    from slowquant_b200.distributed import gradient_segments
+    from slowquant_b200.util import UpsStructure
+
+    ups = UpsStructure()
+    ups.create_tiled(6, {"n_layers": 2, "do_tups": True})
+    types, idxs = list(ups.excitation_operator_type), [tuple(i) for i in ups.excitation_indices]
+    types[10:10] = ["single"]                       # a generic operator inside a local stretch
+    idxs[10:10] = [(4, 10)]
+    ups.excitation_operator_type, ups.excitation_indices, ups.n_params = types, idxs, len(types)
+    P = len(types)
+    # a plan as exchange_plan builds it: maximal ranges, exchange ranges hold one orbital pair
+    plan = [(0, 3, True), (3, 16, False), (16, 19, True), (19, P, False)]
+    seg = gradient_segments(plan, ups)
+    assert seg[0][0] == 0 and seg[-1][1] == P and all(a[1] == b[0] for a, b in zip(seg, seg[1:]))
+    assert [s for s in seg if s[2]] == [(19, P, True)]            # (3, 16) holds the generic single -> not fused
+    assert all(not s[2] for s in gradient_segments(plan, ups, fused_local=False))
+    del types[10], idxs[10]
+    ups.n_params = len(types)
+    seg = gradient_segments([(0, 3, True), (3, 15, False), (15, 18, True), (18, P - 1, False)], ups)
+    assert [s[2] for s in seg] == [False, True, False, True]
