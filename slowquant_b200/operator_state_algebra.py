@@ -725,3 +725,36 @@ def add_operator_matrix(
     op = _string_operator("serial", a_string, len(np.asarray(anni_idx).ravel()), create_screen, factor)
     op_mat += build_operator_matrix(op, _space_of_tables(det2idx), do_unsafe=bool(do_unsafe))
     return op_mat
+
+
+def get_determinant_expansion_from_operator_on_HF(
+    operator: FermionicOperator, num_active_orbs: int, num_active_elec_alpha: int, num_active_elec_beta: int
+) -> tuple[list[float], list[str]]:
+    """Coefficients and determinants (bit strings a0 b0 a1 b1 ..., orbital 0 first) of ``operator|HF>``, one entry per ladder
+    string that does not annihilate the Hartree-Fock determinant (osa.py:2979-3033).  Host only: every string goes through the
+    closed-form string action of the engine (``sq_debug_string_action`` -- screens, flip masks and sign of DESIGN.md section 2)
+    instead of the reference's operator-by-operator bit loop."""
+    lib = _lib.load()
+    n = int(num_active_orbs)
+    handle = C.c_void_p()
+    _lib.check(lib.sq_space_create(n, int(num_active_elec_alpha), int(num_active_elec_beta), -1, 0, -1, C.byref(handle)))
+    occ_a, occ_b = (1 << int(num_active_elec_alpha)) - 1, (1 << int(num_active_elec_beta)) - 1
+    coeffs: list[float] = []
+    dets: list[str] = []
+    valid, sign = C.c_int32(0), C.c_int32(0)
+    tgt_a, tgt_b = C.c_uint32(0), C.c_uint32(0)
+    try:
+        for label, factor in operator.operators.items():
+            ops = np.asarray([2 * int(i) + (1 if dag else 0) for i, dag in label] or [0], dtype=np.int32)
+            _lib.check(
+                lib.sq_debug_string_action(
+                    handle, ops.ctypes.data_as(_PI), len(label), occ_a, occ_b, C.byref(valid), C.byref(tgt_a), C.byref(tgt_b), C.byref(sign)
+                )
+            )
+            if not valid.value:
+                continue
+            coeffs.append(factor * sign.value)
+            dets.append("".join(str((tgt_a.value >> o) & 1) + str((tgt_b.value >> o) & 1) for o in range(n)))
+    finally:
+        lib.sq_space_destroy(handle)
+    return coeffs, dets

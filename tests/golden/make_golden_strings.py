@@ -81,3 +81,24 @@ for n, a, b in EDGE:
 
 np.savez_compressed(os.path.join(HERE, "golden_strings.npz"), **out)
 print("wrote golden_strings.npz:", len(labels), "strings,", N, "determinants")
+
+# get_determinant_expansion_from_operator_on_HF (osa.py:2979-3033): reference outputs for a set of operators on two spaces
+import json  # noqa: E402
+
+hf_cases = []
+for nA_, na_, nb_ in ((4, 2, 2), (5, 3, 1)):
+    ops_ = {
+        "G1": rops.G1(0, 2 * nA_ - 2, True),
+        "G2": rops.G2(0, 1, 2 * nA_ - 2, 2 * nA_ - 1, True),
+        "G1_sa": rops.G1_sa(0, nA_ - 1, True),
+        "G2_sa_1": rops.G2_sa(0, 1, nA_ - 2, nA_ - 1, 1, True),
+        "G2_sa_4": rops.G2_sa(0, 1, nA_ - 2, nA_ - 1, 4, False),
+        "number": rops.Epq(0, 0) * 1.5 + rops.Epq(nA_ - 1, nA_ - 1) * 0.5 + rops.epqrs(0, 0, 1, 1) * 0.25,
+        "mixed": rops.Epq(nA_ - 1, 0) * rops.Epq(nA_ - 2, 1) * 0.7 + rops.Epq(1, 0) * 0.3,
+    }
+    for name, op in ops_.items():
+        c, d = rosa.get_determinant_expansion_from_operator_on_HF(op, nA_, na_, nb_)
+        hf_cases.append({"space": [nA_, na_, nb_], "name": name, "operator": [[[list(x) for x in k], v] for k, v in op.operators.items()],
+                         "coeffs": [float(x) for x in c], "dets": list(d)})
+json.dump(hf_cases, open(os.path.join(HERE, "golden_hf_expansion.json"), "w"))
+print("wrote golden_hf_expansion.json:", len(hf_cases), "cases")

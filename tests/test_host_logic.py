@@ -485,6 +485,27 @@ def test_launch_plan_order_gives_the_same_state(n, na, nb, L, qnp):
         lib.sq_space_destroy(h)
 
 
+def test_determinant_expansion_on_hf_matches_reference():
+    """get_determinant_expansion_from_operator_on_HF (osa.py:2979-3033) through the engine's closed-form string action, against
+    outputs of the reference (tests/golden/make_golden_strings.py): excitation generators, spin-adapted doubles, number
+    operators (creator == annihilator) and products, on CAS(4,4) and CAS(4,5) with 3 alpha / 1 beta electrons."""
+    import json
+    import os
+
+    from slowquant_b200.operator_state_algebra import get_determinant_expansion_from_operator_on_HF
+
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_hf_expansion.json")))
+    assert len(cases) == 14
+    n_terms = 0
+    for case in cases:
+        op = FermionicOperator({tuple((int(i), bool(d)) for i, d in label): float(v) for label, v in case["operator"]})
+        coeffs, dets = get_determinant_expansion_from_operator_on_HF(op, *case["space"])
+        assert dets == case["dets"], case["name"]
+        assert np.allclose(coeffs, case["coeffs"], rtol=0, atol=1e-15), case["name"]
+        n_terms += len(dets)
+    assert n_terms > 20
+
+
 def test_lr_orbital_blocks_match_reference():
     """RDM-only linear-response orbital blocks (reference density_matrix.py:233-563) against outputs of the reference
     itself on seeded random h, g, x, rdm1, rdm2 (tests/golden/make_golden_lr.py), incl. no-inactive / no-virtual spaces."""
