@@ -22,6 +22,11 @@ Label = tuple[Ladder, ...]
 _DROP = 10**-14  # threshold below which a coefficient created by cancellation is removed (fermionic_operator.py:100)
 
 
+def operator_to_qiskit_key(operator_string: Label, remapping: dict[int, int]) -> str:
+    """``"+_i -_j ..."`` key of one ladder string with remapped spin-orbital indices (fermionic_operator.py:7-24)."""
+    return " ".join(("+_" if dagger else "-_") + str(remapping[idx]) for idx, dagger in operator_string)
+
+
 def _canonical_before(x: Ladder, y: Ladder) -> bool:
     """True when x may stand directly left of y in a normal-ordered string (x != y assumed)."""
     if x[1] != y[1]:
@@ -182,6 +187,12 @@ class FermionicOperator:
         }
 
     # ---- folding onto the active space --------------------------------------------------------
+    def get_qiskit_form(self, num_orbs: int) -> dict[str, float]:
+        """Operator as ``{"+_i -_j": coefficient}`` in blocked spin order -- interleaved index 2p + s maps to p + s * num_orbs
+        (all alpha, then all beta; fermionic_operator.py:357-377).  String formatting only; no Qiskit import."""
+        remapping = {2 * p + spin: p + spin * num_orbs for p in range(num_orbs) for spin in (0, 1)}
+        return {operator_to_qiskit_key(label, remapping): factor for label, factor in self.operators.items()}
+
     def get_folded_operator(
         self, num_inactive_orbs: int, num_active_orbs: int, num_virtual_orbs: int
     ) -> "FermionicOperator":

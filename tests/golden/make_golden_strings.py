@@ -102,3 +102,11 @@ for nA_, na_, nb_ in ((4, 2, 2), (5, 3, 1)):
                          "coeffs": [float(x) for x in c], "dets": list(d)})
 json.dump(hf_cases, open(os.path.join(HERE, "golden_hf_expansion.json"), "w"))
 print("wrote golden_hf_expansion.json:", len(hf_cases), "cases")
+
+# FermionicOperator.get_qiskit_form (fermionic_operator.py:357-377): reference key strings and coefficients
+qk = []
+for num_orbs_, op in ((4, rops.G2_sa(0, 1, 2, 3, 4, True)), (3, rops.Epq(0, 2) * rops.Epq(1, 1)), (5, rops.G3(0, 2, 1, 6, 4, 7, False) * 0.5 + rops.G1(3, 8, True))):
+    qk.append({"num_orbs": num_orbs_, "operator": [[[list(x) for x in k], v] for k, v in op.operators.items()],
+               "qiskit_form": [[k, float(v)] for k, v in op.get_qiskit_form(num_orbs_).items()]})
+json.dump(qk, open(os.path.join(HERE, "golden_qiskit_form.json"), "w"))
+print("wrote golden_qiskit_form.json:", len(qk), "operators")

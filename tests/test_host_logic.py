@@ -506,6 +506,23 @@ def test_determinant_expansion_on_hf_matches_reference():
     assert n_terms > 20
 
 
+def test_qiskit_form_matches_reference():
+    """FermionicOperator.get_qiskit_form / operator_to_qiskit_key (fermionic_operator.py:7-24, 357-377): key strings in blocked
+    spin order and coefficients against reference outputs (string formatting only, no Qiskit)."""
+    import json
+    import os
+
+    from slowquant_b200.fermionic_operator import operator_to_qiskit_key
+
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_qiskit_form.json")))
+    for case in cases:
+        op = FermionicOperator({tuple((int(i), bool(d)) for i, d in label): float(v) for label, v in case["operator"]})
+        got = op.get_qiskit_form(case["num_orbs"])
+        assert list(got.keys()) == [k for k, _ in case["qiskit_form"]]
+        assert np.allclose(list(got.values()), [v for _, v in case["qiskit_form"]], rtol=0, atol=0)
+    assert operator_to_qiskit_key(((3, True), (0, False)), {0: 0, 3: 5}) == "+_5 -_0"
+
+
 def test_lr_orbital_blocks_match_reference():
     """RDM-only linear-response orbital blocks (reference density_matrix.py:233-563) against outputs of the reference
     itself on seeded random h, g, x, rdm1, rdm2 (tests/golden/make_golden_lr.py), incl. no-inactive / no-virtual spaces."""
