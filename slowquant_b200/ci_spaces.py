@@ -76,9 +76,15 @@ class CI_Info:
         num_virtual_orbs: int,
         num_active_elec_alpha: int,
         num_active_elec_beta: int,
+        idx2det=None,
+        det2idx=None,
         device: int | None = None,
         row_range: tuple[int, int] | None = None,
     ) -> None:
+        """``idx2det`` / ``det2idx`` occupy the positions they have in the reference's constructor (ci_spaces.py:12-21).  The engine
+        derives both tables from the string lists, so a caller-supplied ``idx2det`` is only checked: it must be the determinant
+        list of this product space in the reference's order (anything else -- e.g. an extended space -- needs
+        ``get_indexing_extended``); ``det2idx`` is ignored."""
         self.num_inactive_orbs = num_inactive_orbs
         self.num_active_orbs = num_active_orbs
         self.num_virtual_orbs = num_virtual_orbs
@@ -104,6 +110,13 @@ class CI_Info:
         self._idx2det: np.ndarray | None = None
         self.det2idx = _Det2Idx(self)
         self._layouts: dict = {}
+        if idx2det is not None:
+            given = np.asarray(idx2det, dtype=np.int64)
+            if given.shape != (self.num_det,) or not np.array_equal(given, self.idx2det):
+                raise ValueError(
+                    "idx2det is not the determinant list of the (num_active_orbs, n_alpha, n_beta) product space in "
+                    "get_indexing order; build extended spaces with get_indexing_extended"
+                )
 
     @property
     def idx2det(self) -> np.ndarray:

@@ -81,6 +81,21 @@ def test_degenerate_spaces_bit_exact():
         lib.sq_space_destroy(h)
 
 
+def test_ci_info_constructor_takes_the_reference_tables(golden):
+    """CI_Info(nI, nA, nV, n_alpha, n_beta, idx2det, det2idx) -- the reference's positional call (ci_spaces.py:12-21): the tables are
+    derived by the engine, a supplied idx2det must be this product space's list in get_indexing order."""
+    from slowquant_b200.ci_spaces import CI_Info
+
+    arrays, _, _ = golden
+    ref = arrays["idx2det_5_2_3"]
+    info = CI_Info(0, 5, 0, 2, 3, ref, {int(d): i for i, d in enumerate(ref)}, device=-1)
+    assert info.num_det == len(ref) and info.det2idx[int(ref[7])] == 7 and int(ref[3]) in info.det2idx and 0 not in info.det2idx
+    with pytest.raises(ValueError):
+        CI_Info(0, 5, 0, 2, 3, ref[::-1].copy(), None, device=-1)
+    with pytest.raises(ValueError):
+        CI_Info(0, 5, 0, 2, 3, ref[:-1].copy(), None, device=-1)
+
+
 def test_space_argument_errors():
     lib = _lib.load()
     h = C.c_void_p()
