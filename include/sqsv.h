@@ -182,6 +182,13 @@ int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double
 int sq_sigma_dist(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
                   double* const* out_ptrs_host, void* stream);
 
+/* The theta-gradient loop (ups_wavefunction.py:1114-1138) over operators [first,last) of an alpha-sharded (bra, ket) pair
+ * whose row pairs may live on two GPUs (sa_single / pair-double operators): g_k = 2 <bra|T_k|ket>, then both vectors <- U_k,
+ * one fused launch per brick with cross-device tiles rotated in place through the peer mappings.  grad_host receives THIS
+ * rank's partial sums (add the ranks' results); device-wide barrier before and after. */
+int sq_ups_grad_sweep_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                           double* const* bra_ptrs_host, double* const* ket_ptrs_host, double* grad_host, void* stream);
+
 /* ---- generic operator application (apply_operator_serial/threaded, :53-219; propagate_state
  *      inner loop, :596-628) -------------------------------------------------------------------- */
 

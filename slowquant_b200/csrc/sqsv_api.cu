@@ -1475,6 +1475,85 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
   return status;
 }
 
+
+// Gradient sweep over operators [first,last) of an ALPHA-SHARDED (bra, ket) pair whose row pairs may live on two GPUs (an exchange
+// stretch of the plan: sa_single / pair-double operators only).  Same arithmetic as sq_ups_grad_sweep, one fused launch per brick;
+// cross-device tiles are read and written in place through the peer mappings.  grad_host receives THIS rank's partial
+// 2 <bra|T_k|ket> (the tiles it processed): the caller adds the ranks' results and puts a device-wide barrier before and after.
+// Written without GPU time (compiled, not yet run); the Python side uses it only on request (peer_gradient=True).
+extern "C" int sq_ups_grad_sweep_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
+                                      double* const* bra_ptrs_host, double* const* ket_ptrs_host, double* grad_host, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !bra_ptrs_host || !ket_ptrs_host || !grad_host) return SQ_ERR_INVALID;
+  const int P = (int)lay->ops.size();
+  if (first < 0 || last > P || first > last) return SQ_ERR_INVALID;
+  if (sp->device < 0 || sp->world < 1 || sp->world > SQ_MAX_WORLD) return SQ_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  for (int k = first; k < last; ++k) grad_host[k - first] = 0.0;
+  double* bra_dev = bra_ptrs_host[sp->rank];
+  double* ket_dev = ket_ptrs_host[sp->rank];
+  if (!bra_dev || !ket_dev) return SQ_ERR_INVALID;
+  std::vector<double> plan_th(P, 1.0);
+  std::vector<int> order;
+  exec_order(first, last, 0, &order);
+  std::vector<std::vector<int>> runs;
+  plan_runs(lay, order, plan_th.data(), &runs);
+  std::vector<int> slot_op;
+  std::vector<int> run_slot0(runs.size(), -1);
+  for (size_t ri = 0; ri < runs.size(); ++ri) {
+    if (!is_tile_op(lay->ops[runs[ri][0]])) {
+      sq_set_error("sq_ups_grad_sweep_dist: operator %d is not a brick operator (sa_single / pair double)", runs[ri][0]);
+      return SQ_ERR_UNSUPPORTED;
+    }
+    run_slot0[ri] = (int)slot_op.size();
+    for (int k : runs[ri])
+      for (int s = 0; s < tile_steps_of(lay->ops[k]); ++s) slot_op.push_back(k);
+  }
+  if (slot_op.empty()) return SQ_OK;
+  // device copies of the two base-pointer tables (pageable source: the copy is staged before the call returns)
+  unsigned long long tabs[2 * SQ_MAX_WORLD];
+  for (int r = 0; r < SQ_MAX_WORLD; ++r) {
+    tabs[r] = r < sp->world ? (unsigned long long)(uintptr_t)bra_ptrs_host[r] : 0ull;
+    tabs[SQ_MAX_WORLD + r] = r < sp->world ? (unsigned long long)(uintptr_t)ket_ptrs_host[r] : 0ull;
+  }
+  unsigned long long* d_tabs = nullptr;
+  double* d_grad = nullptr;
+  SQ_CUDA(cudaMallocAsync(&d_tabs, sizeof(tabs), st));
+  SQ_CUDA(cudaMemcpyAsync(d_tabs, tabs, sizeof(tabs), cudaMemcpyHostToDevice, st));
+  SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st));
+  SQ_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * slot_op.size(), st));
+  int status = SQ_OK;
+  for (size_t ri = 0; ri < runs.size() && status == SQ_OK; ++ri) {
+    const std::vector<int>& run = runs[ri];
+    const LayoutOp& op = lay->ops[run[0]];
+    TileStep steps[SQ_MAX_PROGRAM];
+    int n_steps = 0, step_op[SQ_MAX_PROGRAM];
+    status = run_tile(sp, lay, run, thetas_host, 0, steps, &n_steps, step_op);
+    if (status != SQ_OK) break;
+    for (int s = 0; s < n_steps; ++s)   // zero angles: the gradient is taken, the rotation is the identity
+      if (std::fabs(thetas_host[step_op[s]]) < 1e-28) { steps[s].c = 1.0; steps[s].s = 0.0; }
+    const PairTables& pt = lay->pairs[op.pair];
+    if (pt.n_cross_items > 0)
+      status = sq_launch_tile_grad_peer(sp, pt, steps, n_steps, bra_dev, ket_dev, d_tabs, d_tabs + SQ_MAX_WORLD, d_grad + run_slot0[ri], st);
+    else
+      status = sq_launch_tile_grad(sp, pt, steps, n_steps, bra_dev, ket_dev, d_grad + run_slot0[ri], st);
+  }
+  if (status == SQ_OK) {
+    std::vector<double> g(slot_op.size());
+    cudaError_t e = cudaMemcpyAsync(g.data(), d_grad, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      sq_set_error("sq_ups_grad_sweep_dist: %s", cudaGetErrorString(e));
+      status = SQ_ERR_CUDA;
+    } else {
+      for (size_t i = 0; i < g.size(); ++i) grad_host[slot_op[i] - first] += 2.0 * g[i];
+    }
+  }
+  cudaFreeAsync(d_grad, st);
+  cudaFreeAsync(d_tabs, st);
+  return status;
+}
+
 // ---------------------------------------------------------------------------------------------
 // generic operators and BLAS-1
 // ---------------------------------------------------------------------------------------------

@@ -246,6 +246,9 @@ int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, i
                    const TileStep* steps2, int n2, int sigma2, double* state, cudaStream_t st);
 int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                         double* bra, double* ket, double* grad_out_host, cudaStream_t st);
+int sq_launch_tile_grad_peer(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps, double* bra, double* ket,
+                             const unsigned long long* d_tab_bra, const unsigned long long* d_tab_ket, double* d_out,
+                             cudaStream_t st);
 int sq_launch_gen_rot(sq_space* sp, const GenTables& gt, double c, double s, double* state,
                       cudaStream_t st);
 int sq_launch_gen_apply(sq_space* sp, const GenTables& gt, const double* in, double* out,

@@ -502,6 +502,122 @@ tile_grad_kernel_v2(double* __restrict__ BRA, double* __restrict__ KET, const in
   block_reduce_store<SQ_MAX_PROGRAM>(acc, partial, (int64_t)blockIdx.y * gridDim.x + blockIdx.x);
 }
 
+// tile_grad_peer_kernel: tile_grad_kernel_v2 for an exchange operator of an alpha-sharded (bra, ket) pair -- the two rows of a
+// tile may live on two GPUs; both are read and written in place through the peer mappings (Bases<true>, one table per vector), and a
+// cross-device row pair is split between its two owners by column-CTA parity exactly as in tile_kernel_v2<true> (item_on).  Every
+// rank accumulates <bra|T_step|ket> over the tiles IT processes; the caller adds the ranks' partial sums (all-reduce).
+// Written without GPU time (compiled, not yet run): reached only through sq_ups_grad_sweep_dist.
+__global__ void __launch_bounds__(TILE_THREADS)
+tile_grad_peer_kernel(const Bases<true> BB, const Bases<true> KB, const int2* __restrict__ colItems, int n_colblk_src,
+                      const int4* __restrict__ rowItems, int n_rowchunk_src, int64_t NB, const GradProgram gp,
+                      double* __restrict__ partial) {
+  double acc[SQ_MAX_PROGRAM];
+#pragma unroll
+  for (int k = 0; k < SQ_MAX_PROGRAM; ++k) acc[k] = 0.0;
+  const bool col_src = (int)blockIdx.x < n_colblk_src;
+  const bool row_src = (int)blockIdx.y < n_rowchunk_src;
+  const int2 ci = __ldg(colItems + (int64_t)blockIdx.x * TILE_THREADS + threadIdx.x);
+  if ((col_src || row_src) && ci.x >= 0) {
+    const int64_t ib = ci.x;
+    const int64_t ibp = ci.y & 0x07ffffff;
+    const int cf = (int)((uint32_t)ci.y >> 27);
+    const int sSb = cf & 1, crb = (cf >> 1) & 1;
+    const int4* rit = rowItems + (int64_t)blockIdx.y * TILE_ROWS;
+    if (row_src && col_src) {
+#pragma unroll 1
+      for (int it = 0; it < TILE_ROWS / G2_ROWS_PER_ITER; ++it) {
+        int4 ri[G2_ROWS_PER_ITER];
+        double b[G2_ROWS_PER_ITER][4], k[G2_ROWS_PER_ITER][4];
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * G2_ROWS_PER_ITER + j);
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (item_on<true>(ri[j])) {
+            const double* b0 = rowp0(BB, ri[j], NB);
+            const double* b1 = rowp1(BB, ri[j], NB);
+            const double* k0 = rowp0(KB, ri[j], NB);
+            const double* k1 = rowp1(KB, ri[j], NB);
+            b[j][0] = b0[ib]; b[j][1] = b0[ibp]; b[j][2] = b1[ib]; b[j][3] = b1[ibp];
+            k[j][0] = k0[ib]; k[j][1] = k0[ibp]; k[j][2] = k1[ib]; k[j][3] = k1[ibp];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (item_on<true>(ri[j])) {
+            const int rf = ri[j].z;
+            const int sSa = rf & 1, cra = (rf >> 1) & 1, crap = (rf >> 2) & 1;
+            const int g10 = sSa ^ crb, g01 = sSb ^ cra, g11 = g10 ^ sSb ^ crap;
+            b[j][1] = flip(b[j][1], g01); b[j][2] = flip(b[j][2], g10); b[j][3] = flip(b[j][3], g11);
+            k[j][1] = flip(k[j][1], g01); k[j][2] = flip(k[j][2], g10); k[j][3] = flip(k[j][3], g11);
+#pragma unroll
+            for (int s = 0; s < SQ_MAX_PROGRAM; ++s) {
+              if (s >= gp.n) break;
+              const double c = gp.c[s], sn = gp.s[s], sg = gp.sig[s];
+              if (gp.kind[s] == 0) {
+                grad_pair(b[j][0], b[j][2], k[j][0], k[j][2], c, sn, sg, acc[s]);
+                grad_pair(b[j][1], b[j][3], k[j][1], k[j][3], c, sn, sg, acc[s]);
+              } else if (gp.kind[s] == 1) {
+                grad_pair(b[j][0], b[j][1], k[j][0], k[j][1], c, sn, sg, acc[s]);
+                grad_pair(b[j][2], b[j][3], k[j][2], k[j][3], c, sn, sg, acc[s]);
+              } else {
+                grad_pair(b[j][0], b[j][3], k[j][0], k[j][3], c, sn, sg, acc[s]);
+              }
+            }
+            double* b0 = rowp0(BB, ri[j], NB);
+            double* b1 = rowp1(BB, ri[j], NB);
+            double* k0 = rowp0(KB, ri[j], NB);
+            double* k1 = rowp1(KB, ri[j], NB);
+            b0[ib] = b[j][0]; b0[ibp] = flip(b[j][1], g01);
+            b1[ib] = flip(b[j][2], g10); b1[ibp] = flip(b[j][3], g11);
+            k0[ib] = k[j][0]; k0[ibp] = flip(k[j][1], g01);
+            k1[ib] = flip(k[j][2], g10); k1[ibp] = flip(k[j][3], g11);
+          }
+        }
+      }
+    } else {
+      // 2-amplitude tiles: (src row pair x inert column) feels only alpha steps, (inert row x src column pair) only beta
+      const int want = row_src ? 0 : 1;
+#pragma unroll 1
+      for (int it = 0; it < TILE_ROWS / G2_ROWS_PER_ITER; ++it) {
+        int4 ri[G2_ROWS_PER_ITER];
+        double b0[G2_ROWS_PER_ITER], b1[G2_ROWS_PER_ITER], k0[G2_ROWS_PER_ITER], k1[G2_ROWS_PER_ITER];
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) ri[j] = __ldg(rit + it * G2_ROWS_PER_ITER + j);
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (item_on<true>(ri[j])) {
+            const double* pb0 = rowp0(BB, ri[j], NB) + ib;
+            const double* pb1 = row_src ? rowp1(BB, ri[j], NB) + ib : rowp0(BB, ri[j], NB) + ibp;
+            const double* pk0 = rowp0(KB, ri[j], NB) + ib;
+            const double* pk1 = row_src ? rowp1(KB, ri[j], NB) + ib : rowp0(KB, ri[j], NB) + ibp;
+            b0[j] = *pb0; b1[j] = *pb1; k0[j] = *pk0; k1[j] = *pk1;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G2_ROWS_PER_ITER; ++j) {
+          if (item_on<true>(ri[j])) {
+            const int g = row_src ? ((ri[j].z & 1) ^ crb) : (sSb ^ ((ri[j].z >> 1) & 1));
+            b1[j] = flip(b1[j], g);
+            k1[j] = flip(k1[j], g);
+#pragma unroll
+            for (int s = 0; s < SQ_MAX_PROGRAM; ++s) {
+              if (s >= gp.n) break;
+              if (gp.kind[s] == want) grad_pair(b0[j], b1[j], k0[j], k1[j], gp.c[s], gp.s[s], 1.0, acc[s]);
+            }
+            double* pb0 = rowp0(BB, ri[j], NB) + ib;
+            double* pb1 = row_src ? rowp1(BB, ri[j], NB) + ib : rowp0(BB, ri[j], NB) + ibp;
+            double* pk0 = rowp0(KB, ri[j], NB) + ib;
+            double* pk1 = row_src ? rowp1(KB, ri[j], NB) + ib : rowp0(KB, ri[j], NB) + ibp;
+            *pb0 = b0[j]; *pb1 = flip(b1[j], g);
+            *pk0 = k0[j]; *pk1 = flip(k1[j], g);
+          }
+        }
+      }
+    }
+  }
+  block_reduce_store<SQ_MAX_PROGRAM>(acc, partial, (int64_t)blockIdx.y * gridDim.x + blockIdx.x);
+}
+
 // sum partial[b*NS + k] over b for each k (one block per k, fixed order -> deterministic)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partial, int64_t nblocks,
                                                              int ns, double* __restrict__ out, double scale) {
@@ -863,6 +979,44 @@ int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* step
   tile_grad_kernel<<<grid, TILE_THREADS, 0, st>>>(bra, ket, pt.d_codeA, pt.d_codeB, pt.d_rowsA, pt.n_rows, sp->NB,
                                                  sp->row_begin, prog, sp->d_partial);
   SQ_CHECK(check_launch("tile_grad_kernel"));
+  reduce_partials_kernel<<<n_steps, 256, 0, st>>>(sp->d_partial, nblocks, SQ_MAX_PROGRAM, d_out, 1.0);
+  return check_launch("reduce_partials_kernel");
+}
+
+// Exchange operator on a sharded (bra, ket) pair: d_tab_bra / d_tab_ket = DEVICE tables (SQ_MAX_WORLD entries) of the shard base
+// pointers of every rank as mapped into this process (own rank = the local shard).  d_out as in sq_launch_tile_grad.
+int sq_launch_tile_grad_peer(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps, double* bra, double* ket,
+                             const unsigned long long* d_tab_bra, const unsigned long long* d_tab_ket, double* d_out,
+                             cudaStream_t st) {
+  SQ_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n_steps, st));
+  if (pt.n_rows == 0 && pt.n_cross_items == 0) return SQ_OK;
+  if (pt.sigma == 0) {
+    sq_set_error("gradient sweep: orbital pair (%d,%d) has no gauge-fixed work lists", pt.i, pt.a);
+    return SQ_ERR_UNSUPPORTED;
+  }
+  if (n_steps < 1 || n_steps > SQ_MAX_PROGRAM) {
+    sq_set_error("tile program with %d steps (max %d)", n_steps, SQ_MAX_PROGRAM);
+    return SQ_ERR_INVALID;
+  }
+  GradProgram gp;
+  gp.n = n_steps;
+  for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
+    const bool on = k < n_steps;
+    gp.kind[k] = on ? steps[k].kind : -1;
+    const double sig = (on && steps[k].kind == 2) ? (double)pt.sigma : 1.0;
+    gp.c[k] = on ? steps[k].c : 1.0;
+    gp.s[k] = on ? sig * steps[k].s : 0.0;
+    gp.sig[k] = sig;
+  }
+  const int gx = pt.n_colblk_src + pt.n_colblk_inert, gy = pt.n_rowchunk_src + pt.n_rowchunk_inert;
+  if (gx == 0 || gy == 0) return SQ_OK;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  const int64_t nblocks = (int64_t)grid.x * grid.y;
+  SQ_CHECK(sq_ensure_partial(sp, nblocks * SQ_MAX_PROGRAM + SQ_MAX_PROGRAM));
+  Bases<true> BB{bra, d_tab_bra}, KB{ket, d_tab_ket};
+  tile_grad_peer_kernel<<<grid, TILE_THREADS, 0, st>>>(BB, KB, pt.d_colItems, pt.n_colblk_src, pt.d_rowItems, pt.n_rowchunk_src,
+                                                      sp->NB, gp, sp->d_partial);
+  SQ_CHECK(check_launch("tile_grad_peer_kernel"));
   reduce_partials_kernel<<<n_steps, 256, 0, st>>>(sp->d_partial, nblocks, SQ_MAX_PROGRAM, d_out, 1.0);
   return check_launch("reduce_partials_kernel");
 }

@@ -315,10 +315,14 @@ def shift_rule(R: int) -> tuple[np.ndarray, np.ndarray]:
     return x, w
 
 
-def gradient_segments(plan: list[tuple[int, int, bool]], ups_struct, fused_local: bool = True) -> list[tuple[int, int, bool]]:
-    """Split the exchange plan of a circuit into (first, last, fused) stretches for the sharded theta gradient: ``fused`` = every
-    row pair is local AND every operator is a brick operator (sa_single, or a pair double (2p, 2p+1, 2q, 2q+1)) that the fused
-    tile gradient kernels take; everything else is differentiated with the shift rule, one operator at a time."""
+def gradient_segments(
+    plan: list[tuple[int, int, bool]], ups_struct, fused_local: bool = True, peer_gradient: bool = False
+) -> list[tuple[int, int, str]]:
+    """Split the exchange plan of a circuit into (first, last, mode) stretches for the sharded theta gradient.  Modes:
+    ``"fused"`` -- every row pair is local and every operator is a brick operator (sa_single, or a pair double
+    (2p, 2p+1, 2q, 2q+1)): the fused single-GPU tile gradient kernels run on the shards; ``"peer"`` -- an exchange stretch of brick
+    operators, fused kernel on peer memory (``sq_ups_grad_sweep_dist``; only with ``peer_gradient=True``); ``"shift"`` -- everything
+    else, differentiated with the shift rule one operator at a time."""
     types, idx = ups_struct.excitation_operator_type, ups_struct.excitation_indices
 
     def brick_operator(k: int) -> bool:
@@ -327,26 +331,31 @@ def gradient_segments(plan: list[tuple[int, int, bool]], ups_struct, fused_local
             return True
         return t == "double" and len(ind) == 4 and ind[0] % 2 == 0 and ind[1] == ind[0] + 1 and ind[2] % 2 == 0 and ind[3] == ind[2] + 1
 
-    out: list[tuple[int, int, bool]] = []
+    out: list[tuple[int, int, str]] = []
     for f, l, exchange in plan:
-        fused = bool(fused_local and not exchange and all(brick_operator(k) for k in range(f, l)))
-        if out and out[-1][2] == fused and out[-1][1] == f and fused:
-            out[-1] = (out[-1][0], l, True)      # neighbouring fused stretches: one sweep, one all-reduce
+        bricks = all(brick_operator(k) for k in range(f, l))
+        if bricks and not exchange and fused_local:
+            mode = "fused"
+        elif bricks and exchange and peer_gradient:
+            mode = "peer"
         else:
-            out.append((f, l, fused))
+            mode = "shift"
+        out.append((f, l, mode))
     return out
 
 
 def energy_and_theta_gradient_sharded(
     reference: ShardedState, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0,
     fused_local: bool = True,
+    peer_gradient: bool = False,
 ) -> tuple[float, np.ndarray]:
     r"""Energy and :math:`\partial E/\partial\theta_k` of :math:`U(\theta)|\text{reference}\rangle` on an alpha-sharded
     vector (the theta part of ``_calc_gradient_optimization``, ups_wavefunction.py:1091-1138).  ``reference`` is not modified.
 
     Stretches of bricks whose row pairs are all local (on G GPUs: every pair (p, p+1) with p >= log2 G) go through the fused
     single-GPU gradient kernels on the shards plus one all-reduce per stretch; operators that pair rows of two GPUs use the
-    shift rule (``fused_local=False``: shift rule everywhere).
+    shift rule (``fused_local=False``: shift rule everywhere), or, with ``peer_gradient=True``, the fused gradient kernel on peer
+    memory (``sq_ups_grad_sweep_dist``, also awaiting its first GPU run).
 
     STATUS: composition of GPU-verified sharded primitives with ``sigma_sharded`` (first GPU run pending, see there); the
     shift-rule arithmetic is checked on the CPU against the oracle's literal gradient loop (tests/test_distributed_host.py)."""
@@ -372,8 +381,24 @@ def energy_and_theta_gradient_sharded(
     PD = C.POINTER(C.c_double)
 
     try:
-        for f, l, fused in gradient_segments(sp.exchange_plan(ups_struct, 0, P, False), ups_struct, fused_local):
-            if fused:
+        for f, l, mode in gradient_segments(sp.exchange_plan(ups_struct, 0, P, False), ups_struct, fused_local, peer_gradient):
+            if mode == "peer":
+                # exchange bricks through the fused gradient kernel on peer memory (both owners of a cross-device row pair take
+                # half of its columns); barrier before (all rows complete) and after (remote writes have landed)
+                part = np.zeros(l - f, dtype=np.float64)
+                torch.cuda.synchronize()
+                sp.barrier()
+                _lib.check(lib.sq_ups_grad_sweep_dist(sp.ci_info._handle, lay, th.ctypes.data_as(PD), f, l, bra._peer_ptrs,
+                                                      ket._peer_ptrs, part.ctypes.data_as(PD), osa._stream()))
+                torch.cuda.synchronize()
+                sp.barrier()
+                if sp.world > 1:
+                    t = torch.from_numpy(part).to(ket.local.device)
+                    dist.all_reduce(t)
+                    part = t.cpu().numpy()
+                grad[f:l] = part
+                continue
+            if mode == "fused":
                 # every row pair of these operators is local: the fused single-GPU sweep (g_k and both rotations in one kernel
                 # per brick, sq_ups_grad_sweep) runs on the shards; <bra|T_k|ket> is a sum over rows -> one all-reduce
                 part = np.zeros(l - f, dtype=np.float64)

@@ -69,8 +69,13 @@ def main():
             ref_st.set_determinant(0)
             e2, g2 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0)                       # fused local stretches
             e3, g3 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0, fused_local=False)    # shift rule everywhere
+            e4, g4 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0, peer_gradient=True)   # exchange bricks on peer memory
             ref_st.close()
-            err_g = max(abs(e1 - e2), abs(e1 - e3), float(np.max(np.abs(g1 - g2))), float(np.max(np.abs(g1 - g3)))) / max(1.0, abs(e1))
+            err_g = max(abs(e1 - e2), abs(e1 - e3), abs(e1 - e4), float(np.max(np.abs(g1 - g2))), float(np.max(np.abs(g1 - g3))),
+                        float(np.max(np.abs(g1 - g4)))) / max(1.0, abs(e1))
+            if rank == 0:
+                print(f"    theta gradient: fused-local {np.max(np.abs(g1 - g2)):.2e}, shift rule {np.max(np.abs(g1 - g3)):.2e}, "
+                      f"peer kernel {np.max(np.abs(g1 - g4)):.2e}", flush=True)
         e = torch.tensor([err, max(err_e, err_g)], dtype=torch.float64, device="cuda")
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         if rank == 0:

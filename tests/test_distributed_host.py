@@ -189,9 +189,10 @@ def test_gradient_segments_cover_the_circuit_once():
     plan = [(0, 3, True), (3, 16, False), (16, 19, True), (19, P, False)]
     seg = gradient_segments(plan, ups)
     assert seg[0][0] == 0 and seg[-1][1] == P and all(a[1] == b[0] for a, b in zip(seg, seg[1:]))
-    assert [s for s in seg if s[2]] == [(19, P, True)]            # (3, 16) holds the generic single -> not fused
-    assert all(not s[2] for s in gradient_segments(plan, ups, fused_local=False))
+    assert [s[2] for s in seg] == ["shift", "shift", "shift", "fused"]      # (3, 16) holds the generic single -> not fused
+    assert all(s[2] == "shift" for s in gradient_segments(plan, ups, fused_local=False))
+    assert [s[2] for s in gradient_segments(plan, ups, peer_gradient=True)] == ["peer", "shift", "peer", "fused"]
     del types[10], idxs[10]
     ups.n_params = len(types)
     seg = gradient_segments([(0, 3, True), (3, 15, False), (15, 18, True), (18, P - 1, False)], ups)
-    assert [s[2] for s in seg] == [False, True, False, True]
+    assert [s[2] for s in seg] == ["shift", "fused", "shift", "fused"]
