@@ -1131,7 +1131,7 @@ struct PeerViewRW {
   int world;
 };
 __global__ void __launch_bounds__(256)
-scatter_E_peer_kernel(PeerViewRW pvo, const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+scatter_E_peer_kernel(PeerViewRW pvo, const double* __restrict__ IN, double* OUT /* == pvo.p[own rank]: no restrict */, const double* __restrict__ F,
                       const double* __restrict__ kmat, const int* __restrict__ frow, int64_t W, int64_t j0, int64_t len,
                       const ERec* __restrict__ etab, int n2,
                       const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
