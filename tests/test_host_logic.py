@@ -230,6 +230,46 @@ def test_synthetic_layouts_match_reference(golden):
         assert [list(t) for t in lay.excitation_indices] == m["indices"]
 
 
+def test_layouts_match_reference_over_option_combinations():
+    """312 layouts built by the reference (tests/golden/make_golden_layouts.py): create_fUCC with single flags and seeded random
+    subsets of its 13 excitation flags on three index sets (one with unequal spin-orbital sets), create_SDSfUCC with every subset of
+    {D, pD, GpD}, create_tiled with every combination of do_tups / do_qnp / skip_last_singles for 2..7 orbitals, the UccStructure
+    builders -- types, indices, n_params, grad_param_R, and the same exception type where the reference raises."""
+    import gzip
+    import json
+    import os
+
+    from slowquant_b200.util import UccStructure
+
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_layouts.json.gz"), "rt") as f:
+        d = json.load(f)
+    assert len(d["cases"]) >= 300
+    for x in d["cases"]:
+        label = (x["kind"], x.get("options", x.get("builders")))
+        try:
+            if x["kind"] == "ucc":
+                n, occ, unocc, occs, unoccs = d["spaces"][x["space"]]
+                lay = UccStructure()
+                for b in x["builders"]:
+                    getattr(lay, "add_" + b)(*((occ, unocc) if b in ("sa_singles", "sa_doubles") else (occs, unoccs)))
+            else:
+                lay = UpsStructure()
+                if x["kind"] == "tiled":
+                    lay.create_tiled(x["n"], dict(x["options"]))
+                else:
+                    n, occ, unocc, occs, unoccs = d["spaces"][x["space"]]
+                    getattr(lay, "create_" + x["kind"])(occ, unocc, occs, unoccs, n, dict(x["options"]))
+        except Exception as e:  # noqa: BLE001
+            assert x.get("raises") == type(e).__name__, label
+            continue
+        assert "raises" not in x, label
+        assert lay.excitation_operator_type == x["types"], label
+        assert [[int(i) for i in t] for t in lay.excitation_indices] == x["indices"], label
+        assert lay.n_params == x["n_params"], label
+        if "grad_param_R" in x:
+            assert {str(k): int(v) for k, v in dict(lay.grad_param_R).items()} == x["grad_param_R"], label
+
+
 def test_layout_option_errors():
     lay = UpsStructure()
     with pytest.raises(ValueError):
