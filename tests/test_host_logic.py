@@ -144,6 +144,43 @@ def test_algebra_agrees_with_oracle_on_random_products():
         assert_opdict_close(a.dagger.operators, orc.op_dagger(orc.normal_order(label, 1.5)))
 
 
+def test_operator_factories_match_reference():
+    """221 operators built by the reference's factories (tests/golden/make_golden_factories.py): G2_sa for every index combination
+    incl. i == j / a == b of all five cases (anti-Hermitian and plain), G1..G6, G1_sa, Epq, Eminuspq, epqrs, commutator,
+    double_commutator, the 0i_0a / 1i_1a / 2i_2a / full-space Hamiltonians and one-electron operators on random integrals --
+    identical label sets and coefficients."""
+    import gzip
+    import json
+    import os
+
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_factories.json.gz"), "rt") as f:
+        d = json.load(f)
+    h, g = np.array(d["h"]), np.array(d["g"])
+    A, B, Cc = ops.Epq(0, 2), ops.G2_sa(0, 1, 2, 3, 2, True), ops.G1(1, 4, True)
+    assert len(d["cases"]) == 221
+    for case in d["cases"]:
+        name, args = case["call"]
+        try:
+            if name == "commutator":
+                got = ops.commutator(A, B)
+            elif name == "double_commutator":
+                got = ops.double_commutator(A, B, Cc)
+            elif name.startswith("hamiltonian_"):
+                got = getattr(ops, name)(h, g, *args)
+            elif name.startswith("one_elec_op_"):
+                got = getattr(ops, name)(h, *args)
+            else:
+                got = getattr(ops, name)(*args)
+        except Exception as e:  # noqa: BLE001
+            assert case.get("raises") == type(e).__name__, case["call"]
+            continue
+        assert "raises" not in case, case["call"]
+        ref = {tuple((int(i), bool(dg)) for i, dg in label): v for label, v in case["op"]}
+        mine = {k: v for k, v in got.operators.items() if abs(v) > 1e-14}
+        assert set(mine) == set(ref), case["call"]
+        assert max([abs(mine[k] - ref[k]) for k in ref] or [0.0]) < 1e-12, case["call"]
+
+
 def test_hamiltonian_folding(golden):
     arrays, _, gops = golden
     h, g = arrays["fold_h"], arrays["fold_g"]
