@@ -165,6 +165,40 @@ if which in ("all", "strings"):
         raised += 1
     record("strings: foreign det2idx -> TypeError, inconsistent screen -> ValueError", float(raised != 2), 0.5)
 
+# ---- constructor bookkeeping of the wave-function classes (orbital partitions, index lists, kappa lists) ----
+if which in ("all", "attributes"):
+    import json
+
+    from slowquant_b200.ucc_wavefunction import WaveFunctionUCC
+
+    gj = json.load(open(os.path.join(G, "golden_wf_attributes.json")))
+    ints = ArrayIntegrals(np.array(gj["h_ao"]), np.array(gj["eri_ao"]), int(gj["num_elec"]))
+    c_mo = np.array(gj["c_mo"])
+
+    def norm(v):
+        if isinstance(v, np.ndarray):
+            return v.tolist()
+        if isinstance(v, (list, tuple)):
+            return [norm(x) for x in v]
+        if isinstance(v, (bool, np.bool_)):
+            return bool(v)
+        if isinstance(v, (int, np.integer)):
+            return int(v)
+        return v
+
+    for case in gj["cases"]:
+        with contextlib.redirect_stdout(io.StringIO()):
+            if case["kind"] == "ups":
+                WF = WaveFunctionUPS(tuple(case["cas"]), c_mo, ints, case["ansatz"], dict(case["options"]), include_active_kappa=case["include_active_kappa"])
+            else:
+                WF = WaveFunctionUCC(tuple(case["cas"]), c_mo, ints, case["ansatz"], include_active_kappa=case["include_active_kappa"])
+        missing = [k for k in case["attributes"] if not hasattr(WF, k)]
+        wrong = [k for k, v in case["attributes"].items() if hasattr(WF, k) and norm(getattr(WF, k)) != v]
+        tag = f"{case['kind']} {tuple(case['cas'])} {case['ansatz']} kappa_aa={case['include_active_kappa']}"
+        if missing or wrong:
+            print("   missing:", missing, " wrong:", wrong, flush=True)
+        record(f"attributes {tag}: {len(case['attributes'])} reference attributes", float(len(missing) + len(wrong)), 0.5)
+
 # ---- rdm3 / rdm4 contractions ----
 if which in ("all", "rdm34"):
     g0 = np.load(os.path.join(G, "golden.npz"))

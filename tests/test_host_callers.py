@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("which", ["lr", "saups", "extended", "rdm34", "opt2", "ucc", "strings"])
+@pytest.mark.parametrize("which", ["lr", "saups", "extended", "rdm34", "opt2", "ucc", "strings", "attributes"])
 def test_host_logic_of_callers(which):
     res = subprocess.run([sys.executable, os.path.join(HERE, "host_callers_check.py"), which], capture_output=True, text=True, timeout=600)
     sys.stdout.write(res.stdout[-4000:])
