@@ -311,6 +311,11 @@ extern "C" int sq_layout_create(sq_space* sp, int n_ops, const int32_t* exc_type
                                 const int32_t* idx_flat, sq_layout** out) {
   if (!sp || !out || n_ops < 0 || (n_ops > 0 && (!exc_type || !idx_offsets || !idx_flat))) return SQ_ERR_INVALID;
   *out = nullptr;
+  for (int k = 0; k < n_ops; ++k)   // the offsets delimit the index tuples: non-negative, non-decreasing, at most 12 indices (sextuple)
+    if (idx_offsets[k] < 0 || idx_offsets[k + 1] < idx_offsets[k] || idx_offsets[k + 1] - idx_offsets[k] > 12) {
+      sq_set_error("sq_layout_create: bad index offsets for operator %d ([%d, %d))", k, idx_offsets[k], idx_offsets[k + 1]);
+      return SQ_ERR_INVALID;
+    }
   sq_layout* lay = new sq_layout();
   lay->sp = sp;
   lay->ops.resize(n_ops);
@@ -1115,7 +1120,10 @@ extern "C" int sq_partition_prefix(int n_orb, int n_alpha, int world, int64_t* r
   }
   int k = 0;
   while ((1 << k) < world) ++k;
-  if (k > n_orb) return SQ_ERR_INVALID;
+  if (k > n_orb || n_orb < 1 || n_alpha < 0 || n_alpha > n_orb) {
+    sq_set_error("sq_partition_prefix: need 0 <= n_alpha <= n_orb and log2(world) <= n_orb");
+    return SQ_ERR_INVALID;
+  }
   auto binom = [](int n, int r) -> int64_t {
     if (r < 0 || r > n) return 0;
     long double v = 1;

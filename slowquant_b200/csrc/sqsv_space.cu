@@ -224,6 +224,7 @@ int sq_make_string_action(const sq_space* sp, const int32_t* ops, int n_ops, Str
     sq_set_error("operator string with %d ladder operators (max %d)", n_ops, SQ_MAX_STRING_OPS);
     return SQ_ERR_INVALID;
   }
+  if (!sp || !out || (n_ops > 0 && !ops)) return SQ_ERR_INVALID;
   std::vector<int> anni, crea;
   for (int k = 0; k < n_ops; ++k) {
     int so = ops[k] >> 1;

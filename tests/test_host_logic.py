@@ -671,6 +671,71 @@ def test_table_free_E_records_equal_the_table():
         lib.sq_space_destroy(h)
 
 
+def test_c_abi_rejects_malformed_arguments_without_crashing():
+    """Every entry point returns a status and never throws or dereferences a bad pointer (include/sqsv.h contract): malformed
+    index offsets (decreasing, negative, too long), unknown excitation codes, out-of-range indices, NULL pointers, bad ranges,
+    bad partitions.  Host-only space, no kernels."""
+    lib, h = _host_space(4, 2, 2)
+    E = _lib.EXC_CODES
+    pi32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+    pi64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
+
+    def create(codes, offs, flat):
+        codes, offs = np.asarray(codes, dtype=np.int32), np.asarray(offs, dtype=np.int32)
+        flat = np.asarray(flat if len(flat) else [0], dtype=np.int32)
+        hl = C.c_void_p()
+        st = lib.sq_layout_create(h, len(codes), pi32(codes), pi32(offs), pi32(flat), C.byref(hl))
+        if st == 0:
+            lib.sq_layout_destroy(hl)
+        return st
+
+    assert create([E["sa_single"]], [0, 2], [0, 1]) == 0 and create([], [0], []) == 0
+    for codes, offs, flat in (
+        ([99], [0, 2], [0, 1]), ([E["sa_single"]], [0, 2], [-1, 1]), ([E["sa_single"]], [0, 2], [0, 7]), ([E["sa_single"]], [0, 3], [0, 1, 2]),
+        ([E["double"]], [0, 2], [0, 1]), ([E["double"]], [0, 4], [0, 1, 2, 99]), ([E["sa_single"]], [0, 2], [1, 1]),
+        ([E["sa_single"], E["sa_single"]], [0, 2, 1], [0, 1, 2, 3]), ([E["sa_single"]], [-2, 0], [0, 1, 2, 3]), ([E["sextuple"]], [0, 14], list(range(14))),
+    ):
+        assert create(codes, offs, flat) == _lib.SQ_ERR_INVALID, (codes, offs, flat)
+    assert lib.sq_layout_create(h, 1, None, None, None, C.byref(C.c_void_p())) == _lib.SQ_ERR_INVALID
+    assert lib.sq_layout_create(None, 0, None, None, None, C.byref(C.c_void_p())) == _lib.SQ_ERR_INVALID
+    lay, P = _tups_layout(lib, h, 4, 1)
+    out6 = (C.c_int64 * 6)()
+    assert lib.sq_layout_plan_stats(lay, 0, P, out6) == 0
+    for f, l in ((-1, 3), (0, P + 1), (2, 1)):
+        assert lib.sq_layout_plan_stats(lay, f, l, out6) == _lib.SQ_ERR_INVALID
+    assert lib.sq_layout_plan_stats(None, 0, 1, out6) != 0 and lib.sq_layout_plan_stats(lay, 0, 1, None) != 0
+    assert lib.sq_layout_num_launches(lay, 0, P + 5) == -1 and lib.sq_layout_touched_amplitudes(lay, 5, 2) == -1
+    ops, cf = np.array([1, 4], dtype=np.int32), np.array([1.0])
+    pd = cf.ctypes.data_as(C.POINTER(C.c_double))
+    for offs in ([0, 2], [0, -1], [2, 0], [0, 40]):     # host-only space refuses kernels; bad offsets must not be dereferenced either
+        o = np.array(offs, dtype=np.int32)
+        assert lib.sq_apply_strings(h, 1, pi32(ops), pi32(o), pd, C.c_void_p(8), C.c_void_p(16), 0, 0, None) != 0
+    d2, o2 = np.array([5, 6], dtype=np.int64), np.empty(2, dtype=np.int64)
+    assert lib.sq_space_det2idx(h, 2, None, pi64(o2)) != 0 and lib.sq_space_det2idx(None, 2, pi64(d2), pi64(o2)) != 0
+    assert lib.sq_space_export_idx2det(h, -1, 5, pi64(o2)) != 0 and lib.sq_space_export_idx2det(h, 0, 10**9, pi64(o2)) != 0
+    assert lib.sq_space_export_strings(h, 2, None) != 0 and lib.sq_space_export_strings(h, 0, None) != 0
+    assert lib.sq_space_num_strings(None, 0) == -1 and lib.sq_space_num_det(None) == -1
+    rs = np.zeros(17, dtype=np.int64)
+    for args in ((4, 2, 0), (4, 2, 3), (4, 2, 64), (0, 0, 2), (4, 9, 2), (4, -1, 2)):
+        assert lib.sq_partition_prefix(*args, pi64(rs)) == _lib.SQ_ERR_INVALID, args
+    assert lib.sq_partition_prefix(4, 2, 2, pi64(rs)) == 0 and list(rs[:3]) == [0, 3, 6]
+    bad = np.array([0, 5, 3], dtype=np.int64)
+    assert lib.sq_space_set_partition(h, 2, 0, pi64(bad)) != 0 and lib.sq_space_set_partition(h, 2, 5, pi64(rs)) != 0
+    assert lib.sq_space_set_partition(h, 0, 0, None) != 0
+    v, sgn, ta, tb = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint32()
+    big = np.array([2 * 40 + 1, 0], dtype=np.int32)
+    for ops_ptr, n_ops in ((pi32(big), 2), (pi32(big), 99), (None, 2)):
+        assert lib.sq_debug_string_action(h, ops_ptr, n_ops, 3, 3, C.byref(v), C.byref(ta), C.byref(tb), C.byref(sgn)) == _lib.SQ_ERR_INVALID
+    ex, n_out = np.empty(8, dtype=np.int32), C.c_int()
+    assert lib.sq_layout_plan_export(lay, None, 0, P + 4, 0, pi32(ex), pi32(ex), 8, C.byref(n_out)) != 0
+    assert lib.sq_layout_plan_export(None, None, 0, 3, 0, pi32(ex), pi32(ex), 8, C.byref(n_out)) != 0
+    assert lib.sq_set_option(None, b"1") != 0
+    lib.sq_layout_destroy(lay)
+    lib.sq_layout_destroy(None)
+    lib.sq_space_destroy(h)
+    lib.sq_space_destroy(None)
+
+
 def test_runtime_switches_are_known():
     """sq_set_option: every switch named in include/sqsv.h is accepted, anything else is an error (host call, no kernel)."""
     lib = _lib.load()
