@@ -391,6 +391,12 @@ static int parse_strings(sq_space* sp, int n_strings, const int32_t* ops_flat, c
                          std::vector<double>* cf) {
   acts->clear();
   cf->clear();
+  if (n_strings < 0 || (n_strings > 0 && (!ops_flat || !op_offsets || !coeffs))) return SQ_ERR_INVALID;
+  for (int s = 0; s < n_strings; ++s)
+    if (op_offsets[s] < 0 || op_offsets[s + 1] < op_offsets[s]) {
+      sq_set_error("operator string %d: bad offsets [%d, %d)", s, op_offsets[s], op_offsets[s + 1]);
+      return SQ_ERR_INVALID;
+    }
   for (int s = 0; s < n_strings; ++s) {
     StringAction a;
     SQ_CHECK(sq_make_string_action(sp, ops_flat + op_offsets[s], op_offsets[s + 1] - op_offsets[s], &a));

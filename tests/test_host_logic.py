@@ -730,6 +730,23 @@ def test_c_abi_rejects_malformed_arguments_without_crashing():
     assert lib.sq_layout_plan_export(lay, None, 0, P + 4, 0, pi32(ex), pi32(ex), 8, C.byref(n_out)) != 0
     assert lib.sq_layout_plan_export(None, None, 0, 3, 0, pi32(ex), pi32(ex), 8, C.byref(n_out)) != 0
     assert lib.sq_set_option(None, b"1") != 0
+    # generator strings of an sa_double operator: bad operator index / kind, NULL pointers, bad offsets, spin orbital out of range
+    codes, offs, flat = np.array([E["sa_double_1"], E["sa_single"]], dtype=np.int32), np.array([0, 4, 6], dtype=np.int32), np.array([0, 1, 2, 3, 0, 1], dtype=np.int32)
+    lay2 = C.c_void_p()
+    assert lib.sq_layout_create(h, 2, pi32(codes), pi32(offs), pi32(flat), C.byref(lay2)) == 0
+    gops, goffs = np.array([2 * 4 + 1, 0], dtype=np.int32), np.array([0, 2], dtype=np.int32)
+    assert lib.sq_layout_attach_generator(lay2, 0, 1, pi32(gops), pi32(goffs), pd) == 0
+    for k, n_str, po, poff, pc in (
+        (5, 1, pi32(gops), pi32(goffs), pd), (-1, 1, pi32(gops), pi32(goffs), pd), (1, 1, pi32(gops), pi32(goffs), pd), (0, 1, None, None, None),
+        (0, 1, pi32(gops), pi32(np.array([2, 0], dtype=np.int32)), pd), (0, 1, pi32(gops), pi32(np.array([-2, 0], dtype=np.int32)), pd),
+        (0, -3, pi32(gops), pi32(goffs), pd), (0, 1, pi32(np.array([2 * 40 + 1, 0], dtype=np.int32)), pi32(goffs), pd),
+    ):
+        assert lib.sq_layout_attach_generator(lay2, k, n_str, po, poff, pc) == _lib.SQ_ERR_INVALID
+    assert lib.sq_layout_attach_generator(None, 0, 1, pi32(gops), pi32(goffs), pd) == _lib.SQ_ERR_INVALID
+    assert lib.sq_layout_needs_exchange(lay2, -1, 9) == -1 and lib.sq_layout_needs_exchange(None, 0, 1) == -1
+    assert lib.sq_layout_op_stats(lay2, 7, (C.c_int64 * 6)()) != 0 and lib.sq_layout_op_stats(lay2, 0, None) != 0
+    assert lib.sq_layout_num_ops(lay2) == 2 and lib.sq_layout_num_ops(None) == -1
+    lib.sq_layout_destroy(lay2)
     lib.sq_layout_destroy(lay)
     lib.sq_layout_destroy(None)
     lib.sq_space_destroy(h)
