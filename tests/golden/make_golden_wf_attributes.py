@@ -88,6 +88,26 @@ for kind, cas, ansatz, options, iak in SPECS:
     cases.append({"kind": kind, "cas": list(cas), "ansatz": ansatz, "options": options, "include_active_kappa": iak, "attributes": attrs})
     print(kind, cas, ansatz, sorted(attrs)[:6], len(attrs))
 
+# state-averaged class on the same integrals: (2,2) with the singlet subspace of the reference's test_saups_h2_3states, and (4,3)
+from slowquant.unitary_coupled_cluster.sa_ups_wavefunction import WaveFunctionSAUPS  # noqa: E402
+
+SA_SPECS = [
+    ((2, 2), ([[1.0], [2 ** (-1 / 2), -(2 ** (-1 / 2))], [1.0]], [["1100"], ["1001", "0110"], ["0011"]]), "tUPS", {"n_layers": 1}, True),
+    ((4, 3), ([[1.0], [2 ** (-1 / 2), -(2 ** (-1 / 2))]], [["111100"], ["111001", "110110"]]), "SAfUCCSD", {}, False),
+]
+for cas, states, ansatz, options, iak in SA_SPECS:
+    WF = WaveFunctionSAUPS(cas, c_mo, SQobj, states, ansatz, ansatz_options=dict(options), include_active_kappa=iak)
+    attrs = {}
+    for k, v in WF.__dict__.items():
+        if k.startswith("_"):
+            continue
+        iv = intlike(v)
+        if iv is not None:
+            attrs[k] = iv
+    cases.append({"kind": "saups", "cas": list(cas), "ansatz": ansatz, "options": options, "include_active_kappa": iak,
+                  "states": [states[0], states[1]], "attributes": attrs})
+    print("saups", cas, ansatz, len(attrs))
+
 ig = SQobj.integral
 json.dump(
     {

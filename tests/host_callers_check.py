@@ -190,6 +190,9 @@ if which in ("all", "attributes"):
         with contextlib.redirect_stdout(io.StringIO()):
             if case["kind"] == "ups":
                 WF = WaveFunctionUPS(tuple(case["cas"]), c_mo, ints, case["ansatz"], dict(case["options"]), include_active_kappa=case["include_active_kappa"])
+            elif case["kind"] == "saups":
+                WF = sam.WaveFunctionSAUPS(tuple(case["cas"]), c_mo, ints, (case["states"][0], case["states"][1]), case["ansatz"], dict(case["options"]),
+                                           include_active_kappa=case["include_active_kappa"])
             else:
                 WF = WaveFunctionUCC(tuple(case["cas"]), c_mo, ints, case["ansatz"], include_active_kappa=case["include_active_kappa"])
         missing = [k for k in case["attributes"] if not hasattr(WF, k)]
