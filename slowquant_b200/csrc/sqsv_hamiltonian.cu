@@ -1200,6 +1200,24 @@ extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const doubl
   if (len == 0) return SQ_OK;   // a rank without rows has no sources
   cudaStream_t st = (cudaStream_t)stream;
   SQ_CUDA(cudaSetDevice(sp->device));
+  if (sp->world > 1) {
+    // the images that land in another rank's rows are added with system-scope fp64 atomics through the peer mapping: only
+    // correct when the device pair has native P2P atomics (NVLink); refuse anything else instead of returning a wrong sigma
+    int n_dev = 0;
+    SQ_CUDA(cudaGetDeviceCount(&n_dev));
+    for (int d = 0; d < n_dev; ++d) {
+      if (d == sp->device) continue;
+      int can = 0, native = 0;
+      SQ_CUDA(cudaDeviceCanAccessPeer(&can, sp->device, d));
+      if (!can) continue;   // not a peer of this process's device: its shard cannot be one of the mapped pointers
+      SQ_CUDA(cudaDeviceGetP2PAttribute(&native, cudaDevP2PAttrNativeAtomicSupported, sp->device, d));
+      if (!native) {
+        sq_set_error("sq_sigma_dist: devices %d and %d have no native peer-to-peer atomics (not NVLink-connected); use the RDM route "
+                     "(sq_rdm12_dist) for the energy of a sharded vector on this topology", sp->device, d);
+        return SQ_ERR_UNSUPPORTED;
+      }
+    }
+  }
   HamWork* w = nullptr;
   SQ_CHECK(get_work(sp, false, true, &w));
   const int n = sp->n_orb, n2 = n * n;

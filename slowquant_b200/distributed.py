@@ -260,10 +260,8 @@ def sigma_sharded(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_c
     ups_wavefunction.py:770-784 / :1091-1112 in the active space; ``h_act`` / ``g_act`` are the folded active integrals of
     ``operators.fold_hamiltonian_0i_0a``).  Every rank treats the determinants of its rows as sources (``sq_sigma_dist``):
     alpha partners on other GPUs are read over NVLink, images in other GPUs' rows are added there with system-scope
-    atomics; no transpose, no collective besides the two barriers.
-
-    STATUS: written in a session without GPU time -- compiled for sm_100a, not yet run; its parity test
-    (tests/test_gpu_distributed.py::test_sharded_sigma_matches_single_gpu) is opt-in (SQ_RUN_UNVERIFIED=1) until then."""
+    atomics; no transpose, no collective besides the two barriers.  ``sq_sigma_dist`` refuses device pairs without native
+    peer-to-peer atomics (not NVLink-connected).  Parity: tests/test_gpu_distributed.py::test_sharded_sigma_matches_single_gpu."""
     lib = _lib.load()
     sp = state.space
     n = sp.ci_info.num_active_orbs
@@ -355,10 +353,9 @@ def energy_and_theta_gradient_sharded(
     Stretches of bricks whose row pairs are all local (on G GPUs: every pair (p, p+1) with p >= log2 G) go through the fused
     single-GPU gradient kernels on the shards plus one all-reduce per stretch; operators that pair rows of two GPUs use the
     shift rule (``fused_local=False``: shift rule everywhere), or, with ``peer_gradient=True``, the fused gradient kernel on peer
-    memory (``sq_ups_grad_sweep_dist``, also awaiting its first GPU run).
-
-    STATUS: composition of GPU-verified sharded primitives with ``sigma_sharded`` (first GPU run pending, see there); the
-    shift-rule arithmetic is checked on the CPU against the oracle's literal gradient loop (tests/test_distributed_host.py)."""
+    memory (``sq_ups_grad_sweep_dist``).  All three routes are compared with the fused single-GPU call in
+    tests/dist_sigma_worker.py; the shift-rule arithmetic is also checked on the CPU against the oracle's literal gradient
+    loop (tests/test_distributed_host.py)."""
     sp = reference.space
     types = list(ups_struct.excitation_operator_type)
     P = len(types)

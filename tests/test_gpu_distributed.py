@@ -25,10 +25,6 @@ def test_sharded_ups_matches_single_gpu(world):
     assert res.returncode == 0 and "DIST_CHECK_OK" in res.stdout
 
 
-@pytest.mark.skipif(
-    os.environ.get("SQ_RUN_UNVERIFIED") != "1",
-    reason="sq_sigma_dist was written without GPU time (compiled, never run): opt in with SQ_RUN_UNVERIFIED=1 until its first green run",
-)
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_sigma_matches_single_gpu(world):
     """H|psi> of an alpha-sharded vector (peer gathers + system-scope atomics over NVLink) against the single-GPU sigma

@@ -816,10 +816,6 @@ def test_per_string_kernels_against_reference_outputs(sq):
     assert [osa.bitcount(int(x)) for x in g["bitcount_in"]] == [int(x) for x in g["bitcount_out"]]
 
 
-@pytest.mark.skipif(
-    __import__("os").environ.get("SQ_RUN_UNVERIFIED") != "1",
-    reason="the rdm_tri switch was written without GPU time (compiled, never run): opt in with SQ_RUN_UNVERIFIED=1 until its first green run",
-)
 def test_rdm_triangle_variant_agrees(sq):
     """sq_set_option("rdm_tri", "1"): the symmetric Gram matrix of sq_rdm12 (bra == ket) from three half-size DGEMMs + a host mirror
     must give the same RDMs as the single DGEMM; transition RDMs (bra != ket) are not affected by the switch."""
@@ -847,10 +843,6 @@ def test_rdm_triangle_variant_agrees(sq):
     assert abs(np.trace(e1) - (na + nb)) < 1e-12
 
 
-@pytest.mark.skipif(
-    __import__("os").environ.get("SQ_RUN_UNVERIFIED") != "1",
-    reason="the table-free panel kernels (etab=alu) were written without GPU time (compiled, never run): opt in with SQ_RUN_UNVERIFIED=1",
-)
 def test_table_free_panel_kernels_agree(sq):
     """sq_set_option("etab", "alu"): sigma (symmetric and unsymmetric integrals) against the oracle and RDMs / transition RDMs
     against the table kernels, with small panels (several panels, a partial last one)."""
@@ -886,3 +878,49 @@ def test_table_free_panel_kernels_agree(sq):
         lib.sq_set_option(b"etab", b"smem")
     for x, y in zip(*results):
         assert np.max(np.abs(x - y)) < 1e-12
+
+
+def test_cas16_bench_config(sq):
+    """The benchmarked configuration itself (BASELINE.json config 4: CAS(16,16), 165 636 900 determinants, dense random vector,
+    tUPS): (i) the default window plan (H = 6 windows, time-skewed schedule, 20 x 20 tiles, top-window path) against the
+    one-brick-per-launch path, (ii) the adjoint round trip, (iii) one brick (3 operators, 5 rotations) against the oracle's
+    restatement of the reference loop (osa.py:1002-1085) -- the same call bench.py times as the CPU baseline, (iv) the L = 16
+    circuit of the bench from the HF determinant, window plan against bricks."""
+    lib = sq.lib.load()
+    n, ne = 16, 8
+    info = sq.ci.get_indexing(0, n, 0, ne, ne)
+    dev = torch.device("cuda", info.device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1604)
+    x = torch.randn(info.num_det, dtype=torch.float64, device=dev, generator=gen)
+    x /= torch.linalg.norm(x)
+    types, idx, th, rng = _seeded_case(n, ne, ne, 2, 1616)
+    lay = _layout(sq, types, idx)
+    try:
+        res = sq.osa.construct_ups_state(x, info, th.tolist(), lay)
+        back = sq.osa.construct_ups_state(res, info, th.tolist(), lay, dagger=True)
+        assert float(torch.max(torch.abs(back - x))) < 1e-12                     # (ii)
+        del back
+        sq.lib.check(lib.sq_set_option(b"win", b"0"))
+        ref = sq.osa.construct_ups_state(x, info, th.tolist(), lay)
+        assert float(torch.max(torch.abs(res - ref))) < 1e-13                    # (i)
+        del res, ref
+        # (iv) the bench circuit: L = 16 from the HF determinant (sparse light cone at first, dense at the end)
+        types16, idx16, th16, _ = _seeded_case(n, ne, ne, 16, 1234)
+        lay16 = _layout(sq, types16, idx16)
+        hf = torch.zeros(info.num_det, dtype=torch.float64, device=dev)
+        hf[0] = 1.0
+        ref16 = sq.osa.construct_ups_state(hf, info, th16.tolist(), lay16)
+        sq.lib.check(lib.sq_set_option(b"win", b"1"))
+        res16 = sq.osa.construct_ups_state(hf, info, th16.tolist(), lay16)
+        assert float(torch.max(torch.abs(res16 - ref16))) < 1e-13
+        assert abs(float(torch.linalg.norm(res16)) - 1.0) < 1e-12
+        del res16, ref16, hf
+        # (iii) one brick against the oracle (16 host threads: about 15 s)
+        one = _layout(sq, types[0:3], idx[0:3])
+        got = sq.osa.construct_ups_state(x, info, [0.7, -0.4, 0.3], one).cpu().numpy()
+        sp = orc.get_indexing(0, n, 0, ne, ne)
+        want = orc.construct_ups_state(x.cpu().numpy(), sp, [0.7, -0.4, 0.3], types[0:3], idx[0:3], threaded=True)
+        assert np.max(np.abs(got - want)) < 1e-12
+    finally:
+        sq.lib.check(lib.sq_set_option(b"win", b"1"))
