@@ -8,11 +8,11 @@ the resident 165 636 900-amplitude fp64 CI vector.  `value` = layers/s with the 
 `e2e` = the same through the public `construct_ups_state(numpy_state, ...)` call with pinned HOST buffers
 (H2D of the state + D2H of the result inside the timed region).  One JSON line is printed by rank 0.
 
-N > 1 (torchrun): the CAS(16,16) vector fits one GPU, so by default the ranks run independent replicas of the
-workload (different theta sets, as RotoSolve shifts / finite-difference columns do) -- weak scaling, no data-path
-collective.  --mode sharded (default when the vector exceeds 64 GB, e.g. --cas 20) shards ONE vector by alpha string
-over the N GPUs: local bricks stay on the GPU, bricks that pair rows of two GPUs rotate their tiles through NVLink
-peer memory (strong scaling).
+N > 1 (torchrun): ONE vector sharded by alpha string over the N GPUs (strong scaling, the multi-GPU path BASELINE.json
+names): the circuit runs as a few local phases of window sweeps in two row layouts with an all-to-all re-shard over NVLink
+peer memory between them; the line carries the re-shard's NVLink bandwidth and a sharded-vs-single-GPU parity check.
+--mode replicas runs independent vectors per GPU instead (RotoSolve shifts / finite-difference columns; weak scaling,
+no data-path collective).
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/, OpenMP over all host
 cores) on a bounded sample of the same workload; /root/reference itself is pure Python + numba and does
@@ -573,8 +573,11 @@ def run_ours(args) -> None:
 
 
 def run_sharded(args) -> None:
-    """N > 1: ONE CAS(n,n) vector sharded by alpha string over the N GPUs (strong scaling).  Bricks on orbital
-    pairs (p,p+1) with p >= log2(N) are local; the others rotate their tiles through NVLink peer memory."""
+    """N > 1: ONE CAS(n,n) vector sharded by alpha string over the N GPUs (strong scaling).  The circuit runs as a few local
+    phases (window sweeps on the shard) in two row layouts, with an all-to-all re-shard over NVLink peer memory between them
+    (slowquant_b200/distributed.py)."""
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -588,7 +591,8 @@ def run_sharded(args) -> None:
     dist.init_process_group("nccl", device_id=dev)
 
     from slowquant_b200 import _lib
-    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded
+    from slowquant_b200 import distributed as sqd
+    from slowquant_b200.distributed import ShardedSpace, construct_ups_state_sharded, dot_sharded, reshard_schedule
     from slowquant_b200.operator_state_algebra import compile_layout
     from slowquant_b200.util import UpsStructure
 
@@ -601,19 +605,51 @@ def run_sharded(args) -> None:
     P = lay.n_params
     thetas = np.random.default_rng(1234).uniform(-np.pi, np.pi, P)   # same parameters on every rank
     handle = compile_layout(sp.ci_info, lay)
-    launches_per_step = int(lib.sq_layout_num_launches(handle, 0, P))
-    touched_per_step = int(lib.sq_layout_touched_amplitudes(handle, 0, P))
-    plan = sp.exchange_plan(lay, 0, P, False)
-    n_exchange = sum(1 for _, _, x in plan if x)
-    import ctypes as C
-
-    pstats = [0] * 6   # launch plan summed over the operator ranges of the exchange plan
-    for first, last, _ in plan:
-        one = (C.c_int64 * 6)()
-        _lib.check(lib.sq_layout_plan_stats(handle, first, last, one))
-        pstats = [a + int(b) for a, b in zip(pstats, one)]
+    use_reshard = sp.reshard_ok and sqd._RESHARD_DEFAULT
     st = sp.alloc_state()
     st.set_determinant(0)
+    nb = sp.ci_info.num_beta_strings
+
+    # ---- plan accounting (per rank): phases, sweeps, amplitudes the kernels read and write, rows that cross NVLink ----
+    pstats = [0] * 8
+    n_reshards = 0
+    nvlink_bytes = 0.0   # bytes this rank writes into OTHER ranks' buffers per step
+    gauge_amps = 0
+    if use_reshard:
+        phases = reshard_schedule(lay.excitation_operator_type, lay.excitation_indices, n, world)
+        handle_B = compile_layout(sp.ci_info_B, lay) if any(nm == "B" for nm, _ in phases) else None
+        a2b, b2a = sp.reshard_tables_host
+        where = "A"
+        for nm, ops in phases:
+            arr = np.asarray(ops, dtype=np.int32)
+            one = (C.c_int64 * 8)()
+            tgt = "A" if nm == "X" else nm
+            if tgt != where:
+                tab = a2b if tgt == "B" else b2a
+                nvlink_bytes += 8.0 * nb * float(np.count_nonzero(tab[0] != rank))
+                n_reshards += 1
+                where = tgt
+            if nm == "X":
+                continue
+            _lib.check(lib.sq_layout_plan_stats_list(handle if nm == "A" else handle_B, len(arr), arr.ctypes.data_as(C.POINTER(C.c_int32)), one))
+            pstats = [a + int(b) for a, b in zip(pstats, one)]
+        if where == "B":
+            nvlink_bytes += 8.0 * nb * float(np.count_nonzero(b2a[0] != rank))
+            n_reshards += 1
+        gauge_amps = 2 * max(sp.local_len, sp.local_len_B)   # into the sign-free gauge once, out of it once
+        n_phase = len(phases)
+        plan_desc = (f"{n_phase} local phases per step in two row layouts (rows grouped by the first / the last {world.bit_length() - 1} "
+                     f"orbitals), {n_reshards} all-to-all re-shards over NVLink peer memory (bulk-copy engine), one device-wide barrier each")
+    else:
+        plan = sp.exchange_plan(lay, 0, P, False)
+        for first, last, _ in plan:
+            one = (C.c_int64 * 6)()
+            _lib.check(lib.sq_layout_plan_stats(handle, first, last, one))
+            pstats = [a + int(b) for a, b in zip(pstats[:6], one)] + [0, 0]
+        pstats[7] = int(lib.sq_layout_touched_amplitudes(handle, 0, P))
+        n_exchange = sum(1 for _, _, x in plan if x)
+        plan_desc = f"{n_exchange} of {len(plan)} operator ranges per step exchange tiles over NVLink peer memory, the rest are local"
+    touched_per_step = pstats[7] + gauge_amps
 
     def step():
         construct_ups_state_sharded(st, thetas, lay)
@@ -644,6 +680,67 @@ def run_sharded(args) -> None:
     ms_max = float(t.item())
     value = L * args.steps / (ms_max * 1e-3)
 
+    # ---- the re-shard alone: NVLink bytes per second of one A -> B -> A round trip (timed on the device, max over ranks) ----
+    nvlink = None
+    if use_reshard and st._ptr_B is not None:
+        reps = 5
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            sqd._reshard(st, to_B=True)
+            sqd._reshard(st, to_B=False)
+        ev1.record()
+        barrier()
+        tr = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        out_b = 8.0 * nb * float(np.count_nonzero(sp.reshard_tables_host[0][0] != rank))
+        ob = torch.tensor([out_b], dtype=torch.float64, device=dev)
+        dist.all_reduce(ob, op=dist.ReduceOp.MAX)
+        ms_one = float(tr.item()) / (2 * reps)
+        nvlink = {
+            "kernel": "reshard_bulk_kernel (cp.async.bulk global -> shared -> peer global), one launch + one barrier per re-shard",
+            "bound": "nvlink",
+            "ms_per_reshard": ms_one,
+            "bytes_out_per_gpu": float(ob.item()),
+            "achieved": float(ob.item()) / (ms_one * 1e-3) / 1e9,
+            "peak": 770.0,
+            "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900",
+            "unit": "GB/s",
+            "frac": float(ob.item()) / (ms_one * 1e-3) / 1e9 / 770.0,
+            "reshards_per_step": n_reshards,
+            "share_of_step": n_reshards * ms_one / (ms_max / args.steps),
+        }
+
+    # ---- multi-GPU parity inside the driver's run: the sharded engine against the single-GPU engine on this rank's own GPU,
+    # CAS(12,12), dense random vector, L = 4 (the single-GPU engine is pinned to the oracle / reference goldens in tests/) ----
+    parity = None
+    try:
+        from slowquant_b200.ci_spaces import get_indexing
+        from slowquant_b200.operator_state_algebra import construct_ups_state
+
+        pn, pe, pL = 12, 6, 4
+        psp = ShardedSpace(0, pn, 0, pe, pe, device=local_rank)
+        pinfo = get_indexing(0, pn, 0, pe, pe, device=local_rank)
+        play = UpsStructure()
+        play.create_tiled(pn, {"n_layers": pL, "do_tups": True})
+        prng = np.random.default_rng(4321)
+        pth = prng.uniform(-np.pi, np.pi, play.n_params)
+        full = torch.from_numpy(prng.normal(size=pinfo.num_det)).to(dev)
+        full /= torch.linalg.norm(full)
+        ref = construct_ups_state(full, pinfo, pth.tolist(), play)
+        pst = psp.alloc_state()
+        lo, hi = psp.row_begin * pinfo.num_beta_strings, psp.row_end * pinfo.num_beta_strings
+        pst.local.copy_(full[lo:hi])
+        construct_ups_state_sharded(pst, pth, play)
+        torch.cuda.synchronize()
+        perr = torch.tensor([float(torch.max(torch.abs(pst.local - ref[lo:hi]))) if hi > lo else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(perr, op=dist.ReduceOp.MAX)
+        pst.close()
+        parity = {"check": f"sharded vs single-GPU engine, CAS({pn},{pn}) L={pL}, dense random vector, max over ranks of max|diff| on the rank's rows",
+                  "max_abs_diff": float(perr.item()), "tolerance": 1e-12, "ok": bool(float(perr.item()) < 1e-12)}
+    except Exception as exc:  # an extra, never a gate
+        parity = {"error": repr(exc)}
+
     e2e = None
     if not args.no_e2e:
         host_in = torch.zeros(sp.local_len, dtype=torch.float64).pin_memory()
@@ -669,6 +766,7 @@ def run_sharded(args) -> None:
             "d2h_bytes_per_step": int(8 * sp.ci_info.num_det),
             "steps": n_e2e,
             "norm_check": float(sq.item()) ** 0.5,
+            "api": "every rank copies its rows from pinned host memory into its shard, construct_ups_state_sharded, rows back to the host",
         }
     touched_all = torch.tensor([float(touched_per_step)], dtype=torch.float64, device=dev)
     dist.all_reduce(touched_all)
@@ -692,8 +790,7 @@ def run_sharded(args) -> None:
             "config": {
                 "workload": workload_name(n, L),
                 "l2_policy": "inputs larger than L2" if 8 * sp.local_len > 126e6 else "per-GPU shard may fit L2 (strong scaling of a fixed vector)",
-                "parallelism": f"one vector sharded by alpha string over {world} GPUs (prefix-class row partition); "
-                f"{n_exchange} of {len(plan)} operator ranges per step exchange tiles over NVLink peer memory, the rest are local",
+                "parallelism": f"one vector sharded by alpha string over {world} GPUs; " + plan_desc,
                 "fusion": "per rank and step: %d window sweeps holding %d bricks (3 operators each), %d quad, %d single-brick launches"
                 % (pstats[1], pstats[2], pstats[3], pstats[4]),
             },
@@ -701,7 +798,7 @@ def run_sharded(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "kernel": "win_kernel on the local operator ranges, tile_kernel_v2 over NVLink peer memory on the exchange ranges (per-GPU average)",
+                "kernel": "win_kernel on the rank's shard (HBM bytes of all sweeps of a step over the WHOLE step time, re-shards and barriers included; per-GPU average)",
                 "bound": "hbm",
                 "achieved": achieved,
                 "peak": peak,
@@ -709,9 +806,11 @@ def run_sharded(args) -> None:
                 "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": None,
+                "nvlink": nvlink,
             },
             "cpu_baseline": None,
             "state_norm": norm2 ** 0.5,
+            "multi_gpu_parity": parity,
         }
         print(json.dumps(line), flush=True)
     st.close()
@@ -723,7 +822,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args)
-    elif world > 1 and (args.mode == "sharded" or (args.mode == "auto" and vector_bytes(args.cas) > 64e9)):
+    elif world > 1 and args.mode != "replicas":
+        # the multi-GPU path north_star names: ONE vector sharded by alpha string (strong scaling).  --mode replicas keeps the
+        # independent-vectors-per-GPU run (RotoSolve shifts, finite-difference columns) for comparison.
         run_sharded(args)
     else:
         run_ours(args)

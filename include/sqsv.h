@@ -67,6 +67,12 @@ int sq_version(void);
  * tables, export/rank functions; no kernels). */
 int sq_space_create(int n_orb, int n_alpha, int n_beta, int device, int64_t row_begin,
                     int64_t row_end, sq_space** out);
+/* The same with a CONSTRAINED alpha list: only the strings with (mask & alpha_cmask) == alpha_cpat (bit o = orbital o), in
+ * the order they have in the full list; all of them are local rows.  This is the second row layout of a re-sharded vector
+ * (rows grouped by the occupation of the last log2(G) orbitals, see sq_reshard_rows); operators that move an alpha electron
+ * on a constrained orbital cannot run in such a space (SQ_ERR_UNSUPPORTED).  No reference counterpart (single-process). */
+int sq_space_create_constrained(int n_orb, int n_alpha, int n_beta, int device, uint32_t alpha_cmask,
+                                uint32_t alpha_cpat, sq_space** out);
 int sq_space_destroy(sq_space* sp);
 int64_t sq_space_num_det(const sq_space* sp);
 int64_t sq_space_num_strings(const sq_space* sp, int spin /*0 alpha, 1 beta*/);
@@ -101,6 +107,9 @@ int64_t sq_layout_touched_amplitudes(const sq_layout* lay, int first, int last);
 /* launch plan of ops [first,last): out6 = {launches, window sweeps, bricks inside window sweeps, quad launches,
  * single-brick launches, other launches}.  (No reference counterpart: the reference applies one operator per pass.) */
 int sq_layout_plan_stats(const sq_layout* lay, int first, int last, int64_t* out6);
+/* the same for an explicit operator list (one phase of the re-sharding driver): out8 = the six counters above, then the number
+ * of kernels (without gauge sweeps) and the amplitudes those kernels read and write. */
+int sq_layout_plan_stats_list(const sq_layout* lay, int n_list, const int32_t* op_list, int64_t* out8);
 /* the plan itself (planner tests): operators of [first,last) in execution order (dagger != 0: the reversed circuit) and the
  * launch each one rides in; thetas_host may be NULL (all active; |theta| < 1e-28 is skipped as in sq_ups_apply). */
 int sq_layout_plan_export(const sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
@@ -125,6 +134,14 @@ int sq_set_option(const char* name, const char* value);
  * operator; operators with |theta| < 1e-28 are skipped (:998). */
 int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                  int dagger, double* state_dev, void* stream);
+/* The same product over an explicit operator list: layout operators op_list[0..n_list) in the given EXECUTION order (dagger
+ * != 0 only negates the angles).  The caller vouches that this order is equivalent to the circuit order, i.e. operators that
+ * changed places commute (disjoint orbitals) -- the re-sharding driver runs the part of a circuit that is executable in the
+ * current row layout this way.  gauge_flags bit 0: the vector is in the window kernel's sign-free gauge on entry, bit 1: it
+ * is in that gauge on return; 0 = the reference's sign convention on both sides, as sq_ups_apply.  An empty list with
+ * gauge_flags = 1 just takes the vector out of the gauge. */
+int sq_ups_apply_list(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                      int dagger, int gauge_flags, double* state_dev, void* stream);
 /* out <- T_k in   (get_grad_action, :2757-2865; sa_single uses Ta + Tb) */
 int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, double* out_dev,
                    void* stream);
@@ -167,6 +184,15 @@ int sq_layout_needs_exchange(const sq_layout* lay, int first, int last);
  * process (own shard for r == rank).  Only orbital-pair operators (sa_single, pair double) may exchange. */
 int sq_ups_apply_dist(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                       int dagger, double* const* shard_ptrs_host, void* stream);
+/* Re-shard (the all-to-all exchange step of the sharded engine): the n_rows local rows of src_dev (row r =
+ * NB doubles) move to their owners in the other row layout, row r to local row dst_row_dev[r] of rank dst_rank_dev[r],
+ * written straight into dst_ptrs_host[rank] (that rank's destination buffer as mapped into this process) over NVLink by
+ * the bulk-copy engine.  The tables are device arrays built by the caller from the string lists.  Device-wide barrier
+ * after it (all rows landed) before any rank computes on the destination buffers. */
+int sq_reshard_rows(int device, int64_t n_rows, int64_t NB, const double* src_dev, const int32_t* dst_rank_dev,
+                    const int32_t* dst_row_dev, double* const* dst_ptrs_host, int world, void* stream);
+/* 1 if operator k cannot run in this space (constrained alpha list, sq_space_create_constrained), else 0 */
+int sq_layout_op_blocked(const sq_layout* lay, int k);
 /* 1-/2-RDM contributions of THIS rank's rows of alpha-sharded vectors (same definitions as sq_rdm12; the caller sums the
  * ranks' results, e.g. with an all-reduce).  *_ptrs_host[r] = base pointer of rank r's shard as mapped into this process;
  * alpha partners on other ranks are read in place over NVLink.  All ranks must have finished writing their shards. */

@@ -38,6 +38,7 @@ def _declare(lib: C.CDLL) -> None:
         "sq_last_error": (C.c_char_p, []),
         "sq_version": (i32, []),
         "sq_space_create": (i32, [i32, i32, i32, i32, i64, i64, C.POINTER(vp)]),
+        "sq_space_create_constrained": (i32, [i32, i32, i32, i32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
         "sq_space_destroy": (i32, [vp]),
         "sq_space_num_det": (i64, [vp]),
         "sq_space_num_strings": (i64, [vp, i32]),
@@ -54,6 +55,10 @@ def _declare(lib: C.CDLL) -> None:
         "sq_layout_plan_stats": (i32, [vp, i32, i32, pi64]),
         "sq_set_option": (i32, [C.c_char_p, C.c_char_p]),
         "sq_ups_apply": (i32, [vp, vp, pdbl, i32, i32, i32, vp, vp]),
+        "sq_ups_apply_list": (i32, [vp, vp, pdbl, i32, pi32, i32, i32, vp, vp]),
+        "sq_reshard_rows": (i32, [i32, i64, i64, vp, vp, vp, C.POINTER(vp), i32, vp]),
+        "sq_layout_op_blocked": (i32, [vp, i32]),
+        "sq_layout_plan_stats_list": (i32, [vp, i32, pi32, pi64]),
         "sq_grad_action": (i32, [vp, vp, i32, vp, vp, vp]),
         "sq_ups_grad_sweep": (i32, [vp, vp, pdbl, i32, i32, vp, vp, pdbl, vp]),
         "sq_ups_energy_grad": (i32, [vp, vp, pdbl, dbl, pdbl, pdbl, vp, vp, vp, pdbl, pdbl, vp]),
@@ -97,7 +102,8 @@ EXPORTED_SYMBOLS = (
     "sq_layout_touched_amplitudes sq_layout_plan_stats sq_set_option sq_ups_apply "
     "sq_grad_action sq_ups_grad_sweep sq_ups_energy_grad sq_apply_strings sq_dot sq_axpy sq_scale_copy sq_sigma sq_rdm12 "
     "sq_debug_string_action sq_launch_count sq_partition_prefix sq_space_set_partition sq_dist_alloc sq_dist_free "
-    "sq_ipc_export sq_ipc_import sq_ipc_close sq_layout_needs_exchange sq_ups_apply_dist sq_rdm12_dist sq_sigma_dist sq_layout_op_stats sq_layout_plan_export sq_debug_etab_closed_form sq_ups_grad_sweep_dist"
+    "sq_ipc_export sq_ipc_import sq_ipc_close sq_layout_needs_exchange sq_ups_apply_dist sq_rdm12_dist sq_sigma_dist sq_layout_op_stats sq_layout_plan_export sq_debug_etab_closed_form sq_ups_grad_sweep_dist "
+    "sq_space_create_constrained sq_ups_apply_list sq_reshard_rows sq_layout_op_blocked sq_layout_plan_stats_list"
 ).split()
 
 
@@ -106,7 +112,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    # rebuild when the library is missing OR older than its sources (digest of the .cu / .h files against the build
+    # stamp): the .so is git-ignored and travels with repository snapshots, so a stale binary must never be picked up
+    if os.path.exists(os.path.join(_HERE, "csrc", "sqsv_api.cu")) or not os.path.exists(LIB_PATH):
         from slowquant_b200.build import build_library
 
         build_library()

@@ -80,11 +80,13 @@ class CI_Info:
         det2idx=None,
         device: int | None = None,
         row_range: tuple[int, int] | None = None,
+        alpha_constraint: tuple[int, int] | None = None,
     ) -> None:
         """``idx2det`` / ``det2idx`` occupy the positions they have in the reference's constructor (ci_spaces.py:12-21).  The engine
         derives both tables from the string lists, so a caller-supplied ``idx2det`` is only checked: it must be the determinant
         list of this product space in the reference's order (anything else -- e.g. an extended space -- needs
-        ``get_indexing_extended``); ``det2idx`` is ignored."""
+        ``get_indexing_extended``); ``det2idx`` is ignored.  ``alpha_constraint = (mask, pattern)`` keeps only the alpha strings
+        with ``string & mask == pattern`` (second row layout of a re-sharded vector, ``slowquant_b200.distributed``)."""
         self.num_inactive_orbs = num_inactive_orbs
         self.num_active_orbs = num_active_orbs
         self.num_virtual_orbs = num_virtual_orbs
@@ -95,11 +97,21 @@ class CI_Info:
         lib = _lib.load()
         handle = C.c_void_p()
         rb, re = (0, -1) if row_range is None else row_range
-        _lib.check(
-            lib.sq_space_create(
-                num_active_orbs, num_active_elec_alpha, num_active_elec_beta, self.device, rb, re, C.byref(handle)
+        if alpha_constraint is not None:
+            if row_range is not None:
+                raise ValueError("alpha_constraint and row_range are mutually exclusive")
+            _lib.check(
+                lib.sq_space_create_constrained(
+                    num_active_orbs, num_active_elec_alpha, num_active_elec_beta, self.device,
+                    int(alpha_constraint[0]), int(alpha_constraint[1]), C.byref(handle),
+                )
             )
-        )
+        else:
+            _lib.check(
+                lib.sq_space_create(
+                    num_active_orbs, num_active_elec_alpha, num_active_elec_beta, self.device, rb, re, C.byref(handle)
+                )
+            )
         self._handle = handle
         self.num_det = int(lib.sq_space_num_det(handle))
         self.num_alpha_strings = int(lib.sq_space_num_strings(handle, 0))

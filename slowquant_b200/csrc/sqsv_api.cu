@@ -35,6 +35,11 @@ static int build_pair_tables(sq_space* sp, int i, int a, PairTables* pt) {
   }
   pt->i = i;
   pt->a = a;
+  if (sp->alpha_cmask & ((1u << i) | (1u << a))) {
+    // constrained alpha list: partner rows do not exist in this space; the pair is never launched here
+    pt->blocked = true;
+    return SQ_OK;
+  }
   StringAction actA, actB, actD;
   int32_t la[2] = {2 * (2 * a) + 1, 2 * (2 * i)};
   int32_t lb[2] = {2 * (2 * a + 1) + 1, 2 * (2 * i + 1)};
@@ -236,9 +241,10 @@ static int normal_order_blocks(std::vector<int>& crea, std::vector<int>& anni) {
 
 // Tables for G = a+_{a} a+_{b} ... a_{j} a_{i}  (operators.py:145-359) given the reference's index tuple
 // (i,j,..,a,b,..).
-static int build_gen_tables(sq_space* sp, const std::vector<int>& idx, GenTables* gt, bool* null_op) {
+static int build_gen_tables(sq_space* sp, const std::vector<int>& idx, GenTables* gt, bool* null_op, bool* blocked) {
   const int rank = (int)idx.size() / 2;
   *null_op = false;
+  *blocked = false;
   std::vector<int> crea(idx.begin() + rank, idx.end());            // a, b, c, ... in product order
   std::vector<int> anni(idx.begin(), idx.begin() + rank);          // i, j, k, ...
   std::reverse(anni.begin(), anni.end());                          // product order is ... a_k a_j a_i
@@ -269,6 +275,10 @@ static int build_gen_tables(sq_space* sp, const std::vector<int>& idx, GenTables
     // reference would raise KeyError.  Mirror that.
     sq_set_error("excitation generator does not conserve N_alpha / N_beta");
     return SQ_ERR_OUTSIDE;
+  }
+  if (sp->alpha_cmask & act.flipA) {   // constrained alpha list: the targets are not in this space
+    *blocked = true;
+    return SQ_OK;
   }
   std::vector<int32_t> srcRows, tgtRows, colCode(sp->NB, -1);
   std::vector<int8_t> sgnRows;
@@ -357,10 +367,12 @@ extern "C" int sq_layout_create(sq_space* sp, int n_ops, const int32_t* exc_type
           op.null_op = (op.gen < 0);
         } else {
           GenTables gt;
-          bool null_op = false;
-          status = build_gen_tables(sp, op.idx, &gt, &null_op);
+          bool null_op = false, blocked = false;
+          status = build_gen_tables(sp, op.idx, &gt, &null_op, &blocked);
           if (status != SQ_OK) break;
-          if (null_op) {
+          if (blocked) {
+            op.blocked = true;   // not cached: the next operator with these indices is marked the same way
+          } else if (null_op) {
             op.null_op = true;
             lay->gen_index[op.idx] = -1;
           } else {
@@ -427,6 +439,9 @@ extern "C" int sq_layout_attach_generator(sq_layout* lay, int k, int n_strings, 
   }
   delete op.multi;
   op.multi = g;
+  op.blocked = false;
+  for (const StringAction& a : g->strings)
+    if (lay->sp->alpha_cmask & a.flipA) op.blocked = true;
   return SQ_OK;
 }
 
@@ -454,6 +469,12 @@ extern "C" int sq_layout_destroy(sq_layout* lay) {
 }
 
 extern "C" int sq_layout_num_ops(const sq_layout* lay) { return lay ? (int)lay->ops.size() : -1; }
+
+extern "C" int sq_layout_op_blocked(const sq_layout* lay, int k) {
+  if (!lay || k < 0 || k >= (int)lay->ops.size()) return -1;
+  const LayoutOp& op = lay->ops[k];
+  return (op.blocked || (op.pair >= 0 && lay->pairs[op.pair].blocked)) ? 1 : 0;
+}
 
 // work-list statistics of operator k on this rank: out6 = {orbital-pair id or -1, local row pairs,
 // local inert rows, cross-device row pairs this rank works on, cross_global, touched amplitudes}
@@ -538,6 +559,7 @@ static bool quad_enabled() {
 static int get_quad(sq_layout* lay, int pA, int pB, const QuadTables** out) {
   *out = nullptr;
   if (pA < 0 || pB < 0 || pA == pB) return SQ_OK;
+  if (lay->pairs[pA].blocked || lay->pairs[pB].blocked) return SQ_OK;
   auto key = std::make_pair(pA, pB);
   auto it = lay->quads.find(key);
   if (it == lay->quads.end()) {
@@ -638,6 +660,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
     return SQ_OK;
   }
+  if (strcmp(name, "reshard") == 0) {   // re-shard kernel of sharded vectors: "tma" (default, bulk-copy engine) or "lsu"
+    sq_reshard_set_mode(value && strcmp(value, "lsu") == 0);
+    return SQ_OK;
+  }
   sq_set_error("sq_set_option: unknown option '%s'", name);
   return SQ_ERR_INVALID;
 }
@@ -694,7 +720,7 @@ static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& ru
       return SQ_OK;
     }
   SQ_CHECK(plan_launches_uncached(lay, runs, out));
-  if (lay->plans.size() >= 16) lay->plans.erase(lay->plans.begin());
+  if (lay->plans.size() >= 64) lay->plans.erase(lay->plans.begin());   // the re-sharding driver plans one run list per phase
   lay->plans.push_back({runs, *out});
   return SQ_OK;
 }
@@ -961,6 +987,43 @@ extern "C" int sq_layout_plan_stats(const sq_layout* lay_c, int first, int last,
   return SQ_OK;
 }
 
+// the same summary for an explicit operator list in execution order (one phase of the re-sharding driver):
+// out8 = {launches, window sweeps, bricks inside window sweeps, quad launches, single-brick launches, other launches,
+//         kernels (without gauge sweeps), amplitudes those kernels read and write}
+extern "C" int sq_layout_plan_stats_list(const sq_layout* lay_c, int n_list, const int32_t* op_list, int64_t* out8) {
+  sq_layout* lay = const_cast<sq_layout*>(lay_c);
+  if (!lay || !out8 || n_list < 0 || (n_list > 0 && !op_list)) return SQ_ERR_INVALID;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  std::vector<int> order;
+  for (int i = 0; i < n_list; ++i) {
+    if (op_list[i] < 0 || op_list[i] >= (int)lay->ops.size()) return SQ_ERR_INVALID;
+    const LayoutOp& op = lay->ops[op_list[i]];
+    if (op.blocked || (op.pair >= 0 && lay->pairs[op.pair].blocked)) {
+      sq_set_error("sq_layout_plan_stats_list: operator %d cannot run in this space", op_list[i]);
+      return SQ_ERR_UNSUPPORTED;
+    }
+    order.push_back(op_list[i]);
+  }
+  std::vector<double> th(lay->ops.size(), 1.0);
+  std::vector<std::vector<int>> runs;
+  std::vector<Launch> launches;
+  plan_runs(lay, order, th.data(), &runs);
+  SQ_CHECK(plan_launches(lay, runs, &launches));
+  for (auto& l : launches) {
+    ++out8[0];
+    if (l.kind == 2) { ++out8[1]; out8[2] += (int64_t)l.runs.size(); }
+    else if (l.kind == 1) ++out8[3];
+    else if (is_tile_op(lay->ops[runs[l.runs[0]][0]])) ++out8[4];
+    else ++out8[5];
+    int nk;
+    int64_t t;
+    launch_cost(lay, runs, l, &nk, &t);
+    out8[6] += nk;
+    out8[7] += t;
+  }
+  return SQ_OK;
+}
+
 // the plan itself, for tests of the planner: operators of [first,last) in EXECUTION order (dagger: reversed circuit) with the
 // index of the launch each one rides in.  thetas_host may be NULL (all operators active) -- zero angles are skipped as in
 // sq_ups_apply.  Returns SQ_ERR_INVALID if cap is too small; *n_out = number of entries.
@@ -1089,6 +1152,8 @@ static int run_tile(sq_space* sp, sq_layout* lay, const std::vector<int>& run, c
 
 static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
                           double* state_dev, const PeerPtrs* peers, void* stream);
+static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order, int dagger,
+                           double* state_dev, const PeerPtrs* peers, void* stream, int gauge_flags);
 
 extern "C" int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
                             double* state_dev, void* stream) {
@@ -1214,21 +1279,59 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
     sq_set_error("sq_ups_apply: bad operator range [%d,%d) for %d operators", first, last, P);
     return SQ_ERR_INVALID;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   if (sp->device < 0) {
     sq_set_error("sq_ups_apply: host-only space (device = -1) cannot run kernels");
     return SQ_ERR_INVALID;
   }
-  SQ_CUDA(cudaSetDevice(sp->device));
   std::vector<int> order;
   exec_order(first, last, dagger, &order);
+  return ups_apply_order(sp, lay, thetas_host, order, dagger, state_dev, peers, stream, 0);
+}
+
+// Operators `op_list` (indices into the layout) in the given EXECUTION order; dagger != 0 only negates the angles.  The caller
+// vouches that the order is equivalent to the circuit order (operators that are moved past each other commute) -- this is how
+// the re-sharding driver (slowquant_b200/distributed.py) runs the part of a circuit that is executable in the current row
+// layout.  gauge_flags bit 0: the vector is in the sign-free gauge of the window kernel on entry; bit 1: leave it in that
+// gauge on return (the gauge is a property of the determinant, not of the row layout, so it survives a re-shard).
+extern "C" int sq_ups_apply_list(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                                 int dagger, int gauge_flags, double* state_dev, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !state_dev || n_list < 0 || (n_list > 0 && (!op_list || !thetas_host))) return SQ_ERR_INVALID;
+  if (sp->device < 0) {
+    sq_set_error("sq_ups_apply_list: host-only space (device = -1) cannot run kernels");
+    return SQ_ERR_INVALID;
+  }
+  const int P = (int)lay->ops.size();
+  std::vector<int> order(op_list, op_list + n_list);
+  std::vector<char> seen((size_t)P, 0);
+  for (int k : order) {
+    if (k < 0 || k >= P || seen[k]) {
+      sq_set_error("sq_ups_apply_list: operator index %d out of range or repeated", k);
+      return SQ_ERR_INVALID;
+    }
+    seen[k] = 1;
+  }
+  return ups_apply_order(sp, lay, thetas_host, order, dagger, state_dev, nullptr, stream, gauge_flags);
+}
+
+static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order, int dagger,
+                           double* state_dev, const PeerPtrs* peers, void* stream, int gauge_flags) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  for (int k : order) {
+    const LayoutOp& op = lay->ops[k];
+    if (std::fabs(thetas_host[k]) < 1e-28) continue;
+    if (op.blocked || (op.pair >= 0 && lay->pairs[op.pair].blocked)) {
+      sq_set_error("operator %d moves an alpha electron on a constrained orbital of this space (re-shard first)", k);
+      return SQ_ERR_UNSUPPORTED;
+    }
+  }
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, thetas_host, &runs);
   std::vector<Launch> launches;
   SQ_CHECK(plan_launches(lay, runs, &launches));
   static const bool timing = getenv("SQ_LAUNCH_TIMING") != nullptr;   // debug: per-launch device time on stderr
-  cudaEvent_t tev0 = nullptr, tev1 = nullptr;
-  if (timing) {
+  static cudaEvent_t tev0 = nullptr, tev1 = nullptr;   // created once (debug switch only)
+  if (timing && !tev0) {
     cudaEventCreate(&tev0);
     cudaEventCreate(&tev1);
   }
@@ -1253,7 +1356,7 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
     }
   };
   // window sweeps work in the sign-free gauge (sqsv_win.cu); every other kernel in the reference's sign convention
-  bool in_gauge = false;
+  bool in_gauge = (gauge_flags & 1) != 0;
   for (const Launch& l : launches) {
     if ((l.kind == 2) != in_gauge) {
       SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
@@ -1306,7 +1409,7 @@ static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_hos
       return SQ_ERR_INVALID;
     }
   }
-  if (in_gauge) SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
+  if (in_gauge != ((gauge_flags & 2) != 0)) SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
   return SQ_OK;
 }
 

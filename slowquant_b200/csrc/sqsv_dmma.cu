@@ -1,0 +1,319 @@
+// Hand-written fp64 tensor-core (DMMA) contractions of the sigma / RDM path -- the only GEMM-shaped work of the engine
+// (north_star: "the strided-to-dense 2-RDM contraction ... is the only step allowed onto fp64 tensor cores").  tcgen05 has no
+// fp64, so on sm_100a the fp64 tensor path is mma.sync.aligned.m8n8k4.f64 (DMMA in the SASS); operands are staged in shared
+// memory by multi-stage cp.async pipelines, accumulators live in registers.  These kernels replace the cuBLAS DGEMM calls of
+// round 1 (cuBLAS dispatched an sm_80 CUTLASS kernel for these shapes).
+//
+//   gram_dmma_kernel   G2[a][b] += sum_t X[a][t] Y[b][t]        (a, b < n^2 = 256, t over the W determinants of a panel)
+//                      reference: the <E_pq E_rs> loops of ups_wavefunction.py:432-476.  128 x 128 output tiles, split-K over
+//                      the CTAs of the grid; every (tile, split) owns one slot of a persistent partial-sum buffer that it
+//                      updates in panel order, and one reduction kernel adds the slots in a fixed order at the end: the
+//                      summation order is deterministic (no atomics).  For bra == ket only the upper-triangular tiles run.
+//   sigma_dmma_kernel  F[pq][t] = sum_rs Gm[pq][rs] D[rs][t]    (pq, rs < 136 symmetrised generators, or n^2)
+//                      reference: the two-body part of hamiltonian_0i_0a applied string by string (operators.py:476-529,
+//                      operator_state_algebra.py:596-628).  One CTA = all rows x 128 determinants; the integral matrix
+//                      streams through shared memory in chunks of 8 columns.
+//
+// Fragment layout of mma.m8n8k4.f64 (PTX ISA): A (8x4, row): a0 = A[lane >> 2][lane & 3]; B (4x8, col): b0 = B[lane & 3][lane >> 2];
+// C/D (8x8): c{0,1} = C[lane >> 2][2 * (lane & 3) + {0,1}].
+#include <cstdio>
+#include <cstdlib>
+
+#include "sqsv_internal.h"
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int src_bytes) {
+  // 16-byte async copy; src_bytes = 0 zero-fills the destination (rows / columns beyond the matrix)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Gram matrix: 128 x 128 tile of G2 per CTA, K range [k_begin, k_end) of the panel (multiples of GR_KC).
+// ------------------------------------------------------------------------------------------------------------------
+#define GR_BM 128
+#define GR_KC 16
+#define GR_LD 20            // shared-memory row stride in doubles: = 4 (mod 16) -> conflict-free fragment loads
+#define GR_STAGES 4
+#define GR_THREADS 256
+
+struct GramTiles {          // output tiles of one launch (upper triangle for bra == ket)
+  int n;
+  int ta[16], tb[16];
+};
+
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gram_dmma_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t ld, int nrows, int64_t K, int n_split,
+                 const GramTiles tiles, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double gsm[];
+  const int tile = blockIdx.x / n_split, split = blockIdx.x % n_split;
+  const int a0 = tiles.ta[tile] * GR_BM, b0 = tiles.tb[tile] * GR_BM;
+  const int64_t n_chunks = K / GR_KC;
+  const int64_t c_begin = n_chunks * split / n_split, c_end = n_chunks * (split + 1) / n_split;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps: 64 x 32 outputs each
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(gsm);
+  constexpr int STAGE_D = 2 * GR_BM * GR_LD;         // doubles per stage (X tile, then Y tile)
+  // one stage: 2 x 128 rows x 16 doubles = 2 x 1024 16-byte chunks; thread t copies chunks t, t + 256, ...
+  auto issue = [&](int64_t c, int slot) {
+    const int64_t k0 = c * GR_KC;
+    const uint32_t sb = sbase + (uint32_t)(slot * STAGE_D) * 8u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int id = threadIdx.x + q * GR_THREADS;   // 0 .. 2047
+      const int which = id >> 10, r = (id >> 3) & 127, ch = id & 7;
+      const int row = (which ? b0 : a0) + r;
+      const double* src = (which ? Y : X) + (int64_t)(row < nrows ? row : 0) * ld + k0 + ch * 2;
+      cp16(sb + (uint32_t)(which * GR_BM * GR_LD + r * GR_LD + ch * 2) * 8u, src, row < nrows ? 16 : 0);
+    }
+  };
+  const int64_t n_it = c_end - c_begin;
+  for (int s = 0; s < GR_STAGES - 1; ++s) {
+    if (s < n_it) issue(c_begin + s, s);
+    cp_commit();
+  }
+  for (int64_t it = 0; it < n_it; ++it) {
+    cp_wait<GR_STAGES - 2>();
+    __syncthreads();                                  // stage `it` has landed for everybody; slot (it - 1) is free
+    if (it + GR_STAGES - 1 < n_it) issue(c_begin + it + GR_STAGES - 1, (int)((it + GR_STAGES - 1) % GR_STAGES));
+    cp_commit();
+    const double* xs = gsm + (it % GR_STAGES) * STAGE_D;
+    const double* ys = xs + GR_BM * GR_LD;
+#pragma unroll
+    for (int k4 = 0; k4 < GR_KC / 4; ++k4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = xs[(wm * 64 + i * 8 + (lane >> 2)) * GR_LD + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = ys[(wn * 32 + j * 8 + (lane >> 2)) * GR_LD + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  // this (tile, split) slot is owned by exactly one CTA per launch and launches are stream-ordered: plain read-modify-write
+  double* out = partial + ((size_t)split * 16 + tile) * (GR_BM * GR_BM);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = wm * 64 + i * 8 + (lane >> 2), c = wn * 32 + j * 8 + 2 * (lane & 3);
+      double2* p = reinterpret_cast<double2*>(out + r * GR_BM + c);
+      double2 v = *p;
+      v.x += acc[i][j][0];
+      v.y += acc[i][j][1];
+      *p = v;
+    }
+}
+
+// G2[a][b] (row-major, leading dimension nrows) = sum over the splits, in split order; mirrored tiles are filled from their
+// transposes (bra == ket).
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const double* __restrict__ partial, int n_split, const GramTiles tiles, int nrows, int mirror,
+                   double* __restrict__ G2) {
+  const int tile = blockIdx.y;
+  const int e = blockIdx.x * 256 + threadIdx.x;       // element of the 128 x 128 tile
+  const int r = e / GR_BM, c = e % GR_BM;
+  const int a = tiles.ta[tile] * GR_BM + r, b = tiles.tb[tile] * GR_BM + c;
+  if (a >= nrows || b >= nrows) return;
+  double s = 0.0;
+  for (int k = 0; k < n_split; ++k) s += partial[((size_t)k * 16 + tile) * (GR_BM * GR_BM) + e];
+  G2[(size_t)a * nrows + b] = s;
+  if (mirror && tiles.ta[tile] != tiles.tb[tile]) G2[(size_t)b * nrows + a] = s;
+}
+
+struct GramState {
+  double* d_partial = nullptr;
+  int n_split = 0;
+  GramTiles tiles;
+};
+
+static size_t gram_smem() { return sizeof(double) * GR_STAGES * 2 * GR_BM * GR_LD; }
+
+// begin an accumulation: tiles of the nrows x nrows Gram matrix, zeroed partial sums
+int sq_gram_begin(int nrows, bool symmetric, int n_sm, double** d_partial, size_t* partial_doubles, GramTiles* tiles, int* n_split,
+                  cudaStream_t st) {
+  const int nt = (nrows + GR_BM - 1) / GR_BM;
+  tiles->n = 0;
+  for (int a = 0; a < nt; ++a)
+    for (int b = symmetric ? a : 0; b < nt; ++b) {
+      if (tiles->n >= 16) {
+        sq_set_error("Gram matrix of %d rows needs more than 16 output tiles", nrows);
+        return SQ_ERR_UNSUPPORTED;
+      }
+      tiles->ta[tiles->n] = a;
+      tiles->tb[tiles->n] = b;
+      ++tiles->n;
+    }
+  *n_split = std::max(1, n_sm / tiles->n);             // one CTA per SM (one wave)
+  const size_t need = (size_t)(*n_split) * 16 * GR_BM * GR_BM;
+  if (*partial_doubles < need) {
+    if (*d_partial) cudaFree(*d_partial);
+    *d_partial = nullptr;
+    *partial_doubles = 0;
+    SQ_CUDA(cudaMalloc(d_partial, sizeof(double) * need));
+    *partial_doubles = need;
+  }
+  SQ_CUDA(cudaMemsetAsync(*d_partial, 0, sizeof(double) * need, st));
+  return SQ_OK;
+}
+
+// one panel: partial[tile, split] += X[a-tile rows][k range of the split] . Y[b-tile rows][same]^T
+int sq_gram_panel(const double* X, const double* Y, int64_t ld, int nrows, int64_t K, const GramTiles& tiles, int n_split,
+                  double* d_partial, cudaStream_t st) {
+  if (K % GR_KC != 0 || ld % 2 != 0) {
+    sq_set_error("Gram panel: K = %lld must be a multiple of %d and the leading dimension even", (long long)K, GR_KC);
+    return SQ_ERR_INVALID;
+  }
+  static bool attr = false;
+  if (!attr) {
+    SQ_CUDA(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem()));
+    attr = true;
+  }
+  gram_dmma_kernel<<<(unsigned)(tiles.n * n_split), GR_THREADS, gram_smem(), st>>>(X, Y, ld, nrows, K, n_split, tiles, d_partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("gram_dmma_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, int nrows, bool symmetric, double* d_G2, cudaStream_t st) {
+  const dim3 grid(GR_BM * GR_BM / 256, (unsigned)tiles.n);
+  gram_reduce_kernel<<<grid, 256, 0, st>>>(d_partial, n_split, tiles, nrows, symmetric ? 1 : 0, d_G2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("gram_reduce_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// sigma: F[m][t] = sum_k Gm[m][k] D[k][t], m, k < nrow (padded to MT * 8 rows in registers), t in a tile of 128 determinants
+// ------------------------------------------------------------------------------------------------------------------
+#define SG_BN 128
+#define SG_KC 8
+#define SG_LDA 12           // Gm chunk [m][8] row stride: = 12 (mod 16) -> conflict-free A fragments
+#define SG_LDB 132          // D chunk [8][128] row stride: = 4 (mod 16) -> conflict-free B fragments
+#define SG_STAGES 3
+#define SG_THREADS 256
+
+template <int MT>            // MT = ceil(nrow / 8) row fragments per warp (17 for the 136 symmetrised generators of n = 16)
+__global__ void __launch_bounds__(SG_THREADS, 1)
+sigma_dmma_kernel(const double* __restrict__ Gm, const double* __restrict__ D, double* __restrict__ F, int nrow, int64_t W) {
+  extern __shared__ __align__(16) double ssm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t0 = (int64_t)blockIdx.x * SG_BN;
+  const int MP = MT * 8;                                  // padded rows
+  const int stage_d = MP * SG_LDA + SG_KC * SG_LDB;       // doubles per stage
+  const int n_chunks = (nrow + SG_KC - 1) / SG_KC;
+  double acc[MT][2][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ssm);
+  auto issue = [&](int c, int slot) {
+    const int k0 = c * SG_KC;
+    const uint32_t sa = sbase + (uint32_t)(slot * stage_d) * 8u, sb = sa + (uint32_t)(MP * SG_LDA) * 8u;
+    // Gm chunk: MP rows x 8 doubles = MP * 4 16-byte chunks (rows / columns beyond nrow are zero-filled)
+    for (int id = threadIdx.x; id < MP * 4; id += SG_THREADS) {
+      const int m = id >> 2, ch = id & 3;
+      const bool ok = m < nrow && k0 + ch * 2 < nrow;     // nrow is even for every n (n (n + 1) / 2 or n^2 with ... see launcher)
+      cp16(sa + (uint32_t)(m * SG_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m : 0) * nrow + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
+    }
+    // D chunk: 8 rows x 128 doubles = 512 16-byte chunks
+    for (int id = threadIdx.x; id < SG_KC * (SG_BN / 2); id += SG_THREADS) {
+      const int k = id >> 6, ch = id & 63;
+      const bool ok = k0 + k < nrow;
+      cp16(sb + (uint32_t)(k * SG_LDB + ch * 2) * 8u, D + (size_t)(ok ? k0 + k : 0) * W + t0 + ch * 2, ok ? 16 : 0);
+    }
+  };
+  for (int s = 0; s < SG_STAGES - 1; ++s) {
+    if (s < n_chunks) issue(s, s);
+    cp_commit();
+  }
+  for (int it = 0; it < n_chunks; ++it) {
+    cp_wait<SG_STAGES - 2>();
+    __syncthreads();
+    if (it + SG_STAGES - 1 < n_chunks) issue(it + SG_STAGES - 1, (it + SG_STAGES - 1) % SG_STAGES);
+    cp_commit();
+    const double* as = ssm + (it % SG_STAGES) * stage_d;
+    const double* bs = as + MP * SG_LDA;
+#pragma unroll
+    for (int k4 = 0; k4 < SG_KC / 4; ++k4) {
+      const double b0 = bs[(k4 * 4 + (lane & 3)) * SG_LDB + warp * 16 + (lane >> 2)];
+      const double b1 = bs[(k4 * 4 + (lane & 3)) * SG_LDB + warp * 16 + 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double a = as[(i * 8 + (lane >> 2)) * SG_LDA + k4 * 4 + (lane & 3)];
+        dmma884(acc[i][0][0], acc[i][0][1], a, b0);
+        dmma884(acc[i][1][0], acc[i][1][1], a, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int m = i * 8 + (lane >> 2);
+    if (m < nrow) {
+      double* p = F + (size_t)m * W + t0 + warp * 16 + 2 * (lane & 3);
+      *reinterpret_cast<double2*>(p) = make_double2(acc[i][0][0], acc[i][0][1]);
+      *reinterpret_cast<double2*>(p + 8) = make_double2(acc[i][1][0], acc[i][1][1]);
+    }
+  }
+}
+
+template <int MT>
+static int launch_sigma_mt(const double* Gm, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
+  const size_t smem = sizeof(double) * SG_STAGES * ((size_t)MT * 8 * SG_LDA + SG_KC * SG_LDB);
+  static bool attr = false;
+  if (!attr) {
+    SQ_CUDA(cudaFuncSetAttribute(sigma_dmma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  sigma_dmma_kernel<MT><<<(unsigned)(W / SG_BN), SG_THREADS, smem, st>>>(Gm, D, F, nrow, W);
+  return SQ_OK;
+}
+
+// F (nrow x W, row-major, ld W) = Gm (nrow x nrow, row-major) * D (nrow x W, row-major)
+int sq_sigma_gemm(const double* Gm, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
+  if (W % SG_BN != 0 || nrow < 1 || nrow % 2 != 0) {
+    sq_set_error("sigma GEMM: panel width %lld must be a multiple of %d and the row count %d even", (long long)W, SG_BN, nrow);
+    return SQ_ERR_INVALID;
+  }
+  const int mt = (nrow + 7) / 8;
+  int rc = SQ_ERR_UNSUPPORTED;
+  // accumulators: 4 * MT doubles per thread; instantiations cover n <= 16 symmetrised (136 rows) and n <= 11 general (121 rows)
+  switch (mt) {
+#define SG_CASE(M) case M: rc = launch_sigma_mt<M>(Gm, D, F, nrow, W, st); break;
+    SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8) SG_CASE(9) SG_CASE(10) SG_CASE(11)
+    SG_CASE(12) SG_CASE(13) SG_CASE(14) SG_CASE(15) SG_CASE(16) SG_CASE(17)
+#undef SG_CASE
+    default: break;
+  }
+  if (rc == SQ_ERR_UNSUPPORTED) {
+    sq_set_error("sigma GEMM: %d generator rows exceed the register-tiled kernel (max 136)", nrow);
+    return rc;
+  }
+  SQ_CHECK(rc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("sigma_dmma_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}

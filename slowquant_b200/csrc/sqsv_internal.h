@@ -81,6 +81,7 @@ struct PairTables {       // tables for one spatial orbital pair (i,a)
   int4* d_rowItems = nullptr;
   int n_rowchunk_src = 0, n_rowchunk_inert = 0;
   int sigma = 0;                 // gauge-invariant pair-double sign (+1/-1) if uniform, 0 otherwise
+  bool blocked = false;          // the pair touches a constrained alpha orbital of the space: no tables, never launched
   bool cross_global = false;     // some row pair of this orbital pair spans two devices (same answer on every rank)
   int64_t n_cross_items = 0;     // cross-device row pairs this rank works on (half of the columns each)
 };
@@ -118,6 +119,9 @@ struct sq_space {
   int n_orb, n_alpha, n_beta, device;
   int64_t NA, NB, ndet;
   int64_t row_begin, row_end;       // local alpha rows
+  // constrained alpha list (sq_space_create_constrained): only the strings with (mask & alpha_cmask) == alpha_cpat, in the
+  // order they have in the full list.  Operators that move an alpha electron on a constrained orbital are "blocked".
+  uint32_t alpha_cmask = 0, alpha_cpat = 0;
   int world = 1, rank = 0;          // alpha-row partition over devices (sq_space_set_partition)
   std::vector<int64_t> row_starts;  // [world + 1]; rank r owns rows [row_starts[r], row_starts[r+1])
   unsigned long long* d_peer_tab = nullptr;             // device table of shard base pointers (cross-device tiles)
@@ -149,6 +153,7 @@ struct LayoutOp {
   bool pair_double = false;
   int gen = -1;       // index into sq_layout::gens (generic single-string generator)
   bool null_op = false;  // generator vanishes identically
+  bool blocked = false;  // moves an alpha electron on a constrained orbital of the space (sq_space_create_constrained)
   GenOp* multi = nullptr;
 };
 
@@ -198,6 +203,7 @@ void sq_hamiltonian_set_pipeline(int on);          // sigma / RDM panel pipeline
 void sq_hamiltonian_set_etab_alu(int on);          // panel kernels without an E_pq table (records computed from (p,q); default off)
 void sq_hamiltonian_set_rdm_tri(int on);           // RDMs with bra == ket: three half-size DGEMMs instead of one (default off)
 void sq_hamiltonian_set_etab_mode(int use_const);  // E_pq table in constant (1) or shared (0) memory
+void sq_reshard_set_mode(int lsu);                 // re-shard kernel: 0 bulk-copy engine (default), 1 vector load/store
 int sq_ensure_work(sq_space* sp, int which);
 int sq_ensure_partial(sq_space* sp, int64_t n);
 

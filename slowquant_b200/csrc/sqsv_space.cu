@@ -49,8 +49,29 @@ int sq_rank_mask(const sq_space* sp, int spin, uint32_t mask) {
   return r[mask];
 }
 
+static int space_create_impl(int n_orb, int n_alpha, int n_beta, int device, int64_t row_begin, int64_t row_end,
+                             uint32_t alpha_cmask, uint32_t alpha_cpat, sq_space** out);
+
 extern "C" int sq_space_create(int n_orb, int n_alpha, int n_beta, int device, int64_t row_begin,
                                int64_t row_end, sq_space** out) {
+  return space_create_impl(n_orb, n_alpha, n_beta, device, row_begin, row_end, 0u, 0u, out);
+}
+
+// A space whose alpha list holds only the strings with (mask & alpha_cmask) == alpha_cpat, in the order they have in the full
+// itertools.combinations list (the second layout of a re-sharded vector: rows grouped by the occupation of the LAST log2(G)
+// orbitals).  All rows are local; operators that move an alpha electron on a constrained orbital cannot run in this space.
+extern "C" int sq_space_create_constrained(int n_orb, int n_alpha, int n_beta, int device, uint32_t alpha_cmask,
+                                           uint32_t alpha_cpat, sq_space** out) {
+  if (n_orb >= 1 && n_orb < 32 && ((alpha_cmask >> n_orb) != 0u || (alpha_cpat & ~alpha_cmask) != 0u)) {
+    sq_set_error("sq_space_create_constrained: mask 0x%x / pattern 0x%x do not fit %d orbitals", alpha_cmask, alpha_cpat, n_orb);
+    if (out) *out = nullptr;
+    return SQ_ERR_INVALID;
+  }
+  return space_create_impl(n_orb, n_alpha, n_beta, device, 0, -1, alpha_cmask, alpha_cpat, out);
+}
+
+static int space_create_impl(int n_orb, int n_alpha, int n_beta, int device, int64_t row_begin, int64_t row_end,
+                             uint32_t alpha_cmask, uint32_t alpha_cpat, sq_space** out) {
   if (!out) return SQ_ERR_INVALID;
   *out = nullptr;
   if (n_orb < 1 || n_orb > 26 || n_alpha < 0 || n_beta < 0 || n_alpha > n_orb || n_beta > n_orb) {
@@ -71,6 +92,14 @@ extern "C" int sq_space_create(int n_orb, int n_alpha, int n_beta, int device, i
   }
   enumerate_strings(n_orb, n_alpha, sp->strA);
   enumerate_strings(n_orb, n_beta, sp->strB);
+  sp->alpha_cmask = alpha_cmask;
+  sp->alpha_cpat = alpha_cpat;
+  if (alpha_cmask) {
+    std::vector<uint32_t> keep;
+    for (uint32_t m : sp->strA)
+      if ((m & alpha_cmask) == alpha_cpat) keep.push_back(m);
+    sp->strA.swap(keep);
+  }
   sp->NA = (int64_t)sp->strA.size();
   sp->NB = (int64_t)sp->strB.size();
   sp->ndet = sp->NA * sp->NB;
@@ -108,7 +137,7 @@ extern "C" int sq_space_create(int n_orb, int n_alpha, int n_beta, int device, i
       return SQ_ERR_CUDA;                                                        \
     }                                                                            \
   } while (0)
-  SP_CUDA(cudaMalloc(&sp->d_strA, sizeof(uint32_t) * sp->NA));
+  SP_CUDA(cudaMalloc(&sp->d_strA, sizeof(uint32_t) * (sp->NA > 0 ? sp->NA : 1)));
   SP_CUDA(cudaMalloc(&sp->d_strB, sizeof(uint32_t) * sp->NB));
   SP_CUDA(cudaMalloc(&sp->d_rankA, sizeof(int32_t) * nmask));
   SP_CUDA(cudaMalloc(&sp->d_rankB, sizeof(int32_t) * nmask));

@@ -736,7 +736,7 @@ void sq_free_win_tables(WinTables* wt) {
 bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H) {
   const PairTables& pt = lay->pairs[pair];
   const int lo = std::min(pt.i, pt.a), hi = std::max(pt.i, pt.a);
-  return hi == lo + 1 && lo >= w0 && hi < w0 + H && !pt.cross_global && pt.n_cross_items == 0;
+  return hi == lo + 1 && lo >= w0 && hi < w0 + H && !pt.blocked && !pt.cross_global && pt.n_cross_items == 0;
 }
 
 size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int nbuf, int lta, int ltb, int maxQ, int maxS, int n_bricks) {

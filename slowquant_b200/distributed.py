@@ -22,12 +22,103 @@ from slowquant_b200 import operator_state_algebra as osa
 from slowquant_b200.ci_spaces import CI_Info
 
 
+import os as _os
+
+_RESHARD_DEFAULT = _os.environ.get("SQ_RESHARD", "1") != "0"   # SQ_RESHARD=0: peer-memory exchange route (A/B comparisons)
+
+
 def partition_prefix(n_orb: int, n_alpha: int, world: int) -> np.ndarray:
     """Row ranges of the prefix-class partition: rank r owns rows [starts[r], starts[r+1])."""
     lib = _lib.load()
     out = np.zeros(world + 1, dtype=np.int64)
     _lib.check(lib.sq_partition_prefix(n_orb, n_alpha, world, out.ctypes.data_as(C.POINTER(C.c_int64))))
     return out
+
+
+def operator_orbitals(exc_type: str, indices) -> int:
+    """Bit mask of the spatial orbitals an ansatz operator acts on (``sa_*``: spatial indices; otherwise spin orbitals)."""
+    m = 0
+    for x in indices:
+        m |= 1 << (int(x) if exc_type.startswith("sa_") else int(x) // 2)
+    return m
+
+
+def reshard_schedule(
+    types: Sequence[str], indices: Sequence[Sequence[int]], n_orb: int, world: int, first: int = 0, last: int | None = None,
+    dagger: bool = False, start: str = "A",
+) -> list[tuple[str, list[int]]]:
+    """Phases ``(layout, [operator indices in execution order])`` of operators [first, last) on a vector sharded over
+    ``world`` = 2^k ranks.  Layout "A" can run an operator iff it touches none of the first k orbitals, layout "B" iff it
+    touches none of the last k; ``("X", [op])`` is an operator neither layout can run (it stays in layout A and exchanges
+    tiles over peer memory).  Within a phase an operator may overtake earlier, not yet executed ones only if it shares no
+    orbital with any of them (products of an even number of ladder operators on disjoint orbitals commute), so the
+    concatenation of the phases is equivalent to the circuit order.  Pure function of the circuit: identical on every rank."""
+    n = len(types)
+    last = n if last is None else last
+    k = max(world - 1, 0).bit_length()
+    low = (1 << k) - 1
+    high = low << (n_orb - k) if k else 0
+    full = (1 << n_orb) - 1
+    order = list(range(first, last))
+    if dagger:
+        order.reverse()
+    orbs = {j: operator_orbitals(types[j], indices[j]) for j in order}
+    ok = {"A": lambda j: not (orbs[j] & low), "B": lambda j: not (orbs[j] & high)}
+    phases: list[tuple[str, list[int]]] = []
+    cur = start
+    remaining = order
+    while remaining:
+        sel: list[int] = []
+        rest: list[int] = []
+        blocked = 0
+        for pos, j in enumerate(remaining):
+            if blocked == full:
+                rest.extend(remaining[pos:])
+                break
+            if ok[cur](j) and not (orbs[j] & blocked):
+                sel.append(j)
+            else:
+                blocked |= orbs[j]
+                rest.append(j)
+        if sel:
+            phases.append((cur, sel))
+        remaining = rest
+        if not remaining:
+            break
+        head = remaining[0]
+        other = "B" if cur == "A" else "A"
+        if ok[other](head):
+            cur = other
+        elif not ok[cur](head):   # local in neither layout
+            phases.append(("X", [head]))
+            remaining = remaining[1:]
+            cur = "A"
+        # else: the head was only blocked by a skipped operator that shares an orbital -- cannot happen for the first entry
+    return phases
+
+
+
+def reshard_tables(strings: np.ndarray, n_orb: int, world: int, row_starts: np.ndarray, rank: int):
+    """Destination (rank, local row) of every local row for the re-shards A -> B and B -> A of rank ``rank``.
+
+    ``strings``: occupation masks of ALL alpha strings in itertools.combinations order.  Layout A: rank r owns the contiguous
+    rows [row_starts[r], row_starts[r+1]).  Layout B: rank r owns the strings whose last log2(world) orbitals carry the bit
+    pattern r, in the order they have in the full list (``sq_space_create_constrained``)."""
+    k = max(world - 1, 0).bit_length()
+    strings = np.asarray(strings, dtype=np.int64)
+    pat = (strings >> (n_orb - k)) & (world - 1)                      # owner in layout B
+    b_local = np.zeros(len(strings), dtype=np.int64)
+    for r in range(world):
+        sel = pat == r
+        b_local[sel] = np.arange(int(sel.sum()))
+    idx = np.arange(len(strings), dtype=np.int64)
+    a_owner = np.searchsorted(np.asarray(row_starts[1:], dtype=np.int64), idx, side="right")
+    a_local = idx - np.asarray(row_starts, dtype=np.int64)[a_owner]
+    mine_a = slice(int(row_starts[rank]), int(row_starts[rank + 1]))
+    mine_b = pat == rank
+    a2b = (pat[mine_a].astype(np.int32), b_local[mine_a].astype(np.int32))
+    b2a = (a_owner[mine_b].astype(np.int32), a_local[mine_b].astype(np.int32))
+    return a2b, b2a
 
 
 class ShardedSpace:
@@ -67,6 +158,27 @@ class ShardedSpace:
         self.local_len = self.ci_info.local_len
         self._barrier_token = None
         self._plans: dict = {}
+        # ---- layout B (rows grouped by the occupation of the LAST log2(world) orbitals) and the re-shard tables ----
+        self.ci_info_B: CI_Info | None = None
+        self.local_len_B = 0
+        self._tab_AB = self._tab_BA = None
+        k = max(self.world - 1, 0).bit_length()
+        n = num_active_orbs
+        self.reshard_ok = self.world > 1 and (1 << k) == self.world and 2 * k <= n
+        if self.reshard_ok:
+            cmask = ((1 << k) - 1) << (n - k)
+            self.ci_info_B = CI_Info(
+                num_inactive_orbs, num_active_orbs, num_virtual_orbs, num_active_elec_alpha, num_active_elec_beta,
+                device=self.ci_info.device, alpha_constraint=(cmask, self.rank << (n - k)),
+            )
+            self.local_len_B = self.ci_info_B.num_alpha_strings * self.ci_info_B.num_beta_strings
+            a2b, b2a = reshard_tables(self.ci_info.strings(0), n, self.world, self.row_starts, self.rank)
+            self.reshard_tables_host = (a2b, b2a)
+            if self.ci_info.device >= 0:
+                dev = torch.device("cuda", self.ci_info.device)
+                self._tab_AB = tuple(torch.from_numpy(t).to(dev) for t in a2b)
+                self._tab_BA = tuple(torch.from_numpy(t).to(dev) for t in b2a)
+            assert len(b2a[0]) == self.ci_info_B.num_alpha_strings
 
     # ---- shards -------------------------------------------------------------------------------
     def alloc_state(self, zero: bool = True) -> "ShardedState":
@@ -131,9 +243,20 @@ class ShardedState:
         self.local = torch.as_tensor(self._iface, device=torch.device("cuda", dev))[:n]
         if zero:
             self.local.zero_()
-        self._peer_ptrs = (C.c_void_p * space.world)()
-        self._peer_ptrs[space.rank] = ptr.value
         self._opened: list[C.c_void_p] = []
+        self._peer_ptrs = self._share(ptr)
+        # layout-B buffer of the re-sharding driver: allocated (collectively) the first time a circuit needs it
+        self._ptr_B = None
+        self._peer_ptrs_B = None
+        self.local_B = None
+
+    def _share(self, ptr: C.c_void_p):
+        """Peer pointers of the buffers `ptr` of all ranks (collective: CUDA-IPC handles are all-gathered)."""
+        lib = _lib.load()
+        space = self.space
+        dev = space.ci_info.device
+        peers = (C.c_void_p * space.world)()
+        peers[space.rank] = ptr.value
         if space.world > 1:
             handle = C.create_string_buffer(64)
             _lib.check(lib.sq_ipc_export(ptr, handle))
@@ -144,10 +267,30 @@ class ShardedState:
                     continue
                 p = C.c_void_p()
                 _lib.check(lib.sq_ipc_import(dev, gathered[r], C.byref(p)))
-                self._peer_ptrs[r] = p.value
+                peers[r] = p.value
                 self._opened.append(p)
             torch.cuda.synchronize()
             dist.barrier()
+        return peers
+
+    def ensure_layout_B(self) -> None:
+        """Collective: allocate and peer-map the layout-B buffer (rows grouped by the last log2(world) orbitals)."""
+        if self._ptr_B is not None:
+            return
+        lib = _lib.load()
+        sp = self.space
+        dev = sp.ci_info.device
+        ptr = C.c_void_p()
+        _lib.check(lib.sq_dist_alloc(dev, sp.local_len_B, C.byref(ptr)))
+        self._ptr_B = ptr
+        n = sp.local_len_B
+
+        class _Iface:
+            __cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+
+        self._iface_B = _Iface()
+        self.local_B = torch.as_tensor(self._iface_B, device=torch.device("cuda", dev))[:n]
+        self._peer_ptrs_B = self._share(ptr)
 
     def close(self) -> None:
         lib = _lib.load()
@@ -157,6 +300,10 @@ class ShardedState:
         for p in self._opened:
             lib.sq_ipc_close(p)
         self._opened = []
+        if self._ptr_B:
+            self.local_B = None
+            lib.sq_dist_free(self._ptr_B)
+            self._ptr_B = None
         if self._ptr:
             self.local = None
             lib.sq_dist_free(self._ptr)
@@ -177,10 +324,34 @@ class ShardedState:
             self.local[index - lo] = 1.0
 
 
+def _reshard(state: ShardedState, to_B: bool) -> None:
+    """All-to-all between the two row layouts: every rank writes its rows into the new owners' buffers (``sq_reshard_rows``),
+    then a device-wide barrier (all rows have landed; nobody reads the old buffer any more when it is written next time)."""
+    lib = _lib.load()
+    sp = state.space
+    nb = sp.ci_info.num_beta_strings
+    if to_B:
+        tab, src, n_rows, dst = sp._tab_AB, state.local, sp.row_end - sp.row_begin, state._peer_ptrs_B
+    else:
+        tab, src, n_rows, dst = sp._tab_BA, state.local_B, sp.ci_info_B.num_alpha_strings, state._peer_ptrs
+    _lib.check(
+        lib.sq_reshard_rows(sp.ci_info.device, n_rows, nb, osa._ptr(src), osa._ptr(tab[0]), osa._ptr(tab[1]), dst, sp.world,
+                            osa._stream())
+    )
+    sp.barrier()
+
+
 def construct_ups_state_sharded(
-    state: ShardedState, thetas: Sequence[float], ups_struct, dagger: bool = False, first: int = 0, last: int | None = None
+    state: ShardedState, thetas: Sequence[float], ups_struct, dagger: bool = False, first: int = 0, last: int | None = None,
+    reshard: bool | None = None,
 ) -> None:
-    """In place: state <- U state (or U^dagger state) on the sharded vector (osa.py:963-1412 semantics)."""
+    """In place: state <- U state (or U^dagger state) on the sharded vector (osa.py:963-1412 semantics).
+
+    Default route (``reshard=True`` wherever the partition allows it): the phases of :func:`reshard_schedule`, each one a fused
+    launch sequence on the local shard in the row layout that makes its operators local, with one all-to-all re-shard between
+    phases; the vector stays in the window kernel's sign-free gauge from the first window sweep to the end of the call.
+    ``reshard=False``: the vector stays in layout A and operators whose row pairs span two GPUs rotate their tiles in place
+    over peer memory, one barrier-fenced operator range at a time."""
     lib = _lib.load()
     sp = state.space
     n_ops = len(ups_struct.excitation_operator_type)
@@ -188,6 +359,64 @@ def construct_ups_state_sharded(
     lay = osa.compile_layout(sp.ci_info, ups_struct)
     th = osa._thetas_array(thetas, n_ops)
     thp = th.ctypes.data_as(C.POINTER(C.c_double))
+    if reshard is None:
+        reshard = sp.reshard_ok and _RESHARD_DEFAULT
+    if reshard and sp.world > 1 and sp.reshard_ok:
+        key = ("reshard", id(ups_struct), n_ops, first, last, bool(dagger))
+        phases = sp._plans.get(key)
+        if phases is None:
+            phases = reshard_schedule(
+                ups_struct.excitation_operator_type, ups_struct.excitation_indices, sp.ci_info.num_active_orbs, sp.world, first, last,
+                dagger,
+            )
+            phases = [(name, np.asarray(ops, dtype=np.int32)) for name, ops in phases]
+            sp._plans[key] = phases
+        if any(name == "B" for name, _ in phases):
+            state.ensure_layout_B()
+            lay_B = osa.compile_layout(sp.ci_info_B, ups_struct)
+        PI = C.POINTER(C.c_int32)
+        where, gauge = "A", False
+
+        def leave_gauge():
+            nonlocal gauge
+            if gauge:
+                info, handle, buf, nloc = (
+                    (sp.ci_info, lay, state.local, sp.local_len) if where == "A" else (sp.ci_info_B, lay_B, state.local_B, sp.local_len_B)
+                )
+                if nloc:
+                    _lib.check(lib.sq_ups_apply_list(info._handle, handle, thp, 0, None, 0, 1, osa._ptr(buf), osa._stream()))
+                gauge = False
+
+        for name, ops in phases:
+            if name == "X":
+                # local in neither layout: cross-device tiles are rotated in place over peer memory (layout A, reference gauge)
+                leave_gauge()
+                if where == "B":
+                    _reshard(state, to_B=False)
+                    where = "A"
+                k = int(ops[0])
+                sp.barrier()
+                _lib.check(lib.sq_ups_apply_dist(sp.ci_info._handle, lay, thp, k, k + 1, 1 if dagger else 0, state._peer_ptrs, osa._stream()))
+                sp.barrier()
+                continue
+            if name != where:
+                _reshard(state, to_B=(name == "B"))
+                where = name
+            info, handle, buf, nloc = (
+                (sp.ci_info, lay, state.local, sp.local_len) if where == "A" else (sp.ci_info_B, lay_B, state.local_B, sp.local_len_B)
+            )
+            # every phase ends in the sign-free gauge on EVERY rank (the ranks' launch plans may differ, the gauge of the rows
+            # they exchange must not); it is left once, at the end of the call
+            if nloc:
+                _lib.check(
+                    lib.sq_ups_apply_list(info._handle, handle, thp, len(ops), ops.ctypes.data_as(PI), 1 if dagger else 0,
+                                          (1 if gauge else 0) | 2, osa._ptr(buf), osa._stream())
+                )
+            gauge = True
+        leave_gauge()
+        if where == "B":
+            _reshard(state, to_B=False)
+        return
     key = (id(ups_struct), n_ops, first, last, bool(dagger))
     plan = sp._plans.get(key)
     if plan is None:

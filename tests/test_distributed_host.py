@@ -196,3 +196,148 @@ def test_gradient_segments_cover_the_circuit_once():
     ups.n_params = len(types)
     seg = gradient_segments([(0, 3, True), (3, 15, False), (15, 18, True), (18, P - 1, False)], ups)
     assert [s[2] for s in seg] == ["shift", "fused", "shift", "fused"]
+
+
+# ---- re-sharding route: phase planner, row tables, constrained (layout B) spaces ---------------------------------------
+def _circuits():
+    from oracle import sq_oracle as orc
+
+    out = []
+    for n, L, qnp in [(6, 3, False), (8, 4, False), (9, 2, True), (16, 16, False), (20, 2, False)]:
+        types, idx = orc.tiled_layout(n, L, do_qnp=qnp)
+        out.append((n, list(types), [tuple(int(x) for x in t) for t in idx]))
+    # generic operators in between (single / double on spin orbitals, an sa_double), incl. one that neither layout can run
+    n = 8
+    types, idx = orc.tiled_layout(n, 1)
+    types, idx = list(types), [tuple(int(x) for x in t) for t in idx]
+    types[5:5] = ["single", "double", "sa_double_1", "double"]
+    idx[5:5] = [(4, 8), (2, 5, 10, 13), (2, 3, 4, 5), (0, 1, 14, 15)]
+    out.append((n, types, idx))
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_reshard_schedule_is_an_equivalent_reordering(world):
+    from slowquant_b200.distributed import operator_orbitals, reshard_schedule
+
+    k = world.bit_length() - 1
+    for n, types, idx in _circuits():
+        if 2 * k > n:
+            continue
+        for dagger in (False, True):
+            for first, last in [(0, len(types)), (2, len(types) - 3)]:
+                phases = reshard_schedule(types, idx, n, world, first, last, dagger)
+                flat = [j for _, ops in phases for j in ops]
+                want = list(range(first, last))[::-1] if dagger else list(range(first, last))
+                assert sorted(flat) == sorted(want)                      # every operator exactly once
+                pos = {j: p for p, j in enumerate(flat)}
+                orbs = {j: operator_orbitals(types[j], idx[j]) for j in want}
+                for a_i, a in enumerate(want):                          # operators that share an orbital keep their order
+                    for b in want[a_i + 1:]:
+                        if orbs[a] & orbs[b]:
+                            assert pos[a] < pos[b], (n, world, a, b)
+                low, high = (1 << k) - 1, ((1 << k) - 1) << (n - k)
+                for (name, ops), nxt in zip(phases, phases[1:] + [("end", [])]):
+                    for j in ops:
+                        if name == "A":
+                            assert not orbs[j] & low
+                        elif name == "B":
+                            assert not orbs[j] & high
+                        else:
+                            assert orbs[j] & low and orbs[j] & high and len(ops) == 1
+                    assert name == "X" or nxt[0] != name                 # maximal phases: neighbours differ
+        # a 16-layer tUPS circuit needs only a handful of re-shards
+    from oracle import sq_oracle as orc
+
+    types, idx = orc.tiled_layout(16, 16)
+    assert len(reshard_schedule(types, idx, 16, world)) <= 6
+
+
+def test_reshard_schedule_order_gives_the_same_state():
+    """Executing the phases in order (oracle, full vector) reproduces the circuit's state, forward and adjoint."""
+    from oracle import sq_oracle as orc
+    from slowquant_b200.distributed import reshard_schedule
+
+    n, na, nb = 6, 3, 3
+    types, idx = orc.tiled_layout(n, 3)
+    rng = np.random.default_rng(5)
+    th = rng.uniform(-np.pi, np.pi, len(types))
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    st = rng.normal(size=sp.num_det)
+    st /= np.linalg.norm(st)
+    for world in (2, 4):
+        for dagger in (False, True):
+            ref = orc.construct_ups_state(st, sp, th, types, idx, dagger=dagger)
+            cur = st.copy()
+            for _, ops in reshard_schedule(types, idx, n, world, dagger=dagger):
+                for j in ops:
+                    cur = orc.construct_ups_state(cur, sp, [th[j]], [types[j]], [idx[j]], dagger=dagger)
+            assert np.max(np.abs(cur - ref)) < 1e-13
+
+
+@pytest.mark.parametrize("world,n,na", [(2, 6, 3), (4, 7, 3), (8, 9, 4), (8, 16, 8), (4, 6, 5)])
+def test_reshard_tables_are_inverse_permutations(world, n, na):
+    """A -> B moves every row to exactly one slot of the rank that owns its last-orbitals pattern, B -> A brings it back."""
+    from slowquant_b200.ci_spaces import CI_Info
+    from slowquant_b200.distributed import partition_prefix, reshard_tables
+
+    info = CI_Info(0, n, 0, na, min(na, 2), device=-1)
+    strs = info.strings(0)
+    starts = partition_prefix(n, na, world)
+    k = world.bit_length() - 1
+    tabs = [reshard_tables(strs, n, world, starts, r) for r in range(world)]
+    cmask = ((1 << k) - 1) << (n - k)
+    lists_B = []
+    for r in range(world):
+        b = CI_Info(0, n, 0, na, min(na, 2), device=-1, alpha_constraint=(cmask, r << (n - k)))
+        sb = b.strings(0)
+        assert np.array_equal(sb, strs[(strs & cmask) == (r << (n - k))])      # constrained list = subset in list order
+        lists_B.append(sb)
+    # scatter the string masks themselves through the tables
+    buf_B = [np.full(len(l), -1, dtype=np.int64) for l in lists_B]
+    for r in range(world):
+        rank_t, row_t = tabs[r][0]
+        rows = strs[int(starts[r]):int(starts[r + 1])]
+        assert len(rank_t) == len(rows)
+        for m, dr, dl in zip(rows, rank_t, row_t):
+            assert buf_B[dr][dl] == -1                                          # written once
+            buf_B[dr][dl] = m
+    for r in range(world):
+        assert np.array_equal(buf_B[r], lists_B[r].astype(np.int64))           # every row landed where layout B expects it
+    buf_A = np.full(len(strs), -1, dtype=np.int64)
+    for r in range(world):
+        rank_t, row_t = tabs[r][1]
+        for m, dr, dl in zip(lists_B[r], rank_t, row_t):
+            g = int(starts[dr]) + int(dl)
+            assert buf_A[g] == -1
+            buf_A[g] = m
+    assert np.array_equal(buf_A, strs.astype(np.int64))
+
+
+def test_constrained_space_blocks_the_right_operators():
+    """Layout-B space on the host: operators that move an alpha electron on a constrained orbital are blocked, the others keep
+    complete partner tables; running a blocked operator is refused."""
+    from slowquant_b200 import operator_state_algebra as osa
+    from slowquant_b200.ci_spaces import CI_Info
+    from slowquant_b200.util import UpsStructure
+
+    lib = _lib.load()
+    n, na, nb, k = 7, 3, 4, 2
+    cmask = ((1 << k) - 1) << (n - k)
+    info = CI_Info(0, n, 0, na, nb, device=-1, alpha_constraint=(cmask, 1 << (n - k)))
+    lay = UpsStructure()
+    lay.create_tiled(n, {"n_layers": 1, "do_tups": True})
+    lay.excitation_operator_type += ["single", "single", "double"]
+    lay.excitation_indices += [(0, 4), (2, 12), (1, 3, 9, 11)]      # alpha 0 -> 2 (free), alpha 1 -> 6 (constrained), beta only
+    lay.n_params = len(lay.excitation_operator_type)
+    handle = osa.compile_layout(info, lay)
+    for j, (t, idx) in enumerate(zip(lay.excitation_operator_type, lay.excitation_indices)):
+        if t == "sa_single":
+            want = max(idx) >= n - k
+        elif t == "double" and len(idx) == 4 and idx[0] % 2 == 0 and idx[1] == idx[0] + 1:
+            want = max(idx) // 2 >= n - k
+        else:
+            want = any(x % 2 == 0 and x // 2 >= n - k for x in idx)
+        assert lib.sq_layout_op_blocked(handle, j) == int(want), (j, t, idx)
+    with pytest.raises(ValueError):
+        CI_Info(0, n, 0, na, nb, device=-1, alpha_constraint=(cmask, 1))     # pattern outside the mask
