@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsqsv.so")
 STAMP = os.path.join(CSRC, ".libsqsv.stamp")
-SOURCES = ["sqsv_space.cu", "sqsv_kernels.cu", "sqsv_api.cu", "sqsv_hamiltonian.cu", "sqsv_quad.cu", "sqsv_win.cu", "sqsv_reshard.cu"]
+SOURCES = ["sqsv_space.cu", "sqsv_kernels.cu", "sqsv_api.cu", "sqsv_hamiltonian.cu", "sqsv_quad.cu", "sqsv_win.cu", "sqsv_reshard.cu", "sqsv_dmma.cu"]
 HEADERS = [os.path.join(CSRC, "sqsv_internal.h"), os.path.join(ROOT, "include", "sqsv.h")]
 
 
@@ -48,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         "-shared", "-Xcompiler", "-fPIC",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
         "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcublas", "-lcudart"]
+    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

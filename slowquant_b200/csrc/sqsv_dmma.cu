@@ -41,10 +41,6 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 #define GR_STAGES 4
 #define GR_THREADS 256
 
-struct GramTiles {          // output tiles of one launch (upper triangle for bra == ket)
-  int n;
-  int ta[16], tb[16];
-};
 
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_dmma_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t ld, int nrows, int64_t K, int n_split,
@@ -103,7 +99,7 @@ gram_dmma_kernel(const double* __restrict__ X, const double* __restrict__ Y, int
     }
   }
   // this (tile, split) slot is owned by exactly one CTA per launch and launches are stream-ordered: plain read-modify-write
-  double* out = partial + ((size_t)split * 16 + tile) * (GR_BM * GR_BM);
+  double* out = partial + ((size_t)split * SQ_GRAM_MAXT + tile) * (GR_BM * GR_BM);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -128,16 +124,10 @@ gram_reduce_kernel(const double* __restrict__ partial, int n_split, const GramTi
   const int a = tiles.ta[tile] * GR_BM + r, b = tiles.tb[tile] * GR_BM + c;
   if (a >= nrows || b >= nrows) return;
   double s = 0.0;
-  for (int k = 0; k < n_split; ++k) s += partial[((size_t)k * 16 + tile) * (GR_BM * GR_BM) + e];
+  for (int k = 0; k < n_split; ++k) s += partial[((size_t)k * SQ_GRAM_MAXT + tile) * (GR_BM * GR_BM) + e];
   G2[(size_t)a * nrows + b] = s;
   if (mirror && tiles.ta[tile] != tiles.tb[tile]) G2[(size_t)b * nrows + a] = s;
 }
-
-struct GramState {
-  double* d_partial = nullptr;
-  int n_split = 0;
-  GramTiles tiles;
-};
 
 static size_t gram_smem() { return sizeof(double) * GR_STAGES * 2 * GR_BM * GR_LD; }
 
@@ -148,8 +138,8 @@ int sq_gram_begin(int nrows, bool symmetric, int n_sm, double** d_partial, size_
   tiles->n = 0;
   for (int a = 0; a < nt; ++a)
     for (int b = symmetric ? a : 0; b < nt; ++b) {
-      if (tiles->n >= 16) {
-        sq_set_error("Gram matrix of %d rows needs more than 16 output tiles", nrows);
+      if (tiles->n >= SQ_GRAM_MAXT) {
+        sq_set_error("Gram matrix of %d rows needs more than %d output tiles", nrows, SQ_GRAM_MAXT);
         return SQ_ERR_UNSUPPORTED;
       }
       tiles->ta[tiles->n] = a;
@@ -157,7 +147,7 @@ int sq_gram_begin(int nrows, bool symmetric, int n_sm, double** d_partial, size_
       ++tiles->n;
     }
   *n_split = std::max(1, n_sm / tiles->n);             // one CTA per SM (one wave)
-  const size_t need = (size_t)(*n_split) * 16 * GR_BM * GR_BM;
+  const size_t need = (size_t)(*n_split) * SQ_GRAM_MAXT * GR_BM * GR_BM;
   if (*partial_doubles < need) {
     if (*d_partial) cudaFree(*d_partial);
     *d_partial = nullptr;
@@ -215,7 +205,7 @@ int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, in
 
 template <int MT>            // MT = ceil(nrow / 8) row fragments per warp (17 for the 136 symmetrised generators of n = 16)
 __global__ void __launch_bounds__(SG_THREADS, 1)
-sigma_dmma_kernel(const double* __restrict__ Gm, const double* __restrict__ D, double* __restrict__ F, int nrow, int64_t W) {
+sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restrict__ D, double* __restrict__ F, int nrow, int64_t W) {
   extern __shared__ __align__(16) double ssm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t t0 = (int64_t)blockIdx.x * SG_BN;
@@ -232,8 +222,8 @@ sigma_dmma_kernel(const double* __restrict__ Gm, const double* __restrict__ D, d
     // Gm chunk: MP rows x 8 doubles = MP * 4 16-byte chunks (rows / columns beyond nrow are zero-filled)
     for (int id = threadIdx.x; id < MP * 4; id += SG_THREADS) {
       const int m = id >> 2, ch = id & 3;
-      const bool ok = m < nrow && k0 + ch * 2 < nrow;     // nrow is even for every n (n (n + 1) / 2 or n^2 with ... see launcher)
-      cp16(sa + (uint32_t)(m * SG_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m : 0) * nrow + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
+      const bool ok = m < nrow && k0 + ch * 2 < ldg;      // ldg is even; the pad column of an odd nrow holds zeros
+      cp16(sa + (uint32_t)(m * SG_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m : 0) * ldg + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
     }
     // D chunk: 8 rows x 128 doubles = 512 16-byte chunks
     for (int id = threadIdx.x; id < SG_KC * (SG_BN / 2); id += SG_THREADS) {
@@ -277,28 +267,29 @@ sigma_dmma_kernel(const double* __restrict__ Gm, const double* __restrict__ D, d
 }
 
 template <int MT>
-static int launch_sigma_mt(const double* Gm, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
+static int launch_sigma_mt(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
   const size_t smem = sizeof(double) * SG_STAGES * ((size_t)MT * 8 * SG_LDA + SG_KC * SG_LDB);
   static bool attr = false;
   if (!attr) {
     SQ_CUDA(cudaFuncSetAttribute(sigma_dmma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  sigma_dmma_kernel<MT><<<(unsigned)(W / SG_BN), SG_THREADS, smem, st>>>(Gm, D, F, nrow, W);
+  sigma_dmma_kernel<MT><<<(unsigned)(W / SG_BN), SG_THREADS, smem, st>>>(Gm, ldg, D, F, nrow, W);
   return SQ_OK;
 }
 
-// F (nrow x W, row-major, ld W) = Gm (nrow x nrow, row-major) * D (nrow x W, row-major)
-int sq_sigma_gemm(const double* Gm, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
-  if (W % SG_BN != 0 || nrow < 1 || nrow % 2 != 0) {
-    sq_set_error("sigma GEMM: panel width %lld must be a multiple of %d and the row count %d even", (long long)W, SG_BN, nrow);
+// F (nrow x W, row-major, ld W) = Gm (nrow x nrow, row-major with leading dimension ldg: even, pad column zero) * D (nrow x W,
+// row-major)
+int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
+  if (W % SG_BN != 0 || nrow < 1 || ldg % 2 != 0 || ldg < nrow) {
+    sq_set_error("sigma GEMM: panel width %lld must be a multiple of %d and the leading dimension %d even", (long long)W, SG_BN, ldg);
     return SQ_ERR_INVALID;
   }
   const int mt = (nrow + 7) / 8;
   int rc = SQ_ERR_UNSUPPORTED;
   // accumulators: 4 * MT doubles per thread; instantiations cover n <= 16 symmetrised (136 rows) and n <= 11 general (121 rows)
   switch (mt) {
-#define SG_CASE(M) case M: rc = launch_sigma_mt<M>(Gm, D, F, nrow, W, st); break;
+#define SG_CASE(M) case M: rc = launch_sigma_mt<M>(Gm, ldg, D, F, nrow, W, st); break;
     SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8) SG_CASE(9) SG_CASE(10) SG_CASE(11)
     SG_CASE(12) SG_CASE(13) SG_CASE(14) SG_CASE(15) SG_CASE(16) SG_CASE(17)
 #undef SG_CASE
@@ -312,6 +303,36 @@ int sq_sigma_gemm(const double* Gm, const double* D, double* F, int nrow, int64_
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     sq_set_error("sigma_dmma_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// rdm1 without the 2-RDM: g1[row] += sum_t D[row][t] * x[t]   (one CTA per row: fixed summation order, no atomics)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+panel_gemv_kernel(const double* __restrict__ D, int64_t W, const double* __restrict__ x, int64_t K, double* __restrict__ g1) {
+  __shared__ double red[32];
+  const double* row = D + (size_t)blockIdx.x * W;
+  double s = 0.0;
+  for (int64_t t = threadIdx.x; t < K; t += 1024) s += row[t] * x[t];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) g1[blockIdx.x] += v;
+  }
+}
+
+int sq_panel_gemv(const double* D, int64_t W, int nrows, const double* x, int64_t K, double* g1, cudaStream_t st) {
+  panel_gemv_kernel<<<(unsigned)nrows, 1024, 0, st>>>(D, W, x, K, g1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("panel_gemv_kernel launch failed: %s", cudaGetErrorString(e));
     return SQ_ERR_CUDA;
   }
   g_sq_launches.fetch_add(1);

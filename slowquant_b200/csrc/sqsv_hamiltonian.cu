@@ -10,7 +10,6 @@
 // with k_pq = h_pq - 1/2 sum_r g_prrq.  These dense contractions are the only place this engine uses
 // tensor cores (DMMA through the library GEMM); the gather that builds D and the scatter that applies
 // E_pq are HBM/L2-bound integer-address kernels.
-#include <cublas_v2.h>
 
 #include <cmath>
 #include <cstring>
@@ -26,7 +25,9 @@ struct ERec {                 // one spin component of E_pq acting on a determin
 };
 
 struct HamWork {
-  cublasHandle_t blas = nullptr;
+  double* d_gram = nullptr;   // split-K partial sums of the 2-RDM Gram matrix (sqsv_dmma.cu)
+  size_t gram_doubles = 0;
+  int n_sm = 0;
   ERec* d_etab = nullptr;     // [n*n][2]  (alpha, beta)
   std::vector<ERec> h_etab;
   uint32_t* d_tabG = nullptr; // [n*n][NB] beta gather table of the row kernels (build_D_rows_kernel)
@@ -80,11 +81,9 @@ __host__ __device__ __forceinline__ ERec erec_closed(int p, int q, int spin) {
 // sq_set_option("pipeline", "0"): one panel at a time on the caller's stream (the pre-pipeline behaviour, for A/B runs)
 static int g_panel_pipeline = 1;
 void sq_hamiltonian_set_pipeline(int on) { g_panel_pipeline = on ? 1 : 0; }
-// sq_set_option("rdm_tri", "1"): for bra == ket the Gram matrix D D^T is symmetric -- compute the two diagonal half blocks and ONE
-// off-diagonal block (three DGEMMs of n^2/2 x n^2/2 x W: 3/4 of the flops) and mirror the fourth on the host.  Candidate for the
-// next GPU visit (cublasDsyrk was measured 3 x slower than DGEMM here); off by default until it is measured.
-static int g_rdm_tri = 0;
-void sq_hamiltonian_set_rdm_tri(int on) { g_rdm_tri = on ? 1 : 0; }
+// sq_set_option("rdm_tri", ...): kept as an accepted no-op -- the hand-written Gram kernel always computes only the upper-triangular
+// tiles when bra == ket (round 1 measured the three-half-block cuBLAS variant of this at 631 ms against 729 ms at CAS(16,16)).
+void sq_hamiltonian_set_rdm_tri(int) {}
 // sq_set_option("panel", "<determinants>"): panel width of spaces that have not built their panels yet (tests use it to get
 // several panels at small CAS); "0" restores the 1 GiB default
 static int64_t g_panel_width = 0;
@@ -92,7 +91,7 @@ void sq_hamiltonian_set_panel_width(long long w) { g_panel_width = w > 0 ? (int6
 
 static void free_work(HamWork* w) {
   if (!w) return;
-  if (w->blas) cublasDestroy(w->blas);
+  cudaFree(w->d_gram);
   cudaFree(w->d_etab);
   cudaFree(w->d_tabG);
   cudaFree(w->d_tabS);
@@ -136,11 +135,9 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
     g_work[sp] = w;
   }
   const int n = sp->n_orb, n2 = n * n;
-  if (!w->blas) {
-    if (cublasCreate(&w->blas) != CUBLAS_STATUS_SUCCESS) {
-      sq_set_error("cublasCreate failed");
-      return SQ_ERR_CUDA;
-    }
+  if (!w->n_sm) {
+    SQ_CUDA(cudaDeviceGetAttribute(&w->n_sm, cudaDevAttrMultiProcessorCount, sp->device));
+    if (w->n_sm < 1) w->n_sm = 1;
   }
   if (!w->d_etab) {
     std::vector<ERec> tab(2 * (size_t)n2);
@@ -190,7 +187,7 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
       SQ_CUDA(cudaEventCreateWithFlags(&w->ev_scat[b], cudaEventDisableTiming));
     }
   }
-  if (!w->d_small) SQ_CUDA(cudaMalloc(&w->d_small, sizeof(double) * ((size_t)n2 * n2 + 2 * (size_t)n2)));
+  if (!w->d_small) SQ_CUDA(cudaMalloc(&w->d_small, sizeof(double) * ((size_t)n2 * (n2 + 1) + 2 * (size_t)n2)));   // integral matrix with an even leading dimension + k
   if (!w->d_frow) SQ_CUDA(cudaMalloc(&w->d_frow, sizeof(int) * (size_t)n2));
   *out = w;
   return SQ_OK;
@@ -846,32 +843,32 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     }
   const int nS = n * (n + 1) / 2;
   const int nrow = sym ? nS : n2;   // rows of the D and F panels
-  std::vector<double> Gm((size_t)nrow * nrow);
+  const int ldg = (nrow + 1) & ~1;  // even leading dimension of the integral matrix (16-byte rows for the async copies)
+  std::vector<double> Gm((size_t)nrow * ldg, 0.0);
   std::vector<int> frow((size_t)n2);
   if (sym) {
     auto slot = [](int r, int t) { return r >= t ? r * (r + 1) / 2 + t : t * (t + 1) / 2 + r; };
     for (int p = 0; p < n; ++p)
       for (int q = 0; q <= p; ++q)
         for (int r = 0; r < n; ++r)
-          for (int t = 0; t <= r; ++t) Gm[(size_t)slot(p, q) * nS + slot(r, t)] = 0.5 * G(p, q, r, t);
+          for (int t = 0; t <= r; ++t) Gm[(size_t)slot(p, q) * ldg + slot(r, t)] = 0.5 * G(p, q, r, t);
     for (int p = 0; p < n; ++p)
       for (int q = 0; q < n; ++q) frow[(size_t)p * n + q] = slot(p, q);
   } else {
-    for (size_t i = 0; i < Gm.size(); ++i) Gm[i] = 0.5 * g_act_host[i];
+    for (int a = 0; a < n2; ++a)
+      for (int b = 0; b < n2; ++b) Gm[(size_t)a * ldg + b] = 0.5 * g_act_host[(size_t)a * n2 + b];
     for (int i = 0; i < n2; ++i) frow[i] = i;
   }
   double* d_G = w->d_small;
-  double* d_k = w->d_small + (size_t)n2 * n2;
+  double* d_k = w->d_small + (size_t)n2 * (n2 + 1);
   SQ_CUDA(cudaMemcpyAsync(d_G, Gm.data(), sizeof(double) * Gm.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaMemcpyAsync(d_k, k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaMemcpyAsync(w->d_frow, frow.data(), sizeof(int) * frow.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
   SQ_CHECK(sq_launch_scale_copy(sp, e_core, in_dev, out_dev, st));
-  cublasSetStream(w->blas, st);
   const int64_t len = sp->local_len();
   bool use_const = false;
   SQ_CHECK(bind_etab(sp, w, st, &use_const));
-  const double one = 1.0, zero = 0.0;
   // Three-stage pipeline over the panels: while the DGEMM of panel k runs on the tensor cores, the gather of panel k+1
   // and the scatter of panel k-1 (both address-bound) run beside it.  Two D and two F panels are in flight; with
   // pipeline off (or a single panel) all three stages are issued on the caller's stream.
@@ -883,7 +880,6 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_start, 0));
     SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_start, 0));
   }
-  cublasSetStream(w->blas, s_gemm);
   int64_t ip = 0;
   for (int64_t j0 = 0; j0 < len; j0 += w->W, ++ip) {
     const int b = piped ? (int)(ip & 1) : 0;
@@ -896,14 +892,8 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_built[b], 0));
       if (ip >= 2) SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_scat[b], 0));             // F[b] is free once scatter k-2 has read it
     }
-    // F (W x nrow, column major, ld W) = D (W x nrow) * X (nrow x nrow) with X[rs][pq] = Gm[pq][rs] (Gm row-major)
-    cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, nrow, nrow, &one, Dp, (int)w->W,
-                                    d_G, nrow, &zero, Fp, (int)w->W);
-    if (bs != CUBLAS_STATUS_SUCCESS) {
-      sq_set_error("sq_sigma: cublasDgemm failed (%d)", (int)bs);
-      return SQ_ERR_CUDA;
-    }
-    g_sq_launches.fetch_add(1);
+    // F[pq][t] = sum_rs Gm[pq][rs] D[rs][t]: hand-written DMMA kernel (sqsv_dmma.cu)
+    SQ_CHECK(sq_sigma_gemm(d_G, ldg, Dp, Fp, nrow, w->W, s_gemm));
     if (piped) {
       SQ_CUDA(cudaEventRecord(w->ev_gemm[b], s_gemm));
       SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_gemm[b], 0));
@@ -967,16 +957,16 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   double* d_G2 = w->d_small;                       // [n2][n2] row-major [(q,p)][(r,s)]
   double* d_g1 = w->d_small + (size_t)n2 * n2;     // [n2]
   SQ_CUDA(cudaMemsetAsync(w->d_small, 0, sizeof(double) * ((size_t)n2 * n2 + 2 * (size_t)n2), st));
-  cublasSetStream(w->blas, st);
   bool use_const = false;
   SQ_CHECK(bind_etab(sp, w, st, &use_const));
   const int64_t len = sp->local_len();
-  const double one = 1.0;
   const int n_elec = sp->n_alpha + sp->n_beta;
   // With the 2-RDM accumulator at hand, rdm1 needs no pass of its own: sum_r E_rr = N on this space, so
   // <bra|E_pq|ket> = (1/N) sum_r <bra|E_pq E_rr|ket>  (saves one GEMV sweep over every panel).
   const bool rdm1_from_G2 = rdm2_host && n_elec > 0;
-  const bool tri = g_rdm_tri && same && rdm2_host && n2 >= 2;   // symmetric Gram matrix: three of the four half blocks
+  GramTiles tiles;
+  int n_split = 1;
+  if (rdm2_host) SQ_CHECK(sq_gram_begin(n2, same, w->n_sm, &w->d_gram, &w->gram_doubles, &tiles, &n_split, st));
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -985,7 +975,6 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_start, 0));
     SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_start, 0));
   }
-  cublasSetStream(w->blas, s_gemm);
   int64_t k = 0;
   for (int64_t j0 = 0; j0 < len; j0 += w->W, ++k) {
     const int64_t wl = (len - j0 < w->W) ? len - j0 : w->W;
@@ -1002,39 +991,15 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
       SQ_CUDA(cudaEventRecord(w->ev_built[b], s_build));
       SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_built[b], 0));
     }
-    cublasStatus_t bs = CUBLAS_STATUS_SUCCESS;
     if (!rdm1_from_G2) {
-      // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]
-      bs = cublasDgemv(w->blas, CUBLAS_OP_T, (int)wl, n2, &one, Dket, (int)w->W, bra_dev + j0, 1, &one, d_g1, 1);
-      if (bs != CUBLAS_STATUS_SUCCESS) {
-        sq_set_error("sq_rdm12: cublasDgemv failed (%d)", (int)bs);
-        return SQ_ERR_CUDA;
-      }
-      g_sq_launches.fetch_add(1);
+      // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]   (one CTA per row, fixed summation order)
+      SQ_CHECK(sq_panel_gemv(Dket, w->W, n2, bra_dev + j0, wl, d_g1, s_gemm));
     }
     if (rdm2_host) {
-      // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]  ==  column-major C[b][a] = Dket^T Dbra
-      // (cublasDsyrk would do half the flops for bra == ket but runs 3 x slower than DGEMM at n^2 = 256, k = 5e5)
-      if (tri) {
-        // column-major C (ld n2): blocks (rows i0.., cols j0..) = Dket[:, i0..]^T Dbra[:, j0..]; block (hb.., 0..) is skipped
-        const int hb = n2 / 2, rb = n2 - hb;
-        bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, hb, hb, (int)w->W, &one, Dket, (int)w->W, Dbra, (int)w->W, &one, d_G2, n2);
-        if (bs == CUBLAS_STATUS_SUCCESS)
-          bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, hb, rb, (int)w->W, &one, Dket, (int)w->W, Dbra + (size_t)hb * w->W,
-                           (int)w->W, &one, d_G2 + (size_t)hb * n2, n2);
-        if (bs == CUBLAS_STATUS_SUCCESS)
-          bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, rb, rb, (int)w->W, &one, Dket + (size_t)hb * w->W, (int)w->W,
-                           Dbra + (size_t)hb * w->W, (int)w->W, &one, d_G2 + hb + (size_t)hb * n2, n2);
-        g_sq_launches.fetch_add(2);
-      } else {
-        bs = cublasDgemm(w->blas, CUBLAS_OP_T, CUBLAS_OP_N, n2, n2, (int)w->W, &one, Dket, (int)w->W, Dbra, (int)w->W,
-                         &one, d_G2, n2);
-      }
-      if (bs != CUBLAS_STATUS_SUCCESS) {
-        sq_set_error("sq_rdm12: cublasDgemm failed (%d)", (int)bs);
-        return SQ_ERR_CUDA;
-      }
-      g_sq_launches.fetch_add(1);
+      // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]: hand-written DMMA kernel, 128 x 128 output tiles, split-K partial
+      // sums accumulated across the panels in per-(tile, split) slots (sqsv_dmma.cu); for bra == ket only the upper-triangular
+      // tiles are computed (the Gram matrix is symmetric).  The panel is zero-padded beyond the last determinant.
+      SQ_CHECK(sq_gram_panel(Dbra, Dket, w->W, n2, w->W, tiles, n_split, w->d_gram, s_gemm));
     }
     if (piped) SQ_CUDA(cudaEventRecord(w->ev_gemm[b], s_gemm));
   }
@@ -1044,16 +1009,12 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     SQ_CUDA(cudaEventRecord(w->ev_start, s_build));
     SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
   }
+  if (rdm2_host) SQ_CHECK(sq_gram_end(tiles, n_split, w->d_gram, n2, same, d_G2, st));
   std::vector<double> G2h(rdm2_host ? (size_t)n2 * n2 : 0), g1h((size_t)n2);
   SQ_CUDA(cudaMemcpyAsync(g1h.data(), d_g1, sizeof(double) * n2, cudaMemcpyDeviceToHost, st));
   if (rdm2_host)
     SQ_CUDA(cudaMemcpyAsync(G2h.data(), d_G2, sizeof(double) * (size_t)n2 * n2, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(cudaStreamSynchronize(st));
-  if (tri) {   // the skipped block: column-major C[i][j], i >= hb > j, equals C[j][i]; row-major G2h[a][b] holds C[b][a]
-    const int hb = n2 / 2;
-    for (int a = 0; a < hb; ++a)
-      for (int b = hb; b < n2; ++b) G2h[(size_t)a * n2 + b] = G2h[(size_t)b * n2 + a];
-  }
   if (rdm1_from_G2) {
     for (int p = 0; p < n; ++p)
       for (int q = 0; q < n; ++q) {
@@ -1247,30 +1208,30 @@ extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const doubl
     }
   const int nS = n * (n + 1) / 2;
   const int nrow = sym ? nS : n2;   // rows of the D and F panels
-  std::vector<double> Gm((size_t)nrow * nrow);
+  const int ldg = (nrow + 1) & ~1;  // even leading dimension of the integral matrix (16-byte rows for the async copies)
+  std::vector<double> Gm((size_t)nrow * ldg, 0.0);
   std::vector<int> frow((size_t)n2);
   if (sym) {
     auto slot = [](int r, int t) { return r >= t ? r * (r + 1) / 2 + t : t * (t + 1) / 2 + r; };
     for (int p = 0; p < n; ++p)
       for (int q = 0; q <= p; ++q)
         for (int r = 0; r < n; ++r)
-          for (int t = 0; t <= r; ++t) Gm[(size_t)slot(p, q) * nS + slot(r, t)] = 0.5 * G(p, q, r, t);
+          for (int t = 0; t <= r; ++t) Gm[(size_t)slot(p, q) * ldg + slot(r, t)] = 0.5 * G(p, q, r, t);
     for (int p = 0; p < n; ++p)
       for (int q = 0; q < n; ++q) frow[(size_t)p * n + q] = slot(p, q);
   } else {
-    for (size_t i = 0; i < Gm.size(); ++i) Gm[i] = 0.5 * g_act_host[i];
+    for (int a = 0; a < n2; ++a)
+      for (int b = 0; b < n2; ++b) Gm[(size_t)a * ldg + b] = 0.5 * g_act_host[(size_t)a * n2 + b];
     for (int i = 0; i < n2; ++i) frow[i] = i;
   }
   double* d_G = w->d_small;
-  double* d_k = w->d_small + (size_t)n2 * n2;
+  double* d_k = w->d_small + (size_t)n2 * (n2 + 1);
   SQ_CUDA(cudaMemcpyAsync(d_G, Gm.data(), sizeof(double) * Gm.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaMemcpyAsync(d_k, k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaMemcpyAsync(w->d_frow, frow.data(), sizeof(int) * frow.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
-  cublasSetStream(w->blas, st);
   const double* in_dev = pin.p[sp->rank];
   double* out_dev = pout.p[sp->rank];
-  const double one = 1.0, zero = 0.0;
   const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
   allow_smem(scatter_E_peer_kernel, smem);
   for (int64_t j0 = 0; j0 < len; j0 += w->W) {   // one stream: gather -> DGEMM -> scatter per panel
@@ -1282,13 +1243,7 @@ extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const doubl
     } else {
       SQ_CHECK(launch_build_D(sp, w, in_dev, w->d_D[0], j0, st, false, false, &pin));
     }
-    cublasStatus_t bs = cublasDgemm(w->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)w->W, nrow, nrow, &one, w->d_D[0], (int)w->W, d_G, nrow,
-                                    &zero, w->d_F[0], (int)w->W);
-    if (bs != CUBLAS_STATUS_SUCCESS) {
-      sq_set_error("sq_sigma_dist: cublasDgemm failed (%d)", (int)bs);
-      return SQ_ERR_CUDA;
-    }
-    g_sq_launches.fetch_add(1);
+    SQ_CHECK(sq_sigma_gemm(d_G, ldg, w->d_D[0], w->d_F[0], nrow, w->W, st));
     scatter_E_peer_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(pout, in_dev, out_dev, w->d_F[0], d_k, w->d_frow, w->W, j0, len,
                                                                      w->d_etab, n2, sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB,
                                                                      sp->row_begin);

@@ -204,6 +204,19 @@ void sq_hamiltonian_set_etab_alu(int on);          // panel kernels without an E
 void sq_hamiltonian_set_rdm_tri(int on);           // RDMs with bra == ket: three half-size DGEMMs instead of one (default off)
 void sq_hamiltonian_set_etab_mode(int use_const);  // E_pq table in constant (1) or shared (0) memory
 void sq_reshard_set_mode(int lsu);                 // re-shard kernel: 0 bulk-copy engine (default), 1 vector load/store
+// hand-written fp64 tensor-core contractions (sqsv_dmma.cu)
+#define SQ_GRAM_MAXT 40
+struct GramTiles {          // 128 x 128 output tiles of one Gram matrix (upper triangle for bra == ket)
+  int n;
+  int ta[SQ_GRAM_MAXT], tb[SQ_GRAM_MAXT];
+};
+int sq_gram_begin(int nrows, bool symmetric, int n_sm, double** d_partial, size_t* partial_doubles, GramTiles* tiles, int* n_split,
+                  cudaStream_t st);
+int sq_gram_panel(const double* X, const double* Y, int64_t ld, int nrows, int64_t K, const GramTiles& tiles, int n_split,
+                  double* d_partial, cudaStream_t st);
+int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, int nrows, bool symmetric, double* d_G2, cudaStream_t st);
+int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st);
+int sq_panel_gemv(const double* D, int64_t W, int nrows, const double* x, int64_t K, double* g1, cudaStream_t st);
 int sq_ensure_work(sq_space* sp, int which);
 int sq_ensure_partial(sq_space* sp, int64_t n);
 
