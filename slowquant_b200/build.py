@@ -48,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         "-shared", "-Xcompiler", "-fPIC",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
         "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

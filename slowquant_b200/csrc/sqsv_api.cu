@@ -660,6 +660,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
     return SQ_OK;
   }
+  if (strcmp(name, "sgemm_cta") == 0) {   // sigma DMMA kernel: "1" (default) or "2" CTAs of 4 warps per SM
+    sq_sigma_gemm_set_residency(value ? atoi(value) : 1);
+    return SQ_OK;
+  }
   if (strcmp(name, "reshard") == 0) {   // re-shard kernel of sharded vectors: "tma" (default, bulk-copy engine) or "lsu"
     sq_reshard_set_mode(value && strcmp(value, "lsu") == 0);
     return SQ_OK;
@@ -1315,6 +1319,7 @@ extern "C" int sq_ups_apply_list(sq_space* sp, sq_layout* lay, const double* the
 
 static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order, int dagger,
                            double* state_dev, const PeerPtrs* peers, void* stream, int gauge_flags) {
+  SqRange nvtx_range("sq_ups_apply");
   cudaStream_t st = (cudaStream_t)stream;
   SQ_CUDA(cudaSetDevice(sp->device));
   for (int k : order) {
@@ -1414,6 +1419,7 @@ static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_ho
 }
 
 extern "C" int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, double* out_dev, void* stream) {
+  SqRange nvtx_range("sq_grad_action");
   if (!sp || !lay || lay->sp != sp || !in_dev || !out_dev || k < 0 || k >= (int)lay->ops.size()) return SQ_ERR_INVALID;
   if (in_dev == out_dev) {
     sq_set_error("sq_grad_action: in and out must not alias");
@@ -1460,6 +1466,7 @@ extern "C" int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double*
 
 extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                                  double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+  SqRange nvtx_range("sq_ups_grad_sweep");
   if (!sp || !lay || lay->sp != sp || !bra_dev || !ket_dev || !grad_host) return SQ_ERR_INVALID;
   const int P = (int)lay->ops.size();
   if (first < 0 || last > P || first > last) return SQ_ERR_INVALID;
@@ -1677,6 +1684,7 @@ extern "C" int sq_ups_grad_sweep_dist(sq_space* sp, sq_layout* lay, const double
 extern "C" int sq_apply_strings(sq_space* sp, int n_strings, const int32_t* ops_flat, const int32_t* op_offsets,
                                 const double* coeffs, const double* in_dev, double* out_dev, int accumulate,
                                 int skip_outside, void* stream) {
+  SqRange nvtx_range("sq_apply_strings");
   if (!sp || n_strings < 0 || !in_dev || !out_dev || (n_strings > 0 && (!ops_flat || !op_offsets || !coeffs)))
     return SQ_ERR_INVALID;
   if (in_dev == out_dev) {

@@ -11,8 +11,8 @@
 //                      summation order is deterministic (no atomics).  For bra == ket only the upper-triangular tiles run.
 //   sigma_dmma_kernel  F[pq][t] = sum_rs Gm[pq][rs] D[rs][t]    (pq, rs < 136 symmetrised generators, or n^2)
 //                      reference: the two-body part of hamiltonian_0i_0a applied string by string (operators.py:476-529,
-//                      operator_state_algebra.py:596-628).  One CTA = all rows x 128 determinants; the integral matrix
-//                      streams through shared memory in chunks of 8 columns.
+//                      operator_state_algebra.py:596-628).  One CTA (4 warps) = all rows x 64 determinants; the integral matrix
+//                      streams through shared memory in chunks of 16 columns.
 //
 // Fragment layout of mma.m8n8k4.f64 (PTX ISA): A (8x4, row): a0 = A[lane >> 2][lane & 3]; B (4x8, col): b0 = B[lane & 3][lane >> 2];
 // C/D (8x8): c{0,1} = C[lane >> 2][2 * (lane & 3) + {0,1}].
@@ -194,40 +194,47 @@ int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, in
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// sigma: F[m][t] = sum_k Gm[m][k] D[k][t], m, k < nrow (padded to MT * 8 rows in registers), t in a tile of 128 determinants
+// sigma: F[m][t] = sum_k Gm[m][k] D[k][t], m, k < nrow, t in a tile of 64 determinants.
+// "Thin" CTAs: 4 warps = 2 (row halves) x 2 (32 determinants each), ~190 registers per thread, one or two CTAs per SM -- the
+// tensor pipe is saturated by one warp per SM sub-partition, and most of the SM (registers, warp slots, the LSU pipe) stays
+// free for the gather / scatter kernels of the neighbouring panels that run beside it on other streams (sq_sigma's pipeline).
 // ------------------------------------------------------------------------------------------------------------------
-#define SG_BN 128
-#define SG_KC 8
-#define SG_LDA 12           // Gm chunk [m][8] row stride: = 12 (mod 16) -> conflict-free A fragments
-#define SG_LDB 132          // D chunk [8][128] row stride: = 4 (mod 16) -> conflict-free B fragments
+#define SG_BN 64
+#define SG_KC 16
+#define SG_LDA 20           // Gm chunk [m][16] row stride: = 4 (mod 16) -> conflict-free A fragments
+#define SG_LDB 68           // D chunk [16][64] row stride: = 4 (mod 16) -> conflict-free B fragments
 #define SG_STAGES 3
-#define SG_THREADS 256
+#define SG_THREADS 128
 
-template <int MT>            // MT = ceil(nrow / 8) row fragments per warp (17 for the 136 symmetrised generators of n = 16)
-__global__ void __launch_bounds__(SG_THREADS, 1)
+template <int MH>            // MH = row fragments per warp: the two row-halves of a CTA cover 2 * MH * 8 >= nrow rows (9 for 136 rows)
+__global__ void __launch_bounds__(SG_THREADS, 2)
 sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restrict__ D, double* __restrict__ F, int nrow, int64_t W) {
   extern __shared__ __align__(16) double ssm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
   const int64_t t0 = (int64_t)blockIdx.x * SG_BN;
-  const int MP = MT * 8;                                  // padded rows
-  const int stage_d = MP * SG_LDA + SG_KC * SG_LDB;       // doubles per stage
+  const int m0 = blockIdx.y * (2 * MH * 8);               // first output row of this CTA (row tiles of 16 * MH rows)
+  constexpr int MP = 2 * MH * 8;                          // padded rows held in shared memory
+  constexpr int stage_d = MP * SG_LDA + SG_KC * SG_LDB;   // doubles per stage
   const int n_chunks = (nrow + SG_KC - 1) / SG_KC;
-  double acc[MT][2][2];
+  double acc[MH][4][2];
 #pragma unroll
-  for (int i = 0; i < MT; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+  for (int i = 0; i < MH; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ssm);
   auto issue = [&](int c, int slot) {
     const int k0 = c * SG_KC;
     const uint32_t sa = sbase + (uint32_t)(slot * stage_d) * 8u, sb = sa + (uint32_t)(MP * SG_LDA) * 8u;
-    // Gm chunk: MP rows x 8 doubles = MP * 4 16-byte chunks (rows / columns beyond nrow are zero-filled)
-    for (int id = threadIdx.x; id < MP * 4; id += SG_THREADS) {
-      const int m = id >> 2, ch = id & 3;
-      const bool ok = m < nrow && k0 + ch * 2 < ldg;      // ldg is even; the pad column of an odd nrow holds zeros
-      cp16(sa + (uint32_t)(m * SG_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m : 0) * ldg + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
+    // Gm chunk: MP rows x 16 doubles = MP * 8 16-byte chunks (rows / columns beyond the matrix are zero-filled)
+    for (int id = threadIdx.x; id < MP * 8; id += SG_THREADS) {
+      const int m = id >> 3, ch = id & 7;
+      const bool ok = m0 + m < nrow && k0 + ch * 2 < ldg; // ldg is even; the pad column of an odd nrow holds zeros
+      cp16(sa + (uint32_t)(m * SG_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m0 + m : 0) * ldg + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
     }
-    // D chunk: 8 rows x 128 doubles = 512 16-byte chunks
+    // D chunk: 16 rows x 64 doubles = 512 16-byte chunks
     for (int id = threadIdx.x; id < SG_KC * (SG_BN / 2); id += SG_THREADS) {
-      const int k = id >> 6, ch = id & 63;
+      const int k = id >> 5, ch = id & 31;
       const bool ok = k0 + k < nrow;
       cp16(sb + (uint32_t)(k * SG_LDB + ch * 2) * 8u, D + (size_t)(ok ? k0 + k : 0) * W + t0 + ch * 2, ok ? 16 : 0);
     }
@@ -241,40 +248,45 @@ sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restri
     __syncthreads();
     if (it + SG_STAGES - 1 < n_chunks) issue(it + SG_STAGES - 1, (it + SG_STAGES - 1) % SG_STAGES);
     cp_commit();
-    const double* as = ssm + (it % SG_STAGES) * stage_d;
-    const double* bs = as + MP * SG_LDA;
+    const double* as = ssm + (it % SG_STAGES) * stage_d + (wm * MH * 8) * SG_LDA;
+    const double* bs = ssm + (it % SG_STAGES) * stage_d + MP * SG_LDA + wn * 32;
 #pragma unroll
     for (int k4 = 0; k4 < SG_KC / 4; ++k4) {
-      const double b0 = bs[(k4 * 4 + (lane & 3)) * SG_LDB + warp * 16 + (lane >> 2)];
-      const double b1 = bs[(k4 * 4 + (lane & 3)) * SG_LDB + warp * 16 + 8 + (lane >> 2)];
+      double bf[4];
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(k4 * 4 + (lane & 3)) * SG_LDB + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < MH; ++i) {
         const double a = as[(i * 8 + (lane >> 2)) * SG_LDA + k4 * 4 + (lane & 3)];
-        dmma884(acc[i][0][0], acc[i][0][1], a, b0);
-        dmma884(acc[i][1][0], acc[i][1][1], a, b1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a, bf[j]);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < MT; ++i) {
-    const int m = i * 8 + (lane >> 2);
+  for (int i = 0; i < MH; ++i) {
+    const int m = m0 + (wm * MH + i) * 8 + (lane >> 2);
     if (m < nrow) {
-      double* p = F + (size_t)m * W + t0 + warp * 16 + 2 * (lane & 3);
-      *reinterpret_cast<double2*>(p) = make_double2(acc[i][0][0], acc[i][0][1]);
-      *reinterpret_cast<double2*>(p + 8) = make_double2(acc[i][1][0], acc[i][1][1]);
+      double* p = F + (size_t)m * W + t0 + wn * 32 + 2 * (lane & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
   }
 }
 
-template <int MT>
-static int launch_sigma_mt(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st) {
-  const size_t smem = sizeof(double) * SG_STAGES * ((size_t)MT * 8 * SG_LDA + SG_KC * SG_LDB);
-  static bool attr = false;
-  if (!attr) {
-    SQ_CUDA(cudaFuncSetAttribute(sigma_dmma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+static int g_sigma_cta_per_sm = 1;   // sq_set_option("sgemm_cta", "1" | "2"): GEMM CTAs per SM (the rest of the SM runs gathers / scatters)
+void sq_sigma_gemm_set_residency(int n) { g_sigma_cta_per_sm = n >= 2 ? 2 : 1; }
+
+template <int MH>
+static int launch_sigma_mh(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, int m_tiles, cudaStream_t st) {
+  size_t smem = sizeof(double) * SG_STAGES * ((size_t)2 * MH * 8 * SG_LDA + SG_KC * SG_LDB);
+  if (g_sigma_cta_per_sm == 1 && smem < 116 * 1024) smem = 116 * 1024;   // more than half of the SM's shared memory: one CTA per SM
+  static size_t attr = 0;
+  if (smem > attr) {
+    SQ_CUDA(cudaFuncSetAttribute(sigma_dmma_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
-  sigma_dmma_kernel<MT><<<(unsigned)(W / SG_BN), SG_THREADS, smem, st>>>(Gm, ldg, D, F, nrow, W);
+  sigma_dmma_kernel<MH><<<dim3((unsigned)(W / SG_BN), (unsigned)m_tiles), SG_THREADS, smem, st>>>(Gm, ldg, D, F, nrow, W);
   return SQ_OK;
 }
 
@@ -285,18 +297,19 @@ int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nro
     sq_set_error("sigma GEMM: panel width %lld must be a multiple of %d and the leading dimension %d even", (long long)W, SG_BN, ldg);
     return SQ_ERR_INVALID;
   }
-  const int mt = (nrow + 7) / 8;
+  // accumulators: 8 * MH doubles per thread, MH <= 9: up to 144 rows per CTA; more rows (n = 16 with unsymmetric integrals: 256,
+  // n = 20 symmetrised: 210) are split into equal row tiles along gridDim.y
+  const int m_tiles = (nrow + 143) / 144;
+  const int mh = ((nrow + m_tiles - 1) / m_tiles + 15) / 16;
   int rc = SQ_ERR_UNSUPPORTED;
-  // accumulators: 4 * MT doubles per thread; instantiations cover n <= 16 symmetrised (136 rows) and n <= 11 general (121 rows)
-  switch (mt) {
-#define SG_CASE(M) case M: rc = launch_sigma_mt<M>(Gm, ldg, D, F, nrow, W, st); break;
-    SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8) SG_CASE(9) SG_CASE(10) SG_CASE(11)
-    SG_CASE(12) SG_CASE(13) SG_CASE(14) SG_CASE(15) SG_CASE(16) SG_CASE(17)
+  switch (mh) {
+#define SG_CASE(M) case M: rc = launch_sigma_mh<M>(Gm, ldg, D, F, nrow, W, m_tiles, st); break;
+    SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8) SG_CASE(9)
 #undef SG_CASE
     default: break;
   }
   if (rc == SQ_ERR_UNSUPPORTED) {
-    sq_set_error("sigma GEMM: %d generator rows exceed the register-tiled kernel (max 136)", nrow);
+    sq_set_error("sigma GEMM: no kernel instantiation for %d generator rows", nrow);
     return rc;
   }
   SQ_CHECK(rc);

@@ -804,6 +804,7 @@ static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* 
 
 extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, const double* g_act_host,
                         const double* in_dev, double* out_dev, void* stream) {
+  SqRange nvtx_range("sq_sigma");
   if (!sp || !h_act_host || !g_act_host || !in_dev || !out_dev) return SQ_ERR_INVALID;
   if (in_dev == out_dev) {
     sq_set_error("sq_sigma: in and out must not alias");
@@ -948,6 +949,7 @@ extern "C" int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, c
 
 static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev, const PeerView* pv_bra,
                       const PeerView* pv_ket, double* rdm1_host, double* rdm2_host, void* stream) {
+  SqRange nvtx_range("sq_rdm12");
   cudaStream_t st = (cudaStream_t)stream;
   SQ_CUDA(cudaSetDevice(sp->device));
   const bool same = (bra_dev == ket_dev);
@@ -1138,6 +1140,7 @@ scatter_E_peer_kernel(PeerViewRW pvo, const double* __restrict__ IN, double* OUT
 // barrier, every rank calls sq_sigma_dist, stream synchronise, barrier -- then out holds H|in>.
 extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
                              double* const* out_ptrs_host, void* stream) {
+  SqRange nvtx_range("sq_sigma_dist");
   if (!sp || !h_act_host || !g_act_host || !in_ptrs_host || !out_ptrs_host) return SQ_ERR_INVALID;
   if (sp->device < 0) return SQ_ERR_INVALID;
   if (sp->world < 1 || sp->world > SQ_MAX_WORLD || (int)sp->row_starts.size() != sp->world + 1) {

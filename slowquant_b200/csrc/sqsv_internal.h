@@ -15,6 +15,16 @@
 #define SQ_MAX_STRING_OPS 32   // ladder operators per normal-ordered string
 #define SQ_MAX_PROGRAM 8       // fused rotation steps per tile launch
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler is attached
+
+// NVTX range per kernel family / API call (tracing): visible in nsys / ncu --nvtx timelines
+struct SqRange {
+  explicit SqRange(const char* name) { nvtxRangePushA(name); }
+  ~SqRange() { nvtxRangePop(); }
+  SqRange(const SqRange&) = delete;
+  SqRange& operator=(const SqRange&) = delete;
+};
+
 extern std::atomic<int64_t> g_sq_launches;
 void sq_set_error(const char* fmt, ...);
 
@@ -215,6 +225,7 @@ int sq_gram_begin(int nrows, bool symmetric, int n_sm, double** d_partial, size_
 int sq_gram_panel(const double* X, const double* Y, int64_t ld, int nrows, int64_t K, const GramTiles& tiles, int n_split,
                   double* d_partial, cudaStream_t st);
 int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, int nrows, bool symmetric, double* d_G2, cudaStream_t st);
+void sq_sigma_gemm_set_residency(int n);
 int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st);
 int sq_panel_gemv(const double* D, int64_t W, int nrows, const double* x, int64_t K, double* g1, cudaStream_t st);
 int sq_ensure_work(sq_space* sp, int which);

@@ -124,6 +124,7 @@ void sq_reshard_set_mode(int lsu) { g_reshard_mode = lsu ? 1 : 0; }
 // device-wide barrier (all shards complete before / all rows landed after).
 extern "C" int sq_reshard_rows(int device, int64_t n_rows, int64_t NB, const double* src_dev, const int32_t* dst_rank_dev,
                                const int32_t* dst_row_dev, double* const* dst_ptrs_host, int world, void* stream) {
+  SqRange nvtx_range("sq_reshard_rows");
   if (n_rows < 0 || NB < 1 || world < 1 || world > SQ_MAX_WORLD || !dst_ptrs_host) return SQ_ERR_INVALID;
   if (n_rows == 0) return SQ_OK;
   if (!src_dev || !dst_rank_dev || !dst_row_dev) return SQ_ERR_INVALID;

@@ -315,8 +315,11 @@ def test_transition_rdm_against_oracle(sq):
         assert abs(d2[p, q, r, s] - ref) < 1e-12, (p, q, r, s)
 
 
-@pytest.mark.parametrize("n,na,nb", [(6, 3, 3), (7, 4, 2), (8, 4, 4)])
+@pytest.mark.parametrize("n,na,nb", [(6, 3, 3), (7, 4, 2), (8, 4, 4), (13, 2, 1)])
 def test_sigma_against_oracle(sq, n, na, nb):
+    """sigma and <H> against the oracle's string-by-string restatement (osa.py:596-628).  n = 7: no permutational symmetry;
+    n = 13 (unsymmetric, 169 generator rows): more rows than one CTA of the DMMA kernel holds (row tiles along gridDim.y), an odd
+    row count (padded leading dimension); its RDMs use a 2 x 2-tile Gram matrix (upper triangle + mirror)."""
     from slowquant_b200.operators import hamiltonian_0i_0a
 
     rng = np.random.default_rng(n)
@@ -326,7 +329,7 @@ def test_sigma_against_oracle(sq, n, na, nb):
     g = B + B.transpose(1, 0, 2, 3)
     g = g + g.transpose(0, 1, 3, 2)
     g = g + g.transpose(2, 3, 0, 1)
-    if n == 7:  # no permutational symmetry at all: the kernel must not assume any
+    if n in (7, 13):  # no permutational symmetry at all: the kernel must not assume any
         h = rng.normal(size=(n, n))
         g = 0.1 * rng.normal(size=(n, n, n, n))
     sp = orc.get_indexing(0, n, 0, na, nb)
@@ -340,9 +343,18 @@ def test_sigma_against_oracle(sq, n, na, nb):
     e = sq.osa.expectation_value(st, [H], st, info)
     assert abs(e - float(st @ ref)) < 1e-11
     if n != 7:
+        if n == 13:   # symmetric integrals again (91 symmetrised rows): <H> through sigma against <H> through the RDMs
+            h, g = A + A.T, B + B.transpose(1, 0, 2, 3)
+            g = g + g.transpose(0, 1, 3, 2)
+            g = g + g.transpose(2, 3, 0, 1)
+            e = sq.osa.expectation_value(st, [hamiltonian_0i_0a(h, g, 0, n)], st, info)
         d1, d2 = sq.osa.reduced_density_matrices(st, st, info)
         e_rdm = float(np.sum(h * d1) + 0.5 * np.sum(g * d2))
         assert abs(e - e_rdm) < 1e-10
+        other = rng.normal(size=sp.num_det)
+        t1, t2 = sq.osa.reduced_density_matrices(other, st, info)      # transition RDM: all Gram tiles, no mirror
+        assert abs(np.trace(t1) - (na + nb) * float(other @ st)) < 1e-10
+        assert abs(float(np.einsum("ppqq->", t2)) - (na + nb) * (na + nb - 1) * float(other @ st)) < 1e-9
 
 
 def test_wavefunction_object(sq, golden):
