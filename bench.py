@@ -478,6 +478,38 @@ def run_ours(args) -> None:
             e2e["wavefunction_setter"] = {"error": repr(exc)}
         del out, host_in, np_in
 
+    # ---- the same circuit on a resident batch of S vectors in ONE launch sequence (state-averaged wave functions, the common
+    # tail of RotoSolve's shifted states): the window / gauge sweeps carry the state index as a batch dimension ----
+    batched = None
+    if not args.no_extras and world == 1:
+        try:
+            from slowquant_b200.operator_state_algebra import _ups_apply_batch_inplace
+
+            S = 4
+            batch = torch.zeros((S, info.num_det), dtype=torch.float64, device=dev)
+            batch[:, 0] = 1.0
+            _ups_apply_batch_inplace(batch, info, thetas, lay, 0, P, False)   # warm-up
+            torch.cuda.synchronize()
+            l0 = int(lib.sq_launch_count())
+            ev0.record()
+            reps = max(1, min(args.steps, 3))
+            for _ in range(reps):
+                _ups_apply_batch_inplace(batch, info, thetas, lay, 0, P, False)
+            ev1.record()
+            torch.cuda.synchronize()
+            msb = ev0.elapsed_time(ev1)
+            batched = {
+                "value": S * L * reps / (msb * 1e-3),
+                "unit": UNIT,
+                "states_per_call": S,
+                "launches_per_call": (int(lib.sq_launch_count()) - l0) // reps,
+                "api": "sq_ups_apply_batch on a resident [S, N_det] batch (construct_ups_state_SA with a device tensor)",
+                "max_diff_vs_single_state": float(torch.max(torch.abs(batch[S - 1] - batch[0]))),
+            }
+            del batch
+        except Exception as exc:  # an extra, never a gate
+            batched = {"error": repr(exc)}
+
     extras = None
     if not args.no_extras and world == 1:
         try:
@@ -565,6 +597,7 @@ def run_ours(args) -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
             "state_norm": norm,
+            "batched_resident": batched,
             "energy_gradient": extras,
         }
         print(json.dumps(line), flush=True)

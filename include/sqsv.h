@@ -134,6 +134,11 @@ int sq_set_option(const char* name, const char* value);
  * operator; operators with |theta| < 1e-28 are skipped (:998). */
 int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                  int dagger, double* state_dev, void* stream);
+/* The same circuit on a batch of n_states vectors states_dev + s * state_stride (the *_SA twins: construct_ups_state_SA,
+ * :1415-1864; propagate_unitary_SA, :2312-2754; the common tail of RotoSolve's shifted states, ups_wavefunction.py:1183-1187).
+ * Window and gauge sweeps process the whole batch in one launch (tables and work lists staged once per CTA for all states). */
+int sq_ups_apply_batch(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                       double* states_dev, int n_states, int64_t state_stride, void* stream);
 /* The same product over an explicit operator list: layout operators op_list[0..n_list) in the given EXECUTION order (dagger
  * != 0 only negates the angles).  The caller vouches that this order is equivalent to the circuit order, i.e. operators that
  * changed places commute (disjoint orbitals) -- the re-sharding driver runs the part of a circuit that is executable in the

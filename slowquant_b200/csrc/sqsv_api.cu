@@ -660,8 +660,8 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
     return SQ_OK;
   }
-  if (strcmp(name, "sgemm_cta") == 0) {   // sigma DMMA kernel: "1" (default) or "2" CTAs of 4 warps per SM
-    sq_sigma_gemm_set_residency(value ? atoi(value) : 1);
+  if (strcmp(name, "sgemm_cta") == 0) {   // sigma DMMA kernel: "2" (default) or "1" CTAs of 4 warps per SM
+    sq_sigma_gemm_set_residency(value ? atoi(value) : 2);
     return SQ_OK;
   }
   if (strcmp(name, "reshard") == 0) {   // re-shard kernel of sharded vectors: "tma" (default, bulk-copy engine) or "lsu"
@@ -1157,7 +1157,8 @@ static int run_tile(sq_space* sp, sq_layout* lay, const std::vector<int>& run, c
 static int ups_apply_impl(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
                           double* state_dev, const PeerPtrs* peers, void* stream);
 static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order, int dagger,
-                           double* state_dev, const PeerPtrs* peers, void* stream, int gauge_flags);
+                           double* state_dev, const PeerPtrs* peers, void* stream, int gauge_flags, int n_states = 1,
+                           int64_t state_stride = 0);
 
 extern "C" int sq_ups_apply(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
                             double* state_dev, void* stream) {
@@ -1317,8 +1318,31 @@ extern "C" int sq_ups_apply_list(sq_space* sp, sq_layout* lay, const double* the
   return ups_apply_order(sp, lay, thetas_host, order, dagger, state_dev, nullptr, stream, gauge_flags);
 }
 
+// The same circuit on a BATCH of vectors states_dev + s * state_stride, s < n_states (the *_SA twins of the reference,
+// osa.py:1415-1864 / 2312-2754, and the common tail of RotoSolve's shifted states, ups_wavefunction.py:1183-1187): window sweeps
+// and gauge sweeps take the batch as one launch whose CTAs stage their tables once for all states; the other kernels run per state.
+extern "C" int sq_ups_apply_batch(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                                  double* states_dev, int n_states, int64_t state_stride, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !states_dev || n_states < 1 || (n_states > 1 && state_stride < sp->local_len())) {
+    sq_set_error("sq_ups_apply_batch: need n_states >= 1 and a stride of at least the vector length");
+    return SQ_ERR_INVALID;
+  }
+  const int P = (int)lay->ops.size();
+  if (first < 0 || last > P || first > last || (first < last && !thetas_host)) {
+    sq_set_error("sq_ups_apply_batch: bad operator range [%d,%d) for %d operators", first, last, P);
+    return SQ_ERR_INVALID;
+  }
+  if (sp->device < 0) {
+    sq_set_error("sq_ups_apply_batch: host-only space (device = -1) cannot run kernels");
+    return SQ_ERR_INVALID;
+  }
+  std::vector<int> order;
+  exec_order(first, last, dagger, &order);
+  return ups_apply_order(sp, lay, thetas_host, order, dagger, states_dev, nullptr, stream, 0, n_states, state_stride);
+}
+
 static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order, int dagger,
-                           double* state_dev, const PeerPtrs* peers, void* stream, int gauge_flags) {
+                           double* state_dev0, const PeerPtrs* peers, void* stream, int gauge_flags, int n_states, int64_t state_stride) {
   SqRange nvtx_range("sq_ups_apply");
   cudaStream_t st = (cudaStream_t)stream;
   SQ_CUDA(cudaSetDevice(sp->device));
@@ -1364,7 +1388,7 @@ static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_ho
   bool in_gauge = (gauge_flags & 1) != 0;
   for (const Launch& l : launches) {
     if ((l.kind == 2) != in_gauge) {
-      SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
+      SQ_CHECK(sq_launch_gauge(sp, state_dev0, st, n_states, state_stride));
       in_gauge = !in_gauge;
     }
     TimingScope tscope(tev0, tev1, st, &l);
@@ -1384,8 +1408,12 @@ static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_ho
         sptr[nb] = wsteps[nb];
         ++nb;
       }
-      SQ_CHECK(sq_launch_win(sp, *l.wt, pair_idx, sptr, nst, nb, state_dev, st));
-    } else if (l.kind == 1) {
+      SQ_CHECK(sq_launch_win(sp, *l.wt, pair_idx, sptr, nst, nb, state_dev0, st, n_states, state_stride));
+      continue;
+    }
+    for (int si = 0; si < n_states; ++si) {
+    double* const state_dev = state_dev0 + (int64_t)si * state_stride;
+    if (l.kind == 1) {
       // two bricks on disjoint orbital pairs commute: one sweep for both (sqsv_quad.cu)
       const int pA = op.pair, pB = lay->ops[runs[l.runs[1]][0]].pair;
       SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
@@ -1398,7 +1426,7 @@ static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_ho
       SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, &n_steps, step_op));
       SQ_CHECK(sq_launch_tile(sp, lay->pairs[op.pair], steps, n_steps, state_dev, peers, st));
     } else if (op.null_op) {
-      continue;
+      break;
     } else if (op.gen >= 0) {
       const double th = dagger ? -thetas_host[run[0]] : thetas_host[run[0]];
       SQ_CHECK(sq_launch_gen_rot(sp, lay->gens[op.gen], std::cos(th), std::sin(th), state_dev, st));
@@ -1413,8 +1441,9 @@ static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_ho
       sq_set_error("Got unknown excitation type code %d", op.type);
       return SQ_ERR_INVALID;
     }
+    }   // states of the batch
   }
-  if (in_gauge != ((gauge_flags & 2) != 0)) SQ_CHECK(sq_launch_gauge(sp, state_dev, st));
+  if (in_gauge != ((gauge_flags & 2) != 0)) SQ_CHECK(sq_launch_gauge(sp, state_dev0, st, n_states, state_stride));
   return SQ_OK;
 }
 

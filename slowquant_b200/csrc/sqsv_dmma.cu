@@ -274,8 +274,8 @@ sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restri
   }
 }
 
-static int g_sigma_cta_per_sm = 1;   // sq_set_option("sgemm_cta", "1" | "2"): GEMM CTAs per SM (the rest of the SM runs gathers / scatters)
-void sq_sigma_gemm_set_residency(int n) { g_sigma_cta_per_sm = n >= 2 ? 2 : 1; }
+static int g_sigma_cta_per_sm = 2;   // measured at CAS(16,16): sigma 445 ms with two CTAs per SM, 524 ms with one (profiles/r2_visit5_ab_sgemm_cta.txt); sq_set_option("sgemm_cta", "1" | "2"): GEMM CTAs per SM (the rest of the SM runs gathers / scatters)
+void sq_sigma_gemm_set_residency(int n) { g_sigma_cta_per_sm = n == 1 ? 1 : 2; }
 
 template <int MH>
 static int launch_sigma_mh(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, int m_tiles, cudaStream_t st) {

@@ -262,14 +262,14 @@ struct WinTables {
 };
 int sq_win_max_class(int n, int ne, int w0, int H);
 size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int nbuf, int lta, int ltb, int maxQ, int maxS, int n_bricks);
-int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st);
+int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st, int n_states = 1, int64_t state_stride = 0);
 bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H);
 int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** out);
 void sq_free_win_tables(WinTables* wt);
 int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
                        const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, cudaStream_t st);
 int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
-                  int n_bricks, double* state, cudaStream_t st);
+                  int n_bricks, double* state, cudaStream_t st, int n_states = 1, int64_t state_stride = 0);
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                    double* state, const PeerPtrs* peers, cudaStream_t st);
 int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, int n1, int sigma1,

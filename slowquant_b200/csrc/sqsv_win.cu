@@ -107,7 +107,9 @@ __device__ __forceinline__ void sts128(uint32_t a, double2 v) {
 // single entries, BYTE offsets in 16-bit fields].
 template <int NBUF>
 __global__ void __launch_bounds__(WIN_THREADS, NBUF == 2 ? 2 : 3)
-win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_constant__ WinProgram P) {
+win_kernel(double* __restrict__ C0, int64_t NB, const WinDev W, const __grid_constant__ WinProgram P, int n_states, int64_t state_stride) {
+  // n_states vectors C0 + s * state_stride share this CTA's tables and work lists (state-averaged batches, osa.py:1415-1864:
+  // the class tables, batch bases and brick lists are staged ONCE, then every state streams through the same program)
   extern __shared__ double tile[];
   int* const sdB = reinterpret_cast<int*>(tile + NBUF * W.tile_doubles);
   int* const sdA = sdB + W.LTB;
@@ -142,8 +144,10 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
 
   const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(tile);
   // the whole batch is requested at once with 8-byte async copies
-  auto issue_loads = [&](int it) {
-    const uint32_t tb = tb0 + (uint32_t)((it % NBUF) * W.tile_doubles) * 8u;
+  auto issue_loads = [&](int q) {
+    const int it = q % n_items;
+    const double* C = C0 + (int64_t)(q / n_items) * state_stride;
+    const uint32_t tb = tb0 + (uint32_t)((q % NBUF) * W.tile_doubles) * 8u;
     const int kcnt = skcnt[it];
     const int* sb = sbase + it * WIN_G;
     if (W.lanes_j) {
@@ -203,12 +207,15 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
   // 8 lanes x 2 tiles per work-list entry (32 entries in flight per CTA); every shared-memory access moves 16 bytes
   const int g2 = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
-  for (int it = 0; it < n_items; ++it) {
+  const int n_total = n_items * n_states;
+  for (int q = 0; q < n_total; ++q) {
+    const int it = q % n_items;
+    double* const C = C0 + (int64_t)(q / n_items) * state_stride;
     const int kcnt = skcnt[it];
-    const uint32_t tb = tb0 + (uint32_t)((it % NBUF) * W.tile_doubles) * 8u;
+    const uint32_t tb = tb0 + (uint32_t)((q % NBUF) * W.tile_doubles) * 8u;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();   // batch `it` has landed; every thread is done with the stores of batch it - 1
-    if (NBUF == 2 && it + 1 < n_items) issue_loads(it + 1);   // into the other buffer, in flight during the bricks
+    __syncthreads();   // batch `q` has landed; every thread is done with the stores of batch q - 1
+    if (NBUF == 2 && q + 1 < n_total) issue_loads(q + 1);   // into the other buffer, in flight during the bricks
 
     // ---- bricks ----
     const bool on = 2 * g2 < kcnt;   // an odd batch computes one unused tile along (its lanes are never stored to memory)
@@ -270,7 +277,7 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
 
     // ---- store ----
     const int* sb = sbase + it * WIN_G;
-    const double* tbuf = tile + (it % NBUF) * W.tile_doubles;
+    const double* tbuf = tile + (q % NBUF) * W.tile_doubles;
     if (W.lanes_j) {
       const int NX = kcnt * Wn;
       const float invW = 1.0f / (float)Wn;
@@ -291,9 +298,9 @@ win_kernel(double* __restrict__ C, int64_t NB, const WinDev W, const __grid_cons
         for (int j = lane >> 4; j < Wn; j += 2) stg_stream(dst + sdB[j], srct[j * GP]);
       }
     }
-    if (NBUF == 1 && it + 1 < n_items) {
+    if (NBUF == 1 && q + 1 < n_total) {
       __syncthreads();   // the single buffer is free again
-      issue_loads(it + 1);
+      issue_loads(q + 1);
     }
   }
 }
@@ -537,9 +544,10 @@ win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, 
 // x[Ia][Ib] *= D(A,B) = (-1)^{popc(A & gword(B))}: into / out of the sign-free gauge (its own inverse)
 __global__ void __launch_bounds__(256)
 gauge_kernel(double* __restrict__ C, int64_t NB, int64_t n_rows, int64_t row_begin, const uint32_t* __restrict__ strA,
-             const uint32_t* __restrict__ gwordB) {
+             const uint32_t* __restrict__ gwordB, int64_t state_stride) {
   const int64_t ib = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (ib >= NB) return;
+  C += (int64_t)blockIdx.z * state_stride;   // one vector of a batch per grid plane
   const uint32_t gw = __ldg(gwordB + ib);
   const int64_t r0 = (int64_t)blockIdx.y * 32, r1 = min(r0 + 32, n_rows);
   for (int64_t r = r0; r < r1; ++r) {
@@ -962,7 +970,7 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
 
 // bricks[k] = (layout pair index, rotation steps of the fused program); every pair must be usable in `wt`
 int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
-                  int n_bricks, double* state, cudaStream_t st) {
+                  int n_bricks, double* state, cudaStream_t st, int n_states, int64_t state_stride) {
   if (!wt.ok || n_bricks < 1 || n_bricks > SQ_WIN_MAX_BRICKS) {
     sq_set_error("window launch with %d bricks (max %d) or without tables", n_bricks, SQ_WIN_MAX_BRICKS);
     return SQ_ERR_INVALID;
@@ -1000,8 +1008,8 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
     if (e == cudaSuccess) attr[wt.nbuf] = smem;
   }
   if (e == cudaSuccess) {
-    if (wt.nbuf == 2) win_kernel<2><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P);
-    else win_kernel<1><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P);
+    if (wt.nbuf == 2) win_kernel<2><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, n_states, state_stride);
+    else win_kernel<1><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, n_states, state_stride);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
@@ -1072,7 +1080,7 @@ int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, c
 }
 
 // Multiply the local vector by the sign-free gauge D (an involution).  The beta gauge words live on the space.
-int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st) {
+int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st, int n_states, int64_t state_stride) {
   if (!sp->d_gwordB) {
     std::vector<uint32_t> gw((size_t)sp->NB);
     for (int64_t I = 0; I < sp->NB; ++I) gw[I] = gauge_beta_word(sp->strB[I]);
@@ -1081,8 +1089,8 @@ int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st) {
   }
   const int64_t n_rows = sp->row_end - sp->row_begin;
   if (n_rows == 0) return SQ_OK;
-  const dim3 grid((unsigned)((sp->NB + 255) / 256), (unsigned)((n_rows + 31) / 32));
-  gauge_kernel<<<grid, 256, 0, st>>>(state, sp->NB, n_rows, sp->row_begin, sp->d_strA, sp->d_gwordB);
+  const dim3 grid((unsigned)((sp->NB + 255) / 256), (unsigned)((n_rows + 31) / 32), (unsigned)n_states);
+  gauge_kernel<<<grid, 256, 0, st>>>(state, sp->NB, n_rows, sp->row_begin, sp->d_strA, sp->d_gwordB, state_stride);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     sq_set_error("gauge_kernel launch failed: %s", cudaGetErrorString(e));

@@ -243,6 +243,22 @@ def _ups_apply_inplace(
     )
 
 
+def _ups_apply_batch_inplace(
+    states: torch.Tensor, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, first: int, last: int, dagger: bool
+) -> None:
+    """The same operators [first, last) on every row of a contiguous device batch ``[S, N_det]`` in ONE launch sequence
+    (``sq_ups_apply_batch``: the window / gauge sweeps carry the state index as a batch dimension)."""
+    if states.dim() != 2 or not states.is_contiguous() or states.shape[1] != ci_info.local_len:
+        raise ValueError("batched application needs a contiguous [S, N_det] device tensor")
+    lib = _lib.load()
+    lay = compile_layout(ci_info, ups_struct)
+    th = _thetas_array(thetas, len(ups_struct.excitation_operator_type))
+    _lib.check(
+        lib.sq_ups_apply_batch(ci_info._handle, lay, th.ctypes.data_as(_PD), first, last, 1 if dagger else 0, _ptr(states),
+                               int(states.shape[0]), int(states.shape[1]), _stream())
+    )
+
+
 # ---- public surface -----------------------------------------------------------------------------
 def construct_ups_state(state, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, dagger: bool = False):
     r"""Apply the unitary product :math:`U_N \dots U_0` (or its adjoint) to `state` (osa.py:963-1412)."""
@@ -586,9 +602,13 @@ def _pipelined_host_batch(states, ci_info: CI_Info, run_inplace) -> np.ndarray:
 
 def construct_ups_state_SA(state, ci_info, thetas, ups_struct, dagger=False):
     """Batch twin of construct_ups_state (osa.py:1415-1864); host batches are stream-pipelined."""
+    n = len(ups_struct.excitation_operator_type)
     if not isinstance(state, torch.Tensor) and len(state) > 1:
-        n = len(ups_struct.excitation_operator_type)
         return _pipelined_host_batch(state, ci_info, lambda t: _ups_apply_inplace(t, ci_info, thetas, ups_struct, 0, n, dagger))
+    if isinstance(state, torch.Tensor) and state.is_cuda and state.dim() == 2 and not _is_extended(ci_info):
+        out = state.to(torch.float64).contiguous().clone()      # a fresh [S, N_det] batch; the input is not modified
+        _ups_apply_batch_inplace(out, ci_info, thetas, ups_struct, 0, n, dagger)
+        return out
     return _map_states(lambda s: construct_ups_state(s, ci_info, thetas, ups_struct, dagger), state)
 
 
@@ -599,6 +619,10 @@ def propagate_unitary_SA(state, idx, ci_info, thetas, ups_struct):
         raise IndexError(f"unitary index {idx} out of range for {n} operators")
     if not isinstance(state, torch.Tensor) and len(state) > 1:
         return _pipelined_host_batch(state, ci_info, lambda t: _ups_apply_inplace(t, ci_info, thetas, ups_struct, idx, idx + 1, False))
+    if isinstance(state, torch.Tensor) and state.is_cuda and state.dim() == 2 and not _is_extended(ci_info):
+        out = state.to(torch.float64).contiguous().clone()
+        _ups_apply_batch_inplace(out, ci_info, thetas, ups_struct, idx, idx + 1, False)
+        return out
     return _map_states(lambda s: propagate_unitary(s, idx, ci_info, thetas, ups_struct), state)
 
 

@@ -256,12 +256,15 @@ class WaveFunctionSAUPS(WaveFunctionUPS):
             prefix = self._csf_dev[s].clone()
             if theta_idx > 0:
                 osa._ups_apply_inplace(prefix, self.ci_info, th, self.ups_layout, 0, theta_idx, False)
+            kets = prefix.unsqueeze(0).repeat(len(theta_diffs), 1).contiguous()
             for j, shift in enumerate(theta_diffs):
                 th_s = th.copy()
                 th_s[theta_idx] = shift
-                ket = prefix.clone()
-                osa._ups_apply_inplace(ket, self.ci_info, th_s, self.ups_layout, theta_idx, n, False)
-                energies[j] += osa._dot(osa.propagate_state([H], ket, self.ci_info), ket, self.ci_info)
+                osa._ups_apply_inplace(kets[j], self.ci_info, th_s, self.ups_layout, theta_idx, theta_idx + 1, False)
+            if theta_idx + 1 < n:   # common tail of all shifted states: one batched launch sequence
+                osa._ups_apply_batch_inplace(kets, self.ci_info, th, self.ups_layout, theta_idx + 1, n, False)
+            for j in range(len(theta_diffs)):
+                energies[j] += osa._dot(osa.propagate_state([H], kets[j], self.ci_info), kets[j], self.ci_info)
         self.num_energy_evals += self.num_states
         return energies
 

@@ -552,8 +552,8 @@ class WaveFunctionUPS:
         """Energies at all shifted values of theta[theta_idx] (ups_wavefunction.py:1144-1194), device resident.
 
         The reference propagates operator by operator through its `_SA` kernels; here the prefix
-        U_{idx-1}..U_0|CSF> is built once, and every shift is one single-unitary launch plus ONE fused
-        sq_ups_apply over the whole remaining operator range (window sweeps), a sigma build and a dot.
+        U_{idx-1}..U_0|CSF> is built once, every shift is one single-unitary launch, and the remaining operator range
+        runs once for the whole batch of shifted states (sq_ups_apply_batch), followed by a sigma build and a dot per state.
         """
         th = np.asarray(parameters, dtype=np.float64).copy()
         n = len(th)
@@ -561,13 +561,18 @@ class WaveFunctionUPS:
         if theta_idx > 0:
             osa._ups_apply_inplace(prefix, self.ci_info, th, self.ups_layout, 0, theta_idx, False)
         H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
-        energies = []
-        for shift in theta_diffs:
+        # the shifted operator is applied per shift; the remaining operators are the same for every shifted state, so the whole
+        # [n_shifts, N_det] batch goes through ONE launch sequence (the reference batches them through its _SA kernels, :1183-1187)
+        kets = prefix.unsqueeze(0).repeat(len(theta_diffs), 1).contiguous()
+        for j, shift in enumerate(theta_diffs):
             th_s = th.copy()
             th_s[theta_idx] = shift
-            ket = prefix.clone()
-            osa._ups_apply_inplace(ket, self.ci_info, th_s, self.ups_layout, theta_idx, n, False)
-            Hket = osa.propagate_state([H], ket, self.ci_info)
-            energies.append(osa._dot(Hket, ket, self.ci_info))
+            osa._ups_apply_inplace(kets[j], self.ci_info, th_s, self.ups_layout, theta_idx, theta_idx + 1, False)
+        if theta_idx + 1 < n:
+            osa._ups_apply_batch_inplace(kets, self.ci_info, th, self.ups_layout, theta_idx + 1, n, False)
+        energies = []
+        for j in range(len(theta_diffs)):
+            Hket = osa.propagate_state([H], kets[j], self.ci_info)
+            energies.append(osa._dot(Hket, kets[j], self.ci_info))
         self.num_energy_evals += len(energies)
         return energies

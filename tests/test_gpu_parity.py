@@ -653,7 +653,8 @@ def test_window_gradient_sweep(sq, n, na, nb, L, qnp):
 
 def test_state_averaged_twins(sq):
     """`_SA` batch functions (osa.py:633-781, 827-867, 1415-1864, 2312-2976) on [n_states, N_det] batches: host batches
-    take the stream-pipelined path, device batches the per-state path; both against the oracle state by state."""
+    take the stream-pipelined path, device batches ONE launch sequence with the state index as a batch dimension of the window
+    and gauge sweeps (sq_ups_apply_batch); both against the oracle state by state."""
     n, na, nb = 8, 4, 4
     info = sq.ci.get_indexing(0, n, 0, na, nb)
     sp = orc.get_indexing(0, n, 0, na, nb)
@@ -669,8 +670,20 @@ def test_state_averaged_twins(sq):
     out = sq.osa.construct_ups_state_SA(states, info, th.tolist(), lay)
     assert out.shape == ref.shape and np.max(np.abs(out - ref)) < TOL
     assert np.array_equal(states, keep), "inputs must not be modified"
-    out_dev = sq.osa.construct_ups_state_SA(torch.from_numpy(states).cuda(), info, th.tolist(), lay)
+    dev_in = torch.from_numpy(states).cuda()
+    lib = sq.lib.load()
+    before = lib.sq_launch_count()
+    out_dev = sq.osa.construct_ups_state_SA(dev_in, info, th.tolist(), lay)
+    batched_launches = lib.sq_launch_count() - before
     assert isinstance(out_dev, torch.Tensor) and np.max(np.abs(out_dev.cpu().numpy() - ref)) < TOL
+    assert torch.equal(dev_in.cpu(), torch.from_numpy(keep)), "device inputs must not be modified"
+    before = lib.sq_launch_count()
+    single = sq.osa.construct_ups_state(dev_in[2], info, th.tolist(), lay)
+    single_launches = lib.sq_launch_count() - before
+    assert torch.equal(single, out_dev[2]), "a batched state must be bit-identical to the single-state call"
+    assert batched_launches == single_launches, "the batch must ride in the launches of one state (batch dimension inside the kernels)"
+    u_dev = sq.osa.propagate_unitary_SA(dev_in, 4, info, th.tolist(), lay)
+    assert u_dev.is_cuda and u_dev.shape == dev_in.shape
     back = sq.osa.construct_ups_state_SA(out, info, th.tolist(), lay, dagger=True)
     assert np.max(np.abs(back - states)) < TOL
     one = sq.osa.construct_ups_state_SA(states[:1], info, th.tolist(), lay)
@@ -678,6 +691,7 @@ def test_state_averaged_twins(sq):
     k = 4
     ref_u = np.array([orc.propagate_unitary(s, k, sp, th, lay.excitation_operator_type, lay.excitation_indices) for s in states])
     assert np.max(np.abs(sq.osa.propagate_unitary_SA(states, k, info, th.tolist(), lay) - ref_u)) < TOL
+    assert np.max(np.abs(u_dev.cpu().numpy() - ref_u)) < TOL
     ref_g = np.array([orc.get_grad_action(s, k, sp, lay.excitation_operator_type, lay.excitation_indices) for s in states])
     assert np.max(np.abs(sq.osa.get_grad_action_SA(states, k, info, lay) - ref_g)) < TOL
     from slowquant_b200 import operators as mops
