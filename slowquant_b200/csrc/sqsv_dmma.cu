@@ -21,17 +21,6 @@
 
 #include "sqsv_internal.h"
 
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int src_bytes) {
-  // 16-byte async copy; src_bytes = 0 zero-fills the destination (rows / columns beyond the matrix)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // ------------------------------------------------------------------------------------------------------------------
 // Gram matrix: 128 x 128 tile of G2 per CTA, K range [k_begin, k_end) of the panel (multiples of GR_KC).
 // ------------------------------------------------------------------------------------------------------------------

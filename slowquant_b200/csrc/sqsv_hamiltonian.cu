@@ -773,6 +773,214 @@ static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D,
   return launch_error("build_D_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fused sigma kernel: gather -> DMMA -> scatter for a tile of 64 determinants, without the HBM round trips of the D and F
+// panels (round 1: three kernels per panel, D and F written to and read from 1 GiB buffers).  Per tile:
+//   A  every thread gathers its share of D[rs][t] = <J_t|E_rs (+ E_sr)|in> straight into shared memory (table-free E records);
+//   B  F = Gm . D on the fp64 tensor cores (mma.sync m8n8k4, 4 x 2 warps, accumulators in registers), the integral matrix
+//      streams through shared memory in double-buffered chunks of 8 columns (cp.async, it lives in L2);
+//   C  the accumulators replace the D tile in shared memory and every thread scatters its share:
+//      out[E_pq J_t] += sign (F[pq][t] + k_pq in[J_t]).
+// Two CTAs per SM: while one is in phase B (tensor pipe) the other gathers or scatters (LSU pipe).  Same arithmetic as
+// build_Dsym_kernel / sigma_dmma_kernel / scatter_E_kernel, which remain for spaces with more than 160 generator rows, for
+// alpha-sharded vectors and as the A/B reference (sq_set_option("sigma_fused", "0")).
+// ---------------------------------------------------------------------------------------------------------------------------
+#define SF_BN 64
+#define SF_LDB 68            // D / F tile row stride (doubles): = 4 (mod 16) -> conflict-free B fragments
+#define SF_KC 8
+#define SF_LDA 12            // Gm chunk [m][8] row stride: = 12 (mod 16) -> conflict-free A fragments
+#define SF_THREADS 256
+
+template <int MQ, bool SYM>   // MQ = row fragments per warp: 4 warps x MQ x 8 >= nrow generator rows
+__global__ void __launch_bounds__(SF_THREADS, 2)
+sigma_fused_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ Gm, int ldg, int nrow,
+                   const double* __restrict__ kmat, const int* __restrict__ frow, int n, int64_t len, int64_t n_tiles,
+                   const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                   const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  extern __shared__ __align__(16) double fsm[];
+  constexpr int MP = 4 * MQ * 8;                                  // padded generator rows of the A chunks
+  const int krows = (nrow + 7) & ~7;                              // rows of the D tile (k index), zero-padded
+  double* const Ds = fsm;                                         // [krows][SF_LDB]   (D, later F)
+  double* const As = Ds + (size_t)krows * SF_LDB;                 // 2 stages of [MP][SF_LDA]
+  double* const ks = As + 2 * MP * SF_LDA;                        // [n * n]
+  int* const frs = reinterpret_cast<int*>(ks + n * n);            // [n * n]
+  short2* const slotrq = reinterpret_cast<short2*>(frs + n * n);  // [nrow] (r, q) of every D row
+  const int n2 = n * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int t = threadIdx.x & (SF_BN - 1), part = threadIdx.x >> 6;   // gather / scatter: determinant t of the tile, quarter of the rows
+  for (int i = threadIdx.x; i < n2; i += SF_THREADS) {
+    ks[i] = __ldg(kmat + i);
+    frs[i] = __ldg(frow + i);
+  }
+  if (SYM) {
+    for (int r = 0, s = 0; r < n; ++r)
+      for (int q = 0; q <= r; ++q, ++s)
+        if (s % SF_THREADS == (int)threadIdx.x) slotrq[s] = make_short2((short)r, (short)q);
+  } else {
+    for (int s = threadIdx.x; s < n2; s += SF_THREADS) slotrq[s] = make_short2((short)(s / n), (short)(s % n));
+  }
+  const uint32_t abase = (uint32_t)__cvta_generic_to_shared(As);
+  const int n_chunks = (nrow + SF_KC - 1) / SF_KC;
+  auto issue_A = [&](int c, int slot) {
+    const int k0 = c * SF_KC;
+    const uint32_t sa = abase + (uint32_t)(slot * MP * SF_LDA) * 8u;
+    for (int id = threadIdx.x; id < MP * 4; id += SF_THREADS) {
+      const int m = id >> 2, ch = id & 3;
+      const bool ok = m < nrow && k0 + ch * 2 < ldg;
+      cp16(sa + (uint32_t)(m * SF_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m : 0) * ldg + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
+    }
+  };
+  __syncthreads();
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t j = tile * SF_BN + t;
+    const bool live = j < len;
+    int64_t ia_loc = 0, ib = 0;
+    uint32_t a = 0, b = 0;
+    if (live) {
+      ia_loc = j / NB;
+      ib = j - ia_loc * NB;
+      a = __ldg(strA + row_begin + ia_loc);
+      b = __ldg(strB + ib);
+    }
+    issue_A(0, 0);            // the first integral chunk arrives while the gathers run
+    cp_commit();
+    // ---- phase A: D tile ----
+    auto elem = [&](int p, int q) -> double {   // <J|E_pq|in>, gather form (build_D_alu_kernel)
+      double v = 0.0;
+      const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+      if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+        const uint32_t sa = a ^ ra.flip;
+        const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+        const double x = IN[((int64_t)__ldg(rankA + sa) - row_begin) * NB + ib];
+        v += (par ? -ra.s0 : ra.s0) * x;
+      }
+      if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+        const uint32_t sb = b ^ rb.flip;
+        const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+        const double x = IN[ia_loc * NB + __ldg(rankB + sb)];
+        v += (par ? -rb.s0 : rb.s0) * x;
+      }
+      return v;
+    };
+    for (int s = part; s < krows; s += 4) {
+      double v = 0.0;
+      if (live && s < nrow) {
+        const short2 rq = slotrq[s];
+        v = (SYM && rq.x != rq.y) ? elem(rq.x, rq.y) + elem(rq.y, rq.x) : elem(rq.x, rq.y);
+      }
+      Ds[s * SF_LDB + t] = v;
+    }
+    const double cj = live ? IN[j] : 0.0;
+    __syncthreads();
+    // ---- phase B: F = Gm . D ----
+    double acc[MQ][4][2];
+#pragma unroll
+    for (int i = 0; i < MQ; ++i)
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+    for (int it = 0; it < n_chunks; ++it) {
+      cp_wait<0>();
+      __syncthreads();                                   // chunk `it` has landed; the other stage is free
+      if (it + 1 < n_chunks) issue_A(it + 1, (it + 1) & 1);
+      cp_commit();
+      const double* as = As + (it & 1) * MP * SF_LDA + (wm * MQ * 8) * SF_LDA;
+      const double* bs = Ds + (size_t)(it * SF_KC) * SF_LDB + wn * 32;
+#pragma unroll
+      for (int k4 = 0; k4 < SF_KC / 4; ++k4) {
+        double bf[4];
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) bf[jn] = bs[(k4 * 4 + (lane & 3)) * SF_LDB + jn * 8 + (lane >> 2)];
+#pragma unroll
+        for (int i = 0; i < MQ; ++i) {
+          const double av = as[(i * 8 + (lane >> 2)) * SF_LDA + k4 * 4 + (lane & 3)];
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], av, bf[jn]);
+        }
+      }
+    }
+    __syncthreads();                                     // every warp is done reading the D tile
+    // ---- phase C: F tile into shared memory, scatter ----
+#pragma unroll
+    for (int i = 0; i < MQ; ++i) {
+      const int m = (wm * MQ + i) * 8 + (lane >> 2);
+      if (m < nrow) {
+        double* p = Ds + (size_t)m * SF_LDB + wn * 32 + 2 * (lane & 3);
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) *reinterpret_cast<double2*>(p + jn * 8) = make_double2(acc[i][jn][0], acc[i][jn][1]);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      double diag = 0.0;
+      for (int slot = part; slot < n2; slot += 4) {
+        const int p = slot / n, q = slot - p * n;
+        const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+        const bool va = (a & ra.occ) == ra.occ && (a & ra.emp) == 0u;
+        const bool vb = (b & rb.occ) == rb.occ && (b & rb.emp) == 0u;
+        if (!va && !vb) continue;
+        const double val = Ds[(size_t)frs[slot] * SF_LDB + t] + ks[slot] * cj;
+        if (va) {
+          const int par = (__popc(a & ra.parS) + __popc(b & ra.parO)) & 1;
+          const double sv = (par ? -ra.s0 : ra.s0) * val;
+          if (ra.flip == 0u) diag += sv;
+          else atomicAdd(OUT + ((int64_t)__ldg(rankA + (a ^ ra.flip)) - row_begin) * NB + ib, sv);
+        }
+        if (vb) {
+          const int par = (__popc(b & rb.parS) + __popc(a & rb.parO)) & 1;
+          const double sv = (par ? -rb.s0 : rb.s0) * val;
+          if (rb.flip == 0u) diag += sv;
+          else atomicAdd(OUT + ia_loc * NB + __ldg(rankB + (b ^ rb.flip)), sv);
+        }
+      }
+      atomicAdd(OUT + j, diag);
+    }
+    __syncthreads();                                     // the tile buffer is rewritten by the next tile's gathers
+  }
+}
+
+static int g_sigma_fused = 1;   // sq_set_option("sigma_fused", "0"): the three-kernel panel pipeline instead
+void sq_hamiltonian_set_sigma_fused(int on) { g_sigma_fused = on ? 1 : 0; }
+
+static size_t sigma_fused_smem(int mq, int nrow, int n) {
+  const int krows = (nrow + 7) & ~7, n2 = n * n;
+  return sizeof(double) * ((size_t)krows * SF_LDB + 2 * (size_t)(4 * mq * 8) * SF_LDA + n2) + sizeof(int) * n2 + sizeof(short2) * (size_t)(n2 > nrow ? n2 : nrow) + 16;
+}
+
+template <int MQ, bool SYM>
+static int launch_sigma_fused_t(sq_space* sp, const double* in, double* out, const double* d_G, int ldg, int nrow, const double* d_k,
+                                const int* d_frow, int n_sm, cudaStream_t st) {
+  const int n = sp->n_orb;
+  const size_t smem = sigma_fused_smem(MQ, nrow, n);
+  static size_t attr = 0;
+  if (smem > attr) {
+    SQ_CUDA(cudaFuncSetAttribute(sigma_fused_kernel<MQ, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int64_t len = sp->local_len(), n_tiles = (len + SF_BN - 1) / SF_BN;
+  const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)2 * n_sm * 4);   // persistent CTAs, a few waves for load balance
+  sigma_fused_kernel<MQ, SYM><<<(unsigned)grid, SF_THREADS, smem, st>>>(in, out, d_G, ldg, nrow, d_k, d_frow, n, len, n_tiles, sp->d_strA,
+                                                                       sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);
+  return launch_error("sigma_fused_kernel");
+}
+
+// returns SQ_ERR_UNSUPPORTED (without an error message) when the fused kernel does not cover this shape
+static int launch_sigma_fused(sq_space* sp, const double* in, double* out, const double* d_G, int ldg, int nrow, bool sym,
+                              const double* d_k, const int* d_frow, int n_sm, cudaStream_t st) {
+  const int mq = (nrow + 31) / 32;
+  if (mq < 1 || mq > 5 || sigma_fused_smem(mq, nrow, sp->n_orb) > 110 * 1024) return SQ_ERR_UNSUPPORTED;
+#define SF_CASE(M)                                                                                                     \
+  case M:                                                                                                              \
+    return sym ? launch_sigma_fused_t<M, true>(sp, in, out, d_G, ldg, nrow, d_k, d_frow, n_sm, st)                     \
+               : launch_sigma_fused_t<M, false>(sp, in, out, d_G, ldg, nrow, d_k, d_frow, n_sm, st);
+  switch (mq) {
+    SF_CASE(1) SF_CASE(2) SF_CASE(3) SF_CASE(4) SF_CASE(5)
+    default: break;
+  }
+#undef SF_CASE
+  return SQ_ERR_UNSUPPORTED;
+}
+
 static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* out, const double* F, const double* d_k,
                             int64_t j0, cudaStream_t st, bool use_const) {
   const int n2 = sp->n_orb * sp->n_orb;
@@ -868,6 +1076,10 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   SQ_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
   SQ_CHECK(sq_launch_scale_copy(sp, e_core, in_dev, out_dev, st));
   const int64_t len = sp->local_len();
+  if (g_sigma_fused) {   // one fused gather -> DMMA -> scatter kernel, no D / F panels in HBM
+    const int rc = launch_sigma_fused(sp, in_dev, out_dev, d_G, ldg, nrow, sym, d_k, w->d_frow, w->n_sm, st);
+    if (rc != SQ_ERR_UNSUPPORTED) return rc;
+  }
   bool use_const = false;
   SQ_CHECK(bind_etab(sp, w, st, &use_const));
   // Three-stage pipeline over the panels: while the DGEMM of panel k runs on the tensor cores, the gather of panel k+1

@@ -211,9 +211,26 @@ void sq_hamiltonian_set_rows_cfg(int threads, int ch);  // CTA size / column chu
 void sq_hamiltonian_set_rows_mode(int on);         // row-per-CTA panel kernels (default on) or determinant-per-thread
 void sq_hamiltonian_set_pipeline(int on);          // sigma / RDM panel pipeline over internal streams (default on)
 void sq_hamiltonian_set_etab_alu(int on);          // panel kernels without an E_pq table (records computed from (p,q); default off)
-void sq_hamiltonian_set_rdm_tri(int on);           // RDMs with bra == ket: three half-size DGEMMs instead of one (default off)
+void sq_hamiltonian_set_rdm_tri(int on);
+void sq_hamiltonian_set_sigma_fused(int on);       // sigma through the fused gather -> DMMA -> scatter kernel (default on)           // RDMs with bra == ket: three half-size DGEMMs instead of one (default off)
 void sq_hamiltonian_set_etab_mode(int use_const);  // E_pq table in constant (1) or shared (0) memory
 void sq_reshard_set_mode(int lsu);                 // re-shard kernel: 0 bulk-copy engine (default), 1 vector load/store
+#ifdef __CUDACC__
+// fp64 tensor-core MMA and async-copy primitives shared by sqsv_dmma.cu and the fused sigma kernel (sqsv_hamiltonian.cu).
+// Fragment layout of mma.m8n8k4.f64: A (8x4, row): a0 = A[lane >> 2][lane & 3]; B (4x8, col): b0 = B[lane & 3][lane >> 2];
+// C/D (8x8): c{0,1} = C[lane >> 2][2 * (lane & 3) + {0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int src_bytes) {
+  // 16-byte async copy; src_bytes = 0 zero-fills the destination (rows / columns beyond the matrix)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 // hand-written fp64 tensor-core contractions (sqsv_dmma.cu)
 #define SQ_GRAM_MAXT 40
 struct GramTiles {          // 128 x 128 output tiles of one Gram matrix (upper triangle for bra == ket)

@@ -730,21 +730,23 @@ def test_sigma_and_rdm_kernel_variants_agree(sq):
     results = []
     other = rng.normal(size=sp.num_det)
     try:
-        for rows, etab, pipe in ((b"1", b"smem", b"1"), (b"1", b"smem", b"0"), (b"0", b"smem", b"1"), (b"0", b"const", b"0")):
+        for rows, etab, pipe, fused in ((b"1", b"smem", b"1", b"0"), (b"1", b"smem", b"0", b"0"), (b"0", b"smem", b"1", b"0"),
+                                        (b"0", b"const", b"0", b"0"), (b"0", b"smem", b"1", b"1")):
             lib.sq_set_option(b"panel", b"768")            # 3920 determinants -> 6 panels, the last one partial
+            lib.sq_set_option(b"sigma_fused", fused)       # "1": the fused gather -> DMMA -> scatter kernel (the default)
             lib.sq_set_option(b"rows", rows)
             lib.sq_set_option(b"etab", etab)
             lib.sq_set_option(b"pipeline", pipe)
             info = sq.ci.get_indexing(0, n, 0, na, nb)      # a fresh space picks up the panel width
             for name, gg in (("sym", g), ("unsym", g_unsym)):
                 out = sq.osa.propagate_state([hamiltonian_0i_0a(h, gg, 0, n)], state, info)
-                assert np.max(np.abs(out - refs[name])) < 1e-11, (rows, etab, pipe, name)
+                assert np.max(np.abs(out - refs[name])) < 1e-11, (rows, etab, pipe, fused, name)
             d1, d2 = sq.osa.reduced_density_matrices(state, state, info)
             t1, t2 = sq.osa.reduced_density_matrices(other, state, info)
             results.append((d1, d2, t1, t2))
             assert abs(np.trace(d1) - (na + nb)) < 1e-12
     finally:
-        for name, val in ((b"panel", b"0"), (b"rows", b"0"), (b"etab", b"smem"), (b"pipeline", b"1")):
+        for name, val in ((b"panel", b"0"), (b"rows", b"0"), (b"etab", b"smem"), (b"pipeline", b"1"), (b"sigma_fused", b"1")):
             lib.sq_set_option(name, val)
     for other in results[1:]:
         for x, y in zip(results[0], other):
