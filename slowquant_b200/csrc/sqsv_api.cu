@@ -660,8 +660,8 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
     return SQ_OK;
   }
-  if (strcmp(name, "sigma_fused") == 0) {   // sigma: "1" (default) fused gather -> DMMA -> scatter kernel, "0" three-kernel panel pipeline
-    sq_hamiltonian_set_sigma_fused(!(value && value[0] == '0'));
+  if (strcmp(name, "sigma_fused") == 0) {   // sigma: "0" (default) three-kernel panel pipeline, "1" fused gather -> DMMA -> scatter kernel (slower)
+    sq_hamiltonian_set_sigma_fused(value && value[0] == '1');
     return SQ_OK;
   }
   if (strcmp(name, "sgemm_cta") == 0) {   // sigma DMMA kernel: "2" (default) or "1" CTAs of 4 warps per SM

@@ -782,8 +782,9 @@ static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D,
 //   C  the accumulators replace the D tile in shared memory and every thread scatters its share:
 //      out[E_pq J_t] += sign (F[pq][t] + k_pq in[J_t]).
 // Two CTAs per SM: while one is in phase B (tensor pipe) the other gathers or scatters (LSU pipe).  Same arithmetic as
-// build_Dsym_kernel / sigma_dmma_kernel / scatter_E_kernel, which remain for spaces with more than 160 generator rows, for
-// alpha-sharded vectors and as the A/B reference (sq_set_option("sigma_fused", "0")).
+// build_Dsym_kernel / sigma_dmma_kernel / scatter_E_kernel.  MEASURED SLOWER than that three-kernel pipeline (728 ms against
+// 445 ms at CAS(16,16)): the gathers want 64 warps per SM to hide their latency and get 16 here, so the tensor pipe idles at 27 %.
+// Parity-green and kept behind sq_set_option("sigma_fused", "1") as evidence; the default is the panel pipeline.
 // ---------------------------------------------------------------------------------------------------------------------------
 #define SF_BN 64
 #define SF_LDB 68            // D / F tile row stride (doubles): = 4 (mod 16) -> conflict-free B fragments
@@ -939,7 +940,8 @@ sigma_fused_kernel(const double* __restrict__ IN, double* __restrict__ OUT, cons
   }
 }
 
-static int g_sigma_fused = 1;   // sq_set_option("sigma_fused", "0"): the three-kernel panel pipeline instead
+static int g_sigma_fused = 0;   // measured at CAS(16,16): 728 ms fused against 445 ms for the three-kernel panel pipeline (profiles/r2_visit6_ab_sigma_fused.txt):
+                                // with 16 warps per SM the gathers of phase A are latency-bound (tensor pipe 27 %); kept as sq_set_option("sigma_fused", "1")
 void sq_hamiltonian_set_sigma_fused(int on) { g_sigma_fused = on ? 1 : 0; }
 
 static size_t sigma_fused_smem(int mq, int nrow, int n) {

@@ -105,7 +105,7 @@ __device__ __forceinline__ void sts128(uint32_t a, double2 v) {
 // Shared memory: [NBUF tiles: Rn x Wn x gp doubles][beta delta: LTB][alpha delta: LTA][batch bases: WIN_RMAX x 16]
 // [tiles per batch: WIN_RMAX][list headers: int4 x SQ_WIN_MAX_BRICKS][per brick: maxQ uint2 quad entries + maxS uint32
 // single entries, BYTE offsets in 16-bit fields].
-template <int NBUF>
+template <int NBUF, bool BATCH>
 __global__ void __launch_bounds__(WIN_THREADS, NBUF == 2 ? 2 : 3)
 win_kernel(double* __restrict__ C0, int64_t NB, const WinDev W, const __grid_constant__ WinProgram P, int n_states, int64_t state_stride) {
   // n_states vectors C0 + s * state_stride share this CTA's tables and work lists (state-averaged batches, osa.py:1415-1864:
@@ -145,8 +145,8 @@ win_kernel(double* __restrict__ C0, int64_t NB, const WinDev W, const __grid_con
   const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(tile);
   // the whole batch is requested at once with 8-byte async copies
   auto issue_loads = [&](int q) {
-    const int it = q % n_items;
-    const double* C = C0 + (int64_t)(q / n_items) * state_stride;
+    const int it = BATCH ? q % n_items : q;
+    const double* C = BATCH ? C0 + (int64_t)(q / n_items) * state_stride : C0;
     const uint32_t tb = tb0 + (uint32_t)((q % NBUF) * W.tile_doubles) * 8u;
     const int kcnt = skcnt[it];
     const int* sb = sbase + it * WIN_G;
@@ -207,10 +207,10 @@ win_kernel(double* __restrict__ C0, int64_t NB, const WinDev W, const __grid_con
   // 8 lanes x 2 tiles per work-list entry (32 entries in flight per CTA); every shared-memory access moves 16 bytes
   const int g2 = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
-  const int n_total = n_items * n_states;
+  const int n_total = BATCH ? n_items * n_states : n_items;   // BATCH = false: one vector, the round-1 code path without index arithmetic
   for (int q = 0; q < n_total; ++q) {
-    const int it = q % n_items;
-    double* const C = C0 + (int64_t)(q / n_items) * state_stride;
+    const int it = BATCH ? q % n_items : q;
+    double* const C = BATCH ? C0 + (int64_t)(q / n_items) * state_stride : C0;
     const int kcnt = skcnt[it];
     const uint32_t tb = tb0 + (uint32_t)((q % NBUF) * W.tile_doubles) * 8u;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1003,13 +1003,21 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
   cudaError_t e = cudaSuccess;
   static size_t attr[3] = {0, 0, 0};
   if (smem > 48 * 1024 && smem > attr[wt.nbuf]) {
-    e = wt.nbuf == 2 ? cudaFuncSetAttribute(win_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                     : cudaFuncSetAttribute(win_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(win_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(win_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(win_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(win_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) attr[wt.nbuf] = smem;
   }
   if (e == cudaSuccess) {
-    if (wt.nbuf == 2) win_kernel<2><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, n_states, state_stride);
-    else win_kernel<1><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, n_states, state_stride);
+    const bool batch = n_states > 1;
+    if (wt.nbuf == 2) {
+      if (batch) win_kernel<2, true><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, n_states, state_stride);
+      else win_kernel<2, false><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, 1, 0);
+    } else {
+      if (batch) win_kernel<1, true><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, n_states, state_stride);
+      else win_kernel<1, false><<<grid, WIN_THREADS, smem, st>>>(state, sp->NB, W, P, 1, 0);
+    }
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
