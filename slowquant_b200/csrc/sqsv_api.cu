@@ -660,6 +660,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
     return SQ_OK;
   }
+  if (strcmp(name, "rdm_sym") == 0) {   // sq_rdm12 with bra == ket: "1" (default) two symmetric S / A Gram matrices, "0" the plain n^2 x n^2 one
+    sq_hamiltonian_set_rdm_sym(!(value && value[0] == '0'));
+    return SQ_OK;
+  }
   if (strcmp(name, "sigma_fused") == 0) {   // sigma: "0" (default) three-kernel panel pipeline, "1" fused gather -> DMMA -> scatter kernel (slower)
     sq_hamiltonian_set_sigma_fused(value && value[0] == '1');
     return SQ_OK;

@@ -183,6 +183,154 @@ int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, in
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Symmetric Gram matrices for the 2-RDM of one real vector (bra == ket): with S_pq = E_pq + E_qp (p >= q; S_pp = E_pp) and
+// A_pq = E_pq - E_qp (p > q) the products <S A> and <A S> are commutators, i.e. 1-RDM elements, so
+//     <E_pq E_rs> = sum T T' ( <S_x S_y> | -<A_x A_y> | 1/2 <[Z_x, Z_y]> )
+// needs only the two SYMMETRIC Gram matrices G_SS = Ds Ds^T (136 x 136 at n = 16) and G_AA = Da Da^T (120 x 120): a quarter of
+// the n^4 products of the plain <E_pq E_rs> Gram matrix (the reference's s_lim loops, ups_wavefunction.py:450-475, exploit the
+// same 4-fold symmetry).  One CTA = one matrix (<= 144 rows) and one K range; 12 warps own the 48 x 24 blocks of its upper
+// triangle, operands staged once per stage for rows and columns alike (X = Y).  Split-K partial sums live in per-(matrix, split)
+// slots updated in panel order and are added in a fixed order at the end (deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+#define GS_R 144
+#define GS_KC 16
+#define GS_LD 20
+#define GS_STAGES 4
+#define GS_THREADS 384
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gram_sym_kernel(const double* __restrict__ Z, int64_t ld, int rows0, int rows1, int64_t K, int n_split, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double gsm2[];
+  const int mat = blockIdx.x / n_split, split = blockIdx.x % n_split;
+  const int row0 = mat ? rows0 : 0, nrows = mat ? rows1 : rows0;
+  const int64_t n_chunks = K / GS_KC;
+  const int64_t c_begin = n_chunks * split / n_split, c_end = n_chunks * (split + 1) / n_split;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // warp -> (row block of 48, column block of 24) of the upper triangle: (0, 0..5), (1, 2..5), (2, 4..5)
+  const int bi = warp < 6 ? 0 : (warp < 10 ? 1 : 2);
+  const int bj = warp < 6 ? warp : (warp < 10 ? warp - 4 : warp - 6);
+  double acc[6][3][2];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(gsm2);
+  constexpr int STAGE_D = GS_R * GS_LD;
+  auto issue = [&](int64_t c, int slot) {
+    const int64_t k0 = c * GS_KC;
+    const uint32_t sb = sbase + (uint32_t)(slot * STAGE_D) * 8u;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {                      // 144 rows x 8 chunks of 16 bytes = 1152 = 3 x 384
+      const int id = threadIdx.x + q * GS_THREADS;
+      const int r = id >> 3, ch = id & 7;
+      const bool ok = r < nrows;
+      cp16(sb + (uint32_t)(r * GS_LD + ch * 2) * 8u, Z + (int64_t)(row0 + (ok ? r : 0)) * ld + k0 + ch * 2, ok ? 16 : 0);
+    }
+  };
+  const int64_t n_it = c_end - c_begin;
+  for (int s = 0; s < GS_STAGES - 1; ++s) {
+    if (s < n_it) issue(c_begin + s, s);
+    cp_commit();
+  }
+  for (int64_t it = 0; it < n_it; ++it) {
+    cp_wait<GS_STAGES - 2>();
+    __syncthreads();
+    if (it + GS_STAGES - 1 < n_it) issue(c_begin + it + GS_STAGES - 1, (int)((it + GS_STAGES - 1) % GS_STAGES));
+    cp_commit();
+    const double* xs = gsm2 + (it % GS_STAGES) * STAGE_D;
+#pragma unroll
+    for (int k4 = 0; k4 < GS_KC / 4; ++k4) {
+      double af[6], bf[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) af[i] = xs[(bi * 48 + i * 8 + (lane >> 2)) * GS_LD + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) bf[j] = xs[(bj * 24 + j * 8 + (lane >> 2)) * GS_LD + k4 * 4 + (lane & 3)];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  double* out = partial + ((size_t)split * 2 + mat) * (GS_R * GS_R);   // owned by this CTA: plain read-modify-write
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int r = bi * 48 + i * 8 + (lane >> 2), c = bj * 24 + j * 8 + 2 * (lane & 3);
+      double2* p = reinterpret_cast<double2*>(out + r * GS_R + c);
+      double2 v = *p;
+      v.x += acc[i][j][0];
+      v.y += acc[i][j][1];
+      *p = v;
+    }
+}
+
+// G[mat][r][c] (two 144 x 144 matrices, symmetric) = sum over the splits in split order; only c >= r was computed
+__global__ void __launch_bounds__(256)
+gram_sym_reduce_kernel(const double* __restrict__ partial, int n_split, double* __restrict__ G) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= 2 * GS_R * GS_R) return;
+  const int mat = e / (GS_R * GS_R), rc = e % (GS_R * GS_R), r = rc / GS_R, c = rc % GS_R;
+  if (c < r) return;
+  double s = 0.0;
+  for (int k = 0; k < n_split; ++k) s += partial[((size_t)k * 2 + mat) * (GS_R * GS_R) + rc];
+  G[(size_t)mat * GS_R * GS_R + r * GS_R + c] = s;
+  G[(size_t)mat * GS_R * GS_R + c * GS_R + r] = s;
+}
+
+static size_t gram_sym_smem() { return sizeof(double) * GS_STAGES * GS_R * GS_LD; }
+
+int sq_gram_sym_rows() { return GS_R; }
+
+int sq_gram_sym_begin(int n_sm, double** d_partial, size_t* partial_doubles, int* n_split, cudaStream_t st) {
+  *n_split = std::max(1, n_sm / 2);                  // two matrices: one CTA per SM
+  const size_t need = (size_t)(*n_split) * 2 * GS_R * GS_R;
+  if (*partial_doubles < need) {
+    if (*d_partial) cudaFree(*d_partial);
+    *d_partial = nullptr;
+    *partial_doubles = 0;
+    SQ_CUDA(cudaMalloc(d_partial, sizeof(double) * need));
+    *partial_doubles = need;
+  }
+  SQ_CUDA(cudaMemsetAsync(*d_partial, 0, sizeof(double) * need, st));
+  return SQ_OK;
+}
+
+// one panel Z (rows0 S-rows followed by rows1 A-rows, leading dimension ld, K columns)
+int sq_gram_sym_panel(const double* Z, int64_t ld, int rows0, int rows1, int64_t K, int n_split, double* d_partial, cudaStream_t st) {
+  if (K % GS_KC != 0 || ld % 2 != 0 || rows0 > GS_R || rows1 > GS_R || rows0 < 1) {
+    sq_set_error("symmetric Gram panel: K = %lld must be a multiple of %d, at most %d rows per matrix", (long long)K, GS_KC, GS_R);
+    return SQ_ERR_INVALID;
+  }
+  static bool attr = false;
+  if (!attr) {
+    SQ_CUDA(cudaFuncSetAttribute(gram_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_sym_smem()));
+    attr = true;
+  }
+  const int n_mat = rows1 > 0 ? 2 : 1;
+  gram_sym_kernel<<<(unsigned)(n_mat * n_split), GS_THREADS, gram_sym_smem(), st>>>(Z, ld, rows0, rows1, K, n_split, d_partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("gram_sym_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+// d_G: two 144 x 144 row-major matrices (G_SS, G_AA)
+int sq_gram_sym_end(int n_split, const double* d_partial, double* d_G, cudaStream_t st) {
+  gram_sym_reduce_kernel<<<(2 * GS_R * GS_R + 255) / 256, 256, 0, st>>>(d_partial, n_split, d_G);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("gram_sym_reduce_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // sigma: F[m][t] = sum_k Gm[m][k] D[k][t], m, k < nrow, t in a tile of 64 determinants.
 // "Thin" CTAs: 4 warps = 2 (row halves) x 2 (32 determinants each), ~190 registers per thread, one or two CTAs per SM -- the
 // tensor pipe is saturated by one warp per SM sub-partition, and most of the SM (registers, warp slots, the LSU pipe) stays

@@ -25,6 +25,7 @@ struct ERec {                 // one spin component of E_pq acting on a determin
 };
 
 struct HamWork {
+  double* d_gsym = nullptr;   // G_SS and G_AA (two 144 x 144 matrices) of the symmetric 2-RDM route
   double* d_gram = nullptr;   // split-K partial sums of the 2-RDM Gram matrix (sqsv_dmma.cu)
   size_t gram_doubles = 0;
   int n_sm = 0;
@@ -92,6 +93,7 @@ void sq_hamiltonian_set_panel_width(long long w) { g_panel_width = w > 0 ? (int6
 static void free_work(HamWork* w) {
   if (!w) return;
   cudaFree(w->d_gram);
+  cudaFree(w->d_gsym);
   cudaFree(w->d_etab);
   cudaFree(w->d_tabG);
   cudaFree(w->d_tabS);
@@ -396,6 +398,52 @@ build_D_alu_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_
         v += (par ? -rb.s0 : rb.s0) * x;
       }
       D[(int64_t)slot * W + t] = v;
+    }
+}
+
+// Panel of the symmetric / antisymmetric generators (2-RDM of one real vector, see gram_sym_kernel in sqsv_dmma.cu):
+//   rows [0, nS):       <J_t| S_pq |in>,  S_pq = E_pq + E_qp (p > q), S_pp = E_pp,        slot = p (p + 1) / 2 + q
+//   rows [nS, n^2):     <J_t| A_pq |in>,  A_pq = E_pq - E_qp (p > q),                     slot = nS + p (p - 1) / 2 + q
+__global__ void __launch_bounds__(256)
+build_DSA_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len, int n,
+                 const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                 const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int n2 = n * n, nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  const int64_t ia_loc = j / NB, ib = j - ia_loc * NB;
+  const uint32_t a = __ldg(strA + row_begin + ia_loc), b = __ldg(strB + ib);
+  auto elem = [&](int p, int q) -> double {
+    double v = 0.0;
+    const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      v += (par ? -ra.s0 : ra.s0) * IN[((int64_t)__ldg(rankA + sa) - row_begin) * NB + ib];
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      v += (par ? -rb.s0 : rb.s0) * IN[ia_loc * NB + __ldg(rankB + sb)];
+    }
+    return v;
+  };
+  int ss = 0, as = nS;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q <= p; ++q, ++ss) {
+      if (p == q) {
+        D[(int64_t)ss * W + t] = elem(p, p);
+      } else {
+        const double x = elem(p, q), y = elem(q, p);
+        D[(int64_t)ss * W + t] = x + y;
+        D[(int64_t)as * W + t] = x - y;
+        ++as;
+      }
     }
 }
 
@@ -1161,6 +1209,71 @@ extern "C" int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, c
   return rdm12_impl(sp, pb.p[sp->rank], pk.p[sp->rank], &pb, &pk, rdm1_host, rdm2_host, stream);
 }
 
+// <E_pq E_rs> for all p, q, r, s and the 1-RDM from the two symmetric Gram matrices of the S / A generators (bra == ket, real):
+//   E_pq = (S_pq + A_pq) / 2, E_qp = (S_pq - A_pq) / 2 (p > q), E_pp = S_pp;
+//   <S_x S_y> = G_SS, <A_x A_y> = -G_AA (A is anti-Hermitian), <S_x A_y> = <[S_x, A_y]> / 2, <A_x S_y> = <[A_x, S_y]> / 2 with
+//   <[E_pq, E_rs]> = delta_qr G1_ps - delta_ps G1_rq;  G1_pq = (1 / N) sum_r <E_pq E_rr> = c_pq / N sum_r G_SS[pq][rr].
+// G2h[(q, p)][(r, s)] = <E_pq E_rs> (the layout the plain Gram path produces); ldg = leading dimension of GSS / GAA.
+static void assemble_g2_from_sym(int n, const double* GSS, const double* GAA, int ldg, int n_elec, std::vector<double>* G2h,
+                                 std::vector<double>* g1h) {
+  const int n2 = n * n;
+  auto sslot = [](int p, int q) { return p * (p + 1) / 2 + q; };   // p >= q
+  auto aslot = [](int p, int q) { return p * (p - 1) / 2 + q; };   // p > q
+  std::vector<double>& g1 = *g1h;
+  g1.assign((size_t)n2, 0.0);
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q <= p; ++q) {
+      double v = 0.0;
+      for (int r = 0; r < n; ++r) v += GSS[(size_t)sslot(p, q) * ldg + sslot(r, r)];
+      v *= (p == q ? 1.0 : 0.5) / n_elec;
+      g1[(size_t)p * n + q] = g1[(size_t)q * n + p] = v;
+    }
+  auto C4 = [&](int p, int q, int r, int s) { return (q == r ? g1[(size_t)p * n + s] : 0.0) - (p == s ? g1[(size_t)r * n + q] : 0.0); };
+  struct Term { double c; int kind, slot, p, q; };   // kind 0: S, 1: A; (p, q) with p >= q
+  auto expand = [&](int p, int q, Term* out) -> int {   // E_pq in terms of S / A generators
+    if (p == q) { out[0] = {1.0, 0, sslot(p, p), p, p}; return 1; }
+    const int hi = p > q ? p : q, lo = p > q ? q : p;
+    out[0] = {0.5, 0, sslot(hi, lo), hi, lo};
+    out[1] = {p > q ? 0.5 : -0.5, 1, aslot(hi, lo), hi, lo};
+    return 2;
+  };
+  // <[Z_x, Z_y]> with Z = S or A of the pair (p >= q): Z = E_pq + eps E_qp (eps = +1 S, -1 A; S_pp = E_pp)
+  auto comm = [&](const Term& x, const Term& y) {
+    double v = 0.0;
+    const int nx = x.p == x.q ? 1 : 2, ny = y.p == y.q ? 1 : 2;
+    for (int i = 0; i < nx; ++i)
+      for (int j = 0; j < ny; ++j) {
+        const double ci = (i == 0 ? 1.0 : (x.kind ? -1.0 : 1.0)), cj = (j == 0 ? 1.0 : (y.kind ? -1.0 : 1.0));
+        const int p = i == 0 ? x.p : x.q, q = i == 0 ? x.q : x.p, r = j == 0 ? y.p : y.q, s = j == 0 ? y.q : y.p;
+        v += ci * cj * C4(p, q, r, s);
+      }
+    return v;
+  };
+  G2h->assign((size_t)n2 * n2, 0.0);
+  Term ta[2], tb[2];
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q) {
+      const int na = expand(p, q, ta);
+      for (int r = 0; r < n; ++r)
+        for (int s = 0; s < n; ++s) {
+          const int nb = expand(r, s, tb);
+          double v = 0.0;
+          for (int i = 0; i < na; ++i)
+            for (int j = 0; j < nb; ++j) {
+              double m;
+              if (ta[i].kind == 0 && tb[j].kind == 0) m = GSS[(size_t)ta[i].slot * ldg + tb[j].slot];
+              else if (ta[i].kind == 1 && tb[j].kind == 1) m = -GAA[(size_t)ta[i].slot * ldg + tb[j].slot];
+              else m = 0.5 * comm(ta[i], tb[j]);
+              v += ta[i].c * tb[j].c * m;
+            }
+          (*G2h)[((size_t)(q * n + p)) * n2 + (r * n + s)] = v;
+        }
+    }
+}
+
+static int g_rdm_sym = 1;   // sq_set_option("rdm_sym", "0"): the plain <E_pq E_rs> Gram matrix also for bra == ket
+void sq_hamiltonian_set_rdm_sym(int on) { g_rdm_sym = on ? 1 : 0; }
+
 static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev, const PeerView* pv_bra,
                       const PeerView* pv_ket, double* rdm1_host, double* rdm2_host, void* stream) {
   SqRange nvtx_range("sq_rdm12");
@@ -1182,7 +1295,15 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   const bool rdm1_from_G2 = rdm2_host && n_elec > 0;
   GramTiles tiles;
   int n_split = 1;
-  if (rdm2_host) SQ_CHECK(sq_gram_begin(n2, same, w->n_sm, &w->d_gram, &w->gram_doubles, &tiles, &n_split, st));
+  // bra == ket (real): two symmetric Gram matrices of the S / A generators instead of the n^2 x n^2 one (a quarter of the products)
+  const int nS = n * (n + 1) / 2, nA = n2 - nS, GR = sq_gram_sym_rows();
+  const bool sym_route = g_rdm_sym && same && rdm2_host && !pv_ket && n_elec > 0 && nS <= GR;
+  if (sym_route) {
+    if (!w->d_gsym) SQ_CUDA(cudaMalloc(&w->d_gsym, sizeof(double) * 2 * (size_t)GR * GR));
+    SQ_CHECK(sq_gram_sym_begin(w->n_sm, &w->d_gram, &w->gram_doubles, &n_split, st));
+  } else if (rdm2_host) {
+    SQ_CHECK(sq_gram_begin(n2, same, w->n_sm, &w->d_gram, &w->gram_doubles, &tiles, &n_split, st));
+  }
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -1197,7 +1318,13 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     const int b = piped ? (int)(k & 1) : 0;
     double* Dket = w->d_D[b];
     if (piped && k >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // panels b are free once GEMM k-2 is done
-    SQ_CHECK(launch_build_D(sp, w, ket_dev, Dket, j0, s_build, use_const, false, pv_ket));
+    if (sym_route) {
+      build_DSA_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len, n, sp->d_strA, sp->d_strB, sp->d_rankA,
+                                                                  sp->d_rankB, sp->NB, sp->row_begin);
+      SQ_CHECK(launch_error("build_DSA_kernel"));
+    } else {
+      SQ_CHECK(launch_build_D(sp, w, ket_dev, Dket, j0, s_build, use_const, false, pv_ket));
+    }
     const double* Dbra = Dket;
     if (rdm2_host && !same) {
       SQ_CHECK(launch_build_D(sp, w, bra_dev, w->d_D[2 + b], j0, s_build, use_const, false, pv_bra));
@@ -1211,7 +1338,9 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
       // rdm1[pq] += sum_t bra[j0+t] * Dket[pq][t]   (one CTA per row, fixed summation order)
       SQ_CHECK(sq_panel_gemv(Dket, w->W, n2, bra_dev + j0, wl, d_g1, s_gemm));
     }
-    if (rdm2_host) {
+    if (sym_route) {
+      SQ_CHECK(sq_gram_sym_panel(Dket, w->W, nS, nA, w->W, n_split, w->d_gram, s_gemm));
+    } else if (rdm2_host) {
       // G2 row-major [a][b] = sum_t Dbra[a][t] Dket[b][t]: hand-written DMMA kernel, 128 x 128 output tiles, split-K partial
       // sums accumulated across the panels in per-(tile, split) slots (sqsv_dmma.cu); for bra == ket only the upper-triangular
       // tiles are computed (the Gram matrix is symmetric).  The panel is zero-padded beyond the last determinant.
@@ -1225,13 +1354,21 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     SQ_CUDA(cudaEventRecord(w->ev_start, s_build));
     SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
   }
-  if (rdm2_host) SQ_CHECK(sq_gram_end(tiles, n_split, w->d_gram, n2, same, d_G2, st));
   std::vector<double> G2h(rdm2_host ? (size_t)n2 * n2 : 0), g1h((size_t)n2);
-  SQ_CUDA(cudaMemcpyAsync(g1h.data(), d_g1, sizeof(double) * n2, cudaMemcpyDeviceToHost, st));
-  if (rdm2_host)
-    SQ_CUDA(cudaMemcpyAsync(G2h.data(), d_G2, sizeof(double) * (size_t)n2 * n2, cudaMemcpyDeviceToHost, st));
-  SQ_CUDA(cudaStreamSynchronize(st));
-  if (rdm1_from_G2) {
+  if (sym_route) {
+    SQ_CHECK(sq_gram_sym_end(n_split, w->d_gram, w->d_gsym, st));
+    std::vector<double> gs(2 * (size_t)GR * GR);
+    SQ_CUDA(cudaMemcpyAsync(gs.data(), w->d_gsym, sizeof(double) * gs.size(), cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(cudaStreamSynchronize(st));
+    assemble_g2_from_sym(n, gs.data(), gs.data() + (size_t)GR * GR, GR, n_elec, &G2h, &g1h);
+  } else {
+    if (rdm2_host) SQ_CHECK(sq_gram_end(tiles, n_split, w->d_gram, n2, same, d_G2, st));
+    SQ_CUDA(cudaMemcpyAsync(g1h.data(), d_g1, sizeof(double) * n2, cudaMemcpyDeviceToHost, st));
+    if (rdm2_host)
+      SQ_CUDA(cudaMemcpyAsync(G2h.data(), d_G2, sizeof(double) * (size_t)n2 * n2, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(cudaStreamSynchronize(st));
+  }
+  if (rdm1_from_G2 && !sym_route) {
     for (int p = 0; p < n; ++p)
       for (int q = 0; q < n; ++q) {
         double v = 0.0;

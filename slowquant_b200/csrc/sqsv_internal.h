@@ -212,6 +212,7 @@ void sq_hamiltonian_set_rows_mode(int on);         // row-per-CTA panel kernels 
 void sq_hamiltonian_set_pipeline(int on);          // sigma / RDM panel pipeline over internal streams (default on)
 void sq_hamiltonian_set_etab_alu(int on);          // panel kernels without an E_pq table (records computed from (p,q); default off)
 void sq_hamiltonian_set_rdm_tri(int on);
+void sq_hamiltonian_set_rdm_sym(int on);           // 2-RDM of one vector from the symmetric S / A Gram matrices (default on)
 void sq_hamiltonian_set_sigma_fused(int on);       // sigma through the fused gather -> DMMA -> scatter kernel (default on)           // RDMs with bra == ket: three half-size DGEMMs instead of one (default off)
 void sq_hamiltonian_set_etab_mode(int use_const);  // E_pq table in constant (1) or shared (0) memory
 void sq_reshard_set_mode(int lsu);                 // re-shard kernel: 0 bulk-copy engine (default), 1 vector load/store
@@ -242,6 +243,10 @@ int sq_gram_begin(int nrows, bool symmetric, int n_sm, double** d_partial, size_
 int sq_gram_panel(const double* X, const double* Y, int64_t ld, int nrows, int64_t K, const GramTiles& tiles, int n_split,
                   double* d_partial, cudaStream_t st);
 int sq_gram_end(const GramTiles& tiles, int n_split, const double* d_partial, int nrows, bool symmetric, double* d_G2, cudaStream_t st);
+int sq_gram_sym_rows();
+int sq_gram_sym_begin(int n_sm, double** d_partial, size_t* partial_doubles, int* n_split, cudaStream_t st);
+int sq_gram_sym_panel(const double* Z, int64_t ld, int rows0, int rows1, int64_t K, int n_split, double* d_partial, cudaStream_t st);
+int sq_gram_sym_end(int n_split, const double* d_partial, double* d_G, cudaStream_t st);
 void sq_sigma_gemm_set_residency(int n);
 int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st);
 int sq_panel_gemv(const double* D, int64_t W, int nrows, const double* x, int64_t K, double* g1, cudaStream_t st);

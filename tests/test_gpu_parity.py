@@ -733,6 +733,9 @@ def test_sigma_and_rdm_kernel_variants_agree(sq):
         for rows, etab, pipe, fused in ((b"1", b"smem", b"1", b"0"), (b"1", b"smem", b"0", b"0"), (b"0", b"smem", b"1", b"0"),
                                         (b"0", b"const", b"0", b"0"), (b"0", b"smem", b"1", b"1")):
             lib.sq_set_option(b"panel", b"768")            # 3920 determinants -> 6 panels, the last one partial
+            # 2-RDM of one vector: the plain n^2 x n^2 Gram matrix in the first two rounds, the two symmetric S / A Gram matrices
+            # (the default) in the others -- all must agree to 1e-12
+            lib.sq_set_option(b"rdm_sym", b"0" if rows == b"1" else b"1")
             lib.sq_set_option(b"sigma_fused", fused)       # "1": the fused gather -> DMMA -> scatter kernel (off by default: slower)
             lib.sq_set_option(b"rows", rows)
             lib.sq_set_option(b"etab", etab)
@@ -746,7 +749,7 @@ def test_sigma_and_rdm_kernel_variants_agree(sq):
             results.append((d1, d2, t1, t2))
             assert abs(np.trace(d1) - (na + nb)) < 1e-12
     finally:
-        for name, val in ((b"panel", b"0"), (b"rows", b"0"), (b"etab", b"smem"), (b"pipeline", b"1"), (b"sigma_fused", b"0")):
+        for name, val in ((b"panel", b"0"), (b"rows", b"0"), (b"etab", b"smem"), (b"pipeline", b"1"), (b"sigma_fused", b"0"), (b"rdm_sym", b"1")):
             lib.sq_set_option(name, val)
     for other in results[1:]:
         for x, y in zip(results[0], other):
