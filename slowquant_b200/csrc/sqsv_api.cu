@@ -621,6 +621,7 @@ static WinConfig& win_config() {
   return cfg;
 }
 
+static WinConfig& grad_win_config();
 // run-time switches for A/B comparisons and tests: name "win" takes the SQ_WIN syntax
 extern "C" int sq_set_option(const char* name, const char* value) {
   if (!name) return SQ_ERR_INVALID;
@@ -630,7 +631,12 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     return SQ_OK;
   }
   if (strcmp(name, "wingrad") == 0) {
-    g_win_grad = (value && value[0] == '1') ? 1 : 0;
+    g_win_grad = (value && value[0] == '0') ? 0 : 1;
+    return SQ_OK;
+  }
+  if (strcmp(name, "wingrad_win") == 0) {   // window configuration of the gradient sweep (SQ_WIN syntax)
+    parse_win_config(value, &grad_win_config());
+    ++g_plan_version;
     return SQ_OK;
   }
   if (strcmp(name, "panel") == 0) {   // determinants per sigma / RDM panel for spaces created afterwards ("0": default)
@@ -686,9 +692,24 @@ struct WinCand {
   bool dead = false;
 };
 
+// The gradient sweep stages TWO vectors per batch, so it plans with its own window configuration (narrower windows: the tiles
+// of bra and ket together must leave room for two CTAs per SM) and keeps its own plan cache (sq_layout::grad_plans).
+static WinConfig& grad_win_config() {
+  static WinConfig cfg;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("SQ_WINGRAD_WIN");
+    parse_win_config(e ? e : "5:4:0,40,3,16,2", &cfg);
+  }
+  return cfg;
+}
+static const WinConfig* g_active_cfg = nullptr;   // configuration the planner runs with (nullptr: win_config())
+static inline const WinConfig& active_config() { return g_active_cfg ? *g_active_cfg : win_config(); }
+
 static void win_candidates(const sq_space* sp, std::vector<WinCand>* out) {
   out->clear();
-  const WinConfig& cfg = win_config();
+  const WinConfig& cfg = active_config();
   if (!cfg.enabled) return;
   const int n = sp->n_orb;
   for (int wi = 0; wi < 3; ++wi) {
@@ -721,26 +742,31 @@ static uint32_t run_orbitals(const sq_layout* lay, const std::vector<int>& run) 
 static int plan_launches_uncached(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out);
 
 // plans are cached on the layout (the beam search costs tens of milliseconds for a 720-operator circuit)
-static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out) {
+static int plan_launches(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out, bool grad = false) {
   if (lay->plan_version != g_plan_version) {
     lay->plans.clear();
+    lay->grad_plans.clear();
     lay->plan_version = g_plan_version;
   }
-  for (auto& pc : lay->plans)
+  std::vector<PlanCache>& cache = grad ? lay->grad_plans : lay->plans;
+  for (auto& pc : cache)
     if (pc.runs == runs) {
       *out = pc.launches;
       return SQ_OK;
     }
-  SQ_CHECK(plan_launches_uncached(lay, runs, out));
-  if (lay->plans.size() >= 64) lay->plans.erase(lay->plans.begin());   // the re-sharding driver plans one run list per phase
-  lay->plans.push_back({runs, *out});
+  g_active_cfg = grad ? &grad_win_config() : nullptr;
+  const int rc = plan_launches_uncached(lay, runs, out);
+  g_active_cfg = nullptr;
+  SQ_CHECK(rc);
+  if (cache.size() >= 64) cache.erase(cache.begin());   // the re-sharding driver plans one run list per phase
+  cache.push_back({runs, *out});
   return SQ_OK;
 }
 
 static int plan_launches_uncached(sq_layout* lay, const std::vector<std::vector<int>>& runs, std::vector<Launch>* out) {
   out->clear();
   sq_space* sp = lay->sp;
-  const WinConfig& cfg = win_config();
+  const WinConfig& cfg = active_config();
   const int m = (int)runs.size();
   std::vector<WinCand> cands;
   win_candidates(sp, &cands);
@@ -1532,16 +1558,18 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
     }
   }
   double* d_grad = nullptr;
-  if (!slot_op.empty()) {
-    SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st));
-    SQ_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * slot_op.size(), st));
+  const int n_repl = sq_win_grad_replicas();   // the window kernel spreads its global atomics over replicas of the slot array
+  const size_t n_slot = slot_op.size();
+  if (n_slot) {
+    SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * n_slot * n_repl, st));
+    SQ_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * n_slot * n_repl, st));
   }
   // the same launch plan as sq_ups_apply: bricks of a window sweep are differentiated and applied inside the sweep
   // (commuting bricks may be reordered: <bra|T_k|ket> does not change); quad launches run as two single bricks
   std::vector<Launch> launches;
   int status = SQ_OK;
   if (g_win_grad) {
-    status = plan_launches(lay, runs, &launches);
+    status = plan_launches(lay, runs, &launches, true);
   } else {
     // default: one fused brick per launch (tile_grad_kernel_v2 runs at 0.7 of the HBM roofline; the window gradient
     // kernel is correct but not yet faster per brick)
@@ -1580,7 +1608,7 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
         sptr[nb] = wsteps[nb];
         ++nb;
       }
-      if (status == SQ_OK) status = sq_launch_win_grad(sp, *l.wt, pair_idx, sptr, nst, slot0, nb, bra_dev, ket_dev, d_grad, st);
+      if (status == SQ_OK) status = sq_launch_win_grad(sp, *l.wt, pair_idx, sptr, nst, slot0, nb, bra_dev, ket_dev, d_grad, (int)n_slot, st);
       continue;
     }
     status = set_gauge(false);
@@ -1621,15 +1649,19 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
     }
   }
   if (status == SQ_OK) status = set_gauge(false);
-  if (status == SQ_OK && !slot_op.empty()) {
-    std::vector<double> g(slot_op.size());
+  if (status == SQ_OK && n_slot) {
+    std::vector<double> g(n_slot * n_repl);
     cudaError_t e = cudaMemcpyAsync(g.data(), d_grad, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
       sq_set_error("sq_ups_grad_sweep: %s", cudaGetErrorString(e));
       status = SQ_ERR_CUDA;
     } else {
-      for (size_t i = 0; i < g.size(); ++i) grad_host[slot_op[i] - first] += 2.0 * g[i];
+      for (size_t i = 0; i < n_slot; ++i) {
+        double v = 0.0;
+        for (int r = 0; r < n_repl; ++r) v += g[(size_t)r * n_slot + i];   // replicas in a fixed order
+        grad_host[slot_op[i] - first] += 2.0 * v;
+      }
     }
   }
   if (d_grad) cudaFreeAsync(d_grad, st);

@@ -188,6 +188,7 @@ struct sq_layout {
   std::map<std::vector<int>, int> gen_index;
   std::map<std::pair<int, int>, QuadTables> quads;   // built lazily per (pair1, pair2)
   std::vector<PlanCache> plans;   // launch plans by run structure (sqsv_api.cu)
+  std::vector<PlanCache> grad_plans;   // the same for the gradient sweep (its own window configuration)
   int plan_version = 0;
   std::map<std::array<int, 5>, struct WinTables*> wins;   // built lazily per (w0, H) (sqsv_win.cu)
 };
@@ -288,8 +289,9 @@ int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st, int n_states =
 bool sq_win_pair_ok(const sq_layout* lay, int pair, int w0, int H);
 int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** out);
 void sq_free_win_tables(WinTables* wt);
+int sq_win_grad_replicas();
 int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
-                       const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, cudaStream_t st);
+                       const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, int n_out, cudaStream_t st);
 int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
                   int n_bricks, double* state, cudaStream_t st, int n_states = 1, int64_t state_stride = 0);
 int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,

@@ -330,14 +330,29 @@ __device__ __forceinline__ void grot(double& xs, double& xt, double c, double s)
   xt = c * b + s * a;
 }
 
-// Shared memory: [bra tile][ket tile][accumulators: SQ_WIN_MAX_BRICKS x SQ_MAX_PROGRAM doubles][tables as win_kernel]
+#define WING_REPL 8   // replicas of the output slots (CTAs add into replica blockIdx.x % 8: spreads the global atomics)
+
+__device__ __forceinline__ void grot2(double2& xs, double2& xt, double c, double s) {
+  const double2 a = xs, b = xt;
+  xs = make_double2(c * a.x - s * b.x, c * a.y - s * b.y);
+  xt = make_double2(c * b.x + s * a.x, c * b.y + s * a.y);
+}
+// <bra|T|ket> contribution of one (source, target) amplitude pair: bra_tgt * ket_src - bra_src * ket_tgt, both tiles of the thread
+__device__ __forceinline__ double gdot2(const double2& bs, const double2& bt, const double2& ks, const double2& kt) {
+  return (bt.x * ks.x - bs.x * kt.x) + (bt.y * ks.y - bs.y * kt.y);
+}
+
+// Shared memory: [bra tile][ket tile][per-warp accumulators: WIN_WARPS x SQ_WIN_MAX_BRICKS x SQ_MAX_PROGRAM doubles][tables as
+// win_kernel].  Same thread layout as win_kernel: 8 lanes x 2 tiles per work-list entry, 128-bit shared-memory accesses.  The
+// per-step values of a brick are reduced inside the warp with a packed butterfly (9 double shuffles for 8 values) and added to
+// warp-private accumulators; one global atomic per (brick, step) and CTA at the end.
 __global__ void __launch_bounds__(WIN_THREADS, 2)
 win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, const WinDev W,
-                const __grid_constant__ WinGradProgram P, double* __restrict__ grad_out) {
+                const __grid_constant__ WinGradProgram P, double* __restrict__ grad_out, int n_out) {
   extern __shared__ double tile[];
   const int TD = W.tile_doubles;
   double* const sacc = tile + 2 * TD;
-  int* const sdB = reinterpret_cast<int*>(sacc + SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM);
+  int* const sdB = reinterpret_cast<int*>(sacc + WIN_WARPS * SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM);
   int* const sdA = sdB + W.LTB;
   int* const sbase = sdA + W.LTA;
   int* const skcnt = sbase + WIN_RMAX * WIN_G;
@@ -354,7 +369,7 @@ win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, 
   const int GP = W.gp;
   const int RS = Wn * GP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = threadIdx.x & (WIN_G - 1), slot = threadIdx.x >> 4;
+  const int g = threadIdx.x & (WIN_G - 1);
 
   for (int t = threadIdx.x; t < Wn; t += WIN_THREADS) sdB[t] = __ldg(W.deltaB + clsB * W.LTB + t);
   for (int t = threadIdx.x; t < Rn; t += WIN_THREADS) sdA[t] = __ldg(W.deltaA + clsA * W.LTA + t);
@@ -365,7 +380,7 @@ win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, 
   }
   if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + P.n)
     shdr[threadIdx.x - 128] = __ldg(W.listidx + (P.pair[threadIdx.x - 128] * W.H1 + ca2.y) * W.H1 + cb2.y);
-  if (threadIdx.x < SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM) sacc[threadIdx.x] = 0.0;
+  for (int t = threadIdx.x; t < WIN_WARPS * SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM; t += WIN_THREADS) sacc[t] = 0.0;
   __syncthreads();
 
   const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(tile);
@@ -428,14 +443,17 @@ win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, 
     }
   }
 
+  const int g2 = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const uint32_t lb = (uint32_t)__cvta_generic_to_shared(qall);
   const uint32_t kofs = (uint32_t)TD * 8u;   // ket tile behind the bra tile
+  double* const wacc = sacc + warp * (SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM);
   for (int it = 0; it < n_items; ++it) {
     const int kcnt = skcnt[it];
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const bool on = g < kcnt;
-    const uint32_t tg = tb0 + (uint32_t)g * 8u;   // one tile per thread, 16 lanes per entry
+    const bool on = 2 * g2 < kcnt;
+    const bool second = 2 * g2 + 1 < kcnt;        // the second tile of an odd batch holds stale data: it must not reach the sums
+    const uint32_t tg = tb0 + (uint32_t)g2 * 16u;
     for (int b = 0; b < P.n; ++b) {
       if (b) __syncthreads();
       const WinGradBrick& br = P.br[b];
@@ -446,56 +464,73 @@ win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, 
         const int4 hd = shdr[b];
         const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
         const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
-        for (int e = slot; e < nQ; e += WIN_THREADS / WIN_G) {
+        for (int e = slot; e < nQ; e += WIN_SLOTS) {
           uint32_t ux, uy;
           asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
           const uint32_t a0 = tg + (ux & 0xffffu), a1 = tg + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
-          double b00 = lds64(a0 + c0), b01 = lds64(a0 + c1), b10 = lds64(a1 + c0), b11 = lds64(a1 + c1);
-          double k00 = lds64(a0 + c0 + kofs), k01 = lds64(a0 + c1 + kofs), k10 = lds64(a1 + c0 + kofs), k11 = lds64(a1 + c1 + kofs);
+          double2 b00 = lds128(a0 + c0), b01 = lds128(a0 + c1), b10 = lds128(a1 + c0), b11 = lds128(a1 + c1);
+          double2 k00 = lds128(a0 + c0 + kofs), k01 = lds128(a0 + c1 + kofs), k10 = lds128(a1 + c0 + kofs), k11 = lds128(a1 + c1 + kofs);
+          if (!second) { b00.y = b01.y = b10.y = b11.y = 0.0; k00.y = k01.y = k10.y = k11.y = 0.0; }
 #pragma unroll
           for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
             if (k >= br.n) break;
             const int kind = br.kind[k] & 3;
             const double c = br.c[k], sn = br.s[k];
             if (kind == 0) {
-              acc[k] += (b10 * k00 - b00 * k10) + (b11 * k01 - b01 * k11);
-              grot(b00, b10, c, sn); grot(b01, b11, c, sn); grot(k00, k10, c, sn); grot(k01, k11, c, sn);
+              acc[k] += gdot2(b00, b10, k00, k10) + gdot2(b01, b11, k01, k11);
+              grot2(b00, b10, c, sn); grot2(b01, b11, c, sn); grot2(k00, k10, c, sn); grot2(k01, k11, c, sn);
             } else if (kind == 1) {
-              acc[k] += (b01 * k00 - b00 * k01) + (b11 * k10 - b10 * k11);
-              grot(b00, b01, c, sn); grot(b10, b11, c, sn); grot(k00, k01, c, sn); grot(k10, k11, c, sn);
+              acc[k] += gdot2(b00, b01, k00, k01) + gdot2(b10, b11, k10, k11);
+              grot2(b00, b01, c, sn); grot2(b10, b11, c, sn); grot2(k00, k01, c, sn); grot2(k10, k11, c, sn);
             } else {
-              acc[k] += b11 * k00 - b00 * k11;
-              grot(b00, b11, c, sn); grot(k00, k11, c, sn);
+              acc[k] += gdot2(b00, b11, k00, k11);
+              grot2(b00, b11, c, sn); grot2(k00, k11, c, sn);
             }
           }
-          sts64(a0 + c0, b00); sts64(a0 + c1, b01); sts64(a1 + c0, b10); sts64(a1 + c1, b11);
-          sts64(a0 + c0 + kofs, k00); sts64(a0 + c1 + kofs, k01); sts64(a1 + c0 + kofs, k10); sts64(a1 + c1 + kofs, k11);
+          sts128(a0 + c0, b00); sts128(a0 + c1, b01); sts128(a1 + c0, b10); sts128(a1 + c1, b11);
+          sts128(a0 + c0 + kofs, k00); sts128(a0 + c1 + kofs, k01); sts128(a1 + c0 + kofs, k10); sts128(a1 + c1 + kofs, k11);
         }
-        for (int e = slot; e < nS; e += WIN_THREADS / WIN_G) {
+        for (int e = slot; e < nS; e += WIN_SLOTS) {
           uint32_t u;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
           const uint32_t o0 = tg + (u & 0xffffu), o1 = tg + (u >> 16);
           const int want = e < nSa ? 0 : 1;   // alpha singles see the alpha rotations only, beta singles the beta ones
-          double b0 = lds64(o0), b1 = lds64(o1), k0 = lds64(o0 + kofs), k1 = lds64(o1 + kofs);
+          double2 b0 = lds128(o0), b1 = lds128(o1), k0 = lds128(o0 + kofs), k1 = lds128(o1 + kofs);
+          if (!second) { b0.y = b1.y = 0.0; k0.y = k1.y = 0.0; }
 #pragma unroll
           for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
             if (k >= br.n) break;
             if ((br.kind[k] & 3) != want) continue;
-            acc[k] += b1 * k0 - b0 * k1;
-            grot(b0, b1, br.c[k], br.s[k]);
-            grot(k0, k1, br.c[k], br.s[k]);
+            acc[k] += gdot2(b0, b1, k0, k1);
+            grot2(b0, b1, br.c[k], br.s[k]);
+            grot2(k0, k1, br.c[k], br.s[k]);
           }
-          sts64(o0, b0); sts64(o1, b1); sts64(o0 + kofs, k0); sts64(o1 + kofs, k1);
+          sts128(o0, b0); sts128(o1, b1); sts128(o0 + kofs, k0); sts128(o1 + kofs, k1);
         }
       }
-      // block-level sum of the step values of this brick (all lanes take part in the shuffles)
+      // packed butterfly over the warp: after the three exchange levels lane l holds value (l & 7) summed over 8 lanes, two more
+      // levels finish the sum; lanes 0..7 add the 8 step values to the warp's accumulators (all lanes take part in the shuffles)
+      {
+        double v4[4], v2[2], v1;
+        const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
 #pragma unroll
-      for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
-        if (k >= br.n) break;
-        double v = acc[k];
+        for (int i = 0; i < 4; ++i) {
+          const double keep = h4 ? acc[i + 4] : acc[i], send = h4 ? acc[i] : acc[i + 4];
+          v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0 && v != 0.0) atomicAdd(sacc + b * SQ_MAX_PROGRAM + k, v);
+        for (int i = 0; i < 2; ++i) {
+          const double keep = h2 ? v4[i + 2] : v4[i], send = h2 ? v4[i] : v4[i + 2];
+          v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        {
+          const double keep = h1 ? v2[1] : v2[0], send = h1 ? v2[0] : v2[1];
+          v1 = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+        // lane l (< 8) now holds step index  4 * bit2(l) + 2 * bit1(l) + bit0(l) = l
+        if (lane < 8 && lane < br.n) wacc[b * SQ_MAX_PROGRAM + lane] += v1;
       }
     }
     __syncthreads();
@@ -535,8 +570,10 @@ win_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB, 
   if (threadIdx.x < SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM) {
     const int b = threadIdx.x / SQ_MAX_PROGRAM, k = threadIdx.x - b * SQ_MAX_PROGRAM;
     if (b < P.n && k < P.br[b].n) {
-      const double v = sacc[threadIdx.x];
-      if (v != 0.0) atomicAdd(grad_out + P.br[b].slot0 + k, (P.br[b].kind[k] & 16) ? -v : v);
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < WIN_WARPS; ++w) v += sacc[w * (SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM) + threadIdx.x];
+      if (v != 0.0) atomicAdd(grad_out + (size_t)(blockIdx.x % WING_REPL) * n_out + P.br[b].slot0 + k, (P.br[b].kind[k] & 16) ? -v : v);
     }
   }
 }
@@ -1030,8 +1067,11 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
 
 // Gradient sweep of a window launch: out[slot0[k] + step] += <bra|T_step|ket> for every rotation step of brick k
 // (evaluated before that step), then both vectors are rotated.  Both vectors must be in the sign-free gauge.
+int sq_win_grad_replicas() { return WING_REPL; }
+
+// d_out: WING_REPL replicas of n_out slots (the caller adds the replicas)
 int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, const TileStep* const* steps, const int* n_steps,
-                       const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, cudaStream_t st) {
+                       const int* slot0, int n_bricks, double* bra, double* ket, double* d_out, int n_out, cudaStream_t st) {
   if (!wt.ok || n_bricks < 1 || n_bricks > SQ_WIN_MAX_BRICKS) {
     sq_set_error("window gradient launch with %d bricks (max %d) or without tables", n_bricks, SQ_WIN_MAX_BRICKS);
     return SQ_ERR_INVALID;
@@ -1066,7 +1106,11 @@ int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, c
   W.gp = wt.gp;
   W.tile_doubles = wt.tile_doubles; W.maxQ = wt.maxQ; W.maxS = wt.maxS;
   const size_t smem = sq_win_smem_bytes(wt.max_a, wt.max_b, wt.gp, 2, wt.LTA, wt.LTB, wt.maxQ, wt.maxS, n_bricks) +
-                      sizeof(double) * SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM;
+                      sizeof(double) * WIN_WARPS * SQ_WIN_MAX_BRICKS * SQ_MAX_PROGRAM;
+  if (smem > 220 * 1024) {
+    sq_set_error("window gradient launch: %zu bytes of shared memory for two %d x %d tiles", smem, wt.max_a, wt.max_b);
+    return SQ_ERR_UNSUPPORTED;
+  }
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(win_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1077,7 +1121,7 @@ int sq_launch_win_grad(sq_space* sp, const WinTables& wt, const int* pair_idx, c
     attr = smem;
   }
   const dim3 grid((unsigned)wt.n_ranges_b, (unsigned)wt.n_groups_a);
-  win_grad_kernel<<<grid, WIN_THREADS, smem, st>>>(bra, ket, sp->NB, W, P, d_out);
+  win_grad_kernel<<<grid, WIN_THREADS, smem, st>>>(bra, ket, sp->NB, W, P, d_out, n_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     sq_set_error("win_grad_kernel launch failed: %s", cudaGetErrorString(e));

@@ -641,13 +641,15 @@ def test_window_gradient_sweep(sq, n, na, nb, L, qnp):
             assert np.max(np.abs(g0 - gr)) < 1e-11
             assert np.max(np.abs(k0.cpu().numpy() - k_np)) < TOL
         sq.lib.check(lib.sq_set_option(b"wingrad", b"1"))
-        for cfg in ("1", "5:4:0,72,2,16,2", "6:0:0,100,0,4,1"):
-            sq.lib.check(lib.sq_set_option(b"win", cfg.encode()))
+        # the gradient sweep plans with its own window configuration (two vectors per batch): the default, wide windows (one
+        # CTA per SM), capped brick counts, narrow windows
+        for cfg in ("5:4:0,40,3,16,2", "1", "5:4:0,72,2,16,2", "6:0:0,100,0,4,1", "4:3:0,40,1,16,1"):
+            sq.lib.check(lib.sq_set_option(b"wingrad_win", cfg.encode()))
             g1, b1, k1 = sq.osa.ups_gradient_sweep(bra, ket, info, th.tolist(), lay)
             assert np.max(np.abs(g1 - g0)) < 1e-12, cfg
             assert float(torch.max(torch.abs(b1 - b0))) < 1e-13 and float(torch.max(torch.abs(k1 - k0))) < 1e-13, cfg
     finally:
-        sq.lib.check(lib.sq_set_option(b"win", b"1"))
+        sq.lib.check(lib.sq_set_option(b"wingrad_win", b"5:4:0,40,3,16,2"))
         sq.lib.check(lib.sq_set_option(b"wingrad", b"0"))
 
 
