@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the energy / RDM / theta-gradient timings")
+    ap.add_argument("--profile", action="store_true",
+                    help="for nsys / ncu runs: cudaProfilerStart/Stop and an NVTX range around the timed region (the library's own NVTX "
+                    "ranges -- sq_ups_apply, sq_sigma, sq_rdm12, sq_ups_grad_sweep, sq_reshard_rows -- nest inside it), no e2e / extras / CPU baseline")
     return ap.parse_args()
 
 
@@ -206,7 +209,11 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": 1e3 * layer_s * L,
+        # what was actually timed per step: ONE brick sample (the whole L-layer step is that sample x bricks-per-layer x L, see
+        # `extrapolated_ms_per_full_step`; the driver's clock around this run can only be compared with ms_per_step x steps)
+        "ms_per_step": 1e3 * mean_sample,
+        "step_scale_to_full": BRICKS_PER_LAYER(n) * L,
+        "extrapolated_ms_per_full_step": 1e3 * layer_s * L,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,

@@ -122,6 +122,13 @@ static int space_create_impl(int n_orb, int n_alpha, int n_beta, int device, int
     *out = sp;
     return SQ_OK;
   }
+  if (sp->row_end - sp->row_begin > (int64_t)65535 * 8) {
+    // the brick / generic kernels put chunks of 8 rows into gridDim.y (limit 65535)
+    sq_set_error("sq_space_create: %lld local alpha rows exceed the 524280 rows one device can take: shard the vector by alpha string "
+                 "(row_begin / row_end)", (long long)(sp->row_end - sp->row_begin));
+    delete sp;
+    return SQ_ERR_UNSUPPORTED;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) {
     sq_set_error("sq_space_create: cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));

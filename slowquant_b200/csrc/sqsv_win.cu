@@ -227,47 +227,47 @@ win_kernel(double* __restrict__ C0, int64_t NB, const WinDev W, const __grid_con
       const int nQ = hd.y, nSa = hd.z, nS = hd.z + hd.w;
       const uint32_t ql = lb + (uint32_t)(b * per_brick) * 4u, sl = ql + (uint32_t)W.maxQ * 8u;
       const WinBrick& br = P.br[b];
-      for (int e = slot; e < nQ; e += WIN_SLOTS) {   // 4x4 entries
-        uint32_t ux, uy;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
-        const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
-        const double2 y0 = lds128(a0 + c0), y1 = lds128(a0 + c1), y2 = lds128(a1 + c0), y3 = lds128(a1 + c1);
-        double2 z;
-        z.x = br.m[0] * y0.x + br.m[1] * y1.x + br.m[2] * y2.x + br.m[3] * y3.x;
-        z.y = br.m[0] * y0.y + br.m[1] * y1.y + br.m[2] * y2.y + br.m[3] * y3.y;
-        sts128(a0 + c0, z);
-        z.x = br.m[4] * y0.x + br.m[5] * y1.x + br.m[6] * y2.x + br.m[7] * y3.x;
-        z.y = br.m[4] * y0.y + br.m[5] * y1.y + br.m[6] * y2.y + br.m[7] * y3.y;
-        sts128(a0 + c1, z);
-        z.x = br.m[8] * y0.x + br.m[9] * y1.x + br.m[10] * y2.x + br.m[11] * y3.x;
-        z.y = br.m[8] * y0.y + br.m[9] * y1.y + br.m[10] * y2.y + br.m[11] * y3.y;
-        sts128(a1 + c0, z);
-        z.x = br.m[12] * y0.x + br.m[13] * y1.x + br.m[14] * y2.x + br.m[15] * y3.x;
-        z.y = br.m[12] * y0.y + br.m[13] * y1.y + br.m[14] * y2.y + br.m[15] * y3.y;
-        sts128(a1 + c1, z);
-      }
-      {   // 2x2 entries: alpha singles first, then beta singles; two per step
-        int e = slot;
-        for (; e + WIN_SLOTS < nS; e += 2 * WIN_SLOTS) {
+      // ONE loop over the brick's work: 4x4 entries first (padded to a multiple of 4 = the slots of a warp, so that a warp never
+      // mixes the two entry kinds), then the 2x2 entries two at a time.  The slots left over by the last round of 4x4 entries
+      // take 2x2 entries instead of idling (36 + 96 entries of a 20 x 20 tile: 3 rounds instead of 4).
+      const int nQ4 = (nQ + 3) & ~3, nU = nQ4 + ((nS + 1) >> 1);
+      for (int e = slot; e < nU; e += WIN_SLOTS) {
+        if (e < nQ4) {
+          if (e >= nQ) continue;
+          uint32_t ux, uy;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(ql + (uint32_t)e * 8u));
+          const uint32_t a0 = tgb + (ux & 0xffffu), a1 = tgb + (ux >> 16), c0 = uy & 0xffffu, c1 = uy >> 16;
+          const double2 y0 = lds128(a0 + c0), y1 = lds128(a0 + c1), y2 = lds128(a1 + c0), y3 = lds128(a1 + c1);
+          double2 z;
+          z.x = br.m[0] * y0.x + br.m[1] * y1.x + br.m[2] * y2.x + br.m[3] * y3.x;
+          z.y = br.m[0] * y0.y + br.m[1] * y1.y + br.m[2] * y2.y + br.m[3] * y3.y;
+          sts128(a0 + c0, z);
+          z.x = br.m[4] * y0.x + br.m[5] * y1.x + br.m[6] * y2.x + br.m[7] * y3.x;
+          z.y = br.m[4] * y0.y + br.m[5] * y1.y + br.m[6] * y2.y + br.m[7] * y3.y;
+          sts128(a0 + c1, z);
+          z.x = br.m[8] * y0.x + br.m[9] * y1.x + br.m[10] * y2.x + br.m[11] * y3.x;
+          z.y = br.m[8] * y0.y + br.m[9] * y1.y + br.m[10] * y2.y + br.m[11] * y3.y;
+          sts128(a1 + c0, z);
+          z.x = br.m[12] * y0.x + br.m[13] * y1.x + br.m[14] * y2.x + br.m[15] * y3.x;
+          z.y = br.m[12] * y0.y + br.m[13] * y1.y + br.m[14] * y2.y + br.m[15] * y3.y;
+          sts128(a1 + c1, z);
+        } else {
+          const int e0 = 2 * (e - nQ4), e1 = e0 + 1;   // alpha singles first, then beta singles
           uint32_t u, v;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sl + (uint32_t)(e + WIN_SLOTS) * 4u));
-          const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16), p0 = tgb + (v & 0xffffu), p1 = tgb + (v >> 16);
-          const double2 y0 = lds128(o0), y1 = lds128(o1), w0 = lds128(p0), w1 = lds128(p1);
-          const bool al = e < nSa, bl = e + WIN_SLOTS < nSa;
-          const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb, c2 = bl ? br.ca : br.cb, s2 = bl ? br.sa : br.sb;
-          sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
-          sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
-          sts128(p0, make_double2(c2 * w0.x - s2 * w1.x, c2 * w0.y - s2 * w1.y));
-          sts128(p1, make_double2(c2 * w1.x + s2 * w0.x, c2 * w1.y + s2 * w0.y));
-        }
-        if (e < nS) {
-          uint32_t u;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e * 4u));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sl + (uint32_t)e0 * 4u));
           const uint32_t o0 = tgb + (u & 0xffffu), o1 = tgb + (u >> 16);
-          const bool al = e < nSa;
-          const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb;
           const double2 y0 = lds128(o0), y1 = lds128(o1);
+          const bool al = e0 < nSa;
+          const double c = al ? br.ca : br.cb, sn = al ? br.sa : br.sb;
+          if (e1 < nS) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sl + (uint32_t)e1 * 4u));
+            const uint32_t p0 = tgb + (v & 0xffffu), p1 = tgb + (v >> 16);
+            const double2 w0 = lds128(p0), w1 = lds128(p1);
+            const bool bl = e1 < nSa;
+            const double c2 = bl ? br.ca : br.cb, s2 = bl ? br.sa : br.sb;
+            sts128(p0, make_double2(c2 * w0.x - s2 * w1.x, c2 * w0.y - s2 * w1.y));
+            sts128(p1, make_double2(c2 * w1.x + s2 * w0.x, c2 * w1.y + s2 * w0.y));
+          }
           sts128(o0, make_double2(c * y0.x - sn * y1.x, c * y0.y - sn * y1.y));
           sts128(o1, make_double2(c * y1.x + sn * y0.x, c * y1.y + sn * y0.y));
         }
