@@ -155,6 +155,11 @@ int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double* in_dev, do
 int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                       double* bra_dev, double* ket_dev, double* grad_host, void* stream);
 
+/* The same sweep over an explicit operator list in execution order (one phase of the re-sharding driver: operators that changed
+ * places commute, which leaves every <bra|T_k|ket> unchanged); grad_host[i] belongs to operator op_list[i]. */
+int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                           double* bra_dev, double* ket_dev, double* grad_host, void* stream);
+
 /* Energy and theta gradient of a unitary product state in one call (_calc_energy_optimization /
  * _calc_gradient_optimization, ups_wavefunction.py:1019-1142): psi = U(theta) ref, *energy_host = <psi|H|psi> with H given by
  * the folded integrals of sq_sigma, grad_host[k] = dE/dtheta_k by the reverse sweep (skipped when grad_host is NULL).

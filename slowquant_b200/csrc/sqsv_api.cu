@@ -1527,20 +1527,56 @@ extern "C" int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double*
   return SQ_ERR_INVALID;
 }
 
+static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order,
+                            const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream);
+
 extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                                  double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
-  SqRange nvtx_range("sq_ups_grad_sweep");
   if (!sp || !lay || lay->sp != sp || !bra_dev || !ket_dev || !grad_host) return SQ_ERR_INVALID;
   const int P = (int)lay->ops.size();
   if (first < 0 || last > P || first > last) return SQ_ERR_INVALID;
+  std::vector<int> order, out_pos((size_t)P, -1);
+  exec_order(first, last, 0, &order);
+  for (int k = first; k < last; ++k) out_pos[k] = k - first;
+  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream);
+}
+
+// The same sweep over an explicit operator list in execution order (one phase of the re-sharding driver; the caller vouches that
+// the order is equivalent to the circuit order -- operators that changed places commute, which leaves every <bra|T_k|ket>
+// unchanged).  grad_host[i] belongs to operator op_list[i].
+extern "C" int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                                      double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+  if (!sp || !lay || lay->sp != sp || !bra_dev || !ket_dev || n_list < 0 || (n_list > 0 && (!op_list || !grad_host || !thetas_host)))
+    return SQ_ERR_INVALID;
+  const int P = (int)lay->ops.size();
+  std::vector<int> order, out_pos((size_t)P, -1);
+  for (int i = 0; i < n_list; ++i) {
+    const int k = op_list[i];
+    if (k < 0 || k >= P || out_pos[k] >= 0) {
+      sq_set_error("sq_ups_grad_sweep_list: operator index %d out of range or repeated", k);
+      return SQ_ERR_INVALID;
+    }
+    const LayoutOp& op = lay->ops[k];
+    if (op.blocked || (op.pair >= 0 && lay->pairs[op.pair].blocked)) {
+      sq_set_error("operator %d moves an alpha electron on a constrained orbital of this space (re-shard first)", k);
+      return SQ_ERR_UNSUPPORTED;
+    }
+    out_pos[k] = i;
+    order.push_back(k);
+  }
+  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream);
+}
+
+static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order,
+                            const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+  SqRange nvtx_range("sq_ups_grad_sweep");
+  const int P = (int)lay->ops.size();
   cudaStream_t st = (cudaStream_t)stream;
   SQ_CUDA(cudaSetDevice(sp->device));
-  for (int k = first; k < last; ++k) grad_host[k - first] = 0.0;
+  for (int k : order) grad_host[out_pos[k]] = 0.0;
   // zero-theta operators still contribute a gradient; only the rotation is skipped.  Plan with all
   // operators (thetas replaced by 1 for the planner), rotations with c=1,s=0 are exact identities.
   std::vector<double> plan_th(P, 1.0);
-  std::vector<int> order;
-  exec_order(first, last, 0, &order);
   std::vector<std::vector<int>> runs;
   plan_runs(lay, order, plan_th.data(), &runs);
   // every launch writes its <bra|T|ket> values into a device array; ONE copy back at the end of the sweep
@@ -1637,7 +1673,7 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
         if (status == SQ_OK) status = sq_launch_gather(sp, op.multi->strings, op.multi->coeffs, ket_dev, sp->d_work[2], 0, st);
         double g = 0.0;
         if (status == SQ_OK) status = sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st);
-        grad_host[k - first] = 2.0 * g;
+        grad_host[out_pos[k]] = 2.0 * g;
         if (status == SQ_OK && std::fabs(thetas_host[k]) >= 1e-28) {
           status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st);
           if (status == SQ_OK) status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st);
@@ -1660,7 +1696,7 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
       for (size_t i = 0; i < n_slot; ++i) {
         double v = 0.0;
         for (int r = 0; r < n_repl; ++r) v += g[(size_t)r * n_slot + i];   // replicas in a fixed order
-        grad_host[slot_op[i] - first] += 2.0 * v;
+        grad_host[out_pos[slot_op[i]]] += 2.0 * v;
       }
     }
   }

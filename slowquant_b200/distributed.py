@@ -571,13 +571,97 @@ def gradient_segments(
     return out
 
 
+def _energy_and_theta_gradient_resharded(
+    sp: "ShardedSpace", reference, th: np.ndarray, ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float
+) -> tuple[float, np.ndarray]:
+    """Energy and theta gradient with every circuit traversal (U, U^dagger, the gradient loop of ups_wavefunction.py:1114-1138) as
+    local phases between re-shards."""
+    lib = _lib.load()
+    types, indices = ups_struct.excitation_operator_type, ups_struct.excitation_indices
+    P = len(types)
+    thp = th.ctypes.data_as(C.POINTER(C.c_double))
+    PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    ket = sp.alloc_state(zero=False)
+    _load_reference(ket, reference)
+    construct_ups_state_sharded(ket, th, ups_struct, reshard=True)
+    bra = sigma_sharded(ket, h_act, g_act, e_core)
+    grad = np.zeros(P)
+    try:
+        energy = dot_sharded(ket, bra)
+        construct_ups_state_sharded(bra, th, ups_struct, dagger=True, reshard=True)
+        _load_reference(ket, reference)
+        phases = reshard_schedule(types, indices, sp.ci_info.num_active_orbs, sp.world)
+        lay = osa.compile_layout(sp.ci_info, ups_struct)
+        lay_B = None
+        if any(name == "B" for name, _ in phases):
+            bra.ensure_layout_B()
+            ket.ensure_layout_B()
+            lay_B = osa.compile_layout(sp.ci_info_B, ups_struct)
+        where = "A"
+        for name, ops in phases:
+            arr = np.asarray(ops, dtype=np.int32)
+            if name == "X":
+                # local in neither layout: one operator through the fused gradient kernel on peer memory (layout A)
+                if where == "B":
+                    _reshard(bra, to_B=False)
+                    _reshard(ket, to_B=False)
+                    where = "A"
+                k = int(arr[0])
+                part = np.zeros(1)
+                torch.cuda.synchronize()
+                sp.barrier()
+                _lib.check(lib.sq_ups_grad_sweep_dist(sp.ci_info._handle, lay, thp, k, k + 1, bra._peer_ptrs, ket._peer_ptrs,
+                                                      part.ctypes.data_as(PD), osa._stream()))
+                torch.cuda.synchronize()
+                sp.barrier()
+                grad[k] = part[0]
+                continue
+            if name != where:
+                _reshard(bra, to_B=(name == "B"))
+                _reshard(ket, to_B=(name == "B"))
+                where = name
+            info, handle, b_buf, k_buf, nloc = (
+                (sp.ci_info, lay, bra.local, ket.local, sp.local_len) if where == "A"
+                else (sp.ci_info_B, lay_B, bra.local_B, ket.local_B, sp.local_len_B)
+            )
+            if nloc:
+                part = np.zeros(len(arr))
+                _lib.check(lib.sq_ups_grad_sweep_list(info._handle, handle, thp, len(arr), arr.ctypes.data_as(PI), osa._ptr(b_buf),
+                                                      osa._ptr(k_buf), part.ctypes.data_as(PD), osa._stream()))
+                grad[arr] = part
+        if sp.world > 1:   # every rank holds the partial sums over its rows
+            t = torch.from_numpy(grad).to(ket.local.device)
+            dist.all_reduce(t)
+            grad = t.cpu().numpy()
+    finally:
+        bra.close()
+        ket.close()
+    return energy, grad
+
+
+def _load_reference(dst: "ShardedState", reference) -> None:
+    """dst <- reference: a sharded vector, or the index of a determinant (e.g. 0 = Hartree-Fock; saves one vector of memory)."""
+    if isinstance(reference, ShardedState):
+        dst.local.copy_(reference.local)
+    else:
+        dst.set_determinant(int(reference))
+
+
 def energy_and_theta_gradient_sharded(
-    reference: ShardedState, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0,
+    reference, thetas: Sequence[float], ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float = 0.0,
     fused_local: bool = True,
     peer_gradient: bool = False,
+    reshard: bool | None = None,
+    space: "ShardedSpace | None" = None,
 ) -> tuple[float, np.ndarray]:
     r"""Energy and :math:`\partial E/\partial\theta_k` of :math:`U(\theta)|\text{reference}\rangle` on an alpha-sharded
-    vector (the theta part of ``_calc_gradient_optimization``, ups_wavefunction.py:1091-1138).  ``reference`` is not modified.
+    vector (the theta part of ``_calc_gradient_optimization``, ups_wavefunction.py:1091-1138).  ``reference`` is not modified; it may
+    also be the index of a determinant together with ``space`` (no reference vector is held: CAS(20,20) on 8 GPUs needs it).
+
+    Default route (``reshard``): state construction, adjoint and the gradient loop all run as the local phases of
+    :func:`reshard_schedule` -- bra and ket are re-sharded together between phases and every phase is one fused
+    ``sq_ups_grad_sweep_list`` on the shards (commuting operators may change places, which leaves every <bra|T_k|ket> unchanged);
+    ONE all-reduce of the gradient at the end.  ``reshard=False`` keeps both vectors in layout A:
 
     Stretches of bricks whose row pairs are all local (on G GPUs: every pair (p, p+1) with p >= log2 G) go through the fused
     single-GPU gradient kernels on the shards plus one all-reduce per stretch; operators that pair rows of two GPUs use the
@@ -585,20 +669,26 @@ def energy_and_theta_gradient_sharded(
     memory (``sq_ups_grad_sweep_dist``).  All three routes are compared with the fused single-GPU call in
     tests/dist_sigma_worker.py; the shift-rule arithmetic is also checked on the CPU against the oracle's literal gradient
     loop (tests/test_distributed_host.py)."""
-    sp = reference.space
+    sp = reference.space if isinstance(reference, ShardedState) else space
+    if sp is None:
+        raise ValueError("a determinant index as reference needs space=")
     types = list(ups_struct.excitation_operator_type)
     P = len(types)
     th = osa._thetas_array(thetas, P)
+    if reshard is None:
+        reshard = sp.reshard_ok and _RESHARD_DEFAULT and fused_local and not peer_gradient
+    if reshard and sp.world > 1 and sp.reshard_ok:
+        return _energy_and_theta_gradient_resharded(sp, reference, th, ups_struct, h_act, g_act, e_core)
     for t in types:
         if t not in _AMPLITUDE_FREQUENCIES:
             raise NotImplementedError(f"theta gradient of sharded vectors: no shift rule for operator type {t}")
     ket = sp.alloc_state(zero=False)
-    ket.local.copy_(reference.local)
+    _load_reference(ket, reference)
     construct_ups_state_sharded(ket, th, ups_struct)
     bra = sigma_sharded(ket, h_act, g_act, e_core)
     energy = dot_sharded(ket, bra)
     construct_ups_state_sharded(bra, th, ups_struct, dagger=True)
-    ket.local.copy_(reference.local)
+    _load_reference(ket, reference)
     tmp = sp.alloc_state(zero=False)
     grad = np.zeros(P)
     probe = np.zeros(P)

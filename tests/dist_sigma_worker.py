@@ -67,14 +67,15 @@ def main():
             e1, g1 = osa.ups_energy_and_gradient(hf, info, th, lay, hamiltonian_0i_0a(h, g, 0, n))
             ref_st = sp.alloc_state()
             ref_st.set_determinant(0)
-            e2, g2 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0)                       # fused local stretches
+            e2, g2 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0)                       # re-sharding phases (default)
+            e5, g5 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0, reshard=False)        # layout A only: fused local stretches
             e3, g3 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0, fused_local=False)    # shift rule everywhere
             e4, g4 = energy_and_theta_gradient_sharded(ref_st, th, lay, h, g, 0.0, peer_gradient=True)   # exchange bricks on peer memory
             ref_st.close()
-            err_g = max(abs(e1 - e2), abs(e1 - e3), abs(e1 - e4), float(np.max(np.abs(g1 - g2))), float(np.max(np.abs(g1 - g3))),
-                        float(np.max(np.abs(g1 - g4)))) / max(1.0, abs(e1))
+            err_g = max(abs(e1 - e2), abs(e1 - e3), abs(e1 - e4), abs(e1 - e5), float(np.max(np.abs(g1 - g2))), float(np.max(np.abs(g1 - g3))),
+                        float(np.max(np.abs(g1 - g4))), float(np.max(np.abs(g1 - g5)))) / max(1.0, abs(e1))
             if rank == 0:
-                print(f"    theta gradient: fused-local {np.max(np.abs(g1 - g2)):.2e}, shift rule {np.max(np.abs(g1 - g3)):.2e}, "
+                print(f"    theta gradient: re-sharded {np.max(np.abs(g1 - g2)):.2e}, fused-local {np.max(np.abs(g1 - g5)):.2e}, shift rule {np.max(np.abs(g1 - g3)):.2e}, "
                       f"peer kernel {np.max(np.abs(g1 - g4)):.2e}", flush=True)
         e = torch.tensor([err, max(err_e, err_g)], dtype=torch.float64, device="cuda")
         dist.all_reduce(e, op=dist.ReduceOp.MAX)

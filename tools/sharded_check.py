@@ -52,7 +52,13 @@ def main():
     dist.barrier()
     dt = time.perf_counter() - t0
     norm2 = dot_sharded(st, st) ** 0.5
-    if len(sys.argv) > 3 and sys.argv[3] in ("energy", "energy-nohf"):
+    tokens = set(sys.argv[3:])
+    if "energy" in tokens:
+        tokens |= {"rdm", "hf"}
+    if "energy-nohf" in tokens:
+        tokens |= {"rdm"}
+    energy = None
+    if tokens & {"rdm", "sigma", "grad"}:
         rng = np.random.default_rng(2024)
         A = rng.normal(size=(n, n))
         h = A + A.T
@@ -60,6 +66,7 @@ def main():
         g = B + B.transpose(1, 0, 2, 3)
         g = g + g.transpose(0, 1, 3, 2)
         g = g + g.transpose(2, 3, 0, 1)
+    if "rdm" in tokens:
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -67,7 +74,7 @@ def main():
         t_rdm = time.perf_counter() - t0
         energy = float(np.sum(h * d1) + 0.5 * np.sum(g * d2))
         hf_msg = ""
-        if sys.argv[3] == "energy":     # second vector + second RDM pass; "energy-nohf" skips it
+        if "hf" in tokens:     # second vector + second RDM pass
             hf = sp.alloc_state()
             hf.set_determinant(0)
             h1, h2 = rdm12_sharded(hf, hf)
@@ -84,7 +91,7 @@ def main():
                 f"max|G1 - G1^T| = {sym:.1e}" + hf_msg,
                 flush=True,
             )
-    if len(sys.argv) > 3 and sys.argv[3] in ("energy", "energy-nohf") and len(sys.argv) > 4 and sys.argv[4] == "sigma":
+    if "sigma" in tokens:
         # <H> once more through H|psi> (sq_sigma_dist: peer gathers + NVLink atomics) -- must equal the RDM route
         from slowquant_b200.distributed import energy_sharded_sigma
 
@@ -94,7 +101,10 @@ def main():
         e_sig = energy_sharded_sigma(st, h, g)
         t_sig = time.perf_counter() - t0
         if rank == 0:
-            print(f"CAS({n},{n}) world={world} sharded sigma + dot: {t_sig:.2f} s;  E_sigma = {e_sig:.12f} (E_sigma - E_RDM = {e_sig - energy:.2e})", flush=True)
+            cmp_msg = f" (E_sigma - E_RDM = {e_sig - energy:.2e})" if energy is not None else ""
+            print(f"CAS({n},{n}) world={world} sharded sigma + dot: {t_sig:.2f} s;  E_sigma = {e_sig:.12f}" + cmp_msg, flush=True)
+        if energy is None:
+            energy = e_sig
     # undo both applications: must return to the HF determinant
     construct_ups_state_sharded(st, th, lay, dagger=True)
     construct_ups_state_sharded(st, th, lay, dagger=True)
@@ -116,6 +126,22 @@ def main():
             flush=True,
         )
     st.close()
+    if "grad" in tokens:
+        # energy + theta gradient of U(theta)|HF> (ups_wavefunction.py:1019-1142) on the sharded vector: state, sigma, adjoint and the
+        # gradient loop as local phases between re-shards.  The HF reference is given by its determinant index (no extra vector).
+        from slowquant_b200.distributed import energy_and_theta_gradient_sharded
+
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        e_g, grad = energy_and_theta_gradient_sharded(0, th, lay, h, g, space=sp)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_g = time.perf_counter() - t0
+        if rank == 0:
+            cmp_msg = f" (E - E_sigma/RDM of the same state = {e_g - energy:.2e})" if energy is not None else ""
+            print(f"CAS({n},{n}) world={world} energy + theta gradient ({lay.n_params} parameters): {t_g:.2f} s;  E = {e_g:.12f}" + cmp_msg +
+                  f";  |grad| = {np.linalg.norm(grad):.10f}  max|grad| = {np.max(np.abs(grad)):.10f}", flush=True)
     dist.destroy_process_group()
 
 
