@@ -572,7 +572,8 @@ def gradient_segments(
 
 
 def _energy_and_theta_gradient_resharded(
-    sp: "ShardedSpace", reference, th: np.ndarray, ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float
+    sp: "ShardedSpace", reference, th: np.ndarray, ups_struct, h_act: np.ndarray, g_act: np.ndarray, e_core: float,
+    timings: dict | None = None,
 ) -> tuple[float, np.ndarray]:
     """Energy and theta gradient with every circuit traversal (U, U^dagger, the gradient loop of ups_wavefunction.py:1114-1138) as
     local phases between re-shards."""
@@ -581,15 +582,27 @@ def _energy_and_theta_gradient_resharded(
     P = len(types)
     thp = th.ctypes.data_as(C.POINTER(C.c_double))
     PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    import time as _time
+
+    def _mark(name, t0):
+        if timings is not None:
+            torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + _time.perf_counter() - t0
+        return _time.perf_counter()
+
+    t0 = _time.perf_counter()
     ket = sp.alloc_state(zero=False)
     _load_reference(ket, reference)
     construct_ups_state_sharded(ket, th, ups_struct, reshard=True)
+    t0 = _mark("state_s", t0)
     bra = sigma_sharded(ket, h_act, g_act, e_core)
     grad = np.zeros(P)
     try:
         energy = dot_sharded(ket, bra)
+        t0 = _mark("sigma_s", t0)
         construct_ups_state_sharded(bra, th, ups_struct, dagger=True, reshard=True)
         _load_reference(ket, reference)
+        t0 = _mark("adjoint_s", t0)
         phases = reshard_schedule(types, indices, sp.ci_info.num_active_orbs, sp.world)
         lay = osa.compile_layout(sp.ci_info, ups_struct)
         lay_B = None
@@ -633,6 +646,7 @@ def _energy_and_theta_gradient_resharded(
             t = torch.from_numpy(grad).to(ket.local.device)
             dist.all_reduce(t)
             grad = t.cpu().numpy()
+        _mark("gradient_sweep_s", t0)
     finally:
         bra.close()
         ket.close()
@@ -653,6 +667,7 @@ def energy_and_theta_gradient_sharded(
     peer_gradient: bool = False,
     reshard: bool | None = None,
     space: "ShardedSpace | None" = None,
+    timings: dict | None = None,
 ) -> tuple[float, np.ndarray]:
     r"""Energy and :math:`\partial E/\partial\theta_k` of :math:`U(\theta)|\text{reference}\rangle` on an alpha-sharded
     vector (the theta part of ``_calc_gradient_optimization``, ups_wavefunction.py:1091-1138).  ``reference`` is not modified; it may
@@ -678,7 +693,7 @@ def energy_and_theta_gradient_sharded(
     if reshard is None:
         reshard = sp.reshard_ok and _RESHARD_DEFAULT and fused_local and not peer_gradient
     if reshard and sp.world > 1 and sp.reshard_ok:
-        return _energy_and_theta_gradient_resharded(sp, reference, th, ups_struct, h_act, g_act, e_core)
+        return _energy_and_theta_gradient_resharded(sp, reference, th, ups_struct, h_act, g_act, e_core, timings)
     for t in types:
         if t not in _AMPLITUDE_FREQUENCIES:
             raise NotImplementedError(f"theta gradient of sharded vectors: no shift rule for operator type {t}")

@@ -134,14 +134,15 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        e_g, grad = energy_and_theta_gradient_sharded(0, th, lay, h, g, space=sp)
+        tm = {}
+        e_g, grad = energy_and_theta_gradient_sharded(0, th, lay, h, g, space=sp, timings=tm)
         torch.cuda.synchronize()
         dist.barrier()
         t_g = time.perf_counter() - t0
         if rank == 0:
-            cmp_msg = f" (E - E_sigma/RDM of the same state = {e_g - energy:.2e})" if energy is not None else ""
-            print(f"CAS({n},{n}) world={world} energy + theta gradient ({lay.n_params} parameters): {t_g:.2f} s;  E = {e_g:.12f}" + cmp_msg +
-                  f";  |grad| = {np.linalg.norm(grad):.10f}  max|grad| = {np.max(np.abs(grad)):.10f}", flush=True)
+            parts = ", ".join(f"{k[:-2]} {v:.2f} s" for k, v in tm.items())
+            print(f"CAS({n},{n}) world={world} energy + theta gradient of U|HF> ({lay.n_params} parameters): {t_g:.2f} s ({parts});  "
+                  f"E = {e_g:.12f};  |grad| = {np.linalg.norm(grad):.10f}  max|grad| = {np.max(np.abs(grad)):.10f}", flush=True)
     dist.destroy_process_group()
 
 
