@@ -317,7 +317,7 @@ def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
         "gradient_sweep_algorithmic_GBps": sweep_gbs,
         "gradient_sweep_frac_of_measured_hbm_peak": sweep_gbs / peak,
         "gradient_norm": float(np.linalg.norm(g_out)),
-        "note": "synthetic symmetric integrals (default_rng(2024)); sigma/RDM are DGEMM-bound (D-panel + cuBLAS fp64), the sweep is HBM-bound",
+        "note": "synthetic symmetric integrals (default_rng(2024)); sigma / RDM: D-panel gathers + hand-written DMMA kernels (fp64 tensor pipe), the sweep is HBM-bound",
     }
 
 
@@ -532,7 +532,7 @@ def run_ours(args) -> None:
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
             if n == 16 and plan[1]:
-                with open(os.path.join(ROOT, "profiles", "r1_win_kernel_traffic.json")) as f:
+                with open(os.path.join(ROOT, "profiles", "r2_win_kernel_traffic.json")) as f:
                     traffic = float(json.load(f)["dram_bytes_per_launch"])
         except Exception:
             traffic = None
@@ -546,7 +546,7 @@ def run_ours(args) -> None:
             "unit": "GB/s",
             "frac": achieved / peak,
             "traffic": traffic,
-            "traffic_source": "ncu --set full capture of win_kernel, profiles/r1_win_kernel_ncu_full_summary.csv" if traffic else None,
+            "traffic_source": "ncu --set full capture of win_kernel, profiles/r2_win_kernel_ncu_full_summary.csv" if traffic else None,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "avg_launch_ms": launch_ms,
             "full_sweep_equiv_GBps": 16.0 * info.num_det / (launch_ms * 1e-3) / 1e9,
