@@ -957,3 +957,32 @@ def test_cas16_bench_config(sq):
         assert np.max(np.abs(got - want)) < 1e-12
     finally:
         sq.lib.check(lib.sq_set_option(b"win", b"1"))
+
+
+@pytest.mark.parametrize("nb_cols,n_rows", [(12870, 37), (924, 200), (35, 50), (40000, 5)])
+def test_reshard_rows_kernel_on_one_device(sq, nb_cols, n_rows):
+    """sq_reshard_rows (the all-to-all step of the sharded engine) as a row permutation on ONE device: bulk-copy engine
+    (cp.async.bulk through shared memory, rows longer and shorter than a chunk, partial last stage) and the vector load/store
+    kernel (odd row length: no 16-byte alignment), bit-exact against torch indexing."""
+    import ctypes as C
+
+    lib = sq.lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(nb_cols)
+    src = torch.randn(n_rows, nb_cols, dtype=torch.float64, device=dev, generator=gen)
+    perm = torch.randperm(n_rows, device=dev, generator=gen).to(torch.int32)
+    rank = torch.zeros(n_rows, dtype=torch.int32, device=dev)
+    try:
+        for mode in (b"tma", b"lsu"):
+            sq.lib.check(lib.sq_set_option(b"reshard", mode))
+            dst = torch.full((n_rows, nb_cols), float("nan"), dtype=torch.float64, device=dev)
+            ptrs = (C.c_void_p * 1)(dst.data_ptr())
+            sq.lib.check(lib.sq_reshard_rows(dev.index, n_rows, nb_cols, C.c_void_p(src.data_ptr()), C.c_void_p(rank.data_ptr()),
+                                             C.c_void_p(perm.data_ptr()), ptrs, 1, None))
+            torch.cuda.synchronize()
+            want = torch.empty_like(src)
+            want[perm.long()] = src
+            assert torch.equal(dst, want), mode
+    finally:
+        sq.lib.check(lib.sq_set_option(b"reshard", b"tma"))
