@@ -262,6 +262,12 @@ int sq_debug_string_action(const sq_space* sp, const int32_t* ops, int n_ops, ui
 /* number of (p, q, spin) for which the table-free record of E_pq (sq_set_option("etab", "alu")) differs from the table the
  * sigma / RDM panel kernels use (built from the closed-form string action above); must be 0. */
 int sq_debug_etab_closed_form(const sq_space* sp, int* n_mismatch);
+/* TEST INFRASTRUCTURE, not a compute path: executes the launch plan of operators [first,last) on a HOST vector, every window
+ * sweep through a host emulation of win3_kernel that shares its tables, step grouping and block algebra.  Lets the CPU tests
+ * check that host logic against the oracle on spaces created with device = -1.  SQ_ERR_UNSUPPORTED if the plan holds anything
+ * but window sweeps.  No function of slowquant_b200/ calls it. */
+int sq_debug_win3_emulate(sq_space* sp, sq_layout* layout, const double* thetas_host, int first, int last, int dagger,
+                          double* host_state);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
 /* number of kernels this library has launched since load (all spaces) */

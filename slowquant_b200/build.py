@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsqsv.so")
 STAMP = os.path.join(CSRC, ".libsqsv.stamp")
-SOURCES = ["sqsv_space.cu", "sqsv_kernels.cu", "sqsv_api.cu", "sqsv_hamiltonian.cu", "sqsv_quad.cu", "sqsv_win.cu", "sqsv_reshard.cu", "sqsv_dmma.cu"]
+SOURCES = ["sqsv_space.cu", "sqsv_kernels.cu", "sqsv_api.cu", "sqsv_hamiltonian.cu", "sqsv_quad.cu", "sqsv_win.cu", "sqsv_win3.cu", "sqsv_reshard.cu", "sqsv_dmma.cu"]
 HEADERS = [os.path.join(CSRC, "sqsv_internal.h"), os.path.join(ROOT, "include", "sqsv.h")]
 
 

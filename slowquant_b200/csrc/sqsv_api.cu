@@ -630,6 +630,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     ++g_plan_version;
     return SQ_OK;
   }
+  if (strcmp(name, "win3") == 0) {   // window sweeps: "1" (default) win3_kernel (orbital-triple register blocks, merged tiles), "0" win_kernel
+    sq_win3_set_enabled(!(value && value[0] == '0'));
+    return SQ_OK;
+  }
   if (strcmp(name, "wingrad") == 0) {
     g_win_grad = (value && value[0] == '0') ? 0 : 1;
     return SQ_OK;
@@ -1478,6 +1482,47 @@ static int ups_apply_order(sq_space* sp, sq_layout* lay, const double* thetas_ho
     }   // states of the batch
   }
   if (in_gauge != ((gauge_flags & 2) != 0)) SQ_CHECK(sq_launch_gauge(sp, state_dev0, st, n_states, state_stride));
+  return SQ_OK;
+}
+
+// TEST INFRASTRUCTURE (no product call reaches it): run the launch plan of operators [first,last) on a HOST vector, every window
+// sweep through the host emulation of win3_kernel (sqsv_win3.cu) -- the same tables, step grouping, expanded item lists and block
+// algebra the kernel uses.  The CPU tests compare the result with the oracle on host-only spaces.  A plan that contains anything
+// but window sweeps is refused.
+extern "C" int sq_debug_win3_emulate(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last, int dagger,
+                                     double* host_state) {
+  if (!sp || !lay || lay->sp != sp || !host_state || !thetas_host) return SQ_ERR_INVALID;
+  const int P = (int)lay->ops.size();
+  if (first < 0 || last > P || first > last) return SQ_ERR_INVALID;
+  std::vector<int> order;
+  exec_order(first, last, dagger, &order);
+  std::vector<std::vector<int>> runs;
+  plan_runs(lay, order, thetas_host, &runs);
+  std::vector<Launch> launches;
+  SQ_CHECK(plan_launches(lay, runs, &launches));
+  for (const Launch& l : launches)
+    if (l.kind != 2) {
+      sq_set_error("sq_debug_win3_emulate: the plan holds a launch that is not a window sweep");
+      return SQ_ERR_UNSUPPORTED;
+    }
+  if (launches.empty()) return SQ_OK;
+  sq_gauge_host(sp, host_state);
+  for (const Launch& l : launches) {
+    int pair_idx[SQ_WIN_MAX_BRICKS], nst[SQ_WIN_MAX_BRICKS], step_op[SQ_MAX_PROGRAM];
+    TileStep wsteps[SQ_WIN_MAX_BRICKS][SQ_MAX_PROGRAM];
+    const TileStep* sptr[SQ_WIN_MAX_BRICKS];
+    int nb = 0;
+    for (int t : l.runs) {
+      SQ_CHECK(run_tile(sp, lay, runs[t], thetas_host, dagger, wsteps[nb], &nst[nb], step_op));
+      pair_idx[nb] = lay->ops[runs[t][0]].pair;
+      sptr[nb] = wsteps[nb];
+      ++nb;
+    }
+    Win3Program P3;
+    SQ_CHECK(sq_win3_program(*l.wt, pair_idx, sptr, nst, nb, &P3));
+    SQ_CHECK(sq_win3_emulate_host(sp, *l.wt, P3, host_state));
+  }
+  sq_gauge_host(sp, host_state);
   return SQ_OK;
 }
 

@@ -280,9 +280,69 @@ struct WinTables {
   int4* d_listidx = nullptr;
   std::vector<int> pair_local;     // layout pair index -> pair id inside the window tables, -1 if unusable
   std::vector<int8_t> eps;         // [3 * local pair] constant signs of Ta, Tb, pair double in the window gauge
+  std::vector<int> pair_lo;        // [local pair] lower orbital of the pair, relative to w0
+  std::vector<char> pair_flip;     // [local pair] 1 if the pair's source orbital i is the upper one
   size_t smem = 0;                 // dynamic shared memory per CTA with SQ_WIN_MAX_BRICKS bricks
   int64_t touched = 0;             // amplitudes per launch (the whole local vector)
+  struct Win3Tables* w3 = nullptr; // tables of win3_kernel (sqsv_win3.cu); nullptr / !ok: the launch uses win_kernel
 };
+// host tables of one spin of a window (built by build_side, sqsv_win.cu)
+struct SideHost {
+  std::vector<int2> groups;          // alpha: {first row, class}; beta: {chunk id, class | tiles << 16}
+  std::vector<int> gbase;            // beta: [chunk][WIN_G]
+  std::vector<int2> cls;             // {count, e_w}
+  std::vector<int> delta;
+  std::vector<std::vector<uint32_t>> wl;   // window parts per electron count, combination order
+  int ncls = 0, LT = 0, max_cnt = 0;
+};
+
+// ---- window kernel, version 3 (sqsv_win3.cu): register blocks over THREE orbitals, merged small tiles ----
+#define W3_MAXLISTS 6      // distinct orbital triples per launch (H - 2 for windows of H <= 8 orbitals)
+#define W3_MAXSTEPS 16
+struct WinBrick {
+  double m[16];            // 4x4 on (x[r][c], x[r][c'], x[r'][c], x[r'][c']), row-major
+  double ca, sa, cb, sb;   // alpha single on (x[r][c], x[r'][c]); beta single on (x[r][c], x[r][c'])
+};
+struct Win3Program {
+  int n_steps, n_lists;
+  int list_t0[W3_MAXLISTS];                  // first window orbital of the triple of list l
+  unsigned char step_list[W3_MAXSTEPS];      // list of step s
+  unsigned char step_first[W3_MAXSTEPS + 1]; // bricks [step_first[s], step_first[s+1]) of `br` run in step s
+  unsigned char brick_lp[SQ_WIN_MAX_BRICKS]; // 0: the brick sits on the lower two orbitals of its triple, 1: on the upper two
+  WinBrick br[SQ_WIN_MAX_BRICKS];
+};
+struct Win3Tables {
+  bool ok = false;
+  int H = 0, LTA = 0, LTB = 0, gp = 16, lanes_j = 0;
+  int lmax = 0;          // largest expanded item list of one (work item, triple)
+  int max_rows = 0, max_chunks = 0, tile_doubles = 0;
+  // host mirrors (launch bookkeeping and the host emulation used by the CPU tests)
+  std::vector<int2> agroups;   // class-major: {first row (shard-relative), class}
+  std::vector<int2> acls;      // {rows of a tile, e_w}
+  std::vector<int> adelta;     // [class][LTA]
+  std::vector<int2> bchunks;   // class-major: {chunk id, class | tiles << 16}
+  std::vector<int> bgbase;     // [chunk id][16] first column of every tile
+  std::vector<int2> bcls;
+  std::vector<int> bdelta;
+  std::vector<int4> work;      // one CTA: {a_first, a_cnt | Ka << 16, b_first, n_chunks | Kb << 16}
+  std::vector<uint2> items;    // x: r0 | r1 << 8 | r2 << 16 | type << 24, y: c0 | c1 << 8 | c2 << 16 (tile-local string ranks)
+  std::vector<int4> itemidx;   // [t0][e_wa][e_wb] {offset, items, counts of types 0..3 (bytes), counts of types 4..7}
+  int2 *d_agroups = nullptr, *d_acls = nullptr, *d_bchunks = nullptr, *d_bcls = nullptr;
+  int *d_adelta = nullptr, *d_bgbase = nullptr, *d_bdelta = nullptr;
+  int4 *d_work = nullptr, *d_itemidx = nullptr;
+  uint2* d_items = nullptr;
+};
+int sq_build_win3(sq_space* sp, struct WinTables* wt, const SideHost& hA, const SideHost& hB);
+void sq_free_win3(Win3Tables* w3);
+int sq_win3_program(const struct WinTables& wt, const int* pair_idx, const struct TileStep* const* steps, const int* n_steps, int n_bricks,
+                    Win3Program* P);
+int sq_launch_win3(sq_space* sp, const struct WinTables& wt, const Win3Program& P, double* state, cudaStream_t st, int n_states,
+                   int64_t state_stride);
+int sq_win3_emulate_host(const sq_space* sp, const struct WinTables& wt, const Win3Program& P, double* host_state);
+void sq_gauge_host(const sq_space* sp, double* host_state);
+void sq_win3_set_enabled(int on);
+bool sq_win3_enabled();
+
 int sq_win_max_class(int n, int ne, int w0, int H);
 size_t sq_win_smem_bytes(int max_a, int max_b, int gp, int nbuf, int lta, int ltb, int maxQ, int maxS, int n_bricks);
 int sq_launch_gauge(sq_space* sp, double* state, cudaStream_t st, int n_states = 1, int64_t state_stride = 0);

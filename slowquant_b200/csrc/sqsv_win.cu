@@ -61,10 +61,6 @@ struct WinDev {
   int tile_doubles, maxQ, maxS;
 };
 
-struct WinBrick {
-  double m[16];            // 4x4 on (x[r][c], x[r][c'], x[r'][c], x[r'][c']), row-major
-  double ca, sa, cb, sb;   // alpha single on (x[r][c], x[r'][c]); beta single on (x[r][c], x[r][c'])
-};
 struct WinProgram {
   int n;
   int pair[SQ_WIN_MAX_BRICKS];
@@ -637,15 +633,6 @@ int sq_win_max_class(int n, int ne, int w0, int H) {
 }
 
 
-struct SideHost {
-  std::vector<int2> groups;          // alpha: {first row, class}; beta: {chunk id, class | tiles << 16}
-  std::vector<int> gbase;            // beta: [chunk][WIN_G]
-  std::vector<int2> cls;             // {count, e_w}
-  std::vector<int> delta;
-  std::vector<std::vector<uint32_t>> wl;   // window parts per electron count, combination order
-  int ncls = 0, LT = 0, max_cnt = 0;
-};
-
 // Tables of one spin.  Returns false (no error) when the window cannot be used with this space / partition.
 static bool build_side(const sq_space* sp, int spin, int w0, int H, SideHost* out) {
   const std::vector<uint32_t>& strs = spin ? sp->strB : sp->strA;
@@ -773,6 +760,7 @@ void sq_free_win_tables(WinTables* wt) {
   cudaFree(wt->d_deltaB);
   cudaFree(wt->d_lists);
   cudaFree(wt->d_listidx);
+  sq_free_win3(wt->w3);
   delete wt;
 }
 
@@ -870,6 +858,10 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
   if (pairs.empty()) return SQ_OK;
   // constant signs of the three generators of every pair in the window gauge
   wt->eps.assign(3 * pairs.size(), 1);
+  for (int p : pairs) {
+    wt->pair_lo.push_back(std::min(lay->pairs[p].i, lay->pairs[p].a) - w0);
+    wt->pair_flip.push_back(lay->pairs[p].i > lay->pairs[p].a ? 1 : 0);
+  }
   for (size_t lp = 0; lp < pairs.size(); ++lp)
     if (!gauge_signs(sp, lay->pairs[pairs[lp]], w0, H, w0, H, &wt->eps[3 * lp])) return SQ_OK;
   SideHost hA, hB;
@@ -987,6 +979,7 @@ int sq_get_win(sq_space* sp, sq_layout* lay, int w0, int H, const WinTables** ou
   wt->n_chunks_b = (int)hB.groups.size();
   wt->n_ranges_b = (int)ranges.size();
   wt->touched = sp->local_len();
+  SQ_CHECK(sq_build_win3(sp, wt, hA, hB));   // tables of win3_kernel (register blocks over orbital triples); wt->w3->ok says whether usable
   if (sp->device >= 0) {
     SQ_CUDA(cudaSetDevice(sp->device));
     SQ_CHECK(win_upload(&wt->d_groupsA, hA.groups));
@@ -1011,6 +1004,11 @@ int sq_launch_win(sq_space* sp, const WinTables& wt, const int* pair_idx, const 
   if (!wt.ok || n_bricks < 1 || n_bricks > SQ_WIN_MAX_BRICKS) {
     sq_set_error("window launch with %d bricks (max %d) or without tables", n_bricks, SQ_WIN_MAX_BRICKS);
     return SQ_ERR_INVALID;
+  }
+  if (wt.w3 && wt.w3->ok && sq_win3_enabled()) {
+    Win3Program P3;
+    SQ_CHECK(sq_win3_program(wt, pair_idx, steps, n_steps, n_bricks, &P3));
+    return sq_launch_win3(sp, wt, P3, state, st, n_states, state_stride);
   }
   WinProgram P;
   P.n = n_bricks;

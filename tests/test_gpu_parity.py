@@ -590,15 +590,17 @@ def test_window_sweeps_equal_single_brick_launches(sq, n, na, nb, L, qnp):
             o = orc.construct_ups_state(x.cpu().numpy(), sp, th, types, idx, threaded=True)
             assert np.max(np.abs(ref.cpu().numpy() - o)) < TOL
         used = 0
-        for cfg in WIN_VARIANTS:
+        # both window kernels: win3_kernel (default: register blocks over orbital triples, merged tiles) and win_kernel
+        for cfg, w3 in [(c, w) for c in WIN_VARIANTS for w in (b"1", b"0")]:
+            sq.lib.check(lib.sq_set_option(b"win3", w3))
             sq.lib.check(lib.sq_set_option(b"win", cfg.encode()))
             stats = (C.c_int64 * 6)()
             sq.lib.check(lib.sq_layout_plan_stats(handle, 0, len(types), stats))
             used += int(stats[1])
             res = sq.osa.construct_ups_state(x, info, th.tolist(), lay)
-            assert float(torch.max(torch.abs(res - ref))) < 1e-13, cfg
+            assert float(torch.max(torch.abs(res - ref))) < 1e-13, (cfg, w3)
             res_d = sq.osa.construct_ups_state(x, info, th.tolist(), lay, dagger=True)
-            assert float(torch.max(torch.abs(res_d - ref_d))) < 1e-13, cfg
+            assert float(torch.max(torch.abs(res_d - ref_d))) < 1e-13, (cfg, w3)
             # a sub-range of the circuit (propagate_unitary-style first/last)
             k0, k1 = 2, len(types) - 1
             part = _layout(sq, types[k0:k1], idx[k0:k1])
@@ -610,6 +612,7 @@ def test_window_sweeps_equal_single_brick_launches(sq, n, na, nb, L, qnp):
         assert used > 0, "no window sweep was planned"
     finally:
         sq.lib.check(lib.sq_set_option(b"win", b"1"))
+        sq.lib.check(lib.sq_set_option(b"win3", b"1"))
 
 
 @pytest.mark.parametrize("n,na,nb,L,qnp", [(8, 4, 4, 2, False), (9, 5, 4, 2, True), (12, 6, 6, 2, False)])
