@@ -630,8 +630,8 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     ++g_plan_version;
     return SQ_OK;
   }
-  if (strcmp(name, "win3") == 0) {   // window sweeps: "1" (default) win3_kernel (orbital-triple register blocks, merged tiles), "0" win_kernel
-    sq_win3_set_enabled(!(value && value[0] == '0'));
+  if (strcmp(name, "win3") == 0) {   // window sweeps: "0" (default) win_kernel, "1" win3_kernel (orbital-triple register blocks, merged tiles; measured slower)
+    sq_win3_set_enabled(value && value[0] == '1');
     return SQ_OK;
   }
   if (strcmp(name, "wingrad") == 0) {
@@ -1019,6 +1019,9 @@ extern "C" int sq_layout_plan_stats(const sq_layout* lay_c, int first, int last,
         fprintf(stderr, "win [%d,%d) smem=%zu :", l.wt->w0, l.wt->w0 + l.wt->H, l.wt->smem);
         for (int t : l.runs) fprintf(stderr, " (%d,%d)", lay->pairs[lay->ops[runs[t][0]].pair].i, lay->pairs[lay->ops[runs[t][0]].pair].a);
         fprintf(stderr, "\n");
+        int pidx[SQ_WIN_MAX_BRICKS], nb = 0;
+        for (int t : l.runs) pidx[nb++] = lay->ops[runs[t][0]].pair;
+        sq_win3_print_stats(*l.wt, pidx, nb);
       } else if (l.kind == 1) {
         fprintf(stderr, "quad\n");
       } else {

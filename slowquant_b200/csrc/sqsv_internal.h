@@ -309,13 +309,13 @@ struct Win3Program {
   unsigned char step_list[W3_MAXSTEPS];      // list of step s
   unsigned char step_first[W3_MAXSTEPS + 1]; // bricks [step_first[s], step_first[s+1]) of `br` run in step s
   unsigned char brick_lp[SQ_WIN_MAX_BRICKS]; // 0: the brick sits on the lower two orbitals of its triple, 1: on the upper two
-  WinBrick br[SQ_WIN_MAX_BRICKS];
+  WinBrick brv[SQ_WIN_MAX_BRICKS][8];        // per brick: one matrix set per item type (orientation of hole groups, row / column items)
 };
 struct Win3Tables {
   bool ok = false;
   int H = 0, LTA = 0, LTB = 0, gp = 16, lanes_j = 0;
   int lmax = 0;          // largest expanded item list of one (work item, triple)
-  int max_rows = 0, max_chunks = 0, tile_doubles = 0;
+  int max_rows = 0, max_cols = 0, max_chunks = 0, tile_doubles = 0;
   // host mirrors (launch bookkeeping and the host emulation used by the CPU tests)
   std::vector<int2> agroups;   // class-major: {first row (shard-relative), class}
   std::vector<int2> acls;      // {rows of a tile, e_w}
@@ -340,6 +340,7 @@ int sq_launch_win3(sq_space* sp, const struct WinTables& wt, const Win3Program& 
                    int64_t state_stride);
 int sq_win3_emulate_host(const sq_space* sp, const struct WinTables& wt, const Win3Program& P, double* host_state);
 void sq_gauge_host(const sq_space* sp, double* host_state);
+void sq_win3_print_stats(const struct WinTables& wt, const int* pair_idx, int n_bricks);
 void sq_win3_set_enabled(int on);
 bool sq_win3_enabled();
 

@@ -40,16 +40,20 @@ static int g_win3_enabled = -1;
 void sq_win3_set_enabled(int on) { g_win3_enabled = on ? 1 : 0; }
 bool sq_win3_enabled() {
   if (g_win3_enabled < 0) {
-    const char* e = getenv("SQ_WIN3");
-    g_win3_enabled = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("SQ_WIN3");   // off by default: measured slower than win_kernel on the B200 (profiles/r2_visit14_ab_win3.txt)
+    g_win3_enabled = (e && e[0] == '1') ? 1 : 0;
   }
   return g_win3_enabled == 1;
 }
 
 // ---------------------------------------------------------------------------------------------
 // The brick on a 3 x 3 block (shared by the kernel and the host emulation).  X[3 * i + j], i = row position, j = column
-// position; double2 = the two tiles of a thread.  Item types: 0..3 full (bit 0: hole rows, bit 1: hole columns), 4..5 row item
-// (bit 0: hole rows; its three columns are inert), 6..7 column item (bit 0: hole columns; its three rows are inert).
+// position; double2 = the two tiles of a thread.  The strings of a group are ordered by the position of the particle (particle
+// groups) or of the hole (hole groups), so a brick on the lower pair of the triple acts on positions (0,1) and a brick on the upper
+// pair on (1,2) of EVERY group: the code is the same for all items.  What differs is the orientation -- in a hole group the source
+// string of a hop (lower orbital occupied) comes second -- and that is folded into the matrices: every brick carries 8 variants,
+// one per item type (0..3 full items, bit 0: hole rows, bit 1: hole columns; 4..5 row items, bit 0: hole rows, the three columns
+// are inert, matrix = R_alpha x 1; 6..7 column items, bit 0: hole columns, matrix = 1 x R_beta).
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ void w3_rot(double2& x0, double2& x1, double c, double s) {
   const double2 a = x0, b = x1;
@@ -58,51 +62,51 @@ __host__ __device__ __forceinline__ void w3_rot(double2& x0, double2& x1, double
   x1.x = c * b.x + s * a.x;
   x1.y = c * b.y + s * a.y;
 }
-template <int PR, int PC>
+template <int P>   // P = 0: positions (0,1) of rows and columns, third position 2; P = 1: positions (1,2), third position 0
 __host__ __device__ __forceinline__ void w3_full(double2* X, const WinBrick& br) {
-  constexpr int PR2 = PR == 0 ? 2 : 0, PC2 = PC == 0 ? 2 : 0;
-  const double2 y0 = X[3 * PR + PC], y1 = X[3 * PR + PC + 1], y2 = X[3 * (PR + 1) + PC], y3 = X[3 * (PR + 1) + PC + 1];
+  constexpr int P2 = P == 0 ? 2 : 0;
+  const double2 y0 = X[3 * P + P], y1 = X[3 * P + P + 1], y2 = X[3 * (P + 1) + P], y3 = X[3 * (P + 1) + P + 1];
   double2 z;
   z.x = br.m[0] * y0.x + br.m[1] * y1.x + br.m[2] * y2.x + br.m[3] * y3.x;
   z.y = br.m[0] * y0.y + br.m[1] * y1.y + br.m[2] * y2.y + br.m[3] * y3.y;
-  X[3 * PR + PC] = z;
+  X[3 * P + P] = z;
   z.x = br.m[4] * y0.x + br.m[5] * y1.x + br.m[6] * y2.x + br.m[7] * y3.x;
   z.y = br.m[4] * y0.y + br.m[5] * y1.y + br.m[6] * y2.y + br.m[7] * y3.y;
-  X[3 * PR + PC + 1] = z;
+  X[3 * P + P + 1] = z;
   z.x = br.m[8] * y0.x + br.m[9] * y1.x + br.m[10] * y2.x + br.m[11] * y3.x;
   z.y = br.m[8] * y0.y + br.m[9] * y1.y + br.m[10] * y2.y + br.m[11] * y3.y;
-  X[3 * (PR + 1) + PC] = z;
+  X[3 * (P + 1) + P] = z;
   z.x = br.m[12] * y0.x + br.m[13] * y1.x + br.m[14] * y2.x + br.m[15] * y3.x;
   z.y = br.m[12] * y0.y + br.m[13] * y1.y + br.m[14] * y2.y + br.m[15] * y3.y;
-  X[3 * (PR + 1) + PC + 1] = z;
-  w3_rot(X[3 * PR + PC2], X[3 * (PR + 1) + PC2], br.ca, br.sa);   // alpha single on the column the brick leaves alone
-  w3_rot(X[3 * PR2 + PC], X[3 * PR2 + PC + 1], br.cb, br.sb);     // beta single on the row it leaves alone
+  X[3 * (P + 1) + P + 1] = z;
+  w3_rot(X[3 * P + P2], X[3 * (P + 1) + P2], br.ca, br.sa);   // alpha single on the column the brick leaves alone
+  w3_rot(X[3 * P2 + P], X[3 * P2 + P + 1], br.cb, br.sb);     // beta single on the row it leaves alone
 }
-template <int PR>
-__host__ __device__ __forceinline__ void w3_rows(double2* X, const WinBrick& br) {
-#pragma unroll
-  for (int j = 0; j < 3; ++j) w3_rot(X[3 * PR + j], X[3 * (PR + 1) + j], br.ca, br.sa);
+// lp: 0 the brick sits on the lower two orbitals of the triple, 1 on the upper two (uniform over the CTA)
+__host__ __device__ __forceinline__ void w3_apply(double2* X, int lp, const WinBrick& br) {
+  if (lp == 0) w3_full<0>(X, br);
+  else w3_full<1>(X, br);
 }
-template <int PC>
-__host__ __device__ __forceinline__ void w3_cols(double2* X, const WinBrick& br) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) w3_rot(X[3 * i + PC], X[3 * i + PC + 1], br.cb, br.sb);
-}
-// lp: 0 the brick sits on the lower two orbitals of the triple, 1 on the upper two
-__host__ __device__ __forceinline__ void w3_apply(double2* X, int type, int lp, const WinBrick& br) {
-  int v;
-  if (type < 4) v = ((lp ^ (type & 1)) << 1) | (lp ^ (type >> 1));
-  else if (type < 6) v = 4 + (lp ^ (type & 1));
-  else v = 6 + (lp ^ (type & 1));
-  switch (v) {
-    case 0: w3_full<0, 0>(X, br); break;
-    case 1: w3_full<0, 1>(X, br); break;
-    case 2: w3_full<1, 0>(X, br); break;
-    case 3: w3_full<1, 1>(X, br); break;
-    case 4: w3_rows<0>(X, br); break;
-    case 5: w3_rows<1>(X, br); break;
-    case 6: w3_cols<0>(X, br); break;
-    default: w3_cols<1>(X, br); break;
+// the 8 variants of a brick; `tm` in the natural orientation (source string = lower orbital occupied)
+static void w3_variants(const WinBrick& tm, WinBrick* out8) {
+  for (int t = 0; t < 8; ++t) {
+    WinBrick& o = out8[t];
+    if (t < 4) {
+      const int fr = t & 1, fc = t >> 1, x = (fr ? 2 : 0) ^ (fc ? 1 : 0);
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) o.m[4 * a + b] = tm.m[4 * (a ^ x) + (b ^ x)];
+      o.ca = tm.ca; o.sa = fr ? -tm.sa : tm.sa; o.cb = tm.cb; o.sb = fc ? -tm.sb : tm.sb;
+    } else {
+      const bool rows = t < 6;
+      const double c = rows ? tm.ca : tm.cb, s0 = rows ? tm.sa : tm.sb, s = (t & 1) ? -s0 : s0;
+      const double R[2][2] = {{c, -s}, {s, c}};
+      for (int ar = 0; ar < 2; ++ar)
+        for (int ac = 0; ac < 2; ++ac)
+          for (int br_ = 0; br_ < 2; ++br_)
+            for (int bc = 0; bc < 2; ++bc)
+              o.m[4 * (2 * ar + ac) + (2 * br_ + bc)] = rows ? (ac == bc ? R[ar][br_] : 0.0) : (ar == br_ ? R[ac][bc] : 0.0);
+      o.ca = rows ? c : 1.0; o.sa = rows ? s : 0.0; o.cb = rows ? 1.0 : c; o.sb = rows ? 0.0 : s;
+    }
   }
 }
 
@@ -137,7 +141,7 @@ struct Win3Dev {
   const int4* work;
   const uint2* items;
   const int4* itemidx;
-  int LTA, LTB, H1, lanes_j, gp, tile_doubles, lmax, max_rows, max_chunks;
+  int LTA, LTB, H1, lanes_j, gp, tile_doubles, lmax, max_rows, max_cols, max_chunks;
 };
 
 __device__ __forceinline__ void w3_cp_async8(uint32_t dst_smem, const double* src) {
@@ -155,27 +159,52 @@ __device__ __forceinline__ void w3_sts128(uint32_t a, double2 v) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
 
-// Shared memory: [tile: NROW x NCOL x gp doubles][expanded items: n_lists x lmax uint4][row table: max_rows]
-// [beta delta: LTB][tile bases: max_chunks x 16][tiles per chunk: max_chunks][items per list: W3_MAXLISTS]
+// Copy table of a merged batch: element x of a tile row -> {column in the vector (-1: no such tile), byte offset in the tile row}.
+// Run windows: the tile index is the fastest index (16 consecutive suffixes = 128 contiguous bytes); the top window: the string
+// rank is the fastest index (the columns of one tile are contiguous).  Shared by the kernel and the host emulation.
+__host__ __device__ __forceinline__ int2 w3_copy_entry(int x, int lanes_j, int Wn, int GP, int mb, int Kb, int nch, const int* sbase,
+                                                       const int* skcnt, const int* sdB) {
+  int kb, gg, j;
+  if (lanes_j) {
+    kb = x / (W3_G * Wn);
+    const int y = x - kb * (W3_G * Wn);
+    gg = y / Wn;
+    j = y - gg * Wn;
+  } else {
+    const int cj = x >> 4;
+    gg = x & 15;
+    kb = cj / Wn;
+    j = cj - kb * Wn;
+  }
+  const int c = mb * Kb + kb;
+  int2 e;
+  e.y = ((kb * Wn + j) * GP + gg) * 8;
+  e.x = (c < nch && gg < skcnt[c]) ? sbase[c * W3_G + gg] + sdB[j] : -1;
+  return e;
+}
+
+// Shared memory: [tile: NROW x NCOL x gp doubles][expanded items: n_lists x lmax uint4][copy table: max_cols x 16 int2]
+// [row table: max_rows][beta delta: LTB][tile bases: max_chunks x 16][tiles per chunk: max_chunks][items per list: W3_MAXLISTS]
 template <int THREADS, bool BATCH>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 2)
 win3_kernel(double* __restrict__ C0, int64_t NB, const Win3Dev W, const __grid_constant__ Win3Program P, int n_states, int64_t state_stride) {
   constexpr int WARPS = THREADS / 32, SLOTS = THREADS / 8;
   extern __shared__ double tile[];
   uint4* const sent = reinterpret_cast<uint4*>(tile + W.tile_doubles);
-  int* const srow = reinterpret_cast<int*>(sent + P.n_lists * W.lmax);
+  int2* const selem = reinterpret_cast<int2*>(sent + P.n_lists * W.lmax);
+  int* const srow = reinterpret_cast<int*>(selem + W.max_cols * W3_G);
   int* const sdB = srow + W.max_rows;
   int* const sbase = sdB + W.LTB;
   int* const skcnt = sbase + W.max_chunks * W3_G;
   int* const slcnt = skcnt + W.max_chunks;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = tid & (W3_G - 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int4 wk = __ldg(W.work + blockIdx.x);
   const int a_first = wk.x, a_cnt = wk.y & 0xffff, Ka = wk.y >> 16, b_first = wk.z, nch = wk.w & 0xffff, Kb = wk.w >> 16;
   const int clsA = __ldg(W.agroups + a_first).y, clsB = __ldg(W.bchunks + b_first).y & 0xffff;
   const int2 ca2 = __ldg(W.acls + clsA), cb2 = __ldg(W.bcls + clsB);
   const int Rn = ca2.x, Wn = cb2.x;
-  const int NROW = Ka * Rn, NCOL = Kb * Wn, GP = W.gp, RS = NCOL * GP;
+  const int NROW = Ka * Rn, NCOL = Kb * Wn, GP = W.gp, RS = NCOL * GP, NE = NCOL * W3_G;
   const int n_mb = (nch + Kb - 1) / Kb;   // merged batches of this CTA
 
   // ---- round trip 1: row table, column offsets, tile bases ----
@@ -192,45 +221,29 @@ win3_kernel(double* __restrict__ C0, int64_t NB, const Win3Dev W, const __grid_c
   __syncthreads();
 
   const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tile);
+  const uint32_t selem_s = (uint32_t)__cvta_generic_to_shared(selem);
+  auto build_copy_table = [&](int mb) {
+    for (int x = tid; x < NE; x += THREADS) selem[x] = w3_copy_entry(x, W.lanes_j, Wn, GP, mb, Kb, nch, sbase, skcnt, sdB);
+  };
   auto issue_loads = [&](int q) {
-    const int mb = BATCH ? q % n_mb : q;
     const double* C = BATCH ? C0 + (int64_t)(q / n_mb) * state_stride : C0;
-    for (int kb = 0; kb < Kb; ++kb) {
-      const int c = mb * Kb + kb;
-      if (c >= nch) break;
-      const int kcnt = skcnt[c];
-      const int* sb = sbase + c * W3_G;
-      const uint32_t tkb = tb + (uint32_t)(kb * Wn * GP) * 8u;
-      if (W.lanes_j) {
-        const int NX = kcnt * Wn;
-        const float invW = 1.0f / (float)Wn;
-        for (int r = warp; r < NROW; r += WARPS) {
-          const int rr = srow[r];
-          if (rr < 0) continue;
-          const double* src = C + (int64_t)rr * NB;
-          const uint32_t dst = tkb + (uint32_t)(r * RS) * 8u;
-          for (int x = lane; x < NX; x += 32) {
-            const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
-            w3_cp_async8(dst + (uint32_t)(j * GP + gg) * 8u, src + sb[gg] + sdB[j]);
-          }
-        }
-      } else if (g < kcnt) {
-        const int myb = sb[g];
-        for (int r = warp; r < NROW; r += WARPS) {
-          const int rr = srow[r];
-          if (rr < 0) continue;
-          const double* src = C + (int64_t)rr * NB + myb;
-          const uint32_t dst = tkb + (uint32_t)(r * RS + g) * 8u;
+    for (int r = warp; r < NROW; r += WARPS) {
+      const int rr = srow[r];
+      if (rr < 0) continue;
+      const double* src = C + (int64_t)rr * NB;
+      const uint32_t dst = tb + (uint32_t)(r * RS) * 8u;
 #pragma unroll 4
-          for (int j = lane >> 4; j < Wn; j += 2) w3_cp_async8(dst + (uint32_t)(j * GP) * 8u, src + sdB[j]);
-        }
+      for (int x = lane; x < NE; x += 32) {
+        int so, dof;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(so), "=r"(dof) : "r"(selem_s + (uint32_t)x * 8u));
+        if (so >= 0) w3_cp_async8(dst + (uint32_t)dof, src + so);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   // ---- round trip 2: the first merged batch, and (meanwhile) the item lists, expanded over (ka, kb) ----
-  issue_loads(0);
+  build_copy_table(0);
   {
     const int K = Ka * Kb, RS2 = RS >> 1, GP2 = GP >> 1;
     for (int l = 0; l < P.n_lists; ++l) {
@@ -250,6 +263,8 @@ win3_kernel(double* __restrict__ C0, int64_t NB, const Win3Dev W, const __grid_c
       if (tid == 0) slcnt[l] = total;
     }
   }
+  __syncthreads();
+  issue_loads(0);
 
   // 8 lanes x 2 tiles per item: every shared-memory access moves 16 bytes per lane, conflict-free
   const int g2 = tid & 7, slot = tid >> 3;
@@ -257,10 +272,9 @@ win3_kernel(double* __restrict__ C0, int64_t NB, const Win3Dev W, const __grid_c
   const uint32_t tgb = tb + (uint32_t)g2 * 16u;
   const int n_total = BATCH ? n_mb * n_states : n_mb;
   for (int q = 0; q < n_total; ++q) {
-    const int mb = BATCH ? q % n_mb : q;
     double* const C = BATCH ? C0 + (int64_t)(q / n_mb) * state_stride : C0;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();   // batch q has landed (and, for q = 0, the item lists are written)
+    __syncthreads();   // batch q has landed
 
     // ---- steps: all bricks of a step between one load and one store of a 3 x 3 block ----
     for (int s = 0; s < P.n_steps; ++s) {
@@ -278,7 +292,7 @@ win3_kernel(double* __restrict__ C0, int64_t NB, const Win3Dev W, const __grid_c
         X[0] = w3_lds128(r0 + c0); X[1] = w3_lds128(r0 + c1); X[2] = w3_lds128(r0 + c2);
         X[3] = w3_lds128(r1 + c0); X[4] = w3_lds128(r1 + c1); X[5] = w3_lds128(r1 + c2);
         X[6] = w3_lds128(r2 + c0); X[7] = w3_lds128(r2 + c1); X[8] = w3_lds128(r2 + c2);
-        for (int b = b0; b < b1; ++b) w3_apply(X, type, P.brick_lp[b], P.br[b]);
+        for (int b = b0; b < b1; ++b) w3_apply(X, P.brick_lp[b], P.brv[b][type]);
         w3_sts128(r0 + c0, X[0]); w3_sts128(r0 + c1, X[1]); w3_sts128(r0 + c2, X[2]);
         w3_sts128(r1 + c0, X[3]); w3_sts128(r1 + c1, X[4]); w3_sts128(r1 + c2, X[5]);
         w3_sts128(r2 + c0, X[6]); w3_sts128(r2 + c1, X[7]); w3_sts128(r2 + c2, X[8]);
@@ -287,39 +301,29 @@ win3_kernel(double* __restrict__ C0, int64_t NB, const Win3Dev W, const __grid_c
     __syncthreads();
 
     // ---- store ----
-    for (int kb = 0; kb < Kb; ++kb) {
-      const int c = mb * Kb + kb;
-      if (c >= nch) break;
-      const int kcnt = skcnt[c];
-      const int* sb = sbase + c * W3_G;
-      const double* tkb = tile + kb * Wn * GP;
-      if (W.lanes_j) {
-        const int NX = kcnt * Wn;
-        const float invW = 1.0f / (float)Wn;
-        for (int r = warp; r < NROW; r += WARPS) {
-          const int rr = srow[r];
-          if (rr < 0) continue;
-          double* dst = C + (int64_t)rr * NB;
-          const double* srct = tkb + r * RS;
-          for (int x = lane; x < NX; x += 32) {
-            const int gg = (int)(((float)x + 0.5f) * invW), j = x - gg * Wn;
-            w3_stg_stream(dst + sb[gg] + sdB[j], srct[j * GP + gg]);
-          }
-        }
-      } else if (g < kcnt) {
-        const int myb = sb[g];
-        for (int r = warp; r < NROW; r += WARPS) {
-          const int rr = srow[r];
-          if (rr < 0) continue;
-          double* dst = C + (int64_t)rr * NB + myb;
-          const double* srct = tkb + r * RS + g;
+    for (int r = warp; r < NROW; r += WARPS) {
+      const int rr = srow[r];
+      if (rr < 0) continue;
+      double* dst = C + (int64_t)rr * NB;
+      const uint32_t srct = tb + (uint32_t)(r * RS) * 8u;
 #pragma unroll 4
-          for (int j = lane >> 4; j < Wn; j += 2) w3_stg_stream(dst + sdB[j], srct[j * GP]);
+      for (int x = lane; x < NE; x += 32) {
+        int so, dof;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(so), "=r"(dof) : "r"(selem_s + (uint32_t)x * 8u));
+        if (so >= 0) {
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(srct + (uint32_t)dof));
+          w3_stg_stream(dst + so, v);
         }
       }
     }
     if (q + 1 < n_total) {
-      __syncthreads();   // the tile buffer is free again
+      __syncthreads();   // the tile buffer and the copy table are free again
+      const int mb1 = BATCH ? (q + 1) % n_mb : q + 1;
+      if (!BATCH || n_mb > 1) {
+        build_copy_table(mb1);
+        __syncthreads();
+      }
       issue_loads(q + 1);
     }
   }
@@ -364,8 +368,8 @@ static void triple_side(const std::vector<uint32_t>& wl, int t0, TripleSide* out
     std::array<int, 3> grp;
     bool complete = true;
     for (int k = 0; k < 3; ++k) {
-      // particle groups: block position k = particle on orbital t0 + k; hole groups: position k = hole on orbital t0 + 2 - k
-      const uint32_t part = (n == 1) ? (1u << (t0 + k)) : (T & ~(1u << (t0 + 2 - k)));
+      // particle groups: block position k = particle on orbital t0 + k; hole groups: position k = hole on orbital t0 + k
+      const uint32_t part = (n == 1) ? (1u << (t0 + k)) : (T & ~(1u << (t0 + k)));
       auto it = pos.find(rest | part);
       if (it == pos.end()) { complete = false; break; }
       grp[k] = it->second;
@@ -467,10 +471,10 @@ int sq_build_win3(sq_space* sp, WinTables* wt, const SideHost& hA, const SideHos
   }
   int TMAX = tmax_env ? tmax_env : (wt->gp == 16 ? 448 : 400);
   TMAX = std::max(TMAX, hA.max_cnt * hB.max_cnt);
-  const int RCAP = 64, CCAP = 64;   // rows / columns of a merged tile (table sizes; 8-bit string ranks stay tile-local)
+  const int RCAP = 64, CCAP = 40;   // rows / columns of a merged tile (table sizes; 8-bit string ranks stay tile-local)
   struct WorkW { int4 w; int64_t weight; };
   std::vector<WorkW> work;
-  int max_rows = 1, max_chunks = 1, lmax = 1, tile_amps = 1;
+  int max_rows = 1, max_cols = 1, max_chunks = 1, lmax = 1, tile_amps = 1;
   for (int ca = 0; ca < hA.ncls; ++ca)
     for (int cb = 0; cb < hB.ncls; ++cb) {
       const int nga = afirst[ca + 1] - afirst[ca], nch = bfirst[cb + 1] - bfirst[cb];
@@ -501,6 +505,7 @@ int sq_build_win3(sq_space* sp, WinTables* wt, const SideHost& hA, const SideHos
         }
       }
       max_rows = std::max(max_rows, Ka * Rn);
+      max_cols = std::max(max_cols, Kb * Wn);
       lmax = std::max(lmax, mi * Ka * Kb);
       tile_amps = std::max(tile_amps, Ka * Rn * Kb * Wn);
     }
@@ -508,6 +513,7 @@ int sq_build_win3(sq_space* sp, WinTables* wt, const SideHost& hA, const SideHos
   std::stable_sort(work.begin(), work.end(), [](const WorkW& a, const WorkW& b) { return a.weight > b.weight; });
   for (const WorkW& x : work) w3->work.push_back(x.w);
   w3->max_rows = (max_rows + 3) & ~3;
+  w3->max_cols = (max_cols + 1) & ~1;
   w3->max_chunks = (max_chunks + 3) & ~3;
   w3->lmax = lmax;
   w3->tile_doubles = tile_amps * wt->gp;   // even
@@ -541,7 +547,7 @@ int sq_build_win3(sq_space* sp, WinTables* wt, const SideHost& hA, const SideHos
 }
 
 static size_t w3_smem_bytes(const Win3Tables& w3, int n_lists) {
-  return sizeof(double) * (size_t)w3.tile_doubles + (size_t)n_lists * w3.lmax * 16 +
+  return sizeof(double) * (size_t)w3.tile_doubles + (size_t)n_lists * w3.lmax * 16 + (size_t)w3.max_cols * W3_G * 8 +
          4 * (size_t)(w3.max_rows + w3.LTB + w3.max_chunks * W3_G + w3.max_chunks + W3_MAXLISTS + 2);
 }
 
@@ -609,7 +615,7 @@ int sq_win3_program(const WinTables& wt, const int* pair_idx, const TileStep* co
       TileMatrices tm;
       const int lp = lpair[j];
       sq_build_tile_matrices3(steps[j], n_steps[j], wt.eps[3 * lp], wt.eps[3 * lp + 1], wt.eps[3 * lp + 2], &tm);
-      WinBrick& br = P->br[nb_out];
+      WinBrick br;
       if (wt.pair_flip[lp]) {
         // the pair's source orbital is the upper one: source and target strings change places in both spins
         for (int a = 0; a < 4; ++a)
@@ -619,6 +625,7 @@ int sq_win3_program(const WinTables& wt, const int* pair_idx, const TileStep* co
         for (int e = 0; e < 16; ++e) br.m[e] = tm.m[e];
         br.ca = tm.ca; br.sa = tm.sa; br.cb = tm.cb; br.sb = tm.sb;
       }
+      w3_variants(br, P->brv[nb_out]);
       P->brick_lp[nb_out] = (unsigned char)(lo[j] - best_t0);
       ++nb_out;
     }
@@ -635,7 +642,7 @@ int sq_launch_win3(sq_space* sp, const WinTables& wt, const Win3Program& P, doub
   W.bchunks = w3.d_bchunks; W.bgbase = w3.d_bgbase; W.bcls = w3.d_bcls; W.bdelta = w3.d_bdelta;
   W.work = w3.d_work; W.items = w3.d_items; W.itemidx = w3.d_itemidx;
   W.LTA = w3.LTA; W.LTB = w3.LTB; W.H1 = w3.H + 1; W.lanes_j = w3.lanes_j; W.gp = w3.gp;
-  W.tile_doubles = w3.tile_doubles; W.lmax = w3.lmax; W.max_rows = w3.max_rows; W.max_chunks = w3.max_chunks;
+  W.tile_doubles = w3.tile_doubles; W.lmax = w3.lmax; W.max_rows = w3.max_rows; W.max_cols = w3.max_cols; W.max_chunks = w3.max_chunks;
   const size_t smem = w3_smem_bytes(w3, P.n_lists);
   if (smem > 220 * 1024) {
     sq_set_error("win3_kernel: %zu bytes of shared memory", smem);
@@ -751,21 +758,39 @@ int sq_win3_emulate_host(const sq_space* sp, const WinTables& wt, const Win3Prog
     }
     for (int mb = 0; mb < n_mb; ++mb) {
       std::fill(tile.begin(), tile.end(), 0.0);
+      // the copy table of the kernel (w3_copy_entry), for both of its lane orders; every tile element exactly once
+      std::vector<int> sbase((size_t)nch * W3_G), skcnt(nch), sdB(Wn);
+      for (int c = 0; c < nch; ++c) {
+        const int2 ch = W.bchunks[b_first + c];
+        skcnt[c] = ch.y >> 16;
+        for (int g = 0; g < W3_G; ++g) sbase[(size_t)c * W3_G + g] = W.bgbase[ch.x * W3_G + g];
+      }
+      for (int j = 0; j < Wn; ++j) sdB[j] = W.bdelta[clsB * W.LTB + j];
+      const int NE = NCOL * W3_G;
+      if (NCOL > W.max_cols) {
+        sq_set_error("win3 emulation: merged tile wider than max_cols");
+        return SQ_ERR_INVALID;
+      }
+      std::vector<int2> selem(NE);
+      std::vector<char> hit((size_t)RS, 0);
+      for (int x = 0; x < NE; ++x) {
+        selem[x] = w3_copy_entry(x, W.lanes_j, Wn, GP, mb, Kb, nch, sbase.data(), skcnt.data(), sdB.data());
+        const int d = selem[x].y / 8;
+        if (selem[x].y % 8 || d < 0 || d >= RS || hit[d]) {
+          sq_set_error("win3 emulation: copy table is not a one-to-one map into the tile row");
+          return SQ_ERR_INVALID;
+        }
+        hit[d] = 1;
+      }
       auto copy = [&](bool load) {
-        for (int kb = 0; kb < Kb; ++kb) {
-          const int c = mb * Kb + kb;
-          if (c >= nch) break;
-          const int2 ch = W.bchunks[b_first + c];
-          const int kcnt = ch.y >> 16;
-          for (int r = 0; r < NROW; ++r) {
-            if (srow[r] < 0) continue;
-            for (int g = 0; g < kcnt; ++g)
-              for (int j = 0; j < Wn; ++j) {
-                double& t = tile[(size_t)r * RS + (size_t)(kb * Wn + j) * GP + g];
-                double& x = C[(int64_t)srow[r] * NB + W.bgbase[ch.x * W3_G + g] + W.bdelta[clsB * W.LTB + j]];
-                if (load) t = x;
-                else x = t;
-              }
+        for (int r = 0; r < NROW; ++r) {
+          if (srow[r] < 0) continue;
+          for (int x = 0; x < NE; ++x) {
+            if (selem[x].x < 0) continue;
+            double& t = tile[(size_t)r * RS + selem[x].y / 8];
+            double& xx = C[(int64_t)srow[r] * NB + selem[x].x];
+            if (load) t = xx;
+            else xx = t;
           }
         }
       };
@@ -790,7 +815,7 @@ int sq_win3_emulate_host(const sq_space* sp, const WinTables& wt, const Win3Prog
                 p[3 * i + j] = tile.data() + byte / 8;
                 X[3 * i + j] = make_double2(p[3 * i + j][0], p[3 * i + j][1]);
               }
-            for (int b = P.step_first[s]; b < P.step_first[s + 1]; ++b) w3_apply(X, type, P.brick_lp[b], P.br[b]);
+            for (int b = P.step_first[s]; b < P.step_first[s + 1]; ++b) w3_apply(X, P.brick_lp[b], P.brv[b][type]);
             for (int q = 0; q < 9; ++q) {
               p[q][0] = X[q].x;
               p[q][1] = X[q].y;
@@ -802,4 +827,42 @@ int sq_win3_emulate_host(const sq_space* sp, const WinTables& wt, const Win3Prog
     }
   }
   return SQ_OK;
+}
+
+// debug (SQ_PLAN_DEBUG): work of one launch counted from the tables -- merged batches, item rounds per CTA slot, brick applications
+void sq_win3_print_stats(const WinTables& wt, const int* pair_idx, int n_bricks) {
+  if (!wt.w3 || !wt.w3->ok) return;
+  TileStep one[1] = {{0, 1.0, 0.0}};
+  const TileStep* sp[SQ_WIN_MAX_BRICKS];
+  int ns[SQ_WIN_MAX_BRICKS];
+  for (int k = 0; k < n_bricks; ++k) { sp[k] = one; ns[k] = 1; }
+  Win3Program P;
+  if (sq_win3_program(wt, pair_idx, sp, ns, n_bricks, &P) != SQ_OK) return;
+  const Win3Tables& W = *wt.w3;
+  const int H1 = W.H + 1;
+  double mbs = 0, rounds = 0, items = 0, full_apps = 0, rc_apps = 0, amps = 0, ideal_items = 0;
+  for (const int4& wk : W.work) {
+    const int a_cnt = wk.y & 0xffff, Ka = wk.y >> 16, nch = wk.w & 0xffff, Kb = wk.w >> 16;
+    const int clsA = W.agroups[wk.x].y, clsB = W.bchunks[wk.z].y & 0xffff;
+    const int Rn = W.acls[clsA].x, Wn = W.bcls[clsB].x, ea = W.acls[clsA].y, eb = W.bcls[clsB].y;
+    const int n_mb = (nch + Kb - 1) / Kb, K = Ka * Kb;
+    double tiles = 0;
+    for (int c = 0; c < nch; ++c) tiles += W.bchunks[wk.z + c].y >> 16;
+    amps += tiles * a_cnt * Rn * Wn;
+    mbs += n_mb;
+    for (int s = 0; s < P.n_steps; ++s) {
+      const int4 hd = W.itemidx[((size_t)P.list_t0[P.step_list[s]] * H1 + ea) * H1 + eb];
+      const int nb = P.step_first[s + 1] - P.step_first[s];
+      const int nfull = (hd.z & 255) + ((hd.z >> 8) & 255) + ((hd.z >> 16) & 255) + ((hd.z >> 24) & 255);
+      const int n = hd.y * K;
+      rounds += (double)n_mb * ((n + 31) / 32);
+      items += (double)n_mb * n;
+      ideal_items += tiles / 16.0 * a_cnt * hd.y;
+      full_apps += (double)n_mb * nfull * K * nb;
+      rc_apps += (double)n_mb * (hd.y - nfull) * K * nb;
+    }
+  }
+  fprintf(stderr, "win3 stats [%d,%d): %d bricks in %d steps, %zu CTAs, %.0f merged batches, %.3g amplitudes; items %.4g (%.4g without merge "
+          "padding), rounds of 32 slots %.4g (slot use %.2f); DP warp instructions %.4g M\n", wt.w0, wt.w0 + wt.H, n_bricks, P.n_steps,
+          W.work.size(), mbs, amps, items, ideal_items, rounds, items / (32.0 * rounds), (full_apps * 48 + rc_apps * 24) * 8 / 32 / 1e6);
 }

@@ -590,7 +590,7 @@ def test_window_sweeps_equal_single_brick_launches(sq, n, na, nb, L, qnp):
             o = orc.construct_ups_state(x.cpu().numpy(), sp, th, types, idx, threaded=True)
             assert np.max(np.abs(ref.cpu().numpy() - o)) < TOL
         used = 0
-        # both window kernels: win3_kernel (default: register blocks over orbital triples, merged tiles) and win_kernel
+        # both window kernels: win_kernel (default) and win3_kernel (register blocks over orbital triples, merged tiles)
         for cfg, w3 in [(c, w) for c in WIN_VARIANTS for w in (b"1", b"0")]:
             sq.lib.check(lib.sq_set_option(b"win3", w3))
             sq.lib.check(lib.sq_set_option(b"win", cfg.encode()))
@@ -612,7 +612,7 @@ def test_window_sweeps_equal_single_brick_launches(sq, n, na, nb, L, qnp):
         assert used > 0, "no window sweep was planned"
     finally:
         sq.lib.check(lib.sq_set_option(b"win", b"1"))
-        sq.lib.check(lib.sq_set_option(b"win3", b"1"))
+        sq.lib.check(lib.sq_set_option(b"win3", b"0"))
 
 
 @pytest.mark.parametrize("n,na,nb,L,qnp", [(8, 4, 4, 2, False), (9, 5, 4, 2, True), (12, 6, 6, 2, False)])
