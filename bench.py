@@ -304,7 +304,14 @@ def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
     sweep()
     ms_sweep = min(sweep() for _ in range(2))
     sweep_gbs = 32.0 * touched / (ms_sweep * 1e-3) / 1e9
+    del bra
+    # one whole evaluation through the call the wave-function object makes (sq_ups_energy_grad: state, sigma, dot, and the
+    # gradient sweep run BACKWARDS from (H|psi>, |psi>) -- no adjoint pass); its gradient against the forward sweep above
+    ms_call, (e_call, g_call) = timed(lambda: osa.ups_energy_and_gradient(ket, info, thetas, lay, H), reps=1)
     return {
+        "energy_and_gradient_call_ms": ms_call,
+        "energy_call_minus_energy_sigma": e_call - energy,
+        "gradient_call_vs_forward_sweep_maxdiff": float(np.max(np.abs(g_call - g_out))),
         "sigma_ms": ms_sigma,
         "rdm12_ms": ms_rdm,
         "energy_sigma": energy,

@@ -162,9 +162,11 @@ int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double* thetas_ho
 
 /* Energy and theta gradient of a unitary product state in one call (_calc_energy_optimization /
  * _calc_gradient_optimization, ups_wavefunction.py:1019-1142): psi = U(theta) ref, *energy_host = <psi|H|psi> with H given by
- * the folded integrals of sq_sigma, grad_host[k] = dE/dtheta_k by the reverse sweep (skipped when grad_host is NULL).
+ * the folded integrals of sq_sigma, grad_host[k] = dE/dtheta_k (skipped when grad_host is NULL) by the sweep of :1114-1138 run
+ * backwards through the circuit from (H psi, psi): g_k = 2 <bra|T_k|ket>, then both vectors <- U_k^dagger (T_k commutes with
+ * its own rotation, so these are the reference's numbers without the adjoint pass U^dagger H psi).
  * work_ket_dev / work_bra_dev: two vectors of the state's length, distinct from ref_dev; on return work_ket_dev holds
- * psi when grad_host is NULL and the swept reference state otherwise. */
+ * psi when grad_host is NULL and psi swept back to the reference state otherwise. */
 int sq_ups_energy_grad(sq_space* sp, sq_layout* lay, const double* thetas_host, double e_core,
                        const double* h_act_host, const double* g_act_host, const double* ref_dev,
                        double* work_ket_dev, double* work_bra_dev, double* energy_host, double* grad_host, void* stream);

@@ -1576,7 +1576,8 @@ extern "C" int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double*
 }
 
 static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order,
-                            const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream);
+                            const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream,
+                            int dagger);
 
 extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                                  double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
@@ -1586,7 +1587,7 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
   std::vector<int> order, out_pos((size_t)P, -1);
   exec_order(first, last, 0, &order);
   for (int k = first; k < last; ++k) out_pos[k] = k - first;
-  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream);
+  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream, 0);
 }
 
 // The same sweep over an explicit operator list in execution order (one phase of the re-sharding driver; the caller vouches that
@@ -1612,11 +1613,15 @@ extern "C" int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double
     out_pos[k] = i;
     order.push_back(k);
   }
-  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream);
+  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream, 0);
 }
 
+// dagger = 1: `order` runs backwards through the circuit and every rotation is undone (theta -> -theta) after its gradient
+// has been taken: the sweep of ups_wavefunction.py:1114-1138 started from (H|psi>, |psi>) instead of (U^d H|psi>, |ref>) --
+// the same numbers <bra_k|T_k|ket_k> (T_k commutes with its own rotation), without the adjoint pass over the circuit.
 static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order,
-                            const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+                            const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream,
+                            int dagger) {
   SqRange nvtx_range("sq_ups_grad_sweep");
   const int P = (int)lay->ops.size();
   cudaStream_t st = (cudaStream_t)stream;
@@ -1646,7 +1651,12 @@ static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_h
   const size_t n_slot = slot_op.size();
   if (n_slot) {
     SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * n_slot * n_repl, st));
-    SQ_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * n_slot * n_repl, st));
+    const cudaError_t e0 = cudaMemsetAsync(d_grad, 0, sizeof(double) * n_slot * n_repl, st);
+    if (e0 != cudaSuccess) {
+      cudaFreeAsync(d_grad, st);
+      sq_set_error("sq_ups_grad_sweep: %s", cudaGetErrorString(e0));
+      return SQ_ERR_CUDA;
+    }
   }
   // the same launch plan as sq_ups_apply: bricks of a window sweep are differentiated and applied inside the sweep
   // (commuting bricks may be reordered: <bra|T_k|ket> does not change); quad launches run as two single bricks
@@ -1670,7 +1680,7 @@ static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_h
   };
   auto tile_program = [&](const std::vector<int>& run, TileStep* steps, int* n_steps) -> int {
     int step_op[SQ_MAX_PROGRAM];
-    SQ_CHECK(run_tile(sp, lay, run, thetas_host, 0, steps, n_steps, step_op));
+    SQ_CHECK(run_tile(sp, lay, run, thetas_host, dagger, steps, n_steps, step_op));
     for (int s = 0; s < *n_steps; ++s)
       if (std::fabs(thetas_host[step_op[s]]) < 1e-28) { steps[s].c = 1.0; steps[s].s = 0.0; }
     return SQ_OK;
@@ -1711,7 +1721,7 @@ static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_h
         continue;
       } else if (op.gen >= 0) {
         const int k = run[0];
-        double th = thetas_host[k];
+        double th = dagger ? -thetas_host[k] : thetas_host[k];
         double c = std::cos(th), s = std::sin(th);
         if (std::fabs(th) < 1e-28) { c = 1.0; s = 0.0; }
         status = sq_launch_gen_grad(sp, lay->gens[op.gen], c, s, bra_dev, ket_dev, d_grad + run_slot0[t], st);
@@ -1723,8 +1733,9 @@ static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_h
         if (status == SQ_OK) status = sq_launch_dot(sp, bra_dev, sp->d_work[2], &g, st);
         grad_host[out_pos[k]] = 2.0 * g;
         if (status == SQ_OK && std::fabs(thetas_host[k]) >= 1e-28) {
-          status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], bra_dev, st);
-          if (status == SQ_OK) status = sa_double_poly(sp, *op.multi, op.type, thetas_host[k], ket_dev, st);
+          const double th = dagger ? -thetas_host[k] : thetas_host[k];
+          status = sa_double_poly(sp, *op.multi, op.type, th, bra_dev, st);
+          if (status == SQ_OK) status = sa_double_poly(sp, *op.multi, op.type, th, ket_dev, st);
         }
       } else {
         sq_set_error("sq_ups_grad_sweep: operator %d has no generator", run[0]);
@@ -1795,11 +1806,18 @@ extern "C" int sq_ups_grad_sweep_dist(sq_space* sp, sq_layout* lay, const double
   }
   unsigned long long* d_tabs = nullptr;
   double* d_grad = nullptr;
-  SQ_CUDA(cudaMallocAsync(&d_tabs, sizeof(tabs), st));
-  SQ_CUDA(cudaMemcpyAsync(d_tabs, tabs, sizeof(tabs), cudaMemcpyHostToDevice, st));
-  SQ_CUDA(cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st));
-  SQ_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * slot_op.size(), st));
   int status = SQ_OK;
+  {
+    // both buffers are released on every exit path (the frees at the end of the function see whatever was allocated)
+    cudaError_t e = cudaMallocAsync(&d_tabs, sizeof(tabs), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tabs, tabs, sizeof(tabs), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_grad, sizeof(double) * slot_op.size(), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_grad, 0, sizeof(double) * slot_op.size(), st);
+    if (e != cudaSuccess) {
+      sq_set_error("sq_ups_grad_sweep_dist: %s", cudaGetErrorString(e));
+      status = SQ_ERR_CUDA;
+    }
+  }
   for (size_t ri = 0; ri < runs.size() && status == SQ_OK; ++ri) {
     const std::vector<int>& run = runs[ri];
     const LayoutOp& op = lay->ops[run[0]];
@@ -1826,8 +1844,8 @@ extern "C" int sq_ups_grad_sweep_dist(sq_space* sp, sq_layout* lay, const double
       for (size_t i = 0; i < g.size(); ++i) grad_host[slot_op[i] - first] += 2.0 * g[i];
     }
   }
-  cudaFreeAsync(d_grad, st);
-  cudaFreeAsync(d_tabs, st);
+  if (d_grad) cudaFreeAsync(d_grad, st);
+  if (d_tabs) cudaFreeAsync(d_tabs, st);
   return status;
 }
 
@@ -1878,9 +1896,11 @@ extern "C" int sq_ups_energy_grad(sq_space* sp, sq_layout* lay, const double* th
   SQ_CHECK(sq_sigma(sp, e_core, h_act_host, g_act_host, work_ket_dev, work_bra_dev, stream));        // H|psi>
   SQ_CHECK(sq_dot(sp, work_ket_dev, work_bra_dev, energy_host, stream));
   if (!grad_host) return SQ_OK;
-  SQ_CHECK(sq_ups_apply(sp, lay, thetas_host, 0, P, 1, work_bra_dev, stream));                       // U^d H|psi>
-  SQ_CUDA(cudaMemcpyAsync(work_ket_dev, ref_dev, bytes, cudaMemcpyDeviceToDevice, st));
-  return sq_ups_grad_sweep(sp, lay, thetas_host, 0, P, work_bra_dev, work_ket_dev, grad_host, stream);
+  // backwards through the circuit from (H|psi>, |psi>): no adjoint pass (one state construction less per evaluation)
+  std::vector<int> order, out_pos((size_t)P, -1);
+  exec_order(0, P, 1, &order);
+  for (int k = 0; k < P; ++k) out_pos[k] = k;
+  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, work_bra_dev, work_ket_dev, grad_host, stream, 1);
 }
 
 extern "C" int sq_dot(sq_space* sp, const double* a_dev, const double* b_dev, double* out_host, void* stream) {

@@ -429,8 +429,9 @@ def ups_energy_and_gradient(
     want_gradient: bool = True,
 ) -> tuple[float, np.ndarray | None]:
     r"""Energy and analytic theta gradient of :math:`U(\theta)|\text{ref}\rangle` in ONE library call
-    (``sq_ups_energy_grad``: state construction, sigma build, adjoint sweep and the fused reverse gradient sweep of
-    ups_wavefunction.py:1019-1142 stay on the device; only the scalar and the gradient come back)."""
+    (``sq_ups_energy_grad``: state construction, sigma build and the fused gradient sweep of ups_wavefunction.py:1019-1142,
+    run backwards through the circuit from (H|psi>, |psi>) so that no adjoint pass is needed, stay on the device; only the scalar
+    and the gradient come back)."""
     lib = _lib.load()
     lay = compile_layout(ci_info, ups_struct)
     n = len(ups_struct.excitation_operator_type)
