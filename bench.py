@@ -306,12 +306,23 @@ def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
     sweep_gbs = 32.0 * touched / (ms_sweep * 1e-3) / 1e9
     del bra
     # one whole evaluation through the call the wave-function object makes (sq_ups_energy_grad: state, sigma, dot, and the
-    # gradient sweep run BACKWARDS from (H|psi>, |psi>) -- no adjoint pass); its gradient against the forward sweep above
+    # gradient sweep run BACKWARDS from (H|psi>, |psi>) -- no adjoint pass), checked at size against the step-by-step route
+    # psi = U|HF>, E = <psi|H|psi>, forward sweep from (U^d H psi, |HF>)
     ms_call, (e_call, g_call) = timed(lambda: osa.ups_energy_and_gradient(ket, info, thetas, lay, H), reps=1)
+    psi = osa.construct_ups_state(ket, info, thetas, lay)
+    hpsi = osa.propagate_state([H], psi, info)
+    e_steps = float(torch.dot(psi, hpsi))
+    del psi
+    bra = osa.construct_ups_state(hpsi, info, thetas, lay, dagger=True)
+    del hpsi
+    sweep()
+    g_steps = g_out.copy()
+    del bra
     return {
         "energy_and_gradient_call_ms": ms_call,
-        "energy_call_minus_energy_sigma": e_call - energy,
-        "gradient_call_vs_forward_sweep_maxdiff": float(np.max(np.abs(g_call - g_out))),
+        "energy_call_minus_stepwise": e_call - e_steps,
+        "gradient_call_vs_forward_sweep_maxdiff": float(np.max(np.abs(g_call - g_steps))),
+        "gradient_call_norm": float(np.linalg.norm(g_call)),
         "sigma_ms": ms_sigma,
         "rdm12_ms": ms_rdm,
         "energy_sigma": energy,
