@@ -579,6 +579,7 @@ static int get_quad(sq_layout* lay, int pA, int pB, const QuadTables** out) {
 
 static int g_plan_version = 0;   // bumped by sq_set_option: cached plans of older versions are dropped
 static int g_win_grad = 0;       // sq_set_option("wingrad", "1"): gradient sweep through the window kernel
+static int g_quad_grad = 1;      // sq_set_option("quadgrad", "0"): one brick per launch in the gradient sweep (no quad_grad_kernel)
 
 struct WinConfig {
   bool enabled = true;
@@ -636,6 +637,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
   }
   if (strcmp(name, "wingrad") == 0) {
     g_win_grad = (value && value[0] == '0') ? 0 : 1;
+    return SQ_OK;
+  }
+  if (strcmp(name, "quadgrad") == 0) {   // gradient sweep: "1" (default) two commuting bricks per launch, "0" one brick per launch
+    g_quad_grad = (value && value[0] == '0') ? 0 : 1;
     return SQ_OK;
   }
   if (strcmp(name, "wingrad_win") == 0) {   // window configuration of the gradient sweep (SQ_WIN syntax)
@@ -1667,8 +1672,27 @@ static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_h
   } else {
     // default: one fused brick per launch (tile_grad_kernel_v2 runs at 0.7 of the HBM roofline; the window gradient
     // kernel is correct but not yet faster per brick)
-    launches.resize(runs.size());
-    for (size_t ri = 0; ri < runs.size(); ++ri) launches[ri].runs = {(int)ri};
+    // two consecutive bricks on disjoint orbital pairs share one launch (quad_grad_kernel: one read + one write of bra and ket
+    // for both bricks; every half layer of a tUPS brick wall is such a set)
+    for (size_t ri = 0; ri < runs.size();) {
+      Launch l;
+      l.runs = {(int)ri};
+      if (g_quad_grad && quad_enabled() && ri + 1 < runs.size()) {
+        const LayoutOp &o1 = lay->ops[runs[ri][0]], &o2 = lay->ops[runs[ri + 1][0]];
+        if (is_tile_op(o1) && is_tile_op(o2) && o1.pair != o2.pair) {
+          const QuadTables* qt = nullptr;
+          status = get_quad(lay, o1.pair, o2.pair, &qt);
+          if (status != SQ_OK) break;
+          if (qt && qt->ok) {
+            l.kind = 1;
+            l.runs.push_back((int)ri + 1);
+            l.qt = qt;
+          }
+        }
+      }
+      ri += l.runs.size();
+      launches.push_back(l);
+    }
   }
   bool in_gauge = false;
   auto set_gauge = [&](bool want) -> int {
@@ -1707,6 +1731,18 @@ static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_h
     }
     status = set_gauge(false);
     if (status != SQ_OK) break;
+    if (l.kind == 1) {
+      TileStep s1[SQ_MAX_PROGRAM], s2[SQ_MAX_PROGRAM];
+      int n1 = 0, n2 = 0;
+      const int t1 = l.runs[0], t2 = l.runs[1];
+      status = tile_program(runs[t1], s1, &n1);
+      if (status == SQ_OK) status = tile_program(runs[t2], s2, &n2);
+      if (status == SQ_OK)
+        status = sq_launch_quad_grad(sp, *l.qt, s1, n1, lay->pairs[lay->ops[runs[t1][0]].pair].sigma, s2, n2,
+                                     lay->pairs[lay->ops[runs[t2][0]].pair].sigma, bra_dev, ket_dev, d_grad + run_slot0[t1],
+                                     d_grad + run_slot0[t2], st);
+      continue;
+    }
     for (int t : l.runs) {
       if (status != SQ_OK) break;
       const std::vector<int>& run = runs[t];

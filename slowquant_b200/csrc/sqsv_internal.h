@@ -359,6 +359,9 @@ int sq_launch_tile(sq_space* sp, const PairTables& pt, const TileStep* steps, in
                    double* state, const PeerPtrs* peers, cudaStream_t st);
 int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, int n1, int sigma1,
                    const TileStep* steps2, int n2, int sigma2, double* state, cudaStream_t st);
+int sq_launch_quad_grad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, int n1, int sigma1, const TileStep* steps2,
+                        int n2, int sigma2, double* bra, double* ket, double* d_out1, double* d_out2, cudaStream_t st);
+int sq_reduce_partials(const double* partial, int64_t nblocks, int ns, int n_out, double* out, cudaStream_t st);
 int sq_launch_tile_grad(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps,
                         double* bra, double* ket, double* grad_out_host, cudaStream_t st);
 int sq_launch_tile_grad_peer(sq_space* sp, const PairTables& pt, const TileStep* steps, int n_steps, double* bra, double* ket,

@@ -636,6 +636,18 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   }
 }
 
+// out[k] = sum over blocks of partial[b * ns + k], k < n_out (fixed order: deterministic)
+int sq_reduce_partials(const double* partial, int64_t nblocks, int ns, int n_out, double* out, cudaStream_t st) {
+  if (n_out < 1) return SQ_OK;
+  reduce_partials_kernel<<<n_out, 256, 0, st>>>(partial, nblocks, ns, out, 1.0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("reduce_partials_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  return SQ_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Generic excitation generator G (one ladder string, disjoint annihilated / created sets; single ..
 // sextuple of reference operators.py:145-359): exp(theta (G - G^dagger)) is a Givens rotation on every

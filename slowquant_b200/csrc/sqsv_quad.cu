@@ -288,6 +288,217 @@ quad_kernel(double* __restrict__ C, const int4* __restrict__ colIdx, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gradient sweep on quad tiles: the SAME tiles for two vectors (bra, ket).  For every rotation step of brick 1 and then of
+// brick 2 (reference ups_wavefunction.py:1114-1138): accumulate <bra|T_step|ket> on the tile, then rotate both vectors.  The two
+// bricks commute and map every quad tile onto itself, so "brick 2 after brick 1" holds tile by tile.  One read + one write of
+// bra and ket for SIX ansatz operators (tile_grad_kernel_v2: one per three).  Gauge flips as in quad_apply: inside a brick's
+// 4-amplitude group every alpha / beta generator element is +1 (sigma on the pair double, folded into GradSteps::sig / s).
+// ---------------------------------------------------------------------------------------------
+struct GradSteps {
+  int n;
+  int kind[SQ_MAX_PROGRAM];
+  double c[SQ_MAX_PROGRAM], s[SQ_MAX_PROGRAM], sig[SQ_MAX_PROGRAM];
+};
+struct QuadGradProg { GradSteps g1, g2; };
+
+__device__ __forceinline__ void qgrad_pair(double& bs, double& bt, double& ks, double& kt, double c, double s, double sig, double& acc) {
+  acc += sig * (bt * ks - bs * kt);
+  const double a = bs, b = bt, p = ks, q = kt;
+  bs = c * a - s * b;
+  bt = c * b + s * a;
+  ks = c * p - s * q;
+  kt = c * q + s * p;
+}
+
+// One brick of a quad tile, differentiated step by step.  PAIR1 = true: the brick acts on the (a1, b1) index for every (a2, b2);
+// false: on (a2, b2) for every (a1, b1).  RA / CA: the row / column group is active in this brick's pair.  The step loop is NOT
+// unrolled (the fully unrolled version had 30 000 instructions for the 16 tile shapes and lived in instruction-cache misses);
+// the value of step s is added to this thread's accumulator in shared memory (acc[s * QUAD_THREADS]): 32 registers less than
+// sixteen register accumulators.
+template <bool R1, bool R2, bool C1, bool C2, bool PAIR1>
+__device__ __forceinline__ void quad_grad_brick(double* __restrict__ xb, double* __restrict__ xk, const int rfl, const int cfl,
+                                                const GradSteps& gs, double* __restrict__ acc) {
+  using S = Shape<R1, R2, C1, C2>;
+  constexpr bool RA = PAIR1 ? R1 : R2, CA = PAIR1 ? C1 : C2;
+  if (!RA && !CA) return;
+  constexpr int NO_R = PAIR1 ? S::NR2 : S::NR1, NO_C = PAIR1 ? S::NC2 : S::NC1;   // sizes of the OTHER pair's indices
+  constexpr int HR = RA ? 1 : 0, KC = CA ? 1 : 0;
+  auto at = [](int r, int ro, int c, int co) { return PAIR1 ? S::at(r, ro, c, co) : S::at(ro, r, co, c); };
+  const int sSa = rfl & 1, cra = (rfl >> 1) & 1, crap = (rfl >> 2) & 1;
+  const int sSb = cfl & 1, crb = (cfl >> 1) & 1;
+  const int g10 = sSa ^ crb, g01 = sSb ^ cra, g11 = g10 ^ sSb ^ crap;
+  auto flips = [&]() {
+#pragma unroll
+    for (int ro = 0; ro < NO_R; ++ro)
+#pragma unroll
+      for (int co = 0; co < NO_C; ++co) {
+        if (RA && CA) {
+          xb[at(0, ro, 1, co)] = qflip(xb[at(0, ro, 1, co)], g01); xk[at(0, ro, 1, co)] = qflip(xk[at(0, ro, 1, co)], g01);
+          xb[at(1, ro, 0, co)] = qflip(xb[at(1, ro, 0, co)], g10); xk[at(1, ro, 0, co)] = qflip(xk[at(1, ro, 0, co)], g10);
+          xb[at(1, ro, 1, co)] = qflip(xb[at(1, ro, 1, co)], g11); xk[at(1, ro, 1, co)] = qflip(xk[at(1, ro, 1, co)], g11);
+        } else if (RA) {
+          xb[at(1, ro, 0, co)] = qflip(xb[at(1, ro, 0, co)], g10); xk[at(1, ro, 0, co)] = qflip(xk[at(1, ro, 0, co)], g10);
+        } else {
+          xb[at(0, ro, 1, co)] = qflip(xb[at(0, ro, 1, co)], g01); xk[at(0, ro, 1, co)] = qflip(xk[at(0, ro, 1, co)], g01);
+        }
+      }
+  };
+  flips();
+#pragma unroll 1
+  for (int s = 0; s < gs.n; ++s) {
+    const int kind = gs.kind[s];
+    const double c = gs.c[s], sn = gs.s[s], sg = gs.sig[s];
+    double a = 0.0;
+    if (kind == 0) {
+      if (RA) {
+#pragma unroll
+        for (int ro = 0; ro < NO_R; ++ro)
+#pragma unroll
+          for (int co = 0; co < NO_C; ++co)
+#pragma unroll
+            for (int cc = 0; cc <= KC; ++cc)
+              qgrad_pair(xb[at(0, ro, cc, co)], xb[at(HR, ro, cc, co)], xk[at(0, ro, cc, co)], xk[at(HR, ro, cc, co)], c, sn, 1.0, a);
+      }
+    } else if (kind == 1) {
+      if (CA) {
+#pragma unroll
+        for (int ro = 0; ro < NO_R; ++ro)
+#pragma unroll
+          for (int co = 0; co < NO_C; ++co)
+#pragma unroll
+            for (int rr = 0; rr <= HR; ++rr)
+              qgrad_pair(xb[at(rr, ro, 0, co)], xb[at(rr, ro, KC, co)], xk[at(rr, ro, 0, co)], xk[at(rr, ro, KC, co)], c, sn, 1.0, a);
+      }
+    } else {
+      if (RA && CA) {
+#pragma unroll
+        for (int ro = 0; ro < NO_R; ++ro)
+#pragma unroll
+          for (int co = 0; co < NO_C; ++co)
+            qgrad_pair(xb[at(0, ro, 0, co)], xb[at(HR, ro, KC, co)], xk[at(0, ro, 0, co)], xk[at(HR, ro, KC, co)], c, sn, sg, a);
+      }
+    }
+    acc[s * QUAD_THREADS] += a;   // this thread's accumulator of step s (shared memory, one column per thread: no bank conflicts)
+  }
+  flips();
+}
+
+template <bool R1, bool R2, bool C1, bool C2>
+__device__ __forceinline__ void quad_grad_apply(double* __restrict__ xb, double* __restrict__ xk, const int rf, const int cf,
+                                                const QuadGradProg& qp, double* __restrict__ acc) {
+  quad_grad_brick<R1, R2, C1, C2, true>(xb, xk, rf & 7, cf & 7, qp.g1, acc);
+  quad_grad_brick<R1, R2, C1, C2, false>(xb, xk, (rf >> 4) & 7, (cf >> 4) & 7, qp.g2, acc + SQ_MAX_PROGRAM * QUAD_THREADS);
+}
+
+template <bool R1, bool R2, bool C1, bool C2>
+__device__ __forceinline__ void quad_rows_grad(double* __restrict__ BRA, double* __restrict__ KET, int64_t NB,
+                                               const int4* __restrict__ rowIdx, const int* __restrict__ rowFlags, int64_t r0,
+                                               const int4 cl, const int cf, const QuadGradProg& qp, double* __restrict__ acc) {
+  using S = Shape<R1, R2, C1, C2>;
+  constexpr int TILE = S::TILE;
+  constexpr int GH = S::G > 1 ? S::G / 2 : 1;   // 8 amplitudes of each vector in flight per thread (16 for the 4 x 4 tile)
+  constexpr int NBATCH = QUAD_ROWS / GH;
+#pragma unroll 1
+  for (int b = 0; b < NBATCH; ++b) {
+    int4 rw[GH];
+    double xb[GH][TILE], xk[GH][TILE];
+#pragma unroll
+    for (int g = 0; g < GH; ++g) rw[g] = __ldg(rowIdx + r0 + b * GH + g);
+#pragma unroll
+    for (int g = 0; g < GH; ++g)
+      if (rw[g].x >= 0) {
+        quad_load<R1, R2, C1, C2>(BRA, NB, rw[g], cl, xb[g]);
+        quad_load<R1, R2, C1, C2>(KET, NB, rw[g], cl, xk[g]);
+      }
+#pragma unroll
+    for (int g = 0; g < GH; ++g)
+      if (rw[g].x >= 0) {
+        quad_grad_apply<R1, R2, C1, C2>(xb[g], xk[g], __ldg(rowFlags + r0 + b * GH + g), cf, qp, acc);
+        quad_store<R1, R2, C1, C2>(BRA, NB, rw[g], cl, xb[g]);
+        quad_store<R1, R2, C1, C2>(KET, NB, rw[g], cl, xk[g]);
+      }
+  }
+}
+
+#define QGRAD_NS (2 * SQ_MAX_PROGRAM)
+template <int MINB>
+__global__ void __launch_bounds__(QUAD_THREADS, MINB)
+quad_grad_kernel(double* __restrict__ BRA, double* __restrict__ KET, const int4* __restrict__ colIdx, const int* __restrict__ colFlags,
+                 const int4* __restrict__ rowIdx, const int* __restrict__ rowFlags, int64_t NB, const QuadBounds qb,
+                 const QuadGradProg qp, double* __restrict__ partial) {
+  __shared__ double sacc[QGRAD_NS * QUAD_THREADS];   // [step value][thread]
+  double* const acc = sacc + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < QGRAD_NS; ++k) acc[k * QUAD_THREADS] = 0.0;
+  const int bx = blockIdx.x, by = blockIdx.y;
+  const int ct = bx < qb.c3 ? 3 : (bx < qb.c2 ? 2 : (bx < qb.c1 ? 1 : 0));
+  const int rt = by < qb.r3 ? 3 : (by < qb.r2 ? 2 : (by < qb.r1 ? 1 : 0));
+  const int64_t ci = (int64_t)bx * QUAD_THREADS + threadIdx.x;
+  const int4 cl = __ldg(colIdx + ci);
+  if ((ct != 0 || rt != 0) && cl.x >= 0) {
+    const int cf = __ldg(colFlags + ci);
+    const int64_t r0 = (int64_t)by * QUAD_ROWS;
+    switch (rt * 4 + ct) {
+      case 15: quad_rows_grad<true, true, true, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 14: quad_rows_grad<true, true, true, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 13: quad_rows_grad<true, true, false, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 12: quad_rows_grad<true, true, false, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 11: quad_rows_grad<true, false, true, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 10: quad_rows_grad<true, false, true, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 9: quad_rows_grad<true, false, false, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 8: quad_rows_grad<true, false, false, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 7: quad_rows_grad<false, true, true, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 6: quad_rows_grad<false, true, true, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 5: quad_rows_grad<false, true, false, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 4: quad_rows_grad<false, true, false, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 3: quad_rows_grad<false, false, true, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 2: quad_rows_grad<false, false, true, false>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      case 1: quad_rows_grad<false, false, false, true>(BRA, KET, NB, rowIdx, rowFlags, r0, cl, cf, qp, acc); break;
+      default: break;
+    }
+  }
+  // deterministic block sum of the 16 step values: warp shuffles, then one thread per value adds the warps in order
+  __shared__ double sm[QGRAD_NS][QUAD_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < QGRAD_NS; ++k) {
+    double v = acc[k * QUAD_THREADS];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) sm[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < QGRAD_NS) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < QUAD_THREADS / 32; ++w) v += sm[threadIdx.x][w];
+    // value-major layout: the reduction kernel reads one contiguous run per step value
+    partial[(int64_t)threadIdx.x * ((int64_t)gridDim.x * gridDim.y) + ((int64_t)by * gridDim.x + bx)] = v;
+  }
+}
+
+// out1[k] = sum over CTAs of value k (k < n1), out2[k] = sum of value SQ_MAX_PROGRAM + k (k < n2); one block per value, fixed
+// order of additions (deterministic)
+__global__ void __launch_bounds__(256) quad_grad_reduce_kernel(const double* __restrict__ partial, int64_t nblocks, int n1,
+                                                              double* __restrict__ out1, double* __restrict__ out2) {
+  const int j = blockIdx.x, k = j < n1 ? j : SQ_MAX_PROGRAM + (j - n1);
+  const double* p = partial + (int64_t)k * nblocks;
+  double v = 0.0;
+  for (int64_t b = threadIdx.x; b < nblocks; b += 256) v += p[b];
+  __shared__ double sm[8];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    if (j < n1) out1[j] = t;
+    else out2[j - n1] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: work lists
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -484,5 +695,66 @@ int sq_launch_quad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, i
     return SQ_ERR_CUDA;
   }
   g_sq_launches.fetch_add(1);
+  return SQ_OK;
+}
+
+static void grad_steps(const TileStep* steps, int n, int sigma, GradSteps* gs) {
+  gs->n = n;
+  for (int k = 0; k < SQ_MAX_PROGRAM; ++k) {
+    const bool on = k < n;
+    const double sig = (on && steps[k].kind == 2) ? (double)sigma : 1.0;
+    gs->kind[k] = on ? steps[k].kind : -1;
+    gs->c[k] = on ? steps[k].c : 1.0;
+    gs->s[k] = on ? sig * steps[k].s : 0.0;
+    gs->sig[k] = sig;
+  }
+}
+
+// d_out1[k] / d_out2[k] = <bra|T_k|ket> of step k of brick 1 / 2 (taken before that step), then both vectors are rotated
+int sq_launch_quad_grad(sq_space* sp, const QuadTables& qt, const TileStep* steps1, int n1, int sigma1, const TileStep* steps2,
+                        int n2, int sigma2, double* bra, double* ket, double* d_out1, double* d_out2, cudaStream_t st) {
+  if (!qt.ok || n1 < 1 || n2 < 1 || n1 > SQ_MAX_PROGRAM || n2 > SQ_MAX_PROGRAM) {
+    sq_set_error("quad gradient launch on a pair combination without quad tables or with a bad program");
+    return SQ_ERR_INVALID;
+  }
+  QuadGradProg qp;
+  grad_steps(steps1, n1, sigma1, &qp.g1);
+  grad_steps(steps2, n2, sigma2, &qp.g2);
+  QuadBounds qb = {qt.colblk_end[0], qt.colblk_end[1], qt.colblk_end[2], qt.colblk_end[3],
+                   qt.rowchunk_end[0], qt.rowchunk_end[1], qt.rowchunk_end[2], qt.rowchunk_end[3]};
+  if (qb.c0 == 0 || qb.r0 == 0) {
+    SQ_CUDA(cudaMemsetAsync(d_out1, 0, sizeof(double) * n1, st));
+    SQ_CUDA(cudaMemsetAsync(d_out2, 0, sizeof(double) * n2, st));
+    return SQ_OK;
+  }
+  dim3 grid((unsigned)qb.c0, (unsigned)qb.r0);
+  const int64_t nblocks = (int64_t)grid.x * grid.y;
+  SQ_CHECK(sq_ensure_partial(sp, nblocks * QGRAD_NS + QGRAD_NS));
+  static int minb = 0;
+  if (!minb) {
+    const char* e = getenv("SQ_QGRAD_MINB");   // resident CTAs per SM the kernel is compiled for: 2 (default, 128 registers), 1 or 3
+    minb = (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2);
+  }
+  if (minb == 1)
+    quad_grad_kernel<1><<<grid, QUAD_THREADS, 0, st>>>(bra, ket, qt.d_colIdx, qt.d_colFlags, qt.d_rowIdx, qt.d_rowFlags, sp->NB, qb, qp,
+                                                      sp->d_partial);
+  else if (minb == 3)
+    quad_grad_kernel<3><<<grid, QUAD_THREADS, 0, st>>>(bra, ket, qt.d_colIdx, qt.d_colFlags, qt.d_rowIdx, qt.d_rowFlags, sp->NB, qb, qp,
+                                                      sp->d_partial);
+  else
+    quad_grad_kernel<2><<<grid, QUAD_THREADS, 0, st>>>(bra, ket, qt.d_colIdx, qt.d_colFlags, qt.d_rowIdx, qt.d_rowFlags, sp->NB, qb, qp,
+                                                      sp->d_partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("quad_grad_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
+  g_sq_launches.fetch_add(1);
+  quad_grad_reduce_kernel<<<n1 + n2, 256, 0, st>>>(sp->d_partial, nblocks, n1, d_out1, d_out2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sq_set_error("quad_grad_reduce_kernel launch failed: %s", cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+  }
   return SQ_OK;
 }

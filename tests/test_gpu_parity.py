@@ -643,6 +643,17 @@ def test_window_gradient_sweep(sq, n, na, nb, L, qnp):
                 k_np = orc.propagate_unitary(k_np, k, sp, th, types, idx)
             assert np.max(np.abs(g0 - gr)) < 1e-11
             assert np.max(np.abs(k0.cpu().numpy() - k_np)) < TOL
+        # g0 came from the default plan (quad_grad_kernel: two commuting bricks per launch); one brick per launch must agree
+        sq.lib.check(lib.sq_set_option(b"quadgrad", b"0"))
+        launches_before = lib.sq_launch_count()
+        gs, bs, ks = sq.osa.ups_gradient_sweep(bra, ket, info, th.tolist(), lay)
+        launches_single = lib.sq_launch_count() - launches_before
+        sq.lib.check(lib.sq_set_option(b"quadgrad", b"1"))
+        launches_before = lib.sq_launch_count()
+        sq.osa.ups_gradient_sweep(bra, ket, info, th.tolist(), lay)
+        assert lib.sq_launch_count() - launches_before < launches_single, "no quad gradient launch was used"
+        assert np.max(np.abs(gs - g0)) < 1e-12
+        assert float(torch.max(torch.abs(bs - b0))) < 1e-13 and float(torch.max(torch.abs(ks - k0))) < 1e-13
         sq.lib.check(lib.sq_set_option(b"wingrad", b"1"))
         # the gradient sweep plans with its own window configuration (two vectors per batch): the default, wide windows (one
         # CTA per SM), capped brick counts, narrow windows
@@ -654,6 +665,7 @@ def test_window_gradient_sweep(sq, n, na, nb, L, qnp):
     finally:
         sq.lib.check(lib.sq_set_option(b"wingrad_win", b"5:4:0,40,3,16,2"))
         sq.lib.check(lib.sq_set_option(b"wingrad", b"0"))
+        sq.lib.check(lib.sq_set_option(b"quadgrad", b"1"))
 
 
 def test_state_averaged_twins(sq):

@@ -50,7 +50,12 @@ def sweep(label):
 
 
 lib.sq_set_option(b"wingrad", b"0")
+lib.sq_set_option(b"quadgrad", b"0")
 g0, b0, k0 = sweep("one brick per launch")
+lib.sq_set_option(b"quadgrad", b"1")
+gq, bq, kq = sweep("two bricks per launch (quad)")
+print("    max|grad diff| %.2e  max|bra diff| %.2e  max|ket diff| %.2e" % (
+    float(np.max(np.abs(gq - g0))), float(torch.max(torch.abs(bq - b0))), float(torch.max(torch.abs(kq - k0)))), flush=True)
 lib.sq_set_option(b"wingrad", b"1")
 for cfg in cfgs:
     lib.sq_set_option(b"wingrad_win", cfg.encode())
