@@ -483,7 +483,8 @@ def run_ours(args) -> None:
             g_syn = np.zeros((n, n, n, n))
             WF = WaveFunctionUPS((n, n), np.eye(n), ArrayIntegrals(h_syn + h_syn.T, g_syn, num_elec=n), "tUPS", {"n_layers": L}, device=local_rank)
             th_list = thetas.tolist()
-            WF.thetas = th_list
+            for _ in range(2):   # two warm-up calls: the setter keeps the old state alive until the new one exists, so the
+                WF.thetas = th_list   # caching allocator needs two 1.3 GB blocks before it stops calling cudaMalloc
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(n_e2e):
