@@ -159,6 +159,11 @@ int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, i
  * places commute, which leaves every <bra|T_k|ket> unchanged); grad_host[i] belongs to operator op_list[i]. */
 int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
                            double* bra_dev, double* ket_dev, double* grad_host, void* stream);
+/* The same sweep run BACKWARDS through the circuit: op_list in the execution order of the adjoint circuit; for every operator
+ * 2 <bra|T_k|ket> is taken first, then both vectors <- U_k^dagger.  Started from (H psi, psi) this is the gradient of
+ * ups_wavefunction.py:1114-1138 without the adjoint pass (T_k commutes with its own rotation). */
+int sq_ups_grad_sweep_list_rev(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                               double* bra_dev, double* ket_dev, double* grad_host, void* stream);
 
 /* Energy and theta gradient of a unitary product state in one call (_calc_energy_optimization /
  * _calc_gradient_optimization, ups_wavefunction.py:1019-1142): psi = U(theta) ref, *energy_host = <psi|H|psi> with H given by

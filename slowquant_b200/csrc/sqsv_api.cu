@@ -1583,6 +1583,8 @@ extern "C" int sq_grad_action(sq_space* sp, sq_layout* lay, int k, const double*
 static int grad_sweep_order(sq_space* sp, sq_layout* lay, const double* thetas_host, const std::vector<int>& order,
                             const std::vector<int>& out_pos, double* bra_dev, double* ket_dev, double* grad_host, void* stream,
                             int dagger);
+static int grad_sweep_list_impl(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                                double* bra_dev, double* ket_dev, double* grad_host, void* stream, int dagger);
 
 extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* thetas_host, int first, int last,
                                  double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
@@ -1600,6 +1602,11 @@ extern "C" int sq_ups_grad_sweep(sq_space* sp, sq_layout* lay, const double* the
 // unchanged).  grad_host[i] belongs to operator op_list[i].
 extern "C" int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
                                       double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+  return grad_sweep_list_impl(sp, lay, thetas_host, n_list, op_list, bra_dev, ket_dev, grad_host, stream, 0);
+}
+
+static int grad_sweep_list_impl(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                                double* bra_dev, double* ket_dev, double* grad_host, void* stream, int dagger) {
   if (!sp || !lay || lay->sp != sp || !bra_dev || !ket_dev || n_list < 0 || (n_list > 0 && (!op_list || !grad_host || !thetas_host)))
     return SQ_ERR_INVALID;
   const int P = (int)lay->ops.size();
@@ -1618,7 +1625,15 @@ extern "C" int sq_ups_grad_sweep_list(sq_space* sp, sq_layout* lay, const double
     out_pos[k] = i;
     order.push_back(k);
   }
-  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream, 0);
+  return grad_sweep_order(sp, lay, thetas_host, order, out_pos, bra_dev, ket_dev, grad_host, stream, dagger);
+}
+
+// The sweep run BACKWARDS: op_list is in the execution order of the adjoint circuit; for every operator g = 2 <bra|T_k|ket> is
+// taken first, then both vectors <- U_k^dagger.  Started from (H|psi>, |psi>) it yields the gradient of ups_wavefunction.py:1114-1138
+// without the adjoint pass over the circuit (T_k commutes with its own rotation).
+extern "C" int sq_ups_grad_sweep_list_rev(sq_space* sp, sq_layout* lay, const double* thetas_host, int n_list, const int32_t* op_list,
+                                          double* bra_dev, double* ket_dev, double* grad_host, void* stream) {
+  return grad_sweep_list_impl(sp, lay, thetas_host, n_list, op_list, bra_dev, ket_dev, grad_host, stream, 1);
 }
 
 // dagger = 1: `order` runs backwards through the circuit and every rotation is undone (theta -> -theta) after its gradient
