@@ -235,7 +235,7 @@ def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
     """The rest of north_star's "energy + gradient" at the same CAS, timed with CUDA events on the resident state:
     sigma build H|psi> (ups_wavefunction.py:770-784), 1-/2-RDM (ups_wavefunction.py:409-476) and the reverse
     theta-gradient sweep (ups_wavefunction.py:1114-1138: per operator g_k = 2<bra|T_k|ket>, then both vectors <- U_k).
-    Algorithmic bytes of the sweep: 32 B x touched amplitudes per operator (read + write of bra and ket)."""
+    Algorithmic bytes of the sweep: 32 B x touched amplitudes per LAUNCH (read + write of bra and ket; one or two bricks)."""
     import torch
 
     from slowquant_b200 import _lib
@@ -290,20 +290,37 @@ def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
     PD = C.POINTER(C.c_double)
     th = np.ascontiguousarray(thetas, dtype=np.float64)
 
+    sweep_launches = [0]
+
     def sweep():
         b, k = bra.clone(), ket.clone()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        l0 = lib.sq_launch_count()
         e0.record()
         _lib.check(lib.sq_ups_grad_sweep(info._handle, handle, th.ctypes.data_as(PD), 0, P, C.c_void_p(b.data_ptr()), C.c_void_p(k.data_ptr()),
                                          g_out.ctypes.data_as(PD), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         e1.record()
         torch.cuda.synchronize()
+        sweep_launches[0] = int(lib.sq_launch_count() - l0)
         return e0.elapsed_time(e1)
 
     sweep()
     ms_sweep = min(sweep() for _ in range(2))
-    sweep_gbs = 32.0 * touched / (ms_sweep * 1e-3) / 1e9
+    # Algorithmic bytes of the sweep as it is launched: quad_grad_kernel takes TWO commuting bricks per read + write of bra and
+    # ket and touches the amplitudes whose alpha or beta string is active in either pair; a single-brick launch touches those of
+    # one pair.  `one_brick_equivalent` keeps round 1's accounting (32 B x touched per brick) for comparison.
+    n_bricks = P // 3
+
+    def inert2(ne):   # fraction of strings with 0 or 2 electrons on each of two disjoint orbital pairs
+        return sum(comb(n - 4, ne - o1 - o2) for o1 in (0, 2) for o2 in (0, 2) if 0 <= ne - o1 - o2 <= n - 4) / comb(n, ne)
+
+    # every gradient launch is a kernel + its reduction (2 counted launches): L = 2 (quads + singles), bricks = 2 quads + singles
+    n_quads = max(0, min(n_bricks // 2, n_bricks - sweep_launches[0] // 2)) if sweep_launches[0] else 0
+    n_single = n_bricks - 2 * n_quads
+    touched_plan = (n_quads * (1.0 - inert2(na) * inert2(nb)) + n_single * (1.0 - inert_a * inert_b)) * info.num_det
+    sweep_gbs = 32.0 * touched_plan / (ms_sweep * 1e-3) / 1e9
+    sweep_gbs_one_brick = 32.0 * touched / (ms_sweep * 1e-3) / 1e9
     del bra
     # one whole evaluation through the call the wave-function object makes (sq_ups_energy_grad: state, sigma, dot, and the
     # gradient sweep run BACKWARDS from (H|psi>, |psi>) -- no adjoint pass), checked at size against the step-by-step route
@@ -332,8 +349,10 @@ def energy_gradient_extras(info, lay, thetas, state, dev) -> dict:
         "gradient_sweep_ms": ms_sweep,
         "gradient_sweep_ms_per_operator": ms_sweep / P,
         "gradient_sweep_ms_per_brick": ms_sweep / (P // 3),
+        "gradient_sweep_launches": {"two_bricks": n_quads, "one_brick": n_single},
         "gradient_sweep_algorithmic_GBps": sweep_gbs,
         "gradient_sweep_frac_of_measured_hbm_peak": sweep_gbs / peak,
+        "gradient_sweep_one_brick_equivalent_GBps": sweep_gbs_one_brick,
         "gradient_norm": float(np.linalg.norm(g_out)),
         "note": "synthetic symmetric integrals (default_rng(2024)); sigma / RDM: D-panel gathers + hand-written DMMA kernels (fp64 tensor pipe), the sweep is HBM-bound",
     }

@@ -756,5 +756,6 @@ int sq_launch_quad_grad(sq_space* sp, const QuadTables& qt, const TileStep* step
     sq_set_error("quad_grad_reduce_kernel launch failed: %s", cudaGetErrorString(e));
     return SQ_ERR_CUDA;
   }
+  g_sq_launches.fetch_add(1);
   return SQ_OK;
 }
