@@ -673,6 +673,7 @@ extern "C" int sq_set_option(const char* name, const char* value) {
   if (strcmp(name, "etab") == 0) {   // E_pq table of the sigma / RDM panel kernels: "smem" (default) or "const"
     sq_hamiltonian_set_etab_mode(value && strcmp(value, "const") == 0);
     sq_hamiltonian_set_etab_alu(value && strcmp(value, "alu") == 0);
+    sq_hamiltonian_set_etab_tab(value && strcmp(value, "tab") == 0);
     return SQ_OK;
   }
   if (strcmp(name, "rdm_sym") == 0) {   // sq_rdm12 with bra == ket: "1" (default) two symmetric S / A Gram matrices, "0" the plain n^2 x n^2 one

@@ -33,6 +33,10 @@ struct HamWork {
   std::vector<ERec> h_etab;
   uint32_t* d_tabG = nullptr; // [n*n][NB] beta gather table of the row kernels (build_D_rows_kernel)
   uint32_t* d_tabS = nullptr; // [n*n][NB] beta scatter table (scatter_E_rows_kernel)
+  // per-string partner tables of the table-driven panel kernels (sq_set_option("etab", "tab")): entry = partner string index << 1 |
+  // sign bit of the same-spin factor (s0 folded in), -1 where E_pq does not act; gather (target) form and scatter (source) form
+  int32_t *d_pgA = nullptr, *d_pgB = nullptr, *d_psA = nullptr, *d_psB = nullptr;   // alpha: [NA][n*n], beta: [n*n][NB]
+  uint32_t* d_parO = nullptr;  // [2][n*n] other-spin parity masks: alpha operators (applied to the beta string), beta operators
   double* d_D[4] = {nullptr, nullptr, nullptr, nullptr};   // ket panels (two in flight), bra panels (two in flight)
   double* d_F[2] = {nullptr, nullptr};
   // panel pipeline: gather, GEMM and scatter of neighbouring panels overlap on three internal streams
@@ -65,6 +69,13 @@ void sq_hamiltonian_set_etab_mode(int use_const) { g_etab_const = use_const ? 1 
 // off by default until measured.
 static int g_etab_alu = 0;
 void sq_hamiltonian_set_etab_alu(int on) { g_etab_alu = on ? 1 : 0; }
+// sq_set_option("etab", "tab"): per-STRING partner tables instead of per-(p,q) records: what the record-driven kernels recompute for
+// every determinant and (p,q) -- two mask tests, the flipped string, a popcount and a rank look-up per spin -- depends on one string
+// only (12 870 alpha strings serve 165 M determinants at CAS(16,16)), so it is tabulated once per space (13 MB per table at n = 16);
+// a thread then needs one (row-uniform) table load for the alpha partner, one coalesced load for the beta partner and one popcount
+// for the other-spin sign.  Single-device spaces whose tables stay below 64 MB each; otherwise the record kernels run.
+static int g_etab_tab = 0;
+void sq_hamiltonian_set_etab_tab(int on) { g_etab_tab = on ? 1 : 0; }
 __host__ __device__ __forceinline__ ERec erec_closed(int p, int q, int spin) {
   const uint32_t bp = 1u << p, bq = 1u << q;
   ERec r;
@@ -97,6 +108,7 @@ static void free_work(HamWork* w) {
   cudaFree(w->d_etab);
   cudaFree(w->d_tabG);
   cudaFree(w->d_tabS);
+  cudaFree(w->d_pgA); cudaFree(w->d_pgB); cudaFree(w->d_psA); cudaFree(w->d_psB); cudaFree(w->d_parO);
   for (double* p : w->d_D) cudaFree(p);
   for (double* p : w->d_F) cudaFree(p);
   if (w->s_build) cudaStreamDestroy(w->s_build);
@@ -125,6 +137,8 @@ void sq_hamiltonian_release(const sq_space* sp) {
 
 static int g_rows_kernels = 0;   // sq_set_option("rows", "1"): row-per-CTA panel kernels (see "row kernels" below)
 static bool rows_kernels_fit(const sq_space* sp);
+static bool partner_tables_fit(const sq_space* sp);
+static int build_partner_tables(sq_space* sp, HamWork* w);
 static int build_beta_tables(sq_space* sp, HamWork* w);
 
 static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out) {
@@ -161,6 +175,7 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
     w->h_etab = tab;
   }
   if (g_rows_kernels && rows_kernels_fit(sp) && !w->d_tabG) SQ_CHECK(build_beta_tables(sp, w));
+  if (g_etab_tab && partner_tables_fit(sp) && !w->d_pgA) SQ_CHECK(build_partner_tables(sp, w));
   if (!w->W) {
     // panel width: about 1 GiB per n^2 x W matrix, multiple of 256 determinants
     int64_t Wmax = g_panel_width > 0 ? g_panel_width : ((int64_t)1 << 27) / n2;
@@ -363,6 +378,123 @@ scatter_E_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const 
     }
   }
   atomicAdd(OUT + j, diag);
+}
+
+// ---- table-driven variants (sq_set_option("etab", "tab")): same arithmetic, per-string partner tables --------------------------------
+__global__ void __launch_bounds__(256)
+build_Dsym_tab_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
+                      const int32_t* __restrict__ pgA, const int32_t* __restrict__ pgB, const uint32_t* __restrict__ parO, int n,
+                      const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, int64_t NB) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int n2 = n * n, nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < nS; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  const int64_t ia = j / NB, ib = j - ia * NB;
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  const int32_t* ta = pgA + ia * n2;          // the same for every thread of the row: broadcast loads
+  const double* rowp = IN + ia * NB;
+  auto elem = [&](int pq) -> double {
+    double v = 0.0;
+    const int ea = __ldg(ta + pq);
+    if (ea >= 0) {
+      const double x = IN[(int64_t)(ea >> 1) * NB + ib];
+      v += ((ea ^ __popc(b & __ldg(parO + pq))) & 1) ? -x : x;
+    }
+    const int eb = __ldg(pgB + (int64_t)pq * NB + ib);
+    if (eb >= 0) {
+      const double x = rowp[eb >> 1];
+      v += ((eb ^ __popc(a & __ldg(parO + n2 + pq))) & 1) ? -x : x;
+    }
+    return v;
+  };
+  int slot = 0;
+  for (int r = 0; r < n; ++r)
+    for (int q = 0; q <= r; ++q, ++slot) D[(int64_t)slot * W + t] = (r == q) ? elem(r * n + r) : elem(r * n + q) + elem(q * n + r);
+}
+
+__global__ void __launch_bounds__(256)
+scatter_E_tab_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                     const double* __restrict__ kmat, const int* __restrict__ frow, int64_t W, int64_t j0, int64_t len,
+                     const int32_t* __restrict__ psA, const int32_t* __restrict__ psB, const uint32_t* __restrict__ parO, int n,
+                     const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, int64_t NB) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j = j0 + t;
+  if (t >= W || j >= len) return;
+  const int n2 = n * n;
+  const int64_t ia = j / NB, ib = j - ia * NB;
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  const int32_t* ta = psA + ia * n2;
+  double* orow = OUT + ia * NB;
+  const double cj = IN[j];
+  double diag = 0.0;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < n; ++q) {
+      const int pq = p * n + q;
+      const int ea = __ldg(ta + pq), eb = __ldg(psB + (int64_t)pq * NB + ib);
+      if (ea < 0 && eb < 0) continue;
+      const double val = F[(int64_t)__ldg(frow + pq) * W + t] + __ldg(kmat + pq) * cj;
+      if (ea >= 0) {
+        const double sv = ((ea ^ __popc(b & __ldg(parO + pq))) & 1) ? -val : val;
+        if (p == q) diag += sv;
+        else atomicAdd(OUT + (int64_t)(ea >> 1) * NB + ib, sv);
+      }
+      if (eb >= 0) {
+        const double sv = ((eb ^ __popc(a & __ldg(parO + n2 + pq))) & 1) ? -val : val;
+        if (p == q) diag += sv;
+        else atomicAdd(orow + (eb >> 1), sv);
+      }
+    }
+  atomicAdd(OUT + j, diag);
+}
+
+// host: the partner tables from the E_pq records (w->h_etab) and the string lists of the space
+static int build_partner_tables(sq_space* sp, HamWork* w) {
+  const int n = sp->n_orb, n2 = n * n;
+  const int64_t NA = sp->NA, NB = sp->NB;
+  std::vector<int32_t> gA((size_t)NA * n2), sA((size_t)NA * n2), gB((size_t)n2 * NB), sB((size_t)n2 * NB);
+  std::vector<uint32_t> parO(2 * (size_t)n2);
+  auto entry = [](const std::vector<int32_t>& rank, uint32_t m, const ERec& r, bool gather) -> int32_t {
+    const bool ok = gather ? ((m & r.tocc) == r.tocc && (m & r.temp) == 0u) : ((m & r.occ) == r.occ && (m & r.emp) == 0u);
+    if (!ok) return -1;
+    const uint32_t other = m ^ r.flip;
+    const int par = (__builtin_popcount((gather ? other : m) & r.parS) & 1) ^ (r.s0 < 0 ? 1 : 0);
+    const int32_t idx = rank[other];
+    return idx < 0 ? -1 : (int32_t)((idx << 1) | par);
+  };
+  for (int pq = 0; pq < n2; ++pq) {
+    const ERec &ra = w->h_etab[2 * pq], &rb = w->h_etab[2 * pq + 1];
+    parO[pq] = ra.parO;
+    parO[n2 + pq] = rb.parO;
+    for (int64_t i = 0; i < NA; ++i) {
+      gA[(size_t)i * n2 + pq] = entry(sp->rankA, sp->strA[i], ra, true);
+      sA[(size_t)i * n2 + pq] = entry(sp->rankA, sp->strA[i], ra, false);
+    }
+    for (int64_t i = 0; i < NB; ++i) {
+      gB[(size_t)pq * NB + i] = entry(sp->rankB, sp->strB[i], rb, true);
+      sB[(size_t)pq * NB + i] = entry(sp->rankB, sp->strB[i], rb, false);
+    }
+  }
+  auto up = [](int32_t** d, const std::vector<int32_t>& v) -> int {
+    SQ_CUDA(cudaMalloc(d, sizeof(int32_t) * v.size()));
+    SQ_CUDA(cudaMemcpy(*d, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice));
+    return SQ_OK;
+  };
+  SQ_CHECK(up(&w->d_pgA, gA));
+  SQ_CHECK(up(&w->d_psA, sA));
+  SQ_CHECK(up(&w->d_pgB, gB));
+  SQ_CHECK(up(&w->d_psB, sB));
+  SQ_CUDA(cudaMalloc(&w->d_parO, sizeof(uint32_t) * parO.size()));
+  SQ_CUDA(cudaMemcpy(w->d_parO, parO.data(), sizeof(uint32_t) * parO.size(), cudaMemcpyHostToDevice));
+  return SQ_OK;
+}
+static bool partner_tables_fit(const sq_space* sp) {
+  const size_t n2 = (size_t)sp->n_orb * sp->n_orb;
+  return sp->world <= 1 && sp->row_begin == 0 && sp->row_end == sp->NA && !sp->alpha_cmask &&
+         std::max(sp->NA, sp->NB) * n2 * sizeof(int32_t) <= ((size_t)64 << 20) && std::max(sp->NA, sp->NB) < ((int64_t)1 << 30);
 }
 
 // ---- table-free variants (sq_set_option("etab", "alu")): same arithmetic, records from erec_closed ----------------------------------
@@ -771,6 +903,11 @@ static int launch_build_D(sq_space* sp, HamWork* w, const double* in, double* D,
                                                                      sp->row_begin);
     return launch_error("build_D_peer_kernel");
   }
+  if (g_etab_tab && sym && w->d_pgA) {   // per-string partner tables
+    build_Dsym_tab_kernel<<<(unsigned)(w->W / 256), 256, 0, st>>>(in, D, w->W, j0, sp->local_len(), w->d_pgA, w->d_pgB, w->d_parO, n,
+                                                                  sp->d_strA, sp->d_strB, sp->NB);
+    return launch_error("build_Dsym_tab_kernel");
+  }
   if (g_etab_alu) {   // table-free records (candidate, off by default)
     const unsigned grid_a = (unsigned)(w->W / 256);
     if (sym)
@@ -1034,6 +1171,11 @@ static int launch_sigma_fused(sq_space* sp, const double* in, double* out, const
 static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* out, const double* F, const double* d_k,
                             int64_t j0, cudaStream_t st, bool use_const) {
   const int n2 = sp->n_orb * sp->n_orb;
+  if (g_etab_tab && w->d_psA) {   // per-string partner tables
+    scatter_E_tab_kernel<<<(unsigned)(w->W / 256), 256, 0, st>>>(in, out, F, d_k, w->d_frow, w->W, j0, sp->local_len(), w->d_psA, w->d_psB,
+                                                                 w->d_parO, sp->n_orb, sp->d_strA, sp->d_strB, sp->NB);
+    return launch_error("scatter_E_tab_kernel");
+  }
   if (g_etab_alu) {   // table-free records (candidate, off by default)
     scatter_E_alu_kernel<<<(unsigned)(w->W / 256), 256, 0, st>>>(in, out, F, d_k, w->d_frow, w->W, j0, sp->local_len(), sp->n_orb,
                                                                  sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, sp->row_begin);

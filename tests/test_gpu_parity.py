@@ -723,7 +723,8 @@ def test_state_averaged_twins(sq):
 
 def test_sigma_and_rdm_kernel_variants_agree(sq):
     """The sigma / RDM path has run-time variants (sq_set_option): row-per-CTA or determinant-per-thread panel kernels,
-    E table in shared or constant memory, panels pipelined over internal streams or one at a time.  With small panels (so
+    E table in shared or constant memory or per-string partner tables (etab = tab), panels pipelined over internal streams or
+    one at a time.  With small panels (so
     that several panels, a partial last panel and rows split between panels all occur) every variant must give the oracle's
     sigma vector and identical RDMs."""
     from slowquant_b200.operators import hamiltonian_0i_0a
@@ -748,7 +749,8 @@ def test_sigma_and_rdm_kernel_variants_agree(sq):
     other = rng.normal(size=sp.num_det)
     try:
         for rows, etab, pipe, fused in ((b"1", b"smem", b"1", b"0"), (b"1", b"smem", b"0", b"0"), (b"0", b"smem", b"1", b"0"),
-                                        (b"0", b"const", b"0", b"0"), (b"0", b"smem", b"1", b"1")):
+                                        (b"0", b"const", b"0", b"0"), (b"0", b"smem", b"1", b"1"), (b"0", b"tab", b"1", b"0"),
+                                        (b"0", b"tab", b"0", b"0")):
             lib.sq_set_option(b"panel", b"768")            # 3920 determinants -> 6 panels, the last one partial
             # 2-RDM of one vector: the plain n^2 x n^2 Gram matrix in the first two rounds, the two symmetric S / A Gram matrices
             # (the default) in the others -- all must agree to 1e-12
