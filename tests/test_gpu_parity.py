@@ -833,6 +833,53 @@ def test_fused_energy_gradient_call(sq, golden):
         assert g2 is None and abs(E2 - E) < 1e-13
 
 
+def test_backwards_gradient_sweep_on_a_mixed_circuit(sq):
+    """sq_ups_energy_grad runs the gradient loop BACKWARDS from (H|psi>, |psi>) (no adjoint pass).  On a circuit that mixes every
+    operator family -- tUPS bricks (quad and single gradient launches), generic singles / doubles / a triple, the five sa_double
+    cases (polynomial route) -- with a zero angle in the middle, energy and gradient must equal the step-by-step route
+    (state, sigma, adjoint, forward sweep of ups_wavefunction.py:1114-1138) and the oracle's literal gradient loop."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    n, na, nb = 7, 3, 3
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    info = sq.ci.get_indexing(0, n, 0, na, nb)
+    rng = np.random.default_rng(314)
+    types, idx = orc.tiled_layout(n, 1)
+    types = list(types) + ["single", "double", "sa_double_1", "sa_double_2", "sa_single", "sa_double_3", "triple", "sa_double_4",
+                           "sa_double_5", "double"]
+    # sa_double (i, j, a, b): case 1 i = j and a = b, case 2 i = j, case 3 a = b, cases 4 / 5 all distinct (util.py:26-42)
+    idx = list(idx) + [(3, 13), (0, 1, 8, 13), (0, 0, 4, 4), (1, 1, 3, 5), (1, 5), (0, 2, 5, 5), (0, 1, 2, 8, 11, 12), (0, 1, 4, 6),
+                       (1, 2, 3, 5), (2, 4, 6, 12)]
+    more_t, more_i = orc.tiled_layout(n, 1)
+    types += list(more_t)
+    idx += list(more_i)
+    th = rng.uniform(-1.2, 1.2, len(types))
+    th[len(types) // 2] = 0.0
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    lay = _layout(sq, types, idx)
+    H = hamiltonian_0i_0a(h, g, 0, n)
+    ref_state = np.zeros(sp.num_det)
+    ref_state[0] = 1.0
+    E, grad = sq.osa.ups_energy_and_gradient(ref_state, info, th.tolist(), lay, H)
+    # step by step through the public functions (forward sweep)
+    psi = sq.osa.construct_ups_state(ref_state, info, th.tolist(), lay)
+    hpsi = sq.osa.propagate_state([H], psi, info)
+    assert abs(E - float(psi @ hpsi)) < 1e-12
+    bra = sq.osa.construct_ups_state(hpsi, info, th.tolist(), lay, dagger=True)
+    g_fwd, _, ket_end = sq.osa.ups_gradient_sweep(bra, ref_state, info, th.tolist(), lay)
+    assert np.max(np.abs(ket_end - psi)) < 1e-12
+    assert np.max(np.abs(grad - g_fwd)) < 1e-11
+    # the oracle's literal loop
+    g_orc = orc.theta_gradient(ref_state, th, types, idx, h, g, sp)
+    assert np.max(np.abs(grad - g_orc)) < 1e-10
+    assert abs(E - orc.energy_elec(orc.construct_ups_state(ref_state, sp, th, types, idx), h, g, sp)) < 1e-10
+
+
 def test_per_string_kernels_against_reference_outputs(sq):
     """The reference's per-string entry points (osa.py:33-410: apply_operator_serial / _threaded, their _SA twins,
     add_operator_matrix) through the gather kernel, on CAS(4,5) with 3 alpha / 1 beta electrons, against outputs of the
