@@ -275,6 +275,45 @@ def test_reshard_schedule_order_gives_the_same_state():
             assert np.max(np.abs(cur - ref)) < 1e-13
 
 
+def test_backwards_gradient_loop_over_adjoint_phases_equals_literal_loop():
+    """The sharded energy + gradient driver walks the phases of the ADJOINT circuit from (H|psi>, |psi>): g_k = 2 <bra|T_k|ket>, then
+    both vectors <- U_k^dagger.  With the oracle executing the phases on full vectors this must give the literal gradient loop
+    of ups_wavefunction.py:1091-1138 (which starts from (U^dagger H|psi>, |ref>) and walks forwards) -- T_k commutes with its own
+    rotation, and operators that change places inside a phase commute with each other."""
+    from oracle import sq_oracle as orc
+    from slowquant_b200.distributed import reshard_schedule
+
+    n, na, nb = 6, 3, 3
+    types, idx = orc.tiled_layout(n, 2)
+    types = list(types) + ["single", "double", "sa_single"]
+    idx = list(idx) + [(1, 9), (0, 1, 8, 11), (1, 4)]
+    rng = np.random.default_rng(11)
+    th = rng.uniform(-1.0, 1.0, len(types))
+    th[4] = 0.0
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    sp = orc.get_indexing(0, n, 0, na, nb)
+    ref_state = np.zeros(sp.num_det)
+    ref_state[0] = 1.0
+    want = orc.theta_gradient(ref_state, th, types, idx, h, g, sp)
+    H = orc.hamiltonian_0i_0a(h, g, 0, n)
+    for world in (2, 4):
+        ket = orc.construct_ups_state(ref_state, sp, th, types, idx)
+        bra = orc.propagate_state([H], ket, sp)
+        grad = np.zeros(len(types))
+        for _, ops in reshard_schedule(types, idx, n, world, 0, len(types), True):
+            for k in ops:
+                grad[k] = 2.0 * float(bra @ orc.get_grad_action(ket, k, sp, types, idx))
+                bra = orc.construct_ups_state(bra, sp, [th[k]], [types[k]], [idx[k]], dagger=True)
+                ket = orc.construct_ups_state(ket, sp, [th[k]], [types[k]], [idx[k]], dagger=True)
+        assert np.max(np.abs(grad - want)) < 1e-12, world
+        assert np.max(np.abs(ket - ref_state)) < 1e-12        # the ket is swept back to the reference state
+
+
 @pytest.mark.parametrize("world,n,na", [(2, 6, 3), (4, 7, 3), (8, 9, 4), (8, 16, 8), (4, 6, 5)])
 def test_reshard_tables_are_inverse_permutations(world, n, na):
     """A -> B moves every row to exactly one slot of the rank that owns its last-orbitals pattern, B -> A brings it back."""
