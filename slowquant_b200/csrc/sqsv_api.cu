@@ -680,6 +680,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_rdm_sym(!(value && value[0] == '0'));
     return SQ_OK;
   }
+  if (strcmp(name, "sigma_spinsym") == 0) {   // sigma of a spin-flip symmetric vector from the determinants above the diagonal: "1" (default) / "0"
+    sq_hamiltonian_set_sigma_spinsym(!(value && value[0] == '0'));
+    return SQ_OK;
+  }
   if (strcmp(name, "sigma_fused") == 0) {   // sigma: "0" (default) three-kernel panel pipeline, "1" fused gather -> DMMA -> scatter kernel (slower)
     sq_hamiltonian_set_sigma_fused(value && value[0] == '1');
     return SQ_OK;

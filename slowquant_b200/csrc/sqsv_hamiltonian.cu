@@ -37,6 +37,7 @@ struct HamWork {
   // sign bit of the same-spin factor (s0 folded in), -1 where E_pq does not act; gather (target) form and scatter (source) form
   int32_t *d_pgA = nullptr, *d_pgB = nullptr, *d_psA = nullptr, *d_psB = nullptr;   // alpha: [NA][n*n], beta: [n*n][NB]
   uint32_t* d_parO = nullptr;  // [2][n*n] other-spin parity masks: alpha operators (applied to the beta string), beta operators
+  unsigned long long* d_symres = nullptr;   // 3 words of spinsym_check_kernel
   double* d_D[4] = {nullptr, nullptr, nullptr, nullptr};   // ket panels (two in flight), bra panels (two in flight)
   double* d_F[2] = {nullptr, nullptr};
   // panel pipeline: gather, GEMM and scatter of neighbouring panels overlap on three internal streams
@@ -109,6 +110,7 @@ static void free_work(HamWork* w) {
   cudaFree(w->d_tabG);
   cudaFree(w->d_tabS);
   cudaFree(w->d_pgA); cudaFree(w->d_pgB); cudaFree(w->d_psA); cudaFree(w->d_psB); cudaFree(w->d_parO);
+  cudaFree(w->d_symres);
   for (double* p : w->d_D) cudaFree(p);
   for (double* p : w->d_F) cudaFree(p);
   if (w->s_build) cudaStreamDestroy(w->s_build);
@@ -1168,6 +1170,185 @@ static int launch_sigma_fused(sq_space* sp, const double* in, double* out, const
   return SQ_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Spin-flip symmetric vectors: half of the sigma build.
+//
+// U = "flip the spin of every electron" maps |A,B> (alpha mask A, beta mask B; spin orbitals interleaved a0 b0 a1 b1 ...) to
+// phi(A,B) |B,A> with phi = (-1)^popc(A & B) (one transposition per doubly occupied orbital).  A spin-free Hamiltonian commutes
+// with U, and so does every spin-adapted ansatz operator (sa_single, pair doubles, sa_double_k): a tUPS / QNP / SA-UCC state
+// built on a closed-shell reference is an eigenvector, U psi = lambda psi with lambda = +-1, i.e.
+//     c[B,A] = lambda phi(A,B) c[A,B],
+// and the same holds for sigma = H psi and for every column F[pq][.] of the contraction with the integrals.  With n_alpha = n_beta
+// the panels of the Knowles-Handy build then only need the determinants J = (A,B) with index(A) <= index(B): for a contribution
+// w of J to a target T,   T above / on the diagonal: sigma[T] += w;   T below / on the diagonal: sigma[T^T] += lambda phi(T) w
+// (a diagonal T gets both; a diagonal J contributes only to targets above / on the diagonal), and the lower triangle is filled
+// from the upper one at the end.  Half of the gathers, of the tensor-core work and of the atomics.  The symmetry is a property
+// of the VECTOR: it is measured before every build (max |c[B,A] - lambda phi c[A,B]| <= 1e-12 max|c|), anything else takes the
+// full build.  Reference: the full expectation-value loop of ups_wavefunction.py:770-784 makes no use of it.
+// ---------------------------------------------------------------------------------------------------------------------------
+static int g_sigma_spinsym = 1;   // sq_set_option("sigma_spinsym", "0"): always the full build
+void sq_hamiltonian_set_sigma_spinsym(int on) { g_sigma_spinsym = on ? 1 : 0; }
+
+__device__ __forceinline__ void tri_unrank(int64_t j, int64_t N, int64_t* ia, int64_t* ib) {
+  // j = ia * N - ia (ia - 1) / 2 + (ib - ia), ib >= ia
+  const double b = 2.0 * (double)N + 1.0;
+  int64_t r = (int64_t)((b - sqrt(b * b - 8.0 * (double)j)) * 0.5);
+  if (r < 0) r = 0;
+  if (r > N - 1) r = N - 1;
+  while (r > 0 && r * N - r * (r - 1) / 2 > j) --r;
+  while (r + 1 < N && (r + 1) * N - (r + 1) * r / 2 <= j) ++r;
+  *ia = r;
+  *ib = r + (j - (r * N - r * (r - 1) / 2));
+}
+
+// res[0] = max |c|, res[1] = max |c[B,A] - phi c[A,B]|, res[2] = max |c[B,A] + phi c[A,B]| (bit patterns of non-negative doubles
+// order like integers: atomicMax on the 64-bit words); 32 x 32 tiles transposed through shared memory, upper tiles only
+__global__ void __launch_bounds__(256)
+spinsym_check_kernel(const double* __restrict__ C, int64_t N, const uint32_t* __restrict__ str, unsigned long long* __restrict__ res) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  if (bj >= bi) {
+    for (int k = ty; k < 32; k += 8) {   // lower tile (rows of block bj, columns of block bi), read along its rows
+      const int64_t r = bj * 32 + k, c = bi * 32 + tx;
+      tile[k][tx] = (r < N && c < N) ? C[r * N + c] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (bj >= bi) {
+    for (int k = ty; k < 32; k += 8) {
+      const int64_t r = bi * 32 + k, c = bj * 32 + tx;   // element (r, c) of the upper tile; its mirror is tile[tx][k]
+      if (r < N && c < N) {
+        const double x = C[r * N + c], y = tile[tx][k];
+        const double ph = (__popc(__ldg(str + r) & __ldg(str + c)) & 1) ? -x : x;
+        m0 = fmax(m0, fmax(fabs(x), fabs(y)));
+        m1 = fmax(m1, fabs(y - ph));
+        m2 = fmax(m2, fabs(y + ph));
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    m0 = fmax(m0, __shfl_down_sync(0xffffffffu, m0, off));
+    m1 = fmax(m1, __shfl_down_sync(0xffffffffu, m1, off));
+    m2 = fmax(m2, __shfl_down_sync(0xffffffffu, m2, off));
+  }
+  if (tx == 0 && bj >= bi) {
+    atomicMax(res + 0, (unsigned long long)__double_as_longlong(m0));
+    atomicMax(res + 1, (unsigned long long)__double_as_longlong(m1));
+    atomicMax(res + 2, (unsigned long long)__double_as_longlong(m2));
+  }
+}
+
+// OUT[B,A] = lambda phi(A,B) OUT[A,B] for index(A) < index(B): the lower triangle from the upper one
+__global__ void __launch_bounds__(256)
+spinsym_mirror_kernel(double* __restrict__ OUT, int64_t N, const uint32_t* __restrict__ str, double lambda) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = bi * 32 + k, c = bj * 32 + tx;
+    double v = 0.0;
+    if (r < N && c < N) {
+      v = OUT[r * N + c];
+      if (__popc(__ldg(str + r) & __ldg(str + c)) & 1) v = -v;
+    }
+    tile[k][tx] = lambda * v;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = bj * 32 + k, c = bi * 32 + tx;   // element (r, c) of the lower tile = mirror of upper (c, r)
+    if (r < N && c < N && r > c) OUT[r * N + c] = tile[tx][k];
+  }
+}
+
+// the gather of build_Dsym_kernel for the determinants above / on the diagonal (linear index j over the upper triangle)
+__global__ void __launch_bounds__(256)
+build_Dsym_tri_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
+                      const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB,
+                      const int32_t* __restrict__ rankA, const int32_t* __restrict__ rankB, int64_t NB) {
+  const int n2 = n * n;
+  const ERec* sm = stage_etab<false>(etab, n2);
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < nS; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  int64_t ia, ib;
+  tri_unrank(j, NB, &ia, &ib);
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  auto elem = [&](int slot) -> double {
+    double v = 0.0;
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      v += (par ? -ra.s0 : ra.s0) * IN[(int64_t)__ldg(rankA + sa) * NB + ib];
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      v += (par ? -rb.s0 : rb.s0) * IN[ia * NB + __ldg(rankB + sb)];
+    }
+    return v;
+  };
+  int slot = 0;
+  for (int r = 0; r < n; ++r)
+    for (int q = 0; q <= r; ++q, ++slot) D[(int64_t)slot * W + t] = (r == q) ? elem(r * n + r) : elem(r * n + q) + elem(q * n + r);
+}
+
+// the scatter of scatter_E_kernel for sources above / on the diagonal; targets below the diagonal are folded onto their mirror
+__global__ void __launch_bounds__(256)
+scatter_E_tri_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                     const double* __restrict__ kmat, const int* __restrict__ frow, int64_t W, int64_t j0, int64_t len,
+                     const ERec* __restrict__ etab, int n2, const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB,
+                     const int32_t* __restrict__ rankA, const int32_t* __restrict__ rankB, int64_t NB, double lambda) {
+  const ERec* sm = stage_etab<false>(etab, n2);
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j = j0 + t;
+  if (t >= W || j >= len) return;
+  int64_t ia, ib;
+  tri_unrank(j, NB, &ia, &ib);
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  const bool src_diag = ia == ib;
+  const double cj = IN[ia * NB + ib];
+  double diag = 0.0;
+  // one contribution w to target (ra_, rb_) with masks (ma, mb)
+  auto put = [&](int64_t ra_, int64_t rb_, uint32_t ma, uint32_t mb, double wv) {
+    if (ra_ <= rb_) atomicAdd(OUT + ra_ * NB + rb_, wv);
+    if (ra_ >= rb_ && !src_diag) {
+      const double mv = lambda * ((__popc(ma & mb) & 1) ? -wv : wv);
+      atomicAdd(OUT + rb_ * NB + ra_, mv);
+    }
+  };
+  for (int slot = 0; slot < n2; ++slot) {
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    const bool va = (a & ra.occ) == ra.occ && (a & ra.emp) == 0u;
+    const bool vb = (b & rb.occ) == rb.occ && (b & rb.emp) == 0u;
+    if (!va && !vb) continue;
+    const double val = F[(int64_t)__ldg(frow + slot) * W + t] + __ldg(kmat + slot) * cj;
+    if (va) {
+      const int par = (__popc(a & ra.parS) + __popc(b & ra.parO)) & 1;
+      const double sv = (par ? -ra.s0 : ra.s0) * val;
+      if (ra.flip == 0u) diag += sv;
+      else put((int64_t)__ldg(rankA + (a ^ ra.flip)), ib, a ^ ra.flip, b, sv);
+    }
+    if (vb) {
+      const int par = (__popc(b & rb.parS) + __popc(a & rb.parO)) & 1;
+      const double sv = (par ? -rb.s0 : rb.s0) * val;
+      if (rb.flip == 0u) diag += sv;
+      else put(ia, (int64_t)__ldg(rankB + (b ^ rb.flip)), a, b ^ rb.flip, sv);
+    }
+  }
+  // the determinant itself: above the diagonal it is a plain upper target; on the diagonal it gets the direct term only
+  atomicAdd(OUT + ia * NB + ib, diag);
+}
+
 static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* out, const double* F, const double* d_k,
                             int64_t j0, cudaStream_t st, bool use_const) {
   const int n2 = sp->n_orb * sp->n_orb;
@@ -1274,6 +1455,40 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   }
   bool use_const = false;
   SQ_CHECK(bind_etab(sp, w, st, &use_const));
+  // Spin-flip symmetric input (see "half of the sigma build" above): measured, not assumed
+  bool tri = false;
+  double lambda = 1.0;
+  if (g_sigma_spinsym && sym && !use_const && !g_etab_alu && !g_etab_tab && !(g_rows_kernels && w->d_tabG) && sp->n_alpha == sp->n_beta &&
+      sp->NA == sp->NB && sp->NA > 1) {
+    if (!w->d_symres) SQ_CUDA(cudaMalloc(&w->d_symres, 3 * sizeof(unsigned long long)));
+    SQ_CUDA(cudaMemsetAsync(w->d_symres, 0, 3 * sizeof(unsigned long long), st));
+    const unsigned nb32 = (unsigned)((sp->NA + 31) / 32);
+    spinsym_check_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(in_dev, sp->NA, sp->d_strA, w->d_symres);
+    SQ_CHECK(launch_error("spinsym_check_kernel"));
+    double res[3];
+    SQ_CUDA(cudaMemcpyAsync(res, w->d_symres, sizeof(res), cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(cudaStreamSynchronize(st));
+    const double tol_sym = 1e-12 * res[0];
+    if (res[0] > 0.0 && res[1] <= tol_sym) { tri = true; lambda = 1.0; }
+    else if (res[0] > 0.0 && res[2] <= tol_sym) { tri = true; lambda = -1.0; }
+  }
+  const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : len;
+  auto build_panel = [&](double* Dp, int64_t j0, cudaStream_t s) -> int {
+    if (!tri) return launch_build_D(sp, w, in_dev, Dp, j0, s, use_const, sym);
+    const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+    allow_smem(build_Dsym_tri_kernel, smem);
+    build_Dsym_tri_kernel<<<(unsigned)(w->W / 256), 256, smem, s>>>(in_dev, Dp, w->W, j0, len_eff, w->d_etab, n, sp->d_strA, sp->d_strB,
+                                                                     sp->d_rankA, sp->d_rankB, sp->NB);
+    return launch_error("build_Dsym_tri_kernel");
+  };
+  auto scatter_panel = [&](const double* Fp, int64_t j0, cudaStream_t s) -> int {
+    if (!tri) return launch_scatter_E(sp, w, in_dev, out_dev, Fp, d_k, j0, s, use_const);
+    const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
+    allow_smem(scatter_E_tri_kernel, smem);
+    scatter_E_tri_kernel<<<(unsigned)(w->W / 256), 256, smem, s>>>(in_dev, out_dev, Fp, d_k, w->d_frow, w->W, j0, len_eff, w->d_etab, n2,
+                                                                    sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB, lambda);
+    return launch_error("scatter_E_tri_kernel");
+  };
   // Three-stage pipeline over the panels: while the DGEMM of panel k runs on the tensor cores, the gather of panel k+1
   // and the scatter of panel k-1 (both address-bound) run beside it.  Two D and two F panels are in flight; with
   // pipeline off (or a single panel) all three stages are issued on the caller's stream.
@@ -1286,12 +1501,12 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_start, 0));
   }
   int64_t ip = 0;
-  for (int64_t j0 = 0; j0 < len; j0 += w->W, ++ip) {
+  for (int64_t j0 = 0; j0 < len_eff; j0 += w->W, ++ip) {
     const int b = piped ? (int)(ip & 1) : 0;
     double* Dp = w->d_D[b];
     double* Fp = w->d_F[b];
     if (piped && ip >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // D[b] is free once GEMM k-2 has read it
-    SQ_CHECK(launch_build_D(sp, w, in_dev, Dp, j0, s_build, use_const, sym));
+    SQ_CHECK(build_panel(Dp, j0, s_build));
     if (piped) {
       SQ_CUDA(cudaEventRecord(w->ev_built[b], s_build));
       SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_built[b], 0));
@@ -1303,7 +1518,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       SQ_CUDA(cudaEventRecord(w->ev_gemm[b], s_gemm));
       SQ_CUDA(cudaStreamWaitEvent(s_scat, w->ev_gemm[b], 0));
     }
-    SQ_CHECK(launch_scatter_E(sp, w, in_dev, out_dev, Fp, d_k, j0, s_scat, use_const));
+    SQ_CHECK(scatter_panel(Fp, j0, s_scat));
     if (piped) SQ_CUDA(cudaEventRecord(w->ev_scat[b], s_scat));
   }
   if (piped) {   // the caller's stream continues after the last scatter (which is after everything else)
@@ -1311,6 +1526,11 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
     SQ_CUDA(cudaEventRecord(w->ev_start, s_build));
     SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
+  }
+  if (tri) {   // the lower triangle from the upper one
+    const unsigned nb32 = (unsigned)((sp->NA + 31) / 32);
+    spinsym_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(out_dev, sp->NA, sp->d_strA, lambda);
+    SQ_CHECK(launch_error("spinsym_mirror_kernel"));
   }
   return SQ_OK;
 }

@@ -880,6 +880,58 @@ def test_backwards_gradient_sweep_on_a_mixed_circuit(sq):
     assert abs(E - orc.energy_elec(orc.construct_ups_state(ref_state, sp, th, types, idx), h, g, sp)) < 1e-10
 
 
+@pytest.mark.parametrize("n,ne,L", [(8, 4, 2), (6, 3, 2), (7, 3, 1)])
+def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L):
+    """sq_sigma builds H|psi> of a spin-flip symmetric vector (c[B,A] = lambda phi(A,B) c[A,B]: every tUPS state on a closed-shell
+    reference; lambda = +1 for an even, -1 for an odd number of electron pairs) from the determinants above the diagonal only.
+    The half build must equal the full build (switch off) and the oracle's sigma; a vector without the symmetry -- a random one, or
+    a symmetric one disturbed at 1e-8 -- must take the full build (same launches as with the switch off, plus the check)."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    lib = sq.lib.load()
+    rng = np.random.default_rng(40 + n)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    sp = orc.get_indexing(0, n, 0, ne, ne)
+    types, idx, th, _ = _seeded_case(n, ne, ne, L, 4000 + n)
+    hf = np.zeros(sp.num_det)
+    hf[0] = 1.0
+    psi = orc.construct_ups_state(hf, sp, th, types, idx)
+    H_orc = orc.hamiltonian_0i_0a(h, g, 0, n)
+    try:
+        lib.sq_set_option(b"panel", b"512")                       # several panels, the last one partial, in both builds
+        info = sq.ci.get_indexing(0, n, 0, ne, ne)
+        H = hamiltonian_0i_0a(h, g, 0, n)
+        for label, vec, symmetric in (("tUPS state", psi, True), ("random", rng.normal(size=sp.num_det), False),
+                                      ("disturbed", psi + 1e-8 * rng.normal(size=sp.num_det), False)):
+            ref = orc.propagate_state([H_orc], vec, sp)
+            lib.sq_set_option(b"sigma_spinsym", b"0")
+            l0 = lib.sq_launch_count()
+            full = sq.osa.propagate_state([H], vec, info)
+            launches_full = lib.sq_launch_count() - l0
+            lib.sq_set_option(b"sigma_spinsym", b"1")
+            l0 = lib.sq_launch_count()
+            half = sq.osa.propagate_state([H], vec, info)
+            launches_half = lib.sq_launch_count() - l0
+            assert np.max(np.abs(full - ref)) < 1e-11, label
+            assert np.max(np.abs(half - ref)) < 1e-11, label
+            assert np.max(np.abs(half - full)) < 1e-12, label
+            # fall-back = the full build plus the symmetry check; the half build adds the mirror pass and has about half the panels
+            if symmetric:
+                assert launches_half != launches_full + 1, (label, launches_half, launches_full)
+                if sp.num_det > 4 * 512:
+                    assert launches_half < launches_full, (label, launches_half, launches_full)
+            else:
+                assert launches_half == launches_full + 1, (label, launches_half, launches_full)
+    finally:
+        lib.sq_set_option(b"panel", b"0")
+        lib.sq_set_option(b"sigma_spinsym", b"1")
+
+
 def test_per_string_kernels_against_reference_outputs(sq):
     """The reference's per-string entry points (osa.py:33-410: apply_operator_serial / _threaded, their _SA twins,
     add_operator_matrix) through the gather kernel, on CAS(4,5) with 3 alpha / 1 beta electrons, against outputs of the

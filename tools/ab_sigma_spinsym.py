@@ -1,0 +1,31 @@
+"""A/B at CAS(16,16): sigma build of a tUPS state (spin-flip symmetric) with the half build on / off."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+from slowquant_b200 import _lib
+from slowquant_b200 import operator_state_algebra as osa
+from slowquant_b200.ci_spaces import get_indexing
+from slowquant_b200.operators import hamiltonian_0i_0a
+from slowquant_b200.util import UpsStructure
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+L = 4
+info = get_indexing(0, n, 0, n // 2, n // 2)
+lay = UpsStructure(); lay.create_tiled(n, {"n_layers": L, "do_tups": True})
+th = np.random.default_rng(3).uniform(-np.pi, np.pi, lay.n_params)
+rng = np.random.default_rng(2024)
+A = rng.normal(size=(n, n)); h = A + A.T
+B = 0.1 * rng.normal(size=(n, n, n, n))
+g = B + B.transpose(1, 0, 2, 3); g = g + g.transpose(0, 1, 3, 2); g = g + g.transpose(2, 3, 0, 1)
+H = hamiltonian_0i_0a(h, g, 0, n)
+hf = torch.zeros(info.num_det, dtype=torch.float64, device="cuda"); hf[0] = 1.0
+psi = osa.construct_ups_state(hf, info, th.tolist(), lay)
+lib = _lib.load()
+res = {}
+for mode in (b"0", b"1", b"0", b"1"):
+    lib.sq_set_option(b"sigma_spinsym", mode)
+    osa.propagate_state([H], psi, info); torch.cuda.synchronize()
+    t0 = time.perf_counter(); out = osa.propagate_state([H], psi, info); torch.cuda.synchronize()
+    print(f"CAS({n},{n}) sigma_spinsym={mode.decode()} sigma {1e3*(time.perf_counter()-t0):8.1f} ms  E = {float(torch.dot(psi, out)):.12f}", flush=True)
+    res[mode] = out
+print("max|half - full| =", float(torch.max(torch.abs(res[b'1'] - res[b'0']))), " |sigma| =", float(torch.linalg.norm(res[b'0'])))
