@@ -1349,6 +1349,72 @@ scatter_E_tri_kernel(const double* __restrict__ IN, double* __restrict__ OUT, co
   atomicAdd(OUT + ia * NB + ib, diag);
 }
 
+// The S / A generator panel of build_DSA_kernel for the determinants above / on the diagonal of a spin-flip symmetric vector:
+// <J^T|O|psi> = lambda phi(J) <J|O|psi> for every spin-free O, so the Gram matrices sum_J d_J d_J^T over all determinants are
+// 2 sum_{J above} + sum_{J on the diagonal}; the weight enters as a factor sqrt(2) on the columns above the diagonal.
+__global__ void __launch_bounds__(256)
+build_DSA_tri_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len, int n,
+                     const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                     const int32_t* __restrict__ rankB, int64_t NB) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int n2 = n * n, nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  int64_t ia, ib;
+  tri_unrank(j, NB, &ia, &ib);
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  const double wgt = (ia == ib) ? 1.0 : 1.4142135623730951;
+  auto elem = [&](int p, int q) -> double {
+    double v = 0.0;
+    const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      v += (par ? -ra.s0 : ra.s0) * IN[(int64_t)__ldg(rankA + sa) * NB + ib];
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      v += (par ? -rb.s0 : rb.s0) * IN[ia * NB + __ldg(rankB + sb)];
+    }
+    return v;
+  };
+  int ss = 0, as = nS;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q <= p; ++q, ++ss) {
+      if (p == q) {
+        D[(int64_t)ss * W + t] = wgt * elem(p, p);
+      } else {
+        const double x = elem(p, q), y = elem(q, p);
+        D[(int64_t)ss * W + t] = wgt * (x + y);
+        D[(int64_t)as * W + t] = wgt * (x - y);
+        ++as;
+      }
+    }
+}
+
+// measures the spin-flip symmetry of a vector (see above): *lambda = +-1 if c[B,A] = lambda phi(A,B) c[A,B] to 1e-12 max|c|, else 0
+static int spinsym_measure(sq_space* sp, HamWork* w, const double* vec, cudaStream_t st, double* lambda) {
+  *lambda = 0.0;
+  if (sp->n_alpha != sp->n_beta || sp->NA != sp->NB || sp->NA < 2) return SQ_OK;
+  if (!w->d_symres) SQ_CUDA(cudaMalloc(&w->d_symres, 3 * sizeof(unsigned long long)));
+  SQ_CUDA(cudaMemsetAsync(w->d_symres, 0, 3 * sizeof(unsigned long long), st));
+  const unsigned nb32 = (unsigned)((sp->NA + 31) / 32);
+  spinsym_check_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(vec, sp->NA, sp->d_strA, w->d_symres);
+  SQ_CHECK(launch_error("spinsym_check_kernel"));
+  double res[3];
+  SQ_CUDA(cudaMemcpyAsync(res, w->d_symres, sizeof(res), cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(cudaStreamSynchronize(st));
+  const double tol_sym = 1e-12 * res[0];
+  if (res[0] > 0.0 && res[1] <= tol_sym) *lambda = 1.0;
+  else if (res[0] > 0.0 && res[2] <= tol_sym) *lambda = -1.0;
+  return SQ_OK;
+}
+
 static int launch_scatter_E(sq_space* sp, HamWork* w, const double* in, double* out, const double* F, const double* d_k,
                             int64_t j0, cudaStream_t st, bool use_const) {
   const int n2 = sp->n_orb * sp->n_orb;
@@ -1460,17 +1526,8 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   double lambda = 1.0;
   if (g_sigma_spinsym && sym && !use_const && !g_etab_alu && !g_etab_tab && !(g_rows_kernels && w->d_tabG) && sp->n_alpha == sp->n_beta &&
       sp->NA == sp->NB && sp->NA > 1) {
-    if (!w->d_symres) SQ_CUDA(cudaMalloc(&w->d_symres, 3 * sizeof(unsigned long long)));
-    SQ_CUDA(cudaMemsetAsync(w->d_symres, 0, 3 * sizeof(unsigned long long), st));
-    const unsigned nb32 = (unsigned)((sp->NA + 31) / 32);
-    spinsym_check_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(in_dev, sp->NA, sp->d_strA, w->d_symres);
-    SQ_CHECK(launch_error("spinsym_check_kernel"));
-    double res[3];
-    SQ_CUDA(cudaMemcpyAsync(res, w->d_symres, sizeof(res), cudaMemcpyDeviceToHost, st));
-    SQ_CUDA(cudaStreamSynchronize(st));
-    const double tol_sym = 1e-12 * res[0];
-    if (res[0] > 0.0 && res[1] <= tol_sym) { tri = true; lambda = 1.0; }
-    else if (res[0] > 0.0 && res[2] <= tol_sym) { tri = true; lambda = -1.0; }
+    SQ_CHECK(spinsym_measure(sp, w, in_dev, st, &lambda));
+    tri = lambda != 0.0;
   }
   const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : len;
   auto build_panel = [&](double* Dp, int64_t j0, cudaStream_t s) -> int {
@@ -1666,6 +1723,14 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   } else if (rdm2_host) {
     SQ_CHECK(sq_gram_begin(n2, same, w->n_sm, &w->d_gram, &w->gram_doubles, &tiles, &n_split, st));
   }
+  // spin-flip symmetric vector (measured): the S / A panels of the determinants above / on the diagonal only, weighted
+  bool tri = false;
+  if (sym_route && g_sigma_spinsym) {
+    double lambda = 0.0;
+    SQ_CHECK(spinsym_measure(sp, w, ket_dev, st, &lambda));
+    tri = lambda != 0.0;
+  }
+  const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : len;
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -1675,12 +1740,16 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     SQ_CUDA(cudaStreamWaitEvent(s_gemm, w->ev_start, 0));
   }
   int64_t k = 0;
-  for (int64_t j0 = 0; j0 < len; j0 += w->W, ++k) {
-    const int64_t wl = (len - j0 < w->W) ? len - j0 : w->W;
+  for (int64_t j0 = 0; j0 < len_eff; j0 += w->W, ++k) {
+    const int64_t wl = (len_eff - j0 < w->W) ? len_eff - j0 : w->W;
     const int b = piped ? (int)(k & 1) : 0;
     double* Dket = w->d_D[b];
     if (piped && k >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // panels b are free once GEMM k-2 is done
-    if (sym_route) {
+    if (tri) {
+      build_DSA_tri_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len_eff, n, sp->d_strA, sp->d_strB,
+                                                                      sp->d_rankA, sp->d_rankB, sp->NB);
+      SQ_CHECK(launch_error("build_DSA_tri_kernel"));
+    } else if (sym_route) {
       build_DSA_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len, n, sp->d_strA, sp->d_strB, sp->d_rankA,
                                                                   sp->d_rankB, sp->NB, sp->row_begin);
       SQ_CHECK(launch_error("build_DSA_kernel"));

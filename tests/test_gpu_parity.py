@@ -927,6 +927,19 @@ def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L):
                     assert launches_half < launches_full, (label, launches_half, launches_full)
             else:
                 assert launches_half == launches_full + 1, (label, launches_half, launches_full)
+        # the 1-/2-RDM of the symmetric state: Gram matrices over the determinants above the diagonal (weight 2) against all of them
+        lib.sq_set_option(b"sigma_spinsym", b"0")
+        d1_full, d2_full = sq.osa.reduced_density_matrices(psi, psi, info)
+        lib.sq_set_option(b"sigma_spinsym", b"1")
+        d1_half, d2_half = sq.osa.reduced_density_matrices(psi, psi, info)
+        assert np.max(np.abs(d1_half - d1_full)) < 1e-12 and np.max(np.abs(d2_half - d2_full)) < 1e-12
+        assert abs(np.trace(d1_half) - 2 * ne) < 1e-12
+        e_rdm = float(np.sum(h * d1_half) + 0.5 * np.sum(g * d2_half))
+        assert abs(e_rdm - float(psi @ orc.propagate_state([H_orc], psi, sp))) < 1e-10
+        if n <= 6:
+            r1 = orc.rdm1(psi, sp)
+            assert np.max(np.abs(d1_half - r1)) < 1e-11
+            assert np.max(np.abs(d2_half - orc.rdm2(psi, sp, r1))) < 1e-11
     finally:
         lib.sq_set_option(b"panel", b"0")
         lib.sq_set_option(b"sigma_spinsym", b"1")
