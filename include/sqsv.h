@@ -224,6 +224,16 @@ int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double
  * r's shard as mapped into this process; in and out must not alias.  No symmetry of g is assumed. */
 int sq_sigma_dist(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
                   double* const* out_ptrs_host, void* stream);
+/* Spin-flip symmetric sharded vectors (c[B,A] = lambda (-1)^popc(A & B) c[A,B]; every tUPS state on a closed-shell reference):
+ * sq_spinsym_measure_dist -> this rank's {max|c|, max|c[B,A] - phi c[A,B]|, max|c[B,A] + phi c[A,B]|} over its rows (take the MAX over
+ * the ranks; lambda = +1 / -1 if the second / third is <= 1e-12 of the first);  sq_sigma_dist_sym with lambda = +-1 builds
+ * out += (H - e_core) in on the kept half of every rank's rows only (*used_half = 1; 0: the full build ran, e.g. integrals without
+ * the real-orbital symmetry);  after a device-wide barrier sq_spinsym_mirror_dist writes the other half from its mirrors, and
+ * a second barrier ends the build.  Same energies as sq_sigma_dist (reference ups_wavefunction.py:770-784) at half the work. */
+int sq_spinsym_measure_dist(sq_space* sp, const double* const* in_ptrs_host, double* res3_host, void* stream);
+int sq_sigma_dist_sym(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
+                      double* const* out_ptrs_host, double lambda, int* used_half, void* stream);
+int sq_spinsym_mirror_dist(sq_space* sp, double* const* out_ptrs_host, double lambda, void* stream);
 
 /* The theta-gradient loop (ups_wavefunction.py:1114-1138) over operators [first,last) of an alpha-sharded (bra, ket) pair
  * whose row pairs may live on two GPUs (sa_single / pair-double operators): g_k = 2 <bra|T_k|ket>, then both vectors <- U_k,

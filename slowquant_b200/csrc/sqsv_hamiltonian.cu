@@ -1920,9 +1920,318 @@ scatter_E_peer_kernel(PeerViewRW pvo, const double* __restrict__ IN, double* OUT
 // out (all shards) += sum_pq k_pq E_pq |in> + 1/2 sum_pqrs g_pqrs E_pq E_rs |in> restricted to THIS rank's source rows.
 // Protocol (the caller's, slowquant_b200/distributed.py::sigma_sharded): every rank sets its out shard to e_core * in,
 // barrier, every rank calls sq_sigma_dist, stream synchronise, barrier -- then out holds H|in>.
+// ---------------------------------------------------------------------------------------------------------------------------
+// Spin-flip symmetric ALPHA-SHARDED vectors: half of the sigma build on every rank.  The upper triangle of the single-device
+// route would leave the ranks with the first rows nearly all of the work, so the kept half is the cyclic band
+//     K = { (ia, ib) : (ib - ia) mod N <= (N - 1) / 2,  ties (N even, distance N / 2) kept for ia < ib },
+// which holds the diagonal, exactly one of every pair (J, J^T), and the same number of columns (+-1) in every row.  Sources are the
+// kept determinants of the local rows, scattered to ALL their targets exactly as in the full build (S' = sum over kept sources,
+// diagonal sources with weight 1/2; folding the targets onto the kept half instead would turn the contiguous atomics of a warp into
+// column-strided ones -- measured: 8 x SLOWER than the full build over NVLink).  Since c[J^T] H|J^T> = lambda U (c[J] H|J>),
+// sigma = S' + lambda U S': after a device-wide barrier sq_spinsym_mirror_dist symmetrises the vector in place, pair by pair, 32 x 32
+// tiles through shared memory so that remote reads and writes are 256-byte row segments.  The caller starts from
+// out = 1/2 e_core in (the symmetrisation doubles it).
+// ---------------------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ bool half_kept(int64_t ia, int64_t ib, int64_t N) {
+  int64_t d = ib - ia;
+  if (d < 0) d += N;
+  if (N & 1) return d <= (N - 1) / 2;
+  return d < N / 2 || (d == N / 2 && ia < ib);
+}
+__host__ __device__ __forceinline__ int64_t half_count(int64_t ia, int64_t N) {   // kept columns of row ia: distances 0 .. count - 1
+  return (N & 1) ? (N + 1) / 2 : N / 2 + (ia < N / 2 ? 1 : 0);
+}
+// kept determinants of rows [r0, r1) in row-major order of (row, distance)
+__host__ __device__ __forceinline__ int64_t half_len(int64_t r0, int64_t r1, int64_t N) {
+  if (N & 1) return (r1 - r0) * ((N + 1) / 2);
+  const int64_t mid = N / 2, n1 = (r0 < mid ? (r1 < mid ? r1 : mid) - r0 : 0);
+  return n1 * (N / 2 + 1) + (r1 - r0 - n1) * (N / 2);
+}
+__device__ __forceinline__ void half_unrank(int64_t j, int64_t r0, int64_t r1, int64_t N, int64_t* ia, int64_t* ib) {
+  int64_t row, d;
+  if (N & 1) {
+    const int64_t c = (N + 1) / 2;
+    row = r0 + j / c;
+    d = j % c;
+  } else {
+    const int64_t mid = N / 2, n1 = (r0 < mid ? (r1 < mid ? r1 : mid) - r0 : 0), c1 = N / 2 + 1, c0 = N / 2;
+    if (j < n1 * c1) {
+      row = r0 + j / c1;
+      d = j % c1;
+    } else {
+      const int64_t jj = j - n1 * c1;
+      row = r0 + n1 + jj / c0;
+      d = jj % c0;
+    }
+  }
+  *ia = row;
+  int64_t c = row + d;
+  if (c >= N) c -= N;
+  *ib = c;
+}
+__device__ __forceinline__ int peer_owner(const int64_t* row_starts, int world, int64_t gr) {
+  int o = 0;
+  while (o + 1 < world && gr >= row_starts[o + 1]) ++o;
+  return o;
+}
+
+// per-rank maxima of the symmetry test over the local rows (all columns): res as in spinsym_check_kernel
+__global__ void __launch_bounds__(256)
+spinsym_check_peer_kernel(PeerView pv, const double* __restrict__ IN, int64_t N, int64_t row_begin, int64_t n_rows,
+                          const uint32_t* __restrict__ str, unsigned long long* __restrict__ res) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  for (int k = ty; k < 32; k += 8) {   // mirror tile: rows of column block bj (their owners' shards), columns = the local rows of block bi
+    const int64_t gr = bj * 32 + k, lc = bi * 32 + tx;
+    double v = 0.0;
+    if (gr < N && lc < n_rows) {
+      const int o = peer_owner(pv.row_starts, pv.world, gr);
+      v = pv.p[o][(gr - pv.row_starts[o]) * N + row_begin + lc];
+    }
+    tile[k][tx] = v;
+  }
+  __syncthreads();
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t lr = bi * 32 + k, c = bj * 32 + tx;
+    if (lr < n_rows && c < N) {
+      const double x = IN[lr * N + c], y = tile[tx][k];
+      const double ph = (__popc(__ldg(str + row_begin + lr) & __ldg(str + c)) & 1) ? -x : x;
+      m0 = fmax(m0, fmax(fabs(x), fabs(y)));
+      m1 = fmax(m1, fabs(y - ph));
+      m2 = fmax(m2, fabs(y + ph));
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    m0 = fmax(m0, __shfl_down_sync(0xffffffffu, m0, off));
+    m1 = fmax(m1, __shfl_down_sync(0xffffffffu, m1, off));
+    m2 = fmax(m2, __shfl_down_sync(0xffffffffu, m2, off));
+  }
+  if (tx == 0) {
+    atomicMax(res + 0, (unsigned long long)__double_as_longlong(m0));
+    atomicMax(res + 1, (unsigned long long)__double_as_longlong(m1));
+    atomicMax(res + 2, (unsigned long long)__double_as_longlong(m2));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+build_Dsym_half_peer_kernel(PeerView pv, const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len,
+                            const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB,
+                            const int32_t* __restrict__ rankA, const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin,
+                            int64_t row_end) {
+  const int n2 = n * n;
+  const ERec* sm = stage_etab<false>(etab, n2);
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < nS; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  int64_t ia, ib;
+  half_unrank(j, row_begin, row_end, NB, &ia, &ib);
+  const int64_t ia_loc = ia - row_begin;
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  auto elem = [&](int slot) -> double {
+    double v = 0.0;
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      const int64_t gr = __ldg(rankA + sa);
+      const int o = peer_owner(pv.row_starts, pv.world, gr);
+      v += (par ? -ra.s0 : ra.s0) * pv.p[o][(gr - pv.row_starts[o]) * NB + ib];
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      v += (par ? -rb.s0 : rb.s0) * IN[ia_loc * NB + __ldg(rankB + sb)];
+    }
+    return v;
+  };
+  int slot = 0;
+  for (int r = 0; r < n; ++r)
+    for (int q = 0; q <= r; ++q, ++slot) D[(int64_t)slot * W + t] = (r == q) ? elem(r * n + r) : elem(r * n + q) + elem(q * n + r);
+}
+
+__global__ void __launch_bounds__(256)
+scatter_E_half_peer_kernel(PeerViewRW pvo, const double* __restrict__ IN, const double* __restrict__ F, const double* __restrict__ kmat,
+                           const int* __restrict__ frow, int64_t W, int64_t j0, int64_t len, const ERec* __restrict__ etab, int n2,
+                           const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                           const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin, int64_t row_end) {
+  // the scatter of scatter_E_peer_kernel from the KEPT sources only, to ALL targets (no folding: the atomics of a warp stay
+  // contiguous, also the remote ones); a source on the diagonal enters with weight 1/2.  With S' this partial sum,
+  // sigma = S' + lambda U S' (spinsym_symmetrize_peer_kernel).
+  const ERec* sm = stage_etab<false>(etab, n2);
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j = j0 + t;
+  if (t >= W || j >= len) return;
+  int64_t ia, ib;
+  half_unrank(j, row_begin, row_end, NB, &ia, &ib);
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  const double wsrc = (ia == ib) ? 0.5 : 1.0;
+  const double cj = IN[(ia - row_begin) * NB + ib];
+  double* orow = pvo.p[peer_owner(pvo.row_starts, pvo.world, ia)] + (ia - pvo.row_starts[peer_owner(pvo.row_starts, pvo.world, ia)]) * NB;
+  double diag = 0.0;
+  for (int slot = 0; slot < n2; ++slot) {
+    const ERec ra = sm[2 * slot], rb = sm[2 * slot + 1];
+    const bool va = (a & ra.occ) == ra.occ && (a & ra.emp) == 0u;
+    const bool vb = (b & rb.occ) == rb.occ && (b & rb.emp) == 0u;
+    if (!va && !vb) continue;
+    const double val = wsrc * (F[(int64_t)__ldg(frow + slot) * W + t] + __ldg(kmat + slot) * cj);
+    if (va) {
+      const int par = (__popc(a & ra.parS) + __popc(b & ra.parO)) & 1;
+      const double sv = (par ? -ra.s0 : ra.s0) * val;
+      if (ra.flip == 0u) {
+        diag += sv;
+      } else {
+        const int64_t gr = __ldg(rankA + (a ^ ra.flip));
+        const int o = peer_owner(pvo.row_starts, pvo.world, gr);
+        atomicAdd_system(pvo.p[o] + (gr - pvo.row_starts[o]) * NB + ib, sv);
+      }
+    }
+    if (vb) {
+      const int par = (__popc(b & rb.parS) + __popc(a & rb.parO)) & 1;
+      const double sv = (par ? -rb.s0 : rb.s0) * val;
+      if (rb.flip == 0u) diag += sv;
+      else atomicAdd_system(orow + __ldg(rankB + (b ^ rb.flip)), sv);
+    }
+  }
+  atomicAdd_system(orow + ib, diag);
+}
+
+// In place: X <- X + lambda U X, i.e. x[I] <- x[I] + lambda phi(I) x[I^T] for every determinant.  Every unordered pair {I, I^T}
+// is handled by exactly one thread -- the one that owns the KEPT member (I = (ia, ib), ia a local row) -- which reads both
+// values (the mirror may sit in another rank's shard), and writes both; 32 x 32 tiles go through shared memory so that the
+// remote reads and writes are 256-byte row segments.  A diagonal element becomes (1 + lambda phi) x.
+__global__ void __launch_bounds__(256)
+spinsym_symmetrize_peer_kernel(PeerViewRW pvo, double* OUT /* == pvo.p[own rank] */, int64_t N, int64_t row_begin, int64_t n_rows,
+                               const uint32_t* __restrict__ str, double lambda) {
+  __shared__ double mir[32][33];    // mirror tile: rows of column block bj, columns = the local rows of block bi
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t gr = bj * 32 + k, lc = bi * 32 + tx;
+    double v = 0.0;
+    if (gr < N && lc < n_rows) {
+      const int o = peer_owner(pvo.row_starts, pvo.world, gr);
+      v = pvo.p[o][(gr - pvo.row_starts[o]) * N + row_begin + lc];
+    }
+    mir[k][tx] = v;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t lr = bi * 32 + k, c = bj * 32 + tx, gr = row_begin + lr;
+    double nm = 0.0;
+    bool wr = false;
+    if (lr < n_rows && c < N && half_kept(gr, c, N)) {
+      const double x = OUT[lr * N + c], y = mir[tx][k];
+      const double s = ((__popc(__ldg(str + gr) & __ldg(str + c)) & 1) ? -lambda : lambda);
+      OUT[lr * N + c] = x + s * y;
+      nm = y + s * x;
+      wr = gr != c;
+    }
+    mir[tx][k] = wr ? nm : __longlong_as_double(0x7ff8dead00000000LL);   // tag: not to be written back
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t gr = bj * 32 + k, lc = bi * 32 + tx;
+    const double v = mir[k][tx];
+    if (gr < N && lc < n_rows && __double_as_longlong(v) != 0x7ff8dead00000000LL) {
+      const int o = peer_owner(pvo.row_starts, pvo.world, gr);
+      pvo.p[o][(gr - pvo.row_starts[o]) * N + row_begin + lc] = v;
+    }
+  }
+}
+
+static int sigma_dist_impl(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
+                           double* const* out_ptrs_host, double lambda, int* used_half, void* stream);
+
 extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
                              double* const* out_ptrs_host, void* stream) {
+  return sigma_dist_impl(sp, h_act_host, g_act_host, in_ptrs_host, out_ptrs_host, 0.0, nullptr, stream);
+}
+
+// lambda = +-1: the input is spin-flip symmetric (c[B,A] = lambda phi c[A,B], measured by sq_spinsym_measure_dist + a MAX all-reduce):
+// build sigma on the kept half only.  *used_half = 1 if that happened (real-orbital integrals, n_alpha = n_beta): the caller then
+// puts a device-wide barrier and calls sq_spinsym_mirror_dist; 0: the full build ran (nothing else to do).
+extern "C" int sq_sigma_dist_sym(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
+                                 double* const* out_ptrs_host, double lambda, int* used_half, void* stream) {
+  if (!used_half || (lambda != 1.0 && lambda != -1.0 && lambda != 0.0)) return SQ_ERR_INVALID;
+  return sigma_dist_impl(sp, h_act_host, g_act_host, in_ptrs_host, out_ptrs_host, lambda, used_half, stream);
+}
+
+static int fill_peer_views(sq_space* sp, const double* const* in_ptrs_host, double* const* out_ptrs_host, PeerView* pin, PeerViewRW* pout) {
+  if (sp->world < 1 || sp->world > SQ_MAX_WORLD || (int)sp->row_starts.size() != sp->world + 1) {
+    sq_set_error("the space has no row partition (sq_space_set_partition)");
+    return SQ_ERR_INVALID;
+  }
+  for (int r = 0; r < SQ_MAX_WORLD; ++r) {
+    if (pin) pin->p[r] = (in_ptrs_host && r < sp->world) ? in_ptrs_host[r] : nullptr;
+    if (pout) pout->p[r] = (out_ptrs_host && r < sp->world) ? out_ptrs_host[r] : nullptr;
+    if (r < sp->world && ((pin && !pin->p[r]) || (pout && !pout->p[r]))) {
+      sq_set_error("missing shard pointer for rank %d", r);
+      return SQ_ERR_INVALID;
+    }
+  }
+  for (int r = 0; r <= SQ_MAX_WORLD; ++r) {
+    const int64_t v = r <= sp->world ? sp->row_starts[r] : sp->row_starts[sp->world];
+    if (pin) pin->row_starts[r] = v;
+    if (pout) pout->row_starts[r] = v;
+  }
+  if (pin) pin->world = sp->world;
+  if (pout) pout->world = sp->world;
+  return SQ_OK;
+}
+
+// res3_host = this rank's {max |c|, max |c[B,A] - phi c[A,B]|, max |c[B,A] + phi c[A,B]|} over its rows (the caller takes the MAX over
+// the ranks: lambda = +1 if the second, -1 if the third is <= 1e-12 of the first).  n_alpha = n_beta only; reads remote shards.
+extern "C" int sq_spinsym_measure_dist(sq_space* sp, const double* const* in_ptrs_host, double* res3_host, void* stream) {
+  if (!sp || !in_ptrs_host || !res3_host || sp->device < 0) return SQ_ERR_INVALID;
+  res3_host[0] = res3_host[1] = res3_host[2] = 0.0;
+  if (sp->n_alpha != sp->n_beta || sp->NA != sp->NB) {
+    res3_host[1] = res3_host[2] = 1.0;   // never symmetric
+    return SQ_OK;
+  }
+  PeerView pin;
+  SQ_CHECK(fill_peer_views(sp, in_ptrs_host, nullptr, &pin, nullptr));
+  const int64_t n_rows = sp->row_end - sp->row_begin;
+  if (n_rows == 0) return SQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  HamWork* w = nullptr;
+  SQ_CHECK(get_work(sp, false, true, &w));
+  if (!w->d_symres) SQ_CUDA(cudaMalloc(&w->d_symres, 3 * sizeof(unsigned long long)));
+  SQ_CUDA(cudaMemsetAsync(w->d_symres, 0, 3 * sizeof(unsigned long long), st));
+  spinsym_check_peer_kernel<<<dim3((unsigned)((sp->NB + 31) / 32), (unsigned)((n_rows + 31) / 32)), 256, 0, st>>>(
+      pin, pin.p[sp->rank], sp->NB, sp->row_begin, n_rows, sp->d_strA, w->d_symres);
+  SQ_CHECK(launch_error("spinsym_check_peer_kernel"));
+  SQ_CUDA(cudaMemcpyAsync(res3_host, w->d_symres, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(cudaStreamSynchronize(st));
+  return SQ_OK;
+}
+
+// second half of sq_sigma_dist_sym (after a device-wide barrier): the elements outside the kept band from their mirrors
+extern "C" int sq_spinsym_mirror_dist(sq_space* sp, double* const* out_ptrs_host, double lambda, void* stream) {
+  if (!sp || !out_ptrs_host || sp->device < 0 || (lambda != 1.0 && lambda != -1.0)) return SQ_ERR_INVALID;
+  PeerViewRW pout;
+  SQ_CHECK(fill_peer_views(sp, nullptr, out_ptrs_host, nullptr, &pout));
+  const int64_t n_rows = sp->row_end - sp->row_begin;
+  if (n_rows == 0) return SQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SQ_CUDA(cudaSetDevice(sp->device));
+  spinsym_symmetrize_peer_kernel<<<dim3((unsigned)((sp->NB + 31) / 32), (unsigned)((n_rows + 31) / 32)), 256, 0, st>>>(
+      pout, pout.p[sp->rank], sp->NB, sp->row_begin, n_rows, sp->d_strA, lambda);
+  return launch_error("spinsym_symmetrize_peer_kernel");
+}
+
+static int sigma_dist_impl(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
+                           double* const* out_ptrs_host, double lambda, int* used_half, void* stream) {
   SqRange nvtx_range("sq_sigma_dist");
+  if (used_half) *used_half = 0;
   if (!sp || !h_act_host || !g_act_host || !in_ptrs_host || !out_ptrs_host) return SQ_ERR_INVALID;
   if (sp->device < 0) return SQ_ERR_INVALID;
   if (sp->world < 1 || sp->world > SQ_MAX_WORLD || (int)sp->row_starts.size() != sp->world + 1) {
@@ -2019,6 +2328,29 @@ extern "C" int sq_sigma_dist(sq_space* sp, const double* h_act_host, const doubl
   double* out_dev = pout.p[sp->rank];
   const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
   allow_smem(scatter_E_peer_kernel, smem);
+  if (lambda != 0.0 && !(sym && sp->n_alpha == sp->n_beta && sp->NA == sp->NB)) {
+    sq_set_error("sq_sigma_dist_sym: the half build needs real-orbital integrals (g_pqrs = g_qprs = g_pqsr) and n_alpha = n_beta");
+    return SQ_ERR_UNSUPPORTED;
+  }
+  if (lambda != 0.0) {
+    // spin-flip symmetric input: the kept half of the local rows (cyclic band, see above)
+    const int64_t len_half = half_len(sp->row_begin, sp->row_end, sp->NB);
+    allow_smem(build_Dsym_half_peer_kernel, smem);
+    allow_smem(scatter_E_half_peer_kernel, smem);
+    for (int64_t j0 = 0; j0 < len_half; j0 += w->W) {
+      build_Dsym_half_peer_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(pin, in_dev, w->d_D[0], w->W, j0, len_half, w->d_etab, n,
+                                                                             sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB, sp->NB,
+                                                                             sp->row_begin, sp->row_end);
+      SQ_CHECK(launch_error("build_Dsym_half_peer_kernel"));
+      SQ_CHECK(sq_sigma_gemm(d_G, ldg, w->d_D[0], w->d_F[0], nrow, w->W, st));
+      scatter_E_half_peer_kernel<<<(unsigned)(w->W / 256), 256, smem, st>>>(pout, in_dev, w->d_F[0], d_k, w->d_frow, w->W, j0, len_half,
+                                                                            w->d_etab, n2, sp->d_strA, sp->d_strB, sp->d_rankA, sp->d_rankB,
+                                                                            sp->NB, sp->row_begin, sp->row_end);
+      SQ_CHECK(launch_error("scatter_E_half_peer_kernel"));
+    }
+    if (used_half) *used_half = 1;
+    return SQ_OK;
+  }
   for (int64_t j0 = 0; j0 < len; j0 += w->W) {   // one stream: gather -> DGEMM -> scatter per panel
     if (sym) {
       allow_smem(build_Dsym_peer_kernel, smem);

@@ -25,6 +25,7 @@ from slowquant_b200.ci_spaces import CI_Info
 import os as _os
 
 _RESHARD_DEFAULT = _os.environ.get("SQ_RESHARD", "1") != "0"   # SQ_RESHARD=0: peer-memory exchange route (A/B comparisons)
+_SPINSYM_SHARDED = _os.environ.get("SQ_SPINSYM_SHARDED", "1") != "0"   # 0: always the full sigma build of sharded vectors (A/B)
 
 
 def partition_prefix(n_orb: int, n_alpha: int, world: int) -> np.ndarray:
@@ -500,10 +501,44 @@ def sigma_sharded(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_c
         out = sp.alloc_state(zero=False)
     if out is state:
         raise ValueError("sigma_sharded: out must not be the input state")
+    PD = C.POINTER(C.c_double)
+    # Spin-flip symmetric input (c[B,A] = lambda (-1)^popc(A & B) c[A,B]: every tUPS state on a closed-shell reference) needs half
+    # of the build: MEASURED here (max over the ranks), never assumed; anything else takes the full build.
+    lam = 0.0
+    info = sp.ci_info
+    real_orbital = bool(np.allclose(g, g.transpose(1, 0, 2, 3), rtol=0.0, atol=1e-14 * max(1.0, float(np.max(np.abs(g))))) and
+                        np.allclose(g, g.transpose(0, 1, 3, 2), rtol=0.0, atol=1e-14 * max(1.0, float(np.max(np.abs(g))))) and
+                        np.allclose(h, h.T, rtol=0.0, atol=1e-14 * max(1.0, float(np.max(np.abs(h))))))
+    if _SPINSYM_SHARDED and real_orbital and info.num_active_elec_alpha == info.num_active_elec_beta:
+        torch.cuda.synchronize()
+        sp.barrier()    # every in shard is complete before the remote reads of the measurement
+        res = np.zeros(3)
+        _lib.check(lib.sq_spinsym_measure_dist(info._handle, state._peer_ptrs, res.ctypes.data_as(PD), osa._stream()))
+        if sp.world > 1:
+            t = torch.from_numpy(res).to(state.local.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res = t.cpu().numpy()
+        if res[0] > 0.0 and res[1] <= 1e-12 * res[0]:
+            lam = 1.0
+        elif res[0] > 0.0 and res[2] <= 1e-12 * res[0]:
+            lam = -1.0
+    if lam != 0.0:
+        # S' = sum over the kept half of the sources (all targets), then sigma = S' + lambda U S' in place (doubles the e_core term)
+        torch.mul(state.local, 0.5 * float(e_core), out=out.local)
+        torch.cuda.synchronize()
+        sp.barrier()
+        used = C.c_int(0)
+        _lib.check(lib.sq_sigma_dist_sym(info._handle, h.ctypes.data_as(PD), g.ctypes.data_as(PD), state._peer_ptrs, out._peer_ptrs,
+                                         lam, C.byref(used), osa._stream()))
+        torch.cuda.synchronize()
+        sp.barrier()        # all contributions of the kept sources have landed on every rank
+        _lib.check(lib.sq_spinsym_mirror_dist(info._handle, out._peer_ptrs, lam, osa._stream()))
+        torch.cuda.synchronize()
+        sp.barrier()        # symmetrised
+        return out
     torch.mul(state.local, float(e_core), out=out.local)
     torch.cuda.synchronize()
     sp.barrier()        # every out shard is initialised and every in shard complete before remote reads / atomics start
-    PD = C.POINTER(C.c_double)
     _lib.check(lib.sq_sigma_dist(sp.ci_info._handle, h.ctypes.data_as(PD), g.ctypes.data_as(PD), state._peer_ptrs, out._peer_ptrs, osa._stream()))
     torch.cuda.synchronize()
     sp.barrier()        # all remote contributions have landed

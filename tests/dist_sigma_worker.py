@@ -28,7 +28,7 @@ def main():
     from slowquant_b200.operators import hamiltonian_0i_0a
 
     worst = 0.0
-    for n, na, nb, symmetric in [(6, 3, 3, False), (8, 4, 4, True), (9, 4, 5, False), (10, 5, 5, True)]:
+    for n, na, nb, symmetric in [(6, 3, 3, False), (6, 3, 3, True), (8, 4, 4, True), (9, 4, 5, False), (10, 5, 5, True)]:
         sp = ShardedSpace(0, n, 0, na, nb, device=local_rank)
         info = get_indexing(0, n, 0, na, nb, device=local_rank)
         rng = np.random.default_rng(2000 + n)       # same stream on every rank
@@ -77,7 +77,39 @@ def main():
             if rank == 0:
                 print(f"    theta gradient: re-sharded {np.max(np.abs(g1 - g2)):.2e}, fused-local {np.max(np.abs(g1 - g5)):.2e}, shift rule {np.max(np.abs(g1 - g3)):.2e}, "
                       f"peer kernel {np.max(np.abs(g1 - g4)):.2e}", flush=True)
-        e = torch.tensor([err, max(err_e, err_g)], dtype=torch.float64, device="cuda")
+        # a spin-flip symmetric vector (a tUPS state on the closed-shell reference; lambda = +1 / -1 for even / odd pair counts):
+        # the half build of the sharded sigma (kept cyclic band + mirror pass) against the full build and the single-GPU sigma
+        err_s = 0.0
+        if na == nb and symmetric:
+            import slowquant_b200.distributed as D
+
+            lay_s = UpsStructure()
+            lay_s.create_tiled(n, {"n_layers": 2, "do_tups": True})
+            th_s = rng.uniform(-np.pi, np.pi, lay_s.n_params)
+            hf = np.zeros(info.num_det)
+            hf[0] = 1.0
+            psi = osa.construct_ups_state(hf, info, th_s.tolist(), lay_s)
+            osa._lib.load().sq_set_option(b"sigma_spinsym", b"0")           # the single-GPU reference: full build
+            ref_s = osa.propagate_state([hamiltonian_0i_0a(h, g, 0, n)], psi, info) + e_core * psi
+            osa._lib.load().sq_set_option(b"sigma_spinsym", b"1")
+            st_s = sp.alloc_state()
+            st_s.set_from_full(psi)
+            outs = []
+            for flag in (True, False):
+                D._SPINSYM_SHARDED = flag
+                sg = sigma_sharded(st_s, h, g, e_core)
+                outs.append(sg.local.cpu().numpy().copy())
+                sg.close()
+            D._SPINSYM_SHARDED = True
+            st_s.close()
+            sc = float(np.max(np.abs(ref_s)))
+            if hi > lo:
+                err_s = max(float(np.max(np.abs(outs[0] - ref_s[lo:hi]))), float(np.max(np.abs(outs[1] - ref_s[lo:hi]))),
+                            float(np.max(np.abs(outs[0] - outs[1])))) / sc
+            if rank == 0:
+                print(f"    spin-flip symmetric state: half build vs single GPU {np.max(np.abs(outs[0] - ref_s[lo:hi])) / sc:.2e}, "
+                      f"half vs full sharded build {np.max(np.abs(outs[0] - outs[1])) / sc:.2e}", flush=True)
+        e = torch.tensor([max(err, err_s), max(err_e, err_g)], dtype=torch.float64, device="cuda")
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(f"CAS({na + nb},{n}) world={world} symmetric={symmetric}: sigma rel. max|diff| {e[0]:.2e}, energy / theta gradient {e[1]:.2e}", flush=True)
