@@ -215,6 +215,10 @@ int sq_layout_op_blocked(const sq_layout* lay, int k);
  * alpha partners on other ranks are read in place over NVLink.  All ranks must have finished writing their shards. */
 int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host,
                   double* rdm1_host, double* rdm2_host, void* stream);
+/* sq_rdm12_dist for a spin-flip symmetric vector (bra == ket; lambda = +-1 from sq_spinsym_measure_dist and a MAX all-reduce): the
+ * panels hold the kept half of this rank's rows only, off-diagonal columns weighted by sqrt(2).  lambda = 0: sq_rdm12_dist. */
+int sq_rdm12_dist_sym(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host, double lambda,
+                      double* rdm1_host, double* rdm2_host, void* stream);
 
 /* H|in> of an alpha-sharded vector (the string path of energy_elec, ups_wavefunction.py:770-784, and the sigma vector
  * behind the theta gradient, :1091-1112), accumulated: every rank treats the determinants of ITS rows as sources, reads

@@ -89,6 +89,7 @@ def _declare(lib: C.CDLL) -> None:
         "sq_layout_op_stats": (i32, [vp, i32, pi64]),
         "sq_ups_apply_dist": (i32, [vp, vp, pdbl, i32, i32, i32, C.POINTER(vp), vp]),
         "sq_rdm12_dist": (i32, [vp, C.POINTER(vp), C.POINTER(vp), pdbl, pdbl, vp]),
+        "sq_rdm12_dist_sym": (i32, [vp, C.POINTER(vp), C.POINTER(vp), dbl, pdbl, pdbl, vp]),
         "sq_sigma_dist": (i32, [vp, pdbl, pdbl, C.POINTER(vp), C.POINTER(vp), vp]),
         "sq_spinsym_measure_dist": (i32, [vp, C.POINTER(vp), pdbl, vp]),
         "sq_sigma_dist_sym": (i32, [vp, pdbl, pdbl, C.POINTER(vp), C.POINTER(vp), dbl, C.POINTER(C.c_int), vp]),
@@ -110,7 +111,7 @@ EXPORTED_SYMBOLS = (
     "sq_grad_action sq_ups_grad_sweep sq_ups_energy_grad sq_apply_strings sq_dot sq_axpy sq_scale_copy sq_sigma sq_rdm12 "
     "sq_debug_string_action sq_launch_count sq_partition_prefix sq_space_set_partition sq_dist_alloc sq_dist_free "
     "sq_ipc_export sq_ipc_import sq_ipc_close sq_layout_needs_exchange sq_ups_apply_dist sq_rdm12_dist sq_sigma_dist sq_layout_op_stats sq_layout_plan_export sq_debug_etab_closed_form sq_debug_win3_emulate sq_ups_grad_sweep_dist "
-    "sq_space_create_constrained sq_ups_apply_list sq_reshard_rows sq_layout_op_blocked sq_layout_plan_stats_list sq_ups_apply_batch sq_ups_grad_sweep_list sq_ups_grad_sweep_list_rev sq_spinsym_measure_dist sq_sigma_dist_sym sq_spinsym_mirror_dist"
+    "sq_space_create_constrained sq_ups_apply_list sq_reshard_rows sq_layout_op_blocked sq_layout_plan_stats_list sq_ups_apply_batch sq_ups_grad_sweep_list sq_ups_grad_sweep_list_rev sq_spinsym_measure_dist sq_sigma_dist_sym sq_spinsym_mirror_dist sq_rdm12_dist_sym"
 ).split()
 
 

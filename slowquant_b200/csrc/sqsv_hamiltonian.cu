@@ -1594,6 +1594,10 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
 
 static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev, const PeerView* pv_bra,
                       const PeerView* pv_ket, double* rdm1_host, double* rdm2_host, void* stream);
+static int launch_build_DSA_peer(sq_space* sp, const PeerView* pv, const double* in, double* D, int64_t W, int64_t j0, bool half,
+                                 cudaStream_t st);
+static int64_t half_len_host(const sq_space* sp);
+static thread_local double t_rdm_dist_lambda = 0.0;   // set by sq_rdm12_dist_sym around its call of rdm12_impl
 
 extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_dev, double* rdm1_host,
                         double* rdm2_host, void* stream) {
@@ -1604,6 +1608,19 @@ extern "C" int sq_rdm12(sq_space* sp, const double* bra_dev, const double* ket_d
 
 // This rank's PARTIAL sums over its rows of an alpha-sharded vector (the caller adds the ranks' results: everything is
 // linear in the partial sums).  *_ptrs_host[r] = base pointer of rank r's shard as mapped into this process.
+// sq_rdm12_dist for a spin-flip symmetric vector (bra == ket; lambda = +-1 measured by sq_spinsym_measure_dist + MAX all-reduce):
+// the S / A panels of the kept half of this rank's rows, weighted.  lambda = 0: same as sq_rdm12_dist.
+extern "C" int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host,
+                             double* rdm1_host, double* rdm2_host, void* stream);
+extern "C" int sq_rdm12_dist_sym(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host, double lambda,
+                                 double* rdm1_host, double* rdm2_host, void* stream) {
+  if (lambda != 0.0 && lambda != 1.0 && lambda != -1.0) return SQ_ERR_INVALID;
+  t_rdm_dist_lambda = lambda;
+  const int rc = sq_rdm12_dist(sp, bra_ptrs_host, ket_ptrs_host, rdm1_host, rdm2_host, stream);
+  t_rdm_dist_lambda = 0.0;
+  return rc;
+}
+
 extern "C" int sq_rdm12_dist(sq_space* sp, const double* const* bra_ptrs_host, const double* const* ket_ptrs_host,
                              double* rdm1_host, double* rdm2_host, void* stream) {
   if (!sp || !bra_ptrs_host || !ket_ptrs_host || !rdm1_host) return SQ_ERR_INVALID;
@@ -1716,7 +1733,7 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   int n_split = 1;
   // bra == ket (real): two symmetric Gram matrices of the S / A generators instead of the n^2 x n^2 one (a quarter of the products)
   const int nS = n * (n + 1) / 2, nA = n2 - nS, GR = sq_gram_sym_rows();
-  const bool sym_route = g_rdm_sym && same && rdm2_host && !pv_ket && n_elec > 0 && nS <= GR;
+  const bool sym_route = g_rdm_sym && same && rdm2_host && n_elec > 0 && nS <= GR;   // sharded vectors too (peer gathers)
   if (sym_route) {
     if (!w->d_gsym) SQ_CUDA(cudaMalloc(&w->d_gsym, sizeof(double) * 2 * (size_t)GR * GR));
     SQ_CHECK(sq_gram_sym_begin(w->n_sm, &w->d_gram, &w->gram_doubles, &n_split, st));
@@ -1725,12 +1742,14 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   }
   // spin-flip symmetric vector (measured): the S / A panels of the determinants above / on the diagonal only, weighted
   bool tri = false;
-  if (sym_route && g_sigma_spinsym) {
+  if (sym_route && g_sigma_spinsym && !pv_ket) {
     double lambda = 0.0;
     SQ_CHECK(spinsym_measure(sp, w, ket_dev, st, &lambda));
     tri = lambda != 0.0;
   }
-  const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : len;
+  // sharded vector: the caller measured the symmetry over all ranks (sq_rdm12_dist_sym); the kept cyclic band of the local rows
+  const bool half_band = sym_route && pv_ket && t_rdm_dist_lambda != 0.0 && sp->n_alpha == sp->n_beta && sp->NA == sp->NB;
+  const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : (half_band ? half_len_host(sp) : len);
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -1749,6 +1768,8 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
       build_DSA_tri_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len_eff, n, sp->d_strA, sp->d_strB,
                                                                       sp->d_rankA, sp->d_rankB, sp->NB);
       SQ_CHECK(launch_error("build_DSA_tri_kernel"));
+    } else if (sym_route && pv_ket) {
+      SQ_CHECK(launch_build_DSA_peer(sp, pv_ket, ket_dev, Dket, w->W, j0, half_band, s_build));
     } else if (sym_route) {
       build_DSA_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len, n, sp->d_strA, sp->d_strB, sp->d_rankA,
                                                                   sp->d_rankB, sp->NB, sp->row_begin);
@@ -2146,6 +2167,77 @@ spinsym_symmetrize_peer_kernel(PeerViewRW pvo, double* OUT /* == pvo.p[own rank]
     }
   }
 }
+
+// S / A generator panel of an alpha-sharded vector (alpha partners through the peer mappings).  HALF: only the kept cyclic band of the
+// local rows, off-diagonal columns weighted by sqrt(2) (spin-flip symmetric vector: the Gram sums over all determinants are
+// 2 sum_kept-off-diagonal + sum_diagonal).
+template <bool HALF>
+__global__ void __launch_bounds__(256)
+build_DSA_peer_kernel(PeerView pv, const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t j0, int64_t len, int n,
+                      const uint32_t* __restrict__ strA, const uint32_t* __restrict__ strB, const int32_t* __restrict__ rankA,
+                      const int32_t* __restrict__ rankB, int64_t NB, int64_t row_begin, int64_t row_end) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= W) return;
+  const int64_t j = j0 + t;
+  const int n2 = n * n, nS = n * (n + 1) / 2;
+  if (j >= len) {
+    for (int slot = 0; slot < n2; ++slot) D[(int64_t)slot * W + t] = 0.0;
+    return;
+  }
+  int64_t ia, ib;
+  if (HALF) {
+    half_unrank(j, row_begin, row_end, NB, &ia, &ib);
+  } else {
+    const int64_t l = j / NB;
+    ia = row_begin + l;
+    ib = j - l * NB;
+  }
+  const int64_t ia_loc = ia - row_begin;
+  const uint32_t a = __ldg(strA + ia), b = __ldg(strB + ib);
+  const double wgt = (HALF && ia != ib) ? 1.4142135623730951 : 1.0;
+  auto elem = [&](int p, int q) -> double {
+    double v = 0.0;
+    const ERec ra = erec_closed(p, q, 0), rb = erec_closed(p, q, 1);
+    if ((a & ra.tocc) == ra.tocc && (a & ra.temp) == 0u) {
+      const uint32_t sa = a ^ ra.flip;
+      const int par = (__popc(sa & ra.parS) + __popc(b & ra.parO)) & 1;
+      const int64_t gr = __ldg(rankA + sa);
+      const int o = peer_owner(pv.row_starts, pv.world, gr);
+      v += (par ? -ra.s0 : ra.s0) * pv.p[o][(gr - pv.row_starts[o]) * NB + ib];
+    }
+    if ((b & rb.tocc) == rb.tocc && (b & rb.temp) == 0u) {
+      const uint32_t sb = b ^ rb.flip;
+      const int par = (__popc(sb & rb.parS) + __popc(a & rb.parO)) & 1;
+      v += (par ? -rb.s0 : rb.s0) * IN[ia_loc * NB + __ldg(rankB + sb)];
+    }
+    return v;
+  };
+  int ss = 0, as = nS;
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q <= p; ++q, ++ss) {
+      if (p == q) {
+        D[(int64_t)ss * W + t] = wgt * elem(p, p);
+      } else {
+        const double x = elem(p, q), y = elem(q, p);
+        D[(int64_t)ss * W + t] = wgt * (x + y);
+        D[(int64_t)as * W + t] = wgt * (x - y);
+        ++as;
+      }
+    }
+}
+// launcher used by rdm12_impl (defined above these kernels); *len_eff = number of panel columns of this rank
+static int launch_build_DSA_peer(sq_space* sp, const PeerView* pv, const double* in, double* D, int64_t W, int64_t j0, bool half,
+                                 cudaStream_t st) {
+  const int64_t len = half ? half_len(sp->row_begin, sp->row_end, sp->NB) : sp->local_len();
+  if (half)
+    build_DSA_peer_kernel<true><<<(unsigned)(W / 256), 256, 0, st>>>(*pv, in, D, W, j0, len, sp->n_orb, sp->d_strA, sp->d_strB, sp->d_rankA,
+                                                                     sp->d_rankB, sp->NB, sp->row_begin, sp->row_end);
+  else
+    build_DSA_peer_kernel<false><<<(unsigned)(W / 256), 256, 0, st>>>(*pv, in, D, W, j0, len, sp->n_orb, sp->d_strA, sp->d_strB, sp->d_rankA,
+                                                                      sp->d_rankB, sp->NB, sp->row_begin, sp->row_end);
+  return launch_error("build_DSA_peer_kernel");
+}
+static int64_t half_len_host(const sq_space* sp) { return half_len(sp->row_begin, sp->row_end, sp->NB); }
 
 static int sigma_dist_impl(sq_space* sp, const double* h_act_host, const double* g_act_host, const double* const* in_ptrs_host,
                            double* const* out_ptrs_host, double lambda, int* used_half, void* stream);

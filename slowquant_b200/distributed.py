@@ -448,6 +448,25 @@ def dot_sharded(a: ShardedState, b: ShardedState) -> float:
     return float(t.item())
 
 
+def _measure_spin_flip_symmetry(state: "ShardedState") -> float:
+    """lambda = +-1 if the sharded vector satisfies c[B,A] = lambda (-1)^popc(A & B) c[A,B] to 1e-12 of its largest amplitude (measured
+    on every rank's rows against the mirrored elements in the owners' shards, MAX over the ranks), else 0.  Every shard must be
+    complete (barrier) before the call."""
+    lib = _lib.load()
+    sp = state.space
+    res = np.zeros(3)
+    _lib.check(lib.sq_spinsym_measure_dist(sp.ci_info._handle, state._peer_ptrs, res.ctypes.data_as(C.POINTER(C.c_double)), osa._stream()))
+    if sp.world > 1:
+        t = torch.from_numpy(res).to(state.local.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res = t.cpu().numpy()
+    if res[0] > 0.0 and res[1] <= 1e-12 * res[0]:
+        return 1.0
+    if res[0] > 0.0 and res[2] <= 1e-12 * res[0]:
+        return -1.0
+    return 0.0
+
+
 def rdm12_sharded(bra: ShardedState, ket: ShardedState, want_rdm2: bool = True) -> tuple[np.ndarray, np.ndarray | None]:
     """Active-space (transition) 1-/2-RDMs of alpha-sharded vectors: every rank contracts the determinants of its own rows
     (alpha partners that live on another GPU are read in place through the peer mappings, ``sq_rdm12_dist``), the n^2 + n^4
@@ -458,11 +477,16 @@ def rdm12_sharded(bra: ShardedState, ket: ShardedState, want_rdm2: bool = True) 
     d1 = np.zeros((n, n), dtype=np.float64)
     d2 = np.zeros((n, n, n, n), dtype=np.float64) if want_rdm2 else None
     PD = C.POINTER(C.c_double)
+    torch.cuda.synchronize()
     sp.barrier()        # every shard is complete before anybody reads it remotely
+    lam = 0.0
+    info = sp.ci_info
+    if _SPINSYM_SHARDED and bra is ket and want_rdm2 and info.num_active_elec_alpha == info.num_active_elec_beta:
+        lam = _measure_spin_flip_symmetry(ket)      # +-1: the panels hold the kept half of every rank's rows only (weighted)
     _lib.check(
-        lib.sq_rdm12_dist(
-            sp.ci_info._handle, bra._peer_ptrs, ket._peer_ptrs, d1.ctypes.data_as(PD), d2.ctypes.data_as(PD) if want_rdm2 else None,
-            osa._stream(),
+        lib.sq_rdm12_dist_sym(
+            sp.ci_info._handle, bra._peer_ptrs, ket._peer_ptrs, lam, d1.ctypes.data_as(PD),
+            d2.ctypes.data_as(PD) if want_rdm2 else None, osa._stream(),
         )
     )
     sp.barrier()        # ... and nobody changes a shard while a neighbour may still be reading it
@@ -512,16 +536,7 @@ def sigma_sharded(state: ShardedState, h_act: np.ndarray, g_act: np.ndarray, e_c
     if _SPINSYM_SHARDED and real_orbital and info.num_active_elec_alpha == info.num_active_elec_beta:
         torch.cuda.synchronize()
         sp.barrier()    # every in shard is complete before the remote reads of the measurement
-        res = np.zeros(3)
-        _lib.check(lib.sq_spinsym_measure_dist(info._handle, state._peer_ptrs, res.ctypes.data_as(PD), osa._stream()))
-        if sp.world > 1:
-            t = torch.from_numpy(res).to(state.local.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            res = t.cpu().numpy()
-        if res[0] > 0.0 and res[1] <= 1e-12 * res[0]:
-            lam = 1.0
-        elif res[0] > 0.0 and res[2] <= 1e-12 * res[0]:
-            lam = -1.0
+        lam = _measure_spin_flip_symmetry(state)
     if lam != 0.0:
         # S' = sum over the kept half of the sources (all targets), then sigma = S' + lambda U S' in place (doubles the e_core term)
         torch.mul(state.local, 0.5 * float(e_core), out=out.local)

@@ -94,14 +94,21 @@ def main():
             osa._lib.load().sq_set_option(b"sigma_spinsym", b"1")
             st_s = sp.alloc_state()
             st_s.set_from_full(psi)
-            outs = []
+            outs, rdms = [], []
             for flag in (True, False):
                 D._SPINSYM_SHARDED = flag
                 sg = sigma_sharded(st_s, h, g, e_core)
                 outs.append(sg.local.cpu().numpy().copy())
                 sg.close()
+                rdms.append(D.rdm12_sharded(st_s, st_s))      # S / A Gram route on the shards; half band when the flag is on
             D._SPINSYM_SHARDED = True
             st_s.close()
+            r1, r2 = osa.reduced_density_matrices(psi, psi, info)
+            err_r = max(float(np.max(np.abs(rdms[0][0] - r1))), float(np.max(np.abs(rdms[0][1] - r2))),
+                        float(np.max(np.abs(rdms[1][0] - r1))), float(np.max(np.abs(rdms[1][1] - r2))))
+            err_e = max(err_e, err_r)
+            if rank == 0:
+                print(f"    RDMs of the symmetric state on the shards (half band / full) vs single GPU: {err_r:.2e}", flush=True)
             sc = float(np.max(np.abs(ref_s)))
             if hi > lo:
                 err_s = max(float(np.max(np.abs(outs[0] - ref_s[lo:hi]))), float(np.max(np.abs(outs[1] - ref_s[lo:hi]))),
