@@ -294,6 +294,9 @@ quad_kernel(double* __restrict__ C, const int4* __restrict__ colIdx, const int* 
 // bra and ket for SIX ansatz operators (tile_grad_kernel_v2: one per three).  Gauge flips as in quad_apply: inside a brick's
 // 4-amplitude group every alpha / beta generator element is +1 (sigma on the pair double, folded into GradSteps::sig / s).
 // ---------------------------------------------------------------------------------------------
+#ifndef QGRAD_FULL_BATCH
+#define QGRAD_FULL_BATCH 0   // 1: full batches for every tile shape -- measured: no change (173.5 vs 173.2 ms)
+#endif
 struct GradSteps {
   int n;
   int kind[SQ_MAX_PROGRAM];
@@ -396,7 +399,7 @@ __device__ __forceinline__ void quad_rows_grad(double* __restrict__ BRA, double*
                                                const int4 cl, const int cf, const QuadGradProg& qp, double* __restrict__ acc) {
   using S = Shape<R1, R2, C1, C2>;
   constexpr int TILE = S::TILE;
-  constexpr int GH = S::G > 1 ? S::G / 2 : 1;   // 8 amplitudes of each vector in flight per thread (16 for the 4 x 4 tile)
+  constexpr int GH = QGRAD_FULL_BATCH ? S::G : (S::G > 1 ? S::G / 2 : 1);   // amplitudes of each vector in flight per thread: 16, or 8 (16 for the 4 x 4 tile)
   constexpr int NBATCH = QUAD_ROWS / GH;
 #pragma unroll 1
   for (int b = 0; b < NBATCH; ++b) {
