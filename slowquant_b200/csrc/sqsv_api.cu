@@ -682,6 +682,7 @@ extern "C" int sq_set_option(const char* name, const char* value) {
   }
   if (strcmp(name, "sigma_spinsym") == 0) {   // sigma of a spin-flip symmetric vector from the determinants above the diagonal: "1" (default) / "0"
     sq_hamiltonian_set_sigma_spinsym(!(value && value[0] == '0'));
+    sq_hamiltonian_set_spinsym_blk(!(value && strcmp(value, "tri") == 0));   // "tri": determinant-per-thread kernels instead of the 32 x 32 blocks
     return SQ_OK;
   }
   if (strcmp(name, "sigma_fused") == 0) {   // sigma: "0" (default) three-kernel panel pipeline, "1" fused gather -> DMMA -> scatter kernel (slower)

@@ -184,6 +184,10 @@ static int get_work(sq_space* sp, bool need_second_D, bool need_F, HamWork** out
     Wmax = (Wmax / 256) * 256;
     if (Wmax < 256) Wmax = 256;
     int64_t len = sp->local_len();
+    // blocked half build (build_blk_kernel: one CTA per 1024 determinants, four CTAs per SM): whole waves of CTAs per panel
+    const int64_t unit = (int64_t)w->n_sm * 4;
+    if (g_panel_width <= 0 && sp->n_alpha == sp->n_beta && sp->NA == sp->NB && len >= 8 * Wmax && Wmax / 1024 >= unit / 2)
+      Wmax = std::max<int64_t>(1, (Wmax / 1024 + unit / 2) / unit) * unit * 1024;
     w->W = len < Wmax ? ((len + 255) / 256) * 256 : Wmax;
     if (w->W < 256) w->W = 256;
   }
@@ -1397,6 +1401,303 @@ build_DSA_tri_kernel(const double* __restrict__ IN, double* __restrict__ D, int6
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Spin-flip symmetric vectors, blocked panels: EVERY gather and EVERY atomic of the half build as a contiguous 256-byte run.
+//
+// The determinant-per-thread kernels above run lanes along the beta index: alpha partners (another row, same columns) are
+// coalesced, beta partners (same row, scattered columns) cost one 32-byte sector per lane plus a rank look-up per lane, and those
+// sector requests are what bounds them (L1 wavefronts).  For a spin-flip symmetric vector the beta partner can be read through its
+// mirror, c[A, B'] = lambda phi(A, B') c[B', A]: row B', columns along A.  So a CTA takes a 32 x 32 block of determinants (rows
+// ia0.., columns ib0.. of a block above / on the diagonal) and works on it in two thread mappings,
+//     alpha mapping: a warp holds a row (string uniform), lanes along the columns  -> alpha partners c[A', B0 + lane]
+//     beta mapping : a warp holds a column (string uniform), lanes along the rows  -> beta partners lambda phi c[B', A0 + lane]
+// exchanging the per-determinant values between the mappings through a padded shared-memory tile (double-buffered: one barrier
+// per generator pair).  Screens, parities and rank look-ups are warp-uniform.
+// Scatter: with X = sum over the kept sources (weight 1/2 on the diagonal) of their alpha and beta contributions, H psi =
+// X + lambda U X; the beta contributions are added at their MIRRORED targets (row B', columns along A: coalesced atomics), i.e. the
+// kernel accumulates Y = X_alpha + lambda U X_beta, and sigma = Y + lambda U Y comes from one in-place symmetrisation pass
+// (out starts as e_core / 2 * in).  Panel column t <-> (block t / 1024 of the panel, row (t % 1024) / 32, column t % 32); blocks in
+// tri_unrank order over the (NA / 32)^2 block grid; lower-triangle determinants of diagonal blocks carry zero weight.
+// ---------------------------------------------------------------------------------------------------------------------------
+#define BLK_TS (32 * 33)
+#define BLK_SG 2   // generator pairs per barrier round: the loads of a round (one per determinant, spin and pair) are in flight together
+
+// For p != q at most one of E_pq, E_qp passes the screen of a string (p occupied and q empty, or the reverse): one record, one access.
+struct BlkSel {
+  uint32_t flip, parS;
+  int s0;
+  bool any, second;
+};
+template <bool SRC>
+__device__ __forceinline__ BlkSel blk_select(const ERec& r1, const ERec& r2, bool pair, uint32_t s) {
+  const bool v1 = SRC ? ((s & r1.occ) == r1.occ && (s & r1.emp) == 0u) : ((s & r1.tocc) == r1.tocc && (s & r1.temp) == 0u);
+  const bool v2 = pair && (SRC ? ((s & r2.occ) == r2.occ && (s & r2.emp) == 0u) : ((s & r2.tocc) == r2.tocc && (s & r2.temp) == 0u));
+  return {v1 ? r1.flip : r2.flip, v1 ? r1.parS : r2.parS, v1 ? r1.s0 : r2.s0, v1 || v2, v2};
+}
+
+// Everything that depends on (string, generator pair) only is worked out ONCE per CTA for its 32 row and 32 column strings:
+//   act[(role * nS + slot) * 32 + j], j = 4 * (r % 8) + r / 8 for string r of the block (role 0: row strings under E^alpha, role 1: column
+//   strings under E^beta): -1 if neither E_pq nor E_qp acts, else  rank of the partner string | E_qp taken << 29 | sign << 30
+//   (sign = s0 and the same-spin parity of the SOURCE string; SRC: the string is the source, else the target of the operator);
+//   info[slot] = {other-spin parity masks of E^alpha_pq, E^alpha_qp, E^beta_pq, E^beta_qp | flip mask, p << 8 | q, -, -}.
+// The main loops are left with one uniform 16-byte table load per 4 determinants, one popcount and the memory access itself.
+struct BlkSmem {
+  int32_t* act;
+  uint4* info;
+  double* T;
+};
+template <bool SRC>
+__device__ __forceinline__ BlkSmem blk_stage_actions(const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ str,
+                                                     const int32_t* __restrict__ rank, int64_t N, int64_t ia0, int64_t ib0) {
+  extern __shared__ uint4 blk_raw[];
+  const int n2 = n * n, nS = n * (n + 1) / 2;
+  BlkSmem S;
+  S.act = reinterpret_cast<int32_t*>(blk_raw);
+  S.info = blk_raw + 2 * nS * 8;
+  S.T = reinterpret_cast<double*>(S.info + 2 * nS);
+  ERec* const et = reinterpret_cast<ERec*>(S.T);   // the records, staged in the tile area while the tables are built
+  for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256) reinterpret_cast<uint32_t*>(et)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
+  __syncthreads();
+  for (int s = threadIdx.x; s < nS; s += 256) {
+    int p = (int)((sqrtf(8.0f * (float)s + 1.0f) - 1.0f) * 0.5f);
+    while (p * (p + 1) / 2 > s) --p;
+    while ((p + 1) * (p + 2) / 2 <= s) ++p;
+    const int q = s - p * (p + 1) / 2;
+    S.info[2 * s] = make_uint4(et[2 * (p * n + q)].parO, et[2 * (q * n + p)].parO, et[2 * (p * n + q) + 1].parO, et[2 * (q * n + p) + 1].parO);
+    S.info[2 * s + 1] = make_uint4(et[2 * (p * n + q) + 1].flip, (uint32_t)(p << 8 | q), 0u, 0u);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * nS * 32; idx += 256) {
+    const int role = idx >= nS * 32, rem = idx - role * nS * 32, s = rem >> 5, j = rem & 31, r = (j >> 2) + 8 * (j & 3);
+    const uint32_t pq = S.info[2 * s + 1].y;
+    const int p = (int)(pq >> 8), q = (int)(pq & 255u);
+    const int64_t gi = (role ? ib0 : ia0) + r;
+    const uint32_t sstr = gi < N ? __ldg(str + gi) : 0u;
+    const BlkSel e = blk_select<SRC>(et[2 * (p * n + q) + role], et[2 * (q * n + p) + role], p != q, sstr);
+    int32_t word = -1;
+    if (e.any) {
+      const uint32_t partner = sstr ^ e.flip;
+      const uint32_t neg = (__popc((SRC ? sstr : partner) & e.parS) & 1) ^ (e.s0 < 0 ? 1u : 0u);
+      word = (int32_t)((uint32_t)__ldg(rank + partner) | (e.second ? 1u << 29 : 0u) | neg << 30);
+    }
+    S.act[idx] = word;
+  }
+  __syncthreads();
+  return S;
+}
+
+template <bool DSA>
+__global__ void __launch_bounds__(256, 4)
+build_blk_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t k0, int64_t nblk, int64_t nbg,
+                 const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ str, const int32_t* __restrict__ rank, int64_t N,
+                 double lambda) {
+  const int n2 = n * n, nS = n * (n + 1) / 2;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t kb = k0 + blockIdx.x, t0 = (int64_t)blockIdx.x * 1024;
+  if (kb >= nblk) {   // beyond the last block: zero columns
+    const int rows = DSA ? n2 : nS;
+    for (int slot = 0; slot < rows; ++slot)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) D[(int64_t)slot * W + t0 + (wp + 8 * i) * 32 + lane] = 0.0;
+    return;
+  }
+  int64_t bi, bj;
+  tri_unrank(kb, nbg, &bi, &bj);
+  const int64_t ia0 = bi * 32, ib0 = bj * 32;
+  const BlkSmem S = blk_stage_actions<false>(etab, n, str, rank, N, ia0, ib0);
+  // alpha mapping: rows wp + 8 i (uniform strings), column lane (string bL)
+  // beta mapping : columns wp + 8 i (uniform strings bC), row lane (string aL)
+  uint32_t bC[4];
+  double wgt[4];
+  const int64_t ibL = ib0 + lane, iaL = ia0 + lane;
+  const bool okB = ibL < N, okA = iaL < N;
+  const uint32_t bL = okB ? __ldg(str + ibL) : 0u, aL = okA ? __ldg(str + iaL) : 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t ia = ia0 + wp + 8 * i, ib = ib0 + wp + 8 * i;
+    bC[i] = ib < N ? __ldg(str + ib) : 0u;
+    wgt[i] = (ia < N && okB && ia <= ibL) ? ((DSA && ia != ibL) ? 1.4142135623730951 : 1.0) : 0.0;
+  }
+  const double* const INa = IN + iaL;   // beta partners through their mirrors: row of the partner, column iaL
+  const double* const INb = IN + ibL;   // alpha partners: row of the partner, column ibL
+  const int4* const act4 = reinterpret_cast<const int4*>(S.act);
+  const int jl = ((lane & 7) << 2) | (lane >> 3);   // table position of string `lane`
+  double* const dst = D + t0 + wp * 32 + lane;
+  for (int s0 = 0; s0 < nS; s0 += BLK_SG) {
+    double xb[BLK_SG][4], xa[BLK_SG][4];
+    uint32_t sec[BLK_SG];   // bit i: the row string of determinant i takes E_qp; bit 4: the column string of this lane does
+#pragma unroll
+    for (int s = 0; s < BLK_SG; ++s) {
+      const bool live = s0 + s < nS;
+      const int sl = live ? s0 + s : 0;
+      const uint4 i0 = S.info[2 * sl];
+      const uint32_t flipb = S.info[2 * sl + 1].x;
+      const int4 wa4 = act4[sl * 8 + wp], wb4 = act4[(nS + sl) * 8 + wp];
+      const int wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+      sec[s] = 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        {   // <J|E^beta|in> through the mirror of the beta partner: lambda phi(a, b') in[b', a]
+          const int w = wb[i];
+          const uint32_t sb = bC[i] ^ flipb;
+          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(aL & (((w >> 29) & 1 ? i0.w : i0.z) ^ sb))) & 1u;
+          const double v = (live && w >= 0 && okA) ? INa[(int64_t)(w & 0xffffff) * N] : 0.0;
+          xb[s][i] = neg ? -v : v;
+        }
+        {   // <J|E^alpha|in>
+          const int w = wa[i];
+          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(bL & ((w >> 29) & 1 ? i0.y : i0.x))) & 1u;
+          const double v = (live && w >= 0 && okB) ? INb[(int64_t)(w & 0xffffff) * N] : 0.0;
+          xa[s][i] = neg ? -v : v;
+          if (DSA) sec[s] |= (uint32_t)((w >> 29) & 1) << i;
+        }
+      }
+      if (DSA) sec[s] |= (uint32_t)((S.act[(nS + sl) * 32 + jl] >> 29) & 1) << 4;
+    }
+#pragma unroll
+    for (int s = 0; s < BLK_SG; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) S.T[s * BLK_TS + (wp + 8 * i) * 33 + lane] = lambda * xb[s][i];
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < BLK_SG; ++s) {
+      if (s0 + s >= nS) continue;
+      const uint32_t pq = S.info[2 * (s0 + s) + 1].y;
+      const int p = (int)(pq >> 8), q = (int)(pq & 255u);
+      const int64_t ss = s0 + s, as = nS + p * (p - 1) / 2 + q;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double tb = S.T[s * BLK_TS + lane * 33 + wp + 8 * i];
+        dst[ss * W + i * 256] = wgt[i] * (xa[s][i] + tb);
+        if (DSA && p != q) dst[as * W + i * 256] = wgt[i] * (((sec[s] >> i) & 1u ? -xa[s][i] : xa[s][i]) + ((sec[s] >> 4) & 1u ? -tb : tb));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Y += contributions of the kept sources of one panel (see above); F has the n (n + 1) / 2 symmetrised rows, k_pq = k_qp
+__global__ void __launch_bounds__(256, 4)
+scatter_blk_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
+                   const double* __restrict__ kmat, int64_t W, int64_t k0, int64_t nblk, int64_t nbg, const ERec* __restrict__ etab, int n,
+                   const uint32_t* __restrict__ str, const int32_t* __restrict__ rank, int64_t N, double lambda) {
+  const int nS = n * (n + 1) / 2;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t kb = k0 + blockIdx.x, t0 = (int64_t)blockIdx.x * 1024;
+  if (kb >= nblk) return;
+  int64_t bi, bj;
+  tri_unrank(kb, nbg, &bi, &bj);
+  const int64_t ia0 = bi * 32, ib0 = bj * 32;
+  const BlkSmem S = blk_stage_actions<true>(etab, n, str, rank, N, ia0, ib0);
+  uint32_t bC[4];
+  double wJ[4], cjw[4];
+  const int64_t ibL = ib0 + lane, iaL = ia0 + lane;
+  const bool okB = ibL < N, okA = iaL < N;
+  const uint32_t bL = okB ? __ldg(str + ibL) : 0u, aL = okA ? __ldg(str + iaL) : 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t ia = ia0 + wp + 8 * i, ib = ib0 + wp + 8 * i;
+    bC[i] = ib < N ? __ldg(str + ib) : 0u;
+    const bool kept = ia < N && okB && ia <= ibL;
+    wJ[i] = kept ? (ia == ibL ? 0.5 : 1.0) : 0.0;   // masked determinants (lower triangle of a diagonal block, beyond N) carry value 0 everywhere below
+    cjw[i] = kept ? wJ[i] * IN[ia * N + ibL] : 0.0;
+  }
+  double* const OUTa = OUT + iaL;   // mirrored beta targets: row of the target string, column iaL
+  double* const OUTb = OUT + ibL;   // alpha targets
+  const double* const Fb = F + t0 + wp * 32 + lane;
+  const int4* const act4 = reinterpret_cast<const int4*>(S.act);
+  for (int s0 = 0; s0 < nS; s0 += BLK_SG) {
+    double val[BLK_SG][4];
+#pragma unroll
+    for (int s = 0; s < BLK_SG; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) val[s][i] = (s0 + s < nS && wJ[i] != 0.0) ? Fb[(int64_t)(s0 + s) * W + i * 256] : 0.0;
+    // ---- alpha mapping: value of every source, alpha contributions at their targets
+#pragma unroll
+    for (int s = 0; s < BLK_SG; ++s) {
+      const bool live = s0 + s < nS;
+      const int sl = live ? s0 + s : 0;
+      const uint4 i0 = S.info[2 * sl];
+      const uint32_t pq = S.info[2 * sl + 1].y;
+      const double kk = __ldg(kmat + (pq >> 8) * n + (pq & 255u));
+      const int4 wa4 = act4[sl * 8 + wp];
+      const int wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double v = live ? wJ[i] * val[s][i] + kk * cjw[i] : 0.0;
+        S.T[s * BLK_TS + (wp + 8 * i) * 33 + lane] = v;
+        const int w = wa[i];
+        if (w >= 0 && v != 0.0) {
+          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(bL & ((w >> 29) & 1 ? i0.y : i0.x))) & 1u;
+          atomicAdd(OUTb + (int64_t)(w & 0xffffff) * N, neg ? -v : v);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- beta mapping: beta contributions at the mirrors of their targets
+#pragma unroll
+    for (int s = 0; s < BLK_SG; ++s) {
+      const int sl = s0 + s < nS ? s0 + s : 0;
+      const uint4 i0 = S.info[2 * sl];
+      const uint32_t flipb = S.info[2 * sl + 1].x;
+      const int4 wb4 = act4[(nS + sl) * 8 + wp];
+      const int wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double v = S.T[s * BLK_TS + lane * 33 + wp + 8 * i];
+        const int w = wb[i];
+        if (w >= 0 && v != 0.0) {
+          const uint32_t tb = bC[i] ^ flipb;
+          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(aL & (((w >> 29) & 1 ? i0.w : i0.z) ^ tb))) & 1u;
+          atomicAdd(OUTa + (int64_t)(w & 0xffffff) * N, lambda * (neg ? -v : v));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dynamic shared memory of the two kernels: action table, generator info, tiles (the staged records share the tile area)
+static size_t blk_smem_bytes(int n) {
+  const size_t nS = (size_t)n * (n + 1) / 2, tiles = sizeof(double) * BLK_SG * BLK_TS, recs = sizeof(ERec) * 2 * (size_t)n * n;
+  return 2 * nS * 32 * sizeof(int32_t) + 2 * nS * sizeof(uint4) + std::max(tiles, recs);
+}
+
+// OUT <- OUT + lambda U OUT in place: (U x)[A,B] = phi(A,B) x[B,A]; 32 x 32 tile pairs through shared memory
+__global__ void __launch_bounds__(256)
+spinsym_symmetrize_kernel(double* __restrict__ OUT, int64_t N, const uint32_t* __restrict__ str, double lambda) {
+  __shared__ double tl[32][33], tu[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  for (int k = ty; k < 32; k += 8) {   // lower tile, along its rows
+    const int64_t r = bj * 32 + k, c = bi * 32 + tx;
+    tl[k][tx] = (r < N && c < N) ? OUT[r * N + c] : 0.0;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = bi * 32 + k, c = bj * 32 + tx;
+    double m = 0.0;
+    if (r < N && c < N) {
+      const bool neg = __popc(__ldg(str + r) & __ldg(str + c)) & 1;
+      const double y = tl[tx][k];
+      const double v = OUT[r * N + c] + lambda * (neg ? -y : y);
+      OUT[r * N + c] = v;
+      m = lambda * (neg ? -v : v);
+    }
+    tu[k][tx] = m;
+  }
+  __syncthreads();
+  if (bj > bi)
+    for (int k = ty; k < 32; k += 8) {
+      const int64_t r = bj * 32 + k, c = bi * 32 + tx;
+      if (r < N && c < N) OUT[r * N + c] = tu[tx][k];
+    }
+}
+
+static int g_spinsym_blk = 1;   // sq_set_option("sigma_spinsym", "tri"): the determinant-per-thread kernels of the half build
+void sq_hamiltonian_set_spinsym_blk(int on) { g_spinsym_blk = on ? 1 : 0; }
+
 // measures the spin-flip symmetry of a vector (see above): *lambda = +-1 if c[B,A] = lambda phi(A,B) c[A,B] to 1e-12 max|c|, else 0
 static int spinsym_measure(sq_space* sp, HamWork* w, const double* vec, cudaStream_t st, double* lambda) {
   *lambda = 0.0;
@@ -1513,24 +1814,36 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   SQ_CUDA(cudaMemcpyAsync(d_k, k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaMemcpyAsync(w->d_frow, frow.data(), sizeof(int) * frow.size(), cudaMemcpyHostToDevice, st));
   SQ_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
-  SQ_CHECK(sq_launch_scale_copy(sp, e_core, in_dev, out_dev, st));
   const int64_t len = sp->local_len();
-  if (g_sigma_fused) {   // one fused gather -> DMMA -> scatter kernel, no D / F panels in HBM
-    const int rc = launch_sigma_fused(sp, in_dev, out_dev, d_G, ldg, nrow, sym, d_k, w->d_frow, w->n_sm, st);
-    if (rc != SQ_ERR_UNSUPPORTED) return rc;
-  }
   bool use_const = false;
   SQ_CHECK(bind_etab(sp, w, st, &use_const));
   // Spin-flip symmetric input (see "half of the sigma build" above): measured, not assumed
   bool tri = false;
   double lambda = 1.0;
-  if (g_sigma_spinsym && sym && !use_const && !g_etab_alu && !g_etab_tab && !(g_rows_kernels && w->d_tabG) && sp->n_alpha == sp->n_beta &&
-      sp->NA == sp->NB && sp->NA > 1) {
+  if (g_sigma_spinsym && !g_sigma_fused && sym && !use_const && !g_etab_alu && !g_etab_tab && !(g_rows_kernels && w->d_tabG) &&
+      sp->n_alpha == sp->n_beta && sp->NA == sp->NB && sp->NA > 1) {
     SQ_CHECK(spinsym_measure(sp, w, in_dev, st, &lambda));
     tri = lambda != 0.0;
   }
-  const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : len;
+  // blocked panels (32 x 32 blocks of determinants, every access a contiguous run) when a panel holds at least one block
+  const bool blk = tri && g_spinsym_blk && w->W >= 1024 && sp->NA < ((int64_t)1 << 24) && n < 256 && blk_smem_bytes(n) <= 200 * 1024;
+  const int64_t nbg = (sp->NA + 31) / 32, nblk = nbg * (nbg + 1) / 2, bpp = w->W / 1024;   // block grid, kept blocks, blocks per panel
+  SQ_CHECK(sq_launch_scale_copy(sp, blk ? 0.5 * e_core : e_core, in_dev, out_dev, st));
+  if (g_sigma_fused) {   // one fused gather -> DMMA -> scatter kernel, no D / F panels in HBM
+    const int rc = launch_sigma_fused(sp, in_dev, out_dev, d_G, ldg, nrow, sym, d_k, w->d_frow, w->n_sm, st);
+    if (rc != SQ_ERR_UNSUPPORTED) return rc;
+  }
+  const int64_t len_eff = blk ? ((nblk + bpp - 1) / bpp) * w->W : (tri ? sp->NA * (sp->NA + 1) / 2 : len);
+  const size_t blk_smem = blk_smem_bytes(n);
   auto build_panel = [&](double* Dp, int64_t j0, cudaStream_t s) -> int {
+    if (blk) {
+      allow_smem(build_blk_kernel<false>, blk_smem);
+      if (w->W > bpp * 1024)   // columns behind the last block of the panel
+        SQ_CUDA(cudaMemset2DAsync(Dp + bpp * 1024, sizeof(double) * (size_t)w->W, 0, sizeof(double) * (size_t)(w->W - bpp * 1024), (size_t)nrow, s));
+      build_blk_kernel<false><<<(unsigned)bpp, 256, blk_smem, s>>>(in_dev, Dp, w->W, (j0 / w->W) * bpp, nblk, nbg, w->d_etab, n, sp->d_strA,
+                                                                  sp->d_rankA, sp->NA, lambda);
+      return launch_error("build_blk_kernel");
+    }
     if (!tri) return launch_build_D(sp, w, in_dev, Dp, j0, s, use_const, sym);
     const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
     allow_smem(build_Dsym_tri_kernel, smem);
@@ -1539,6 +1852,12 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     return launch_error("build_Dsym_tri_kernel");
   };
   auto scatter_panel = [&](const double* Fp, int64_t j0, cudaStream_t s) -> int {
+    if (blk) {
+      allow_smem(scatter_blk_kernel, blk_smem);
+      scatter_blk_kernel<<<(unsigned)bpp, 256, blk_smem, s>>>(in_dev, out_dev, Fp, d_k, w->W, (j0 / w->W) * bpp, nblk, nbg, w->d_etab, n,
+                                                             sp->d_strA, sp->d_rankA, sp->NA, lambda);
+      return launch_error("scatter_blk_kernel");
+    }
     if (!tri) return launch_scatter_E(sp, w, in_dev, out_dev, Fp, d_k, j0, s, use_const);
     const size_t smem = sizeof(ERec) * 2 * (size_t)n2;
     allow_smem(scatter_E_tri_kernel, smem);
@@ -1584,7 +1903,10 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     SQ_CUDA(cudaEventRecord(w->ev_start, s_build));
     SQ_CUDA(cudaStreamWaitEvent(st, w->ev_start, 0));
   }
-  if (tri) {   // the lower triangle from the upper one
+  if (blk) {   // sigma = Y + lambda U Y
+    spinsym_symmetrize_kernel<<<dim3((unsigned)nbg, (unsigned)nbg), 256, 0, st>>>(out_dev, sp->NA, sp->d_strA, lambda);
+    SQ_CHECK(launch_error("spinsym_symmetrize_kernel"));
+  } else if (tri) {   // the lower triangle from the upper one
     const unsigned nb32 = (unsigned)((sp->NA + 31) / 32);
     spinsym_mirror_kernel<<<dim3(nb32, nb32), 256, 0, st>>>(out_dev, sp->NA, sp->d_strA, lambda);
     SQ_CHECK(launch_error("spinsym_mirror_kernel"));
@@ -1742,14 +2064,17 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   }
   // spin-flip symmetric vector (measured): the S / A panels of the determinants above / on the diagonal only, weighted
   bool tri = false;
+  double tri_lambda = 0.0;
   if (sym_route && g_sigma_spinsym && !pv_ket) {
-    double lambda = 0.0;
-    SQ_CHECK(spinsym_measure(sp, w, ket_dev, st, &lambda));
-    tri = lambda != 0.0;
+    SQ_CHECK(spinsym_measure(sp, w, ket_dev, st, &tri_lambda));
+    tri = tri_lambda != 0.0;
   }
   // sharded vector: the caller measured the symmetry over all ranks (sq_rdm12_dist_sym); the kept cyclic band of the local rows
   const bool half_band = sym_route && pv_ket && t_rdm_dist_lambda != 0.0 && sp->n_alpha == sp->n_beta && sp->NA == sp->NB;
-  const int64_t len_eff = tri ? sp->NA * (sp->NA + 1) / 2 : (half_band ? half_len_host(sp) : len);
+  const bool blk = tri && g_spinsym_blk && w->W >= 1024 && sp->NA < ((int64_t)1 << 24) && n < 256 && blk_smem_bytes(n) <= 200 * 1024;   // blocked panels (build_blk_kernel)
+  const int64_t nbg = (sp->NA + 31) / 32, nblk = nbg * (nbg + 1) / 2, bpp = w->W / 1024;
+  const size_t blk_smem = blk_smem_bytes(n);
+  const int64_t len_eff = blk ? ((nblk + bpp - 1) / bpp) * w->W : (tri ? sp->NA * (sp->NA + 1) / 2 : (half_band ? half_len_host(sp) : len));
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -1764,7 +2089,14 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     const int b = piped ? (int)(k & 1) : 0;
     double* Dket = w->d_D[b];
     if (piped && k >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // panels b are free once GEMM k-2 is done
-    if (tri) {
+    if (blk) {
+      allow_smem(build_blk_kernel<true>, blk_smem);
+      if (w->W > bpp * 1024)
+        SQ_CUDA(cudaMemset2DAsync(Dket + bpp * 1024, sizeof(double) * (size_t)w->W, 0, sizeof(double) * (size_t)(w->W - bpp * 1024), (size_t)n2, s_build));
+      build_blk_kernel<true><<<(unsigned)bpp, 256, blk_smem, s_build>>>(ket_dev, Dket, w->W, k * bpp, nblk, nbg, w->d_etab, n, sp->d_strA,
+                                                                       sp->d_rankA, sp->NA, tri_lambda);
+      SQ_CHECK(launch_error("build_blk_kernel"));
+    } else if (tri) {
       build_DSA_tri_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len_eff, n, sp->d_strA, sp->d_strB,
                                                                       sp->d_rankA, sp->d_rankB, sp->NB);
       SQ_CHECK(launch_error("build_DSA_tri_kernel"));

@@ -213,6 +213,7 @@ void sq_hamiltonian_set_rows_mode(int on);         // row-per-CTA panel kernels 
 void sq_hamiltonian_set_pipeline(int on);          // sigma / RDM panel pipeline over internal streams (default on)
 void sq_hamiltonian_set_etab_alu(int on);          // panel kernels without an E_pq table (records computed from (p,q); default off)
 void sq_hamiltonian_set_sigma_spinsym(int on);     // half sigma build for spin-flip symmetric vectors (default on)
+void sq_hamiltonian_set_spinsym_blk(int on);       // 32 x 32 blocked panels of the half build (default on); off: determinant-per-thread kernels
 void sq_hamiltonian_set_etab_tab(int on);          // panel kernels on per-string partner tables
 void sq_hamiltonian_set_rdm_tri(int on);
 void sq_hamiltonian_set_rdm_sym(int on);           // 2-RDM of one vector from the symmetric S / A Gram matrices (default on)

@@ -880,12 +880,15 @@ def test_backwards_gradient_sweep_on_a_mixed_circuit(sq):
     assert abs(E - orc.energy_elec(orc.construct_ups_state(ref_state, sp, th, types, idx), h, g, sp)) < 1e-10
 
 
-@pytest.mark.parametrize("n,ne,L", [(8, 4, 2), (6, 3, 2), (7, 3, 1)])
-def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L):
+@pytest.mark.parametrize("n,ne,L,panel", [(8, 4, 2, 512), (6, 3, 2, 512), (7, 3, 1, 512), (8, 4, 2, 2048), (8, 4, 2, 1536), (7, 3, 2, 1024),
+                                          (10, 5, 2, 0), (9, 4, 2, 3072)])
+def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L, panel):
     """sq_sigma builds H|psi> of a spin-flip symmetric vector (c[B,A] = lambda phi(A,B) c[A,B]: every tUPS state on a closed-shell
     reference; lambda = +1 for an even, -1 for an odd number of electron pairs) from the determinants above the diagonal only.
     The half build must equal the full build (switch off) and the oracle's sigma; a vector without the symmetry -- a random one, or
-    a symmetric one disturbed at 1e-8 -- must take the full build (same launches as with the switch off, plus the check)."""
+    a symmetric one disturbed at 1e-8 -- must take the full build (same launches as with the switch off, plus the check).
+    Panels of fewer than 1024 determinants take the determinant-per-thread kernels of the half build, wider ones the blocked
+    kernels (32 x 32 blocks of determinants; 1536 and 3072: panels whose width is no multiple of a block, 0: the default width)."""
     from slowquant_b200.operators import hamiltonian_0i_0a
 
     lib = sq.lib.load()
@@ -903,7 +906,7 @@ def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L):
     psi = orc.construct_ups_state(hf, sp, th, types, idx)
     H_orc = orc.hamiltonian_0i_0a(h, g, 0, n)
     try:
-        lib.sq_set_option(b"panel", b"512")                       # several panels, the last one partial, in both builds
+        lib.sq_set_option(b"panel", str(panel).encode())          # several panels, the last one partial, in both builds
         info = sq.ci.get_indexing(0, n, 0, ne, ne)
         H = hamiltonian_0i_0a(h, g, 0, n)
         for label, vec, symmetric in (("tUPS state", psi, True), ("random", rng.normal(size=sp.num_det), False),
@@ -923,7 +926,7 @@ def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L):
             # fall-back = the full build plus the symmetry check; the half build adds the mirror pass and has about half the panels
             if symmetric:
                 assert launches_half != launches_full + 1, (label, launches_half, launches_full)
-                if sp.num_det > 4 * 512:
+                if panel and sp.num_det > 8 * panel:
                     assert launches_half < launches_full, (label, launches_half, launches_full)
             else:
                 assert launches_half == launches_full + 1, (label, launches_half, launches_full)

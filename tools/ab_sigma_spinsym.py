@@ -1,4 +1,5 @@
-"""A/B at CAS(16,16): sigma build of a tUPS state (spin-flip symmetric) with the half build on / off."""
+"""A/B at CAS(16,16): sigma build of a tUPS state (spin-flip symmetric): full build ("0"), half build on 32 x 32 blocked panels ("1"),
+half build with the determinant-per-thread kernels ("tri")."""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -22,17 +23,18 @@ hf = torch.zeros(info.num_det, dtype=torch.float64, device="cuda"); hf[0] = 1.0
 psi = osa.construct_ups_state(hf, info, th.tolist(), lay)
 lib = _lib.load()
 res = {}
-for mode in (b"0", b"1", b"0", b"1"):
+for mode in (b"0", b"tri", b"1", b"0", b"tri", b"1"):
     lib.sq_set_option(b"sigma_spinsym", mode)
     osa.propagate_state([H], psi, info); torch.cuda.synchronize()
     t0 = time.perf_counter(); out = osa.propagate_state([H], psi, info); torch.cuda.synchronize()
     print(f"CAS({n},{n}) sigma_spinsym={mode.decode()} sigma {1e3*(time.perf_counter()-t0):8.1f} ms  E = {float(torch.dot(psi, out)):.12f}", flush=True)
     res[mode] = out
-for mode in (b"0", b"1", b"0", b"1"):
+for mode in (b"0", b"tri", b"1", b"0", b"tri", b"1"):
     lib.sq_set_option(b"sigma_spinsym", mode)
     osa.reduced_density_matrices(psi, psi, info); torch.cuda.synchronize()
     t0 = time.perf_counter(); d1, d2 = osa.reduced_density_matrices(psi, psi, info); torch.cuda.synchronize()
     print(f"CAS({n},{n}) sigma_spinsym={mode.decode()} rdm12 {1e3*(time.perf_counter()-t0):8.1f} ms  E_rdm = {float(np.sum(h*d1)+0.5*np.sum(g*d2)):.12f}  tr = {np.trace(d1):.12f}", flush=True)
     res[(mode, 'rdm')] = (d1, d2)
 print("rdm1 diff", float(np.max(np.abs(res[(b'1','rdm')][0]-res[(b'0','rdm')][0]))), "rdm2 diff", float(np.max(np.abs(res[(b'1','rdm')][1]-res[(b'0','rdm')][1]))))
-print("max|half - full| =", float(torch.max(torch.abs(res[b'1'] - res[b'0']))), " |sigma| =", float(torch.linalg.norm(res[b'0'])))
+print("max|half - full| =", float(torch.max(torch.abs(res[b'1'] - res[b'0']))), " max|tri - full| =", float(torch.max(torch.abs(res[b'tri'] - res[b'0']))), " |sigma| =", float(torch.linalg.norm(res[b'0'])))
+lib.sq_set_option(b"sigma_spinsym", b"1")
