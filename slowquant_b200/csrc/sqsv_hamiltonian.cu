@@ -1422,6 +1422,11 @@ build_DSA_tri_kernel(const double* __restrict__ IN, double* __restrict__ D, int6
 #define BLK_TS (32 * 33)
 #define BLK_SG 2   // generator pairs per barrier round: the loads of a round (one per determinant, spin and pair) are in flight together
 
+// x with its sign flipped when bit 31 of `neg` is set (one logic operation on the high word instead of a negation and a select)
+__device__ __forceinline__ double blk_flip_sign(double x, uint32_t neg) {
+  return __hiloint2double(__double2hiint(x) ^ (int)(neg & 0x80000000u), __double2loint(x));
+}
+
 // For p != q at most one of E_pq, E_qp passes the screen of a string (p occupied and q empty, or the reverse): one record, one access.
 struct BlkSel {
   uint32_t flip, parS;
@@ -1436,10 +1441,12 @@ __device__ __forceinline__ BlkSel blk_select(const ERec& r1, const ERec& r2, boo
 }
 
 // Everything that depends on (string, generator pair) only is worked out ONCE per CTA for its 32 row and 32 column strings:
-//   act[(role * nS + slot) * 32 + j], j = 4 * (r % 8) + r / 8 for string r of the block (role 0: row strings under E^alpha, role 1: column
-//   strings under E^beta): -1 if neither E_pq nor E_qp acts, else  rank of the partner string | E_qp taken << 29 | sign << 30
+//   act[(role * nSp + slot) * 32 + j], j = 4 * (r % 8) + r / 8 for string r of the block (role 0: row strings under E^alpha, role 1:
+//   column strings under E^beta): -1 (all ones) if neither E_pq nor E_qp acts, else
+//       rank of the partner string (24 bits) | E_qp taken << 29 | sign << 31
 //   (sign = s0 and the same-spin parity of the SOURCE string; SRC: the string is the source, else the target of the operator);
-//   info[slot] = {other-spin parity masks of E^alpha_pq, E^alpha_qp, E^beta_pq, E^beta_qp | flip mask, p << 8 | q, -, -}.
+//   info[slot] = {other-spin parity mask of E^alpha_pq (= that of E^alpha_qp, checked on the host), the same for E^beta, flip mask,
+//   p << 8 | q}; slots padded to whole rounds (no action).
 // The main loops are left with one uniform 16-byte table load per 4 determinants, one popcount and the memory access itself.
 struct BlkSmem {
   int32_t* act;
@@ -1450,26 +1457,33 @@ template <bool SRC>
 __device__ __forceinline__ BlkSmem blk_stage_actions(const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ str,
                                                      const int32_t* __restrict__ rank, int64_t N, int64_t ia0, int64_t ib0) {
   extern __shared__ uint4 blk_raw[];
-  const int n2 = n * n, nS = n * (n + 1) / 2;
+  const int n2 = n * n, nS = n * (n + 1) / 2, nSp = (nS + BLK_SG - 1) / BLK_SG * BLK_SG;
   BlkSmem S;
   S.act = reinterpret_cast<int32_t*>(blk_raw);
-  S.info = blk_raw + 2 * nS * 8;
-  S.T = reinterpret_cast<double*>(S.info + 2 * nS);
+  S.info = blk_raw + 2 * nSp * 8;
+  S.T = reinterpret_cast<double*>(S.info + nSp);
   ERec* const et = reinterpret_cast<ERec*>(S.T);   // the records, staged in the tile area while the tables are built
   for (int w = threadIdx.x; w < 2 * n2 * (int)(sizeof(ERec) / 4); w += 256) reinterpret_cast<uint32_t*>(et)[w] = reinterpret_cast<const uint32_t*>(etab)[w];
   __syncthreads();
-  for (int s = threadIdx.x; s < nS; s += 256) {
+  for (int s = threadIdx.x; s < nSp; s += 256) {
+    if (s >= nS) {
+      S.info[s] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
     int p = (int)((sqrtf(8.0f * (float)s + 1.0f) - 1.0f) * 0.5f);
     while (p * (p + 1) / 2 > s) --p;
     while ((p + 1) * (p + 2) / 2 <= s) ++p;
     const int q = s - p * (p + 1) / 2;
-    S.info[2 * s] = make_uint4(et[2 * (p * n + q)].parO, et[2 * (q * n + p)].parO, et[2 * (p * n + q) + 1].parO, et[2 * (q * n + p) + 1].parO);
-    S.info[2 * s + 1] = make_uint4(et[2 * (p * n + q) + 1].flip, (uint32_t)(p << 8 | q), 0u, 0u);
+    S.info[s] = make_uint4(et[2 * (p * n + q)].parO, et[2 * (p * n + q) + 1].parO, et[2 * (p * n + q) + 1].flip, (uint32_t)(p << 8 | q));
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * nS * 32; idx += 256) {
-    const int role = idx >= nS * 32, rem = idx - role * nS * 32, s = rem >> 5, j = rem & 31, r = (j >> 2) + 8 * (j & 3);
-    const uint32_t pq = S.info[2 * s + 1].y;
+  for (int idx = threadIdx.x; idx < 2 * nSp * 32; idx += 256) {
+    const int role = idx >= nSp * 32, rem = idx - role * nSp * 32, s = rem >> 5, j = rem & 31, r = (j >> 2) + 8 * (j & 3);
+    if (s >= nS) {
+      S.act[idx] = -1;
+      continue;
+    }
+    const uint32_t pq = S.info[s].w;
     const int p = (int)(pq >> 8), q = (int)(pq & 255u);
     const int64_t gi = (role ? ib0 : ia0) + r;
     const uint32_t sstr = gi < N ? __ldg(str + gi) : 0u;
@@ -1478,7 +1492,7 @@ __device__ __forceinline__ BlkSmem blk_stage_actions(const ERec* __restrict__ et
     if (e.any) {
       const uint32_t partner = sstr ^ e.flip;
       const uint32_t neg = (__popc((SRC ? sstr : partner) & e.parS) & 1) ^ (e.s0 < 0 ? 1u : 0u);
-      word = (int32_t)((uint32_t)__ldg(rank + partner) | (e.second ? 1u << 29 : 0u) | neg << 30);
+      word = (int32_t)((uint32_t)__ldg(rank + partner) | (e.second ? 1u << 29 : 0u) | neg << 31);
     }
     S.act[idx] = word;
   }
@@ -1486,11 +1500,13 @@ __device__ __forceinline__ BlkSmem blk_stage_actions(const ERec* __restrict__ et
   return S;
 }
 
+// N8: bytes per row of the vector (N < 2^24), a kernel parameter so that every address is one 32 x 32 -> 64-bit multiply-add.
+// Lanes beyond the last row / column of an edge block address row / column N - 1 instead: their values carry weight zero.
 template <bool DSA>
 __global__ void __launch_bounds__(256, 4)
 build_blk_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t W, int64_t k0, int64_t nblk, int64_t nbg,
                  const ERec* __restrict__ etab, int n, const uint32_t* __restrict__ str, const int32_t* __restrict__ rank, int64_t N,
-                 double lambda) {
+                 uint32_t N8, double lambda) {
   const int n2 = n * n, nS = n * (n + 1) / 2;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int64_t kb = k0 + blockIdx.x, t0 = (int64_t)blockIdx.x * 1024;
@@ -1509,67 +1525,67 @@ build_blk_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t 
   // beta mapping : columns wp + 8 i (uniform strings bC), row lane (string aL)
   uint32_t bC[4];
   double wgt[4];
-  const int64_t ibL = ib0 + lane, iaL = ia0 + lane;
-  const bool okB = ibL < N, okA = iaL < N;
-  const uint32_t bL = okB ? __ldg(str + ibL) : 0u, aL = okA ? __ldg(str + iaL) : 0u;
+  const int64_t ibL = min(ib0 + lane, N - 1), iaL = min(ia0 + lane, N - 1);
+  const uint32_t bL = __ldg(str + ibL), aL = __ldg(str + iaL);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t ia = ia0 + wp + 8 * i, ib = ib0 + wp + 8 * i;
     bC[i] = ib < N ? __ldg(str + ib) : 0u;
-    wgt[i] = (ia < N && okB && ia <= ibL) ? ((DSA && ia != ibL) ? 1.4142135623730951 : 1.0) : 0.0;
+    wgt[i] = (ia < N && ib0 + lane < N && ia <= ib0 + lane) ? ((DSA && ia != ib0 + lane) ? 1.4142135623730951 : 1.0) : 0.0;
   }
-  const double* const INa = IN + iaL;   // beta partners through their mirrors: row of the partner, column iaL
-  const double* const INb = IN + ibL;   // alpha partners: row of the partner, column ibL
-  const int4* const act4 = reinterpret_cast<const int4*>(S.act);
-  const int jl = ((lane & 7) << 2) | (lane >> 3);   // table position of string `lane`
+  const char* const INa = reinterpret_cast<const char*>(IN + iaL);   // beta partners through their mirrors: row of the partner, column iaL
+  const char* const INb = reinterpret_cast<const char*>(IN + ibL);   // alpha partners: row of the partner, column ibL
+  const int nSp = (nS + BLK_SG - 1) / BLK_SG * BLK_SG;
+  const int4* const actA = reinterpret_cast<const int4*>(S.act) + wp;
+  const int4* const actB = actA + nSp * 8;
+  const int32_t* const actL = S.act + nSp * 32 + (((lane & 7) << 2) | (lane >> 3));   // table entries of column string `lane`
   double* const dst = D + t0 + wp * 32 + lane;
+  double* const Tw = S.T + wp * 33 + lane;        // beta mapping writes [column wp + 8 i][row lane]
+  const double* const Tr = S.T + lane * 33 + wp;  // alpha mapping reads [column lane][row wp + 8 i]
   for (int s0 = 0; s0 < nS; s0 += BLK_SG) {
     double xb[BLK_SG][4], xa[BLK_SG][4];
-    uint32_t sec[BLK_SG];   // bit i: the row string of determinant i takes E_qp; bit 4: the column string of this lane does
+    uint32_t sec[BLK_SG];   // DSA: bit i: the row string of determinant i takes E_qp; bit 4: the column string of this lane does
 #pragma unroll
     for (int s = 0; s < BLK_SG; ++s) {
-      const bool live = s0 + s < nS;
-      const int sl = live ? s0 + s : 0;
-      const uint4 i0 = S.info[2 * sl];
-      const uint32_t flipb = S.info[2 * sl + 1].x;
-      const int4 wa4 = act4[sl * 8 + wp], wb4 = act4[(nS + sl) * 8 + wp];
+      const uint4 inf = S.info[s0 + s];
+      const int4 wa4 = actA[(s0 + s) * 8], wb4 = actB[(s0 + s) * 8];
       const int wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+      const uint32_t ma = bL & inf.x;                 // alpha operators: other-spin parity on the column string
+      const uint32_t pa = (uint32_t)__popc(ma) << 31;
       sec[s] = 0u;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         {   // <J|E^beta|in> through the mirror of the beta partner: lambda phi(a, b') in[b', a]
           const int w = wb[i];
-          const uint32_t sb = bC[i] ^ flipb;
-          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(aL & (((w >> 29) & 1 ? i0.w : i0.z) ^ sb))) & 1u;
-          const double v = (live && w >= 0 && okA) ? INa[(int64_t)(w & 0xffffff) * N] : 0.0;
-          xb[s][i] = neg ? -v : v;
+          const uint32_t neg = (uint32_t)w ^ ((uint32_t)__popc(aL & (inf.y ^ bC[i] ^ inf.z)) << 31);
+          const double v = (w != -1) ? *reinterpret_cast<const double*>(INa + (uint64_t)((uint32_t)w & 0xffffffu) * N8) : 0.0;
+          xb[s][i] = blk_flip_sign(v, neg);
         }
         {   // <J|E^alpha|in>
           const int w = wa[i];
-          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(bL & ((w >> 29) & 1 ? i0.y : i0.x))) & 1u;
-          const double v = (live && w >= 0 && okB) ? INb[(int64_t)(w & 0xffffff) * N] : 0.0;
-          xa[s][i] = neg ? -v : v;
+          const double v = (w != -1) ? *reinterpret_cast<const double*>(INb + (uint64_t)((uint32_t)w & 0xffffffu) * N8) : 0.0;
+          xa[s][i] = blk_flip_sign(v, (uint32_t)w ^ pa);
           if (DSA) sec[s] |= (uint32_t)((w >> 29) & 1) << i;
         }
       }
-      if (DSA) sec[s] |= (uint32_t)((S.act[(nS + sl) * 32 + jl] >> 29) & 1) << 4;
+      if (DSA) sec[s] |= (uint32_t)((actL[(s0 + s) * 32] >> 29) & 1) << 4;
     }
 #pragma unroll
     for (int s = 0; s < BLK_SG; ++s)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) S.T[s * BLK_TS + (wp + 8 * i) * 33 + lane] = lambda * xb[s][i];
+      for (int i = 0; i < 4; ++i) Tw[s * BLK_TS + i * (8 * 33)] = lambda * xb[s][i];
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < BLK_SG; ++s) {
       if (s0 + s >= nS) continue;
-      const uint32_t pq = S.info[2 * (s0 + s) + 1].y;
+      const uint32_t pq = S.info[s0 + s].w;
       const int p = (int)(pq >> 8), q = (int)(pq & 255u);
       const int64_t ss = s0 + s, as = nS + p * (p - 1) / 2 + q;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double tb = S.T[s * BLK_TS + lane * 33 + wp + 8 * i];
+        const double tb = Tr[s * BLK_TS + i * 8];
         dst[ss * W + i * 256] = wgt[i] * (xa[s][i] + tb);
-        if (DSA && p != q) dst[as * W + i * 256] = wgt[i] * (((sec[s] >> i) & 1u ? -xa[s][i] : xa[s][i]) + ((sec[s] >> 4) & 1u ? -tb : tb));
+        if (DSA && p != q) dst[as * W + i * 256] = wgt[i] * (blk_flip_sign(xa[s][i], sec[s] << (31 - i)) + blk_flip_sign(tb, sec[s] << 27));
       }
     }
     __syncthreads();
@@ -1580,7 +1596,7 @@ build_blk_kernel(const double* __restrict__ IN, double* __restrict__ D, int64_t 
 __global__ void __launch_bounds__(256, 4)
 scatter_blk_kernel(const double* __restrict__ IN, double* __restrict__ OUT, const double* __restrict__ F,
                    const double* __restrict__ kmat, int64_t W, int64_t k0, int64_t nblk, int64_t nbg, const ERec* __restrict__ etab, int n,
-                   const uint32_t* __restrict__ str, const int32_t* __restrict__ rank, int64_t N, double lambda) {
+                   const uint32_t* __restrict__ str, const int32_t* __restrict__ rank, int64_t N, uint32_t N8, double lambda) {
   const int nS = n * (n + 1) / 2;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int64_t kb = k0 + blockIdx.x, t0 = (int64_t)blockIdx.x * 1024;
@@ -1591,21 +1607,24 @@ scatter_blk_kernel(const double* __restrict__ IN, double* __restrict__ OUT, cons
   const BlkSmem S = blk_stage_actions<true>(etab, n, str, rank, N, ia0, ib0);
   uint32_t bC[4];
   double wJ[4], cjw[4];
-  const int64_t ibL = ib0 + lane, iaL = ia0 + lane;
-  const bool okB = ibL < N, okA = iaL < N;
-  const uint32_t bL = okB ? __ldg(str + ibL) : 0u, aL = okA ? __ldg(str + iaL) : 0u;
+  const int64_t ibL = min(ib0 + lane, N - 1), iaL = min(ia0 + lane, N - 1);
+  const uint32_t bL = __ldg(str + ibL), aL = __ldg(str + iaL);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t ia = ia0 + wp + 8 * i, ib = ib0 + wp + 8 * i;
     bC[i] = ib < N ? __ldg(str + ib) : 0u;
-    const bool kept = ia < N && okB && ia <= ibL;
-    wJ[i] = kept ? (ia == ibL ? 0.5 : 1.0) : 0.0;   // masked determinants (lower triangle of a diagonal block, beyond N) carry value 0 everywhere below
+    const bool kept = ia < N && ib0 + lane < N && ia <= ib0 + lane;
+    wJ[i] = kept ? (ia == ib0 + lane ? 0.5 : 1.0) : 0.0;   // masked determinants (lower triangle of a diagonal block, beyond N) carry value 0 everywhere below
     cjw[i] = kept ? wJ[i] * IN[ia * N + ibL] : 0.0;
   }
-  double* const OUTa = OUT + iaL;   // mirrored beta targets: row of the target string, column iaL
-  double* const OUTb = OUT + ibL;   // alpha targets
+  char* const OUTa = reinterpret_cast<char*>(OUT + iaL);   // mirrored beta targets: row of the target string, column iaL
+  char* const OUTb = reinterpret_cast<char*>(OUT + ibL);   // alpha targets
+  const int nSp = (nS + BLK_SG - 1) / BLK_SG * BLK_SG;
   const double* const Fb = F + t0 + wp * 32 + lane;
-  const int4* const act4 = reinterpret_cast<const int4*>(S.act);
+  const int4* const actA = reinterpret_cast<const int4*>(S.act) + wp;
+  const int4* const actB = actA + nSp * 8;
+  double* const Tw = S.T + wp * 33 + lane;        // alpha mapping writes [row wp + 8 i][column lane]
+  const double* const Tr = S.T + lane * 33 + wp;  // beta mapping reads [row lane][column wp + 8 i]
   for (int s0 = 0; s0 < nS; s0 += BLK_SG) {
     double val[BLK_SG][4];
 #pragma unroll
@@ -1615,41 +1634,34 @@ scatter_blk_kernel(const double* __restrict__ IN, double* __restrict__ OUT, cons
     // ---- alpha mapping: value of every source, alpha contributions at their targets
 #pragma unroll
     for (int s = 0; s < BLK_SG; ++s) {
-      const bool live = s0 + s < nS;
-      const int sl = live ? s0 + s : 0;
-      const uint4 i0 = S.info[2 * sl];
-      const uint32_t pq = S.info[2 * sl + 1].y;
-      const double kk = __ldg(kmat + (pq >> 8) * n + (pq & 255u));
-      const int4 wa4 = act4[sl * 8 + wp];
+      const uint4 inf = S.info[s0 + s];
+      const double kk = __ldg(kmat + (inf.w >> 8) * n + (inf.w & 255u));   // a padded slot reads k_00 and adds nothing (no action)
+      const int4 wa4 = actA[(s0 + s) * 8];
       const int wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+      const uint32_t pa = (uint32_t)__popc(bL & inf.x) << 31;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double v = live ? wJ[i] * val[s][i] + kk * cjw[i] : 0.0;
-        S.T[s * BLK_TS + (wp + 8 * i) * 33 + lane] = v;
+        const double v = wJ[i] * val[s][i] + kk * cjw[i];
+        Tw[s * BLK_TS + i * (8 * 33)] = v;
         const int w = wa[i];
-        if (w >= 0 && v != 0.0) {
-          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(bL & ((w >> 29) & 1 ? i0.y : i0.x))) & 1u;
-          atomicAdd(OUTb + (int64_t)(w & 0xffffff) * N, neg ? -v : v);
-        }
+        if (w != -1 && v != 0.0)
+          atomicAdd(reinterpret_cast<double*>(OUTb + (uint64_t)((uint32_t)w & 0xffffffu) * N8), blk_flip_sign(v, (uint32_t)w ^ pa));
       }
     }
     __syncthreads();
     // ---- beta mapping: beta contributions at the mirrors of their targets
 #pragma unroll
     for (int s = 0; s < BLK_SG; ++s) {
-      const int sl = s0 + s < nS ? s0 + s : 0;
-      const uint4 i0 = S.info[2 * sl];
-      const uint32_t flipb = S.info[2 * sl + 1].x;
-      const int4 wb4 = act4[(nS + sl) * 8 + wp];
+      const uint4 inf = S.info[s0 + s];
+      const int4 wb4 = actB[(s0 + s) * 8];
       const int wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double v = S.T[s * BLK_TS + lane * 33 + wp + 8 * i];
+        const double v = Tr[s * BLK_TS + i * 8];
         const int w = wb[i];
-        if (w >= 0 && v != 0.0) {
-          const uint32_t tb = bC[i] ^ flipb;
-          const uint32_t neg = ((uint32_t)(w >> 30) ^ (uint32_t)__popc(aL & (((w >> 29) & 1 ? i0.w : i0.z) ^ tb))) & 1u;
-          atomicAdd(OUTa + (int64_t)(w & 0xffffff) * N, lambda * (neg ? -v : v));
+        if (w != -1 && v != 0.0) {
+          const uint32_t neg = (uint32_t)w ^ ((uint32_t)__popc(aL & (inf.y ^ bC[i] ^ inf.z)) << 31);
+          atomicAdd(reinterpret_cast<double*>(OUTa + (uint64_t)((uint32_t)w & 0xffffffu) * N8), lambda * blk_flip_sign(v, neg));
         }
       }
     }
@@ -1659,8 +1671,20 @@ scatter_blk_kernel(const double* __restrict__ IN, double* __restrict__ OUT, cons
 
 // dynamic shared memory of the two kernels: action table, generator info, tiles (the staged records share the tile area)
 static size_t blk_smem_bytes(int n) {
-  const size_t nS = (size_t)n * (n + 1) / 2, tiles = sizeof(double) * BLK_SG * BLK_TS, recs = sizeof(ERec) * 2 * (size_t)n * n;
-  return 2 * nS * 32 * sizeof(int32_t) + 2 * nS * sizeof(uint4) + std::max(tiles, recs);
+  const size_t nSp = ((size_t)n * (n + 1) / 2 + BLK_SG - 1) / BLK_SG * BLK_SG, tiles = sizeof(double) * BLK_SG * BLK_TS, recs = sizeof(ERec) * 2 * (size_t)n * n;
+  return 2 * nSp * 32 * sizeof(int32_t) + nSp * sizeof(uint4) + std::max(tiles, recs);
+}
+
+// the other-spin parity mask of E_pq must equal that of E_qp (it counts the other spin's electrons between p and q) for the
+// kernels above to use one mask per generator pair: checked on the host records, anything else keeps the determinant-per-thread route
+static bool blk_tables_ok(const std::vector<ERec>& tab, int n) {
+  for (int p = 0; p < n; ++p)
+    for (int q = 0; q < p; ++q)
+      for (int spin = 0; spin < 2; ++spin) {
+        const ERec &a = tab[2 * ((size_t)p * n + q) + spin], &b = tab[2 * ((size_t)q * n + p) + spin];
+        if (a.parO != b.parO || a.flip != b.flip) return false;
+      }
+  return true;
 }
 
 // OUT <- OUT + lambda U OUT in place: (U x)[A,B] = phi(A,B) x[B,A]; 32 x 32 tile pairs through shared memory
@@ -1826,7 +1850,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     tri = lambda != 0.0;
   }
   // blocked panels (32 x 32 blocks of determinants, every access a contiguous run) when a panel holds at least one block
-  const bool blk = tri && g_spinsym_blk && w->W >= 1024 && sp->NA < ((int64_t)1 << 24) && n < 256 && blk_smem_bytes(n) <= 200 * 1024;
+  const bool blk = tri && g_spinsym_blk && w->W >= 1024 && sp->NA < ((int64_t)1 << 24) && n < 256 && blk_smem_bytes(n) <= 200 * 1024 && blk_tables_ok(w->h_etab, n);
   const int64_t nbg = (sp->NA + 31) / 32, nblk = nbg * (nbg + 1) / 2, bpp = w->W / 1024;   // block grid, kept blocks, blocks per panel
   SQ_CHECK(sq_launch_scale_copy(sp, blk ? 0.5 * e_core : e_core, in_dev, out_dev, st));
   if (g_sigma_fused) {   // one fused gather -> DMMA -> scatter kernel, no D / F panels in HBM
@@ -1841,7 +1865,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
       if (w->W > bpp * 1024)   // columns behind the last block of the panel
         SQ_CUDA(cudaMemset2DAsync(Dp + bpp * 1024, sizeof(double) * (size_t)w->W, 0, sizeof(double) * (size_t)(w->W - bpp * 1024), (size_t)nrow, s));
       build_blk_kernel<false><<<(unsigned)bpp, 256, blk_smem, s>>>(in_dev, Dp, w->W, (j0 / w->W) * bpp, nblk, nbg, w->d_etab, n, sp->d_strA,
-                                                                  sp->d_rankA, sp->NA, lambda);
+                                                                  sp->d_rankA, sp->NA, (uint32_t)(sp->NA * 8), lambda);
       return launch_error("build_blk_kernel");
     }
     if (!tri) return launch_build_D(sp, w, in_dev, Dp, j0, s, use_const, sym);
@@ -1855,7 +1879,7 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
     if (blk) {
       allow_smem(scatter_blk_kernel, blk_smem);
       scatter_blk_kernel<<<(unsigned)bpp, 256, blk_smem, s>>>(in_dev, out_dev, Fp, d_k, w->W, (j0 / w->W) * bpp, nblk, nbg, w->d_etab, n,
-                                                             sp->d_strA, sp->d_rankA, sp->NA, lambda);
+                                                             sp->d_strA, sp->d_rankA, sp->NA, (uint32_t)(sp->NA * 8), lambda);
       return launch_error("scatter_blk_kernel");
     }
     if (!tri) return launch_scatter_E(sp, w, in_dev, out_dev, Fp, d_k, j0, s, use_const);
@@ -2071,7 +2095,7 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   }
   // sharded vector: the caller measured the symmetry over all ranks (sq_rdm12_dist_sym); the kept cyclic band of the local rows
   const bool half_band = sym_route && pv_ket && t_rdm_dist_lambda != 0.0 && sp->n_alpha == sp->n_beta && sp->NA == sp->NB;
-  const bool blk = tri && g_spinsym_blk && w->W >= 1024 && sp->NA < ((int64_t)1 << 24) && n < 256 && blk_smem_bytes(n) <= 200 * 1024;   // blocked panels (build_blk_kernel)
+  const bool blk = tri && g_spinsym_blk && w->W >= 1024 && sp->NA < ((int64_t)1 << 24) && n < 256 && blk_smem_bytes(n) <= 200 * 1024 && blk_tables_ok(w->h_etab, n);   // blocked panels (build_blk_kernel)
   const int64_t nbg = (sp->NA + 31) / 32, nblk = nbg * (nbg + 1) / 2, bpp = w->W / 1024;
   const size_t blk_smem = blk_smem_bytes(n);
   const int64_t len_eff = blk ? ((nblk + bpp - 1) / bpp) * w->W : (tri ? sp->NA * (sp->NA + 1) / 2 : (half_band ? half_len_host(sp) : len));
@@ -2094,7 +2118,7 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
       if (w->W > bpp * 1024)
         SQ_CUDA(cudaMemset2DAsync(Dket + bpp * 1024, sizeof(double) * (size_t)w->W, 0, sizeof(double) * (size_t)(w->W - bpp * 1024), (size_t)n2, s_build));
       build_blk_kernel<true><<<(unsigned)bpp, 256, blk_smem, s_build>>>(ket_dev, Dket, w->W, k * bpp, nblk, nbg, w->d_etab, n, sp->d_strA,
-                                                                       sp->d_rankA, sp->NA, tri_lambda);
+                                                                       sp->d_rankA, sp->NA, (uint32_t)(sp->NA * 8), tri_lambda);
       SQ_CHECK(launch_error("build_blk_kernel"));
     } else if (tri) {
       build_DSA_tri_kernel<<<(unsigned)(w->W / 256), 256, 0, s_build>>>(ket_dev, Dket, w->W, j0, len_eff, n, sp->d_strA, sp->d_strB,
