@@ -689,6 +689,10 @@ extern "C" int sq_set_option(const char* name, const char* value) {
     sq_hamiltonian_set_sigma_fused(value && value[0] == '1');
     return SQ_OK;
   }
+  if (strcmp(name, "sgemm_wm") == 0) {   // sigma DMMA kernel: "2" (default) four warps per CTA, "3" six warps (slower)
+    sq_sigma_gemm_set_row_parts(value ? atoi(value) : 2);
+    return SQ_OK;
+  }
   if (strcmp(name, "sgemm_cta") == 0) {   // sigma DMMA kernel: "2" (default) or "1" CTAs of 4 warps per SM
     sq_sigma_gemm_set_residency(value ? atoi(value) : 2);
     return SQ_OK;

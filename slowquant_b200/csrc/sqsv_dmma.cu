@@ -343,15 +343,18 @@ int sq_gram_sym_end(int n_split, const double* d_partial, double* d_G, cudaStrea
 #define SG_STAGES 3
 #define SG_THREADS 128
 
-template <int MH>            // MH = row fragments per warp: the two row-halves of a CTA cover 2 * MH * 8 >= nrow rows (9 for 136 rows)
-__global__ void __launch_bounds__(SG_THREADS, 2)
+// WM = row parts of a CTA (2 warps each: 32 determinants per warp), MH = row fragments per warp: WM * MH * 8 >= nrow rows per CTA
+// (136 rows: 2 x 9 -- four warps, the default; 3 x 6 -- six warps per CTA, three per SM sub-partition with two CTAs per SM: slower)
+template <int WM, int MH>
+__global__ void __launch_bounds__(WM * 64, 2)
 sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restrict__ D, double* __restrict__ F, int nrow, int64_t W) {
   extern __shared__ __align__(16) double ssm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int64_t t0 = (int64_t)blockIdx.x * SG_BN;
-  const int m0 = blockIdx.y * (2 * MH * 8);               // first output row of this CTA (row tiles of 16 * MH rows)
-  constexpr int MP = 2 * MH * 8;                          // padded rows held in shared memory
+  constexpr int NT = WM * 64;                             // threads
+  constexpr int MP = WM * MH * 8;                         // padded rows held in shared memory
+  const int m0 = blockIdx.y * MP;                         // first output row of this CTA
   constexpr int stage_d = MP * SG_LDA + SG_KC * SG_LDB;   // doubles per stage
   const int n_chunks = (nrow + SG_KC - 1) / SG_KC;
   double acc[MH][4][2];
@@ -364,13 +367,13 @@ sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restri
     const int k0 = c * SG_KC;
     const uint32_t sa = sbase + (uint32_t)(slot * stage_d) * 8u, sb = sa + (uint32_t)(MP * SG_LDA) * 8u;
     // Gm chunk: MP rows x 16 doubles = MP * 8 16-byte chunks (rows / columns beyond the matrix are zero-filled)
-    for (int id = threadIdx.x; id < MP * 8; id += SG_THREADS) {
+    for (int id = threadIdx.x; id < MP * 8; id += NT) {
       const int m = id >> 3, ch = id & 7;
       const bool ok = m0 + m < nrow && k0 + ch * 2 < ldg; // ldg is even; the pad column of an odd nrow holds zeros
       cp16(sa + (uint32_t)(m * SG_LDA + ch * 2) * 8u, Gm + (size_t)(ok ? m0 + m : 0) * ldg + (ok ? k0 + ch * 2 : 0), ok ? 16 : 0);
     }
     // D chunk: 16 rows x 64 doubles = 512 16-byte chunks
-    for (int id = threadIdx.x; id < SG_KC * (SG_BN / 2); id += SG_THREADS) {
+    for (int id = threadIdx.x; id < SG_KC * (SG_BN / 2); id += NT) {
       const int k = id >> 5, ch = id & 31;
       const bool ok = k0 + k < nrow;
       cp16(sb + (uint32_t)(k * SG_LDB + ch * 2) * 8u, D + (size_t)(ok ? k0 + k : 0) * W + t0 + ch * 2, ok ? 16 : 0);
@@ -411,19 +414,23 @@ sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restri
   }
 }
 
+static int g_sigma_row_parts = 2;    // sq_set_option("sgemm_wm", "2" | "3"): row parts (pairs of warps) of a sigma GEMM CTA.  Measured at CAS(16,16): sigma 174 ms
+                                     // with 2 x 9 fragments, 187 ms with 3 x 6 (more A-fragment loads per DMMA: the kernel is bound by the shared-memory
+                                     // data pipe, not by warps per sub-partition; profiles/r2_visit38_ab_sgemm_wm.txt)
+void sq_sigma_gemm_set_row_parts(int n) { g_sigma_row_parts = n == 3 ? 3 : 2; }
 static int g_sigma_cta_per_sm = 2;   // measured at CAS(16,16): sigma 445 ms with two CTAs per SM, 524 ms with one (profiles/r2_visit5_ab_sgemm_cta.txt); sq_set_option("sgemm_cta", "1" | "2"): GEMM CTAs per SM (the rest of the SM runs gathers / scatters)
 void sq_sigma_gemm_set_residency(int n) { g_sigma_cta_per_sm = n == 1 ? 1 : 2; }
 
-template <int MH>
+template <int WM, int MH>
 static int launch_sigma_mh(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, int m_tiles, cudaStream_t st) {
-  size_t smem = sizeof(double) * SG_STAGES * ((size_t)2 * MH * 8 * SG_LDA + SG_KC * SG_LDB);
+  size_t smem = sizeof(double) * SG_STAGES * ((size_t)WM * MH * 8 * SG_LDA + SG_KC * SG_LDB);
   if (g_sigma_cta_per_sm == 1 && smem < 116 * 1024) smem = 116 * 1024;   // more than half of the SM's shared memory: one CTA per SM
   static size_t attr = 0;
   if (smem > attr) {
-    SQ_CUDA(cudaFuncSetAttribute(sigma_dmma_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SQ_CUDA(cudaFuncSetAttribute(sigma_dmma_kernel<WM, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  sigma_dmma_kernel<MH><<<dim3((unsigned)(W / SG_BN), (unsigned)m_tiles), SG_THREADS, smem, st>>>(Gm, ldg, D, F, nrow, W);
+  sigma_dmma_kernel<WM, MH><<<dim3((unsigned)(W / SG_BN), (unsigned)m_tiles), WM * 64, smem, st>>>(Gm, ldg, D, F, nrow, W);
   return SQ_OK;
 }
 
@@ -437,13 +444,22 @@ int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nro
   // accumulators: 8 * MH doubles per thread, MH <= 9: up to 144 rows per CTA; more rows (n = 16 with unsymmetric integrals: 256,
   // n = 20 symmetrised: 210) are split into equal row tiles along gridDim.y
   const int m_tiles = (nrow + 143) / 144;
-  const int mh = ((nrow + m_tiles - 1) / m_tiles + 15) / 16;
+  const int rows_cta = (nrow + m_tiles - 1) / m_tiles;
   int rc = SQ_ERR_UNSUPPORTED;
-  switch (mh) {
-#define SG_CASE(M) case M: rc = launch_sigma_mh<M>(Gm, ldg, D, F, nrow, W, m_tiles, st); break;
-    SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8) SG_CASE(9)
+  if (g_sigma_row_parts == 3 && rows_cta > 48) {   // six warps per CTA: 24 * MH rows
+    switch ((rows_cta + 23) / 24) {
+#define SG_CASE(M) case M: rc = launch_sigma_mh<3, M>(Gm, ldg, D, F, nrow, W, m_tiles, st); break;
+      SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6)
 #undef SG_CASE
-    default: break;
+      default: break;
+    }
+  } else {
+    switch ((rows_cta + 15) / 16) {
+#define SG_CASE(M) case M: rc = launch_sigma_mh<2, M>(Gm, ldg, D, F, nrow, W, m_tiles, st); break;
+      SG_CASE(1) SG_CASE(2) SG_CASE(3) SG_CASE(4) SG_CASE(5) SG_CASE(6) SG_CASE(7) SG_CASE(8) SG_CASE(9)
+#undef SG_CASE
+      default: break;
+    }
   }
   if (rc == SQ_ERR_UNSUPPORTED) {
     sq_set_error("sigma GEMM: no kernel instantiation for %d generator rows", nrow);

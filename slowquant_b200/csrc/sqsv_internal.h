@@ -252,6 +252,7 @@ int sq_gram_sym_begin(int n_sm, double** d_partial, size_t* partial_doubles, int
 int sq_gram_sym_panel(const double* Z, int64_t ld, int rows0, int rows1, int64_t K, int n_split, double* d_partial, cudaStream_t st);
 int sq_gram_sym_end(int n_split, const double* d_partial, double* d_G, cudaStream_t st);
 void sq_sigma_gemm_set_residency(int n);
+void sq_sigma_gemm_set_row_parts(int n);   // 2 (default): four warps per sigma GEMM CTA, 3: six
 int sq_sigma_gemm(const double* Gm, int ldg, const double* D, double* F, int nrow, int64_t W, cudaStream_t st);
 int sq_panel_gemv(const double* D, int64_t W, int nrows, const double* x, int64_t K, double* g1, cudaStream_t st);
 int sq_ensure_work(sq_space* sp, int which);

@@ -1,5 +1,6 @@
 """A/B of a run-time switch of the sigma / RDM path at a given CAS:  python tools/ab_option.py [n] [option] [value_a] [value_b]
-(defaults: 16 pipeline 0 1; e.g. `16 etab smem const`).  Prints timings of both settings (twice) and the result differences."""
+(defaults: 16 pipeline 0 1; e.g. `16 etab smem const`; a fifth argument `tups` takes a spin-flip symmetric tUPS state instead of a
+random vector).  Prints timings of both settings (twice) and the result differences."""
 import sys
 import time
 
@@ -27,8 +28,17 @@ g = g + g.transpose(0, 1, 3, 2)
 g = g + g.transpose(2, 3, 0, 1)
 H = hamiltonian_0i_0a(h, g, 0, n)
 dev = torch.device("cuda", info.device)
-ci = torch.randn(info.num_det, dtype=torch.float64, device=dev)
-ci /= torch.linalg.norm(ci)
+if len(sys.argv) > 5 and sys.argv[5] == "tups":
+    from slowquant_b200.util import UpsStructure  # noqa: E402
+
+    lay = UpsStructure()
+    lay.create_tiled(n, {"n_layers": 4, "do_tups": True})
+    hf = torch.zeros(info.num_det, dtype=torch.float64, device=dev)
+    hf[0] = 1.0
+    ci = osa.construct_ups_state(hf, info, np.random.default_rng(3).uniform(-np.pi, np.pi, lay.n_params).tolist(), lay)
+else:
+    ci = torch.randn(info.num_det, dtype=torch.float64, device=dev)
+    ci /= torch.linalg.norm(ci)
 lib = _lib.load()
 res = {}
 for mode in (va, vb, va, vb):
