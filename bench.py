@@ -513,16 +513,18 @@ def run_ours(args) -> None:
             g_syn = np.zeros((n, n, n, n))
             WF = WaveFunctionUPS((n, n), np.eye(n), ArrayIntegrals(h_syn + h_syn.T, g_syn, num_elec=n), "tUPS", {"n_layers": L}, device=local_rank)
             th_list = thetas.tolist()
-            for _ in range(2):   # two warm-up calls: the setter keeps the old state alive until the new one exists, so the
-                WF.thetas = th_list   # caching allocator needs two 1.3 GB blocks before it stops calling cudaMalloc
+            for _ in range(3):   # warm-up calls: the setter keeps the old state alive until the new one exists, so the caching
+                WF.thetas = th_list   # allocator needs two 1.3 GB blocks (carved out of what the earlier stages left) before it stops calling cudaMalloc
             torch.cuda.synchronize()
+            n_set = max(n_e2e, 8)     # 42 ms per call: enough calls that one allocator hiccup does not decide the number
             t0 = time.perf_counter()
-            for _ in range(n_e2e):
+            for _ in range(n_set):
                 WF.thetas = th_list
                 probe = float(WF.ci_coeffs_device[0].item())
             dtw = time.perf_counter() - t0
             e2e["wavefunction_setter"] = {
-                "value": L * n_e2e / dtw,
+                "value": L * n_set / dtw,
+                "calls": n_set,
                 "unit": UNIT,
                 "api": "WaveFunctionUPS.thetas = x (reference state resident on the device), one amplitude read back",
                 "h2d_bytes_per_step": int(8 * P),

@@ -350,13 +350,16 @@ __global__ void __launch_bounds__(WM * 64, 2)
 sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restrict__ D, double* __restrict__ F, int nrow, int64_t W) {
   extern __shared__ __align__(16) double ssm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 1, wn = warp & 1;
+  // row part and column half of this warp; with two row parts the assignment alternates with the CTA index, so that the two CTAs
+  // of an SM put one warp of each row part on every sub-partition (the parts differ in their number of live row fragments)
+  const int wm = WM == 2 ? ((warp >> 1) ^ (int)(blockIdx.x & 1u)) : warp >> 1, wn = warp & 1;
   const int64_t t0 = (int64_t)blockIdx.x * SG_BN;
   constexpr int NT = WM * 64;                             // threads
   constexpr int MP = WM * MH * 8;                         // padded rows held in shared memory
   const int m0 = blockIdx.y * MP;                         // first output row of this CTA
   constexpr int stage_d = MP * SG_LDA + SG_KC * SG_LDB;   // doubles per stage
   const int n_chunks = (nrow + SG_KC - 1) / SG_KC;
+  const int nfrag = min(MH, (nrow - m0 - wm * MH * 8 + 7) / 8);   // live row fragments of this warp (136 rows: 9 and 8); the others stay zero, unstored
   double acc[MH][4][2];
 #pragma unroll
   for (int i = 0; i < MH; ++i)
@@ -390,16 +393,20 @@ sigma_dmma_kernel(const double* __restrict__ Gm, int ldg, const double* __restri
     cp_commit();
     const double* as = ssm + (it % SG_STAGES) * stage_d + (wm * MH * 8) * SG_LDA;
     const double* bs = ssm + (it % SG_STAGES) * stage_d + MP * SG_LDA + wn * 32;
+    const int kleft = nrow - it * SG_KC;   // rows of D in this chunk; the zero-filled rest of the last chunk is skipped
 #pragma unroll
     for (int k4 = 0; k4 < SG_KC / 4; ++k4) {
+      if (k4 * 4 >= kleft) break;
       double bf[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bf[j] = bs[(k4 * 4 + (lane & 3)) * SG_LDB + j * 8 + (lane >> 2)];
 #pragma unroll
       for (int i = 0; i < MH; ++i) {
-        const double a = as[(i * 8 + (lane >> 2)) * SG_LDA + k4 * 4 + (lane & 3)];
+        if (i < nfrag) {
+          const double a = as[(i * 8 + (lane >> 2)) * SG_LDA + k4 * 4 + (lane & 3)];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a, bf[j]);
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a, bf[j]);
+        }
       }
     }
   }
