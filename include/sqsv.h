@@ -123,7 +123,14 @@ int sq_layout_plan_export(const sq_layout* lay, const double* thetas_host, int f
  * scatter kernels, "1" row-per-CTA kernels with the row staged in shared memory (measured slower; "rows_cfg" =
  * "threads,chunks" sets their geometry).  name "panel": determinants per
  * panel for spaces that build their panels afterwards ("0": about 1 GiB per panel).  name "rdm_tri": "1" builds the symmetric
- * Gram matrix of sq_rdm12 with bra == ket from three half-size DGEMMs (3/4 of the flops), "0" (default) from one DGEMM. */
+ * Gram matrix of sq_rdm12 with bra == ket from three half-size DGEMMs (3/4 of the flops), "0" (default) from one DGEMM.
+ * name "sigma_spinsym": sq_sigma / sq_rdm12 of a spin-flip symmetric vector (c[B,A] = lambda (-1)^popc(A & B) c[A,B], measured on
+ * every call) from the determinants above the diagonal: "1" (default; 32 x 32 blocks of determinants, beta partners through their
+ * mirrors), "tri" (determinant-per-thread kernels of the half build), "0" (always the full build).  name "quadgrad": "1" (default)
+ * two commuting bricks per launch of the theta-gradient sweep, "0" one.  name "win3": "1" window sweeps with register blocks over
+ * orbital triples (measured slower; default "0").  name "rdm_sym": "1" (default) two symmetric Gram matrices of the S / A generators
+ * for bra == ket.  name "sgemm_cta" / "sgemm_wm": CTAs per SM ("2") and row parts per CTA ("2") of the sigma DMMA kernel.
+ * The switches are process-global (not per space): set them before the calls they affect, from one thread. */
 int sq_set_option(const char* name, const char* value);
 
 /* ---- unitary product state (construct_ups_state, operator_state_algebra.py:963-1412;
