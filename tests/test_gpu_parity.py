@@ -948,6 +948,49 @@ def test_sigma_of_spin_flip_symmetric_vectors(sq, n, ne, L, panel):
         lib.sq_set_option(b"sigma_spinsym", b"1")
 
 
+def test_sigma_half_builds_at_cas14(sq):
+    """At a size with many panels of whole CTA waves (CAS(14,14): 11 778 624 determinants, 5 886 blocks of 32 x 32 determinants
+    above the diagonal, default panel width): the blocked half build, the determinant-per-thread half build and the full build
+    of H|psi> for a tUPS state agree to 1e-13, and so do the energies <psi|H|psi> from sigma and from the 1-/2-RDMs of the
+    blocked route (trace of the 1-RDM = number of electrons)."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    lib = sq.lib.load()
+    n, ne = 14, 7
+    rng = np.random.default_rng(1414)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    info = sq.ci.get_indexing(0, n, 0, ne, ne)
+    dev = torch.device("cuda", info.device)
+    types, idx, th, _ = _seeded_case(n, ne, ne, 3, 1407)
+    lay = _layout(sq, types, idx)
+    hf = torch.zeros(info.num_det, dtype=torch.float64, device=dev)
+    hf[0] = 1.0
+    psi = sq.osa.construct_ups_state(hf, info, th.tolist(), lay)
+    H = hamiltonian_0i_0a(h, g, 0, n)
+    out = {}
+    try:
+        for mode in (b"0", b"tri", b"1"):
+            lib.sq_set_option(b"sigma_spinsym", mode)
+            l0 = lib.sq_launch_count()
+            out[mode] = sq.osa.propagate_state([H], psi, info)
+            out[mode, "launches"] = lib.sq_launch_count() - l0
+        scale = float(torch.max(torch.abs(out[b"0"])))
+        assert float(torch.max(torch.abs(out[b"1"] - out[b"0"]))) < 1e-13 * max(1.0, scale)
+        assert float(torch.max(torch.abs(out[b"tri"] - out[b"0"]))) < 1e-13 * max(1.0, scale)
+        assert out[b"1", "launches"] < out[b"0", "launches"] and out[b"tri", "launches"] < out[b"0", "launches"]
+        e_sigma = float(torch.dot(psi, out[b"1"]))
+        d1, d2 = sq.osa.reduced_density_matrices(psi, psi, info)
+        assert abs(np.trace(d1) - 2 * ne) < 1e-11
+        assert abs(float(np.sum(h * d1) + 0.5 * np.sum(g * d2)) - e_sigma) < 1e-10
+    finally:
+        lib.sq_set_option(b"sigma_spinsym", b"1")
+
+
 def test_per_string_kernels_against_reference_outputs(sq):
     """The reference's per-string entry points (osa.py:33-410: apply_operator_serial / _threaded, their _SA twins,
     add_operator_matrix) through the gather kernel, on CAS(4,5) with 3 alpha / 1 beta electrons, against outputs of the
