@@ -122,6 +122,12 @@ def load() -> C.CDLL:
         return _lib
     # rebuild when the library is missing OR older than its sources (digest of the .cu / .h files against the build
     # stamp): the .so is git-ignored and travels with repository snapshots, so a stale binary must never be picked up
+    alt = os.environ.get("SQSV_LIB")   # developer switch: A/B of compile-time variants of the library (tools/ab_quad_rows.sh)
+    if alt:
+        lib = C.CDLL(alt, mode=C.RTLD_GLOBAL)
+        _declare(lib)
+        _lib = lib
+        return lib
     if os.path.exists(os.path.join(_HERE, "csrc", "sqsv_api.cu")) or not os.path.exists(LIB_PATH):
         from slowquant_b200.build import build_library
 

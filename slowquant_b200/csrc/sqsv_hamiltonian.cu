@@ -1859,9 +1859,12 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   }
   const int64_t len_eff = blk ? ((nblk + bpp - 1) / bpp) * w->W : (tri ? sp->NA * (sp->NA + 1) / 2 : len);
   const size_t blk_smem = blk_smem_bytes(n);
+  if (blk) {
+    allow_smem(build_blk_kernel<false>, blk_smem);
+    allow_smem(scatter_blk_kernel, blk_smem);
+  }
   auto build_panel = [&](double* Dp, int64_t j0, cudaStream_t s) -> int {
     if (blk) {
-      allow_smem(build_blk_kernel<false>, blk_smem);
       if (w->W > bpp * 1024)   // columns behind the last block of the panel
         SQ_CUDA(cudaMemset2DAsync(Dp + bpp * 1024, sizeof(double) * (size_t)w->W, 0, sizeof(double) * (size_t)(w->W - bpp * 1024), (size_t)nrow, s));
       build_blk_kernel<false><<<(unsigned)bpp, 256, blk_smem, s>>>(in_dev, Dp, w->W, (j0 / w->W) * bpp, nblk, nbg, w->d_etab, n, sp->d_strA,
@@ -1877,7 +1880,6 @@ extern "C" int sq_sigma(sq_space* sp, double e_core, const double* h_act_host, c
   };
   auto scatter_panel = [&](const double* Fp, int64_t j0, cudaStream_t s) -> int {
     if (blk) {
-      allow_smem(scatter_blk_kernel, blk_smem);
       scatter_blk_kernel<<<(unsigned)bpp, 256, blk_smem, s>>>(in_dev, out_dev, Fp, d_k, w->W, (j0 / w->W) * bpp, nblk, nbg, w->d_etab, n,
                                                              sp->d_strA, sp->d_rankA, sp->NA, (uint32_t)(sp->NA * 8), lambda);
       return launch_error("scatter_blk_kernel");
@@ -2099,6 +2101,7 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
   const int64_t nbg = (sp->NA + 31) / 32, nblk = nbg * (nbg + 1) / 2, bpp = w->W / 1024;
   const size_t blk_smem = blk_smem_bytes(n);
   const int64_t len_eff = blk ? ((nblk + bpp - 1) / bpp) * w->W : (tri ? sp->NA * (sp->NA + 1) / 2 : (half_band ? half_len_host(sp) : len));
+  if (blk) allow_smem(build_blk_kernel<true>, blk_smem);
   // Two-stage pipeline: the gather of panel k+1 runs beside the DGEMM of panel k (two panels per vector in flight).
   const bool piped = g_panel_pipeline && w->d_D[1] && (same || !rdm2_host || w->d_D[3]);
   cudaStream_t s_build = piped ? w->s_build : st, s_gemm = piped ? w->s_gemm : st;
@@ -2114,7 +2117,6 @@ static int rdm12_impl(sq_space* sp, const double* bra_dev, const double* ket_dev
     double* Dket = w->d_D[b];
     if (piped && k >= 2) SQ_CUDA(cudaStreamWaitEvent(s_build, w->ev_gemm[b], 0));   // panels b are free once GEMM k-2 is done
     if (blk) {
-      allow_smem(build_blk_kernel<true>, blk_smem);
       if (w->W > bpp * 1024)
         SQ_CUDA(cudaMemset2DAsync(Dket + bpp * 1024, sizeof(double) * (size_t)w->W, 0, sizeof(double) * (size_t)(w->W - bpp * 1024), (size_t)n2, s_build));
       build_blk_kernel<true><<<(unsigned)bpp, 256, blk_smem, s_build>>>(ket_dev, Dket, w->W, k * bpp, nblk, nbg, w->d_etab, n, sp->d_strA,

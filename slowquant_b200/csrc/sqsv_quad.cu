@@ -36,7 +36,9 @@
 #define QUAD_MINBLOCKS 3     // <= 85 registers per thread -> 24 resident warps per SM
 #endif
 #endif
-#define QUAD_ROWS 16
+#ifndef QUAD_ROWS
+#define QUAD_ROWS 16   // row groups per CTA
+#endif
 #define QUAD_STAGES 3
 
 struct QuadMats {

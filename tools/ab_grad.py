@@ -57,8 +57,9 @@ gq, bq, kq = sweep("two bricks per launch (quad)")
 print("    max|grad diff| %.2e  max|bra diff| %.2e  max|ket diff| %.2e" % (
     float(np.max(np.abs(gq - g0))), float(torch.max(torch.abs(bq - b0))), float(torch.max(torch.abs(kq - k0)))), flush=True)
 lib.sq_set_option(b"wingrad", b"1")
-for cfg in cfgs:
+for cfg in ([] if cfgs == ["none"] else cfgs):
     lib.sq_set_option(b"wingrad_win", cfg.encode())
     g1, b1, k1 = sweep("window kernel " + cfg)
     print("    max|grad diff| %.2e  max|bra diff| %.2e  max|ket diff| %.2e" % (
         float(np.max(np.abs(g1 - g0))), float(torch.max(torch.abs(b1 - b0))), float(torch.max(torch.abs(k1 - k0)))), flush=True)
+lib.sq_set_option(b"wingrad", b"0")
