@@ -207,6 +207,11 @@ class WaveFunctionUPS:
         else:
             raise ValueError(f"Got unknown ansatz, {ansatz}")
         self._thetas = np.zeros(self.ups_layout.n_params).tolist()
+        # a single-determinant reference: the `thetas` setter runs the head of the circuit in the orbital window it can reach
+        # (operator_state_algebra.construct_ups_state_from_determinant); `light_cone = False` takes the plain route
+        nz = np.flatnonzero(self.csf_coeffs)
+        self._ref_det: int | None = int(nz[0]) if nz.size == 1 and self.csf_coeffs[nz[0]] == 1.0 else None
+        self.light_cone = True
         dev = torch.device("cuda", self.ci_info.device)
         self._csf_dev = torch.from_numpy(self.csf_coeffs).to(dev)
         self._ci_dev = self._csf_dev.clone()
@@ -265,7 +270,10 @@ class WaveFunctionUPS:
         self._rdm3 = self._rdm4 = None
         self._energy_elec = None
         self._thetas = [float(x) for x in theta_vals]
-        self._ci_dev = osa.construct_ups_state(self._csf_dev, self.ci_info, self._thetas, self.ups_layout)
+        if self._ref_det is not None and self.light_cone:
+            self._ci_dev = osa.construct_ups_state_from_determinant(self._ref_det, self.ci_info, self._thetas, self.ups_layout)
+        else:
+            self._ci_dev = osa.construct_ups_state(self._csf_dev, self.ci_info, self._thetas, self.ups_layout)
         self._ci_host = None
 
     @property

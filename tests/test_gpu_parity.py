@@ -991,6 +991,30 @@ def test_sigma_half_builds_at_cas14(sq):
         lib.sq_set_option(b"sigma_spinsym", b"1")
 
 
+@pytest.mark.parametrize("n,ne,L,qnp", [(8, 4, 3, False), (9, 4, 3, True), (10, 5, 4, False), (12, 6, 5, False), (16, 8, 16, False)])
+def test_light_cone_state_construction(sq, n, ne, L, qnp):
+    """construct_ups_state_from_determinant: the head of the circuit in the orbital window the reference determinant's light cone
+    reaches (a smaller CAS space, same kernels), embedded, then the tail in the full space -- against the plain route (all
+    operators on the full vector) to 1e-13, against the oracle at the small sizes; (16, 8, 16) is the circuit of the bench."""
+    types, idx, th, _ = _seeded_case(n, ne, ne, L, 7700 + n, qnp=qnp)
+    lay = _layout(sq, types, idx)
+    info = sq.ci.get_indexing(0, n, 0, ne, ne)
+    a = int(info.strings(0)[0])
+    plan = sq.osa._light_cone_plan(info, lay, a, a)
+    assert plan is not None and plan["window"][1] - plan["window"][0] < n and plan["k0"] > len(plan["head"])
+    plain = sq.osa.construct_ups_state_from_determinant(0, info, th.tolist(), lay, light_cone=False)
+    l0 = sq.lib.load().sq_launch_count()
+    cone = sq.osa.construct_ups_state_from_determinant(0, info, th.tolist(), lay, light_cone=True)
+    assert sq.lib.load().sq_launch_count() > l0
+    assert float(torch.max(torch.abs(cone - plain))) < 1e-13
+    assert abs(float(torch.linalg.norm(cone)) - 1.0) < 1e-12
+    if n <= 10:
+        sp = orc.get_indexing(0, n, 0, ne, ne)
+        hf = np.zeros(sp.num_det)
+        hf[0] = 1.0
+        assert np.max(np.abs(cone.cpu().numpy() - orc.construct_ups_state(hf, sp, th, types, idx))) < 1e-12
+
+
 def test_per_string_kernels_against_reference_outputs(sq):
     """The reference's per-string entry points (osa.py:33-410: apply_operator_serial / _threaded, their _SA twins,
     add_operator_matrix) through the gather kernel, on CAS(4,5) with 3 alpha / 1 beta electrons, against outputs of the
