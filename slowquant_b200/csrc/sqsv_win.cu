@@ -67,8 +67,11 @@ struct WinProgram {
   WinBrick br[SQ_WIN_MAX_BRICKS];
 };
 
+#ifndef WIN_CP_HINT
+#define WIN_CP_HINT ""   // L2 prefetch hint of the tile copies (".L2::128B" / ".L2::256B": compile-time A/B, tools/ab_win_variants.sh)
+#endif
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const double* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+  asm volatile("cp.async.ca.shared.global" WIN_CP_HINT " [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
