@@ -545,6 +545,29 @@ def ups_gradient_sweep(
     return g, _from_device(b, b_np), _from_device(k, k_np)
 
 
+def ups_gradient_sweep_backward(bra, ket, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure):
+    r"""The gradient loop of ups_wavefunction.py:1114-1138 run BACKWARDS through the circuit: started from
+    (bra, ket) = (H|psi>, |psi>) with |psi> = U(theta)|ref>, for k = P-1 ... 0: g_k = 2 <bra|T_k|ket>, then both vectors
+    <- U_k^dagger (``sq_ups_grad_sweep_list_rev``).  T_k commutes with its own rotation, so these are the numbers of the
+    reference's forward loop from (U^dagger H|psi>, |ref>) without the adjoint pass.  Returns (gradient, bra, ket) with the two
+    vectors rotated back to (U^dagger H|psi>, |ref>); the inputs are not modified."""
+    lib = _lib.load()
+    lay = compile_layout(ci_info, ups_struct)
+    n = len(ups_struct.excitation_operator_type)
+    th = _thetas_array(thetas, n)
+    b, b_np = _to_device(bra, ci_info)
+    k, k_np = _to_device(ket, ci_info)
+    ops = np.arange(n - 1, -1, -1, dtype=np.int32)
+    out = np.zeros(max(n, 1), dtype=np.float64)
+    _lib.check(
+        lib.sq_ups_grad_sweep_list_rev(ci_info._handle, lay, th.ctypes.data_as(_PD), n, ops.ctypes.data_as(_PI), _ptr(b), _ptr(k),
+                                       out.ctypes.data_as(_PD), _stream())
+    )
+    g = np.zeros(n, dtype=np.float64)
+    g[ops] = out[:n]
+    return g, _from_device(b, b_np), _from_device(k, k_np)
+
+
 def ups_energy_and_gradient(
     ref_state, ci_info: CI_Info, thetas: Sequence[float], ups_struct: UpsStructure, hamiltonian: ActiveSpaceHamiltonian,
     want_gradient: bool = True,

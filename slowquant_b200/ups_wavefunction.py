@@ -212,6 +212,8 @@ class WaveFunctionUPS:
         nz = np.flatnonzero(self.csf_coeffs)
         self._ref_det: int | None = int(nz[0]) if nz.size == 1 and self.csf_coeffs[nz[0]] == 1.0 else None
         self.light_cone = True
+        self._sigma_dev: torch.Tensor | None = None   # H|psi> of the current state and integrals (shared by energy and gradient)
+        self._ci_from_thetas = True                   # the device state is U(thetas)|reference>
         dev = torch.device("cuda", self.ci_info.device)
         self._csf_dev = torch.from_numpy(self.csf_coeffs).to(dev)
         self._ci_dev = self._csf_dev.clone()
@@ -253,6 +255,7 @@ class WaveFunctionUPS:
         self._h_mo = None
         self._g_mo = None
         self._energy_elec = None
+        self._sigma_dev = None
         self._kappa = list(k)
         self._c_mo = self.c_mo
         self._kappa_old = self.kappa
@@ -269,6 +272,8 @@ class WaveFunctionUPS:
         self._rdm1 = self._rdm2 = None
         self._rdm3 = self._rdm4 = None
         self._energy_elec = None
+        self._sigma_dev = None
+        self._ci_from_thetas = True
         self._thetas = [float(x) for x in theta_vals]
         if self._ref_det is not None and self.light_cone:
             self._ci_dev = osa.construct_ups_state_from_determinant(self._ref_det, self.ci_info, self._thetas, self.ups_layout)
@@ -290,6 +295,8 @@ class WaveFunctionUPS:
         self._rdm1 = self._rdm2 = None
         self._rdm3 = self._rdm4 = None
         self._energy_elec = None
+        self._sigma_dev = None
+        self._ci_from_thetas = False
 
     @property
     def ci_coeffs_device(self) -> torch.Tensor:
@@ -369,6 +376,19 @@ class WaveFunctionUPS:
             self._energy_elec = osa.expectation_value(self._ci_dev, [H], self._ci_dev, self.ci_info)
         return self._energy_elec
 
+    def _sigma(self) -> torch.Tensor:
+        """H|psi> of the current state with the current integrals, kept until the state or the integrals change."""
+        if self._sigma_dev is None:
+            H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
+            self._sigma_dev = osa.propagate_state([H], self._ci_dev, self.ci_info)
+        return self._sigma_dev
+
+    def _set_thetas_if_changed(self, theta_vals) -> None:
+        """The optimiser asks for the energy and then for the gradient at the same parameters: one state construction, not two."""
+        new = [float(x) for x in theta_vals]
+        if new != self._thetas or not self._ci_from_thetas:
+            self.thetas = new
+
     # ---- optimisation callables (ups_wavefunction.py:1019-1142) -----------------------------------
     def _calc_energy_optimization(self, parameters, theta_optimization: bool, kappa_optimization: bool) -> float:
         if np.max(np.abs(np.array(self._old_opt_parameters) - np.array(parameters))) < 10**-14:
@@ -378,14 +398,13 @@ class WaveFunctionUPS:
             num_kappa = len(self.kappa_idx)
             self.kappa = list(parameters[:num_kappa])
         if theta_optimization:
-            self.thetas = list(parameters[num_kappa:])
+            self._set_thetas_if_changed(parameters[num_kappa:])
         if kappa_optimization:
             E = get_electronic_energy(
                 self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs, self.rdm1, self.rdm2
             )
         else:
-            H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
-            E = osa.expectation_value(self._ci_dev, [H], self._ci_dev, self.ci_info)
+            E = osa._dot(self._ci_dev, self._sigma(), self.ci_info)
         self._E_opt_old = E
         self._old_opt_parameters = np.copy(parameters)
         self.num_energy_evals += 1
@@ -398,16 +417,16 @@ class WaveFunctionUPS:
             num_kappa = len(self.kappa_idx)
             self.kappa = list(parameters[:num_kappa])
         if theta_optimization:
-            self.thetas = list(parameters[num_kappa:])
+            self._set_thetas_if_changed(parameters[num_kappa:])
         if kappa_optimization:
             gradient[:num_kappa] = get_orbital_gradient(
                 self.h_mo, self.g_mo, self.kappa_idx, self.num_inactive_orbs, self.num_active_orbs, self.rdm1, self.rdm2
             )
         if theta_optimization:
-            H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
-            bra = osa.propagate_state([H], self._ci_dev, self.ci_info)
-            osa._ups_apply_inplace(bra, self.ci_info, self._thetas, self.ups_layout, 0, len(self._thetas), True)
-            g, _, _ = osa.ups_gradient_sweep(bra, self._csf_dev, self.ci_info, self._thetas, self.ups_layout)
+            # the loop of ups_wavefunction.py:1114-1138 run BACKWARDS through the circuit from (H|psi>, |psi>): 2 <bra|T_k|ket>, then
+            # both vectors <- U_k^dagger (T_k commutes with its own rotation: the same numbers, without the adjoint pass U^dagger H|psi>
+            # and without rebuilding the state from the reference); H|psi> is shared with the energy evaluation at the same parameters
+            g, _, _ = osa.ups_gradient_sweep_backward(self._sigma(), self._ci_dev, self.ci_info, self._thetas, self.ups_layout)
             gradient[num_kappa:] += g
             self.num_energy_evals += 2 * int(np.sum(list(self.ups_layout.grad_param_R.values())))
         return gradient

@@ -70,6 +70,14 @@ def ups_gradient_sweep(bra, ket, ci, thetas, lay):
         _ups_apply_inplace(b, ci, thetas, lay, i, i + 1, False); _ups_apply_inplace(k, ci, thetas, lay, i, i + 1, False)
     return g, b, k
 osa.ups_gradient_sweep = ups_gradient_sweep
+def ups_gradient_sweep_backward(bra, ket, ci, thetas, lay):
+    b, _ = _to_device(bra, ci); k, _ = _to_device(ket, ci)
+    n = len(lay.excitation_operator_type); g = np.zeros(n)
+    for i in reversed(range(n)):
+        g[i] = 2 * float(torch.dot(b, get_grad_action(k, i, ci, lay)))
+        _ups_apply_inplace(b, ci, thetas, lay, i, i + 1, True); _ups_apply_inplace(k, ci, thetas, lay, i, i + 1, True)
+    return g, b, k
+osa.ups_gradient_sweep_backward = ups_gradient_sweep_backward
 def reduced_density_matrices(bra, ket, ci, want_rdm2=True):
     from slowquant_b200 import operators as mops
     n = ci.num_active_orbs; sp = space_of(ci)

@@ -1015,6 +1015,40 @@ def test_light_cone_state_construction(sq, n, ne, L, qnp):
         assert np.max(np.abs(cone.cpu().numpy() - orc.construct_ups_state(hf, sp, th, types, idx))) < 1e-12
 
 
+@pytest.mark.parametrize("n,ne,L,qnp", [(6, 3, 2, False), (8, 4, 2, True), (9, 4, 2, False)])
+def test_backward_gradient_sweep_entry(sq, n, ne, L, qnp):
+    """operator_state_algebra.ups_gradient_sweep_backward (what WaveFunctionUPS._calc_gradient_optimization calls): from
+    (H|psi>, |psi>) backwards through the circuit -- against the reference's forward loop from (U^dagger H|psi>, |ref>)
+    (ups_wavefunction.py:1114-1138) and the oracle's gradient; the vectors come back as (U^dagger H|psi>, |ref>), the inputs are
+    left alone."""
+    from slowquant_b200.operators import hamiltonian_0i_0a
+
+    rng = np.random.default_rng(900 + n)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g = B + B.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    types, idx, th, _ = _seeded_case(n, ne, ne, L, 9100 + n, qnp=qnp)
+    lay = _layout(sq, types, idx)
+    info = sq.ci.get_indexing(0, n, 0, ne, ne)
+    dev = torch.device("cuda", info.device)
+    ref = torch.zeros(info.num_det, dtype=torch.float64, device=dev)
+    ref[0] = 1.0
+    psi = sq.osa.construct_ups_state(ref, info, th.tolist(), lay)
+    sigma = sq.osa.propagate_state([hamiltonian_0i_0a(h, g, 0, n)], psi, info)
+    psi0, sigma0 = psi.clone(), sigma.clone()
+    g_b, bra_b, ket_b = sq.osa.ups_gradient_sweep_backward(sigma, psi, info, th.tolist(), lay)
+    assert torch.equal(psi, psi0) and torch.equal(sigma, sigma0)
+    bra_f = sq.osa.construct_ups_state(sigma, info, th.tolist(), lay, dagger=True)
+    g_f, _, _ = sq.osa.ups_gradient_sweep(bra_f, ref, info, th.tolist(), lay)
+    assert np.max(np.abs(g_b - g_f)) < 1e-12
+    assert float(torch.max(torch.abs(ket_b - ref))) < 1e-12 and float(torch.max(torch.abs(bra_b - bra_f))) < 1e-12
+    sp = orc.get_indexing(0, n, 0, ne, ne)
+    assert np.max(np.abs(g_b - orc.theta_gradient(ref.cpu().numpy(), th, types, idx, h, g, sp))) < 1e-10
+
+
 def test_per_string_kernels_against_reference_outputs(sq):
     """The reference's per-string entry points (osa.py:33-410: apply_operator_serial / _threaded, their _SA twins,
     add_operator_matrix) through the gather kernel, on CAS(4,5) with 3 alpha / 1 beta electrons, against outputs of the
