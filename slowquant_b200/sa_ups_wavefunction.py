@@ -236,11 +236,11 @@ class WaveFunctionSAUPS(WaveFunctionUPS):
             )
         if theta_optimization:
             H = self._hamiltonian()
-            n = len(self._thetas)
             for s in range(self.num_states):
+                # backwards through the circuit from (H|psi_s>, |psi_s>): the numbers of the reference's forward loop without its
+                # adjoint pass (operator_state_algebra.ups_gradient_sweep_backward)
                 bra = osa.propagate_state([H], self._ci_dev[s], self.ci_info)
-                osa._ups_apply_inplace(bra, self.ci_info, self._thetas, self.ups_layout, 0, n, True)
-                g, _, _ = osa.ups_gradient_sweep(bra, self._csf_dev[s], self.ci_info, self._thetas, self.ups_layout)
+                g, _, _ = osa.ups_gradient_sweep_backward(bra, self._ci_dev[s], self.ci_info, self._thetas, self.ups_layout)
                 gradient[num_kappa:] += g / self.num_states
             self.num_energy_evals += 2 * int(np.sum(list(self.ups_layout.grad_param_R.values()))) * self.num_states
         return gradient
