@@ -372,8 +372,7 @@ class WaveFunctionUPS:
     def energy_elec(self) -> float:
         """<Psi|H|Psi> through the sigma kernel (ups_wavefunction.py:770-784)."""
         if self._energy_elec is None:
-            H = hamiltonian_0i_0a(self.h_mo, self.g_mo, self.num_inactive_orbs, self.num_active_orbs)
-            self._energy_elec = osa.expectation_value(self._ci_dev, [H], self._ci_dev, self.ci_info)
+            self._energy_elec = osa._dot(self._ci_dev, self._sigma(), self.ci_info)   # <psi|H|psi> with the kept H|psi>
         return self._energy_elec
 
     def _sigma(self) -> torch.Tensor:
