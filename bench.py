@@ -541,6 +541,24 @@ def run_ours(args) -> None:
                 "d2h_bytes_per_step": 8,
                 "probe": probe,
             }
+            # one optimiser iteration through the class: fun(x) and jac(x) at the same (new) parameters -- one state construction,
+            # one H|psi>, the backwards gradient sweep
+            try:
+                th_it = [x + 1e-3 for x in th_list]
+                for rep in range(2):   # first pass: warm-up (sigma work buffers, allocator)
+                    th_it = [x + 1e-3 for x in th_it]
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    e_it = WF._calc_energy_optimization(th_it, True, False)
+                    g_it = WF._calc_gradient_optimization(th_it, True, False)
+                    torch.cuda.synchronize()
+                    dti = time.perf_counter() - t0
+                e2e["wavefunction_setter"]["optimizer_iteration"] = {
+                    "ms": 1e3 * dti, "energy": float(e_it), "gradient_norm": float(np.linalg.norm(g_it)),
+                    "api": "WaveFunctionUPS._calc_energy_optimization(x) + _calc_gradient_optimization(x), what scipy.optimize.minimize calls per iteration",
+                }
+            except Exception as exc:  # an extra of an extra
+                e2e["wavefunction_setter"]["optimizer_iteration"] = {"error": repr(exc)}
             del WF
         except Exception as exc:  # an extra, never a gate
             e2e["wavefunction_setter"] = {"error": repr(exc)}
