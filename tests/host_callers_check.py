@@ -255,6 +255,61 @@ if which in ("all", "opt2"):
     record("SA-UPS two-step excitation energies (reference literals)", d(WS.excitation_energies, [0.838466, 0.838466]), 1e-6)
     record("SA-UPS two-step oscillator strengths (reference literals)", d(WS.get_oscillator_strenghts(), [0.7569, 0.7569]), 1e-3)
 
+# ---- one optimiser iteration of WaveFunctionUPS: what the class asks of the engine per parameter set ----
+if which in ("all", "iteration"):
+    n = 6
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(n, n))
+    h = A + A.T
+    B = 0.1 * rng.normal(size=(n, n, n, n))
+    g4 = B + B.transpose(1, 0, 2, 3)
+    g4 = g4 + g4.transpose(0, 1, 3, 2)
+    g4 = g4 + g4.transpose(2, 3, 0, 1)
+    WF = WaveFunctionUPS((n, n), np.eye(n), ArrayIntegrals(h, g4, num_elec=n), "tUPS", {"n_layers": 2})
+    calls = {"sigma": 0, "cone": 0, "plain": 0, "backward": 0}
+
+    def count(name, key):
+        fn = getattr(osa, name)
+
+        def wrapped(*a, **k):
+            calls[key] += 1
+            return fn(*a, **k)
+
+        setattr(osa, name, wrapped)
+
+    for name, key in (("propagate_state", "sigma"), ("construct_ups_state_from_determinant", "cone"), ("construct_ups_state", "plain"),
+                      ("ups_gradient_sweep_backward", "backward")):
+        count(name, key)
+    th = list(np.random.default_rng(1).uniform(-1, 1, len(WF.thetas)))
+    E = WF._calc_energy_optimization(th, True, False)
+    grad = WF._calc_gradient_optimization(th, True, False)
+    # fun(x) + jac(x) at the same x: ONE state construction (light cone of the HF determinant), ONE H|psi>, ONE backwards sweep
+    record("iteration: engine calls per parameter set", abs(calls["sigma"] - 1) + abs(calls["cone"] - 1) + calls["plain"] + abs(calls["backward"] - 1), 0)
+    record("iteration: energy_elec reuses H|psi>", abs(WF.energy_elec - E) + abs(calls["sigma"] - 1), 1e-12)
+    fd = []
+    for k in (1, 4, 9, len(th) - 1):
+        tp, tm = list(th), list(th)
+        tp[k] += 1e-5
+        tm[k] -= 1e-5
+        fd.append((WF._calc_energy_optimization(tp, True, False) - WF._calc_energy_optimization(tm, True, False)) / 2e-5 - grad[k])
+    record("iteration: backwards-sweep gradient vs finite differences", max(abs(x) for x in fd), 1e-7)
+    # the kept H|psi> follows the state: new parameters and a directly set state both invalidate it
+    before = calls["sigma"]
+    E2 = WF._calc_energy_optimization(th, True, False)
+    record("iteration: new parameters rebuild state and H|psi>", abs(E2 - E) + abs(calls["sigma"] - before - 1), 1e-12)
+    WF.light_cone = False
+    WF.thetas = th
+    plain = np.array(WF.ci_coeffs, copy=True)
+    WF.light_cone = True
+    WF.thetas = th
+    record("iteration: light-cone state vs every operator on the full vector", d(WF.ci_coeffs, plain), 1e-13)
+    plans = [v for v in WF.ci_info.__dict__.get("_light_cone", {}).values()]
+    record("iteration: the light-cone plan is a proper window", 0.0 if plans and plans[0] is not None and plans[0]["window"][1] - plans[0]["window"][0] < n else 1.0, 0)
+    WF.ci_coeffs = plain[::-1].copy()
+    e_rev = WF.energy_elec
+    WF.ci_coeffs = plain
+    record("iteration: ci_coeffs setter invalidates H|psi>", abs(WF.energy_elec - E) + (0.0 if abs(e_rev - E) > 1e-6 else 1.0), 1e-10)
+
 bad = {k: v for k, v in worst.items() if not v[0] <= v[1]}
 if bad:
     print("HOST_CALLERS_FAILED", bad, flush=True)
